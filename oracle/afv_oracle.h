@@ -1,0 +1,125 @@
+/*
+ * afv_oracle.h -- CPU ORACLE (test infrastructure, NOT product code).
+ *
+ * Plain-C restatement of the reference's per-frame feature front end for orb32 and of the
+ * FeatureMatcher inner loops.  Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+ * --impl reference legs may load this library; the product path (anyfeature-vslam_b200/csrc) never does.
+ *
+ * Where the reference's arithmetic lives in un-vendored OpenCV (cv::ORB), the algorithm is restated from
+ * OpenCV's published behaviour and PINNED against cv2 4.13.0 run in the build container
+ * (tests/test_oracle_vs_cv2.py, golden fixtures in tests/golden/ made by tools/make_golden.py).
+ * Every function cites the reference file:line (relative to /root/reference) it follows.
+ */
+#ifndef AFV_ORACLE_H
+#define AFV_ORACLE_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ORC_MAX_LEVELS 16
+
+/* == cv::KeyPoint field order (28 bytes) */
+typedef struct { float x, y, size, angle, response; int octave, class_id; } orc_keypoint;
+
+/* Geometry of cv::ORB's pyramid (scaleFactor 1.2f default kept by src/Feature_orb32.cpp:20-24). */
+int  orc_orb_level_geometry(int w, int h, int nlevels, float orb_scale_factor,
+                            int* lw, int* lh, float* lscale);
+/* cv::ORB's per-level quota from maxFeatures (= nfeatures*10, src/Feature_orb32.cpp:22) and the
+ * extractor's own per-level quota (src/FeatureExtractor.cpp:97-108): same formula. */
+void orc_features_per_level(int nfeatures, int nlevels, float scale_factor, int* quota);
+
+/* cv::resize(..., INTER_LINEAR_EXACT) 8UC1 (used by cv::ORB to build level l from level l-1). */
+void orc_resize_linear_exact_u8(const uint8_t* src, int sw, int sh, int sstride,
+                                uint8_t* dst, int dw, int dh, int dstride);
+/* Whole pyramid into one tight buffer; level l starts at offs[l], stride lw[l]. Returns total bytes. */
+long orc_orb_pyramid(const uint8_t* gray, int w, int h, int stride, int nlevels, float orb_scale_factor,
+                     uint8_t* out, long* offs, int* lw, int* lh, float* lscale);
+
+/* cv::FAST(threshold, nonmax=true, TYPE_9_16): raster-ordered (x,y,score). Returns count (may exceed cap;
+ * only the first cap are written). */
+int  orc_fast9_16_nms(const uint8_t* img, int w, int h, int stride, int threshold,
+                      int* xs, int* ys, int* scores, int cap);
+/* HarrisResponses(blockSize 7, k 0.04) of cv::ORB at integer level coords, reflect-101 outside. */
+float orc_harris7(const uint8_t* img, int w, int h, int stride, int x, int y);
+/* ICAngles (radius 15) + scalar cv::fastAtan2. */
+float orc_ic_angle(const uint8_t* img, int w, int h, int stride, int x, int y);
+float orc_fast_atan2(float y, float x);
+/* The 7x7 sigma=2 blur cv::ORB::compute applies to each level ROI (float separable path). */
+void orc_blur7_level(const uint8_t* img, int w, int h, int stride, uint8_t* out, int ostride);
+/* 256-bit steered BRIEF at level coords (x,y); img = un-blurred level (read outside), blur = blurred. */
+void orc_rbrief32(const uint8_t* img, const uint8_t* blur, int w, int h, int stride,
+                  int x, int y, float angle_deg, uint8_t* desc32);
+
+/* cv::ORB::detect restated for one level: FAST -> retainBest(2q) -> Harris -> retainBest(q), canonical
+ * (raster) order. Writes level coords + harris response + fast score. Returns count. */
+int  orc_orb_detect_level(const uint8_t* img, int w, int h, int stride, int fast_th, int quota,
+                          int* xs, int* ys, float* harris, int* fastscore, int cap);
+
+/* DistributeOctTree (src/ORBextractor.cc:239-458) on keypoints in level-0 coords; bounds (0,w,0,h).
+ * `order[i]` is the canonical rank used to break exact max-response ties inside one node (smaller wins);
+ * pointer-order ties in the (size,node*) sort are broken by node creation order (later-created = larger).
+ * Writes the indices (into the input arrays) of the kept keypoints in list order. Returns count. */
+int  orc_distribute_octree(const float* px, const float* py, const float* resp, const int* order, int n,
+                           int minX, int maxX, int minY, int maxY, int N, int* keep, int cap);
+
+/* Full orb32 FeatureExtractor::operator() (src/FeatureExtractor.cpp:111-121 with
+ * src/Feature_orb32.cpp:11-65): returns merged keypoints (levels ascending) + n x 32 descriptors +
+ * per-keypoint size (computeSize, src/FeatureExtractor.cpp:132-142). n_out may be NULL-checked by caller. */
+int  orc_orb32_extract(const uint8_t* gray, int w, int h, int stride,
+                       int nfeatures, int nlevels, float scale_factor, float detect_th,
+                       orc_keypoint* kps, uint8_t* desc, float* kpsize, int cap, int* n_out,
+                       int* n_candidates /* optional: total cv::ORB::detect keypoints */);
+
+/* ------------------------------------------------------------------ matcher restatement ---------- */
+/* DescriptorDistance_* (src/Feature_orb32.cpp:67-83, Feature_akaze61.cpp:75-77, Feature_brisk48.cpp:62-64,
+ * Feature_sift128.cpp:132-134). desc_type uses include/Types.h:24-34 ids (0 orb,1 akaze61,2 brisk,5 sift). */
+float orc_descriptor_distance(int desc_type, const void* a, const void* b);
+int   orc_descriptor_bytes(int desc_type);
+
+/* Frame grid (src/Frame.cc:225-240, :384-394; 64x48 cells include/Frame.h:40-41).
+ * cell_start has 64*48+1 entries (column-major [ix][iy] like mGrid), cell_items n entries. */
+void orc_grid_build(const orc_keypoint* kps, int n, float minX, float minY, float invW, float invH,
+                    int* cell_start, int* cell_items);
+/* Frame::GetFeaturesInArea (src/Frame.cc:333-382). Returns count, indices in reference order. */
+int  orc_features_in_area(const orc_keypoint* kps, const float* kpsize, const int* cell_start,
+                          const int* cell_items, float minX, float minY, float invW, float invH,
+                          float x, float y, float r, float minSize, float maxSize, int* out, int cap);
+
+/* FeatureMatcher::SearchForInitialization (src/FeatureMatcher.cc:399-557) on plain arrays.
+ * prev_matched (n1 x 2 floats) is updated in place like vbPrevMatched; matches12 gets n1 ints. */
+int  orc_search_for_initialization(int desc_type,
+        const orc_keypoint* k1, const void* d1, int n1,
+        const orc_keypoint* k2, const void* d2, const float* size2, int n2,
+        float minX, float minY, float maxX, float maxY, float max_kpt_size,
+        float* prev_matched, int window, float th_low, float nnratio, int check_ori, int* matches12);
+
+/* Stateless windowed best/second search (the data-parallel core of SearchByProjection,
+ * src/FeatureMatcher.cc:73-154: candidates from GetFeaturesInArea, best/second distance + sizes). */
+void orc_match_window(int desc_type, const void* q, const float* qxy, const float* qr,
+        const float* qmin_size, const float* qmax_size, int nq,
+        const orc_keypoint* tk, const void* td, const float* tsize, int nt,
+        float minX, float minY, float maxX, float maxY,
+        int* best, float* bestd, float* secondd, float* best_size, float* second_size);
+
+/* Brute force N x M best / second (first minimum wins). */
+void orc_match_bruteforce(int desc_type, const void* q, int nq, const void* t, int nt,
+                          int* best, float* bestd, float* secondd);
+
+/* SearchByBoW(KF,F) (src/FeatureMatcher.cc:186-283) with the FeatureVectors given as sorted
+ * (node id, index list) segments; every KF keypoint is assumed to carry a valid map point. */
+int  orc_search_by_bow(int desc_type,
+        const void* dkf, const int* kf_node, const int* kf_start, const int* kf_idx, int kf_nodes,
+        const orc_keypoint* kkf,
+        const void* df, const int* f_node, const int* f_start, const int* f_idx, int f_nodes,
+        const orc_keypoint* kf_f, int nf,
+        float th_low, float nnratio, int check_ori, int* match_f /* nf: KF index or -1 */);
+
+/* rotation-consistency helpers (src/FeatureMatcher.cc:1579-1668) */
+int  orc_rot_bin(float angle1, float angle2);
+void orc_three_maxima(const int* hist_counts, int len, int* ind1, int* ind2, int* ind3);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

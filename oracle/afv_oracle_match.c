@@ -1,0 +1,295 @@
+/*
+ * afv_oracle_match.c -- CPU ORACLE for the FeatureMatcher path (test infrastructure, NOT product code).
+ *
+ * Restates the reference's matcher loops on plain arrays (no Frame/KeyFrame/MapPoint graph):
+ * src/FeatureMatcher.cc:399-557 (SearchForInitialization), :186-283 (SearchByBoW), :73-154 (window search
+ * core of SearchByProjection), :1508-1531 (DescriptorDistance), :1579-1668 (rotation histogram), and
+ * src/Frame.cc:225-240, :333-394 (grid).  All of this arithmetic is in-repo C++ in the reference (integer
+ * popcounts, float compares), so the restatement is definitional; no third-party numerics involved except
+ * cv::norm(NORM_L2SQR) for sift128 (float diff, double accumulation; 1e-5 tolerance applies).
+ */
+#include "afv_oracle.h"
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+#include <float.h>
+
+#define GRID_COLS 64   /* include/Frame.h:41 */
+#define GRID_ROWS 48   /* include/Frame.h:40 */
+#define HISTO_LENGTH 30 /* src/FeatureMatcher.cc:64 */
+
+int orc_descriptor_bytes(int desc_type) {
+    switch (desc_type) {
+        case 0: return 32;      /* DESC_ORB */
+        case 1: return 61;      /* DESC_AKAZE61 */
+        case 2: return 48;      /* DESC_BRISK */
+        case 5: return 512;     /* DESC_SIFT128: 128 float */
+        default: return -1;
+    }
+}
+
+static inline int popc8(unsigned v) { return __builtin_popcount(v & 0xffu); }
+
+float orc_descriptor_distance(int desc_type, const void* a, const void* b) {
+    if (desc_type == 5) {                       /* cv::norm(a,b,NORM_L2SQR) on CV_32F: normL2Sqr<float,double> */
+        const float *x = (const float*)a, *y = (const float*)b;
+        double s = 0;
+        for (int i = 0; i < 128; i += 4) {
+            double v0 = (double)(x[i] - y[i]), v1 = (double)(x[i + 1] - y[i + 1]);
+            double v2 = (double)(x[i + 2] - y[i + 2]), v3 = (double)(x[i + 3] - y[i + 3]);
+            s += v0 * v0 + v1 * v1 + v2 * v2 + v3 * v3;
+        }
+        return (float)s;
+    }
+    int nb = orc_descriptor_bytes(desc_type), d = 0;
+    const uint8_t *x = (const uint8_t*)a, *y = (const uint8_t*)b;
+    for (int i = 0; i < nb; ++i) d += popc8((unsigned)(x[i] ^ y[i]));
+    return (float)d;
+}
+
+/* ---------------------------------------------------------------- grid ---------------------------- */
+/* Frame::PosInGrid + AssignFeaturesToGrid; cells stored [ix][iy] (ix major) as CSR, items ascending. */
+static inline int pos_in_grid(const orc_keypoint* kp, float minX, float minY, float invW, float invH,
+                              int* cx, int* cy) {
+    int px = (int)roundf((kp->x - minX) * invW);
+    int py = (int)roundf((kp->y - minY) * invH);
+    if (px < 0 || px >= GRID_COLS || py < 0 || py >= GRID_ROWS) return 0;
+    *cx = px; *cy = py;
+    return 1;
+}
+
+void orc_grid_build(const orc_keypoint* kps, int n, float minX, float minY, float invW, float invH,
+                    int* cell_start, int* cell_items) {
+    const int nc = GRID_COLS * GRID_ROWS;
+    memset(cell_start, 0, sizeof(int) * (nc + 1));
+    for (int i = 0; i < n; ++i) {
+        int cx, cy;
+        if (pos_in_grid(&kps[i], minX, minY, invW, invH, &cx, &cy)) cell_start[cx * GRID_ROWS + cy + 1]++;
+    }
+    for (int c = 0; c < nc; ++c) cell_start[c + 1] += cell_start[c];
+    int* cur = (int*)malloc(sizeof(int) * nc);
+    memcpy(cur, cell_start, sizeof(int) * nc);
+    for (int i = 0; i < n; ++i) {
+        int cx, cy;
+        if (pos_in_grid(&kps[i], minX, minY, invW, invH, &cx, &cy)) cell_items[cur[cx * GRID_ROWS + cy]++] = i;
+    }
+    free(cur);
+}
+
+int orc_features_in_area(const orc_keypoint* kps, const float* kpsize, const int* cell_start,
+                         const int* cell_items, float minX, float minY, float invW, float invH,
+                         float x, float y, float r, float minSize, float maxSize, int* out, int cap) {
+    int n = 0;
+    int c0 = (int)floorf((x - minX - r) * invW); if (c0 < 0) c0 = 0;
+    if (c0 >= GRID_COLS) return 0;
+    int c1 = (int)ceilf((x - minX + r) * invW); if (c1 > GRID_COLS - 1) c1 = GRID_COLS - 1;
+    if (c1 < 0) return 0;
+    int r0 = (int)floorf((y - minY - r) * invH); if (r0 < 0) r0 = 0;
+    if (r0 >= GRID_ROWS) return 0;
+    int r1 = (int)ceilf((y - minY + r) * invH); if (r1 > GRID_ROWS - 1) r1 = GRID_ROWS - 1;
+    if (r1 < 0) return 0;
+    for (int ix = c0; ix <= c1; ++ix)
+        for (int iy = r0; iy <= r1; ++iy) {
+            int c = ix * GRID_ROWS + iy;
+            for (int j = cell_start[c]; j < cell_start[c + 1]; ++j) {
+                int idx = cell_items[j];
+                if (kpsize[idx] < minSize) continue;
+                if (kpsize[idx] > maxSize) continue;
+                float dx = kps[idx].x - x, dy = kps[idx].y - y;
+                if (fabsf(dx) < r && fabsf(dy) < r) { if (n < cap) out[n] = idx; ++n; }
+            }
+        }
+    return n;
+}
+
+/* ---------------------------------------------------------------- rotation histogram -------------- */
+/* updateRotationHistogram (src/FeatureMatcher.cc:1587-1597): rotFactor = 1/30 so only bins 0..12 fill. */
+int orc_rot_bin(float angle1, float angle2) {
+    float rot = angle1 - angle2;
+    if (rot < 0.0) rot += 360.0f;
+    const float rotFactor = 1.0f / (float)HISTO_LENGTH;
+    int bin = (int)roundf(rot * rotFactor);
+    if (bin == HISTO_LENGTH) bin = 0;
+    return bin;
+}
+
+void orc_three_maxima(const int* cnt, int len, int* ind1, int* ind2, int* ind3) {
+    int max1 = 0, max2 = 0, max3 = 0;
+    *ind1 = *ind2 = *ind3 = -1;
+    for (int i = 0; i < len; ++i) {
+        const int s = cnt[i];
+        if (s > max1) { max3 = max2; max2 = max1; max1 = s; *ind3 = *ind2; *ind2 = *ind1; *ind1 = i; }
+        else if (s > max2) { max3 = max2; max2 = s; *ind3 = *ind2; *ind2 = i; }
+        else if (s > max3) { max3 = s; *ind3 = i; }
+    }
+    if ((float)max2 < 0.1f * (float)max1) { *ind2 = -1; *ind3 = -1; }
+    else if ((float)max3 < 0.1f * (float)max1) { *ind3 = -1; }
+}
+
+/* ---------------------------------------------------------------- SearchForInitialization --------- */
+int orc_search_for_initialization(int desc_type,
+        const orc_keypoint* k1, const void* d1, int n1,
+        const orc_keypoint* k2, const void* d2, const float* size2, int n2,
+        float minX, float minY, float maxX, float maxY, float max_kpt_size,
+        float* prev_matched, int window, float th_low, float nnratio, int check_ori, int* matches12) {
+    const int D = orc_descriptor_bytes(desc_type);
+    const float invW = (float)GRID_COLS / (maxX - minX), invH = (float)GRID_ROWS / (maxY - minY);
+    int* cs = (int*)malloc(sizeof(int) * (GRID_COLS * GRID_ROWS + 1));
+    int* ci = (int*)malloc(sizeof(int) * (n2 + 1));
+    orc_grid_build(k2, n2, minX, minY, invW, invH, cs, ci);
+    int* cand = (int*)malloc(sizeof(int) * (n2 + 1));
+    float* matchedDist = (float*)malloc(sizeof(float) * (n2 + 1));
+    int* matches21 = (int*)malloc(sizeof(int) * (n2 + 1));
+    int* hist_items = (int*)malloc(sizeof(int) * (n1 + 1));   /* (bin of i1) or -1 */
+    int hist_cnt[HISTO_LENGTH] = {0};
+    for (int i = 0; i < n2; ++i) { matchedDist[i] = FLT_MAX; matches21[i] = -1; }
+    for (int i = 0; i < n1; ++i) { matches12[i] = -1; hist_items[i] = -1; }
+    int nMatches = 0;
+    const float r = (float)window;
+    for (int i1 = 0; i1 < n1; ++i1) {
+        if (k1[i1].octave > 0) continue;
+        int nc = orc_features_in_area(k2, size2, cs, ci, minX, minY, invW, invH,
+                                      prev_matched[2 * i1], prev_matched[2 * i1 + 1], r, 0.0f, max_kpt_size, cand, n2);
+        if (nc == 0) continue;
+        const uint8_t* ref = (const uint8_t*)d1 + (long)i1 * D;
+        float bestDist = FLT_MAX, bestDist2 = FLT_MAX;
+        int bestIdx2 = -1;
+        for (int c = 0; c < nc; ++c) {
+            int i2 = cand[c];
+            float dist = orc_descriptor_distance(desc_type, ref, (const uint8_t*)d2 + (long)i2 * D);
+            if (matchedDist[i2] <= dist) continue;
+            if (dist < bestDist) { bestDist2 = bestDist; bestDist = dist; bestIdx2 = i2; }
+            else if (dist < bestDist2) bestDist2 = dist;
+        }
+        if (bestDist <= th_low) {
+            if (bestDist < bestDist2 * nnratio) {
+                if (matches21[bestIdx2] >= 0) { matches12[matches21[bestIdx2]] = -1; nMatches--; }
+                matches12[i1] = bestIdx2;
+                matches21[bestIdx2] = i1;
+                matchedDist[bestIdx2] = bestDist;
+                nMatches++;
+                if (check_ori) {
+                    int bin = orc_rot_bin(k1[i1].angle, k2[bestIdx2].angle);
+                    hist_items[i1] = bin; hist_cnt[bin]++;
+                }
+            }
+        }
+    }
+    if (check_ori) {
+        int i1m, i2m, i3m;
+        orc_three_maxima(hist_cnt, HISTO_LENGTH, &i1m, &i2m, &i3m);
+        for (int i1 = 0; i1 < n1; ++i1) {
+            int b = hist_items[i1];
+            if (b < 0 || b == i1m || b == i2m || b == i3m) continue;
+            if (matches12[i1] >= 0) { matches12[i1] = -1; nMatches--; }
+        }
+    }
+    for (int i1 = 0; i1 < n1; ++i1)
+        if (matches12[i1] >= 0) { prev_matched[2 * i1] = k2[matches12[i1]].x; prev_matched[2 * i1 + 1] = k2[matches12[i1]].y; }
+    free(cs); free(ci); free(cand); free(matchedDist); free(matches21); free(hist_items);
+    return nMatches;
+}
+
+/* ---------------------------------------------------------------- stateless window search --------- */
+void orc_match_window(int desc_type, const void* q, const float* qxy, const float* qr,
+        const float* qmin_size, const float* qmax_size, int nq,
+        const orc_keypoint* tk, const void* td, const float* tsize, int nt,
+        float minX, float minY, float maxX, float maxY,
+        int* best, float* bestd, float* secondd, float* best_size, float* second_size) {
+    const int D = orc_descriptor_bytes(desc_type);
+    const float invW = (float)GRID_COLS / (maxX - minX), invH = (float)GRID_ROWS / (maxY - minY);
+    int* cs = (int*)malloc(sizeof(int) * (GRID_COLS * GRID_ROWS + 1));
+    int* ci = (int*)malloc(sizeof(int) * (nt + 1));
+    int* cand = (int*)malloc(sizeof(int) * (nt + 1));
+    orc_grid_build(tk, nt, minX, minY, invW, invH, cs, ci);
+    for (int i = 0; i < nq; ++i) {
+        int nc = orc_features_in_area(tk, tsize, cs, ci, minX, minY, invW, invH, qxy[2 * i], qxy[2 * i + 1],
+                                      qr[i], qmin_size[i], qmax_size[i], cand, nt);
+        float bd = FLT_MAX, bd2 = FLT_MAX, bs = -1.0f, bs2 = -1.0f;
+        int bi = -1;
+        const uint8_t* ref = (const uint8_t*)q + (long)i * D;
+        for (int c = 0; c < nc; ++c) {
+            int idx = cand[c];
+            float dist = orc_descriptor_distance(desc_type, ref, (const uint8_t*)td + (long)idx * D);
+            if (dist < bd) { bd2 = bd; bd = dist; bi = idx; bs2 = bs; bs = tsize[idx]; }
+            else if (dist < bd2) { bd2 = dist; bs2 = tsize[idx]; }
+        }
+        best[i] = bi; bestd[i] = bd; secondd[i] = bd2;
+        if (best_size) best_size[i] = bs;
+        if (second_size) second_size[i] = bs2;
+    }
+    free(cs); free(ci); free(cand);
+}
+
+void orc_match_bruteforce(int desc_type, const void* q, int nq, const void* t, int nt,
+                          int* best, float* bestd, float* secondd) {
+    const int D = orc_descriptor_bytes(desc_type);
+    for (int i = 0; i < nq; ++i) {
+        float bd = FLT_MAX, bd2 = FLT_MAX;
+        int bi = -1;
+        const uint8_t* ref = (const uint8_t*)q + (long)i * D;
+        for (int j = 0; j < nt; ++j) {
+            float dist = orc_descriptor_distance(desc_type, ref, (const uint8_t*)t + (long)j * D);
+            if (dist < bd) { bd2 = bd; bd = dist; bi = j; }
+            else if (dist < bd2) bd2 = dist;
+        }
+        best[i] = bi; bestd[i] = bd; secondd[i] = bd2;
+    }
+}
+
+/* ---------------------------------------------------------------- SearchByBoW(KF, F) --------------- */
+int orc_search_by_bow(int desc_type,
+        const void* dkf, const int* kf_node, const int* kf_start, const int* kf_idx, int kf_nodes,
+        const orc_keypoint* kkf,
+        const void* df, const int* f_node, const int* f_start, const int* f_idx, int f_nodes,
+        const orc_keypoint* kf_f, int nf,
+        float th_low, float nnratio, int check_ori, int* match_f) {
+    const int D = orc_descriptor_bytes(desc_type);
+    int* bin_of = (int*)malloc(sizeof(int) * (nf + 1));
+    int hist_cnt[HISTO_LENGTH] = {0};
+    for (int i = 0; i < nf; ++i) { match_f[i] = -1; bin_of[i] = -1; }
+    int nMatches = 0, a = 0, b = 0;
+    while (a < kf_nodes && b < f_nodes) {
+        if (kf_node[a] == f_node[b]) {
+            for (int iKF = kf_start[a]; iKF < kf_start[a + 1]; ++iKF) {
+                const int realKF = kf_idx[iKF];
+                const uint8_t* ref = (const uint8_t*)dkf + (long)realKF * D;
+                float bd1 = FLT_MAX, bd2 = FLT_MAX;
+                int bestF = -1;
+                for (int iF = f_start[b]; iF < f_start[b + 1]; ++iF) {
+                    const int realF = f_idx[iF];
+                    if (match_f[realF] >= 0) continue;
+                    float dist = orc_descriptor_distance(desc_type, ref, (const uint8_t*)df + (long)realF * D);
+                    if (dist < bd1) { bd2 = bd1; bd1 = dist; bestF = realF; }
+                    else if (dist < bd2) bd2 = dist;
+                }
+                if (bd1 <= th_low) {
+                    if (bd1 < nnratio * bd2) {
+                        match_f[bestF] = realKF;
+                        nMatches++;
+                        if (check_ori) {
+                            int bin = orc_rot_bin(kkf[realKF].angle, kf_f[bestF].angle);
+                            bin_of[bestF] = bin; hist_cnt[bin]++;
+                        }
+                    }
+                }
+            }
+            ++a; ++b;
+        } else if (kf_node[a] < f_node[b]) {
+            while (a < kf_nodes && kf_node[a] < f_node[b]) ++a;     /* lower_bound */
+        } else {
+            while (b < f_nodes && f_node[b] < kf_node[a]) ++b;
+        }
+    }
+    if (check_ori) {
+        int i1m, i2m, i3m;
+        orc_three_maxima(hist_cnt, HISTO_LENGTH, &i1m, &i2m, &i3m);
+        for (int i = 0; i < nf; ++i) {
+            int bn = bin_of[i];
+            if (bn < 0 || bn == i1m || bn == i2m || bn == i3m) continue;
+            match_f[i] = -1; nMatches--;
+        }
+    }
+    free(bin_of);
+    return nMatches;
+}

@@ -1,0 +1,187 @@
+"""ctypes front end of the CPU ORACLE (oracle/libafv_oracle.so).
+
+TEST INFRASTRUCTURE ONLY: import this from tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+--impl reference legs.  The product package never imports it.
+"""
+import ctypes as C
+import os
+import subprocess
+import numpy as np
+
+_DIR = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+KP_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("size", "<f4"), ("angle", "<f4"),
+                     ("response", "<f4"), ("octave", "<i4"), ("class_id", "<i4")])
+assert KP_DTYPE.itemsize == 28
+
+DESC_ORB, DESC_AKAZE61, DESC_BRISK, DESC_SIFT128 = 0, 1, 2, 5      # include/Types.h:24-34
+
+
+def build(force=False):
+    so = os.path.join(_DIR, "libafv_oracle.so")
+    srcs = [os.path.join(_DIR, f) for f in ("afv_oracle.c", "afv_oracle_match.c", "afv_oracle.h", "orb_pattern.inc")]
+    if force or not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
+        subprocess.check_call(["make", "-s", "-C", _DIR, "libafv_oracle.so"])
+    return so
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        _LIB = C.CDLL(build())
+        _LIB.orc_orb_pyramid.restype = C.c_long
+        _LIB.orc_harris7.restype = C.c_float
+        _LIB.orc_ic_angle.restype = C.c_float
+        _LIB.orc_fast_atan2.restype = C.c_float
+        _LIB.orc_fast_atan2.argtypes = [C.c_float, C.c_float]
+        _LIB.orc_descriptor_distance.restype = C.c_float
+    return _LIB
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def _f(v):
+    return C.c_float(float(v))
+
+
+def level_geometry(w, h, nlevels=8, sf=1.2):
+    lw = np.zeros(nlevels, np.int32); lh = np.zeros(nlevels, np.int32); ls = np.zeros(nlevels, np.float32)
+    lib().orc_orb_level_geometry(w, h, nlevels, _f(sf), _p(lw), _p(lh), _p(ls))
+    return lw, lh, ls
+
+
+def features_per_level(nfeatures, nlevels=8, sf=1.2):
+    q = np.zeros(nlevels, np.int32)
+    lib().orc_features_per_level(nfeatures, nlevels, _f(sf), _p(q))
+    return q
+
+
+def pyramid(gray, nlevels=8, sf=1.2):
+    gray = np.ascontiguousarray(gray, np.uint8)
+    h, w = gray.shape
+    offs = np.zeros(nlevels, np.int64); lw = np.zeros(nlevels, np.int32); lh = np.zeros(nlevels, np.int32)
+    ls = np.zeros(nlevels, np.float32)
+    total = lib().orc_orb_pyramid(_p(gray), w, h, w, nlevels, _f(sf), None, _p(offs), _p(lw), _p(lh), _p(ls))
+    buf = np.zeros(total, np.uint8)
+    lib().orc_orb_pyramid(_p(gray), w, h, w, nlevels, _f(sf), _p(buf), _p(offs), _p(lw), _p(lh), _p(ls))
+    return [buf[offs[l]:offs[l] + int(lw[l]) * int(lh[l])].reshape(lh[l], lw[l]) for l in range(nlevels)], ls
+
+
+def fast(img, threshold=20):
+    img = np.ascontiguousarray(img, np.uint8)
+    h, w = img.shape
+    cap = w * h // 4 + 16
+    xs = np.zeros(cap, np.int32); ys = np.zeros(cap, np.int32); sc = np.zeros(cap, np.int32)
+    n = lib().orc_fast9_16_nms(_p(img), w, h, w, threshold, _p(xs), _p(ys), _p(sc), cap)
+    return xs[:n].copy(), ys[:n].copy(), sc[:n].copy()
+
+
+def harris(img, x, y):
+    img = np.ascontiguousarray(img, np.uint8)
+    h, w = img.shape
+    return lib().orc_harris7(_p(img), w, h, w, int(x), int(y))
+
+
+def ic_angle(img, x, y):
+    img = np.ascontiguousarray(img, np.uint8)
+    h, w = img.shape
+    return lib().orc_ic_angle(_p(img), w, h, w, int(x), int(y))
+
+
+def blur7(img):
+    img = np.ascontiguousarray(img, np.uint8)
+    h, w = img.shape
+    out = np.zeros_like(img)
+    lib().orc_blur7_level(_p(img), w, h, w, _p(out), w)
+    return out
+
+
+def detect_level(img, fast_th, quota):
+    img = np.ascontiguousarray(img, np.uint8)
+    h, w = img.shape
+    cap = w * h // 4 + 16
+    xs = np.zeros(cap, np.int32); ys = np.zeros(cap, np.int32); fs = np.zeros(cap, np.int32)
+    hr = np.zeros(cap, np.float32)
+    n = lib().orc_orb_detect_level(_p(img), w, h, w, int(fast_th), int(quota), _p(xs), _p(ys), _p(hr), _p(fs), cap)
+    assert n >= 0
+    return xs[:n].copy(), ys[:n].copy(), hr[:n].copy(), fs[:n].copy()
+
+
+def octree(px, py, resp, w, h, N):
+    px = np.ascontiguousarray(px, np.float32); py = np.ascontiguousarray(py, np.float32)
+    resp = np.ascontiguousarray(resp, np.float32)
+    n = len(px)
+    keep = np.zeros(max(n, 1), np.int32)
+    m = lib().orc_distribute_octree(_p(px), _p(py), _p(resp), None, n, 0, int(w), 0, int(h), int(N), _p(keep), n)
+    assert m >= 0
+    return keep[:m].copy()
+
+
+def orb32_extract(gray, nfeatures=1000, nlevels=8, scale_factor=1.2, detect_th=20.0, cap=None):
+    gray = np.ascontiguousarray(gray, np.uint8)
+    h, w = gray.shape
+    cap = cap or nfeatures + 3 * nlevels + 64
+    kps = np.zeros(cap, KP_DTYPE); desc = np.zeros((cap, 32), np.uint8); ksz = np.zeros(cap, np.float32)
+    n = C.c_int(0); nc = C.c_int(0)
+    rc = lib().orc_orb32_extract(_p(gray), w, h, w, nfeatures, nlevels, _f(scale_factor), _f(detect_th),
+                                 _p(kps), _p(desc), _p(ksz), cap, C.byref(n), C.byref(nc))
+    assert rc == 0, rc
+    return kps[:n.value].copy(), desc[:n.value].copy(), ksz[:n.value].copy(), nc.value
+
+
+def descriptor_distance(desc_type, a, b):
+    a = np.ascontiguousarray(a); b = np.ascontiguousarray(b)
+    return lib().orc_descriptor_distance(desc_type, _p(a), _p(b))
+
+
+def search_for_initialization(desc_type, k1, d1, k2, d2, size2, bounds, max_kpt_size, prev_matched,
+                              window=100, th_low=75.0, nnratio=0.9, check_ori=True):
+    k1 = np.ascontiguousarray(k1); k2 = np.ascontiguousarray(k2)
+    d1 = np.ascontiguousarray(d1); d2 = np.ascontiguousarray(d2)
+    size2 = np.ascontiguousarray(size2, np.float32)
+    pm = np.ascontiguousarray(prev_matched, np.float32).copy()
+    m12 = np.zeros(max(len(k1), 1), np.int32)
+    minX, minY, maxX, maxY = bounds
+    n = lib().orc_search_for_initialization(desc_type, _p(k1), _p(d1), len(k1), _p(k2), _p(d2), _p(size2), len(k2),
+                                            _f(minX), _f(minY), _f(maxX), _f(maxY), _f(max_kpt_size), _p(pm),
+                                            int(window), _f(th_low), _f(nnratio), int(bool(check_ori)), _p(m12))
+    return n, m12[:len(k1)].copy(), pm
+
+
+def match_window(desc_type, q, qxy, qr, qmin, qmax, tk, td, tsize, bounds):
+    q = np.ascontiguousarray(q); td = np.ascontiguousarray(td); tk = np.ascontiguousarray(tk)
+    qxy = np.ascontiguousarray(qxy, np.float32); qr = np.ascontiguousarray(qr, np.float32)
+    qmin = np.ascontiguousarray(qmin, np.float32); qmax = np.ascontiguousarray(qmax, np.float32)
+    tsize = np.ascontiguousarray(tsize, np.float32)
+    nq = len(q)
+    best = np.zeros(nq, np.int32); bd = np.zeros(nq, np.float32); sd = np.zeros(nq, np.float32)
+    bs = np.zeros(nq, np.float32); ss = np.zeros(nq, np.float32)
+    minX, minY, maxX, maxY = bounds
+    lib().orc_match_window(desc_type, _p(q), _p(qxy), _p(qr), _p(qmin), _p(qmax), nq, _p(tk), _p(td), _p(tsize),
+                           len(tk), _f(minX), _f(minY), _f(maxX), _f(maxY), _p(best), _p(bd), _p(sd), _p(bs), _p(ss))
+    return best, bd, sd, bs, ss
+
+
+def match_bruteforce(desc_type, q, t):
+    q = np.ascontiguousarray(q); t = np.ascontiguousarray(t)
+    nq = len(q)
+    best = np.zeros(nq, np.int32); bd = np.zeros(nq, np.float32); sd = np.zeros(nq, np.float32)
+    lib().orc_match_bruteforce(desc_type, _p(q), nq, _p(t), len(t), _p(best), _p(bd), _p(sd))
+    return best, bd, sd
+
+
+def search_by_bow(desc_type, dkf, kkf, kf_segs, df, kf_f, f_segs, th_low=75.0, nnratio=0.7, check_ori=True):
+    """kf_segs / f_segs: (node_ids, starts(len+1), idx) sorted by node id."""
+    dkf = np.ascontiguousarray(dkf); df = np.ascontiguousarray(df)
+    kkf = np.ascontiguousarray(kkf); kf_f = np.ascontiguousarray(kf_f)
+    a = [np.ascontiguousarray(v, np.int32) for v in kf_segs]
+    b = [np.ascontiguousarray(v, np.int32) for v in f_segs]
+    nf = len(df)
+    out = np.zeros(max(nf, 1), np.int32)
+    n = lib().orc_search_by_bow(desc_type, _p(dkf), _p(a[0]), _p(a[1]), _p(a[2]), len(a[0]), _p(kkf),
+                                _p(df), _p(b[0]), _p(b[1]), _p(b[2]), len(b[0]), _p(kf_f), nf,
+                                _f(th_low), _f(nnratio), int(bool(check_ori)), _p(out))
+    return n, out[:nf].copy()
