@@ -1,0 +1,171 @@
+"""anyfeature-vslam_b200 -- B200-native feature front end (orb32 extract + FeatureMatcher kernels).
+
+Python host side above the C ABI (include/afv.h), used by tests/ and bench.py.  It mirrors the reference's
+FeatureExtractor / FeatureMatcher call surface on arrays (numpy for host buffers, torch tensors for device
+buffers: torch is only plumbing for device memory, streams and torch.distributed).  There is NO CPU fallback:
+importing works without a GPU (so the symbol/ABI tests can run), but every compute entry point raises
+AfvError when the CUDA library or device is missing.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libafv_b200.so")
+
+KP_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("size", "<f4"), ("angle", "<f4"),
+                     ("response", "<f4"), ("octave", "<i4"), ("class_id", "<i4")])
+FEAT_ORB32, FEAT_AKAZE61, FEAT_BRISK48, FEAT_SIFT128 = 0, 1, 2, 5       # reference include/Types.h:35-45
+DESC_BYTES = {0: 32, 1: 61, 2: 48, 5: 512}
+
+# settings/<feat>_settings.yaml of the reference (numOctaves, scaleFactor, detectionTh, matchingTh)
+FEATURE_SETTINGS = {
+    "orb32": dict(feature_id=0, n_octaves=8, scale_factor=1.2, detect_th=20.0, matching_th=75.0),
+    "akaze61": dict(feature_id=1, n_octaves=8, scale_factor=1.1892, detect_th=0.0005, matching_th=128.0),
+    "brisk48": dict(feature_id=2, n_octaves=8, scale_factor=1.5, detect_th=34.0, matching_th=120.0),
+    "sift128": dict(feature_id=5, n_octaves=8, scale_factor=2.0, detect_th=10.0, matching_th=0.5),
+}
+
+
+class AfvError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def lib():
+    """Load the CUDA library; raises loudly if it was not built (no fallback path exists)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise AfvError("CUDA extension %s is missing: run `python __graft_entry__.py` / build.py first; "
+                           "there is no CPU fallback" % LIB_PATH)
+        _lib = C.CDLL(LIB_PATH)
+        _lib.afv_last_error.restype = C.c_char_p
+        _lib.afv_version.restype = C.c_char_p
+        _lib.afv_kernel_launches.restype = C.c_longlong
+    return _lib
+
+
+def _check(rc):
+    if rc != 0:
+        raise AfvError("afv error %d: %s" % (rc, lib().afv_last_error().decode()))
+
+
+def kernel_launches():
+    return int(lib().afv_kernel_launches())
+
+
+def _vp(x):
+    """void* of a numpy array or a torch tensor (device or host)."""
+    if x is None:
+        return None
+    if isinstance(x, np.ndarray):
+        return x.ctypes.data_as(C.c_void_p)
+    return C.c_void_p(x.data_ptr())
+
+
+def _stream_ptr(stream):
+    if stream is None:
+        import torch
+        stream = torch.cuda.current_stream()
+    return C.c_void_p(stream.cuda_stream)
+
+
+class FeatureExtractor:
+    """Mirror of the reference's FeatureExtractor_<feat> (include/FeatureExtractor.h:68-161).
+
+    __call__(gray) == operator()(Image, keypoints, descriptors, ..., size) for one host frame; extract_batch
+    is the batched extension.  Construction == the reference factory (src/Tracking.cc:1505-1553) with the
+    values of settings/<feat>_settings.yaml.
+    """
+
+    def __init__(self, feature="orb32", nfeatures=1000, device=0, max_batch=1, max_w=640, max_h=480,
+                 n_octaves=None, scale_factor=None, detect_th=None):
+        s = FEATURE_SETTINGS[feature]
+        self.feature = feature
+        self.nfeatures = nfeatures
+        self.n_octaves = n_octaves or s["n_octaves"]
+        self.scale_factor = scale_factor or s["scale_factor"]
+        self.detect_th = detect_th if detect_th is not None else s["detect_th"]
+        self.desc_bytes = DESC_BYTES[s["feature_id"]]
+        self.max_batch = max_batch
+        self._h = C.c_void_p()
+        _check(lib().afv_extractor_create(C.byref(self._h), s["feature_id"], nfeatures, self.n_octaves,
+                                          C.c_float(self.scale_factor), C.c_float(self.detect_th), device,
+                                          max_batch, max_w, max_h))
+        self.cap = lib().afv_extractor_output_cap(self._h)
+        self.device = device
+
+    def close(self):
+        if self._h:
+            lib().afv_extractor_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def levels(self):
+        sf = np.zeros(self.n_octaves, np.float32); q = np.zeros(self.n_octaves, np.int32)
+        lib().afv_extractor_levels(self._h, _vp(sf), _vp(q))
+        return sf, q
+
+    # ---- host buffers (numpy) -------------------------------------------------------------------------
+    def extract_batch(self, gray, out=None):
+        """gray: uint8 [B,H,W] numpy (C-contiguous).  Returns (kps [B,cap] KP_DTYPE, desc [B,cap,D], size [B,cap], n [B])."""
+        gray = np.ascontiguousarray(gray, np.uint8)
+        B, h, w = gray.shape
+        if out is None:
+            out = (np.zeros((B, self.cap), KP_DTYPE), np.zeros((B, self.cap, self.desc_bytes), np.uint8),
+                   np.zeros((B, self.cap), np.float32), np.zeros(B, np.int32))
+        kps, desc, size, n = out
+        _check(lib().afv_extract_batch(self._h, _vp(gray), B, w, h, w, C.c_long(w * h), _vp(kps), _vp(desc), _vp(size),
+                                       self.cap, _vp(n)))
+        return kps, desc, size, n
+
+    def __call__(self, gray):
+        kps, desc, size, n = self.extract_batch(np.asarray(gray)[None])
+        m = int(n[0])
+        return kps[0, :m], desc[0, :m], size[0, :m]
+
+    # ---- device buffers (torch) -----------------------------------------------------------------------
+    def alloc_device_outputs(self, B):
+        import torch
+        dev = torch.device("cuda", self.device)
+        return (torch.zeros((B, self.cap, 7), dtype=torch.float32, device=dev),       # afv_keypoint rows (28 B)
+                torch.zeros((B, self.cap, self.desc_bytes), dtype=torch.uint8, device=dev),
+                torch.zeros((B, self.cap), dtype=torch.float32, device=dev),
+                torch.zeros((B,), dtype=torch.int32, device=dev))
+
+    def extract_batch_device(self, d_gray, out, stream=None):
+        """d_gray: uint8 cuda tensor [B,H,W]; out from alloc_device_outputs. Asynchronous on `stream`."""
+        B, h, w = d_gray.shape
+        kps, desc, size, n = out
+        _check(lib().afv_extract_batch_device(self._h, _vp(d_gray), B, w, h, d_gray.stride(1), C.c_long(d_gray.stride(0)),
+                                              _vp(kps), _vp(desc), _vp(size), self.cap, _vp(n), _stream_ptr(stream)))
+        return out
+
+    def status(self):
+        _check(lib().afv_extractor_status(self._h))
+
+    def debug_read(self, what, frame, level, nbytes_cap=1 << 24):
+        buf = np.zeros(nbytes_cap, np.uint8)
+        n = C.c_long(0)
+        _check(lib().afv_debug_read(self._h, what, frame, level, _vp(buf), C.c_long(nbytes_cap), C.byref(n)))
+        return buf[:n.value].copy()
+
+
+def kps_from_device(t, n):
+    """[cap,7] float32 device rows -> numpy structured afv_keypoint array of length n."""
+    a = t[:n].contiguous().cpu().numpy()
+    return a.view(np.uint8).reshape(n, 28).view(KP_DTYPE).reshape(n)
+
+
+from . import matcher as matcher  # noqa: E402  (FeatureMatcher mirror)
+from . import synth as synth  # noqa: E402  (synthetic frame generator)
+from .matcher import FeatureMatcher  # noqa: E402,F401

@@ -1,0 +1,541 @@
+// afv_match.cu -- hand-written sm_100a kernels + C ABI of the FeatureMatcher path.
+//
+// Reference: src/FeatureMatcher.cc (SearchForInitialization :399-557, SearchByBoW :186-283, window search of
+// SearchByProjection :73-154, DescriptorDistance :1508-1531, rotation histogram :1579-1668) and the Frame grid
+// (src/Frame.cc:225-240, :333-394).  The reference walks Frame/KeyFrame/MapPoint graphs one candidate at a
+// time; here the same decisions are taken on flat arrays:
+//   * distances are warp/CTA-parallel popcounts (binary descriptors) or float-diff / double-accumulate L2^2;
+//   * "first minimum wins" of the sequential loops is an explicit order key carried through the reductions:
+//     (distance, enumeration position) compared lexicographically, top-2 of that order = (best, second);
+//   * loops whose iterations depend on earlier ones ("already matched", match stealing) stay sequential over
+//     queries inside one CTA per frame pair, with all candidate work of a query done in parallel.
+#include "afv_common.cuh"
+#include <float.h>
+
+#define NCELLS (AFV_GRID_COLS * AFV_GRID_ROWS)
+
+static inline cudaStream_t as_stream(void* s) { return (cudaStream_t)s; }
+
+__host__ __device__ inline int desc_bytes(int desc_type) {
+    return desc_type == AFV_FEAT_ORB32 ? 32 : desc_type == AFV_FEAT_AKAZE61 ? 61 : desc_type == AFV_FEAT_BRISK48 ? 48
+         : desc_type == AFV_FEAT_SIFT128 ? 512 : -1;
+}
+
+// ---- distances ----------------------------------------------------------------------------------------
+// Binary: popcount of XOR over D bytes (== the reference's bit-hack for orb32, cv::norm(NORM_HAMMING) for
+// akaze61/brisk48).  `a`/`b` may be unaligned (61-byte rows): word path only when both are 4-byte aligned.
+__device__ __forceinline__ int hamming_bytes(const uint8_t* __restrict__ a, const uint8_t* __restrict__ b, int D) {
+    int d = 0;
+    if ((((uintptr_t)a | (uintptr_t)b) & 3) == 0) {
+        const uint32_t* x = reinterpret_cast<const uint32_t*>(a);
+        const uint32_t* y = reinterpret_cast<const uint32_t*>(b);
+        const int nw = D >> 2;
+        for (int i = 0; i < nw; ++i) d += __popc(x[i] ^ y[i]);
+        for (int i = nw * 4; i < D; ++i) d += __popc((uint32_t)(a[i] ^ b[i]));
+    } else {
+        for (int i = 0; i < D; ++i) d += __popc((uint32_t)(a[i] ^ b[i]));
+    }
+    return d;
+}
+// cv::norm(a,b,NORM_L2SQR) on CV_32F (normL2Sqr<float,double>): float differences, double accumulation in
+// groups of four, result narrowed to float (Descriptor_Distance_Type).
+__device__ __forceinline__ float l2sqr128(const float* __restrict__ a, const float* __restrict__ b) {
+    double s = 0.0;
+    for (int i = 0; i < 128; i += 4) {
+        const double v0 = (double)(a[i] - b[i]), v1 = (double)(a[i + 1] - b[i + 1]);
+        const double v2 = (double)(a[i + 2] - b[i + 2]), v3 = (double)(a[i + 3] - b[i + 3]);
+        s += v0 * v0 + v1 * v1 + v2 * v2 + v3 * v3;
+    }
+    return (float)s;
+}
+__device__ __forceinline__ float desc_distance(int desc_type, const void* a, const void* b, int D) {
+    if (desc_type == AFV_FEAT_SIFT128) return l2sqr128((const float*)a, (const float*)b);
+    return (float)hamming_bytes((const uint8_t*)a, (const uint8_t*)b, D);
+}
+
+// ---- (distance, order) top-2 --------------------------------------------------------------------------
+// key = distance bits (non-negative float => monotone as uint) << 32 | enumeration order.  Smaller = better.
+struct Top2 { unsigned long long k1, k2; };
+#define KEY_NONE 0xffffffffffffffffull
+__device__ __forceinline__ void top2_push(Top2& t, unsigned long long k) {
+    if (k < t.k1) { t.k2 = t.k1; t.k1 = k; } else if (k < t.k2) t.k2 = k;
+}
+__device__ __forceinline__ void top2_warp_reduce(Top2& t) {
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+        const unsigned long long a = __shfl_xor_sync(0xffffffffu, t.k1, o);
+        const unsigned long long b = __shfl_xor_sync(0xffffffffu, t.k2, o);
+        top2_push(t, a); top2_push(t, b);
+    }
+}
+__device__ __forceinline__ unsigned long long make_key(float dist, uint32_t order) {
+    return ((unsigned long long)__float_as_uint(dist) << 32) | order;
+}
+__device__ __forceinline__ float key_dist(unsigned long long k) {
+    return k == KEY_NONE ? FLT_MAX : __uint_as_float((uint32_t)(k >> 32));
+}
+
+// ---- Frame grid ---------------------------------------------------------------------------------------
+// Frame::PosInGrid (src/Frame.cc:384-394): round() of the scaled coordinate, dropped when outside 64x48.
+__device__ __forceinline__ int grid_cell(float x, float y, float minX, float minY, float invW, float invH) {
+    const int px = (int)roundf(__fmul_rn(__fsub_rn(x, minX), invW));
+    const int py = (int)roundf(__fmul_rn(__fsub_rn(y, minY), invH));
+    if (px < 0 || px >= AFV_GRID_COLS || py < 0 || py >= AFV_GRID_ROWS) return -1;
+    return px * AFV_GRID_ROWS + py;
+}
+// Frame::GetFeaturesInArea cell range (src/Frame.cc:339-353). Returns false when the window misses the grid.
+__device__ __forceinline__ bool window_cells(float x, float y, float r, float minX, float minY, float invW, float invH,
+                                             int& c0, int& c1, int& r0, int& r1) {
+    c0 = max(0, (int)floorf(__fmul_rn(__fsub_rn(__fsub_rn(x, minX), r), invW)));
+    if (c0 >= AFV_GRID_COLS) return false;
+    c1 = min(AFV_GRID_COLS - 1, (int)ceilf(__fmul_rn(__fadd_rn(__fsub_rn(x, minX), r), invW)));
+    if (c1 < 0) return false;
+    r0 = max(0, (int)floorf(__fmul_rn(__fsub_rn(__fsub_rn(y, minY), r), invH)));
+    if (r0 >= AFV_GRID_ROWS) return false;
+    r1 = min(AFV_GRID_ROWS - 1, (int)ceilf(__fmul_rn(__fadd_rn(__fsub_rn(y, minY), r), invH)));
+    if (r1 < 0) return false;
+    return true;
+}
+
+// One CTA per frame: CSR grid with items ascending inside each cell (== push_back order of the reference).
+__global__ void __launch_bounds__(256) k_grid_build(const afv_keypoint* __restrict__ kps, const int* __restrict__ n_arr,
+                                                    int cap, float minX, float minY, float invW, float invH,
+                                                    int* __restrict__ cell_start, int* __restrict__ cell_items) {
+    __shared__ int cnt[NCELLS + 1];
+    __shared__ int warp_tot[8];
+    const int f = blockIdx.x, tid = threadIdx.x;
+    const int n = min(n_arr[f], cap);
+    const afv_keypoint* k = kps + (long long)f * cap;
+    int* cs = cell_start + (long long)f * (NCELLS + 1);
+    int* ci = cell_items + (long long)f * cap;
+    for (int i = tid; i <= NCELLS; i += 256) cnt[i] = 0;
+    __syncthreads();
+    for (int i = tid; i < n; i += 256) {
+        const int c = grid_cell(k[i].x, k[i].y, minX, minY, invW, invH);
+        if (c >= 0) atomicAdd(&cnt[c], 1);
+    }
+    __syncthreads();
+    // exclusive scan of 3072 counters: 12 per thread
+    const int items = (NCELLS + 255) / 256, beg = tid * items, end = min(beg + items, NCELLS);
+    int sum = 0;
+    for (int i = beg; i < end; ++i) sum += cnt[i];
+    const int lane = tid & 31, wid = tid >> 5;
+    int incl = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+    if (lane == 31) warp_tot[wid] = incl;
+    __syncthreads();
+    int base = 0;
+    for (int w = 0; w < wid; ++w) base += warp_tot[w];
+    int run = base + incl - sum;
+    for (int i = beg; i < end; ++i) { const int v = cnt[i]; cnt[i] = run; cs[i] = run; run += v; }
+    if (tid == 255) cs[NCELLS] = run;
+    __syncthreads();
+    for (int i = tid; i < n; i += 256) {
+        const int c = grid_cell(k[i].x, k[i].y, minX, minY, invW, invH);
+        if (c >= 0) ci[atomicAdd(&cnt[c], 1)] = i;
+    }
+    __syncthreads();
+    // restore ascending index order inside each cell (cells hold a handful of items)
+    for (int c = tid; c < NCELLS; c += 256) {
+        const int b = cs[c], e = cnt[c];
+        for (int i = b + 1; i < e; ++i) {
+            const int v = ci[i];
+            int j = i - 1;
+            while (j >= b && ci[j] > v) { ci[j + 1] = ci[j]; --j; }
+            ci[j + 1] = v;
+        }
+    }
+}
+
+extern "C" int afv_grid_build(const afv_keypoint* d_kps, const int* d_n, int B, int cap,
+                              float min_x, float min_y, float max_x, float max_y,
+                              int* d_cell_start, int* d_cell_items, void* cuda_stream) {
+    if (!d_kps || !d_n || !d_cell_start || !d_cell_items || B < 1) { afv_set_error("afv_grid_build: bad argument"); return AFV_ERR_INVALID; }
+    const float invW = (float)AFV_GRID_COLS / (max_x - min_x), invH = (float)AFV_GRID_ROWS / (max_y - min_y);
+    k_grid_build<<<B, 256, 0, as_stream(cuda_stream)>>>(d_kps, d_n, cap, min_x, min_y, invW, invH, d_cell_start, d_cell_items);
+    ++g_afv_launches;
+    AFV_CUDA_CHECK(cudaGetLastError());
+    return AFV_OK;
+}
+
+// ---- stateless window search: one warp per query ---------------------------------------------------------
+__global__ void __launch_bounds__(256) k_match_window(int desc_type, int D, const uint8_t* __restrict__ q,
+        const float* __restrict__ qxy, const float* __restrict__ qr, const float* __restrict__ qmin,
+        const float* __restrict__ qmax, int nq, const afv_keypoint* __restrict__ tk, const uint8_t* __restrict__ td,
+        const float* __restrict__ tsize, const int* __restrict__ cs, const int* __restrict__ ci,
+        float minX, float minY, float invW, float invH,
+        int* __restrict__ best, float* __restrict__ bestd, float* __restrict__ secondd,
+        float* __restrict__ best_size, float* __restrict__ second_size) {
+    const int qi = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (qi >= nq) return;
+    const float x = qxy[2 * qi], y = qxy[2 * qi + 1], r = qr[qi], smin = qmin[qi], smax = qmax[qi];
+    Top2 t; t.k1 = t.k2 = KEY_NONE;
+    int c0, c1, r0, r1;
+    if (window_cells(x, y, r, minX, minY, invW, invH, c0, c1, r0, r1)) {
+        const uint8_t* qd = q + (long long)qi * D;
+        uint32_t ebase = 0;
+        for (int ix = c0; ix <= c1; ++ix) {
+            const int sb = cs[ix * AFV_GRID_ROWS + r0], se = cs[ix * AFV_GRID_ROWS + r1 + 1];
+            for (int j = sb + lane; j < se; j += 32) {
+                const int idx = ci[j];
+                const float sz = tsize[idx];
+                if (sz < smin || sz > smax) continue;
+                const float dx = __fsub_rn(tk[idx].x, x), dy = __fsub_rn(tk[idx].y, y);
+                if (fabsf(dx) < r && fabsf(dy) < r) {
+                    const float d = desc_distance(desc_type, qd, td + (long long)idx * D, D);
+                    // order = enumeration position; idx is recovered from ci[] through it
+                    top2_push(t, make_key(d, ebase + (uint32_t)(j - sb)));
+                }
+            }
+            ebase += (uint32_t)(se - sb);
+        }
+        top2_warp_reduce(t);
+    }
+    if (lane == 0) {
+        // map enumeration positions back to train indices
+        int bi = -1, si = -1;
+        if (t.k1 != KEY_NONE || t.k2 != KEY_NONE) {
+            uint32_t e1 = (uint32_t)t.k1, e2 = (uint32_t)t.k2, ebase = 0;
+            for (int ix = c0; ix <= c1; ++ix) {
+                const int sb = cs[ix * AFV_GRID_ROWS + r0], se = cs[ix * AFV_GRID_ROWS + r1 + 1];
+                const uint32_t len = (uint32_t)(se - sb);
+                if (t.k1 != KEY_NONE && e1 >= ebase && e1 < ebase + len) bi = ci[sb + (e1 - ebase)];
+                if (t.k2 != KEY_NONE && e2 >= ebase && e2 < ebase + len) si = ci[sb + (e2 - ebase)];
+                ebase += len;
+            }
+        }
+        best[qi] = bi; bestd[qi] = key_dist(t.k1); secondd[qi] = key_dist(t.k2);
+        if (best_size) best_size[qi] = bi >= 0 ? tsize[bi] : -1.0f;
+        if (second_size) second_size[qi] = si >= 0 ? tsize[si] : -1.0f;
+    }
+}
+
+extern "C" int afv_match_window(int desc_type, const void* d_q, const float* d_qxy, const float* d_qr,
+                                const float* d_qmin_size, const float* d_qmax_size, int nq,
+                                const afv_keypoint* d_tk, const void* d_td, const float* d_tsize, int nt,
+                                const int* d_cell_start, const int* d_cell_items,
+                                float min_x, float min_y, float max_x, float max_y,
+                                int* d_best, float* d_bestd, float* d_secondd, float* d_best_size, float* d_second_size,
+                                void* cuda_stream) {
+    const int D = desc_bytes(desc_type);
+    if (D < 0 || !d_q || !d_qxy || !d_qr || !d_qmin_size || !d_qmax_size || !d_tk || !d_td || !d_tsize || !d_cell_start ||
+        !d_cell_items || !d_best || !d_bestd || !d_secondd || nq < 0 || nt < 0) { afv_set_error("afv_match_window: bad argument"); return AFV_ERR_INVALID; }
+    if (nq == 0) return AFV_OK;
+    const float invW = (float)AFV_GRID_COLS / (max_x - min_x), invH = (float)AFV_GRID_ROWS / (max_y - min_y);
+    k_match_window<<<(nq + 7) / 8, 256, 0, as_stream(cuda_stream)>>>(desc_type, D, (const uint8_t*)d_q, d_qxy, d_qr, d_qmin_size,
+        d_qmax_size, nq, d_tk, (const uint8_t*)d_td, d_tsize, d_cell_start, d_cell_items, min_x, min_y, invW, invH,
+        d_best, d_bestd, d_secondd, d_best_size, d_second_size);
+    ++g_afv_launches;
+    AFV_CUDA_CHECK(cudaGetLastError());
+    return AFV_OK;
+}
+
+// ---- SearchForInitialization: one CTA per frame pair ----------------------------------------------------
+// Train frame staged in shared memory (x, y, size, grid cell, descriptor when it fits); queries processed in
+// index order; per query every thread scans a slice of the train keypoints: a keypoint is a candidate iff its
+// grid cell lies in the query's cell range (this reproduces the round()-vs-floor/ceil quirk of the reference
+// grid exactly), passes the size gate and |dx|,|dy| < r.  Enumeration order of the reference (cell x, cell y,
+// index) is the order key.
+#define SFI_THREADS 128
+__device__ __forceinline__ int rot_bin(float a1, float a2) {       // updateRotationHistogram (:1587-1597)
+    float rot = __fsub_rn(a1, a2);
+    if (rot < 0.0f) rot = __fadd_rn(rot, 360.0f);
+    const float rotFactor = __fdiv_rn(1.0f, (float)AFV_HISTO_LENGTH);
+    int bin = (int)roundf(__fmul_rn(rot, rotFactor));
+    if (bin == AFV_HISTO_LENGTH) bin = 0;
+    return bin;
+}
+__device__ __forceinline__ void three_maxima(const int* cnt, int& ind1, int& ind2, int& ind3) {   // :1631-1668
+    int max1 = 0, max2 = 0, max3 = 0;
+    ind1 = ind2 = ind3 = -1;
+    for (int i = 0; i < AFV_HISTO_LENGTH; ++i) {
+        const int s = cnt[i];
+        if (s > max1) { max3 = max2; max2 = max1; max1 = s; ind3 = ind2; ind2 = ind1; ind1 = i; }
+        else if (s > max2) { max3 = max2; max2 = s; ind3 = ind2; ind2 = i; }
+        else if (s > max3) { max3 = s; ind3 = i; }
+    }
+    if ((float)max2 < __fmul_rn(0.1f, (float)max1)) { ind2 = -1; ind3 = -1; }
+    else if ((float)max3 < __fmul_rn(0.1f, (float)max1)) { ind3 = -1; }
+}
+
+__global__ void __launch_bounds__(SFI_THREADS) k_search_init(int desc_type, int D, int Dpad, int stage_desc,
+        const afv_keypoint* __restrict__ kps, const uint8_t* __restrict__ desc, const float* __restrict__ kpsize,
+        const int* __restrict__ n_arr, int cap, const int* __restrict__ pair_a, const int* __restrict__ pair_b,
+        float minX, float minY, float invW, float invH, float max_kpt_size,
+        float* __restrict__ prev_matched, float window, float th_low, float nnratio, int check_ori,
+        int* __restrict__ matches12, int* __restrict__ nmatches) {
+    extern __shared__ __align__(16) unsigned char sm[];
+    const int p = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int fa = pair_a[p], fb = pair_b[p];
+    const int n1 = min(n_arr[fa], cap), n2 = min(n_arr[fb], cap);
+    const afv_keypoint* k1 = kps + (long long)fa * cap;
+    const afv_keypoint* k2 = kps + (long long)fb * cap;
+    const uint8_t* d1 = desc + (long long)fa * cap * D;
+    const uint8_t* d2 = desc + (long long)fb * cap * D;
+    const float* size2 = kpsize + (long long)fb * cap;
+    float* pm = prev_matched + (long long)p * cap * 2;
+    int* m12 = matches12 + (long long)p * cap;
+
+    float* tx = reinterpret_cast<float*>(sm);                       // [cap]
+    float* ty = tx + cap;
+    float* matchedDist = ty + cap;
+    int* m21 = reinterpret_cast<int*>(matchedDist + cap);
+    unsigned short* tcell = reinterpret_cast<unsigned short*>(m21 + cap);     // cx<<8|cy, 0xffff = not in grid / size-gated
+    signed char* hbin = reinterpret_cast<signed char*>(tcell + cap);          // [cap] histogram bin of query i1 (or -1)
+    uint8_t* tdesc = reinterpret_cast<uint8_t*>(sm) + (((size_t)cap * (4 + 4 + 4 + 4 + 2 + 1)) + 15 & ~(size_t)15);
+    __shared__ Top2 wtop[SFI_THREADS / 32];
+    __shared__ int hist[AFV_HISTO_LENGTH];
+    __shared__ int s_nm;
+
+    for (int i = tid; i < n2; i += SFI_THREADS) {
+        const float x = k2[i].x, y = k2[i].y, sz = size2[i];
+        tx[i] = x; ty[i] = y; matchedDist[i] = FLT_MAX; m21[i] = -1;
+        const int c = grid_cell(x, y, minX, minY, invW, invH);
+        // GetFeaturesInArea(…, minSize 0, maxSize F1.maxKeyPtSize) size gate folded in (:495-496, Frame.cc:365-368)
+        const bool ok = c >= 0 && !(sz < 0.0f) && !(sz > max_kpt_size);
+        tcell[i] = ok ? (unsigned short)(((c / AFV_GRID_ROWS) << 8) | (c % AFV_GRID_ROWS)) : (unsigned short)0xffff;
+    }
+    if (stage_desc) {
+        for (int i = tid; i < n2 * (Dpad / 4); i += SFI_THREADS) {
+            const int r = i / (Dpad / 4), w = i % (Dpad / 4);
+            uint32_t v = 0;
+            for (int b = 0; b < 4; ++b) { const int o = w * 4 + b; if (o < D) v |= (uint32_t)d2[(long long)r * D + o] << (8 * b); }
+            reinterpret_cast<uint32_t*>(tdesc)[i] = v;
+        }
+    }
+    for (int i = tid; i < n1; i += SFI_THREADS) { m12[i] = -1; hbin[i] = -1; }
+    if (tid < AFV_HISTO_LENGTH) hist[tid] = 0;
+    if (tid == 0) s_nm = 0;
+    __syncthreads();
+
+    const int nw = Dpad / 4;
+    for (int i1 = 0; i1 < n1; ++i1) {
+        if (k1[i1].octave > 0) continue;                              // :491-493
+        const float x = pm[2 * i1], y = pm[2 * i1 + 1];
+        int c0, c1, r0, r1;
+        Top2 t; t.k1 = t.k2 = KEY_NONE;
+        if (window_cells(x, y, window, minX, minY, invW, invH, c0, c1, r0, r1)) {
+            uint32_t qd[16];
+            if (desc_type != AFV_FEAT_SIFT128) {
+                const uint8_t* qrow = d1 + (long long)i1 * D;
+                if ((D & 3) == 0 && ((uintptr_t)qrow & 3) == 0) {
+                    for (int w = 0; w < nw; ++w) qd[w] = reinterpret_cast<const uint32_t*>(qrow)[w];
+                } else {
+                    for (int w = 0; w < nw; ++w) {
+                        uint32_t v = 0;
+                        for (int b = 0; b < 4; ++b) { const int o = w * 4 + b; if (o < D) v |= (uint32_t)qrow[o] << (8 * b); }
+                        qd[w] = v;
+                    }
+                }
+            }
+            for (int i2 = tid; i2 < n2; i2 += SFI_THREADS) {
+                const unsigned short cc = tcell[i2];
+                if (cc == 0xffff) continue;
+                const int cx = cc >> 8, cy = cc & 0xff;
+                if (cx < c0 || cx > c1 || cy < r0 || cy > r1) continue;
+                const float dx = __fsub_rn(tx[i2], x), dy = __fsub_rn(ty[i2], y);
+                if (!(fabsf(dx) < window && fabsf(dy) < window)) continue;
+                float dist;
+                if (desc_type == AFV_FEAT_SIFT128) dist = l2sqr128((const float*)(d1 + (long long)i1 * D), (const float*)(d2 + (long long)i2 * D));
+                else if (stage_desc) {
+                    const uint32_t* y32 = reinterpret_cast<const uint32_t*>(tdesc) + (long long)i2 * nw;
+                    int d = 0;
+                    for (int w = 0; w < nw; ++w) d += __popc(qd[w] ^ y32[w]);
+                    dist = (float)d;
+                } else dist = (float)hamming_bytes(d1 + (long long)i1 * D, d2 + (long long)i2 * D, D);
+                if (matchedDist[i2] <= dist) continue;                // :511-512
+                top2_push(t, make_key(dist, ((uint32_t)cx << 26) | ((uint32_t)cy << 20) | (uint32_t)i2));
+            }
+        }
+        top2_warp_reduce(t);
+        if (lane == 0) wtop[wid] = t;
+        __syncthreads();
+        if (tid == 0) {
+            Top2 r = wtop[0];
+            for (int w = 1; w < SFI_THREADS / 32; ++w) { top2_push(r, wtop[w].k1); top2_push(r, wtop[w].k2); }
+            if (r.k1 != KEY_NONE) {
+                const float bestDist = key_dist(r.k1), bestDist2 = key_dist(r.k2);
+                const int bestIdx2 = (int)((uint32_t)r.k1 & 0xfffffu);
+                if (bestDist <= th_low && bestDist < __fmul_rn(bestDist2, nnratio)) {       // :526-528
+                    if (m21[bestIdx2] >= 0) { m12[m21[bestIdx2]] = -1; s_nm--; }
+                    m12[i1] = bestIdx2; m21[bestIdx2] = i1; matchedDist[bestIdx2] = bestDist; s_nm++;
+                    if (check_ori) { const int bin = rot_bin(k1[i1].angle, k2[bestIdx2].angle); hbin[i1] = (signed char)bin; hist[bin]++; }
+                }
+            }
+        }
+        __syncthreads();
+    }
+    if (check_ori) {
+        __shared__ int keepbin[3];
+        if (tid == 0) three_maxima(hist, keepbin[0], keepbin[1], keepbin[2]);
+        __syncthreads();
+        int removed = 0;
+        for (int i = tid; i < n1; i += SFI_THREADS) {
+            const int b = hbin[i];
+            if (b < 0 || b == keepbin[0] || b == keepbin[1] || b == keepbin[2]) continue;
+            if (m12[i] >= 0) { m12[i] = -1; ++removed; }
+        }
+        if (removed) atomicSub(&s_nm, removed);
+        __syncthreads();
+    }
+    for (int i = tid; i < n1; i += SFI_THREADS)                       // :552-554
+        if (m12[i] >= 0) { pm[2 * i] = k2[m12[i]].x; pm[2 * i + 1] = k2[m12[i]].y; }
+    if (tid == 0) nmatches[p] = s_nm;
+}
+
+extern "C" int afv_search_for_initialization(int desc_type, const afv_keypoint* d_kps, const void* d_desc,
+        const float* d_kpsize, const int* d_n, int B, int cap, const int* d_pair_a, const int* d_pair_b, int P,
+        float min_x, float min_y, float max_x, float max_y, float max_kpt_size,
+        float* d_prev_matched, int window, float th_low, float nnratio, int check_orientation,
+        int* d_matches12, int* d_nmatches, void* cuda_stream) {
+    const int D = desc_bytes(desc_type);
+    if (D < 0 || !d_kps || !d_desc || !d_kpsize || !d_n || !d_pair_a || !d_pair_b || !d_prev_matched || !d_matches12 ||
+        !d_nmatches || B < 1 || P < 0 || cap < 1) { afv_set_error("afv_search_for_initialization: bad argument"); return AFV_ERR_INVALID; }
+    if (P == 0) return AFV_OK;
+    if (cap >= (1 << 20)) { afv_set_error("cap too large for the order key"); return AFV_ERR_INVALID; }
+    const int Dpad = (D + 3) & ~3;
+    size_t base = (((size_t)cap * (4 + 4 + 4 + 4 + 2 + 1)) + 15) & ~(size_t)15;
+    int stage = desc_type != AFV_FEAT_SIFT128 && Dpad <= 64 && base + (size_t)cap * Dpad <= 200 * 1024;
+    size_t smem = base + (stage ? (size_t)cap * Dpad : 0);
+    static size_t configured = 0;
+    if (smem > configured) {
+        AFV_CUDA_CHECK(cudaFuncSetAttribute(k_search_init, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
+    }
+    const float invW = (float)AFV_GRID_COLS / (max_x - min_x), invH = (float)AFV_GRID_ROWS / (max_y - min_y);
+    k_search_init<<<P, SFI_THREADS, smem, as_stream(cuda_stream)>>>(desc_type, D, Dpad, stage, d_kps, (const uint8_t*)d_desc, d_kpsize,
+        d_n, cap, d_pair_a, d_pair_b, min_x, min_y, invW, invH, max_kpt_size, d_prev_matched, (float)window, th_low, nnratio,
+        check_orientation, d_matches12, d_nmatches);
+    ++g_afv_launches;
+    AFV_CUDA_CHECK(cudaGetLastError());
+    return AFV_OK;
+}
+
+// ---- brute force N x M: one warp per query, lanes stride over train descriptors ----------------------------
+__global__ void __launch_bounds__(256) k_match_bf(int desc_type, int D, const uint8_t* __restrict__ q, int nq,
+        const uint8_t* __restrict__ t, int nt, int* __restrict__ best, float* __restrict__ bestd, float* __restrict__ secondd) {
+    const int qi = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (qi >= nq) return;
+    Top2 tt; tt.k1 = tt.k2 = KEY_NONE;
+    const uint8_t* qd = q + (long long)qi * D;
+    if (desc_type == AFV_FEAT_ORB32 && (((uintptr_t)q | (uintptr_t)t) & 15) == 0) {
+        const uint4 a0 = reinterpret_cast<const uint4*>(qd)[0], a1 = reinterpret_cast<const uint4*>(qd)[1];
+        for (int j = lane; j < nt; j += 32) {
+            const uint4 b0 = reinterpret_cast<const uint4*>(t + (long long)j * 32)[0], b1 = reinterpret_cast<const uint4*>(t + (long long)j * 32)[1];
+            const int d = __popc(a0.x ^ b0.x) + __popc(a0.y ^ b0.y) + __popc(a0.z ^ b0.z) + __popc(a0.w ^ b0.w) +
+                          __popc(a1.x ^ b1.x) + __popc(a1.y ^ b1.y) + __popc(a1.z ^ b1.z) + __popc(a1.w ^ b1.w);
+            top2_push(tt, make_key((float)d, (uint32_t)j));
+        }
+    } else {
+        for (int j = lane; j < nt; j += 32)
+            top2_push(tt, make_key(desc_distance(desc_type, qd, t + (long long)j * D, D), (uint32_t)j));
+    }
+    top2_warp_reduce(tt);
+    if (lane == 0) {
+        best[qi] = tt.k1 == KEY_NONE ? -1 : (int)(uint32_t)tt.k1;
+        bestd[qi] = key_dist(tt.k1); secondd[qi] = key_dist(tt.k2);
+    }
+}
+
+extern "C" int afv_match_bruteforce(int desc_type, const void* d_q, int nq, const void* d_t, int nt,
+                                    int* d_best, float* d_bestd, float* d_secondd, void* cuda_stream) {
+    const int D = desc_bytes(desc_type);
+    if (D < 0 || !d_q || !d_t || !d_best || !d_bestd || !d_secondd || nq < 0 || nt < 0) { afv_set_error("afv_match_bruteforce: bad argument"); return AFV_ERR_INVALID; }
+    if (nq == 0) return AFV_OK;
+    k_match_bf<<<(nq + 7) / 8, 256, 0, as_stream(cuda_stream)>>>(desc_type, D, (const uint8_t*)d_q, nq, (const uint8_t*)d_t, nt, d_best, d_bestd, d_secondd);
+    ++g_afv_launches;
+    AFV_CUDA_CHECK(cudaGetLastError());
+    return AFV_OK;
+}
+
+// ---- SearchByBoW(KF, F): one warp walks the merge-join; lanes share a bucket's frame features ---------------
+__global__ void __launch_bounds__(32) k_search_bow(int desc_type, int D, const uint8_t* __restrict__ dkf,
+        const afv_keypoint* __restrict__ kkf, const int* __restrict__ kf_node, const int* __restrict__ kf_start,
+        const int* __restrict__ kf_idx, int kf_nodes, const uint8_t* __restrict__ df, const afv_keypoint* __restrict__ kf_f,
+        int nf, const int* __restrict__ f_node, const int* __restrict__ f_start, const int* __restrict__ f_idx, int f_nodes,
+        float th_low, float nnratio, int check_ori, int* __restrict__ match_f, int* __restrict__ nmatches, signed char* __restrict__ bin_of) {
+    __shared__ int hist[AFV_HISTO_LENGTH];
+    const int lane = threadIdx.x;
+    for (int i = lane; i < nf; i += 32) { match_f[i] = -1; bin_of[i] = -1; }
+    if (lane < AFV_HISTO_LENGTH) hist[lane] = 0;
+    __syncwarp();
+    int nm = 0, a = 0, b = 0;
+    while (a < kf_nodes && b < f_nodes) {
+        const int na = kf_node[a], nb = f_node[b];
+        if (na == nb) {
+            const int fb0 = f_start[b], fb1 = f_start[b + 1];
+            for (int iKF = kf_start[a]; iKF < kf_start[a + 1]; ++iKF) {
+                const int realKF = kf_idx[iKF];
+                const uint8_t* ref = dkf + (long long)realKF * D;
+                Top2 t; t.k1 = t.k2 = KEY_NONE;
+                for (int iF = fb0 + lane; iF < fb1; iF += 32) {
+                    const int realF = f_idx[iF];
+                    if (match_f[realF] >= 0) continue;                       // :232-233
+                    top2_push(t, make_key(desc_distance(desc_type, ref, df + (long long)realF * D, D), (uint32_t)(iF - fb0)));
+                }
+                top2_warp_reduce(t);
+                if (lane == 0 && t.k1 != KEY_NONE) {
+                    const float bd1 = key_dist(t.k1), bd2 = key_dist(t.k2);
+                    if (bd1 <= th_low && bd1 < __fmul_rn(nnratio, bd2)) {
+                        const int bestF = f_idx[fb0 + (int)(uint32_t)t.k1];
+                        match_f[bestF] = realKF; ++nm;
+                        if (check_ori) { const int bin = rot_bin(kkf[realKF].angle, kf_f[bestF].angle); bin_of[bestF] = (signed char)bin; hist[bin]++; }
+                    }
+                }
+                __syncwarp();
+                __threadfence_block();
+            }
+            ++a; ++b;
+        } else if (na < nb) ++a; else ++b;
+    }
+    nm = __shfl_sync(0xffffffffu, nm, 0);
+    if (check_ori) {
+        __shared__ int keepbin[3];
+        if (lane == 0) three_maxima(hist, keepbin[0], keepbin[1], keepbin[2]);
+        __syncwarp();
+        int removed = 0;
+        for (int i = lane; i < nf; i += 32) {
+            const int bn = bin_of[i];
+            if (bn < 0 || bn == keepbin[0] || bn == keepbin[1] || bn == keepbin[2]) continue;
+            match_f[i] = -1; ++removed;
+        }
+#pragma unroll
+        for (int o = 16; o; o >>= 1) removed += __shfl_xor_sync(0xffffffffu, removed, o);
+        nm -= removed;
+    }
+    if (lane == 0) *nmatches = nm;
+}
+
+extern "C" int afv_search_by_bow(int desc_type, const void* d_dkf, const afv_keypoint* d_kkf,
+        const int* d_kf_node, const int* d_kf_start, const int* d_kf_idx, int kf_nodes,
+        const void* d_df, const afv_keypoint* d_kf_f, int nf,
+        const int* d_f_node, const int* d_f_start, const int* d_f_idx, int f_nodes,
+        float th_low, float nnratio, int check_orientation, int* d_match_f, int* d_nmatches, void* cuda_stream) {
+    const int D = desc_bytes(desc_type);
+    if (D < 0 || !d_dkf || !d_kkf || !d_kf_node || !d_kf_start || !d_kf_idx || !d_df || !d_kf_f || !d_f_node || !d_f_start ||
+        !d_f_idx || !d_match_f || !d_nmatches || nf < 0) { afv_set_error("afv_search_by_bow: bad argument"); return AFV_ERR_INVALID; }
+    signed char* bin_of = nullptr;
+    AFV_CUDA_CHECK(cudaMallocAsync((void**)&bin_of, (size_t)(nf > 0 ? nf : 1), as_stream(cuda_stream)));
+    k_search_bow<<<1, 32, 0, as_stream(cuda_stream)>>>(desc_type, D, (const uint8_t*)d_dkf, d_kkf, d_kf_node, d_kf_start, d_kf_idx, kf_nodes,
+        (const uint8_t*)d_df, d_kf_f, nf, d_f_node, d_f_start, d_f_idx, f_nodes, th_low, nnratio, check_orientation, d_match_f, d_nmatches, bin_of);
+    ++g_afv_launches;
+    AFV_CUDA_CHECK(cudaGetLastError());
+    AFV_CUDA_CHECK(cudaFreeAsync(bin_of, as_stream(cuda_stream)));
+    return AFV_OK;
+}
+
+// ---- DescriptorDistance for n pairs ----------------------------------------------------------------------
+__global__ void k_desc_distance(int desc_type, int D, const uint8_t* __restrict__ a, const uint8_t* __restrict__ b, int n, float* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = desc_distance(desc_type, a + (long long)i * D, b + (long long)i * D, D);
+}
+extern "C" int afv_descriptor_distance(int desc_type, const void* d_a, const void* d_b, int n, float* d_out, void* cuda_stream) {
+    const int D = desc_bytes(desc_type);
+    if (D < 0 || !d_a || !d_b || !d_out || n < 0) { afv_set_error("afv_descriptor_distance: bad argument"); return AFV_ERR_INVALID; }
+    if (n == 0) return AFV_OK;
+    k_desc_distance<<<(n + 127) / 128, 128, 0, as_stream(cuda_stream)>>>(desc_type, D, (const uint8_t*)d_a, (const uint8_t*)d_b, n, d_out);
+    ++g_afv_launches;
+    AFV_CUDA_CHECK(cudaGetLastError());
+    return AFV_OK;
+}

@@ -1,0 +1,769 @@
+// afv_orb.cu -- hand-written sm_100a kernels of the orb32 extraction path.
+//
+// Replaces, behind the C ABI of include/afv.h, what the reference's FeatureExtractor_orb32 runs on the CPU
+// per frame (reference src/Feature_orb32.cpp:11-65 -> cv::ORB::detect / DistributeOctTree / cv::ORB::compute):
+//   K2 k_resize          cv::resize INTER_LINEAR_EXACT pyramid (level l from l-1)
+//   K3 k_fast            FAST-9/16 score + 3x3 NMS, unordered candidate append
+//   K4/K5 k_harris_select retainBest(2q, FAST score) -> Harris 7x7 -> retainBest(q, Harris) (radix select)
+//   K9 k_octree          DistributeOctTree (src/ORBextractor.cc:181-458), one CTA per (frame, level)
+//   K7 k_blur            7x7 sigma-2 float separable blur of every level
+//   K6/K8/K10 k_describe IC angle + 256-bit steered BRIEF + merge into the caller's cv::KeyPoint layout
+// Every arithmetic step is written to round exactly like the pinned CPU path (see oracle/afv_oracle.c):
+// integer fixed point, explicit __f*_rn intrinsics (no contraction) and explicit __fmaf_rn where the pinned
+// binary fuses.  Results are bit-exact with the oracle; tests/test_extract_gpu.py checks that.
+#include "afv_common.cuh"
+#include <stdio.h>
+
+static __constant__ int8_t c_pattern[1024] = {
+#include "orb_pattern.inc"
+};
+static __constant__ int c_umax[16] = {15, 15, 15, 15, 14, 14, 14, 13, 13, 12, 11, 10, 9, 8, 6, 3};
+
+__device__ __forceinline__ int refl101(int i, int n) {
+    if (i < 0) i = -i;
+    if (i >= n) i = 2 * n - 2 - i;
+    return min(max(i, 0), n - 1);
+}
+
+// ------------------------------------------------------------------------------------------------------
+// K2: pyramid level from the previous one.  thread = 4 consecutive output pixels (one 32-bit store).
+// ------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_resize(const __grid_constant__ AfvParams P, int l) {
+    const AfvLevel& D = P.lv[l];
+    const AfvLevel& S = P.lv[l - 1];
+    const int f = blockIdx.z;
+    const int y = blockIdx.y * 8 + threadIdx.y;
+    const int x0 = (blockIdx.x * 32 + threadIdx.x) * 4;
+    if (y >= D.h || x0 >= D.w) return;
+    const uint8_t* src = S.img + (long long)f * S.img_fstride;
+    uint8_t* dst = const_cast<uint8_t*>(D.img) + (long long)f * D.img_fstride + (long long)y * D.img_stride;
+    const int yo = D.yofs[y], c1y = D.yc1[y], c0y = 256 - c1y;
+    const uint8_t* r0 = src + (long long)yo * S.img_stride;
+    const uint8_t* r1 = src + (long long)min(yo + 1, S.h - 1) * S.img_stride;
+    uint32_t out = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int x = min(x0 + k, D.w - 1);
+        const int xo = D.xofs[x], c1 = D.xc1[x], c0 = 256 - c1;
+        const int x1 = min(xo + 1, S.w - 1);
+        const uint32_t h0 = c0 * r0[xo] + c1 * r0[x1];
+        const uint32_t h1 = c0 * r1[xo] + c1 * r1[x1];
+        const uint32_t v = (uint32_t)c0y * h0 + (uint32_t)c1y * h1;
+        out |= ((v + (1u << 15)) >> 16) << (8 * k);
+    }
+    *reinterpret_cast<uint32_t*>(dst + x0) = out;       // rows are padded to 128 B: the tail store stays in-row
+}
+
+// ------------------------------------------------------------------------------------------------------
+// K3: FAST-9/16 + NMS.  Tile 128x16 (+4 halo), 256 threads.
+// ------------------------------------------------------------------------------------------------------
+#define FT_W 128
+#define FT_H 16
+#define FT_PW (FT_W + 8)
+#define FT_PH (FT_H + 8)
+#define FT_RW (FT_W + 2)
+#define FT_RH (FT_H + 2)
+#define FT_SW 132
+
+struct FastTiles { int start[AFV_MAX_LEVELS + 1]; int tiles_x[AFV_MAX_LEVELS]; };
+
+__device__ __forceinline__ bool has_arc9(uint32_t m) {
+    m |= m << 16;
+    uint32_t a = m & (m >> 1);
+    a &= a >> 2;
+    a &= a >> 4;
+    a &= m >> 8;
+    return (a & 0xffffu) != 0;
+}
+
+#define CIRC16(F) F(0, 0, 3) F(1, 1, 3) F(2, 2, 2) F(3, 3, 1) F(4, 3, 0) F(5, 3, -1) F(6, 2, -2) F(7, 1, -3) \
+                  F(8, 0, -3) F(9, -1, -3) F(10, -2, -2) F(11, -3, -1) F(12, -3, 0) F(13, -3, 1) F(14, -2, 2) F(15, -1, 3)
+
+__global__ void __launch_bounds__(256) k_fast(const __grid_constant__ AfvParams P, const __grid_constant__ FastTiles T) {
+    __shared__ __align__(16) uint8_t pix[FT_PH][FT_PW];
+    __shared__ uint8_t score[FT_RH][FT_SW];
+    __shared__ uint16_t clist[FT_RW * FT_RH];
+    __shared__ uint32_t surv[(FT_W / 2) * (FT_H / 2) + 64];
+    __shared__ int ncorner, nsurv, gbase;
+
+    int l = 0;
+    while (l + 1 < P.nlevels && (int)blockIdx.x >= T.start[l + 1]) ++l;
+    const AfvLevel& L = P.lv[l];
+    const int tile = blockIdx.x - T.start[l];
+    const int tx = tile % T.tiles_x[l], ty = tile / T.tiles_x[l];
+    const int f = blockIdx.y;
+    const int x0 = tx * FT_W, y0 = ty * FT_H;
+    const int tid = threadIdx.x;
+    const uint8_t* img = L.img + (long long)f * L.img_fstride;
+    const int t = P.fast_th;
+
+    if (tid == 0) { ncorner = 0; nsurv = 0; }
+    // stage the pixel tile (aligned 32-bit loads; rows outside the image read as 0)
+    for (int i = tid; i < FT_PH * (FT_PW / 4); i += 256) {
+        const int r = i / (FT_PW / 4), c4 = i % (FT_PW / 4);
+        const int gy = y0 - 4 + r, gx = x0 - 4 + c4 * 4;
+        uint32_t v = 0;
+        if (gy >= 0 && gy < L.h && gx >= 0 && gx < L.img_stride)
+            v = *reinterpret_cast<const uint32_t*>(img + (long long)gy * L.img_stride + gx);
+        *reinterpret_cast<uint32_t*>(&pix[r][c4 * 4]) = v;
+    }
+    for (int i = tid; i < FT_RH * FT_SW / 4; i += 256) reinterpret_cast<uint32_t*>(&score[0][0])[i] = 0;
+    __syncthreads();
+
+    // segment test on the score region (tile + 1 ring)
+    for (int i = tid; i < FT_RW * FT_RH; i += 256) {
+        const int r = i / FT_RW, c = i % FT_RW;
+        const int gx = x0 - 1 + c, gy = y0 - 1 + r;
+        if (gx < 3 || gy < 3 || gx >= L.w - 3 || gy >= L.h - 3) continue;
+        const uint8_t* p = &pix[r + 3][c + 3];
+        const int v = p[0], hi = v + t, lo = v - t;
+        const int p0 = p[3 * FT_PW], p8 = p[-3 * FT_PW];
+        if (!((p0 > hi) | (p0 < lo) | (p8 > hi) | (p8 < lo))) continue;
+        const int p4 = p[3], p12 = p[-3];
+        if (!((p4 > hi) | (p4 < lo) | (p12 > hi) | (p12 < lo))) continue;
+        uint32_t br = 0, dk = 0;
+#define FMASK(k, dx, dy) { const int q = p[(dy) * FT_PW + (dx)]; br |= (uint32_t)(q > hi) << k; dk |= (uint32_t)(q < lo) << k; }
+        CIRC16(FMASK)
+#undef FMASK
+        if (has_arc9(br) || has_arc9(dk)) clist[atomicAdd(&ncorner, 1)] = (uint16_t)i;
+    }
+    __syncthreads();
+
+    // corner score = max over the 16 arcs of 9 of min|v - p| (same sign), minus 1 (OpenCV cornerScore<16>)
+    const int nc = ncorner;
+    for (int j = tid; j < nc; j += 256) {
+        const int i = clist[j];
+        const int r = i / FT_RW, c = i % FT_RW;
+        const uint8_t* p = &pix[r + 3][c + 3];
+        const int v = p[0];
+        int d[16];
+#define FDIFF(k, dx, dy) d[k] = v - (int)p[(dy) * FT_PW + (dx)];
+        CIRC16(FDIFF)
+#undef FDIFF
+        int mn2[16], mx2[16], mn4[16], mx4[16];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) { mn2[k] = min(d[k], d[(k + 1) & 15]); mx2[k] = max(d[k], d[(k + 1) & 15]); }
+#pragma unroll
+        for (int k = 0; k < 16; ++k) { mn4[k] = min(mn2[k], mn2[(k + 2) & 15]); mx4[k] = max(mx2[k], mx2[(k + 2) & 15]); }
+        int best = -256;
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            const int mn9 = min(min(mn4[k], mn4[(k + 4) & 15]), d[(k + 8) & 15]);
+            const int mx9 = max(max(mx4[k], mx4[(k + 4) & 15]), d[(k + 8) & 15]);
+            best = max(best, max(mn9, -mx9));
+        }
+        score[r][c] = (uint8_t)(best - 1);
+    }
+    __syncthreads();
+
+    // 3x3 non-max suppression (strictly greater than all 8 neighbours), interior of the tile only
+    for (int j = tid; j < nc; j += 256) {
+        const int i = clist[j];
+        const int r = i / FT_RW, c = i % FT_RW;
+        if (r < 1 || r > FT_H || c < 1 || c > FT_W) continue;
+        const int s = score[r][c];
+        if (s > score[r][c - 1] && s > score[r][c + 1] && s > score[r - 1][c - 1] && s > score[r - 1][c] &&
+            s > score[r - 1][c + 1] && s > score[r + 1][c - 1] && s > score[r + 1][c] && s > score[r + 1][c + 1]) {
+            const int gx = x0 - 1 + c, gy = y0 - 1 + r;
+            surv[atomicAdd(&nsurv, 1)] = (uint32_t)gx | ((uint32_t)gy << 12) | ((uint32_t)s << 24);
+        }
+    }
+    __syncthreads();
+    const int ns = nsurv;
+    if (ns == 0) return;
+    if (tid == 0) {
+        gbase = atomicAdd(&P.counts[afv_cnt_idx(f, AFV_CNT_CAND, l)], ns);
+        if (gbase + ns > L.cand_cap) atomicOr(&P.status[f], AFV_ST_CAND_OVERFLOW);
+    }
+    __syncthreads();
+    uint32_t* out = L.cand + (long long)f * L.cand_cap;
+    for (int j = tid; j < ns; j += 256)
+        if (gbase + j < L.cand_cap) out[gbase + j] = surv[j];
+}
+
+// ------------------------------------------------------------------------------------------------------
+// K4/K5: per (frame, level): retainBest(2*q_orb) on the FAST score, Harris for the survivors,
+// retainBest(q_orb) on the Harris response.  "retainBest(n)" keeps the n best plus everything tying with
+// the n-th (OpenCV KeyPointsFilter::retainBest) -> exact 256-bin / radix selection, no sort needed.
+// ------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t f2ord(float f) {       // order-preserving float -> uint
+    uint32_t u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float ord2f(uint32_t o) {
+    return __uint_as_float((o & 0x80000000u) ? (o & 0x7fffffffu) : ~o);
+}
+
+__device__ float harris7(const uint8_t* img, int w, int h, int stride, int x0, int y0) {
+    uint8_t pt[9][9];
+    if (x0 >= 4 && y0 >= 4 && x0 + 4 < w && y0 + 4 < h) {
+#pragma unroll
+        for (int r = 0; r < 9; ++r)
+#pragma unroll
+            for (int c = 0; c < 9; ++c) pt[r][c] = img[(long long)(y0 - 4 + r) * stride + x0 - 4 + c];
+    } else {
+#pragma unroll
+        for (int r = 0; r < 9; ++r)
+#pragma unroll
+            for (int c = 0; c < 9; ++c)
+                pt[r][c] = img[(long long)refl101(y0 - 4 + r, h) * stride + refl101(x0 - 4 + c, w)];
+    }
+    int a = 0, b = 0, c2 = 0;
+#pragma unroll
+    for (int r = 1; r < 8; ++r)
+#pragma unroll
+        for (int c = 1; c < 8; ++c) {
+            const int Ix = ((int)pt[r][c + 1] - pt[r][c - 1]) * 2 + ((int)pt[r - 1][c + 1] - pt[r - 1][c - 1]) +
+                           ((int)pt[r + 1][c + 1] - pt[r + 1][c - 1]);
+            const int Iy = ((int)pt[r + 1][c] - pt[r - 1][c]) * 2 + ((int)pt[r + 1][c - 1] - pt[r - 1][c - 1]) +
+                           ((int)pt[r + 1][c + 1] - pt[r - 1][c + 1]);
+            a += Ix * Ix; b += Iy * Iy; c2 += Ix * Iy;
+        }
+    // ((float)a*b - (float)c*c - 0.04f*((float)a+b)*((float)a+b)) * scale^4, float32, one rounding per op
+    const float scale = __fdiv_rn(1.f, 7140.f);            // 1/((1<<2)*7*255.f)
+    const float s4 = __fmul_rn(__fmul_rn(__fmul_rn(scale, scale), scale), scale);
+    const float fa = (float)a, fb = (float)b, fc = (float)c2;
+    const float s = __fadd_rn(fa, fb);
+    const float t2 = __fmul_rn(__fmul_rn(0.04f, s), s);
+    const float r = __fsub_rn(__fsub_rn(__fmul_rn(fa, fb), __fmul_rn(fc, fc)), t2);
+    return __fmul_rn(r, s4);
+}
+
+__global__ void __launch_bounds__(256) k_harris_select(const __grid_constant__ AfvParams P) {
+    __shared__ int hist[256];
+    __shared__ int s_thr, s_np, s_k, s_m;
+    __shared__ uint32_t s_prefix, s_mask;
+    const int l = blockIdx.x, f = blockIdx.y, tid = threadIdx.x;
+    const AfvLevel& L = P.lv[l];
+    const int cnt = min(P.counts[afv_cnt_idx(f, AFV_CNT_CAND, l)], L.cand_cap);
+    const uint32_t* cand = L.cand + (long long)f * L.cand_cap;
+    float* resp = L.cand_resp + (long long)f * L.cand_cap;
+    uint2* det = L.det + (long long)f * L.det_cap;
+    const uint8_t* img = L.img + (long long)f * L.img_fstride;
+
+    hist[tid] = 0;
+    if (tid == 0) s_m = 0;
+    __syncthreads();
+    for (int i = tid; i < cnt; i += 256) atomicAdd(&hist[cand[i] >> 24], 1);
+    __syncthreads();
+    if (tid == 0) {
+        const int n2 = 2 * L.q_orb;
+        int thr = 0, np = cnt;
+        if (cnt > n2) {
+            if (n2 == 0) { thr = 256; np = 0; }
+            else {
+                int acc = 0, s = 255;
+                for (; s >= 0; --s) { acc += hist[s]; if (acc >= n2) break; }
+                thr = s; np = acc;
+            }
+        }
+        s_thr = thr; s_np = np;
+    }
+    __syncthreads();
+    const int thr = s_thr, np = s_np;
+    for (int i = tid; i < cnt; i += 256) {
+        const uint32_t c = cand[i];
+        if ((int)(c >> 24) >= thr) resp[i] = harris7(img, L.w, L.h, L.img_stride, c & 0xfff, (c >> 12) & 0xfff);
+    }
+    __syncthreads();
+
+    uint32_t kth = 0;                        // keep ord(resp) >= kth
+    bool none = false;
+    if (np > L.q_orb) {
+        if (L.q_orb == 0) none = true;
+        else {
+            if (tid == 0) { s_prefix = 0; s_mask = 0; s_k = L.q_orb; }
+            for (int pass = 3; pass >= 0; --pass) {
+                hist[tid] = 0;
+                __syncthreads();
+                const uint32_t prefix = s_prefix, mask = s_mask;
+                for (int i = tid; i < cnt; i += 256) {
+                    if ((int)(cand[i] >> 24) < thr) continue;
+                    const uint32_t key = f2ord(resp[i]);
+                    if ((key & mask) == prefix) atomicAdd(&hist[(key >> (8 * pass)) & 255], 1);
+                }
+                __syncthreads();
+                if (tid == 0) {
+                    int k = s_k, acc = 0, dgt = 255;
+                    for (; dgt >= 0; --dgt) { if (acc + hist[dgt] >= k) break; acc += hist[dgt]; }
+                    s_k = k - acc;
+                    s_prefix = prefix | ((uint32_t)dgt << (8 * pass));
+                    s_mask = mask | (0xffu << (8 * pass));
+                }
+                __syncthreads();
+            }
+            kth = s_prefix;
+        }
+    }
+    if (!none) {
+        for (int i = tid; i < cnt; i += 256) {
+            const uint32_t c = cand[i];
+            if ((int)(c >> 24) < thr) continue;
+            const float r = resp[i];
+            if (f2ord(r) >= kth) {
+                const int slot = atomicAdd(&s_m, 1);
+                if (slot < L.det_cap) det[slot] = make_uint2(c & 0xffffffu, __float_as_uint(r));
+            }
+        }
+    }
+    __syncthreads();
+    if (tid == 0) {
+        int m = s_m;
+        if (m > L.det_cap) { atomicOr(&P.status[f], AFV_ST_DET_OVERFLOW); m = L.det_cap; }
+        P.counts[afv_cnt_idx(f, AFV_CNT_DET, l)] = m;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// K9: DistributeOctTree, one CTA per (frame, level).
+// The reference grows a std::list of nodes: every pass divides nodes into 4 children that are pushed to
+// the FRONT of the list; when the next full pass could overshoot N it divides the biggest nodes first
+// (sort by (nKeys, node*)) and stops at N.  Here the list is an array rebuilt per pass: position of the
+// t-th child of the r-th divided node = K-1-(P_r+t) (K = children created this pass, P_r = exclusive prefix
+// in division order), undivided nodes follow in their old order.  Keys only carry their node's list
+// position.  Ties: equal-nKeys nodes are divided later-created-first (= smaller list position first);
+// the per-node max-response pick prefers the smaller raster index (the oracle's canonical order).
+// ------------------------------------------------------------------------------------------------------
+struct OctNode { short ulx, uly, urx, bry; };
+
+__device__ __forceinline__ int block_scan_excl(int* data, int n, int* warp_tot, int tid) {
+    // in-place exclusive scan of data[0..n) by 256 threads; returns the total. n <= 256*items.
+    const int items = (n + 255) / 256;
+    const int beg = tid * items, end = min(beg + items, n);
+    int sum = 0;
+    for (int i = beg; i < end; ++i) sum += data[i];
+    const int lane = tid & 31, wid = tid >> 5;
+    int incl = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+    if (lane == 31) warp_tot[wid] = incl;
+    __syncthreads();
+    int wbase = 0, total = 0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) { const int v = warp_tot[w]; if (w < wid) wbase += v; total += v; }
+    int run = wbase + incl - sum;
+    for (int i = beg; i < end; ++i) { const int v = data[i]; data[i] = run; run += v; }
+    __syncthreads();
+    return total;
+}
+
+__global__ void __launch_bounds__(256) k_octree(const __grid_constant__ AfvParams P, int mcap, int ncap) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    // keys
+    float* kx = reinterpret_cast<float*>(smem_raw);                  // [mcap] level-0 x
+    float* ky = kx + mcap;                                           // [mcap]
+    uint32_t* kresp = reinterpret_cast<uint32_t*>(ky + mcap);        // [mcap] ordered response
+    uint32_t* kras = kresp + mcap;                                   // [mcap] raster index y*w+x (level coords)
+    unsigned short* knode = reinterpret_cast<unsigned short*>(kras + mcap);   // [mcap] list position of the key's node
+    unsigned char* kquad = reinterpret_cast<unsigned char*>(knode + mcap);    // [mcap]
+    // nodes (double buffered by list position)
+    size_t off = ((size_t)mcap * (4 + 4 + 4 + 4 + 2 + 1) + 15) & ~(size_t)15;
+    OctNode* nd[2]; int* ncnt[2];
+    nd[0] = reinterpret_cast<OctNode*>(smem_raw + off); off += sizeof(OctNode) * ncap;
+    nd[1] = reinterpret_cast<OctNode*>(smem_raw + off); off += sizeof(OctNode) * ncap;
+    ncnt[0] = reinterpret_cast<int*>(smem_raw + off); off += 4 * ncap;
+    ncnt[1] = reinterpret_cast<int*>(smem_raw + off); off += 4 * ncap;
+    int* qcnt = reinterpret_cast<int*>(smem_raw + off); off += 16 * ncap;         // [ncap][4]
+    int* scanA = reinterpret_cast<int*>(smem_raw + off); off += 4 * ncap;         // children prefix (division order)
+    int* scanB = reinterpret_cast<int*>(smem_raw + off); off += 4 * ncap;         // survivor prefix (list order)
+    int* drank = reinterpret_cast<int*>(smem_raw + off); off += 4 * ncap;         // division rank of node (or -1)
+    int* order = reinterpret_cast<int*>(smem_raw + off); off += 4 * ncap;         // node at division rank r
+    int* newpos = reinterpret_cast<int*>(smem_raw + off); off += 4 * ncap;        // survivor's new position / child base
+    unsigned long long* best = reinterpret_cast<unsigned long long*>(smem_raw + ((off + 7) & ~(size_t)7));
+    __shared__ int warp_tot[8];
+    __shared__ int s_size, s_flag, s_J, s_nexp;
+
+    const int l = blockIdx.x, f = blockIdx.y, tid = threadIdx.x;
+    const AfvLevel& L = P.lv[l];
+    const int N = L.q_ext;
+    int M = min(P.counts[afv_cnt_idx(f, AFV_CNT_DET, l)], L.det_cap);
+    if (M > mcap) { if (tid == 0) atomicOr(&P.status[f], AFV_ST_OCTREE_OVERFLOW); M = mcap; }
+    const uint2* det = L.det + (long long)f * L.det_cap;
+    uint2* keep = L.keep + (long long)f * L.keep_cap;
+
+    int cur = 0;
+    // ---- roots (reference :243-283): nIni = round(w/h) boxes of width hX; empty roots erased
+    const int nIni = P.n_ini;
+    for (int i = tid; i < nIni; i += 256) {
+        OctNode n; n.ulx = (short)(int)__fmul_rn(P.hX, (float)i); n.uly = 0;
+        n.urx = (short)(int)__fmul_rn(P.hX, (float)(i + 1)); n.bry = (short)P.H;
+        nd[0][i] = n; ncnt[0][i] = 0;
+    }
+    __syncthreads();
+    for (int k = tid; k < M; k += 256) {
+        const uint2 d = det[k];
+        const int x = d.x & 0xfff, y = (d.x >> 12) & 0xfff;
+        const float fx = __fmul_rn((float)x, L.scale), fy = __fmul_rn((float)y, L.scale);
+        kx[k] = fx; ky[k] = fy;
+        kresp[k] = f2ord(__uint_as_float(d.y));
+        kras[k] = (uint32_t)(y * L.w + x);
+        const int b = min((int)__fdiv_rn(fx, P.hX), nIni - 1);
+        knode[k] = (unsigned short)b;
+        atomicAdd(&ncnt[0][b], 1);
+    }
+    __syncthreads();
+    // compact away empty roots (order preserved)
+    for (int i = tid; i < nIni; i += 256) scanB[i] = ncnt[0][i] > 0 ? 1 : 0;
+    __syncthreads();
+    int size = block_scan_excl(scanB, nIni, warp_tot, tid);
+    for (int i = tid; i < nIni; i += 256)
+        if (ncnt[0][i] > 0) { nd[1][scanB[i]] = nd[0][i]; ncnt[1][scanB[i]] = ncnt[0][i]; }
+    for (int k = tid; k < M; k += 256) knode[k] = (unsigned short)scanB[knode[k]];
+    __syncthreads();
+    cur = 1;
+
+    bool finish = false, careful = false;
+    while (!finish) {
+        const int prevSize = size;
+        OctNode* A = nd[cur]; int* Ac = ncnt[cur];
+        OctNode* Bn = nd[cur ^ 1]; int* Bc = ncnt[cur ^ 1];
+        // ---- tentative division of every expandable node: quadrant populations
+        for (int i = tid; i < size * 4; i += 256) qcnt[i] = 0;
+        __syncthreads();
+        for (int k = tid; k < M; k += 256) {
+            const int p = knode[k];
+            if (Ac[p] > 1) {
+                const OctNode n = A[p];
+                const int halfX = (int)ceilf(__fdiv_rn((float)(n.urx - n.ulx), 2.f));
+                const int halfY = (int)ceilf(__fdiv_rn((float)(n.bry - n.uly), 2.f));
+                const float sx = (float)(n.ulx + halfX), sy = (float)(n.uly + halfY);
+                const int q = (kx[k] < sx) ? ((ky[k] < sy) ? 0 : 2) : ((ky[k] < sy) ? 1 : 3);
+                kquad[k] = (unsigned char)q;
+                atomicAdd(&qcnt[p * 4 + q], 1);
+            }
+        }
+        __syncthreads();
+        // ---- division order: list order (full pass) or (nKeys desc, position asc) (careful pass)
+        if (!careful) {
+            for (int p = tid; p < size; p += 256) scanA[p] = Ac[p] > 1 ? 1 : 0;
+            __syncthreads();
+            const int ne = block_scan_excl(scanA, size, warp_tot, tid);
+            for (int p = tid; p < size; p += 256) {
+                if (Ac[p] > 1) { drank[p] = scanA[p]; order[scanA[p]] = p; } else drank[p] = -1;
+            }
+            if (tid == 0) s_nexp = ne;
+            __syncthreads();
+        } else {
+            int ne_local = 0;
+            for (int p = tid; p < size; p += 256) {
+                int r = -1;
+                if (Ac[p] > 1) {
+                    r = 0;
+                    const int c = Ac[p];
+                    for (int o = 0; o < size; ++o) {
+                        const int co = Ac[o];
+                        r += (co > 1) && (co > c || (co == c && o < p));
+                    }
+                    order[r] = p;
+                    ++ne_local;
+                }
+                drank[p] = r;
+            }
+            if (tid == 0) s_nexp = 0;
+            __syncthreads();
+            if (ne_local) atomicAdd(&s_nexp, ne_local);
+            __syncthreads();
+        }
+        const int nexp = s_nexp;
+        // children per division rank, prefix in division order
+        for (int r = tid; r < nexp; r += 256) {
+            const int p = order[r];
+            scanA[r] = (qcnt[p * 4] > 0) + (qcnt[p * 4 + 1] > 0) + (qcnt[p * 4 + 2] > 0) + (qcnt[p * 4 + 3] > 0);
+        }
+        __syncthreads();
+        // how many divisions happen (J): all in a full pass; in a careful pass stop once size >= N
+        if (tid == 0) s_J = nexp;
+        __syncthreads();
+        if (careful) {
+            // running size after r+1 divisions = size + sum_{i<=r}(c_i - 1); find the first r reaching N
+            for (int r = tid; r < nexp; r += 256) newpos[r] = scanA[r] - 1;
+            __syncthreads();
+            block_scan_excl(newpos, nexp, warp_tot, tid);
+            for (int r = tid; r < nexp; r += 256)
+                if (size + newpos[r] + scanA[r] - 1 >= N) atomicMin(&s_J, r + 1);
+            __syncthreads();
+        }
+        const int J = s_J;
+        const int K = block_scan_excl(scanA, J, warp_tot, tid);            // scanA[r] = P_r for r < J
+        // survivors (every node that is not divided this pass), prefix in list order
+        for (int p = tid; p < size; p += 256) scanB[p] = (drank[p] >= 0 && drank[p] < J) ? 0 : 1;
+        __syncthreads();
+        const int nsurv = block_scan_excl(scanB, size, warp_tot, tid);
+        const int newSize = K + nsurv;
+        if (newSize > ncap) {                 // cannot happen with ncap >= N + 4*... ; flag and stop
+            if (tid == 0) atomicOr(&P.status[f], AFV_ST_OCTREE_OVERFLOW);
+            break;
+        }
+        if (tid == 0) s_nexp = 0;
+        __syncthreads();
+        // ---- build the new list
+        int nexp_local = 0;
+        for (int p = tid; p < size; p += 256) {
+            const int r = drank[p];
+            if (r >= 0 && r < J) {
+                const OctNode n = A[p];
+                const int halfX = (int)ceilf(__fdiv_rn((float)(n.urx - n.ulx), 2.f));
+                const int halfY = (int)ceilf(__fdiv_rn((float)(n.bry - n.uly), 2.f));
+                int tnum = 0;
+                const int base = K - 1 - scanA[r];
+                newpos[p] = base;                                  // children: base - t
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int c = qcnt[p * 4 + q];
+                    if (c > 0) {
+                        OctNode ch;
+                        ch.ulx = (q & 1) ? (short)(n.ulx + halfX) : n.ulx;
+                        ch.urx = (q & 1) ? n.urx : (short)(n.ulx + halfX);
+                        ch.uly = (q & 2) ? (short)(n.uly + halfY) : n.uly;
+                        ch.bry = (q & 2) ? n.bry : (short)(n.uly + halfY);
+                        Bn[base - tnum] = ch; Bc[base - tnum] = c;
+                        qcnt[p * 4 + q] = -(base - tnum) - 1;       // remember the child's position (negative-coded)
+                        nexp_local += (c > 1);
+                        ++tnum;
+                    }
+                }
+            } else {
+                const int np = K + scanB[p];
+                newpos[p] = np;
+                Bn[np] = A[p]; Bc[np] = Ac[p];
+            }
+        }
+        if (nexp_local) atomicAdd(&s_nexp, nexp_local);
+        __syncthreads();
+        for (int k = tid; k < M; k += 256) {
+            const int p = knode[k];
+            const int r = drank[p];
+            knode[k] = (unsigned short)((r >= 0 && r < J) ? (-qcnt[p * 4 + kquad[k]] - 1) : newpos[p]);
+        }
+        __syncthreads();
+        const int nToExpand = s_nexp;
+        size = newSize;
+        cur ^= 1;
+        // ---- termination (reference :357-362 / :437-438)
+        if (size >= N || size == prevSize) finish = true;
+        else if (!careful && size + nToExpand * 3 > N) careful = true;
+        __syncthreads();
+    }
+
+    // ---- best key per node: max response, ties -> smaller raster index
+    for (int p = tid; p < size; p += 256) best[p] = 0ull;
+    __syncthreads();
+    for (int k = tid; k < M; k += 256)
+        atomicMax(&best[knode[k]], ((unsigned long long)kresp[k] << 32) | (unsigned long long)(0xffffffffu - kras[k]));
+    __syncthreads();
+    for (int p = tid; p < size; p += 256) {
+        const unsigned long long b = best[p];
+        const uint32_t ras = 0xffffffffu - (uint32_t)(b & 0xffffffffu);
+        const int x = ras % L.w, y = ras / L.w;
+        if (p < L.keep_cap) keep[p] = make_uint2((uint32_t)x | ((uint32_t)y << 12), __float_as_uint(ord2f((uint32_t)(b >> 32))));
+    }
+    if (tid == 0) {
+        if (size > L.keep_cap) { atomicOr(&P.status[f], AFV_ST_OCTREE_OVERFLOW); size = L.keep_cap; }
+        P.counts[afv_cnt_idx(f, AFV_CNT_KEEP, l)] = size;
+    }
+}
+
+size_t afv_octree_smem_bytes(int mcap, int ncap) {
+    size_t off = ((size_t)mcap * (4 + 4 + 4 + 4 + 2 + 1) + 15) & ~(size_t)15;
+    off += sizeof(OctNode) * ncap * 2 + 4 * (size_t)ncap * 2 + 16 * (size_t)ncap + 4 * (size_t)ncap * 5;
+    off = (off + 7) & ~(size_t)7;
+    off += 8 * (size_t)ncap;
+    return off;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// K7: 7x7 sigma=2 blur, float separable, arithmetic pinned to OpenCV's FMA-contracted filter engine:
+//   row:    s = k0*p0; s = fma(kj, pj, s)                     column: s = k3*r0; s = fma(k3+j, r+j + r-j, s)
+// Tile 128x16 outputs, 256 threads; each thread finishes 8 output pixels (2 x uchar4 stores).
+// ------------------------------------------------------------------------------------------------------
+#define BT_W 128
+#define BT_H 16
+__constant__ float c_g7[7] = {0x1.1f5f62p-4f, 0x1.0c70fcp-3f, 0x1.869472p-3f, 0x1.ba95cp-3f,
+                              0x1.869472p-3f, 0x1.0c70fcp-3f, 0x1.1f5f62p-4f};
+
+__global__ void __launch_bounds__(256) k_blur(const __grid_constant__ AfvParams P, const __grid_constant__ FastTiles T) {
+    __shared__ uint8_t in[BT_H + 6][BT_W + 8];
+    __shared__ float mid[BT_H + 6][BT_W];
+    int l = 0;
+    while (l + 1 < P.nlevels && (int)blockIdx.x >= T.start[l + 1]) ++l;
+    const AfvLevel& L = P.lv[l];
+    const int tile = blockIdx.x - T.start[l];
+    const int tx = tile % T.tiles_x[l], ty = tile / T.tiles_x[l];
+    const int f = blockIdx.y, tid = threadIdx.x;
+    const int x0 = tx * BT_W, y0 = ty * BT_H;
+    const uint8_t* img = L.img + (long long)f * L.img_fstride;
+    for (int i = tid; i < (BT_H + 6) * (BT_W + 6); i += 256) {
+        const int r = i / (BT_W + 6), c = i % (BT_W + 6);
+        in[r][c] = img[(long long)refl101(y0 - 3 + r, L.h) * L.img_stride + refl101(x0 - 3 + c, L.w)];
+    }
+    __syncthreads();
+    for (int i = tid; i < (BT_H + 6) * BT_W; i += 256) {
+        const int r = i / BT_W, c = i % BT_W;
+        float s = __fmul_rn(c_g7[0], (float)in[r][c]);
+#pragma unroll
+        for (int k = 1; k < 7; ++k) s = __fmaf_rn(c_g7[k], (float)in[r][c + k], s);
+        mid[r][c] = s;
+    }
+    __syncthreads();
+    uint8_t* out = L.blur + (long long)f * L.fstride;
+    for (int i = tid; i < BT_H * (BT_W / 4); i += 256) {
+        const int r = i / (BT_W / 4), c4 = (i % (BT_W / 4)) * 4;
+        const int gy = y0 + r, gx = x0 + c4;
+        if (gy >= L.h || gx >= L.w) continue;
+        uint32_t pk = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int c = c4 + k;
+            float s = __fmul_rn(c_g7[3], mid[r + 3][c]);
+#pragma unroll
+            for (int j = 1; j <= 3; ++j) s = __fmaf_rn(c_g7[3 + j], __fadd_rn(mid[r + 3 + j][c], mid[r + 3 - j][c]), s);
+            int v = __float2int_rn(s);
+            v = min(max(v, 0), 255);
+            pk |= (uint32_t)v << (8 * k);
+        }
+        *reinterpret_cast<uint32_t*>(out + (long long)gy * L.stride + gx) = pk;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// K6/K8/K10: one warp per kept keypoint: IC angle (31 rows of the radius-15 disc, lane = column), steered
+// BRIEF (lane = descriptor byte), and the merged cv::KeyPoint / descriptor / size rows (levels ascending).
+// ------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float fast_atan2_deg(float y, float x) {
+    const float p1 = 0x1.ca44dep+5f, p3 = -0x1.2aaddcp+4f, p5 = 0x1.1d3f7ep+3f, p7 = -0x1.4515b2p+1f;
+    const float eps = 0x1p-52f;                                   // (float)DBL_EPSILON
+    const float ax = fabsf(x), ay = fabsf(y);
+    float a, c, c2;
+    if (ax >= ay) {
+        c = __fdiv_rn(ay, __fadd_rn(ax, eps));
+        c2 = __fmul_rn(c, c);
+        a = __fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(p7, c2), p5), c2), p3), c2), p1), c);
+    } else {
+        c = __fdiv_rn(ax, __fadd_rn(ay, eps));
+        c2 = __fmul_rn(c, c);
+        a = __fsub_rn(90.f, __fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(p7, c2), p5), c2), p3), c2), p1), c));
+    }
+    if (x < 0) a = __fsub_rn(180.f, a);
+    if (y < 0) a = __fsub_rn(360.f, a);
+    return a;
+}
+
+__global__ void __launch_bounds__(256) k_describe(const __grid_constant__ AfvParams P, afv_keypoint* __restrict__ kps,
+                                                  uint8_t* __restrict__ desc, float* __restrict__ kpsize,
+                                                  int* __restrict__ n_out) {
+    __shared__ int8_t pat[1024];
+    __shared__ int lvl_start[AFV_MAX_LEVELS + 1];
+    const int f = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int i = tid; i < 1024; i += 256) pat[i] = c_pattern[i];
+    if (tid == 0) {
+        int acc = 0;
+        for (int l = 0; l < P.nlevels; ++l) {
+            lvl_start[l] = acc;
+            acc += min(P.counts[afv_cnt_idx(f, AFV_CNT_KEEP, l)], P.lv[l].keep_cap);
+        }
+        lvl_start[P.nlevels] = acc;
+        if (blockIdx.x == 0) {
+            if (acc > P.out_cap) atomicOr(&P.status[f], AFV_ST_OUT_OVERFLOW);
+            n_out[f] = min(acc, P.out_cap);
+        }
+    }
+    __syncthreads();
+    const int total = min(lvl_start[P.nlevels], P.out_cap);
+    const int i = blockIdx.x * 8 + warp;
+    if (i >= total) return;
+    int l = 0;
+    while (i >= lvl_start[l + 1]) ++l;
+    const AfvLevel& L = P.lv[l];
+    const uint2 kd = (L.keep + (long long)f * L.keep_cap)[i - lvl_start[l]];
+    const int x0 = kd.x & 0xfff, y0 = (kd.x >> 12) & 0xfff;
+    const uint8_t* img = L.img + (long long)f * L.img_fstride;
+    const uint8_t* blr = L.blur + (long long)f * L.fstride;
+
+    // intensity-centroid moments over the radius-15 disc (cv::ORB ICAngles); lane = u + 15
+    int m10 = 0, m01 = 0;
+    const int u = lane - 15;
+    const bool inner = (x0 >= 15 && y0 >= 15 && x0 + 15 < L.w && y0 + 15 < L.h);
+    for (int v = -15; v <= 15; ++v) {
+        const int dmax = c_umax[v < 0 ? -v : v];
+        if (u >= -dmax && u <= dmax) {
+            const int xx = inner ? x0 + u : refl101(x0 + u, L.w);
+            const int yy = inner ? y0 + v : refl101(y0 + v, L.h);
+            const int val = img[(long long)yy * L.img_stride + xx];
+            m10 += u * val; m01 += v * val;
+        }
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) { m10 += __shfl_xor_sync(0xffffffffu, m10, o); m01 += __shfl_xor_sync(0xffffffffu, m01, o); }
+    const float angle = fast_atan2_deg((float)m01, (float)m10);
+
+    const float fx = __fmul_rn((float)x0, L.scale), fy = __fmul_rn((float)y0, L.scale);
+    // descriptor centre as cv::ORB::compute recovers it from the scaled keypoint
+    const int cx = __float2int_rn(__fmul_rn(fx, L.inv_scale)), cy = __float2int_rn(__fmul_rn(fy, L.inv_scale));
+    const float ang = __fmul_rn(angle, 0x1.1df46ap-6f);            // (float)(CV_PI/180.f)
+    const float a = (float)cos((double)ang), b = (float)sin((double)ang);
+    const bool dinner = (cx >= 19 && cy >= 19 && cx + 19 < L.w && cy + 19 < L.h);
+    const int8_t* pp = pat + lane * 32;
+    uint32_t byte = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        int tv[2];
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const float px = (float)pp[4 * k + 2 * j], py = (float)pp[4 * k + 2 * j + 1];
+            const int ix = cx + __float2int_rn(__fsub_rn(__fmul_rn(px, a), __fmul_rn(py, b)));
+            const int iy = cy + __float2int_rn(__fadd_rn(__fmul_rn(px, b), __fmul_rn(py, a)));
+            if (dinner || (ix >= 0 && ix < L.w && iy >= 0 && iy < L.h)) tv[j] = blr[(long long)iy * L.stride + ix];
+            else tv[j] = img[(long long)refl101(iy, L.h) * L.img_stride + refl101(ix, L.w)];
+        }
+        byte |= (uint32_t)(tv[0] < tv[1]) << k;
+    }
+    const long long o = (long long)f * P.out_cap + i;
+    desc[o * 32 + lane] = (uint8_t)byte;
+    if (lane == 0) {
+        afv_keypoint kp;
+        kp.x = fx; kp.y = fy; kp.size = L.kp_size; kp.angle = angle;
+        kp.response = __uint_as_float(kd.y); kp.octave = l; kp.class_id = -1;
+        kps[o] = kp;
+        if (kpsize) kpsize[o] = L.size_norm;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// host-side launch sequence for one batch (all on one stream, no host synchronisation inside)
+// ------------------------------------------------------------------------------------------------------
+static int g_oct_mcap = 0, g_oct_ncap = 0;
+
+int afv_orb_configure(int max_det_cap, int max_keep_cap) {
+    g_oct_mcap = max_det_cap;
+    g_oct_ncap = max_keep_cap + 8;
+    size_t smem = afv_octree_smem_bytes(g_oct_mcap, g_oct_ncap);
+    if (smem > 227 * 1024) { afv_set_error("octree shared memory %zu B exceeds 227 KB (nfeatures too large)", smem); return AFV_ERR_INVALID; }
+    AFV_CUDA_CHECK(cudaFuncSetAttribute(k_octree, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    return AFV_OK;
+}
+
+void afv_launch_extract(const AfvParams& P, afv_keypoint* d_kps, uint8_t* d_desc, float* d_kpsize,
+                        int* d_n_out, cudaStream_t st) {
+    FastTiles T;
+    int acc = 0;
+    for (int l = 0; l < P.nlevels; ++l) {
+        T.start[l] = acc;
+        T.tiles_x[l] = (P.lv[l].w + FT_W - 1) / FT_W;
+        acc += T.tiles_x[l] * ((P.lv[l].h + FT_H - 1) / FT_H);
+    }
+    T.start[P.nlevels] = acc;
+    cudaMemsetAsync(P.counts, 0, sizeof(int) * 4 * AFV_MAX_LEVELS * P.B, st);
+    cudaMemsetAsync(P.status, 0, sizeof(int) * P.B, st);
+    for (int l = 1; l < P.nlevels; ++l) {
+        dim3 g((P.lv[l].w + 127) / 128, (P.lv[l].h + 7) / 8, P.B);
+        k_resize<<<g, dim3(32, 8), 0, st>>>(P, l);
+        ++g_afv_launches;
+    }
+    k_fast<<<dim3(acc, P.B), 256, 0, st>>>(P, T); ++g_afv_launches;
+    k_harris_select<<<dim3(P.nlevels, P.B), 256, 0, st>>>(P); ++g_afv_launches;
+    k_octree<<<dim3(P.nlevels, P.B), 256, afv_octree_smem_bytes(g_oct_mcap, g_oct_ncap), st>>>(P, g_oct_mcap, g_oct_ncap);
+    ++g_afv_launches;
+    k_blur<<<dim3(acc, P.B), 256, 0, st>>>(P, T); ++g_afv_launches;
+    k_describe<<<dim3((P.out_cap + 7) / 8, P.B), 256, 0, st>>>(P, d_kps, d_desc, d_kpsize, d_n_out);
+    ++g_afv_launches;
+}

@@ -1,0 +1,104 @@
+"""FeatureMatcher mirror (reference include/FeatureMatcher.h:36-118) above the C ABI, on device arrays.
+
+The reference methods take Frame / KeyFrame / MapPoint graphs; here the same searches run on the flat
+outputs of FeatureExtractor.extract_batch_device (torch cuda tensors).  Thresholds follow
+FeatureMatcher::setDescriptorDistanceThresholds (src/FeatureMatcher.cc:1533-1545): TH_LOW = TH_HIGH =
+FeatureMatcher.matchingTh of settings/<feat>_settings.yaml.
+"""
+import ctypes as C
+
+
+def _afv():
+    from . import lib, _check, _vp, _stream_ptr
+    return lib(), _check, _vp, _stream_ptr
+
+
+class FeatureMatcher:
+    HISTO_LENGTH = 30                       # src/FeatureMatcher.cc:64
+
+    def __init__(self, nnratio=0.6, check_ori=True, desc_type=0, th_low=75.0):
+        self.nnratio = float(nnratio)
+        self.check_ori = bool(check_ori)
+        self.desc_type = int(desc_type)
+        self.th_low = float(th_low)         # TH_LOW == TH_HIGH == reloc thresholds
+
+    # -- SearchForInitialization (src/FeatureMatcher.cc:399-557), batched over frame pairs ------------
+    def search_for_initialization(self, kps, desc, kpsize, n, pair_a, pair_b, prev_matched, bounds,
+                                  max_kpt_size, window=100, matches12=None, nmatches=None, stream=None):
+        """kps [B,cap,7] f32, desc [B,cap,D] u8, kpsize [B,cap] f32, n [B] i32, pair_a/pair_b [P] i32,
+        prev_matched [P,cap,2] f32 (in/out).  Returns (matches12 [P,cap] i32, nmatches [P] i32)."""
+        import torch
+        lib, _check, _vp, _sp = _afv()
+        B, cap = kps.shape[0], kps.shape[1]
+        P = pair_a.shape[0]
+        if matches12 is None:
+            matches12 = torch.empty((P, cap), dtype=torch.int32, device=kps.device)
+        if nmatches is None:
+            nmatches = torch.empty((P,), dtype=torch.int32, device=kps.device)
+        minx, miny, maxx, maxy = bounds
+        _check(lib.afv_search_for_initialization(
+            self.desc_type, _vp(kps), _vp(desc), _vp(kpsize), _vp(n), B, cap, _vp(pair_a), _vp(pair_b), P,
+            C.c_float(minx), C.c_float(miny), C.c_float(maxx), C.c_float(maxy), C.c_float(max_kpt_size),
+            _vp(prev_matched), int(window), C.c_float(self.th_low), C.c_float(self.nnratio), int(self.check_ori),
+            _vp(matches12), _vp(nmatches), _sp(stream)))
+        return matches12, nmatches
+
+    # -- Frame grid + stateless window search (core of SearchByProjection) ------------------------------
+    @staticmethod
+    def grid_build(kps, n, bounds, stream=None):
+        import torch
+        lib, _check, _vp, _sp = _afv()
+        B, cap = kps.shape[0], kps.shape[1]
+        cs = torch.empty((B, 64 * 48 + 1), dtype=torch.int32, device=kps.device)
+        ci = torch.empty((B, cap), dtype=torch.int32, device=kps.device)
+        minx, miny, maxx, maxy = bounds
+        _check(lib.afv_grid_build(_vp(kps), _vp(n), B, cap, C.c_float(minx), C.c_float(miny), C.c_float(maxx),
+                                  C.c_float(maxy), _vp(cs), _vp(ci), _sp(stream)))
+        return cs, ci
+
+    def match_window(self, q, qxy, qr, qmin, qmax, tk, td, tsize, nt, cell_start, cell_items, bounds, stream=None):
+        import torch
+        lib, _check, _vp, _sp = _afv()
+        nq = q.shape[0]
+        dev = q.device
+        best = torch.empty(nq, dtype=torch.int32, device=dev)
+        bd = torch.empty(nq, dtype=torch.float32, device=dev); sd = torch.empty_like(bd)
+        bs = torch.empty_like(bd); ss = torch.empty_like(bd)
+        minx, miny, maxx, maxy = bounds
+        _check(lib.afv_match_window(self.desc_type, _vp(q), _vp(qxy), _vp(qr), _vp(qmin), _vp(qmax), nq,
+                                    _vp(tk), _vp(td), _vp(tsize), int(nt), _vp(cell_start), _vp(cell_items),
+                                    C.c_float(minx), C.c_float(miny), C.c_float(maxx), C.c_float(maxy),
+                                    _vp(best), _vp(bd), _vp(sd), _vp(bs), _vp(ss), _sp(stream)))
+        return best, bd, sd, bs, ss
+
+    def match_bruteforce(self, q, t, stream=None):
+        import torch
+        lib, _check, _vp, _sp = _afv()
+        nq, nt = q.shape[0], t.shape[0]
+        best = torch.empty(nq, dtype=torch.int32, device=q.device)
+        bd = torch.empty(nq, dtype=torch.float32, device=q.device); sd = torch.empty_like(bd)
+        _check(lib.afv_match_bruteforce(self.desc_type, _vp(q), nq, _vp(t), nt, _vp(best), _vp(bd), _vp(sd), _sp(stream)))
+        return best, bd, sd
+
+    # -- SearchByBoW(KF, F) (src/FeatureMatcher.cc:186-283) ---------------------------------------------
+    def search_by_bow(self, dkf, kkf, kf_segs, df, kf_f, f_segs, stream=None):
+        import torch
+        lib, _check, _vp, _sp = _afv()
+        nf = df.shape[0]
+        match_f = torch.empty(max(nf, 1), dtype=torch.int32, device=df.device)
+        nm = torch.zeros(1, dtype=torch.int32, device=df.device)
+        _check(lib.afv_search_by_bow(self.desc_type, _vp(dkf), _vp(kkf), _vp(kf_segs[0]), _vp(kf_segs[1]), _vp(kf_segs[2]),
+                                     kf_segs[0].shape[0], _vp(df), _vp(kf_f), nf, _vp(f_segs[0]), _vp(f_segs[1]),
+                                     _vp(f_segs[2]), f_segs[0].shape[0], C.c_float(self.th_low), C.c_float(self.nnratio),
+                                     int(self.check_ori), _vp(match_f), _vp(nm), _sp(stream)))
+        return match_f[:nf], nm
+
+    # -- static DescriptorDistance (src/FeatureMatcher.cc:1508-1531) -------------------------------------
+    @staticmethod
+    def descriptor_distance(desc_type, a, b, stream=None):
+        import torch
+        lib, _check, _vp, _sp = _afv()
+        n = a.shape[0]
+        out = torch.empty(n, dtype=torch.float32, device=a.device)
+        _check(lib.afv_descriptor_distance(int(desc_type), _vp(a), _vp(b), n, _vp(out), _sp(stream)))
+        return out

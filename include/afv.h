@@ -1,0 +1,148 @@
+/*
+ * afv.h -- C ABI of the B200-native feature front end (drop-in boundary for AnyFeature-VSLAM's
+ * FeatureExtractor / FeatureMatcher hot path).
+ *
+ * The reference has no FFI: its boundary is two C++ types.  Each entry point below names the reference
+ * interface it replaces (file:line relative to the reference tree); the C++ mirror classes that keep the
+ * reference's virtual signatures and call these functions are in anyfeature-vslam_b200/host/, and the
+ * binding a reference maintainer would add is shown in INTEGRATION.md.
+ *
+ * Conventions: plain pointers and sizes, no exceptions across the ABI, 0 = success / negative = error
+ * (text via afv_last_error()), caller-owned output buffers with explicit capacity.  All compute runs in
+ * hand-written sm_100a CUDA kernels; there is NO CPU fallback: without a usable CUDA device every entry
+ * point fails with AFV_ERR_NO_DEVICE.
+ */
+#ifndef AFV_H
+#define AFV_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AFV_OK               0
+#define AFV_ERR_INVALID     -1   /* bad argument */
+#define AFV_ERR_NO_DEVICE   -2   /* CUDA device / driver unavailable: the product path has no CPU fallback */
+#define AFV_ERR_CUDA        -3   /* CUDA runtime error (see afv_last_error) */
+#define AFV_ERR_CAPACITY    -4   /* an internal or caller buffer capacity was exceeded (frame reported in text) */
+#define AFV_ERR_UNSUPPORTED -5   /* feature id not built in this round */
+
+/* feature / descriptor ids == reference include/Types.h:11-45 and get_feature_id (:102-124) */
+#define AFV_FEAT_ORB32      0
+#define AFV_FEAT_AKAZE61    1
+#define AFV_FEAT_BRISK48    2
+#define AFV_FEAT_SIFT128    5
+
+/* == cv::KeyPoint POD (28 bytes, same field order): what the reference's operator() fills
+ * (include/FeatureExtractor.h:84-93). */
+typedef struct { float x, y, size, angle, response; int octave, class_id; } afv_keypoint;
+
+typedef struct afv_extractor afv_extractor;
+
+/* ---- FeatureExtractor (reference include/FeatureExtractor.h:68-161, src/FeatureExtractor.cpp:74-129,
+ *      src/Feature_orb32.cpp:11-65; factory src/Tracking.cc:1505-1553) ------------------------------------ */
+
+/* Replaces the FeatureExtractor_<feat> constructor + FeatureExtractorSettings (nfeatures, numOctaves,
+ * scaleFactor, detectionTh from settings/<feat>_settings.yaml).  max_batch/max_w/max_h size the device
+ * arenas once (no allocation on the per-frame path). */
+int  afv_extractor_create(afv_extractor** out, int feature_id, int nfeatures, int n_octaves,
+                          float scale_factor, float detect_th, int device,
+                          int max_batch, int max_w, int max_h);
+void afv_extractor_destroy(afv_extractor* ex);
+
+/* Smallest `cap` the per-frame output buffers must have: nfeatures + 3*n_octaves (DistributeOctTree can
+ * overshoot each level's quota by up to 3, src/ORBextractor.cc:357-360). */
+int  afv_extractor_output_cap(const afv_extractor* ex);
+/* GetScaleFactors / mnFeaturesPerLevel (include/FeatureExtractor.h:95-99, src/FeatureExtractor.cpp:97-108). */
+int  afv_extractor_levels(const afv_extractor* ex, float* scale_factors, int* features_per_level);
+
+/* FeatureExtractor::operator()(Image, keypoints, descriptors, ..., size) for ONE frame, host buffers
+ * (src/FeatureExtractor.cpp:111-129).  gray: 8-bit single channel, `stride` bytes per row.
+ * kps[cap], desc[cap*D] (D = 32 for orb32), kpsize[cap] (computeSize, :132-142; may be NULL). */
+int  afv_extract(afv_extractor* ex, const uint8_t* gray, int w, int h, int stride,
+                 afv_keypoint* kps, void* desc, float* kpsize, int cap, int* n_out);
+
+/* Batched form (additive extension: the reference handles one frame per call).  B frames, frame b starts
+ * at gray + b*frame_stride.  Outputs are B x cap.  Host buffers; H2D/D2H copies are inside the call. */
+int  afv_extract_batch(afv_extractor* ex, const uint8_t* gray, int B, int w, int h, int stride,
+                       long frame_stride, afv_keypoint* kps, void* desc, float* kpsize, int cap, int* n_out);
+
+/* Same with DEVICE buffers, asynchronous on `cuda_stream` (a cudaStream_t; NULL = the extractor's own
+ * stream, synchronised before return).  Capacity overflows are reported by afv_extractor_status(). */
+int  afv_extract_batch_device(afv_extractor* ex, const uint8_t* d_gray, int B, int w, int h, int stride,
+                              long frame_stride, afv_keypoint* d_kps, void* d_desc, float* d_kpsize,
+                              int cap, int* d_n_out, void* cuda_stream);
+/* Synchronises the last device batch and returns AFV_OK or AFV_ERR_CAPACITY. */
+int  afv_extractor_status(afv_extractor* ex);
+
+/* Stage taps for parity tests (device -> host copy of an intermediate of the LAST batch):
+ *   what = 0: pyramid level image (w_l*h_l bytes, tight)      1: blurred level image
+ *          2: FAST+NMS candidates (uint32 x | y<<12 | score<<24, unordered)
+ *          3: cv::ORB::detect-equivalent list after both retainBest culls (uint32 packed xy, float response
+ *             pairs: 8 bytes each, unordered)
+ *          4: octree-kept list in node-list order (8 bytes each as in 3)                                   */
+int  afv_debug_read(afv_extractor* ex, int what, int frame, int level, void* out, long cap_bytes, long* n_bytes);
+
+/* ---- FeatureMatcher (reference include/FeatureMatcher.h:36-118, src/FeatureMatcher.cc) ------------------
+ * The reference methods take Frame/KeyFrame/MapPoint graphs; the ABI sits one step inside, on arrays:
+ * (query descriptors, window / bucket / all candidates, train descriptors) -> best index, best and second
+ * distance.  desc_type uses the ids above; distances are returned as float like Descriptor_Distance_Type
+ * (include/Types.h:127).  All pointers are DEVICE pointers; calls are asynchronous on `cuda_stream`.       */
+
+/* Train-frame side of Frame::AssignFeaturesToGrid (src/Frame.cc:225-240, 64x48 cells): builds the CSR grid
+ * cell_start[64*48+1], cell_items[nt] for each of B frames (frame b at offset b*cap). n[b] keypoints each. */
+int  afv_grid_build(const afv_keypoint* d_kps, const int* d_n, int B, int cap,
+                    float min_x, float min_y, float max_x, float max_y,
+                    int* d_cell_start, int* d_cell_items, void* cuda_stream);
+
+/* Data-parallel core of SearchByProjection (src/FeatureMatcher.cc:73-154) / GetFeaturesInArea
+ * (src/Frame.cc:333-382): for each query (descriptor, window centre qxy, radius, size gate) the best and
+ * second-best train keypoint inside the window, first-minimum-wins in (cell x, cell y, index) order.      */
+int  afv_match_window(int desc_type, const void* d_q, const float* d_qxy, const float* d_qr,
+                      const float* d_qmin_size, const float* d_qmax_size, int nq,
+                      const afv_keypoint* d_tk, const void* d_td, const float* d_tsize, int nt,
+                      const int* d_cell_start, const int* d_cell_items,
+                      float min_x, float min_y, float max_x, float max_y,
+                      int* d_best, float* d_bestd, float* d_secondd, float* d_best_size, float* d_second_size,
+                      void* cuda_stream);
+
+/* FeatureMatcher::SearchForInitialization (src/FeatureMatcher.cc:399-557), batched over P independent
+ * frame pairs: pair p matches frame a[p] (queries, octave-0 only) against frame b[p] (train) of a B x cap
+ * extraction result.  Reproduces the sequential "already matched with a smaller distance" rule (:511-512),
+ * match stealing (:530-537), the rotation histogram (:1579-1668) and the vbPrevMatched update (:552-554).
+ * d_prev_matched: P x cap x 2 floats in/out; d_matches12: P x cap ints out; d_nmatches: P ints out.        */
+int  afv_search_for_initialization(int desc_type, const afv_keypoint* d_kps, const void* d_desc,
+                                   const float* d_kpsize, const int* d_n, int B, int cap,
+                                   const int* d_pair_a, const int* d_pair_b, int P,
+                                   float min_x, float min_y, float max_x, float max_y, float max_kpt_size,
+                                   float* d_prev_matched, int window, float th_low, float nnratio,
+                                   int check_orientation, int* d_matches12, int* d_nmatches,
+                                   void* cuda_stream);
+
+/* Brute-force N x M best / second (upper bound of every matcher; also MapPoint::ComputeDistinctiveDescriptors'
+ * distance matrix, src/MapPoint.cc:312-324). */
+int  afv_match_bruteforce(int desc_type, const void* d_q, int nq, const void* d_t, int nt,
+                          int* d_best, float* d_bestd, float* d_secondd, void* cuda_stream);
+
+/* SearchByBoW(KF,F) (src/FeatureMatcher.cc:186-283) on FeatureVector segments (sorted node ids + CSR). */
+int  afv_search_by_bow(int desc_type,
+                       const void* d_dkf, const afv_keypoint* d_kkf,
+                       const int* d_kf_node, const int* d_kf_start, const int* d_kf_idx, int kf_nodes,
+                       const void* d_df, const afv_keypoint* d_kf_f, int nf,
+                       const int* d_f_node, const int* d_f_start, const int* d_f_idx, int f_nodes,
+                       float th_low, float nnratio, int check_orientation,
+                       int* d_match_f, int* d_nmatches, void* cuda_stream);
+
+/* FeatureMatcher::DescriptorDistance (src/FeatureMatcher.cc:1508-1531) for n pairs (a[i], b[i]). */
+int  afv_descriptor_distance(int desc_type, const void* d_a, const void* d_b, int n, float* d_out,
+                             void* cuda_stream);
+
+/* ---- misc ------------------------------------------------------------------------------------------------ */
+const char* afv_last_error(void);
+/* number of kernels this library has launched since load (bench.py's gpu_launches) */
+long long   afv_kernel_launches(void);
+const char* afv_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AFV_H */
