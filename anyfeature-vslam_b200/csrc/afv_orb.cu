@@ -136,22 +136,24 @@ __global__ void __launch_bounds__(256) k_fast(const __grid_constant__ AfvParams 
         const int r = i / FT_RW, c = i % FT_RW;
         const uint8_t* p = &pix[r + 3][c + 3];
         const int v = p[0];
-        int d[16];
-#define FDIFF(k, dx, dy) d[k] = v - (int)p[(dy) * FT_PW + (dx)];
+        // d[k] = v - p[k] in [-255,255]: packed as (d, -d) in the two signed 16-bit halves so one __vmins2 chain
+        // gives both min(d) (darker arcs) and min(-d) (brighter arcs); sliding minimum over 9 by doubling.
+        // NB: the scalar form max(min9(d), -max9(d)) is MISCOMPILED by nvcc 12.9 / ptxas for sm_100a (3-input
+        // VIMNMX3 with a negated operand; repro in tools/dbg/minmax_dbg.cu) - keep this formulation.
+        uint32_t e[16];
+#define FDIFF(k, dx, dy) { const int dv = v - (int)p[(dy) * FT_PW + (dx)]; e[k] = ((uint32_t)dv & 0xffffu) | ((uint32_t)(-dv) << 16); }
         CIRC16(FDIFF)
 #undef FDIFF
-        int mn2[16], mx2[16], mn4[16], mx4[16];
+        uint32_t m2[16], m4[16];
 #pragma unroll
-        for (int k = 0; k < 16; ++k) { mn2[k] = min(d[k], d[(k + 1) & 15]); mx2[k] = max(d[k], d[(k + 1) & 15]); }
+        for (int k = 0; k < 16; ++k) m2[k] = __vmins2(e[k], e[(k + 1) & 15]);
 #pragma unroll
-        for (int k = 0; k < 16; ++k) { mn4[k] = min(mn2[k], mn2[(k + 2) & 15]); mx4[k] = max(mx2[k], mx2[(k + 2) & 15]); }
-        int best = -256;
+        for (int k = 0; k < 16; ++k) m4[k] = __vmins2(m2[k], m2[(k + 2) & 15]);
+        uint32_t acc = 0x80008000u;
 #pragma unroll
-        for (int k = 0; k < 16; ++k) {
-            const int mn9 = min(min(mn4[k], mn4[(k + 4) & 15]), d[(k + 8) & 15]);
-            const int mx9 = max(max(mx4[k], mx4[(k + 4) & 15]), d[(k + 8) & 15]);
-            best = max(best, max(mn9, -mx9));
-        }
+        for (int k = 0; k < 16; ++k) acc = __vmaxs2(acc, __vmins2(__vmins2(m4[k], m4[(k + 4) & 15]), e[(k + 8) & 15]));
+        const int bd = (int)(short)(acc & 0xffffu), bb = (int)(short)(acc >> 16);
+        const int best = bd > bb ? bd : bb;
         score[r][c] = (uint8_t)(best - 1);
     }
     __syncthreads();
