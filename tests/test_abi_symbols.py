@@ -1,0 +1,46 @@
+"""The C-ABI library builds, loads and exports every entry point include/afv.h declares (no GPU needed),
+and fails loudly (no CPU fallback) when no CUDA device is usable."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared():
+    txt = open(os.path.join(ROOT, "include", "afv.h")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(afv_[a-z_0-9]+)\s*\(", txt)))
+
+
+def test_library_exports_every_declared_symbol():
+    import __graft_entry__ as g
+    g.build()
+    pkg = g._load_pkg()
+    lib = pkg.lib()
+    names = _declared()
+    assert len(names) >= 17
+    for n in names:
+        assert hasattr(lib, n), "missing export %s" % n
+    assert b"sm_100a" in lib.afv_version()
+
+
+def test_no_cpu_fallback_without_device():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    import __graft_entry__ as g
+    pkg = g._load_pkg()
+    with pytest.raises(pkg.AfvError) as e:
+        pkg.FeatureExtractor("orb32")
+    assert "no CPU fallback" in str(e.value)
+
+
+def test_unsupported_feature_is_an_error_not_a_fallback():
+    import __graft_entry__ as g
+    pkg = g._load_pkg()
+    h = C.c_void_p()
+    rc = pkg.lib().afv_extractor_create(C.byref(h), 5, 1000, 8, C.c_float(2.0), C.c_float(10.0), 0, 1, 640, 480)
+    assert rc in (-5, -2) and not h.value

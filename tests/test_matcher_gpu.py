@@ -1,0 +1,158 @@
+"""Parity of the CUDA FeatureMatcher kernels (through the C ABI) against the CPU oracle: bit-exact match
+indices / Hamming distances; L2^2 (sift128 layout) within 1e-5 relative."""
+import numpy as np
+import pytest
+
+from oracle import pyoracle as po
+
+pytestmark = pytest.mark.gpu
+BOUNDS = (0.0, 0.0, 640.0, 480.0)
+MAXSZ = float(np.float32(1.2) ** 7)
+
+
+@pytest.fixture(scope="module")
+def extracted(pkg, synth):
+    import torch
+    frames = np.concatenate([synth.stream_frames(640, 480, s, 4)[0] for s in (0, 5)], axis=0)
+    ex = pkg.FeatureExtractor("orb32", nfeatures=1000, max_batch=len(frames), max_w=640, max_h=480)
+    out = ex.alloc_device_outputs(len(frames))
+    ex.extract_batch_device(torch.from_numpy(frames).cuda(), out)
+    torch.cuda.synchronize()
+    ex.status()
+    n = out[3].cpu().numpy()
+    host = []
+    for f in range(len(frames)):
+        m = int(n[f])
+        host.append((pkg.kps_from_device(out[0][f], m), out[1][f, :m].cpu().numpy(), out[2][f, :m].cpu().numpy()))
+    yield out, host, ex.cap
+    ex.close()
+
+
+@pytest.mark.parametrize("nnratio,check_ori", [(0.9, True), (0.6, False)])
+def test_search_for_initialization_batched(pkg, extracted, nnratio, check_ori):
+    import torch
+    out, host, cap = extracted
+    pairs = [(0, 1), (1, 2), (2, 3), (4, 5), (5, 6), (6, 7), (3, 0), (0, 0)]
+    pa = torch.tensor([p[0] for p in pairs], dtype=torch.int32, device="cuda")
+    pb = torch.tensor([p[1] for p in pairs], dtype=torch.int32, device="cuda")
+    pm = torch.zeros((len(pairs), cap, 2), dtype=torch.float32, device="cuda")
+    for i, (a, b) in enumerate(pairs):
+        pm[i] = out[0][a, :, :2]
+    fm = pkg.FeatureMatcher(nnratio=nnratio, check_ori=check_ori, desc_type=0, th_low=75.0)
+    m12, nm = fm.search_for_initialization(out[0], out[1], out[2], out[3], pa, pb, pm, BOUNDS, MAXSZ, window=100)
+    torch.cuda.synchronize()
+    m12 = m12.cpu().numpy(); nm = nm.cpu().numpy(); pmh = pm.cpu().numpy()
+    for i, (a, b) in enumerate(pairs):
+        k1, d1, s1 = host[a]; k2, d2, s2 = host[b]
+        prev = np.stack([k1["x"], k1["y"]], axis=1)
+        rn, rm, rpm = po.search_for_initialization(0, k1, d1, k2, d2, s2, BOUNDS, MAXSZ, prev, window=100, th_low=75.0,
+                                                   nnratio=nnratio, check_ori=check_ori)
+        assert nm[i] == rn, "pair %s: %d vs %d matches" % ((a, b), nm[i], rn)
+        assert (m12[i, :len(k1)] == rm).all()
+        assert (pmh[i, :len(k1)] == rpm).all()
+    assert nm[:6].min() > 30
+
+
+def test_second_round_uses_updated_prev_matched(pkg, extracted):
+    """vbPrevMatched feeds the next call (reference src/Tracking.cc:473-474): chain two calls."""
+    import torch
+    out, host, cap = extracted
+    fm = pkg.FeatureMatcher(nnratio=0.9, check_ori=True, desc_type=0, th_low=75.0)
+    pa = torch.tensor([0], dtype=torch.int32, device="cuda")
+    pm = torch.zeros((1, cap, 2), dtype=torch.float32, device="cuda"); pm[0] = out[0][0, :, :2]
+    k1, d1, s1 = host[0]
+    prev = np.stack([k1["x"], k1["y"]], axis=1)
+    for b in (1, 2):
+        pb = torch.tensor([b], dtype=torch.int32, device="cuda")
+        m12, nm = fm.search_for_initialization(out[0], out[1], out[2], out[3], pa, pb, pm, BOUNDS, MAXSZ, window=100)
+        k2, d2, s2 = host[b]
+        rn, rm, prev = po.search_for_initialization(0, k1, d1, k2, d2, s2, BOUNDS, MAXSZ, prev, window=100, th_low=75.0, nnratio=0.9, check_ori=True)
+        assert int(nm[0]) == rn and (m12[0, :len(k1)].cpu().numpy() == rm).all()
+
+
+def test_grid_and_window_search(pkg, extracted):
+    import torch
+    out, host, cap = extracted
+    fm = pkg.FeatureMatcher(desc_type=0)
+    cs, ci = fm.grid_build(out[0], out[3], BOUNDS)
+    torch.cuda.synchronize()
+    rng = np.random.default_rng(4)
+    for (qa, tb) in ((0, 1), (5, 4)):
+        kq, dq, sq = host[qa]; kt, dt, st = host[tb]
+        nq = len(kq)
+        qxy = np.stack([kq["x"], kq["y"]], axis=1) + rng.uniform(-6, 6, (nq, 2)).astype(np.float32)
+        qr = rng.choice(np.array([5.0, 15.0, 30.0, 100.0, 1000.0], np.float32), nq)
+        qmin = (sq / np.float32(1.2)).astype(np.float32); qmax = (sq * np.float32(1.2)).astype(np.float32)
+        qmin[::7] = 0.0; qmax[::7] = 1e9
+        rb, rbd, rsd, rbs, rss = po.match_window(0, dq, qxy, qr, qmin, qmax, kt, dt, st, BOUNDS)
+        t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+        b, bd, sd, bs, ss = fm.match_window(out[1][qa, :nq], t(qxy), t(qr), t(qmin), t(qmax), out[0][tb], out[1][tb], out[2][tb],
+                                            len(kt), cs[tb], ci[tb], BOUNDS)
+        torch.cuda.synchronize()
+        assert (b.cpu().numpy() == rb).all()
+        assert (bd.cpu().numpy() == rbd).all() and (sd.cpu().numpy() == rsd).all()
+        assert (bs.cpu().numpy() == rbs).all() and (ss.cpu().numpy() == rss).all()
+        assert (rb >= 0).sum() > nq // 2
+
+
+@pytest.mark.parametrize("desc_type,D", [(0, 32), (1, 61), (2, 48)])
+def test_bruteforce_hamming(pkg, desc_type, D):
+    import torch
+    rng = np.random.default_rng(10 + desc_type)
+    t = rng.integers(0, 256, (777, D), dtype=np.uint8)
+    q = t[rng.integers(0, 777, 500)].copy()
+    flip = rng.integers(0, 256, q.shape, dtype=np.uint8) & rng.integers(0, 256, q.shape, dtype=np.uint8) & rng.integers(0, 256, q.shape, dtype=np.uint8)
+    q ^= flip
+    q[:5] = t[:5]; t[100] = t[0]                                     # exact ties: first index must win
+    fm = pkg.FeatureMatcher(desc_type=desc_type)
+    b, bd, sd = fm.match_bruteforce(torch.from_numpy(q).cuda(), torch.from_numpy(t).cuda())
+    rb, rbd, rsd = po.match_bruteforce(desc_type, q, t)
+    assert (b.cpu().numpy() == rb).all() and (bd.cpu().numpy() == rbd).all() and (sd.cpu().numpy() == rsd).all()
+    assert rb[0] == 0 and rbd[0] == 0 and rsd[0] == 0
+    d = pkg.FeatureMatcher.descriptor_distance(desc_type, torch.from_numpy(q).cuda(), torch.from_numpy(t[:500].copy()).cuda())
+    ref = np.array([po.descriptor_distance(desc_type, q[i], t[i]) for i in range(500)], np.float32)
+    assert (d.cpu().numpy() == ref).all()
+
+
+def test_bruteforce_l2_sift_layout(pkg):
+    import torch
+    rng = np.random.default_rng(20)
+    t = rng.normal(size=(300, 128)).astype(np.float32); t /= np.linalg.norm(t, axis=1, keepdims=True)
+    q = t[rng.integers(0, 300, 200)] + rng.normal(scale=0.02, size=(200, 128)).astype(np.float32)
+    q = (q / np.linalg.norm(q, axis=1, keepdims=True)).astype(np.float32)
+    fm = pkg.FeatureMatcher(desc_type=5)
+    b, bd, sd = fm.match_bruteforce(torch.from_numpy(q).cuda().view(torch.uint8), torch.from_numpy(t).cuda().view(torch.uint8))
+    rb, rbd, rsd = po.match_bruteforce(5, q, t)
+    assert (b.cpu().numpy() == rb).all()
+    assert np.allclose(bd.cpu().numpy(), rbd, rtol=1e-5, atol=1e-7) and np.allclose(sd.cpu().numpy(), rsd, rtol=1e-5, atol=1e-7)
+
+
+def test_search_by_bow(pkg, extracted):
+    import torch
+    out, host, cap = extracted
+    k1, d1, s1 = host[0]; k2, d2, s2 = host[1]
+
+    def segs(k):
+        node = (k["x"] // 80).astype(np.int32) * 10 + (k["y"] // 80).astype(np.int32)
+        order = np.argsort(node, kind="stable")
+        ids, starts = np.unique(node[order], return_index=True)
+        return ids.astype(np.int32), np.append(starts, len(k)).astype(np.int32), order.astype(np.int32)
+    sa, sb = segs(k1), segs(k2)
+    for nnratio, ori in ((0.7, True), (0.75, False)):
+        rn, rmf = po.search_by_bow(0, d1, k1, sa, d2, k2, sb, th_low=75.0, nnratio=nnratio, check_ori=ori)
+        fm = pkg.FeatureMatcher(nnratio=nnratio, check_ori=ori, desc_type=0, th_low=75.0)
+        t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+        mf, nm = fm.search_by_bow(out[1][0, :len(k1)], out[0][0], [t(v) for v in sa], out[1][1, :len(k2)], out[0][1], [t(v) for v in sb])
+        torch.cuda.synchronize()
+        assert int(nm[0]) == rn and (mf.cpu().numpy() == rmf).all() and rn > 100
+
+
+def test_empty_inputs(pkg):
+    import torch
+    fm = pkg.FeatureMatcher(desc_type=0)
+    q = torch.zeros((0, 32), dtype=torch.uint8, device="cuda"); t = torch.zeros((4, 32), dtype=torch.uint8, device="cuda")
+    b, bd, sd = fm.match_bruteforce(q, t)
+    assert b.numel() == 0
+    b, bd, sd = fm.match_bruteforce(t, q)              # no train descriptors: best -1, distances FLT_MAX
+    torch.cuda.synchronize()
+    assert (b.cpu().numpy() == -1).all() and (bd.cpu().numpy() == np.finfo(np.float32).max).all()
