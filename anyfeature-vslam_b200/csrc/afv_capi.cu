@@ -23,6 +23,50 @@ extern "C" const char* afv_last_error(void) { return g_err; }
 extern "C" long long afv_kernel_launches(void) { return g_afv_launches; }
 extern "C" const char* afv_version(void) { return "afv-b200 0.1 (sm_100a)"; }
 
+// ---- per-kernel event timing --------------------------------------------------------------------------
+#include <map>
+#include <string>
+static bool g_prof_on = false;
+struct ProfRec { std::string name; cudaEvent_t e0, e1; };
+static std::vector<ProfRec> g_prof_recs;
+static std::vector<cudaEvent_t> g_prof_pool;
+static cudaEvent_t prof_event() {
+    if (!g_prof_pool.empty()) { cudaEvent_t e = g_prof_pool.back(); g_prof_pool.pop_back(); return e; }
+    cudaEvent_t e; cudaEventCreate(&e); return e;
+}
+void afv_prof_begin(const char* name, cudaStream_t st) {
+    if (!g_prof_on) return;
+    ProfRec r; r.name = name; r.e0 = prof_event(); r.e1 = prof_event();
+    cudaEventRecord(r.e0, st);
+    g_prof_recs.push_back(r);
+}
+void afv_prof_end(cudaStream_t st) {
+    if (!g_prof_on || g_prof_recs.empty()) return;
+    cudaEventRecord(g_prof_recs.back().e1, st);
+}
+extern "C" int afv_profile_enable(int on) { g_prof_on = on != 0; return AFV_OK; }
+// Synchronises, sums the recorded launches per kernel name and clears the records.
+// names: max_n x 32 chars; ms / calls: max_n.  Returns the number of distinct kernels.
+extern "C" int afv_profile_read(char* names, float* ms, int* calls, int max_n) {
+    std::map<std::string, std::pair<double, int>> acc;
+    std::vector<std::string> order;
+    for (auto& r : g_prof_recs) {
+        cudaEventSynchronize(r.e1);
+        float t = 0; cudaEventElapsedTime(&t, r.e0, r.e1);
+        if (!acc.count(r.name)) order.push_back(r.name);
+        acc[r.name].first += t; acc[r.name].second += 1;
+        g_prof_pool.push_back(r.e0); g_prof_pool.push_back(r.e1);
+    }
+    g_prof_recs.clear();
+    int n = 0;
+    for (auto& k : order) {
+        if (n >= max_n) break;
+        strncpy(names + 32 * n, k.c_str(), 31); names[32 * n + 31] = 0;
+        ms[n] = (float)acc[k].first; calls[n] = acc[k].second; ++n;
+    }
+    return n;
+}
+
 static inline int round_half_even_f(float v) { return (int)lrintf(v); }     // cvRound
 
 struct afv_extractor {

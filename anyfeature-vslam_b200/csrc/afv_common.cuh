@@ -68,6 +68,10 @@ int afv_orb_configure(int max_det_cap, int max_keep_cap);   // sets smem attribu
 // matcher launches (afv_match.cu) are called directly from afv_capi.cu through the C ABI.
 
 extern long long g_afv_launches;
+// optional per-kernel CUDA-event timing (bench.py's roofline leg): AFV_PROF_BEGIN/END bracket one launch
+void afv_prof_begin(const char* name, cudaStream_t st);
+void afv_prof_end(cudaStream_t st);
+struct AfvProfScope { cudaStream_t st; AfvProfScope(const char* n, cudaStream_t s) : st(s) { afv_prof_begin(n, s); } ~AfvProfScope() { afv_prof_end(st); } };
 void afv_set_error(const char* fmt, ...);
 #define AFV_CUDA_CHECK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { \
     afv_set_error("%s failed: %s (%s:%d)", #x, cudaGetErrorString(e_), __FILE__, __LINE__); return AFV_ERR_CUDA; } } while (0)

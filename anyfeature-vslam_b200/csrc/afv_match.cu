@@ -274,7 +274,7 @@ __global__ void __launch_bounds__(SFI_THREADS) k_search_init(int desc_type, int 
     const uint8_t* d1 = desc + (long long)fa * cap * D;
     const uint8_t* d2 = desc + (long long)fb * cap * D;
     const float* size2 = kpsize + (long long)fb * cap;
-    float* pm = prev_matched + (long long)p * cap * 2;
+    float* pm = prev_matched ? prev_matched + (long long)p * cap * 2 : nullptr;
     int* m12 = matches12 + (long long)p * cap;
 
     float* tx = reinterpret_cast<float*>(sm);                       // [cap]
@@ -312,7 +312,7 @@ __global__ void __launch_bounds__(SFI_THREADS) k_search_init(int desc_type, int 
     const int nw = Dpad / 4;
     for (int i1 = 0; i1 < n1; ++i1) {
         if (k1[i1].octave > 0) continue;                              // :491-493
-        const float x = pm[2 * i1], y = pm[2 * i1 + 1];
+        const float x = pm ? pm[2 * i1] : k1[i1].x, y = pm ? pm[2 * i1 + 1] : k1[i1].y;
         int c0, c1, r0, r1;
         Top2 t; t.k1 = t.k2 = KEY_NONE;
         if (window_cells(x, y, window, minX, minY, invW, invH, c0, c1, r0, r1)) {
@@ -379,7 +379,7 @@ __global__ void __launch_bounds__(SFI_THREADS) k_search_init(int desc_type, int 
         if (removed) atomicSub(&s_nm, removed);
         __syncthreads();
     }
-    for (int i = tid; i < n1; i += SFI_THREADS)                       // :552-554
+    if (pm) for (int i = tid; i < n1; i += SFI_THREADS)                       // :552-554
         if (m12[i] >= 0) { pm[2 * i] = k2[m12[i]].x; pm[2 * i + 1] = k2[m12[i]].y; }
     if (tid == 0) nmatches[p] = s_nm;
 }
@@ -390,7 +390,7 @@ extern "C" int afv_search_for_initialization(int desc_type, const afv_keypoint* 
         float* d_prev_matched, int window, float th_low, float nnratio, int check_orientation,
         int* d_matches12, int* d_nmatches, void* cuda_stream) {
     const int D = desc_bytes(desc_type);
-    if (D < 0 || !d_kps || !d_desc || !d_kpsize || !d_n || !d_pair_a || !d_pair_b || !d_prev_matched || !d_matches12 ||
+    if (D < 0 || !d_kps || !d_desc || !d_kpsize || !d_n || !d_pair_a || !d_pair_b || !d_matches12 ||
         !d_nmatches || B < 1 || P < 0 || cap < 1) { afv_set_error("afv_search_for_initialization: bad argument"); return AFV_ERR_INVALID; }
     if (P == 0) return AFV_OK;
     if (cap >= (1 << 20)) { afv_set_error("cap too large for the order key"); return AFV_ERR_INVALID; }
@@ -404,6 +404,7 @@ extern "C" int afv_search_for_initialization(int desc_type, const afv_keypoint* 
         configured = smem;
     }
     const float invW = (float)AFV_GRID_COLS / (max_x - min_x), invH = (float)AFV_GRID_ROWS / (max_y - min_y);
+    AfvProfScope ps("k_search_init", as_stream(cuda_stream));
     k_search_init<<<P, SFI_THREADS, smem, as_stream(cuda_stream)>>>(desc_type, D, Dpad, stage, d_kps, (const uint8_t*)d_desc, d_kpsize,
         d_n, cap, d_pair_a, d_pair_b, min_x, min_y, invW, invH, max_kpt_size, d_prev_matched, (float)window, th_low, nnratio,
         check_orientation, d_matches12, d_nmatches);
@@ -441,8 +442,9 @@ __global__ void __launch_bounds__(256) k_match_bf(int desc_type, int D, const ui
 extern "C" int afv_match_bruteforce(int desc_type, const void* d_q, int nq, const void* d_t, int nt,
                                     int* d_best, float* d_bestd, float* d_secondd, void* cuda_stream) {
     const int D = desc_bytes(desc_type);
-    if (D < 0 || !d_q || !d_t || !d_best || !d_bestd || !d_secondd || nq < 0 || nt < 0) { afv_set_error("afv_match_bruteforce: bad argument"); return AFV_ERR_INVALID; }
+    if (D < 0 || nq < 0 || nt < 0) { afv_set_error("afv_match_bruteforce: bad argument"); return AFV_ERR_INVALID; }
     if (nq == 0) return AFV_OK;
+    if (!d_q || (!d_t && nt > 0) || !d_best || !d_bestd || !d_secondd) { afv_set_error("afv_match_bruteforce: NULL argument"); return AFV_ERR_INVALID; }
     k_match_bf<<<(nq + 7) / 8, 256, 0, as_stream(cuda_stream)>>>(desc_type, D, (const uint8_t*)d_q, nq, (const uint8_t*)d_t, nt, d_best, d_bestd, d_secondd);
     ++g_afv_launches;
     AFV_CUDA_CHECK(cudaGetLastError());

@@ -758,14 +758,16 @@ void afv_launch_extract(const AfvParams& P, afv_keypoint* d_kps, uint8_t* d_desc
     cudaMemsetAsync(P.status, 0, sizeof(int) * P.B, st);
     for (int l = 1; l < P.nlevels; ++l) {
         dim3 g((P.lv[l].w + 127) / 128, (P.lv[l].h + 7) / 8, P.B);
+        AfvProfScope ps("k_resize", st);
         k_resize<<<g, dim3(32, 8), 0, st>>>(P, l);
         ++g_afv_launches;
     }
-    k_fast<<<dim3(acc, P.B), 256, 0, st>>>(P, T); ++g_afv_launches;
-    k_harris_select<<<dim3(P.nlevels, P.B), 256, 0, st>>>(P); ++g_afv_launches;
-    k_octree<<<dim3(P.nlevels, P.B), 256, afv_octree_smem_bytes(g_oct_mcap, g_oct_ncap), st>>>(P, g_oct_mcap, g_oct_ncap);
-    ++g_afv_launches;
-    k_blur<<<dim3(acc, P.B), 256, 0, st>>>(P, T); ++g_afv_launches;
-    k_describe<<<dim3((P.out_cap + 7) / 8, P.B), 256, 0, st>>>(P, d_kps, d_desc, d_kpsize, d_n_out);
-    ++g_afv_launches;
+    { AfvProfScope ps("k_fast", st); k_fast<<<dim3(acc, P.B), 256, 0, st>>>(P, T); ++g_afv_launches; }
+    { AfvProfScope ps("k_harris_select", st); k_harris_select<<<dim3(P.nlevels, P.B), 256, 0, st>>>(P); ++g_afv_launches; }
+    { AfvProfScope ps("k_octree", st);
+      k_octree<<<dim3(P.nlevels, P.B), 256, afv_octree_smem_bytes(g_oct_mcap, g_oct_ncap), st>>>(P, g_oct_mcap, g_oct_ncap);
+      ++g_afv_launches; }
+    { AfvProfScope ps("k_blur", st); k_blur<<<dim3(acc, P.B), 256, 0, st>>>(P, T); ++g_afv_launches; }
+    { AfvProfScope ps("k_describe", st);
+      k_describe<<<dim3((P.out_cap + 7) / 8, P.B), 256, 0, st>>>(P, d_kps, d_desc, d_kpsize, d_n_out); ++g_afv_launches; }
 }

@@ -1,0 +1,357 @@
+#!/usr/bin/env python3
+"""bench.py -- frames/sec of the orb32 extract+match hot path on B200 (BASELINE.json metric).
+
+One "step" = one pass of the hot path over one batch of B synthetic 640x480 frames (1000 kp/frame):
+orb32 extraction of all B frames (CUDA, batched) + FeatureMatcher::SearchForInitialization of every frame
+against its successor in the same stream (B pairs, wrap-around inside a stream).
+
+  python bench.py --gpus 1 --steps K --warmup W          # this repo's arm
+  python bench.py --impl reference ...                   # CPU arm: the oracle port of the reference's path
+  torchrun --nproc-per-node N bench.py --gpus N ...      # one rank per GPU, streams sharded over ranks
+
+Rank 0 prints ONE JSON line (see README / DESIGN.md for the fields).
+"""
+import argparse
+import importlib.util
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "frames/sec (extract+match) orb32 640x480x1000kp"
+UNIT = "frames/s"
+W, H, NFEAT = 640, 480, 1000
+BOUNDS = (0.0, 0.0, float(W), float(H))
+MAX_KPT_SIZE = float(np.float32(1.2) ** np.float32(7))       # FeatureExtractor::GetMaxKeyPtSize
+P_PIX = 950532                                                  # sum of pyramid pixels at 640x480
+
+
+def load_pkg():
+    name = "anyfeature_vslam_b200"
+    if name in sys.modules:
+        return sys.modules[name]
+    path = os.path.join(ROOT, "anyfeature-vslam_b200", "__init__.py")
+    spec = importlib.util.spec_from_file_location(name, path, submodule_search_locations=[os.path.dirname(path)])
+    mod = importlib.util.module_from_spec(spec)
+    sys.modules[name] = mod
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def make_frames(pkg, batch, rank, unique_streams=8, frames_per_stream=16):
+    """batch frames = tiles of `unique_streams` streams x `frames_per_stream` consecutive frames (stream ids are
+    offset by rank so ranks see different data).  Returns (u8 [batch,H,W], pair_a, pair_b)."""
+    per = frames_per_stream
+    base = np.concatenate([pkg.synth.stream_frames(W, H, 100 * rank + s, per)[0] for s in range(unique_streams)], axis=0)
+    reps = (batch + len(base) - 1) // len(base)
+    frames = np.concatenate([base] * reps, axis=0)[:batch]
+    idx = np.arange(batch)
+    start = (idx // per) * per
+    nxt = start + (idx - start + 1) % per
+    nxt = np.minimum(nxt, batch - 1)
+    return np.ascontiguousarray(frames), idx.astype(np.int32), nxt.astype(np.int32)
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        super().__init__(daemon=True)
+        self.gpu = gpu_index
+        self.samples = []
+        self.stop_flag = False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([v.strip() for v in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        sm = sorted(int(s[0]) for s in self.samples if s[0].isdigit())
+        mx = [int(s[1]) for s in self.samples if s[1].isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(s[2 + i].lower().startswith("active") for s in self.samples)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(self.samples)}
+
+
+# ---------------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port of the reference's per-frame path, all host threads (ctypes releases the GIL)
+# ---------------------------------------------------------------------------------------------------------
+def cpu_arm(frames, pair_b, nthreads, seconds_budget):
+    from concurrent.futures import ThreadPoolExecutor
+    from oracle import pyoracle as po
+    po.lib()
+    n = len(frames)
+
+    def step(sample):
+        # extract every frame of the sample once, then match consecutive frames (same work as the GPU step)
+        with ThreadPoolExecutor(nthreads) as ex:
+            res = list(ex.map(lambda i: po.orb32_extract(frames[i], NFEAT)[:3], sample))
+
+            def match(t):
+                a, b = res[t], res[(t + 1) % len(res)]
+                prev = np.stack([a[0]["x"], a[0]["y"]], axis=1)
+                return po.search_for_initialization(0, a[0], a[1], b[0], b[1], b[2], BOUNDS, MAX_KPT_SIZE, prev,
+                                                    window=100, th_low=75.0, nnratio=0.9, check_ori=True)[0]
+            list(ex.map(match, range(len(res))))
+
+    # size the sample from a one-thread probe so a step stays within the budget
+    t0 = time.perf_counter(); step([0, 1]); t1 = time.perf_counter()
+    per_frame = (t1 - t0) / 2
+    sample_n = int(max(nthreads, min(n, seconds_budget / per_frame * nthreads)))
+    sample = list(range(min(sample_n, n)))
+    return step, sample, per_frame
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    pkg_synth = importlib.util.spec_from_file_location("afv_synth", os.path.join(ROOT, "anyfeature-vslam_b200", "synth.py"))
+    synth = importlib.util.module_from_spec(pkg_synth); pkg_synth.loader.exec_module(synth)
+
+    class _P:
+        pass
+    P = _P(); P.synth = synth
+    frames, pa, pb = make_frames(P, min(args.batch, 256), 0)
+    nthreads = os.cpu_count() or 1
+    step, sample, per_frame = cpu_arm(frames, pb, nthreads, seconds_budget=4.0)
+    for _ in range(max(1, min(args.warmup, 1))):
+        step(sample)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step(sample)
+    dt = time.perf_counter() - t0
+    fps = len(sample) * args.steps / dt
+    line = {
+        "impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": {"workload": "orb32 640x480 synthetic batch, 1000 kp/frame, extract+SearchForInitialization (configs[1])",
+                   "frames_per_step": len(sample)},
+        "cpu_baseline": {"value": fps, "unit": UNIT, "cores": nthreads, "kind": "port",
+                         "sample": "%d frames/step x %d steps, oracle C port of the reference path (cv::ORB restated + octree + matcher), %d threads; 1 thread: %.1f fps"
+                                   % (len(sample), args.steps, nthreads, 1.0 / per_frame)},
+        "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# ---------------------------------------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------------------------------------
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the product path has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    pkg = load_pkg()
+    lib = pkg.lib()
+    B = args.batch
+    frames, pa, pb = make_frames(pkg, B, rank)
+    ex = pkg.FeatureExtractor("orb32", nfeatures=NFEAT, device=local, max_batch=B, max_w=W, max_h=H)
+    cap = ex.cap
+    fm = pkg.FeatureMatcher(nnratio=0.9, check_ori=True, desc_type=0, th_low=75.0)
+    d_gray = torch.from_numpy(frames).to(dev)
+    h_gray = torch.from_numpy(frames).pin_memory()
+    d_pa = torch.from_numpy(pa).to(dev); d_pb = torch.from_numpy(pb).to(dev)
+    out = ex.alloc_device_outputs(B)
+    m12 = torch.empty((B, cap), dtype=torch.int32, device=dev)
+    nm = torch.empty((B,), dtype=torch.int32, device=dev)
+    stream = torch.cuda.current_stream()
+    gathered = None
+    if world > 1 and args.gather:
+        # C5: fixed-capacity packed results gathered to rank 0 over NCCL/NVLink (n, matches, nmatches, kps, desc)
+        pack_bytes = B * (4 + 4 + cap * (28 + 32 + 4))
+        d_pack = torch.empty(pack_bytes, dtype=torch.uint8, device=dev)
+        gathered = [torch.empty(pack_bytes, dtype=torch.uint8, device=dev) for _ in range(world)] if rank == 0 else None
+
+    def device_step(src):
+        ex.extract_batch_device(src, out, stream)
+        fm.search_for_initialization(out[0], out[1], out[2], out[3], d_pa, d_pb, None, BOUNDS, MAX_KPT_SIZE,
+                                     window=100, matches12=m12, nmatches=nm, stream=stream)
+        if world > 1 and args.gather:
+            o = 0
+            for t in (out[3].view(torch.uint8).view(-1), nm.view(torch.uint8).view(-1), m12.view(torch.uint8).view(-1),
+                      out[0].view(torch.uint8).view(-1), out[1].view(-1)):
+                d_pack[o:o + t.numel()].copy_(t, non_blocking=True); o += t.numel()
+            dist.gather(d_pack, gathered, dst=0)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- warm-up (also the validity check: capacity flags, plausible match counts)
+    for _ in range(max(args.warmup, 3)):
+        device_step(d_gray)
+    torch.cuda.synchronize()
+    ex.status()
+    n_host = out[3].cpu().numpy(); nm_host = nm.cpu().numpy()
+    assert n_host.min() >= NFEAT and n_host.max() <= cap, "unexpected keypoint counts %d..%d" % (n_host.min(), n_host.max())
+
+    # ---- timed region 1: inputs resident in HBM (value)
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    launches0 = pkg.kernel_launches()
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        device_step(d_gray)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = pkg.kernel_launches() - launches0
+
+    # ---- timed region 2: end to end from pinned host frames, results read back to the host (e2e)
+    h_out = [torch.empty(t.shape, dtype=t.dtype).pin_memory() for t in (out[0], out[1], out[3], m12, nm)]
+    d_in = torch.empty_like(d_gray)
+
+    def e2e_step():
+        d_in.copy_(h_gray, non_blocking=True)
+        device_step(d_in)
+        for hdst, dsrc in zip(h_out, (out[0], out[1], out[3], m12, nm)):
+            hdst.copy_(dsrc, non_blocking=True)
+        torch.cuda.current_stream().synchronize()          # the caller needs the results on the host
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    f0 = torch.cuda.Event(enable_timing=True); f1 = torch.cuda.Event(enable_timing=True)
+    f0.record()
+    for _ in range(args.steps):
+        e2e_step()
+    f1.record()
+    barrier()
+    ms_e2e = f0.elapsed_time(f1)
+    if sampler:
+        sampler.stop_flag = True
+    h2d = int(h_gray.numel()); d2h = int(sum(t.numel() * t.element_size() for t in h_out))
+
+    # ---- max over ranks
+    if world > 1:
+        t = torch.tensor([ms, ms_e2e], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, ms_e2e = float(t[0]), float(t[1])
+    total_frames = B * world * args.steps
+    value = total_frames / (ms * 1e-3)
+    e2e_value = total_frames / (ms_e2e * 1e-3)
+
+    line = None
+    if rank == 0:
+        # ---- per-kernel event timing on instrumented extra steps (same inputs), dominant kernel -> roofline
+        import ctypes as C
+        lib.afv_profile_enable(1)
+        for _ in range(3):
+            device_step(d_gray)
+        torch.cuda.synchronize()
+        names = C.create_string_buffer(32 * 32); kms = (C.c_float * 32)(); kcalls = (C.c_int * 32)()
+        nk = lib.afv_profile_read(names, kms, kcalls, 32)
+        lib.afv_profile_enable(0)
+        kern = {names.raw[32 * i:32 * i + 32].split(b"\0")[0].decode(): (kms[i] / 3.0, kcalls[i] // 3) for i in range(nk)}
+        # algorithmic bytes per step of each kernel (DESIGN.md "kernels"): P = pyramid pixels, C = FAST candidates,
+        # M = detect list, N = kept keypoints, all per frame
+        Ccand = float(np.mean([ex.debug_read(2, 0, l).size // 4 for l in range(8)])) * 8
+        N = float(n_host.mean())
+        alg = {
+            "k_resize": B * (P_PIX - 179 * 134 + P_PIX - W * H),          # read levels 0..6, write levels 1..7
+            "k_fast": B * (P_PIX + 4 * Ccand),
+            "k_harris_select": B * (4 * Ccand * 3 + 81 * Ccand * 0.5 + 8 * 8539),
+            "k_octree": B * (8 * 8539 + 8 * N),
+            "k_blur": B * (2 * P_PIX),
+            "k_describe": B * N * (8 + 709 + 512 + 28 + 32 + 4),
+            "k_search_init": B * (2 * N * (32 + 12) + 4 * N + 4),
+        }
+        dom = max(kern, key=lambda k: kern[k][0])
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        dom_ms = kern[dom][0]
+        achieved = alg.get(dom, 0.0) / (dom_ms * 1e-3) / 1e9
+        roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                    "traffic": None, "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback",
+                    "kernel_ms_per_step": {k: round(v[0], 4) for k, v in kern.items()},
+                    "step_algorithmic_gbs": B * (4 * P_PIX + 12 * Ccand + 60 * N) / (ms / args.steps * 1e-3) / 1e9}
+        # ---- CPU baseline (oracle port) on this host, bounded sample
+        nthreads = os.cpu_count() or 1
+        step, sample, per_frame = cpu_arm(frames, pb, nthreads, seconds_budget=3.0)
+        step(sample)
+        t0 = time.perf_counter(); reps = 2
+        for _ in range(reps):
+            step(sample)
+        cpu_fps = len(sample) * reps / (time.perf_counter() - t0)
+        cpu_baseline = {"value": cpu_fps, "unit": UNIT, "cores": nthreads, "kind": "port",
+                        "sample": "%d frames x %d passes of the same workload, oracle C port, %d threads (1 thread: %.1f fps)"
+                                  % (len(sample), reps, nthreads, 1.0 / per_frame)}
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u8", "data": "synthetic",
+            "config": {"workload": "orb32 640x480 synthetic batch, 1000 kp/frame, extract+SearchForInitialization on 1xB200 per rank (configs[1])",
+                       "frames_per_step_per_gpu": B, "pairs_per_step_per_gpu": B, "parallelism": "frames sharded, dp%d" % world,
+                       "l2": "inputs+intermediates (%.1f GB/step) larger than L2, no flush" % (B * 3.1e6 / 1e9),
+                       "gather": bool(world > 1 and args.gather)},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": int(launches),
+            "clocks": sampler.summary() if sampler else None,
+            "roofline": roofline,
+            "cpu_baseline": cpu_baseline,
+            "check": {"kps_per_frame": [int(n_host.min()), int(n_host.max())], "matches_per_pair_mean": float(nm_host.mean())},
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    ex.close()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--batch", type=int, default=512, help="frames per step per GPU")
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-gather", dest="gather", action="store_false")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_gpu(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -109,7 +109,9 @@ int  afv_match_window(int desc_type, const void* d_q, const float* d_qxy, const 
  * frame pairs: pair p matches frame a[p] (queries, octave-0 only) against frame b[p] (train) of a B x cap
  * extraction result.  Reproduces the sequential "already matched with a smaller distance" rule (:511-512),
  * match stealing (:530-537), the rotation histogram (:1579-1668) and the vbPrevMatched update (:552-554).
- * d_prev_matched: P x cap x 2 floats in/out; d_matches12: P x cap ints out; d_nmatches: P ints out.        */
+ * d_prev_matched: P x cap x 2 floats in/out, or NULL = first call of MonocularInitialization: vbPrevMatched is
+ * F1's own keypoint positions (src/Tracking.cc:440-445) and nothing is written back;
+ * d_matches12: P x cap ints out; d_nmatches: P ints out.                                                   */
 int  afv_search_for_initialization(int desc_type, const afv_keypoint* d_kps, const void* d_desc,
                                    const float* d_kpsize, const int* d_n, int B, int cap,
                                    const int* d_pair_a, const int* d_pair_b, int P,
@@ -141,6 +143,10 @@ const char* afv_last_error(void);
 /* number of kernels this library has launched since load (bench.py's gpu_launches) */
 long long   afv_kernel_launches(void);
 const char* afv_version(void);
+/* Optional per-kernel CUDA-event timing used by bench.py's roofline leg (events on the launching stream).
+ * afv_profile_read synchronises, sums elapsed ms and launch counts per kernel name (32-char slots), clears. */
+int         afv_profile_enable(int on);
+int         afv_profile_read(char* names, float* ms, int* calls, int max_n);
 
 #ifdef __cplusplus
 }

@@ -138,8 +138,21 @@ int orc_fast9_16_nms(const uint8_t* img, int w, int h, int stride, int threshold
     if (w < 7 || h < 7) return 0;
     uint8_t* sc = (uint8_t*)calloc((size_t)w * h, 1);
     for (int y = 3; y < h - 3; ++y)
-        for (int x = 3; x < w - 3; ++x)
-            sc[(long)y * w + x] = (uint8_t)fast_score(img + (long)y * stride + x, stride, threshold);
+        for (int x = 3; x < w - 3; ++x) {
+            /* cheap necessary condition first (any arc of 9 holds one pixel of each antipodal pair), as
+             * OpenCV's scalar loop does; fast_score decides. */
+            const uint8_t* p = img + (long)y * stride + x;
+            int v = p[0], hi = v + threshold, lo = v - threshold;
+            int a = p[3 * stride], b = p[-3 * stride];
+            if (!(a > hi || a < lo || b > hi || b < lo)) continue;
+            a = p[3]; b = p[-3];
+            if (!(a > hi || a < lo || b > hi || b < lo)) continue;
+            a = p[2 * stride + 2]; b = p[-2 * stride - 2];
+            if (!(a > hi || a < lo || b > hi || b < lo)) continue;
+            a = p[-2 * stride + 2]; b = p[2 * stride - 2];
+            if (!(a > hi || a < lo || b > hi || b < lo)) continue;
+            sc[(long)y * w + x] = (uint8_t)fast_score(p, stride, threshold);
+        }
     for (int y = 3; y < h - 3; ++y)
         for (int x = 3; x < w - 3; ++x) {
             int s = sc[(long)y * w + x];
