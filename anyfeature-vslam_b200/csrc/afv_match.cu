@@ -259,6 +259,15 @@ __device__ __forceinline__ void three_maxima(const int* cnt, int& ind1, int& ind
     else if ((float)max3 < __fmul_rn(0.1f, (float)max1)) { ind3 = -1; }
 }
 
+// Shared-memory plan (cap = per-frame capacity, Dpad = descriptor bytes padded to 4):
+//   train keypoints are staged SORTED BY GRID COLUMN (counting sort, 64 bins) so a query only scans the slots of
+//   its cell-column range; slot order inside a column is arbitrary - ties are decided by the explicit order key.
+struct SfiSmem {
+    float* sx; float* sy; float* sang; float* matched; int* m21; int* m12;
+    unsigned short* scell; unsigned short* sorig; unsigned short* qlist; signed char* hbin; uint8_t* sdesc;
+};
+__host__ __device__ inline size_t sfi_base_bytes(int cap) { return (((size_t)cap * (4 * 6 + 2 * 3 + 1)) + 15) & ~(size_t)15; }
+
 __global__ void __launch_bounds__(SFI_THREADS) k_search_init(int desc_type, int D, int Dpad, int stage_desc,
         const afv_keypoint* __restrict__ kps, const uint8_t* __restrict__ desc, const float* __restrict__ kpsize,
         const int* __restrict__ n_arr, int cap, const int* __restrict__ pair_a, const int* __restrict__ pair_b,
@@ -275,77 +284,127 @@ __global__ void __launch_bounds__(SFI_THREADS) k_search_init(int desc_type, int 
     const uint8_t* d2 = desc + (long long)fb * cap * D;
     const float* size2 = kpsize + (long long)fb * cap;
     float* pm = prev_matched ? prev_matched + (long long)p * cap * 2 : nullptr;
-    int* m12 = matches12 + (long long)p * cap;
+    int* m12g = matches12 + (long long)p * cap;
 
-    float* tx = reinterpret_cast<float*>(sm);                       // [cap]
-    float* ty = tx + cap;
-    float* matchedDist = ty + cap;
-    int* m21 = reinterpret_cast<int*>(matchedDist + cap);
-    unsigned short* tcell = reinterpret_cast<unsigned short*>(m21 + cap);     // cx<<8|cy, 0xffff = not in grid / size-gated
-    signed char* hbin = reinterpret_cast<signed char*>(tcell + cap);          // [cap] histogram bin of query i1 (or -1)
-    uint8_t* tdesc = reinterpret_cast<uint8_t*>(sm) + (((size_t)cap * (4 + 4 + 4 + 4 + 2 + 1)) + 15 & ~(size_t)15);
+    SfiSmem S;
+    S.sx = reinterpret_cast<float*>(sm); S.sy = S.sx + cap; S.sang = S.sy + cap; S.matched = S.sang + cap;
+    S.m21 = reinterpret_cast<int*>(S.matched + cap); S.m12 = S.m21 + cap;
+    S.scell = reinterpret_cast<unsigned short*>(S.m12 + cap); S.sorig = S.scell + cap; S.qlist = S.sorig + cap;
+    S.hbin = reinterpret_cast<signed char*>(S.qlist + cap);
+    S.sdesc = sm + sfi_base_bytes(cap);
     __shared__ Top2 wtop[SFI_THREADS / 32];
     __shared__ int hist[AFV_HISTO_LENGTH];
-    __shared__ int s_nm;
+    __shared__ int colstart[AFV_GRID_COLS + 1], colfill[AFV_GRID_COLS];
+    __shared__ int s_nm, s_nq, keepbin[3];
+    const int nw = Dpad / 4;
 
+    // ---- prologue: column histogram -> counting sort of the train frame; query list = octave-0 keypoints
+    if (tid < AFV_GRID_COLS) { colstart[tid] = 0; colfill[tid] = 0; }
+    if (tid < AFV_HISTO_LENGTH) hist[tid] = 0;
+    if (tid == 0) { s_nm = 0; s_nq = 0; colstart[AFV_GRID_COLS] = 0; }
+    __syncthreads();
     for (int i = tid; i < n2; i += SFI_THREADS) {
-        const float x = k2[i].x, y = k2[i].y, sz = size2[i];
-        tx[i] = x; ty[i] = y; matchedDist[i] = FLT_MAX; m21[i] = -1;
-        const int c = grid_cell(x, y, minX, minY, invW, invH);
-        // GetFeaturesInArea(…, minSize 0, maxSize F1.maxKeyPtSize) size gate folded in (:495-496, Frame.cc:365-368)
+        const float sz = size2[i];
+        const int c = grid_cell(k2[i].x, k2[i].y, minX, minY, invW, invH);
+        // GetFeaturesInArea(..., minSize 0, maxSize F1.maxKeyPtSize) size gate folded in (:495-496, Frame.cc:365-368)
         const bool ok = c >= 0 && !(sz < 0.0f) && !(sz > max_kpt_size);
-        tcell[i] = ok ? (unsigned short)(((c / AFV_GRID_ROWS) << 8) | (c % AFV_GRID_ROWS)) : (unsigned short)0xffff;
+        S.m21[i] = ok ? c : -1;                                     // temp: cell id
+        if (ok) atomicAdd(&colstart[c / AFV_GRID_ROWS + 1], 1);
     }
+    for (int i = tid; i < n1; i += SFI_THREADS) S.m12[i] = (k1[i].octave > 0) ? -2 : -1;      // -2: never a query
+    __syncthreads();
+    if (wid == 0) {                                                 // inclusive scan of 64 column counts
+        int v0 = colstart[1 + lane], v1 = colstart[33 + lane];
+        int a0 = v0, a1 = v1;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { int t0 = __shfl_up_sync(0xffffffffu, a0, o), t1 = __shfl_up_sync(0xffffffffu, a1, o); if (lane >= o) { a0 += t0; a1 += t1; } }
+        const int tot0 = __shfl_sync(0xffffffffu, a0, 31);
+        colstart[1 + lane] = a0; colstart[33 + lane] = tot0 + a1;
+    }
+    if (wid == 1) {                                                 // ordered compaction of the octave-0 queries
+        int base = 0;
+        for (int i0 = 0; i0 < n1; i0 += 32) {
+            const int i = i0 + lane;
+            const bool q = i < n1 && S.m12[i] == -1;
+            const unsigned m = __ballot_sync(0xffffffffu, q);
+            if (q) S.qlist[base + __popc(m & ((1u << lane) - 1))] = (unsigned short)i;
+            base += __popc(m);
+        }
+        if (lane == 0) s_nq = base;
+    }
+    __syncthreads();
+    for (int i = tid; i < n2; i += SFI_THREADS) {
+        const int c = S.m21[i];
+        if (c < 0) continue;
+        const int cx = c / AFV_GRID_ROWS;
+        const int slot = colstart[cx] + atomicAdd(&colfill[cx], 1);
+        S.sx[slot] = k2[i].x; S.sy[slot] = k2[i].y; S.sang[slot] = k2[i].angle;
+        S.scell[slot] = (unsigned short)((cx << 8) | (c % AFV_GRID_ROWS));
+        S.sorig[slot] = (unsigned short)i;
+    }
+    __syncthreads();
+    const int n2s = colstart[AFV_GRID_COLS];
+    for (int i = tid; i < n2s; i += SFI_THREADS) { S.matched[i] = FLT_MAX; S.m21[i] = -1; }
+    for (int i = tid; i < n1; i += SFI_THREADS) { S.hbin[i] = -1; if (S.m12[i] == -2) S.m12[i] = -1; }
     if (stage_desc) {
-        for (int i = tid; i < n2 * (Dpad / 4); i += SFI_THREADS) {
-            const int r = i / (Dpad / 4), w = i % (Dpad / 4);
-            uint32_t v = 0;
-            for (int b = 0; b < 4; ++b) { const int o = w * 4 + b; if (o < D) v |= (uint32_t)d2[(long long)r * D + o] << (8 * b); }
-            reinterpret_cast<uint32_t*>(tdesc)[i] = v;
+        for (int i = tid; i < n2s * nw; i += SFI_THREADS) {
+            const int r = i / nw, w = i % nw;
+            const uint8_t* row = d2 + (long long)S.sorig[r] * D;
+            uint32_t v;
+            if ((D & 3) == 0) v = reinterpret_cast<const uint32_t*>(row)[w];
+            else { v = 0; for (int b = 0; b < 4; ++b) { const int o = w * 4 + b; if (o < D) v |= (uint32_t)row[o] << (8 * b); } }
+            reinterpret_cast<uint32_t*>(S.sdesc)[i] = v;
         }
     }
-    for (int i = tid; i < n1; i += SFI_THREADS) { m12[i] = -1; hbin[i] = -1; }
-    if (tid < AFV_HISTO_LENGTH) hist[tid] = 0;
-    if (tid == 0) s_nm = 0;
     __syncthreads();
 
-    const int nw = Dpad / 4;
-    for (int i1 = 0; i1 < n1; ++i1) {
-        if (k1[i1].octave > 0) continue;                              // :491-493
-        const float x = pm ? pm[2 * i1] : k1[i1].x, y = pm ? pm[2 * i1 + 1] : k1[i1].y;
+    // ---- queries in index order; the next query's descriptor / position / angle are prefetched
+    const int nq = s_nq;
+    uint32_t qd[16], qdn[16];
+    float qx = 0, qy = 0, qa = 0, qxn = 0, qyn = 0, qan = 0;
+    auto load_query = [&](int qi, uint32_t* dst, float& x, float& y, float& a) {
+        const int i1 = S.qlist[qi];
+        x = pm ? pm[2 * i1] : k1[i1].x; y = pm ? pm[2 * i1 + 1] : k1[i1].y; a = k1[i1].angle;
+        if (desc_type != AFV_FEAT_SIFT128) {
+            const uint8_t* qrow = d1 + (long long)i1 * D;
+            if ((D & 3) == 0) {
+#pragma unroll
+                for (int w = 0; w < 16; ++w) if (w < nw) dst[w] = reinterpret_cast<const uint32_t*>(qrow)[w];
+            } else {
+#pragma unroll
+                for (int w = 0; w < 16; ++w) if (w < nw) { uint32_t v = 0; for (int b = 0; b < 4; ++b) { const int o = w * 4 + b; if (o < D) v |= (uint32_t)qrow[o] << (8 * b); } dst[w] = v; }
+            }
+        }
+    };
+    if (nq > 0) load_query(0, qdn, qxn, qyn, qan);
+    for (int qi = 0; qi < nq; ++qi) {
+        const int i1 = S.qlist[qi];
+#pragma unroll
+        for (int w = 0; w < 16; ++w) qd[w] = qdn[w];
+        qx = qxn; qy = qyn; qa = qan;
+        if (qi + 1 < nq) load_query(qi + 1, qdn, qxn, qyn, qan);
         int c0, c1, r0, r1;
         Top2 t; t.k1 = t.k2 = KEY_NONE;
-        if (window_cells(x, y, window, minX, minY, invW, invH, c0, c1, r0, r1)) {
-            uint32_t qd[16];
-            if (desc_type != AFV_FEAT_SIFT128) {
-                const uint8_t* qrow = d1 + (long long)i1 * D;
-                if ((D & 3) == 0 && ((uintptr_t)qrow & 3) == 0) {
-                    for (int w = 0; w < nw; ++w) qd[w] = reinterpret_cast<const uint32_t*>(qrow)[w];
-                } else {
-                    for (int w = 0; w < nw; ++w) {
-                        uint32_t v = 0;
-                        for (int b = 0; b < 4; ++b) { const int o = w * 4 + b; if (o < D) v |= (uint32_t)qrow[o] << (8 * b); }
-                        qd[w] = v;
-                    }
-                }
-            }
-            for (int i2 = tid; i2 < n2; i2 += SFI_THREADS) {
-                const unsigned short cc = tcell[i2];
-                if (cc == 0xffff) continue;
-                const int cx = cc >> 8, cy = cc & 0xff;
-                if (cx < c0 || cx > c1 || cy < r0 || cy > r1) continue;
-                const float dx = __fsub_rn(tx[i2], x), dy = __fsub_rn(ty[i2], y);
+        if (window_cells(qx, qy, window, minX, minY, invW, invH, c0, c1, r0, r1)) {
+            const int s0 = colstart[c0], s1 = colstart[c1 + 1];
+            for (int sl = s0 + tid; sl < s1; sl += SFI_THREADS) {
+                const int cy = S.scell[sl] & 0xff;
+                if (cy < r0 || cy > r1) continue;
+                const float dx = __fsub_rn(S.sx[sl], qx), dy = __fsub_rn(S.sy[sl], qy);
                 if (!(fabsf(dx) < window && fabsf(dy) < window)) continue;
                 float dist;
+                const int i2 = S.sorig[sl];
                 if (desc_type == AFV_FEAT_SIFT128) dist = l2sqr128((const float*)(d1 + (long long)i1 * D), (const float*)(d2 + (long long)i2 * D));
                 else if (stage_desc) {
-                    const uint32_t* y32 = reinterpret_cast<const uint32_t*>(tdesc) + (long long)i2 * nw;
+                    const uint32_t* y32 = reinterpret_cast<const uint32_t*>(S.sdesc) + (long long)sl * nw;
                     int d = 0;
-                    for (int w = 0; w < nw; ++w) d += __popc(qd[w] ^ y32[w]);
+#pragma unroll
+                    for (int w = 0; w < 16; ++w) if (w < nw) d += __popc(qd[w] ^ y32[w]);
                     dist = (float)d;
                 } else dist = (float)hamming_bytes(d1 + (long long)i1 * D, d2 + (long long)i2 * D, D);
-                if (matchedDist[i2] <= dist) continue;                // :511-512
-                top2_push(t, make_key(dist, ((uint32_t)cx << 26) | ((uint32_t)cy << 20) | (uint32_t)i2));
+                if (S.matched[sl] <= dist) continue;                  // :511-512
+                // order key = reference enumeration order (cell x, cell y, keypoint index); slot rides along
+                top2_push(t, make_key(dist, ((uint32_t)(S.scell[sl] >> 8) << 26) | ((uint32_t)cy << 20) | (uint32_t)i2));
             }
         }
         top2_warp_reduce(t);
@@ -356,31 +415,37 @@ __global__ void __launch_bounds__(SFI_THREADS) k_search_init(int desc_type, int 
             for (int w = 1; w < SFI_THREADS / 32; ++w) { top2_push(r, wtop[w].k1); top2_push(r, wtop[w].k2); }
             if (r.k1 != KEY_NONE) {
                 const float bestDist = key_dist(r.k1), bestDist2 = key_dist(r.k2);
-                const int bestIdx2 = (int)((uint32_t)r.k1 & 0xfffffu);
                 if (bestDist <= th_low && bestDist < __fmul_rn(bestDist2, nnratio)) {       // :526-528
-                    if (m21[bestIdx2] >= 0) { m12[m21[bestIdx2]] = -1; s_nm--; }
-                    m12[i1] = bestIdx2; m21[bestIdx2] = i1; matchedDist[bestIdx2] = bestDist; s_nm++;
-                    if (check_ori) { const int bin = rot_bin(k1[i1].angle, k2[bestIdx2].angle); hbin[i1] = (signed char)bin; hist[bin]++; }
+                    const int bestIdx2 = (int)((uint32_t)r.k1 & 0xfffffu);
+                    // slot of bestIdx2: search its column segment (a handful of entries)
+                    const int bcx = (int)(((uint32_t)r.k1) >> 26);
+                    int sl = colstart[bcx];
+                    while (S.sorig[sl] != bestIdx2) ++sl;
+                    if (S.m21[sl] >= 0) { S.m12[S.m21[sl]] = -1; s_nm--; }
+                    S.m12[i1] = bestIdx2; S.m21[sl] = i1; S.matched[sl] = bestDist; s_nm++;
+                    if (check_ori) { const int bin = rot_bin(qa, S.sang[sl]); S.hbin[i1] = (signed char)bin; hist[bin]++; }
                 }
             }
         }
         __syncthreads();
     }
     if (check_ori) {
-        __shared__ int keepbin[3];
         if (tid == 0) three_maxima(hist, keepbin[0], keepbin[1], keepbin[2]);
         __syncthreads();
         int removed = 0;
         for (int i = tid; i < n1; i += SFI_THREADS) {
-            const int b = hbin[i];
+            const int b = S.hbin[i];
             if (b < 0 || b == keepbin[0] || b == keepbin[1] || b == keepbin[2]) continue;
-            if (m12[i] >= 0) { m12[i] = -1; ++removed; }
+            if (S.m12[i] >= 0) { S.m12[i] = -1; ++removed; }
         }
         if (removed) atomicSub(&s_nm, removed);
         __syncthreads();
     }
-    if (pm) for (int i = tid; i < n1; i += SFI_THREADS)                       // :552-554
-        if (m12[i] >= 0) { pm[2 * i] = k2[m12[i]].x; pm[2 * i + 1] = k2[m12[i]].y; }
+    for (int i = tid; i < n1; i += SFI_THREADS) {
+        const int m = S.m12[i];
+        m12g[i] = m;
+        if (pm && m >= 0) { pm[2 * i] = k2[m].x; pm[2 * i + 1] = k2[m].y; }                 // :552-554
+    }
     if (tid == 0) nmatches[p] = s_nm;
 }
 
@@ -393,9 +458,10 @@ extern "C" int afv_search_for_initialization(int desc_type, const afv_keypoint* 
     if (D < 0 || !d_kps || !d_desc || !d_kpsize || !d_n || !d_pair_a || !d_pair_b || !d_matches12 ||
         !d_nmatches || B < 1 || P < 0 || cap < 1) { afv_set_error("afv_search_for_initialization: bad argument"); return AFV_ERR_INVALID; }
     if (P == 0) return AFV_OK;
-    if (cap >= (1 << 20)) { afv_set_error("cap too large for the order key"); return AFV_ERR_INVALID; }
+    if (cap >= 65535) { afv_set_error("cap too large for the 16-bit slot indices"); return AFV_ERR_INVALID; }
     const int Dpad = (D + 3) & ~3;
-    size_t base = (((size_t)cap * (4 + 4 + 4 + 4 + 2 + 1)) + 15) & ~(size_t)15;
+    const size_t base = sfi_base_bytes(cap);
+    if (base > 200 * 1024) { afv_set_error("cap %d too large for the shared-memory staging", cap); return AFV_ERR_INVALID; }
     int stage = desc_type != AFV_FEAT_SIFT128 && Dpad <= 64 && base + (size_t)cap * Dpad <= 200 * 1024;
     size_t smem = base + (stage ? (size_t)cap * Dpad : 0);
     static size_t configured = 0;

@@ -79,9 +79,23 @@ __device__ __forceinline__ bool has_arc9(uint32_t m) {
 #define CIRC16(F) F(0, 0, 3) F(1, 1, 3) F(2, 2, 2) F(3, 3, 1) F(4, 3, 0) F(5, 3, -1) F(6, 2, -2) F(7, 1, -3) \
                   F(8, 0, -3) F(9, -1, -3) F(10, -2, -2) F(11, -3, -1) F(12, -3, 0) F(13, -3, 1) F(14, -2, 2) F(15, -1, 3)
 
+// Byte-parallel segment test: one work item = 4 horizontally adjacent pixels held in one aligned 32-bit shared
+// word.  The 16 circle points of the 4 pixels are 16 words built with funnel shifts from the 3 aligned words of
+// each of the 7 rows; brighter / darker flags are per-byte 0xFF/0x00 lanes (__vcmpgtu4 / __vcmpltu4 against the
+// saturated v+t / v-t), and "9 contiguous of 16" is three rounds of 3-input ANDs on those lanes.
+#define FT_WP 36                      // words per staged row: [pad][34 data words][pad]
+__device__ __forceinline__ uint32_t arc9_lanes(const uint32_t* f) {      // f[k]: per-byte flags of circle point k
+    uint32_t a3[16], any = 0;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) a3[k] = f[k] & f[(k + 1) & 15] & f[(k + 2) & 15];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) any |= a3[k] & a3[(k + 3) & 15] & a3[(k + 6) & 15];
+    return any;
+}
+
 __global__ void __launch_bounds__(256) k_fast(const __grid_constant__ AfvParams P, const __grid_constant__ FastTiles T) {
-    __shared__ __align__(16) uint8_t pix[FT_PH][FT_PW];
-    __shared__ uint8_t score[FT_RH][FT_SW];
+    __shared__ __align__(16) uint32_t pixw[FT_PH][FT_WP];
+    __shared__ __align__(4) uint8_t score[FT_RH][FT_SW];
     __shared__ uint16_t clist[FT_RW * FT_RH];
     __shared__ uint32_t surv[(FT_W / 2) * (FT_H / 2) + 64];
     __shared__ int ncorner, nsurv, gbase;
@@ -98,50 +112,77 @@ __global__ void __launch_bounds__(256) k_fast(const __grid_constant__ AfvParams 
     const int t = P.fast_th;
 
     if (tid == 0) { ncorner = 0; nsurv = 0; }
-    // stage the pixel tile (aligned 32-bit loads; rows outside the image read as 0)
-    for (int i = tid; i < FT_PH * (FT_PW / 4); i += 256) {
-        const int r = i / (FT_PW / 4), c4 = i % (FT_PW / 4);
-        const int gy = y0 - 4 + r, gx = x0 - 4 + c4 * 4;
+    // stage the pixel tile: data word q (pixels x0-4+4q ..) lives at pixw[r][q+1]; rows outside the image read as 0
+    for (int i = tid; i < FT_PH * FT_WP; i += 256) {
+        const int r = i / FT_WP, q = i % FT_WP - 1;
+        const int gy = y0 - 4 + r, gx = x0 - 4 + q * 4;
         uint32_t v = 0;
-        if (gy >= 0 && gy < L.h && gx >= 0 && gx < L.img_stride)
+        if (q >= 0 && q < FT_PW / 4 && gy >= 0 && gy < L.h && gx >= 0 && gx < L.img_stride)
             v = *reinterpret_cast<const uint32_t*>(img + (long long)gy * L.img_stride + gx);
-        *reinterpret_cast<uint32_t*>(&pix[r][c4 * 4]) = v;
+        pixw[r][q + 1] = v;
     }
     for (int i = tid; i < FT_RH * FT_SW / 4; i += 256) reinterpret_cast<uint32_t*>(&score[0][0])[i] = 0;
     __syncthreads();
 
-    // segment test on the score region (tile + 1 ring)
-    for (int i = tid; i < FT_RW * FT_RH; i += 256) {
-        const int r = i / FT_RW, c = i % FT_RW;
-        const int gx = x0 - 1 + c, gy = y0 - 1 + r;
-        if (gx < 3 || gy < 3 || gx >= L.w - 3 || gy >= L.h - 3) continue;
-        const uint8_t* p = &pix[r + 3][c + 3];
-        const int v = p[0], hi = v + t, lo = v - t;
-        const int p0 = p[3 * FT_PW], p8 = p[-3 * FT_PW];
-        if (!((p0 > hi) | (p0 < lo) | (p8 > hi) | (p8 < lo))) continue;
-        const int p4 = p[3], p12 = p[-3];
-        if (!((p4 > hi) | (p4 < lo) | (p12 > hi) | (p12 < lo))) continue;
-        uint32_t br = 0, dk = 0;
-#define FMASK(k, dx, dy) { const int q = p[(dy) * FT_PW + (dx)]; br |= (uint32_t)(q > hi) << k; dk |= (uint32_t)(q < lo) << k; }
-        CIRC16(FMASK)
-#undef FMASK
-        if (has_arc9(br) || has_arc9(dk)) clist[atomicAdd(&ncorner, 1)] = (uint16_t)i;
+    const uint32_t t4 = (uint32_t)t * 0x01010101u;
+    for (int u = tid; u < FT_RH * (FT_PW / 4); u += 256) {
+        const int rr = u / (FT_PW / 4), Q = u % (FT_PW / 4);
+        const int gy = y0 - 1 + rr;
+        if (gy < 3 || gy >= L.h - 3) continue;
+        const int gx0 = x0 - 4 + 4 * Q;
+        // lanes that are real centres: inside the score region [x0-1, x0+FT_W] and 3 px away from the border
+        uint32_t valid = 0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int gx = gx0 + j, c = 4 * Q + j - 3;
+            if (c >= 0 && c < FT_RW && gx >= 3 && gx < L.w - 3) valid |= 0xffu << (8 * j);
+        }
+        if (!valid) continue;
+        const int R = rr + 3;
+#define ROWP(dy) (&pixw[R + (dy)][Q])
+#define PT(dx, dy) ((dx) == 0 ? ROWP(dy)[1] : (dx) > 0 ? __funnelshift_r(ROWP(dy)[1], ROWP(dy)[2], 8 * (dx)) \
+                                                        : __funnelshift_r(ROWP(dy)[0], ROWP(dy)[1], 8 * (4 + (dx))))
+        const uint32_t v4 = ROWP(0)[1];
+        const uint32_t hi4 = __vaddus4(v4, t4), lo4 = __vsubus4(v4, t4);
+#define BR(p) __vcmpgtu4((p), hi4)
+#define DK(p) __vcmpltu4((p), lo4)
+        const uint32_t p0 = PT(0, 3), p8 = PT(0, -3);
+        uint32_t cont = valid & (BR(p0) | DK(p0) | BR(p8) | DK(p8));
+        if (!cont) continue;
+        const uint32_t p4 = PT(3, 0), p12 = PT(-3, 0);
+        cont &= BR(p4) | DK(p4) | BR(p12) | DK(p12);
+        if (!cont) continue;
+        uint32_t fb[16], fd[16];
+#define FLAGS(k, dx, dy) { const uint32_t q_ = PT(dx, dy); fb[k] = BR(q_); fd[k] = DK(q_); }
+        CIRC16(FLAGS)
+#undef FLAGS
+        const uint32_t corner = cont & (arc9_lanes(fb) | arc9_lanes(fd));
+#undef BR
+#undef DK
+#undef PT
+#undef ROWP
+        if (corner) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (corner & (0x80u << (8 * j))) clist[atomicAdd(&ncorner, 1)] = (uint16_t)(rr * FT_RW + 4 * Q + j - 3);
+        }
     }
     __syncthreads();
 
     // corner score = max over the 16 arcs of 9 of min|v - p| (same sign), minus 1 (OpenCV cornerScore<16>)
+    const uint8_t* pb = reinterpret_cast<const uint8_t*>(&pixw[0][0]);
     const int nc = ncorner;
     for (int j = tid; j < nc; j += 256) {
         const int i = clist[j];
         const int r = i / FT_RW, c = i % FT_RW;
-        const uint8_t* p = &pix[r + 3][c + 3];
+        const uint8_t* p = pb + (r + 3) * (FT_WP * 4) + 4 + (c + 3);
         const int v = p[0];
         // d[k] = v - p[k] in [-255,255]: packed as (d, -d) in the two signed 16-bit halves so one __vmins2 chain
         // gives both min(d) (darker arcs) and min(-d) (brighter arcs); sliding minimum over 9 by doubling.
         // NB: the scalar form max(min9(d), -max9(d)) is MISCOMPILED by nvcc 12.9 / ptxas for sm_100a (3-input
         // VIMNMX3 with a negated operand; repro in tools/dbg/minmax_dbg.cu) - keep this formulation.
         uint32_t e[16];
-#define FDIFF(k, dx, dy) { const int dv = v - (int)p[(dy) * FT_PW + (dx)]; e[k] = ((uint32_t)dv & 0xffffu) | ((uint32_t)(-dv) << 16); }
+#define FDIFF(k, dx, dy) { const int dv = v - (int)p[(dy) * (FT_WP * 4) + (dx)]; e[k] = ((uint32_t)dv & 0xffffu) | ((uint32_t)(-dv) << 16); }
         CIRC16(FDIFF)
 #undef FDIFF
         uint32_t m2[16], m4[16];
@@ -583,9 +624,13 @@ size_t afv_octree_smem_bytes(int mcap, int ncap) {
 __constant__ float c_g7[7] = {0x1.1f5f62p-4f, 0x1.0c70fcp-3f, 0x1.869472p-3f, 0x1.ba95cp-3f,
                               0x1.869472p-3f, 0x1.0c70fcp-3f, 0x1.1f5f62p-4f};
 
+// Staged input: rows y0-3 .. y0+BT_H+2, byte columns x0-4 .. x0+BT_W+3 as 34 aligned words per row (interior
+// tiles: straight 32-bit loads; border tiles: per-byte REFLECT_101 gather).  Row pass: one thread = 4 outputs
+// from 3 words; column pass: one thread = 4 columns x 2 rows from 8 float4 rows.
+#define BT_WW ((BT_W + 8) / 4)
 __global__ void __launch_bounds__(256) k_blur(const __grid_constant__ AfvParams P, const __grid_constant__ FastTiles T) {
-    __shared__ uint8_t in[BT_H + 6][BT_W + 8];
-    __shared__ float mid[BT_H + 6][BT_W];
+    __shared__ __align__(16) uint32_t in[BT_H + 6][BT_WW + 2];
+    __shared__ __align__(16) float mid[BT_H + 6][BT_W];
     int l = 0;
     while (l + 1 < P.nlevels && (int)blockIdx.x >= T.start[l + 1]) ++l;
     const AfvLevel& L = P.lv[l];
@@ -594,36 +639,70 @@ __global__ void __launch_bounds__(256) k_blur(const __grid_constant__ AfvParams 
     const int f = blockIdx.y, tid = threadIdx.x;
     const int x0 = tx * BT_W, y0 = ty * BT_H;
     const uint8_t* img = L.img + (long long)f * L.img_fstride;
-    for (int i = tid; i < (BT_H + 6) * (BT_W + 6); i += 256) {
-        const int r = i / (BT_W + 6), c = i % (BT_W + 6);
-        in[r][c] = img[(long long)refl101(y0 - 3 + r, L.h) * L.img_stride + refl101(x0 - 3 + c, L.w)];
+    const bool interior = x0 >= 4 && y0 >= 3 && x0 + BT_W + 4 <= L.w && y0 + BT_H + 3 <= L.h;
+    if (interior) {
+        for (int i = tid; i < (BT_H + 6) * BT_WW; i += 256) {
+            const int r = i / BT_WW, q = i % BT_WW;
+            in[r][q] = *reinterpret_cast<const uint32_t*>(img + (long long)(y0 - 3 + r) * L.img_stride + x0 - 4 + 4 * q);
+        }
+    } else {
+        for (int i = tid; i < (BT_H + 6) * BT_WW; i += 256) {
+            const int r = i / BT_WW, q = i % BT_WW;
+            const uint8_t* row = img + (long long)refl101(y0 - 3 + r, L.h) * L.img_stride;
+            uint32_t v = 0;
+#pragma unroll
+            for (int b2 = 0; b2 < 4; ++b2) v |= (uint32_t)row[refl101(x0 - 4 + 4 * q + b2, L.w)] << (8 * b2);
+            in[r][q] = v;
+        }
     }
     __syncthreads();
-    for (int i = tid; i < (BT_H + 6) * BT_W; i += 256) {
-        const int r = i / BT_W, c = i % BT_W;
-        float s = __fmul_rn(c_g7[0], (float)in[r][c]);
+    // row pass: outputs 4q..4q+3 need staged bytes 4q+1 .. 4q+10
+    for (int i = tid; i < (BT_H + 6) * (BT_W / 4); i += 256) {
+        const int r = i / (BT_W / 4), q = i % (BT_W / 4);
+        const uint32_t w0 = in[r][q], w1 = in[r][q + 1], w2 = in[r][q + 2];
+        float pf[10];
+        pf[0] = (float)((w0 >> 8) & 0xff); pf[1] = (float)((w0 >> 16) & 0xff); pf[2] = (float)(w0 >> 24);
+        pf[3] = (float)(w1 & 0xff); pf[4] = (float)((w1 >> 8) & 0xff); pf[5] = (float)((w1 >> 16) & 0xff); pf[6] = (float)(w1 >> 24);
+        pf[7] = (float)(w2 & 0xff); pf[8] = (float)((w2 >> 8) & 0xff); pf[9] = (float)((w2 >> 16) & 0xff);
+        float4 o;
+        float* op = &o.x;
 #pragma unroll
-        for (int k = 1; k < 7; ++k) s = __fmaf_rn(c_g7[k], (float)in[r][c + k], s);
-        mid[r][c] = s;
+        for (int k = 0; k < 4; ++k) {
+            float sacc = __fmul_rn(c_g7[0], pf[k]);
+#pragma unroll
+            for (int j = 1; j < 7; ++j) sacc = __fmaf_rn(c_g7[j], pf[k + j], sacc);
+            op[k] = sacc;
+        }
+        *reinterpret_cast<float4*>(&mid[r][4 * q]) = o;
     }
     __syncthreads();
     uint8_t* out = L.blur + (long long)f * L.fstride;
-    for (int i = tid; i < BT_H * (BT_W / 4); i += 256) {
-        const int r = i / (BT_W / 4), c4 = (i % (BT_W / 4)) * 4;
-        const int gy = y0 + r, gx = x0 + c4;
-        if (gy >= L.h || gx >= L.w) continue;
-        uint32_t pk = 0;
+    {
+        const int q = tid % (BT_W / 4), rg = tid / (BT_W / 4);       // 32 column quads x 8 row pairs
+        const int gx = x0 + 4 * q;
+        if (gx < L.w) {
+            float4 m[8];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const int c = c4 + k;
-            float s = __fmul_rn(c_g7[3], mid[r + 3][c]);
+            for (int j = 0; j < 8; ++j) m[j] = *reinterpret_cast<const float4*>(&mid[2 * rg + j][4 * q]);
 #pragma unroll
-            for (int j = 1; j <= 3; ++j) s = __fmaf_rn(c_g7[3 + j], __fadd_rn(mid[r + 3 + j][c], mid[r + 3 - j][c]), s);
-            int v = __float2int_rn(s);
-            v = min(max(v, 0), 255);
-            pk |= (uint32_t)v << (8 * k);
+            for (int rr = 0; rr < 2; ++rr) {
+                const int gy = y0 + 2 * rg + rr;
+                if (gy >= L.h) break;
+                uint32_t pk = 0;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const float c0 = (&m[rr + 3].x)[k];
+                    float sacc = __fmul_rn(c_g7[3], c0);
+#pragma unroll
+                    for (int j = 1; j <= 3; ++j)
+                        sacc = __fmaf_rn(c_g7[3 + j], __fadd_rn((&m[rr + 3 + j].x)[k], (&m[rr + 3 - j].x)[k]), sacc);
+                    int v = __float2int_rn(sacc);
+                    v = min(max(v, 0), 255);
+                    pk |= (uint32_t)v << (8 * k);
+                }
+                *reinterpret_cast<uint32_t*>(out + (long long)gy * L.stride + gx) = pk;
+            }
         }
-        *reinterpret_cast<uint32_t*>(out + (long long)gy * L.stride + gx) = pk;
     }
 }
 
