@@ -260,13 +260,21 @@ __device__ __forceinline__ void three_maxima(const int* cnt, int& ind1, int& ind
 }
 
 // Shared-memory plan (cap = per-frame capacity, Dpad = descriptor bytes padded to 4):
-//   train keypoints are staged SORTED BY GRID COLUMN (counting sort, 64 bins) so a query only scans the slots of
-//   its cell-column range; slot order inside a column is arbitrary - ties are decided by the explicit order key.
-struct SfiSmem {
-    float* sx; float* sy; float* sang; float* matched; int* m21; int* m12;
-    unsigned short* scell; unsigned short* sorig; unsigned short* qlist; signed char* hbin; uint8_t* sdesc;
-};
-__host__ __device__ inline size_t sfi_base_bytes(int cap) { return (((size_t)cap * (4 * 6 + 2 * 3 + 1)) + 15) & ~(size_t)15; }
+//   * the train frame is staged SORTED BY GRID COLUMN (counting sort, 64 bins) so a query only scans the slots of
+//     its cell-column range; slot order inside a column is arbitrary - ties are decided by the explicit order key;
+//   * phase 1 (parallel, one thread per query): top-SFI_K candidates of every query by (distance, reference
+//     enumeration order), IGNORING the sequential "already matched" state, plus the query's candidate count;
+//   * phase 2 (one warp, queries in index order): the reference's sequential rule skips candidates whose recorded
+//     match distance is <= this distance (:511-512); the first two surviving entries of the sorted top-K list are
+//     exactly (best, second) whenever two survive or the list holds all candidates - otherwise the warp rescans
+//     that one query with the live state (exact fallback).  Acceptance, match stealing and the rotation histogram
+//     are then applied by lane 0 as in the reference.
+#define SFI_K 4
+#define SFI_TOPQ 512
+__host__ __device__ inline size_t sfi_base_bytes(int cap) { return (((size_t)cap * (4 * 4 + 2 * 6 + 1)) + 15) & ~(size_t)15; }
+__host__ __device__ inline size_t sfi_topk_bytes() { return (size_t)SFI_TOPQ * (SFI_K * 8 + 4 + 2); }
+
+struct SfiQuery { float x, y; int c0, c1, r0, r1; bool ok; };
 
 __global__ void __launch_bounds__(SFI_THREADS) k_search_init(int desc_type, int D, int Dpad, int stage_desc,
         const afv_keypoint* __restrict__ kps, const uint8_t* __restrict__ desc, const float* __restrict__ kpsize,
@@ -286,17 +294,20 @@ __global__ void __launch_bounds__(SFI_THREADS) k_search_init(int desc_type, int 
     float* pm = prev_matched ? prev_matched + (long long)p * cap * 2 : nullptr;
     int* m12g = matches12 + (long long)p * cap;
 
-    SfiSmem S;
-    S.sx = reinterpret_cast<float*>(sm); S.sy = S.sx + cap; S.sang = S.sy + cap; S.matched = S.sang + cap;
-    S.m21 = reinterpret_cast<int*>(S.matched + cap); S.m12 = S.m21 + cap;
-    S.scell = reinterpret_cast<unsigned short*>(S.m12 + cap); S.sorig = S.scell + cap; S.qlist = S.sorig + cap;
-    S.hbin = reinterpret_cast<signed char*>(S.qlist + cap);
-    S.sdesc = sm + sfi_base_bytes(cap);
-    __shared__ Top2 wtop[SFI_THREADS / 32];
+    float* sx = reinterpret_cast<float*>(sm); float* sy = sx + cap; float* sang = sy + cap; float* matched = sang + cap;
+    unsigned short* m21 = reinterpret_cast<unsigned short*>(matched + cap);
+    unsigned short* m12 = m21 + cap; unsigned short* scell = m12 + cap; unsigned short* sorig = scell + cap;
+    unsigned short* qlist = sorig + cap; unsigned short* slotof = qlist + cap;
+    signed char* hbin = reinterpret_cast<signed char*>(slotof + cap);
+    uint8_t* sdesc = sm + sfi_base_bytes(cap);
+    unsigned long long* topk = reinterpret_cast<unsigned long long*>(sdesc + (stage_desc ? (size_t)cap * Dpad : 0));
+    float* qangle = reinterpret_cast<float*>(topk + SFI_TOPQ * SFI_K);
+    unsigned short* qncand = reinterpret_cast<unsigned short*>(qangle + SFI_TOPQ);
     __shared__ int hist[AFV_HISTO_LENGTH];
     __shared__ int colstart[AFV_GRID_COLS + 1], colfill[AFV_GRID_COLS];
     __shared__ int s_nm, s_nq, keepbin[3];
     const int nw = Dpad / 4;
+    const unsigned short NONE16 = 0xffff;
 
     // ---- prologue: column histogram -> counting sort of the train frame; query list = octave-0 keypoints
     if (tid < AFV_GRID_COLS) { colstart[tid] = 0; colfill[tid] = 0; }
@@ -308,14 +319,13 @@ __global__ void __launch_bounds__(SFI_THREADS) k_search_init(int desc_type, int 
         const int c = grid_cell(k2[i].x, k2[i].y, minX, minY, invW, invH);
         // GetFeaturesInArea(..., minSize 0, maxSize F1.maxKeyPtSize) size gate folded in (:495-496, Frame.cc:365-368)
         const bool ok = c >= 0 && !(sz < 0.0f) && !(sz > max_kpt_size);
-        S.m21[i] = ok ? c : -1;                                     // temp: cell id
+        m21[i] = ok ? (unsigned short)c : NONE16;                   // temp: cell id
         if (ok) atomicAdd(&colstart[c / AFV_GRID_ROWS + 1], 1);
     }
-    for (int i = tid; i < n1; i += SFI_THREADS) S.m12[i] = (k1[i].octave > 0) ? -2 : -1;      // -2: never a query
+    for (int i = tid; i < n1; i += SFI_THREADS) m12[i] = (k1[i].octave > 0) ? 1 : 0;          // temp: 0 = query (:491-493)
     __syncthreads();
     if (wid == 0) {                                                 // inclusive scan of 64 column counts
-        int v0 = colstart[1 + lane], v1 = colstart[33 + lane];
-        int a0 = v0, a1 = v1;
+        int a0 = colstart[1 + lane], a1 = colstart[33 + lane];
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) { int t0 = __shfl_up_sync(0xffffffffu, a0, o), t1 = __shfl_up_sync(0xffffffffu, a1, o); if (lane >= o) { a0 += t0; a1 += t1; } }
         const int tot0 = __shfl_sync(0xffffffffu, a0, 31);
@@ -325,106 +335,158 @@ __global__ void __launch_bounds__(SFI_THREADS) k_search_init(int desc_type, int 
         int base = 0;
         for (int i0 = 0; i0 < n1; i0 += 32) {
             const int i = i0 + lane;
-            const bool q = i < n1 && S.m12[i] == -1;
+            const bool q = i < n1 && m12[i] == 0;
             const unsigned m = __ballot_sync(0xffffffffu, q);
-            if (q) S.qlist[base + __popc(m & ((1u << lane) - 1))] = (unsigned short)i;
+            if (q) qlist[base + __popc(m & ((1u << lane) - 1))] = (unsigned short)i;
             base += __popc(m);
         }
         if (lane == 0) s_nq = base;
     }
     __syncthreads();
     for (int i = tid; i < n2; i += SFI_THREADS) {
-        const int c = S.m21[i];
-        if (c < 0) continue;
+        const int c = m21[i];
+        if (c == NONE16) continue;
         const int cx = c / AFV_GRID_ROWS;
         const int slot = colstart[cx] + atomicAdd(&colfill[cx], 1);
-        S.sx[slot] = k2[i].x; S.sy[slot] = k2[i].y; S.sang[slot] = k2[i].angle;
-        S.scell[slot] = (unsigned short)((cx << 8) | (c % AFV_GRID_ROWS));
-        S.sorig[slot] = (unsigned short)i;
+        sx[slot] = k2[i].x; sy[slot] = k2[i].y; sang[slot] = k2[i].angle;
+        scell[slot] = (unsigned short)((cx << 8) | (c % AFV_GRID_ROWS));
+        sorig[slot] = (unsigned short)i; slotof[i] = (unsigned short)slot;
     }
     __syncthreads();
     const int n2s = colstart[AFV_GRID_COLS];
-    for (int i = tid; i < n2s; i += SFI_THREADS) { S.matched[i] = FLT_MAX; S.m21[i] = -1; }
-    for (int i = tid; i < n1; i += SFI_THREADS) { S.hbin[i] = -1; if (S.m12[i] == -2) S.m12[i] = -1; }
+    for (int i = tid; i < n2s; i += SFI_THREADS) { matched[i] = FLT_MAX; m21[i] = NONE16; }
+    for (int i = tid; i < n1; i += SFI_THREADS) { hbin[i] = -1; m12[i] = NONE16; }
     if (stage_desc) {
         for (int i = tid; i < n2s * nw; i += SFI_THREADS) {
             const int r = i / nw, w = i % nw;
-            const uint8_t* row = d2 + (long long)S.sorig[r] * D;
+            const uint8_t* row = d2 + (long long)sorig[r] * D;
             uint32_t v;
             if ((D & 3) == 0) v = reinterpret_cast<const uint32_t*>(row)[w];
             else { v = 0; for (int b = 0; b < 4; ++b) { const int o = w * 4 + b; if (o < D) v |= (uint32_t)row[o] << (8 * b); } }
-            reinterpret_cast<uint32_t*>(S.sdesc)[i] = v;
+            reinterpret_cast<uint32_t*>(sdesc)[i] = v;
         }
     }
     __syncthreads();
 
-    // ---- queries in index order; the next query's descriptor / position / angle are prefetched
-    const int nq = s_nq;
-    uint32_t qd[16], qdn[16];
-    float qx = 0, qy = 0, qa = 0, qxn = 0, qyn = 0, qan = 0;
-    auto load_query = [&](int qi, uint32_t* dst, float& x, float& y, float& a) {
-        const int i1 = S.qlist[qi];
-        x = pm ? pm[2 * i1] : k1[i1].x; y = pm ? pm[2 * i1 + 1] : k1[i1].y; a = k1[i1].angle;
-        if (desc_type != AFV_FEAT_SIFT128) {
-            const uint8_t* qrow = d1 + (long long)i1 * D;
-            if ((D & 3) == 0) {
+    auto query_setup = [&](int i1) {
+        SfiQuery q;
+        q.x = pm ? pm[2 * i1] : k1[i1].x; q.y = pm ? pm[2 * i1 + 1] : k1[i1].y;
+        q.ok = window_cells(q.x, q.y, window, minX, minY, invW, invH, q.c0, q.c1, q.r0, q.r1);
+        return q;
+    };
+    auto load_desc = [&](int i1, uint32_t* dst) {
+        const uint8_t* qrow = d1 + (long long)i1 * D;
+        if ((D & 3) == 0) {
 #pragma unroll
-                for (int w = 0; w < 16; ++w) if (w < nw) dst[w] = reinterpret_cast<const uint32_t*>(qrow)[w];
-            } else {
+            for (int w = 0; w < 16; ++w) if (w < nw) dst[w] = reinterpret_cast<const uint32_t*>(qrow)[w];
+        } else {
 #pragma unroll
-                for (int w = 0; w < 16; ++w) if (w < nw) { uint32_t v = 0; for (int b = 0; b < 4; ++b) { const int o = w * 4 + b; if (o < D) v |= (uint32_t)qrow[o] << (8 * b); } dst[w] = v; }
-            }
+            for (int w = 0; w < 16; ++w) if (w < nw) { uint32_t v = 0; for (int b = 0; b < 4; ++b) { const int o = w * 4 + b; if (o < D) v |= (uint32_t)qrow[o] << (8 * b); } dst[w] = v; }
         }
     };
-    if (nq > 0) load_query(0, qdn, qxn, qyn, qan);
-    for (int qi = 0; qi < nq; ++qi) {
-        const int i1 = S.qlist[qi];
+    // distance of query (descriptor words qd / index i1) to the train keypoint in slot sl, or -1 when it is no candidate
+    auto cand_dist = [&](const SfiQuery& q, const uint32_t* qd, int i1, int sl, uint32_t& order) -> float {
+        const unsigned short cc = scell[sl];
+        const int cy = cc & 0xff;
+        if (cy < q.r0 || cy > q.r1) return -1.0f;
+        const float dx = __fsub_rn(sx[sl], q.x), dy = __fsub_rn(sy[sl], q.y);
+        if (!(fabsf(dx) < window && fabsf(dy) < window)) return -1.0f;
+        const int i2 = sorig[sl];
+        order = ((uint32_t)(cc >> 8) << 26) | ((uint32_t)cy << 20) | (uint32_t)i2;     // reference enumeration order
+        if (desc_type == AFV_FEAT_SIFT128) return l2sqr128((const float*)(d1 + (long long)i1 * D), (const float*)(d2 + (long long)i2 * D));
+        if (stage_desc) {
+            const uint32_t* y32 = reinterpret_cast<const uint32_t*>(sdesc) + (long long)sl * nw;
+            int d = 0;
 #pragma unroll
-        for (int w = 0; w < 16; ++w) qd[w] = qdn[w];
-        qx = qxn; qy = qyn; qa = qan;
-        if (qi + 1 < nq) load_query(qi + 1, qdn, qxn, qyn, qan);
-        int c0, c1, r0, r1;
-        Top2 t; t.k1 = t.k2 = KEY_NONE;
-        if (window_cells(qx, qy, window, minX, minY, invW, invH, c0, c1, r0, r1)) {
-            const int s0 = colstart[c0], s1 = colstart[c1 + 1];
-            for (int sl = s0 + tid; sl < s1; sl += SFI_THREADS) {
-                const int cy = S.scell[sl] & 0xff;
-                if (cy < r0 || cy > r1) continue;
-                const float dx = __fsub_rn(S.sx[sl], qx), dy = __fsub_rn(S.sy[sl], qy);
-                if (!(fabsf(dx) < window && fabsf(dy) < window)) continue;
-                float dist;
-                const int i2 = S.sorig[sl];
-                if (desc_type == AFV_FEAT_SIFT128) dist = l2sqr128((const float*)(d1 + (long long)i1 * D), (const float*)(d2 + (long long)i2 * D));
-                else if (stage_desc) {
-                    const uint32_t* y32 = reinterpret_cast<const uint32_t*>(S.sdesc) + (long long)sl * nw;
-                    int d = 0;
-#pragma unroll
-                    for (int w = 0; w < 16; ++w) if (w < nw) d += __popc(qd[w] ^ y32[w]);
-                    dist = (float)d;
-                } else dist = (float)hamming_bytes(d1 + (long long)i1 * D, d2 + (long long)i2 * D, D);
-                if (S.matched[sl] <= dist) continue;                  // :511-512
-                // order key = reference enumeration order (cell x, cell y, keypoint index); slot rides along
-                top2_push(t, make_key(dist, ((uint32_t)(S.scell[sl] >> 8) << 26) | ((uint32_t)cy << 20) | (uint32_t)i2));
-            }
+            for (int w = 0; w < 16; ++w) if (w < nw) d += __popc(qd[w] ^ y32[w]);
+            return (float)d;
         }
-        top2_warp_reduce(t);
-        if (lane == 0) wtop[wid] = t;
-        __syncthreads();
-        if (tid == 0) {
-            Top2 r = wtop[0];
-            for (int w = 1; w < SFI_THREADS / 32; ++w) { top2_push(r, wtop[w].k1); top2_push(r, wtop[w].k2); }
-            if (r.k1 != KEY_NONE) {
-                const float bestDist = key_dist(r.k1), bestDist2 = key_dist(r.k2);
-                if (bestDist <= th_low && bestDist < __fmul_rn(bestDist2, nnratio)) {       // :526-528
-                    const int bestIdx2 = (int)((uint32_t)r.k1 & 0xfffffu);
-                    // slot of bestIdx2: search its column segment (a handful of entries)
-                    const int bcx = (int)(((uint32_t)r.k1) >> 26);
-                    int sl = colstart[bcx];
-                    while (S.sorig[sl] != bestIdx2) ++sl;
-                    if (S.m21[sl] >= 0) { S.m12[S.m21[sl]] = -1; s_nm--; }
-                    S.m12[i1] = bestIdx2; S.m21[sl] = i1; S.matched[sl] = bestDist; s_nm++;
-                    if (check_ori) { const int bin = rot_bin(qa, S.sang[sl]); S.hbin[i1] = (signed char)bin; hist[bin]++; }
+        return (float)hamming_bytes(d1 + (long long)i1 * D, d2 + (long long)i2 * D, D);
+    };
+
+    const int nq = s_nq;
+    for (int qbase = 0; qbase < nq; qbase += SFI_TOPQ) {
+        const int nchunk = min(SFI_TOPQ, nq - qbase);
+        // ---- phase 1: speculative top-K per query (state-free)
+        for (int qi = tid; qi < nchunk; qi += SFI_THREADS) {
+            const int i1 = qlist[qbase + qi];
+            const SfiQuery q = query_setup(i1);
+            unsigned long long tk[SFI_K];
+#pragma unroll
+            for (int j = 0; j < SFI_K; ++j) tk[j] = KEY_NONE;
+            int ncand = 0;
+            if (q.ok) {
+                uint32_t qd[16];
+                if (desc_type != AFV_FEAT_SIFT128) load_desc(i1, qd);
+                const int s0 = colstart[q.c0], s1 = colstart[q.c1 + 1];
+                for (int sl = s0; sl < s1; ++sl) {
+                    uint32_t order;
+                    const float dist = cand_dist(q, qd, i1, sl, order);
+                    if (dist < 0.0f) continue;
+                    ++ncand;
+                    const unsigned long long key = make_key(dist, order);
+                    if (key < tk[SFI_K - 1]) {
+                        tk[SFI_K - 1] = key;
+#pragma unroll
+                        for (int j = SFI_K - 1; j > 0; --j)
+                            if (tk[j] < tk[j - 1]) { const unsigned long long tmp = tk[j]; tk[j] = tk[j - 1]; tk[j - 1] = tmp; }
+                    }
                 }
+            }
+#pragma unroll
+            for (int j = 0; j < SFI_K; ++j) topk[qi * SFI_K + j] = tk[j];
+            qncand[qi] = (unsigned short)min(ncand, 65535);
+            qangle[qi] = k1[i1].angle;
+        }
+        __syncthreads();
+        // ---- phase 2: sequential resolution by warp 0
+        if (wid == 0) {
+            for (int qi = 0; qi < nchunk; ++qi) {
+                const int i1 = qlist[qbase + qi];
+                const int ncand = qncand[qi];
+                if (ncand == 0) continue;
+                unsigned long long key = lane < SFI_K ? topk[qi * SFI_K + lane] : KEY_NONE;
+                bool alive = false;
+                if (key != KEY_NONE) {
+                    const int sl = slotof[(uint32_t)key & 0xfffffu];
+                    alive = !(matched[sl] <= key_dist(key));                        // :511-512
+                }
+                const unsigned am = __ballot_sync(0xffffffffu, alive);
+                unsigned long long k1st = KEY_NONE, k2nd = KEY_NONE;
+                if (__popc(am) >= 2 || ncand <= SFI_K) {
+                    const int l1 = am ? __ffs(am) - 1 : 0;
+                    const unsigned am2 = am & (am - 1);
+                    const int l2 = am2 ? __ffs(am2) - 1 : 0;
+                    const unsigned long long a = __shfl_sync(0xffffffffu, key, l1), b = __shfl_sync(0xffffffffu, key, l2);
+                    if (am) k1st = a;
+                    if (am2) k2nd = b;
+                } else {
+                    // exact fallback: rescan this query with the live state
+                    const SfiQuery q = query_setup(i1);
+                    uint32_t qd[16];
+                    if (desc_type != AFV_FEAT_SIFT128) load_desc(i1, qd);
+                    Top2 t; t.k1 = t.k2 = KEY_NONE;
+                    const int s0 = colstart[q.c0], s1 = colstart[q.c1 + 1];
+                    for (int sl = s0 + lane; sl < s1; sl += 32) {
+                        uint32_t order;
+                        const float dist = cand_dist(q, qd, i1, sl, order);
+                        if (dist < 0.0f || matched[sl] <= dist) continue;
+                        top2_push(t, make_key(dist, order));
+                    }
+                    top2_warp_reduce(t);
+                    k1st = t.k1; k2nd = t.k2;
+                }
+                if (lane == 0 && k1st != KEY_NONE) {
+                    const float bestDist = key_dist(k1st), bestDist2 = key_dist(k2nd);
+                    if (bestDist <= th_low && bestDist < __fmul_rn(bestDist2, nnratio)) {       // :526-528
+                        const int bestIdx2 = (int)((uint32_t)k1st & 0xfffffu);
+                        const int sl = slotof[bestIdx2];
+                        if (m21[sl] != NONE16) { m12[m21[sl]] = NONE16; s_nm--; }             // :530-534
+                        m12[i1] = (unsigned short)bestIdx2; m21[sl] = (unsigned short)i1; matched[sl] = bestDist; s_nm++;
+                        if (check_ori) { const int bin = rot_bin(qangle[qi], sang[sl]); hbin[i1] = (signed char)bin; hist[bin]++; }
+                    }
+                }
+                __syncwarp();
             }
         }
         __syncthreads();
@@ -434,15 +496,15 @@ __global__ void __launch_bounds__(SFI_THREADS) k_search_init(int desc_type, int 
         __syncthreads();
         int removed = 0;
         for (int i = tid; i < n1; i += SFI_THREADS) {
-            const int b = S.hbin[i];
+            const int b = hbin[i];
             if (b < 0 || b == keepbin[0] || b == keepbin[1] || b == keepbin[2]) continue;
-            if (S.m12[i] >= 0) { S.m12[i] = -1; ++removed; }
+            if (m12[i] != NONE16) { m12[i] = NONE16; ++removed; }
         }
         if (removed) atomicSub(&s_nm, removed);
         __syncthreads();
     }
     for (int i = tid; i < n1; i += SFI_THREADS) {
-        const int m = S.m12[i];
+        const int m = m12[i] == NONE16 ? -1 : (int)m12[i];
         m12g[i] = m;
         if (pm && m >= 0) { pm[2 * i] = k2[m].x; pm[2 * i + 1] = k2[m].y; }                 // :552-554
     }
@@ -460,7 +522,7 @@ extern "C" int afv_search_for_initialization(int desc_type, const afv_keypoint* 
     if (P == 0) return AFV_OK;
     if (cap >= 65535) { afv_set_error("cap too large for the 16-bit slot indices"); return AFV_ERR_INVALID; }
     const int Dpad = (D + 3) & ~3;
-    const size_t base = sfi_base_bytes(cap);
+    const size_t base = sfi_base_bytes(cap) + sfi_topk_bytes();
     if (base > 200 * 1024) { afv_set_error("cap %d too large for the shared-memory staging", cap); return AFV_ERR_INVALID; }
     int stage = desc_type != AFV_FEAT_SIFT128 && Dpad <= 64 && base + (size_t)cap * Dpad <= 200 * 1024;
     size_t smem = base + (stage ? (size_t)cap * Dpad : 0);

@@ -79,26 +79,27 @@ __device__ __forceinline__ bool has_arc9(uint32_t m) {
 #define CIRC16(F) F(0, 0, 3) F(1, 1, 3) F(2, 2, 2) F(3, 3, 1) F(4, 3, 0) F(5, 3, -1) F(6, 2, -2) F(7, 1, -3) \
                   F(8, 0, -3) F(9, -1, -3) F(10, -2, -2) F(11, -3, -1) F(12, -3, 0) F(13, -3, 1) F(14, -2, 2) F(15, -1, 3)
 
-// Byte-parallel segment test: one work item = 4 horizontally adjacent pixels held in one aligned 32-bit shared
-// word.  The 16 circle points of the 4 pixels are 16 words built with funnel shifts from the 3 aligned words of
-// each of the 7 rows; brighter / darker flags are per-byte 0xFF/0x00 lanes (__vcmpgtu4 / __vcmpltu4 against the
-// saturated v+t / v-t), and "9 contiguous of 16" is three rounds of 3-input ANDs on those lanes.
+// Two-stage segment test with compaction (keeps warps converged): stage 1 runs the two cheap antipodal-pair
+// rejections on every pixel of the score region and compacts the survivors (warp ballot + one shared atomic per
+// warp); stage 2 builds the two 16-bit brighter/darker masks only for survivors and compacts the corners.
 #define FT_WP 36                      // words per staged row: [pad][34 data words][pad]
-__device__ __forceinline__ uint32_t arc9_lanes(const uint32_t* f) {      // f[k]: per-byte flags of circle point k
-    uint32_t a3[16], any = 0;
-#pragma unroll
-    for (int k = 0; k < 16; ++k) a3[k] = f[k] & f[(k + 1) & 15] & f[(k + 2) & 15];
-#pragma unroll
-    for (int k = 0; k < 16; ++k) any |= a3[k] & a3[(k + 3) & 15] & a3[(k + 6) & 15];
-    return any;
+__device__ __forceinline__ void warp_push(bool pass, uint16_t val, uint16_t* list, int* counter, int lane) {
+    const unsigned m = __ballot_sync(0xffffffffu, pass);
+    if (m == 0) return;
+    int base = 0;
+    const int leader = __ffs(m) - 1;
+    if (lane == leader) base = atomicAdd(counter, __popc(m));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (pass) list[base + __popc(m & ((1u << lane) - 1))] = val;
 }
 
 __global__ void __launch_bounds__(256) k_fast(const __grid_constant__ AfvParams P, const __grid_constant__ FastTiles T) {
     __shared__ __align__(16) uint32_t pixw[FT_PH][FT_WP];
     __shared__ __align__(4) uint8_t score[FT_RH][FT_SW];
-    __shared__ uint16_t clist[FT_RW * FT_RH];
+    __shared__ uint16_t slist[FT_RW * FT_RH];        // stage-1 survivors
+    __shared__ uint16_t clist[FT_RW * FT_RH];        // corners
     __shared__ uint32_t surv[(FT_W / 2) * (FT_H / 2) + 64];
-    __shared__ int ncorner, nsurv, gbase;
+    __shared__ int nstage1, ncorner, nsurv, gbase;
 
     int l = 0;
     while (l + 1 < P.nlevels && (int)blockIdx.x >= T.start[l + 1]) ++l;
@@ -107,11 +108,11 @@ __global__ void __launch_bounds__(256) k_fast(const __grid_constant__ AfvParams 
     const int tx = tile % T.tiles_x[l], ty = tile / T.tiles_x[l];
     const int f = blockIdx.y;
     const int x0 = tx * FT_W, y0 = ty * FT_H;
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31;
     const uint8_t* img = L.img + (long long)f * L.img_fstride;
     const int t = P.fast_th;
 
-    if (tid == 0) { ncorner = 0; nsurv = 0; }
+    if (tid == 0) { nstage1 = 0; ncorner = 0; nsurv = 0; }
     // stage the pixel tile: data word q (pixels x0-4+4q ..) lives at pixw[r][q+1]; rows outside the image read as 0
     for (int i = tid; i < FT_PH * FT_WP; i += 256) {
         const int r = i / FT_WP, q = i % FT_WP - 1;
@@ -124,53 +125,50 @@ __global__ void __launch_bounds__(256) k_fast(const __grid_constant__ AfvParams 
     for (int i = tid; i < FT_RH * FT_SW / 4; i += 256) reinterpret_cast<uint32_t*>(&score[0][0])[i] = 0;
     __syncthreads();
 
-    const uint32_t t4 = (uint32_t)t * 0x01010101u;
-    for (int u = tid; u < FT_RH * (FT_PW / 4); u += 256) {
-        const int rr = u / (FT_PW / 4), Q = u % (FT_PW / 4);
-        const int gy = y0 - 1 + rr;
-        if (gy < 3 || gy >= L.h - 3) continue;
-        const int gx0 = x0 - 4 + 4 * Q;
-        // lanes that are real centres: inside the score region [x0-1, x0+FT_W] and 3 px away from the border
-        uint32_t valid = 0;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int gx = gx0 + j, c = 4 * Q + j - 3;
-            if (c >= 0 && c < FT_RW && gx >= 3 && gx < L.w - 3) valid |= 0xffu << (8 * j);
+    const uint8_t* pb = reinterpret_cast<const uint8_t*>(&pixw[0][0]);
+    constexpr int PITCH = FT_WP * 4;
+    const unsigned t2 = 2u * (unsigned)t;
+    // |p - v| > t  <=>  (unsigned)(p - v + t) > 2t
+#define FAR(p, v) ((unsigned)((int)(p) - (v) + t) > t2)
+    // stage 1: any arc of 9 contains one pixel of each antipodal pair -> both pairs (0,8) and (4,12) must have a far pixel
+    for (int i0 = 0; i0 < FT_RW * FT_RH; i0 += 256) {
+        const int i = i0 + tid;
+        bool pass = false;
+        if (i < FT_RW * FT_RH) {
+            const int r = i / FT_RW, c = i % FT_RW;
+            const int gx = x0 - 1 + c, gy = y0 - 1 + r;
+            if (gx >= 3 && gy >= 3 && gx < L.w - 3 && gy < L.h - 3) {
+                const uint8_t* p = pb + (r + 3) * PITCH + 4 + (c + 3);
+                const int v = p[0];
+                pass = (FAR(p[3 * PITCH], v) | FAR(p[-3 * PITCH], v)) & (FAR(p[3], v) | FAR(p[-3], v));
+            }
         }
-        if (!valid) continue;
-        const int R = rr + 3;
-#define ROWP(dy) (&pixw[R + (dy)][Q])
-#define PT(dx, dy) ((dx) == 0 ? ROWP(dy)[1] : (dx) > 0 ? __funnelshift_r(ROWP(dy)[1], ROWP(dy)[2], 8 * (dx)) \
-                                                        : __funnelshift_r(ROWP(dy)[0], ROWP(dy)[1], 8 * (4 + (dx))))
-        const uint32_t v4 = ROWP(0)[1];
-        const uint32_t hi4 = __vaddus4(v4, t4), lo4 = __vsubus4(v4, t4);
-#define BR(p) __vcmpgtu4((p), hi4)
-#define DK(p) __vcmpltu4((p), lo4)
-        const uint32_t p0 = PT(0, 3), p8 = PT(0, -3);
-        uint32_t cont = valid & (BR(p0) | DK(p0) | BR(p8) | DK(p8));
-        if (!cont) continue;
-        const uint32_t p4 = PT(3, 0), p12 = PT(-3, 0);
-        cont &= BR(p4) | DK(p4) | BR(p12) | DK(p12);
-        if (!cont) continue;
-        uint32_t fb[16], fd[16];
-#define FLAGS(k, dx, dy) { const uint32_t q_ = PT(dx, dy); fb[k] = BR(q_); fd[k] = DK(q_); }
-        CIRC16(FLAGS)
-#undef FLAGS
-        const uint32_t corner = cont & (arc9_lanes(fb) | arc9_lanes(fd));
-#undef BR
-#undef DK
-#undef PT
-#undef ROWP
-        if (corner) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-                if (corner & (0x80u << (8 * j))) clist[atomicAdd(&ncorner, 1)] = (uint16_t)(rr * FT_RW + 4 * Q + j - 3);
-        }
+        warp_push(pass, (uint16_t)i, slist, &nstage1, lane);
     }
+    __syncthreads();
+    // stage 2: full 16-point masks for the survivors
+    const int n1 = nstage1;
+    for (int j0 = 0; j0 < n1; j0 += 256) {
+        const int j = j0 + tid;
+        bool corner = false;
+        int i = 0;
+        if (j < n1) {
+            i = slist[j];
+            const int r = i / FT_RW, c = i % FT_RW;
+            const uint8_t* p = pb + (r + 3) * PITCH + 4 + (c + 3);
+            const int v = p[0], hi = v + t, lo = v - t;
+            uint32_t br = 0, dk = 0;
+#define FMASK(k, dx, dy) { const int q = p[(dy) * PITCH + (dx)]; br |= (uint32_t)(q > hi) << k; dk |= (uint32_t)(q < lo) << k; }
+            CIRC16(FMASK)
+#undef FMASK
+            corner = has_arc9(br) || has_arc9(dk);
+        }
+        warp_push(corner, (uint16_t)i, clist, &ncorner, lane);
+    }
+#undef FAR
     __syncthreads();
 
     // corner score = max over the 16 arcs of 9 of min|v - p| (same sign), minus 1 (OpenCV cornerScore<16>)
-    const uint8_t* pb = reinterpret_cast<const uint8_t*>(&pixw[0][0]);
     const int nc = ncorner;
     for (int j = tid; j < nc; j += 256) {
         const int i = clist[j];
@@ -760,18 +758,32 @@ __global__ void __launch_bounds__(256) k_describe(const __grid_constant__ AfvPar
     const uint8_t* img = L.img + (long long)f * L.img_fstride;
     const uint8_t* blr = L.blur + (long long)f * L.fstride;
 
-    // intensity-centroid moments over the radius-15 disc (cv::ORB ICAngles); lane = u + 15
+    // intensity-centroid moments over the radius-15 disc (cv::ORB ICAngles); lane = u + 15.  Fully unrolled so the
+    // 31 independent row loads are in flight together (the loop was latency-bound on one load per iteration).
     int m10 = 0, m01 = 0;
     const int u = lane - 15;
-    const bool inner = (x0 >= 15 && y0 >= 15 && x0 + 15 < L.w && y0 + 15 < L.h);
-    for (int v = -15; v <= 15; ++v) {
-        const int dmax = c_umax[v < 0 ? -v : v];
-        if (u >= -dmax && u <= dmax) {
-            const int xx = inner ? x0 + u : refl101(x0 + u, L.w);
-            const int yy = inner ? y0 + v : refl101(y0 + v, L.h);
-            const int val = img[(long long)yy * L.img_stride + xx];
-            m10 += u * val; m01 += v * val;
+    const int au = u < 0 ? -u : u;
+    const bool inner = (x0 >= 15 && y0 >= 15 && x0 + 16 < L.w && y0 + 15 < L.h);
+    {
+        constexpr int UM[16] = {15, 15, 15, 15, 14, 14, 14, 13, 13, 12, 11, 10, 9, 8, 6, 3};
+        int vals[31];
+        if (inner) {
+            const uint8_t* base = img + (long long)(y0 - 15) * L.img_stride + x0 + u;
+#pragma unroll
+            for (int r = 0; r < 31; ++r) vals[r] = base[(long long)r * L.img_stride];
+        } else {
+            const int xx = refl101(x0 + u, L.w);
+#pragma unroll
+            for (int r = 0; r < 31; ++r) vals[r] = img[(long long)refl101(y0 - 15 + r, L.h) * L.img_stride + xx];
         }
+        int colsum = 0;
+#pragma unroll
+        for (int r = 0; r < 31; ++r) {
+            const int v = r - 15, av = v < 0 ? -v : v;
+            const int val = (au <= UM[av]) ? vals[r] : 0;
+            colsum += val; m01 += v * val;
+        }
+        m10 = u * colsum;
     }
 #pragma unroll
     for (int o = 16; o; o >>= 1) { m10 += __shfl_xor_sync(0xffffffffu, m10, o); m01 += __shfl_xor_sync(0xffffffffu, m01, o); }
