@@ -269,7 +269,7 @@ __device__ __forceinline__ void three_maxima(const int* cnt, int& ind1, int& ind
 //     exactly (best, second) whenever two survive or the list holds all candidates - otherwise the warp rescans
 //     that one query with the live state (exact fallback).  Acceptance, match stealing and the rotation histogram
 //     are then applied by lane 0 as in the reference.
-#define SFI_K 4
+#define SFI_K 8
 #define SFI_TOPQ 512
 __host__ __device__ inline size_t sfi_base_bytes(int cap) { return (((size_t)cap * (4 * 4 + 2 * 6 + 1)) + 15) & ~(size_t)15; }
 __host__ __device__ inline size_t sfi_topk_bytes() { return (size_t)SFI_TOPQ * (SFI_K * 8 + 4 + 2); }
