@@ -1,0 +1,114 @@
+// afv_host.hpp -- C++ host mirror of the reference's feature front end API on top of the C ABI (include/afv.h).
+//
+// Same class names, method names, argument meaning and error behaviour as the reference:
+//   FeatureExtractorSettings  include/FeatureExtractor.h:24-66, src/FeatureExtractor.cpp:21-56
+//   FeatureExtractor          include/FeatureExtractor.h:68-161 (operator() 6-arg / 3-arg, getters, protected virtuals)
+//   FeatureExtractor_orb32    include/Feature_orb32.h, src/Feature_orb32.cpp
+//   getFeatureExtractor       src/Tracking.cc:1505-1553 (factory, nfeatures clamp :1515-1520)
+//   FeatureMatcher            include/FeatureMatcher.h:36-118 (SearchForInitialization, static DescriptorDistance,
+//                             setDescriptorDistanceThresholds; TH_LOW/TH_HIGH statics)
+// Differences, all additive: the per-frame work runs in libafv_b200.so (CUDA, no CPU fallback: a missing device
+// terminates like the reference's fatal paths, src/Feature_sift128.cpp:61); `Image` carries only the gray image;
+// the matcher works on `FrameView`s (the arrays the reference's Frame owns: mvKeysUn, mDescriptors, keyPtsSize,
+// image bounds, maxKeyPtSize) instead of the full Frame graph.
+#pragma once
+#include <memory>
+#include <string>
+#include <vector>
+#include "cv_compat.h"
+#include "../../include/afv.h"
+
+namespace ANYFEATURE_VSLAM_B200 {
+using afv_host::mat2f;
+using afvcv::KeyPoint;
+using afvcv::Mat;
+
+enum KeypointType { KEYP_ORB = 0, KEYP_AKAZE = 1, KEYP_BRISK = 2, KEYP_SIFT = 5 };         // include/Types.h:11-21
+enum DescriptorType { DESC_ORB = 0, DESC_AKAZE61 = 1, DESC_BRISK = 2, DESC_SIFT128 = 5 };  // include/Types.h:23-33
+enum FeatureType { FEAT_ORB = 0, FEAT_AKAZE61 = 1, FEAT_BRISK = 2, FEAT_SIFT128 = 5 };     // include/Types.h:35-45
+int get_feature_id(const std::string& str);                                                // include/Types.h:102-124
+typedef float Descriptor_Distance_Type;                                                    // include/Types.h:127
+
+struct Image {                     // include/Image.h:12-27 (gray image only; imread / cvtColor stay with the caller)
+    Mat grayImg, mask;
+};
+
+class FeatureExtractorSettings {
+public:
+    static int numOctaves0; static float scaleFactor0; static float th0;
+    // "none" keeps the static nominal values of the previous constructor (reference quirk, :26-38)
+    FeatureExtractorSettings(const KeypointType& keypointType_, const DescriptorType& descriptorType_, const std::string& settingsYamlFile);
+    static float GetDetectorNominalScaleFactor() { return scaleFactor0; }
+    static int GetDetectorNominalNumOctaves() { return numOctaves0; }
+    static float GetDetectorNominalThreshold() { return th0; }
+    bool ON_automaticTuning; float scaleFactor; int nOctaves; int iniThFAST, minThFAST; float detectTh;
+    KeypointType keypointType; DescriptorType descriptorType;
+    float maxKeyPtSize{0.0f}, minKeyPtSize{1.0f}, maxKeyPtSize0{}, maxKeyPtSigma0{};
+    float scaleFactorOrb{1.2f}; int nOctavesOrb{8};
+};
+
+class FeatureExtractor {
+public:
+    FeatureExtractor(const int& nfeatures_, std::shared_ptr<FeatureExtractorSettings>& settings_);
+    virtual ~FeatureExtractor();
+    std::shared_ptr<FeatureExtractorSettings> settings{};
+    void operator()(const Image& img, std::vector<KeyPoint>& keypoints, Mat& descriptors, std::vector<mat2f>& keyPtsSigma2,
+                    std::vector<mat2f>& keyPtsInf, std::vector<float>& keyPtsSize);
+    void operator()(const Image& img, std::vector<KeyPoint>& keypoints, Mat& descriptors);
+    // batched extension (not in the reference): B frames of equal size in one call
+    void extractBatch(const std::vector<const Image*>& imgs, std::vector<std::vector<KeyPoint>>& keypoints, std::vector<Mat>& descriptors,
+                      std::vector<std::vector<float>>& sizes);
+    int GetLevels() { return settings->nOctaves; }
+    float GetScaleFactor() { return settings->scaleFactor; }
+    std::vector<float> GetScaleFactors() { return mvScaleFactor; }
+    float GetMaxKeyPtSize() const { return settings->maxKeyPtSize0; }
+    float GetMaxKeyPtSigma() const { return settings->maxKeyPtSigma0; }
+    const std::vector<int>& GetFeaturesPerLevel() const { return mnFeaturesPerLevel; }
+protected:
+    int nfeatures;
+    std::vector<int> mnFeaturesPerLevel;
+    std::vector<float> mvScaleFactor;
+    void computeSigma(std::vector<mat2f>& keyPtsSigma2, std::vector<mat2f>& keyPtsInf, const std::vector<float>& keyPtsSize);
+    void automaticTuning(const Image& img);
+    // Functions to override (same hooks as the reference; orb32 implements detectAndCompute as one C-ABI call)
+    virtual void initializeExtractor(const Image&) {}
+    virtual int GetKeypointOctave(const KeyPoint& keypoint) const = 0;
+    virtual float GetKeypointSize(const KeyPoint& keypoint) const = 0;
+    virtual void detectAndCompute(const Image& img, std::vector<KeyPoint>& keypoints, Mat& descriptors, std::vector<float>& sizes) = 0;
+    afv_extractor* handle_ = nullptr;
+    int handle_w_ = 0, handle_h_ = 0, handle_batch_ = 0;
+    void ensureHandle(int feature_id, int w, int h, int batch);
+};
+
+class FeatureExtractor_orb32 : public FeatureExtractor {
+public:
+    FeatureExtractor_orb32(const int& nfeatures_, std::shared_ptr<FeatureExtractorSettings>& settings_) : FeatureExtractor(nfeatures_, settings_) {}
+protected:
+    int GetKeypointOctave(const KeyPoint& keypoint) const override { return keypoint.octave; }
+    float GetKeypointSize(const KeyPoint& keypoint) const override;
+    void detectAndCompute(const Image& img, std::vector<KeyPoint>& keypoints, Mat& descriptors, std::vector<float>& sizes) override;
+};
+
+// Tracking::getFeatureExtractor (src/Tracking.cc:1505-1553): nfeatures scaled with resolution, clamped to [1000,2000]
+std::shared_ptr<FeatureExtractor> getFeatureExtractor(const int& scaleNumFeaturesMonocular, const std::string& feature_settings_yaml_file,
+                                                      const std::string& feature, int imWidth, int imHeight);
+
+// the arrays a reference Frame hands to the matcher
+struct FrameView {
+    std::vector<KeyPoint> mvKeysUn; Mat mDescriptors; std::vector<float> keyPtsSize;
+    float mnMinX = 0, mnMinY = 0, mnMaxX = 0, mnMaxY = 0, maxKeyPtSize = 0;
+};
+
+class FeatureMatcher {
+public:
+    FeatureMatcher(float nnratio = 0.6f, bool checkOri = true) : mfNNratio(nnratio), mbCheckOrientation(checkOri) {}
+    static Descriptor_Distance_Type DescriptorDistance(const Mat& a, const Mat& b, const DescriptorType& descriptorType_);
+    int SearchForInitialization(FrameView& F1, FrameView& F2, std::vector<afvcv::Point2f>& vbPrevMatched, std::vector<int>& vnMatches12,
+                                const int& windowSize, const DescriptorType& descriptorType);
+    static void setDescriptorDistanceThresholds(const std::string& feature_settings_yaml_file);
+    static Descriptor_Distance_Type TH_LOW, TH_HIGH, descDistTh_high_reloc, descDistTh_low_reloc;
+    static const int HISTO_LENGTH;
+protected:
+    float mfNNratio; bool mbCheckOrientation;
+};
+}  // namespace ANYFEATURE_VSLAM_B200

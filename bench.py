@@ -188,8 +188,8 @@ def run_gpu(args):
     stream = torch.cuda.current_stream()
     gathered = None
     if world > 1 and args.gather:
-        # C5: fixed-capacity packed results gathered to rank 0 over NCCL/NVLink (n, matches, nmatches, kps, desc)
-        pack_bytes = B * (4 + 4 + cap * (28 + 32 + 4))
+        # C5: fixed-capacity packed results gathered to rank 0 over NCCL/NVLink (n, nmatches, matches, kps, desc)
+        _, pack_bytes = pkg.sharding.pack_layout(B, cap, 32)
         d_pack = torch.empty(pack_bytes, dtype=torch.uint8, device=dev)
         gathered = [torch.empty(pack_bytes, dtype=torch.uint8, device=dev) for _ in range(world)] if rank == 0 else None
 
@@ -198,11 +198,8 @@ def run_gpu(args):
         fm.search_for_initialization(out[0], out[1], out[2], out[3], d_pa, d_pb, None, BOUNDS, MAX_KPT_SIZE,
                                      window=100, matches12=m12, nmatches=nm, stream=stream)
         if world > 1 and args.gather:
-            o = 0
-            for t in (out[3].view(torch.uint8).view(-1), nm.view(torch.uint8).view(-1), m12.view(torch.uint8).view(-1),
-                      out[0].view(torch.uint8).view(-1), out[1].view(-1)):
-                d_pack[o:o + t.numel()].copy_(t, non_blocking=True); o += t.numel()
-            dist.gather(d_pack, gathered, dst=0)
+            pkg.sharding.pack_results(d_pack, out[3], nm, m12, out[0], out[1])
+            pkg.sharding.gather_to_root(d_pack, gathered, world, rank)
 
     def barrier():
         if world > 1:

@@ -44,3 +44,13 @@ def test_unsupported_feature_is_an_error_not_a_fallback():
     h = C.c_void_p()
     rc = pkg.lib().afv_extractor_create(C.byref(h), 5, 1000, 8, C.c_float(2.0), C.c_float(10.0), 0, 1, 640, 480)
     assert rc in (-5, -2) and not h.value
+
+
+def test_cpp_host_mirror_builds_and_links():
+    """The C++ classes that keep the reference's FeatureExtractor / FeatureMatcher signatures compile and link
+    against the C-ABI library without OpenCV."""
+    import subprocess
+    import __graft_entry__ as g
+    g.build()
+    subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "anyfeature-vslam_b200", "host")])
+    assert os.path.exists(os.path.join(ROOT, "anyfeature-vslam_b200", "host", "host_api_test"))
