@@ -237,7 +237,6 @@ extern "C" int afv_match_window(int desc_type, const void* d_q, const float* d_q
 // grid cell lies in the query's cell range (this reproduces the round()-vs-floor/ceil quirk of the reference
 // grid exactly), passes the size gate and |dx|,|dy| < r.  Enumeration order of the reference (cell x, cell y,
 // index) is the order key.
-#define SFI_THREADS 128
 __device__ __forceinline__ int rot_bin(float a1, float a2) {       // updateRotationHistogram (:1587-1597)
     float rot = __fsub_rn(a1, a2);
     if (rot < 0.0f) rot = __fadd_rn(rot, 360.0f);
@@ -259,29 +258,39 @@ __device__ __forceinline__ void three_maxima(const int* cnt, int& ind1, int& ind
     else if ((float)max3 < __fmul_rn(0.1f, (float)max1)) { ind3 = -1; }
 }
 
-// Shared-memory plan (cap = per-frame capacity, Dpad = descriptor bytes padded to 4):
-//   * the train frame is staged SORTED BY GRID COLUMN (counting sort, 64 bins) so a query only scans the slots of
-//     its cell-column range; slot order inside a column is arbitrary - ties are decided by the explicit order key;
-//   * phase 1 (parallel, one thread per query): top-SFI_K candidates of every query by (distance, reference
-//     enumeration order), IGNORING the sequential "already matched" state, plus the query's candidate count;
-//   * phase 2 (one warp, queries in index order): the reference's sequential rule skips candidates whose recorded
-//     match distance is <= this distance (:511-512); the first two surviving entries of the sorted top-K list are
-//     exactly (best, second) whenever two survive or the list holds all candidates - otherwise the warp rescans
-//     that one query with the live state (exact fallback).  Acceptance, match stealing and the rotation histogram
-//     are then applied by lane 0 as in the reference.
-#define SFI_K 8
-#define SFI_TOPQ 512
-__host__ __device__ inline size_t sfi_base_bytes(int cap) { return (((size_t)cap * (4 * 4 + 2 * 6 + 1)) + 15) & ~(size_t)15; }
-__host__ __device__ inline size_t sfi_topk_bytes() { return (size_t)SFI_TOPQ * (SFI_K * 8 + 4 + 2); }
+// v4 design: two kernels.
+//  k_sfi_lists   (throughput part, one CTA per frame pair, one WARP per query): the train frame is counting-sorted by
+//                grid column into shared memory (positions, cells, descriptors) so a query scans only its cell-column
+//                range with converged lanes; every (query, candidate) distance is computed exactly once and appended
+//                to the pair's candidate pool in global memory (two passes per query: count -> bump-allocate -> fill).
+//                Nothing here depends on the sequential matching state.
+//  k_sfi_resolve (sequential part, one WARP per frame pair, state in shared memory): queries in index order; lanes
+//                stream the query's candidate list, drop candidates whose recorded match distance is <= this distance
+//                (:511-512), reduce (distance, reference enumeration order) top-2, and lane 0 applies the acceptance /
+//                stealing / rotation-histogram logic.  A query whose list did not fit the pool is rescanned brute force
+//                with the same candidate definition (exact fallback).
+#define SFL_THREADS 256
+#define SFR_WARPS 4
+__host__ __device__ inline size_t sfl_base_bytes(int cap) { return (((size_t)cap * (4 * 2 + 2 * 4)) + 15) & ~(size_t)15; }
+__host__ __device__ inline size_t sfr_warp_bytes(int cap) { return (((size_t)cap * (4 * 2 + 2 * 3 + 1)) + 15) & ~(size_t)15; }
 
 struct SfiQuery { float x, y; int c0, c1, r0, r1; bool ok; };
+struct SfiQMeta { int i1, off, cnt; float angle; };         // per query, written by k_sfi_lists
 
-__global__ void __launch_bounds__(SFI_THREADS) k_search_init(int desc_type, int D, int Dpad, int stage_desc,
+// candidate test shared by both kernels: grid cell of the train keypoint inside the query's cell range + window test
+__device__ __forceinline__ bool sfi_in_window(const SfiQuery& q, int cx, int cy, float tx, float ty, float window) {
+    if (cx < q.c0 || cx > q.c1 || cy < q.r0 || cy > q.r1) return false;
+    const float dx = __fsub_rn(tx, q.x), dy = __fsub_rn(ty, q.y);
+    return fabsf(dx) < window && fabsf(dy) < window;
+}
+
+template <bool BINARY>
+__global__ void __launch_bounds__(SFL_THREADS) k_sfi_lists(int desc_type, int D, int Dpad, int stage_desc,
         const afv_keypoint* __restrict__ kps, const uint8_t* __restrict__ desc, const float* __restrict__ kpsize,
         const int* __restrict__ n_arr, int cap, const int* __restrict__ pair_a, const int* __restrict__ pair_b,
         float minX, float minY, float invW, float invH, float max_kpt_size,
-        float* __restrict__ prev_matched, float window, float th_low, float nnratio, int check_ori,
-        int* __restrict__ matches12, int* __restrict__ nmatches) {
+        const float* __restrict__ prev_matched, float window,
+        void* __restrict__ pool_v, int pool_cap, SfiQMeta* __restrict__ qmeta, int* __restrict__ nq_out) {
     extern __shared__ __align__(16) unsigned char sm[];
     const int p = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int fa = pair_a[p], fb = pair_b[p];
@@ -291,38 +300,29 @@ __global__ void __launch_bounds__(SFI_THREADS) k_search_init(int desc_type, int 
     const uint8_t* d1 = desc + (long long)fa * cap * D;
     const uint8_t* d2 = desc + (long long)fb * cap * D;
     const float* size2 = kpsize + (long long)fb * cap;
-    float* pm = prev_matched ? prev_matched + (long long)p * cap * 2 : nullptr;
-    int* m12g = matches12 + (long long)p * cap;
+    const float* pm = prev_matched ? prev_matched + (long long)p * cap * 2 : nullptr;
+    SfiQMeta* qm = qmeta + (long long)p * cap;
 
-    float* sx = reinterpret_cast<float*>(sm); float* sy = sx + cap; float* sang = sy + cap; float* matched = sang + cap;
-    unsigned short* m21 = reinterpret_cast<unsigned short*>(matched + cap);
-    unsigned short* m12 = m21 + cap; unsigned short* scell = m12 + cap; unsigned short* sorig = scell + cap;
-    unsigned short* qlist = sorig + cap; unsigned short* slotof = qlist + cap;
-    signed char* hbin = reinterpret_cast<signed char*>(slotof + cap);
-    uint8_t* sdesc = sm + sfi_base_bytes(cap);
-    unsigned long long* topk = reinterpret_cast<unsigned long long*>(sdesc + (stage_desc ? (size_t)cap * Dpad : 0));
-    float* qangle = reinterpret_cast<float*>(topk + SFI_TOPQ * SFI_K);
-    unsigned short* qncand = reinterpret_cast<unsigned short*>(qangle + SFI_TOPQ);
-    __shared__ int hist[AFV_HISTO_LENGTH];
+    float* sx = reinterpret_cast<float*>(sm); float* sy = sx + cap;
+    unsigned short* scell = reinterpret_cast<unsigned short*>(sy + cap);
+    unsigned short* sorig = scell + cap; unsigned short* qlist = sorig + cap; unsigned short* tmpc = qlist + cap;
+    uint8_t* sdesc = sm + sfl_base_bytes(cap);
     __shared__ int colstart[AFV_GRID_COLS + 1], colfill[AFV_GRID_COLS];
-    __shared__ int s_nm, s_nq, keepbin[3];
+    __shared__ int s_nq, s_pool;
     const int nw = Dpad / 4;
     const unsigned short NONE16 = 0xffff;
 
-    // ---- prologue: column histogram -> counting sort of the train frame; query list = octave-0 keypoints
     if (tid < AFV_GRID_COLS) { colstart[tid] = 0; colfill[tid] = 0; }
-    if (tid < AFV_HISTO_LENGTH) hist[tid] = 0;
-    if (tid == 0) { s_nm = 0; s_nq = 0; colstart[AFV_GRID_COLS] = 0; }
+    if (tid == 0) { s_nq = 0; s_pool = 0; colstart[AFV_GRID_COLS] = 0; }
     __syncthreads();
-    for (int i = tid; i < n2; i += SFI_THREADS) {
+    for (int i = tid; i < n2; i += SFL_THREADS) {
         const float sz = size2[i];
         const int c = grid_cell(k2[i].x, k2[i].y, minX, minY, invW, invH);
         // GetFeaturesInArea(..., minSize 0, maxSize F1.maxKeyPtSize) size gate folded in (:495-496, Frame.cc:365-368)
         const bool ok = c >= 0 && !(sz < 0.0f) && !(sz > max_kpt_size);
-        m21[i] = ok ? (unsigned short)c : NONE16;                   // temp: cell id
+        tmpc[i] = ok ? (unsigned short)c : NONE16;
         if (ok) atomicAdd(&colstart[c / AFV_GRID_ROWS + 1], 1);
     }
-    for (int i = tid; i < n1; i += SFI_THREADS) m12[i] = (k1[i].octave > 0) ? 1 : 0;          // temp: 0 = query (:491-493)
     __syncthreads();
     if (wid == 0) {                                                 // inclusive scan of 64 column counts
         int a0 = colstart[1 + lane], a1 = colstart[33 + lane];
@@ -331,33 +331,32 @@ __global__ void __launch_bounds__(SFI_THREADS) k_search_init(int desc_type, int 
         const int tot0 = __shfl_sync(0xffffffffu, a0, 31);
         colstart[1 + lane] = a0; colstart[33 + lane] = tot0 + a1;
     }
-    if (wid == 1) {                                                 // ordered compaction of the octave-0 queries
+    if (wid == 1) {                                                 // ordered compaction of the octave-0 queries (:491-493)
         int base = 0;
         for (int i0 = 0; i0 < n1; i0 += 32) {
             const int i = i0 + lane;
-            const bool q = i < n1 && m12[i] == 0;
+            const bool q = i < n1 && k1[i].octave <= 0;
             const unsigned m = __ballot_sync(0xffffffffu, q);
             if (q) qlist[base + __popc(m & ((1u << lane) - 1))] = (unsigned short)i;
             base += __popc(m);
         }
-        if (lane == 0) s_nq = base;
+        if (lane == 0) { s_nq = base; nq_out[p] = base; }
     }
     __syncthreads();
-    for (int i = tid; i < n2; i += SFI_THREADS) {
-        const int c = m21[i];
+    for (int i = tid; i < n2; i += SFL_THREADS) {                   // scatter into column order
+        const int c = tmpc[i];
         if (c == NONE16) continue;
         const int cx = c / AFV_GRID_ROWS;
         const int slot = colstart[cx] + atomicAdd(&colfill[cx], 1);
-        sx[slot] = k2[i].x; sy[slot] = k2[i].y; sang[slot] = k2[i].angle;
+        sx[slot] = k2[i].x; sy[slot] = k2[i].y;
         scell[slot] = (unsigned short)((cx << 8) | (c % AFV_GRID_ROWS));
-        sorig[slot] = (unsigned short)i; slotof[i] = (unsigned short)slot;
+        sorig[slot] = (unsigned short)i;
     }
     __syncthreads();
     const int n2s = colstart[AFV_GRID_COLS];
-    for (int i = tid; i < n2s; i += SFI_THREADS) { matched[i] = FLT_MAX; m21[i] = NONE16; }
-    for (int i = tid; i < n1; i += SFI_THREADS) { hbin[i] = -1; m12[i] = NONE16; }
+    const int nq = s_nq;
     if (stage_desc) {
-        for (int i = tid; i < n2s * nw; i += SFI_THREADS) {
+        for (int i = tid; i < n2s * nw; i += SFL_THREADS) {
             const int r = i / nw, w = i % nw;
             const uint8_t* row = d2 + (long long)sorig[r] * D;
             uint32_t v;
@@ -368,147 +367,187 @@ __global__ void __launch_bounds__(SFI_THREADS) k_search_init(int desc_type, int 
     }
     __syncthreads();
 
-    auto query_setup = [&](int i1) {
+    for (int qi = wid; qi < nq; qi += SFL_THREADS / 32) {
+        const int i1 = qlist[qi];
         SfiQuery q;
         q.x = pm ? pm[2 * i1] : k1[i1].x; q.y = pm ? pm[2 * i1 + 1] : k1[i1].y;
         q.ok = window_cells(q.x, q.y, window, minX, minY, invW, invH, q.c0, q.c1, q.r0, q.r1);
-        return q;
-    };
-    auto load_desc = [&](int i1, uint32_t* dst) {
-        const uint8_t* qrow = d1 + (long long)i1 * D;
-        if ((D & 3) == 0) {
-#pragma unroll
-            for (int w = 0; w < 16; ++w) if (w < nw) dst[w] = reinterpret_cast<const uint32_t*>(qrow)[w];
-        } else {
-#pragma unroll
-            for (int w = 0; w < 16; ++w) if (w < nw) { uint32_t v = 0; for (int b = 0; b < 4; ++b) { const int o = w * 4 + b; if (o < D) v |= (uint32_t)qrow[o] << (8 * b); } dst[w] = v; }
-        }
-    };
-    // distance of query (descriptor words qd / index i1) to the train keypoint in slot sl, or -1 when it is no candidate
-    auto cand_dist = [&](const SfiQuery& q, const uint32_t* qd, int i1, int sl, uint32_t& order) -> float {
-        const unsigned short cc = scell[sl];
-        const int cy = cc & 0xff;
-        if (cy < q.r0 || cy > q.r1) return -1.0f;
-        const float dx = __fsub_rn(sx[sl], q.x), dy = __fsub_rn(sy[sl], q.y);
-        if (!(fabsf(dx) < window && fabsf(dy) < window)) return -1.0f;
-        const int i2 = sorig[sl];
-        order = ((uint32_t)(cc >> 8) << 26) | ((uint32_t)cy << 20) | (uint32_t)i2;     // reference enumeration order
-        if (desc_type == AFV_FEAT_SIFT128) return l2sqr128((const float*)(d1 + (long long)i1 * D), (const float*)(d2 + (long long)i2 * D));
-        if (stage_desc) {
-            const uint32_t* y32 = reinterpret_cast<const uint32_t*>(sdesc) + (long long)sl * nw;
-            int d = 0;
-#pragma unroll
-            for (int w = 0; w < 16; ++w) if (w < nw) d += __popc(qd[w] ^ y32[w]);
-            return (float)d;
-        }
-        return (float)hamming_bytes(d1 + (long long)i1 * D, d2 + (long long)i2 * D, D);
-    };
-
-    const int nq = s_nq;
-    for (int qbase = 0; qbase < nq; qbase += SFI_TOPQ) {
-        const int nchunk = min(SFI_TOPQ, nq - qbase);
-        // ---- phase 1: speculative top-K per query (state-free)
-        for (int qi = tid; qi < nchunk; qi += SFI_THREADS) {
-            const int i1 = qlist[qbase + qi];
-            const SfiQuery q = query_setup(i1);
-            unsigned long long tk[SFI_K];
-#pragma unroll
-            for (int j = 0; j < SFI_K; ++j) tk[j] = KEY_NONE;
-            int ncand = 0;
-            if (q.ok) {
+        int cnt = 0, off = 0;
+        if (q.ok) {
+            const int s0 = colstart[q.c0], s1 = colstart[q.c1 + 1];
+            // pass 1: count
+            for (int sb = s0; sb < s1; sb += 32) {
+                const int sl = sb + lane;
+                bool pass = false;
+                if (sl < s1) { const unsigned short cc = scell[sl]; pass = sfi_in_window(q, cc >> 8, cc & 0xff, sx[sl], sy[sl], window); }
+                cnt += __popc(__ballot_sync(0xffffffffu, pass));
+            }
+            if (cnt > 0) {
+                if (lane == 0) off = atomicAdd(&s_pool, cnt);
+                off = __shfl_sync(0xffffffffu, off, 0);
+                if (off + cnt > pool_cap) off = -1;                 // pool exhausted: the resolver rescans this query
+            }
+            if (cnt > 0 && off >= 0) {
                 uint32_t qd[16];
-                if (desc_type != AFV_FEAT_SIFT128) load_desc(i1, qd);
-                const int s0 = colstart[q.c0], s1 = colstart[q.c1 + 1];
-                for (int sl = s0; sl < s1; ++sl) {
-                    uint32_t order;
-                    const float dist = cand_dist(q, qd, i1, sl, order);
-                    if (dist < 0.0f) continue;
-                    ++ncand;
-                    const unsigned long long key = make_key(dist, order);
-                    if (key < tk[SFI_K - 1]) {
-                        tk[SFI_K - 1] = key;
+                if (BINARY) {
+                    const uint8_t* qrow = d1 + (long long)i1 * D;
+                    if ((D & 3) == 0) {
 #pragma unroll
-                        for (int j = SFI_K - 1; j > 0; --j)
-                            if (tk[j] < tk[j - 1]) { const unsigned long long tmp = tk[j]; tk[j] = tk[j - 1]; tk[j - 1] = tmp; }
+                        for (int w = 0; w < 16; ++w) if (w < nw) qd[w] = reinterpret_cast<const uint32_t*>(qrow)[w];
+                    } else {
+#pragma unroll
+                        for (int w = 0; w < 16; ++w) if (w < nw) { uint32_t v = 0; for (int b = 0; b < 4; ++b) { const int o = w * 4 + b; if (o < D) v |= (uint32_t)qrow[o] << (8 * b); } qd[w] = v; }
                     }
+                }
+                int run = off;
+                for (int sb = s0; sb < s1; sb += 32) {
+                    const int sl = sb + lane;
+                    bool pass = false;
+                    if (sl < s1) { const unsigned short cc = scell[sl]; pass = sfi_in_window(q, cc >> 8, cc & 0xff, sx[sl], sy[sl], window); }
+                    const unsigned m = __ballot_sync(0xffffffffu, pass);
+                    if (pass) {
+                        const int i2 = sorig[sl];
+                        const int pos = run + __popc(m & ((1u << lane) - 1));
+                        if (BINARY) {
+                            int d = 0;
+                            if (stage_desc) {
+                                const uint32_t* y32 = reinterpret_cast<const uint32_t*>(sdesc) + (long long)sl * nw;
+#pragma unroll
+                                for (int w = 0; w < 16; ++w) if (w < nw) d += __popc(qd[w] ^ y32[w]);
+                            } else d = hamming_bytes(d1 + (long long)i1 * D, d2 + (long long)i2 * D, D);
+                            reinterpret_cast<uint32_t*>(pool_v)[(long long)p * pool_cap + pos] = ((uint32_t)d << 20) | (uint32_t)i2;
+                        } else {
+                            const float dist = l2sqr128((const float*)(d1 + (long long)i1 * D), (const float*)(d2 + (long long)i2 * D));
+                            reinterpret_cast<unsigned long long*>(pool_v)[(long long)p * pool_cap + pos] = make_key(dist, (uint32_t)i2);
+                        }
+                    }
+                    run += __popc(m);
                 }
             }
-#pragma unroll
-            for (int j = 0; j < SFI_K; ++j) topk[qi * SFI_K + j] = tk[j];
-            qncand[qi] = (unsigned short)min(ncand, 65535);
-            qangle[qi] = k1[i1].angle;
         }
-        __syncthreads();
-        // ---- phase 2: sequential resolution by warp 0
-        if (wid == 0) {
-            for (int qi = 0; qi < nchunk; ++qi) {
-                const int i1 = qlist[qbase + qi];
-                const int ncand = qncand[qi];
-                if (ncand == 0) continue;
-                unsigned long long key = lane < SFI_K ? topk[qi * SFI_K + lane] : KEY_NONE;
-                bool alive = false;
-                if (key != KEY_NONE) {
-                    const int sl = slotof[(uint32_t)key & 0xfffffu];
-                    alive = !(matched[sl] <= key_dist(key));                        // :511-512
-                }
-                const unsigned am = __ballot_sync(0xffffffffu, alive);
-                unsigned long long k1st = KEY_NONE, k2nd = KEY_NONE;
-                if (__popc(am) >= 2 || ncand <= SFI_K) {
-                    const int l1 = am ? __ffs(am) - 1 : 0;
-                    const unsigned am2 = am & (am - 1);
-                    const int l2 = am2 ? __ffs(am2) - 1 : 0;
-                    const unsigned long long a = __shfl_sync(0xffffffffu, key, l1), b = __shfl_sync(0xffffffffu, key, l2);
-                    if (am) k1st = a;
-                    if (am2) k2nd = b;
-                } else {
-                    // exact fallback: rescan this query with the live state
-                    const SfiQuery q = query_setup(i1);
-                    uint32_t qd[16];
-                    if (desc_type != AFV_FEAT_SIFT128) load_desc(i1, qd);
-                    Top2 t; t.k1 = t.k2 = KEY_NONE;
-                    const int s0 = colstart[q.c0], s1 = colstart[q.c1 + 1];
-                    for (int sl = s0 + lane; sl < s1; sl += 32) {
-                        uint32_t order;
-                        const float dist = cand_dist(q, qd, i1, sl, order);
-                        if (dist < 0.0f || matched[sl] <= dist) continue;
-                        top2_push(t, make_key(dist, order));
+        if (lane == 0) { SfiQMeta m; m.i1 = i1; m.off = off; m.cnt = cnt; m.angle = k1[i1].angle; qm[qi] = m; }
+    }
+}
+
+template <bool BINARY>
+__global__ void __launch_bounds__(SFR_WARPS * 32) k_sfi_resolve(int desc_type, int D,
+        const afv_keypoint* __restrict__ kps, const uint8_t* __restrict__ desc, const float* __restrict__ kpsize,
+        const int* __restrict__ n_arr, int cap, const int* __restrict__ pair_a, const int* __restrict__ pair_b, int P,
+        float minX, float minY, float invW, float invH, float max_kpt_size,
+        float* __restrict__ prev_matched, float window, float th_low, float nnratio, int check_ori,
+        const void* __restrict__ pool_v, int pool_cap, const SfiQMeta* __restrict__ qmeta, const int* __restrict__ nq_arr,
+        int* __restrict__ matches12, int* __restrict__ nmatches) {
+    extern __shared__ __align__(16) unsigned char sm[];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int p = blockIdx.x * SFR_WARPS + wid;
+    if (p >= P) return;                                            // whole warp exits; no block-wide barriers below
+    unsigned char* base = sm + (size_t)wid * sfr_warp_bytes(cap);
+    float* matched = reinterpret_cast<float*>(base); float* tang = matched + cap;
+    unsigned short* m21 = reinterpret_cast<unsigned short*>(tang + cap);
+    unsigned short* m12 = m21 + cap; unsigned short* tcell = m12 + cap;
+    signed char* hbin = reinterpret_cast<signed char*>(tcell + cap);
+    __shared__ int hist_all[SFR_WARPS][AFV_HISTO_LENGTH + 2];
+    int* hist = hist_all[wid];
+    const unsigned short NONE16 = 0xffff;
+
+    const int fa = pair_a[p], fb = pair_b[p];
+    const int n1 = min(n_arr[fa], cap), n2 = min(n_arr[fb], cap);
+    const afv_keypoint* k1 = kps + (long long)fa * cap;
+    const afv_keypoint* k2 = kps + (long long)fb * cap;
+    const uint8_t* d1 = desc + (long long)fa * cap * D;
+    const uint8_t* d2 = desc + (long long)fb * cap * D;
+    const float* size2 = kpsize + (long long)fb * cap;
+    float* pm = prev_matched ? prev_matched + (long long)p * cap * 2 : nullptr;
+    int* m12g = matches12 + (long long)p * cap;
+    const SfiQMeta* qm = qmeta + (long long)p * cap;
+    const int nq = nq_arr[p];
+
+    for (int i = lane; i < n2; i += 32) {
+        matched[i] = FLT_MAX; m21[i] = NONE16; tang[i] = k2[i].angle;
+        const float sz = size2[i];
+        const int c = grid_cell(k2[i].x, k2[i].y, minX, minY, invW, invH);
+        const bool ok = c >= 0 && !(sz < 0.0f) && !(sz > max_kpt_size);
+        tcell[i] = ok ? (unsigned short)(((c / AFV_GRID_ROWS) << 8) | (c % AFV_GRID_ROWS)) : NONE16;
+    }
+    for (int i = lane; i < n1; i += 32) { m12[i] = NONE16; hbin[i] = -1; }
+    if (lane < AFV_HISTO_LENGTH) hist[lane] = 0;
+    __syncwarp();
+    int nm = 0;                                                    // lane 0's copy is authoritative
+
+    for (int qi = 0; qi < nq; ++qi) {
+        const SfiQMeta q = qm[qi];
+        if (q.cnt == 0) continue;
+        Top2 t; t.k1 = t.k2 = KEY_NONE;
+        if (q.off >= 0) {
+            for (int j0 = 0; j0 < q.cnt; j0 += 128) {              // 4 independent loads in flight per lane
+                unsigned long long key[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int j = j0 + u * 32 + lane;
+                    key[u] = KEY_NONE;
+                    if (j < q.cnt) {
+                        if (BINARY) {
+                            const uint32_t e = reinterpret_cast<const uint32_t*>(pool_v)[(long long)p * pool_cap + q.off + j];
+                            key[u] = ((unsigned long long)__float_as_uint((float)(e >> 20)) << 32) | (e & 0xfffffu);
+                        } else key[u] = reinterpret_cast<const unsigned long long*>(pool_v)[(long long)p * pool_cap + q.off + j];
                     }
-                    top2_warp_reduce(t);
-                    k1st = t.k1; k2nd = t.k2;
                 }
-                if (lane == 0 && k1st != KEY_NONE) {
-                    const float bestDist = key_dist(k1st), bestDist2 = key_dist(k2nd);
-                    if (bestDist <= th_low && bestDist < __fmul_rn(bestDist2, nnratio)) {       // :526-528
-                        const int bestIdx2 = (int)((uint32_t)k1st & 0xfffffu);
-                        const int sl = slotof[bestIdx2];
-                        if (m21[sl] != NONE16) { m12[m21[sl]] = NONE16; s_nm--; }             // :530-534
-                        m12[i1] = (unsigned short)bestIdx2; m21[sl] = (unsigned short)i1; matched[sl] = bestDist; s_nm++;
-                        if (check_ori) { const int bin = rot_bin(qangle[qi], sang[sl]); hbin[i1] = (signed char)bin; hist[bin]++; }
-                    }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    if (key[u] == KEY_NONE) continue;
+                    const int i2 = (int)((uint32_t)key[u] & 0xfffffu);
+                    const float dist = key_dist(key[u]);
+                    if (matched[i2] <= dist) continue;              // :511-512
+                    const unsigned short cc = tcell[i2];
+                    top2_push(t, make_key(dist, ((uint32_t)(cc >> 8) << 26) | ((uint32_t)(cc & 0xff) << 20) | (uint32_t)i2));
                 }
-                __syncwarp();
+            }
+        } else {
+            // exact fallback (candidate pool exhausted): rescan every train keypoint with the same candidate definition
+            SfiQuery w;
+            w.x = pm ? pm[2 * q.i1] : k1[q.i1].x; w.y = pm ? pm[2 * q.i1 + 1] : k1[q.i1].y;
+            w.ok = window_cells(w.x, w.y, window, minX, minY, invW, invH, w.c0, w.c1, w.r0, w.r1);
+            for (int i2 = lane; w.ok && i2 < n2; i2 += 32) {
+                const unsigned short cc = tcell[i2];
+                if (cc == NONE16 || !sfi_in_window(w, cc >> 8, cc & 0xff, k2[i2].x, k2[i2].y, window)) continue;
+                const float dist = desc_distance(desc_type, d1 + (long long)q.i1 * D, d2 + (long long)i2 * D, D);
+                if (matched[i2] <= dist) continue;
+                top2_push(t, make_key(dist, ((uint32_t)(cc >> 8) << 26) | ((uint32_t)(cc & 0xff) << 20) | (uint32_t)i2));
             }
         }
-        __syncthreads();
+        top2_warp_reduce(t);
+        if (lane == 0 && t.k1 != KEY_NONE) {
+            const float bestDist = key_dist(t.k1), bestDist2 = key_dist(t.k2);
+            if (bestDist <= th_low && bestDist < __fmul_rn(bestDist2, nnratio)) {           // :526-528
+                const int bestIdx2 = (int)((uint32_t)t.k1 & 0xfffffu);
+                if (m21[bestIdx2] != NONE16) { m12[m21[bestIdx2]] = NONE16; nm--; }         // :530-534
+                m12[q.i1] = (unsigned short)bestIdx2; m21[bestIdx2] = (unsigned short)q.i1; matched[bestIdx2] = bestDist; nm++;
+                if (check_ori) { const int bin = rot_bin(q.angle, tang[bestIdx2]); hbin[q.i1] = (signed char)bin; hist[bin]++; }
+            }
+        }
+        __syncwarp();
     }
     if (check_ori) {
-        if (tid == 0) three_maxima(hist, keepbin[0], keepbin[1], keepbin[2]);
-        __syncthreads();
+        int kb0 = 0, kb1 = 0, kb2 = 0;
+        if (lane == 0) three_maxima(hist, kb0, kb1, kb2);
+        kb0 = __shfl_sync(0xffffffffu, kb0, 0); kb1 = __shfl_sync(0xffffffffu, kb1, 0); kb2 = __shfl_sync(0xffffffffu, kb2, 0);
         int removed = 0;
-        for (int i = tid; i < n1; i += SFI_THREADS) {
+        for (int i = lane; i < n1; i += 32) {
             const int b = hbin[i];
-            if (b < 0 || b == keepbin[0] || b == keepbin[1] || b == keepbin[2]) continue;
+            if (b < 0 || b == kb0 || b == kb1 || b == kb2) continue;
             if (m12[i] != NONE16) { m12[i] = NONE16; ++removed; }
         }
-        if (removed) atomicSub(&s_nm, removed);
-        __syncthreads();
+#pragma unroll
+        for (int o = 16; o; o >>= 1) removed += __shfl_xor_sync(0xffffffffu, removed, o);
+        nm -= removed;
+        __syncwarp();
     }
-    for (int i = tid; i < n1; i += SFI_THREADS) {
+    for (int i = lane; i < n1; i += 32) {
         const int m = m12[i] == NONE16 ? -1 : (int)m12[i];
         m12g[i] = m;
         if (pm && m >= 0) { pm[2 * i] = k2[m].x; pm[2 * i + 1] = k2[m].y; }                 // :552-554
     }
-    if (tid == 0) nmatches[p] = s_nm;
+    if (lane == 0) nmatches[p] = nm;
 }
 
 extern "C" int afv_search_for_initialization(int desc_type, const afv_keypoint* d_kps, const void* d_desc,
@@ -520,24 +559,55 @@ extern "C" int afv_search_for_initialization(int desc_type, const afv_keypoint* 
     if (D < 0 || !d_kps || !d_desc || !d_kpsize || !d_n || !d_pair_a || !d_pair_b || !d_matches12 ||
         !d_nmatches || B < 1 || P < 0 || cap < 1) { afv_set_error("afv_search_for_initialization: bad argument"); return AFV_ERR_INVALID; }
     if (P == 0) return AFV_OK;
-    if (cap >= 65535) { afv_set_error("cap too large for the 16-bit slot indices"); return AFV_ERR_INVALID; }
+    if (cap >= 65535) { afv_set_error("cap too large for the 16-bit indices"); return AFV_ERR_INVALID; }
+    cudaStream_t st = as_stream(cuda_stream);
+    const bool binary = desc_type != AFV_FEAT_SIFT128;
     const int Dpad = (D + 3) & ~3;
-    const size_t base = sfi_base_bytes(cap) + sfi_topk_bytes();
-    if (base > 200 * 1024) { afv_set_error("cap %d too large for the shared-memory staging", cap); return AFV_ERR_INVALID; }
-    int stage = desc_type != AFV_FEAT_SIFT128 && Dpad <= 64 && base + (size_t)cap * Dpad <= 200 * 1024;
-    size_t smem = base + (stage ? (size_t)cap * Dpad : 0);
-    static size_t configured = 0;
-    if (smem > configured) {
-        AFV_CUDA_CHECK(cudaFuncSetAttribute(k_search_init, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
+    const size_t baseA = sfl_base_bytes(cap);
+    const int stage = binary && Dpad <= 64 && baseA + (size_t)cap * Dpad <= 200 * 1024;
+    const size_t smemA = baseA + (stage ? (size_t)cap * Dpad : 0);
+    const size_t smemB = sfr_warp_bytes(cap) * SFR_WARPS;
+    if (smemA > 220 * 1024 || smemB > 220 * 1024) { afv_set_error("cap %d too large for the shared-memory staging", cap); return AFV_ERR_INVALID; }
+    static size_t confA[2] = {0, 0}, confB[2] = {0, 0};
+    if (smemA > confA[binary]) {
+        AFV_CUDA_CHECK(binary ? cudaFuncSetAttribute(k_sfi_lists<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemA)
+                              : cudaFuncSetAttribute(k_sfi_lists<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemA));
+        confA[binary] = smemA;
     }
+    if (smemB > confB[binary]) {
+        AFV_CUDA_CHECK(binary ? cudaFuncSetAttribute(k_sfi_resolve<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemB)
+                              : cudaFuncSetAttribute(k_sfi_resolve<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemB));
+        confB[binary] = smemB;
+    }
+    // candidate pool: entries per pair (u32 for Hamming: dist<<20 | index; u64 for L2: float bits<<32 | index)
+    const int pool_cap = 64 * 1024;
+    const size_t esz = binary ? 4 : 8;
+    unsigned char* scratch = nullptr;
+    const size_t pool_bytes = (size_t)P * pool_cap * esz, meta_bytes = (size_t)P * cap * sizeof(SfiQMeta), nq_bytes = (size_t)P * sizeof(int);
+    AFV_CUDA_CHECK(cudaMallocAsync((void**)&scratch, pool_bytes + meta_bytes + nq_bytes + 256, st));
+    void* pool = scratch;
+    SfiQMeta* qmeta = reinterpret_cast<SfiQMeta*>(scratch + pool_bytes);
+    int* nq = reinterpret_cast<int*>(scratch + pool_bytes + meta_bytes);
     const float invW = (float)AFV_GRID_COLS / (max_x - min_x), invH = (float)AFV_GRID_ROWS / (max_y - min_y);
-    AfvProfScope ps("k_search_init", as_stream(cuda_stream));
-    k_search_init<<<P, SFI_THREADS, smem, as_stream(cuda_stream)>>>(desc_type, D, Dpad, stage, d_kps, (const uint8_t*)d_desc, d_kpsize,
-        d_n, cap, d_pair_a, d_pair_b, min_x, min_y, invW, invH, max_kpt_size, d_prev_matched, (float)window, th_low, nnratio,
-        check_orientation, d_matches12, d_nmatches);
-    ++g_afv_launches;
+    {
+        AfvProfScope ps("k_sfi_lists", st);
+        if (binary) k_sfi_lists<true><<<P, SFL_THREADS, smemA, st>>>(desc_type, D, Dpad, stage, d_kps, (const uint8_t*)d_desc, d_kpsize, d_n, cap,
+                d_pair_a, d_pair_b, min_x, min_y, invW, invH, max_kpt_size, d_prev_matched, (float)window, pool, pool_cap, qmeta, nq);
+        else k_sfi_lists<false><<<P, SFL_THREADS, smemA, st>>>(desc_type, D, Dpad, stage, d_kps, (const uint8_t*)d_desc, d_kpsize, d_n, cap,
+                d_pair_a, d_pair_b, min_x, min_y, invW, invH, max_kpt_size, d_prev_matched, (float)window, pool, pool_cap, qmeta, nq);
+        ++g_afv_launches;
+    }
+    {
+        AfvProfScope ps("k_sfi_resolve", st);
+        const int grid = (P + SFR_WARPS - 1) / SFR_WARPS;
+        if (binary) k_sfi_resolve<true><<<grid, SFR_WARPS * 32, smemB, st>>>(desc_type, D, d_kps, (const uint8_t*)d_desc, d_kpsize, d_n, cap, d_pair_a, d_pair_b, P,
+                min_x, min_y, invW, invH, max_kpt_size, d_prev_matched, (float)window, th_low, nnratio, check_orientation, pool, pool_cap, qmeta, nq, d_matches12, d_nmatches);
+        else k_sfi_resolve<false><<<grid, SFR_WARPS * 32, smemB, st>>>(desc_type, D, d_kps, (const uint8_t*)d_desc, d_kpsize, d_n, cap, d_pair_a, d_pair_b, P,
+                min_x, min_y, invW, invH, max_kpt_size, d_prev_matched, (float)window, th_low, nnratio, check_orientation, pool, pool_cap, qmeta, nq, d_matches12, d_nmatches);
+        ++g_afv_launches;
+    }
     AFV_CUDA_CHECK(cudaGetLastError());
+    AFV_CUDA_CHECK(cudaFreeAsync(scratch, st));
     return AFV_OK;
 }
 
