@@ -270,9 +270,10 @@ __device__ __forceinline__ void three_maxima(const int* cnt, int& ind1, int& ind
 //                stealing / rotation-histogram logic.  A query whose list did not fit the pool is rescanned brute force
 //                with the same candidate definition (exact fallback).
 #define SFL_THREADS 256
-#define SFR_WARPS 4
+#define SFR_WARPS 2
+#define SFR_QSTAGE 512
 __host__ __device__ inline size_t sfl_base_bytes(int cap) { return (((size_t)cap * (4 * 2 + 2 * 4)) + 15) & ~(size_t)15; }
-__host__ __device__ inline size_t sfr_warp_bytes(int cap) { return (((size_t)cap * (4 * 2 + 2 * 3 + 1)) + 15) & ~(size_t)15; }
+__host__ __device__ inline size_t sfr_warp_bytes(int cap) { return ((((size_t)cap * (4 * 2 + 2 * 3 + 1)) + 15) & ~(size_t)15) + (size_t)SFR_QSTAGE * 16; }
 
 struct SfiQuery { float x, y; int c0, c1, r0, r1; bool ok; };
 struct SfiQMeta { int i1, off, cnt; float angle; };         // per query, written by k_sfi_lists
@@ -446,6 +447,7 @@ __global__ void __launch_bounds__(SFR_WARPS * 32) k_sfi_resolve(int desc_type, i
     unsigned short* m21 = reinterpret_cast<unsigned short*>(tang + cap);
     unsigned short* m12 = m21 + cap; unsigned short* tcell = m12 + cap;
     signed char* hbin = reinterpret_cast<signed char*>(tcell + cap);
+    SfiQMeta* qms = reinterpret_cast<SfiQMeta*>(base + sfr_warp_bytes(cap) - (size_t)SFR_QSTAGE * 16);
     __shared__ int hist_all[SFR_WARPS][AFV_HISTO_LENGTH + 2];
     int* hist = hist_all[wid];
     const unsigned short NONE16 = 0xffff;
@@ -474,24 +476,36 @@ __global__ void __launch_bounds__(SFR_WARPS * 32) k_sfi_resolve(int desc_type, i
     __syncwarp();
     int nm = 0;                                                    // lane 0's copy is authoritative
 
+    // stage the query metadata (16 B each) so the sequential loop never waits on it, and prefetch the first 128
+    // candidates of query qi+1 while query qi is resolved
+    for (int i = lane; i < min(nq, SFR_QSTAGE); i += 32) qms[i] = qm[i];
+    __syncwarp();
+    auto load_keys = [&](const SfiQMeta& m, int j0, unsigned long long* key) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int j = j0 + u * 32 + lane;
+            key[u] = KEY_NONE;
+            if (m.off >= 0 && j < m.cnt) {
+                if (BINARY) {
+                    const uint32_t e = reinterpret_cast<const uint32_t*>(pool_v)[(long long)p * pool_cap + m.off + j];
+                    key[u] = ((unsigned long long)__float_as_uint((float)(e >> 20)) << 32) | (e & 0xfffffu);
+                } else key[u] = reinterpret_cast<const unsigned long long*>(pool_v)[(long long)p * pool_cap + m.off + j];
+            }
+        }
+    };
+    unsigned long long knext[4] = {KEY_NONE, KEY_NONE, KEY_NONE, KEY_NONE};
+    if (nq > 0) { const SfiQMeta m0 = qms[0]; load_keys(m0, 0, knext); }
     for (int qi = 0; qi < nq; ++qi) {
-        const SfiQMeta q = qm[qi];
+        const SfiQMeta q = qi < SFR_QSTAGE ? qms[qi] : qm[qi];
+        unsigned long long key[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) key[u] = knext[u];
+        if (qi + 1 < nq) { const SfiQMeta mn = (qi + 1) < SFR_QSTAGE ? qms[qi + 1] : qm[qi + 1]; load_keys(mn, 0, knext); }
         if (q.cnt == 0) continue;
         Top2 t; t.k1 = t.k2 = KEY_NONE;
         if (q.off >= 0) {
-            for (int j0 = 0; j0 < q.cnt; j0 += 128) {              // 4 independent loads in flight per lane
-                unsigned long long key[4];
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const int j = j0 + u * 32 + lane;
-                    key[u] = KEY_NONE;
-                    if (j < q.cnt) {
-                        if (BINARY) {
-                            const uint32_t e = reinterpret_cast<const uint32_t*>(pool_v)[(long long)p * pool_cap + q.off + j];
-                            key[u] = ((unsigned long long)__float_as_uint((float)(e >> 20)) << 32) | (e & 0xfffffu);
-                        } else key[u] = reinterpret_cast<const unsigned long long*>(pool_v)[(long long)p * pool_cap + q.off + j];
-                    }
-                }
+            for (int j0 = 0; j0 < q.cnt; j0 += 128) {
+                if (j0 > 0) load_keys(q, j0, key);
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
                     if (key[u] == KEY_NONE) continue;
@@ -578,6 +592,14 @@ extern "C" int afv_search_for_initialization(int desc_type, const afv_keypoint* 
         AFV_CUDA_CHECK(binary ? cudaFuncSetAttribute(k_sfi_resolve<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemB)
                               : cudaFuncSetAttribute(k_sfi_resolve<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemB));
         confB[binary] = smemB;
+    }
+    static bool pool_cfg = false;
+    if (!pool_cfg) {        // keep freed scratch cached in the stream-ordered pool instead of returning it to the OS
+        int dev = 0; cudaMemPool_t mp;
+        if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetDefaultMemPool(&mp, dev) == cudaSuccess) {
+            unsigned long long thr = ~0ull; cudaMemPoolSetAttribute(mp, cudaMemPoolAttrReleaseThreshold, &thr);
+        }
+        pool_cfg = true;
     }
     // candidate pool: entries per pair (u32 for Hamming: dist<<20 | index; u64 for L2: float bits<<32 | index)
     const int pool_cap = 64 * 1024;

@@ -130,20 +130,49 @@ __global__ void __launch_bounds__(256) k_fast(const __grid_constant__ AfvParams 
     const unsigned t2 = 2u * (unsigned)t;
     // |p - v| > t  <=>  (unsigned)(p - v + t) > 2t
 #define FAR(p, v) ((unsigned)((int)(p) - (v) + t) > t2)
-    // stage 1: any arc of 9 contains one pixel of each antipodal pair -> both pairs (0,8) and (4,12) must have a far pixel
-    for (int i0 = 0; i0 < FT_RW * FT_RH; i0 += 256) {
-        const int i = i0 + tid;
-        bool pass = false;
-        if (i < FT_RW * FT_RH) {
-            const int r = i / FT_RW, c = i % FT_RW;
-            const int gx = x0 - 1 + c, gy = y0 - 1 + r;
-            if (gx >= 3 && gy >= 3 && gx < L.w - 3 && gy < L.h - 3) {
-                const uint8_t* p = pb + (r + 3) * PITCH + 4 + (c + 3);
-                const int v = p[0];
-                pass = (FAR(p[3 * PITCH], v) | FAR(p[-3 * PITCH], v)) & (FAR(p[3], v) | FAR(p[-3], v));
+    // stage 1: any arc of 9 contains one pixel of each antipodal pair -> both pairs (0,8) and (4,12) must have a far
+    // pixel.  One thread walks 9 rows of one column with a rolling 15-pixel register window (centre, 3 above, 3 below
+    // come from the window; only left/right are extra loads) and appends its survivors with one warp-aggregated atomic.
+    static_assert(FT_RH == 18, "two halves of 9 rows");
+    for (int round = 0; round < 2; ++round) {
+        if (round == 1 && tid >= 32) break;                      // items 256..259 live in warp 0
+        const int item = round * 256 + tid;
+        uint32_t smask = 0;
+        int c = 0, half = 0;
+        if (item < 2 * FT_RW) {
+            half = item >= FT_RW; c = item - half * FT_RW;
+            const int gx = x0 - 1 + c;
+            if (gx >= 3 && gx < L.w - 3) {
+                const uint8_t* pc = pb + 4 + (c + 3) + (9 * half) * PITCH;      // window row k <-> region row 9*half + k - 3
+                int col[15];
+#pragma unroll
+                for (int k = 0; k < 15; ++k) col[k] = pc[k * PITCH];
+#pragma unroll
+                for (int j = 0; j < 9; ++j) {
+                    const int gy = y0 - 1 + 9 * half + j;
+                    const int v = col[j + 3];
+                    const bool pass = (gy >= 3) & (gy < L.h - 3) &
+                                      ((FAR(col[j + 6], v) | FAR(col[j], v)) & (FAR(pc[(j + 3) * PITCH + 3], v) | FAR(pc[(j + 3) * PITCH - 3], v)));
+                    smask |= (uint32_t)pass << j;
+                }
             }
         }
-        warp_push(pass, (uint16_t)i, slist, &nstage1, lane);
+        const int cnt = __popc(smask);
+        int incl = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int t_ = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t_; }
+        const int total = __shfl_sync(0xffffffffu, incl, 31);
+        int base = 0;
+        if (total) {
+            if (lane == 31) base = atomicAdd(&nstage1, total);
+            base = __shfl_sync(0xffffffffu, base, 31);
+        }
+        int o = base + incl - cnt;
+        while (smask) {
+            const int j = __ffs(smask) - 1;
+            smask &= smask - 1;
+            slist[o++] = (uint16_t)((9 * half + j) * FT_RW + c);
+        }
     }
     __syncthreads();
     // stage 2: full 16-point masks for the survivors
