@@ -80,8 +80,9 @@ struct afv_extractor {
     uint8_t* blur[AFV_MAX_LEVELS];
     uint32_t* cand[AFV_MAX_LEVELS]; float* cand_resp[AFV_MAX_LEVELS];
     uint2* det[AFV_MAX_LEVELS]; uint2* keep[AFV_MAX_LEVELS];
-    uint16_t* tab[AFV_MAX_LEVELS];    // xofs,xc1,yofs,yc1 packed
+    uint32_t* tab[AFV_MAX_LEVELS];    // xtab | ytab (offset << 16 | c1)
     int* counts; int* status;
+    AfvTile* tiles; int tiles_cap;
     afv_keypoint* o_kps; uint8_t* o_desc; float* o_size; int* o_n;   // device outputs for the host-buffer API
     int* h_status; int* h_counts;     // pinned
     int max_stride[AFV_MAX_LEVELS], max_lh[AFV_MAX_LEVELS], cand_cap[AFV_MAX_LEVELS], det_cap[AFV_MAX_LEVELS], keep_cap[AFV_MAX_LEVELS];
@@ -176,13 +177,25 @@ static int configure_geometry(afv_extractor* ex, int w, int h) {
         L.det_cap = ex->det_cap[l]; L.det = ex->det[l];
         L.keep_cap = ex->keep_cap[l]; L.keep = ex->keep[l];
         if (l > 0) {
-            std::vector<uint16_t> t(2 * (size_t)lw[l] + 2 * (size_t)lh[l]);
-            lin_exact_tables(lw[l - 1], lw[l], t.data(), t.data() + lw[l]);
-            lin_exact_tables(lh[l - 1], lh[l], t.data() + 2 * lw[l], t.data() + 2 * lw[l] + lh[l]);
-            AFV_CUDA_CHECK(cudaMemcpy(ex->tab[l], t.data(), t.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
-            L.xofs = ex->tab[l]; L.xc1 = ex->tab[l] + lw[l];
-            L.yofs = ex->tab[l] + 2 * lw[l]; L.yc1 = ex->tab[l] + 2 * lw[l] + lh[l];
+            const int wpad = (lw[l] + 3) & ~3;
+            std::vector<uint16_t> xo(lw[l]), xc(lw[l]), yo(lh[l]), yc(lh[l]);
+            lin_exact_tables(lw[l - 1], lw[l], xo.data(), xc.data());
+            lin_exact_tables(lh[l - 1], lh[l], yo.data(), yc.data());
+            std::vector<uint32_t> t((size_t)wpad + lh[l]);
+            for (int x = 0; x < wpad; ++x) { const int xx = x < lw[l] ? x : lw[l] - 1; t[x] = ((uint32_t)xo[xx] << 16) | xc[xx]; }
+            for (int y = 0; y < lh[l]; ++y) t[wpad + y] = ((uint32_t)yo[y] << 16) | yc[y];
+            AFV_CUDA_CHECK(cudaMemcpy(ex->tab[l], t.data(), t.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+            L.xtab = ex->tab[l]; L.ytab = ex->tab[l] + wpad;
         }
+    }
+    {
+        std::vector<AfvTile> tl;
+        for (int l = 0; l < ex->nlevels; ++l)
+            for (int y = 0; y < lh[l]; y += AFV_TILE_H)
+                for (int x = 0; x < lw[l]; x += AFV_TILE_W) { AfvTile t; t.level = (short)l; t.pad = 0; t.x0 = (short)x; t.y0 = (short)y; tl.push_back(t); }
+        if ((int)tl.size() > ex->tiles_cap) { afv_set_error("internal: tile table too small"); return AFV_ERR_INVALID; }
+        AFV_CUDA_CHECK(cudaMemcpy(ex->tiles, tl.data(), tl.size() * sizeof(AfvTile), cudaMemcpyHostToDevice));
+        P.tiles = ex->tiles; P.ntiles = (int)tl.size();
     }
     ex->cur_w = w; ex->cur_h = h;
     return AFV_OK;
@@ -242,9 +255,14 @@ extern "C" int afv_extractor_create(afv_extractor** out, int feature_id, int nfe
         if ((rc = dev_alloc(ex, &ex->cand_resp[l], (size_t)ex->cand_cap[l] * B))) break;
         if ((rc = dev_alloc(ex, &ex->det[l], (size_t)ex->det_cap[l] * B))) break;
         if ((rc = dev_alloc(ex, &ex->keep[l], (size_t)ex->keep_cap[l] * B))) break;
-        if ((rc = dev_alloc(ex, &ex->tab[l], 2 * (size_t)(lw[l] + lh[l]) + 16))) break;
+        if ((rc = dev_alloc(ex, &ex->tab[l], (size_t)(lw[l] + lh[l]) + 16))) break;
     }
     const int ocap = nfeatures + 3 * n_octaves;
+    if (rc == AFV_OK) {
+        ex->tiles_cap = 0;
+        for (int l = 0; l < n_octaves; ++l) ex->tiles_cap += ((lw[l] + AFV_TILE_W - 1) / AFV_TILE_W + 1) * ((lh[l] + AFV_TILE_H - 1) / AFV_TILE_H + 1);
+        rc = dev_alloc(ex, &ex->tiles, (size_t)ex->tiles_cap);
+    }
     if (rc == AFV_OK) rc = dev_alloc(ex, &ex->counts, 4 * AFV_MAX_LEVELS * B);
     if (rc == AFV_OK) rc = dev_alloc(ex, &ex->status, B);
     if (rc == AFV_OK) rc = dev_alloc(ex, &ex->o_kps, (size_t)ocap * B);

@@ -32,12 +32,17 @@ struct AfvLevel {
     int keep_cap;             // q_ext + 3 (+ slack)
     uint2* keep;              // [frame][keep_cap] octree output in node-list order
     // resize tables for building this level from level l-1 (INTER_LINEAR_EXACT 8.8 fixed point)
-    const uint16_t* xofs; const uint16_t* xc1;   // [w]
-    const uint16_t* yofs; const uint16_t* yc1;   // [h]
+    const uint32_t* xtab;     // [w rounded up to 4] source offset << 16 | c1 (8.8 fixed point, c0 = 256 - c1)
+    const uint32_t* ytab;     // [h]
 };
+
+#define AFV_TILE_W 128
+#define AFV_TILE_H 32
+struct AfvTile { short level, pad; short x0, y0; };      // one stencil tile of one pyramid level
 
 struct AfvParams {
     int nlevels, B;
+    const AfvTile* tiles; int ntiles;   // AFV_TILE_W x AFV_TILE_H tiles of all levels (k_fast / k_blur grids)
     int W, H;                 // level-0 size
     int fast_th;
     int n_ini; float hX;      // octree roots (reference src/ORBextractor.cc:243-245)

@@ -363,7 +363,7 @@ __global__ void __launch_bounds__(SFL_THREADS) k_sfi_lists(int desc_type, int D,
             uint32_t v;
             if ((D & 3) == 0) v = reinterpret_cast<const uint32_t*>(row)[w];
             else { v = 0; for (int b = 0; b < 4; ++b) { const int o = w * 4 + b; if (o < D) v |= (uint32_t)row[o] << (8 * b); } }
-            reinterpret_cast<uint32_t*>(sdesc)[i] = v;
+            reinterpret_cast<uint32_t*>(sdesc)[(size_t)w * cap + r] = v;      // word-interleaved: lanes on consecutive slots hit consecutive banks
         }
     }
     __syncthreads();
@@ -412,9 +412,9 @@ __global__ void __launch_bounds__(SFL_THREADS) k_sfi_lists(int desc_type, int D,
                         if (BINARY) {
                             int d = 0;
                             if (stage_desc) {
-                                const uint32_t* y32 = reinterpret_cast<const uint32_t*>(sdesc) + (long long)sl * nw;
+                                const uint32_t* y32 = reinterpret_cast<const uint32_t*>(sdesc) + sl;
 #pragma unroll
-                                for (int w = 0; w < 16; ++w) if (w < nw) d += __popc(qd[w] ^ y32[w]);
+                                for (int w = 0; w < 16; ++w) if (w < nw) d += __popc(qd[w] ^ y32[(size_t)w * cap]);
                             } else d = hamming_bytes(d1 + (long long)i1 * D, d2 + (long long)i2 * D, D);
                             reinterpret_cast<uint32_t*>(pool_v)[(long long)p * pool_cap + pos] = ((uint32_t)d << 20) | (uint32_t)i2;
                         } else {

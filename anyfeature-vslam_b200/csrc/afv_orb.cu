@@ -14,7 +14,7 @@
 #include "afv_common.cuh"
 #include <stdio.h>
 
-static __constant__ int8_t c_pattern[1024] = {
+static __constant__ __align__(16) int8_t c_pattern[1024] = {
 #include "orb_pattern.inc"
 };
 static __constant__ int c_umax[16] = {15, 15, 15, 15, 14, 14, 14, 13, 13, 12, 11, 10, 9, 8, 6, 3};
@@ -28,6 +28,9 @@ __device__ __forceinline__ int refl101(int i, int n) {
 // ------------------------------------------------------------------------------------------------------
 // K2: pyramid level from the previous one.  thread = 4 consecutive output pixels (one 32-bit store).
 // ------------------------------------------------------------------------------------------------------
+// Source pixels come in as 3 aligned 32-bit words per source row (the 4 outputs of a thread span <= 9 source bytes
+// at scale 1.2), taps are cut out with funnel shifts; coefficients come as one 128-bit load of 4 packed table
+// entries (offset << 16 | c1).
 __global__ void __launch_bounds__(256) k_resize(const __grid_constant__ AfvParams P, int l) {
     const AfvLevel& D = P.lv[l];
     const AfvLevel& S = P.lv[l - 1];
@@ -37,17 +40,29 @@ __global__ void __launch_bounds__(256) k_resize(const __grid_constant__ AfvParam
     if (y >= D.h || x0 >= D.w) return;
     const uint8_t* src = S.img + (long long)f * S.img_fstride;
     uint8_t* dst = const_cast<uint8_t*>(D.img) + (long long)f * D.img_fstride + (long long)y * D.img_stride;
-    const int yo = D.yofs[y], c1y = D.yc1[y], c0y = 256 - c1y;
-    const uint8_t* r0 = src + (long long)yo * S.img_stride;
-    const uint8_t* r1 = src + (long long)min(yo + 1, S.h - 1) * S.img_stride;
+    const uint32_t yt = D.ytab[y];
+    const int yo = yt >> 16, c1y = yt & 0xffff, c0y = 256 - c1y;
+    const uint4 xt = *reinterpret_cast<const uint4*>(D.xtab + x0);       // table padded to a multiple of 4 entries
+    const uint32_t xe[4] = {xt.x, xt.y, xt.z, xt.w};
+    const int xbase = (int)(xe[0] >> 16) & ~3;
+    const int lastw = (S.img_stride >> 2) - 1;
+    const int wb = xbase >> 2;
+    const uint32_t* r0 = reinterpret_cast<const uint32_t*>(src + (long long)yo * S.img_stride);
+    const uint32_t* r1 = reinterpret_cast<const uint32_t*>(src + (long long)min(yo + 1, S.h - 1) * S.img_stride);
+    const int i0 = min(wb, lastw), i1 = min(wb + 1, lastw), i2 = min(wb + 2, lastw);
+    const uint32_t a0 = r0[i0], a1 = r0[i1], a2 = r0[i2];
+    const uint32_t b0 = r1[i0], b1 = r1[i1], b2 = r1[i2];
     uint32_t out = 0;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-        const int x = min(x0 + k, D.w - 1);
-        const int xo = D.xofs[x], c1 = D.xc1[x], c0 = 256 - c1;
-        const int x1 = min(xo + 1, S.w - 1);
-        const uint32_t h0 = c0 * r0[xo] + c1 * r0[x1];
-        const uint32_t h1 = c0 * r1[xo] + c1 * r1[x1];
+        const int xo = xe[k] >> 16, c1 = xe[k] & 0xffff, c0 = 256 - c1;
+        const int bo = xo - xbase;                                         // 0..8: byte offset of the left tap
+        const bool hiw = bo >= 4;
+        const int sh = (bo & 3) * 8;
+        const uint32_t pa = __funnelshift_r(hiw ? a1 : a0, hiw ? a2 : a1, sh);   // bytes bo, bo+1 of row 0
+        const uint32_t pb = __funnelshift_r(hiw ? b1 : b0, hiw ? b2 : b1, sh);
+        const uint32_t h0 = c0 * (pa & 0xff) + c1 * ((pa >> 8) & 0xff);
+        const uint32_t h1 = c0 * (pb & 0xff) + c1 * ((pb >> 8) & 0xff);
         const uint32_t v = (uint32_t)c0y * h0 + (uint32_t)c1y * h1;
         out |= ((v + (1u << 15)) >> 16) << (8 * k);
     }
@@ -57,15 +72,14 @@ __global__ void __launch_bounds__(256) k_resize(const __grid_constant__ AfvParam
 // ------------------------------------------------------------------------------------------------------
 // K3: FAST-9/16 + NMS.  Tile 128x16 (+4 halo), 256 threads.
 // ------------------------------------------------------------------------------------------------------
-#define FT_W 128
-#define FT_H 16
+#define FT_W AFV_TILE_W
+#define FT_H AFV_TILE_H
 #define FT_PW (FT_W + 8)
 #define FT_PH (FT_H + 8)
 #define FT_RW (FT_W + 2)
 #define FT_RH (FT_H + 2)
 #define FT_SW 132
-
-struct FastTiles { int start[AFV_MAX_LEVELS + 1]; int tiles_x[AFV_MAX_LEVELS]; };
+#define FT_HALF (FT_RH / 2)           // rows walked by one stage-1 thread
 
 __device__ __forceinline__ bool has_arc9(uint32_t m) {
     m |= m << 16;
@@ -93,7 +107,7 @@ __device__ __forceinline__ void warp_push(bool pass, uint16_t val, uint16_t* lis
     if (pass) list[base + __popc(m & ((1u << lane) - 1))] = val;
 }
 
-__global__ void __launch_bounds__(256) k_fast(const __grid_constant__ AfvParams P, const __grid_constant__ FastTiles T) {
+__global__ void __launch_bounds__(256) k_fast(const __grid_constant__ AfvParams P) {
     __shared__ __align__(16) uint32_t pixw[FT_PH][FT_WP];
     __shared__ __align__(4) uint8_t score[FT_RH][FT_SW];
     __shared__ uint16_t slist[FT_RW * FT_RH];        // stage-1 survivors
@@ -101,26 +115,31 @@ __global__ void __launch_bounds__(256) k_fast(const __grid_constant__ AfvParams 
     __shared__ uint32_t surv[(FT_W / 2) * (FT_H / 2) + 64];
     __shared__ int nstage1, ncorner, nsurv, gbase;
 
-    int l = 0;
-    while (l + 1 < P.nlevels && (int)blockIdx.x >= T.start[l + 1]) ++l;
+    const AfvTile ti = P.tiles[blockIdx.x];
+    const int l = ti.level;
     const AfvLevel& L = P.lv[l];
-    const int tile = blockIdx.x - T.start[l];
-    const int tx = tile % T.tiles_x[l], ty = tile / T.tiles_x[l];
     const int f = blockIdx.y;
-    const int x0 = tx * FT_W, y0 = ty * FT_H;
-    const int tid = threadIdx.x, lane = tid & 31;
+    const int x0 = ti.x0, y0 = ti.y0;
+    const int tid = threadIdx.x, lane = tid & 31, wrp = tid >> 5;
     const uint8_t* img = L.img + (long long)f * L.img_fstride;
     const int t = P.fast_th;
 
     if (tid == 0) { nstage1 = 0; ncorner = 0; nsurv = 0; }
-    // stage the pixel tile: data word q (pixels x0-4+4q ..) lives at pixw[r][q+1]; rows outside the image read as 0
-    for (int i = tid; i < FT_PH * FT_WP; i += 256) {
-        const int r = i / FT_WP, q = i % FT_WP - 1;
-        const int gy = y0 - 4 + r, gx = x0 - 4 + q * 4;
-        uint32_t v = 0;
-        if (q >= 0 && q < FT_PW / 4 && gy >= 0 && gy < L.h && gx >= 0 && gx < L.img_stride)
-            v = *reinterpret_cast<const uint32_t*>(img + (long long)gy * L.img_stride + gx);
-        pixw[r][q + 1] = v;
+    // stage the pixel tile: data word q (pixels x0-4+4q ..) lives at pixw[r][q+1]; rows outside the image read as 0.
+    // warp w stages rows w, w+8, ...; lane = word slot (slots 32..35 by lanes 0..3)
+    for (int r = wrp; r < FT_PH; r += 8) {
+        const int gy = y0 - 4 + r;
+        const bool rowok = gy >= 0 && gy < L.h;
+        const uint8_t* rowp = img + (long long)gy * L.img_stride;
+#pragma unroll
+        for (int part = 0; part < 2; ++part) {
+            const int slot = part * 32 + lane;
+            if (slot >= FT_WP) break;
+            const int q = slot - 1, gx = x0 - 4 + q * 4;
+            uint32_t v = 0;
+            if (rowok && q >= 0 && q < FT_PW / 4 && gx >= 0 && gx < L.img_stride) v = *reinterpret_cast<const uint32_t*>(rowp + gx);
+            pixw[r][slot] = v;
+        }
     }
     for (int i = tid; i < FT_RH * FT_SW / 4; i += 256) reinterpret_cast<uint32_t*>(&score[0][0])[i] = 0;
     __syncthreads();
@@ -133,7 +152,7 @@ __global__ void __launch_bounds__(256) k_fast(const __grid_constant__ AfvParams 
     // stage 1: any arc of 9 contains one pixel of each antipodal pair -> both pairs (0,8) and (4,12) must have a far
     // pixel.  One thread walks 9 rows of one column with a rolling 15-pixel register window (centre, 3 above, 3 below
     // come from the window; only left/right are extra loads) and appends its survivors with one warp-aggregated atomic.
-    static_assert(FT_RH == 18, "two halves of 9 rows");
+    static_assert(FT_RH == 2 * FT_HALF && FT_HALF <= 32, "two halves");
     for (int round = 0; round < 2; ++round) {
         if (round == 1 && tid >= 32) break;                      // items 256..259 live in warp 0
         const int item = round * 256 + tid;
@@ -143,18 +162,21 @@ __global__ void __launch_bounds__(256) k_fast(const __grid_constant__ AfvParams 
             half = item >= FT_RW; c = item - half * FT_RW;
             const int gx = x0 - 1 + c;
             if (gx >= 3 && gx < L.w - 3) {
-                const uint8_t* pc = pb + 4 + (c + 3) + (9 * half) * PITCH;      // window row k <-> region row 9*half + k - 3
-                int col[15];
+                const uint8_t* pc = pb + 4 + (c + 3) + (FT_HALF * half) * PITCH;   // window row k <-> region row FT_HALF*half + k - 3
+                // rows that are real centres: 3 <= gy < h-3 with gy = y0 - 1 + FT_HALF*half + j
+                const int gy0 = y0 - 1 + FT_HALF * half;
+                const int jlo = max(0, 3 - gy0), jhi = min(FT_HALF, L.h - 3 - gy0);
+                int col[FT_HALF + 6];
 #pragma unroll
-                for (int k = 0; k < 15; ++k) col[k] = pc[k * PITCH];
+                for (int k = 0; k < FT_HALF + 6; ++k) col[k] = pc[k * PITCH];
 #pragma unroll
-                for (int j = 0; j < 9; ++j) {
-                    const int gy = y0 - 1 + 9 * half + j;
+                for (int j = 0; j < FT_HALF; ++j) {
                     const int v = col[j + 3];
-                    const bool pass = (gy >= 3) & (gy < L.h - 3) &
-                                      ((FAR(col[j + 6], v) | FAR(col[j], v)) & (FAR(pc[(j + 3) * PITCH + 3], v) | FAR(pc[(j + 3) * PITCH - 3], v)));
+                    const bool pass = ((FAR(col[j + 6], v) | FAR(col[j], v)) & (FAR(pc[(j + 3) * PITCH + 3], v) | FAR(pc[(j + 3) * PITCH - 3], v)));
                     smask |= (uint32_t)pass << j;
                 }
+                const uint32_t rowmask = jhi > jlo ? (((jhi >= 32) ? 0xffffffffu : ((1u << jhi) - 1u)) & ~((1u << jlo) - 1u)) : 0u;
+                smask &= rowmask;
             }
         }
         const int cnt = __popc(smask);
@@ -171,7 +193,7 @@ __global__ void __launch_bounds__(256) k_fast(const __grid_constant__ AfvParams 
         while (smask) {
             const int j = __ffs(smask) - 1;
             smask &= smask - 1;
-            slist[o++] = (uint16_t)((9 * half + j) * FT_RW + c);
+            slist[o++] = (uint16_t)((FT_HALF * half + j) * FT_RW + c);
         }
     }
     __syncthreads();
@@ -265,30 +287,34 @@ __device__ __forceinline__ float ord2f(uint32_t o) {
 }
 
 __device__ float harris7(const uint8_t* img, int w, int h, int stride, int x0, int y0) {
-    uint8_t pt[9][9];
-    if (x0 >= 4 && y0 >= 4 && x0 + 4 < w && y0 + 4 < h) {
+    // 9x9 support walked with three rolling rows (27 live pixels instead of 81: the full patch cost 128 registers)
+    const bool inner = x0 >= 4 && y0 >= 4 && x0 + 4 < w && y0 + 4 < h;
+    int ra[9], rb[9], rc[9];
+    auto load_row = [&](int rr, int* dst) {
+        if (inner) {
+            const uint8_t* p = img + (long long)(y0 - 4 + rr) * stride + x0 - 4;
 #pragma unroll
-        for (int r = 0; r < 9; ++r)
+            for (int c = 0; c < 9; ++c) dst[c] = p[c];
+        } else {
+            const uint8_t* p = img + (long long)refl101(y0 - 4 + rr, h) * stride;
 #pragma unroll
-            for (int c = 0; c < 9; ++c) pt[r][c] = img[(long long)(y0 - 4 + r) * stride + x0 - 4 + c];
-    } else {
-#pragma unroll
-        for (int r = 0; r < 9; ++r)
-#pragma unroll
-            for (int c = 0; c < 9; ++c)
-                pt[r][c] = img[(long long)refl101(y0 - 4 + r, h) * stride + refl101(x0 - 4 + c, w)];
-    }
+            for (int c = 0; c < 9; ++c) dst[c] = p[refl101(x0 - 4 + c, w)];
+        }
+    };
+    load_row(0, ra); load_row(1, rb);
     int a = 0, b = 0, c2 = 0;
 #pragma unroll
-    for (int r = 1; r < 8; ++r)
+    for (int r = 1; r < 8; ++r) {
+        load_row(r + 1, rc);
 #pragma unroll
         for (int c = 1; c < 8; ++c) {
-            const int Ix = ((int)pt[r][c + 1] - pt[r][c - 1]) * 2 + ((int)pt[r - 1][c + 1] - pt[r - 1][c - 1]) +
-                           ((int)pt[r + 1][c + 1] - pt[r + 1][c - 1]);
-            const int Iy = ((int)pt[r + 1][c] - pt[r - 1][c]) * 2 + ((int)pt[r + 1][c - 1] - pt[r - 1][c - 1]) +
-                           ((int)pt[r + 1][c + 1] - pt[r - 1][c + 1]);
+            const int Ix = (rb[c + 1] - rb[c - 1]) * 2 + (ra[c + 1] - ra[c - 1]) + (rc[c + 1] - rc[c - 1]);
+            const int Iy = (rc[c] - ra[c]) * 2 + (rc[c - 1] - ra[c - 1]) + (rc[c + 1] - ra[c + 1]);
             a += Ix * Ix; b += Iy * Iy; c2 += Ix * Iy;
         }
+#pragma unroll
+        for (int c = 0; c < 9; ++c) { ra[c] = rb[c]; rb[c] = rc[c]; }
+    }
     // ((float)a*b - (float)c*c - 0.04f*((float)a+b)*((float)a+b)) * scale^4, float32, one rounding per op
     const float scale = __fdiv_rn(1.f, 7140.f);            // 1/((1<<2)*7*255.f)
     const float s4 = __fmul_rn(__fmul_rn(__fmul_rn(scale, scale), scale), scale);
@@ -646,46 +672,50 @@ size_t afv_octree_smem_bytes(int mcap, int ncap) {
 //   row:    s = k0*p0; s = fma(kj, pj, s)                     column: s = k3*r0; s = fma(k3+j, r+j + r-j, s)
 // Tile 128x16 outputs, 256 threads; each thread finishes 8 output pixels (2 x uchar4 stores).
 // ------------------------------------------------------------------------------------------------------
-#define BT_W 128
-#define BT_H 16
+#define BT_W AFV_TILE_W
+#define BT_H AFV_TILE_H
 __constant__ float c_g7[7] = {0x1.1f5f62p-4f, 0x1.0c70fcp-3f, 0x1.869472p-3f, 0x1.ba95cp-3f,
                               0x1.869472p-3f, 0x1.0c70fcp-3f, 0x1.1f5f62p-4f};
 
-// Staged input: rows y0-3 .. y0+BT_H+2, byte columns x0-4 .. x0+BT_W+3 as 34 aligned words per row (interior
-// tiles: straight 32-bit loads; border tiles: per-byte REFLECT_101 gather).  Row pass: one thread = 4 outputs
-// from 3 words; column pass: one thread = 4 columns x 2 rows from 8 float4 rows.
+// Staged input: rows y0-3 .. y0+BT_H+2, byte columns x0-4 .. x0+BT_W+3 as 34 aligned words per row.  Words that lie
+// inside the image are straight 32-bit loads (the row index is reflected once per row); only words that straddle the
+// left/right border take the per-byte REFLECT_101 gather.  Row pass: one thread = 4 outputs from 3 words; column
+// pass: one thread = 4 columns x 4 rows from 10 float4 rows.
 #define BT_WW ((BT_W + 8) / 4)
-__global__ void __launch_bounds__(256) k_blur(const __grid_constant__ AfvParams P, const __grid_constant__ FastTiles T) {
+__device__ __forceinline__ uint32_t sat_u8(float v) {       // cv::saturate_cast<uchar>(float): round-half-even, clamp
+    uint32_t r;
+    asm("cvt.rni.sat.u8.f32 %0, %1;" : "=r"(r) : "f"(v));
+    return r;
+}
+__global__ void __launch_bounds__(256) k_blur(const __grid_constant__ AfvParams P) {
     __shared__ __align__(16) uint32_t in[BT_H + 6][BT_WW + 2];
     __shared__ __align__(16) float mid[BT_H + 6][BT_W];
-    int l = 0;
-    while (l + 1 < P.nlevels && (int)blockIdx.x >= T.start[l + 1]) ++l;
-    const AfvLevel& L = P.lv[l];
-    const int tile = blockIdx.x - T.start[l];
-    const int tx = tile % T.tiles_x[l], ty = tile / T.tiles_x[l];
-    const int f = blockIdx.y, tid = threadIdx.x;
-    const int x0 = tx * BT_W, y0 = ty * BT_H;
+    const AfvTile ti = P.tiles[blockIdx.x];
+    const AfvLevel& L = P.lv[ti.level];
+    const int f = blockIdx.y, tid = threadIdx.x, lane = tid & 31, wrp = tid >> 5;
+    const int x0 = ti.x0, y0 = ti.y0;
     const uint8_t* img = L.img + (long long)f * L.img_fstride;
-    const bool interior = x0 >= 4 && y0 >= 3 && x0 + BT_W + 4 <= L.w && y0 + BT_H + 3 <= L.h;
-    if (interior) {
-        for (int i = tid; i < (BT_H + 6) * BT_WW; i += 256) {
-            const int r = i / BT_WW, q = i % BT_WW;
-            in[r][q] = *reinterpret_cast<const uint32_t*>(img + (long long)(y0 - 3 + r) * L.img_stride + x0 - 4 + 4 * q);
-        }
-    } else {
-        for (int i = tid; i < (BT_H + 6) * BT_WW; i += 256) {
-            const int r = i / BT_WW, q = i % BT_WW;
-            const uint8_t* row = img + (long long)refl101(y0 - 3 + r, L.h) * L.img_stride;
-            uint32_t v = 0;
+    for (int r = wrp; r < BT_H + 6; r += 8) {
+        const uint8_t* row = img + (long long)refl101(y0 - 3 + r, L.h) * L.img_stride;
 #pragma unroll
-            for (int b2 = 0; b2 < 4; ++b2) v |= (uint32_t)row[refl101(x0 - 4 + 4 * q + b2, L.w)] << (8 * b2);
+        for (int part = 0; part < 2; ++part) {
+            const int q = part * 32 + lane;
+            if (q >= BT_WW) break;
+            const int gx = x0 - 4 + 4 * q;
+            uint32_t v;
+            if (gx >= 0 && gx + 3 < L.w) v = *reinterpret_cast<const uint32_t*>(row + gx);
+            else {
+                v = 0;
+#pragma unroll
+                for (int b2 = 0; b2 < 4; ++b2) v |= (uint32_t)row[refl101(gx + b2, L.w)] << (8 * b2);
+            }
             in[r][q] = v;
         }
     }
     __syncthreads();
-    // row pass: outputs 4q..4q+3 need staged bytes 4q+1 .. 4q+10
-    for (int i = tid; i < (BT_H + 6) * (BT_W / 4); i += 256) {
-        const int r = i / (BT_W / 4), q = i % (BT_W / 4);
+    // row pass: outputs 4q..4q+3 need staged bytes 4q+1 .. 4q+10; warp w takes rows w, w+8, ..., lane = quad
+    for (int r = wrp; r < BT_H + 6; r += 8) {
+        const int q = lane;
         const uint32_t w0 = in[r][q], w1 = in[r][q + 1], w2 = in[r][q + 2];
         float pf[10];
         pf[0] = (float)((w0 >> 8) & 0xff); pf[1] = (float)((w0 >> 16) & 0xff); pf[2] = (float)(w0 >> 24);
@@ -705,27 +735,24 @@ __global__ void __launch_bounds__(256) k_blur(const __grid_constant__ AfvParams 
     __syncthreads();
     uint8_t* out = L.blur + (long long)f * L.fstride;
     {
-        const int q = tid % (BT_W / 4), rg = tid / (BT_W / 4);       // 32 column quads x 8 row pairs
+        const int q = lane, rg = wrp;                             // 32 column quads x 8 groups of 4 rows
         const int gx = x0 + 4 * q;
         if (gx < L.w) {
-            float4 m[8];
+            float4 m[10];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) m[j] = *reinterpret_cast<const float4*>(&mid[2 * rg + j][4 * q]);
+            for (int j = 0; j < 10; ++j) m[j] = *reinterpret_cast<const float4*>(&mid[4 * rg + j][4 * q]);
 #pragma unroll
-            for (int rr = 0; rr < 2; ++rr) {
-                const int gy = y0 + 2 * rg + rr;
+            for (int rr = 0; rr < 4; ++rr) {
+                const int gy = y0 + 4 * rg + rr;
                 if (gy >= L.h) break;
                 uint32_t pk = 0;
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
-                    const float c0 = (&m[rr + 3].x)[k];
-                    float sacc = __fmul_rn(c_g7[3], c0);
+                    float sacc = __fmul_rn(c_g7[3], (&m[rr + 3].x)[k]);
 #pragma unroll
                     for (int j = 1; j <= 3; ++j)
                         sacc = __fmaf_rn(c_g7[3 + j], __fadd_rn((&m[rr + 3 + j].x)[k], (&m[rr + 3 - j].x)[k]), sacc);
-                    int v = __float2int_rn(sacc);
-                    v = min(max(v, 0), 255);
-                    pk |= (uint32_t)v << (8 * k);
+                    pk |= sat_u8(sacc) << (8 * k);
                 }
                 *reinterpret_cast<uint32_t*>(out + (long long)gy * L.stride + gx) = pk;
             }
@@ -759,10 +786,10 @@ __device__ __forceinline__ float fast_atan2_deg(float y, float x) {
 __global__ void __launch_bounds__(256) k_describe(const __grid_constant__ AfvParams P, afv_keypoint* __restrict__ kps,
                                                   uint8_t* __restrict__ desc, float* __restrict__ kpsize,
                                                   int* __restrict__ n_out) {
-    __shared__ int8_t pat[1024];
+    __shared__ uint32_t patw[8][32];         // patw[k][lane] = (x0,y0,x1,y1) int8 of test k of descriptor byte `lane`
     __shared__ int lvl_start[AFV_MAX_LEVELS + 1];
     const int f = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    for (int i = tid; i < 1024; i += 256) pat[i] = c_pattern[i];
+    { const int pl = tid & 31, pk = tid >> 5; patw[pk][pl] = *reinterpret_cast<const uint32_t*>(&c_pattern[pl * 32 + pk * 4]); }
     if (tid == 0) {
         int acc = 0;
         for (int l = 0; l < P.nlevels; ++l) {
@@ -824,14 +851,14 @@ __global__ void __launch_bounds__(256) k_describe(const __grid_constant__ AfvPar
     const float ang = __fmul_rn(angle, 0x1.1df46ap-6f);            // (float)(CV_PI/180.f)
     const float a = (float)cos((double)ang), b = (float)sin((double)ang);
     const bool dinner = (cx >= 19 && cy >= 19 && cx + 19 < L.w && cy + 19 < L.h);
-    const int8_t* pp = pat + lane * 32;
     uint32_t byte = 0;
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
+        const uint32_t pw = patw[k][lane];
         int tv[2];
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
-            const float px = (float)pp[4 * k + 2 * j], py = (float)pp[4 * k + 2 * j + 1];
+            const float px = (float)(int)(int8_t)(pw >> (16 * j)), py = (float)(int)(int8_t)(pw >> (16 * j + 8));
             const int ix = cx + __float2int_rn(__fsub_rn(__fmul_rn(px, a), __fmul_rn(py, b)));
             const int iy = cy + __float2int_rn(__fadd_rn(__fmul_rn(px, b), __fmul_rn(py, a)));
             if (dinner || (ix >= 0 && ix < L.w && iy >= 0 && iy < L.h)) tv[j] = blr[(long long)iy * L.stride + ix];
@@ -866,14 +893,7 @@ int afv_orb_configure(int max_det_cap, int max_keep_cap) {
 
 void afv_launch_extract(const AfvParams& P, afv_keypoint* d_kps, uint8_t* d_desc, float* d_kpsize,
                         int* d_n_out, cudaStream_t st) {
-    FastTiles T;
-    int acc = 0;
-    for (int l = 0; l < P.nlevels; ++l) {
-        T.start[l] = acc;
-        T.tiles_x[l] = (P.lv[l].w + FT_W - 1) / FT_W;
-        acc += T.tiles_x[l] * ((P.lv[l].h + FT_H - 1) / FT_H);
-    }
-    T.start[P.nlevels] = acc;
+    const int acc = P.ntiles;
     cudaMemsetAsync(P.counts, 0, sizeof(int) * 4 * AFV_MAX_LEVELS * P.B, st);
     cudaMemsetAsync(P.status, 0, sizeof(int) * P.B, st);
     for (int l = 1; l < P.nlevels; ++l) {
@@ -882,12 +902,12 @@ void afv_launch_extract(const AfvParams& P, afv_keypoint* d_kps, uint8_t* d_desc
         k_resize<<<g, dim3(32, 8), 0, st>>>(P, l);
         ++g_afv_launches;
     }
-    { AfvProfScope ps("k_fast", st); k_fast<<<dim3(acc, P.B), 256, 0, st>>>(P, T); ++g_afv_launches; }
+    { AfvProfScope ps("k_fast", st); k_fast<<<dim3(acc, P.B), 256, 0, st>>>(P); ++g_afv_launches; }
     { AfvProfScope ps("k_harris_select", st); k_harris_select<<<dim3(P.nlevels, P.B), 256, 0, st>>>(P); ++g_afv_launches; }
     { AfvProfScope ps("k_octree", st);
       k_octree<<<dim3(P.nlevels, P.B), 256, afv_octree_smem_bytes(g_oct_mcap, g_oct_ncap), st>>>(P, g_oct_mcap, g_oct_ncap);
       ++g_afv_launches; }
-    { AfvProfScope ps("k_blur", st); k_blur<<<dim3(acc, P.B), 256, 0, st>>>(P, T); ++g_afv_launches; }
+    { AfvProfScope ps("k_blur", st); k_blur<<<dim3(acc, P.B), 256, 0, st>>>(P); ++g_afv_launches; }
     { AfvProfScope ps("k_describe", st);
       k_describe<<<dim3((P.out_cap + 7) / 8, P.B), 256, 0, st>>>(P, d_kps, d_desc, d_kpsize, d_n_out); ++g_afv_launches; }
 }
