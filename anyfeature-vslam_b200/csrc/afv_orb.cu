@@ -28,45 +28,56 @@ __device__ __forceinline__ int refl101(int i, int n) {
 // ------------------------------------------------------------------------------------------------------
 // K2: pyramid level from the previous one.  thread = 4 consecutive output pixels (one 32-bit store).
 // ------------------------------------------------------------------------------------------------------
-// Source pixels come in as 3 aligned 32-bit words per source row (the 4 outputs of a thread span <= 9 source bytes
-// at scale 1.2), taps are cut out with funnel shifts; coefficients come as one 128-bit load of 4 packed table
-// entries (offset << 16 | c1).
+// One CTA = 128x16 output pixels.  The source footprint (<= 160 x 22 bytes at scale 1.2) is staged in shared memory
+// with aligned 32-bit loads; taps are byte LDS with 32-bit addressing (the global-pointer version spent most of its
+// instructions on 64-bit address arithmetic).  Thread = 4 columns x 2 rows; coefficients come as one 128-bit load of
+// 4 packed table entries (offset << 16 | c1).
+#define RS_ROWS 24
+#define RS_PITCH 176
 __global__ void __launch_bounds__(256) k_resize(const __grid_constant__ AfvParams P, int l) {
+    __shared__ __align__(16) uint8_t sp[RS_ROWS][RS_PITCH];
     const AfvLevel& D = P.lv[l];
     const AfvLevel& S = P.lv[l - 1];
-    const int f = blockIdx.z;
-    const int y = blockIdx.y * 8 + threadIdx.y;
-    const int x0 = (blockIdx.x * 32 + threadIdx.x) * 4;
-    if (y >= D.h || x0 >= D.w) return;
+    const int f = blockIdx.z, tid = threadIdx.x, lane = tid & 31, wrp = tid >> 5;
+    const int tx0 = blockIdx.x * 128, ty0 = blockIdx.y * 16;
     const uint8_t* src = S.img + (long long)f * S.img_fstride;
-    uint8_t* dst = const_cast<uint8_t*>(D.img) + (long long)f * D.img_fstride + (long long)y * D.img_stride;
-    const uint32_t yt = D.ytab[y];
-    const int yo = yt >> 16, c1y = yt & 0xffff, c0y = 256 - c1y;
+    const int sxb = (int)(D.xtab[tx0] >> 16) & ~3;                 // first staged source column (word aligned)
+    const int syb = (int)(D.ytab[ty0] >> 16);                      // first staged source row
+    const int lastw = (S.img_stride >> 2) - 1;
+    for (int r = wrp; r < RS_ROWS; r += 8) {
+        const uint32_t* row = reinterpret_cast<const uint32_t*>(src + (long long)min(syb + r, S.h - 1) * S.img_stride);
+#pragma unroll
+        for (int part = 0; part < 2; ++part) {
+            const int q = part * 32 + lane;
+            if (q >= RS_PITCH / 4) break;
+            reinterpret_cast<uint32_t*>(&sp[r][0])[q] = row[min((sxb >> 2) + q, lastw)];
+        }
+    }
+    __syncthreads();
+    const int x0 = tx0 + 4 * lane;
+    if (x0 >= D.w) return;
     const uint4 xt = *reinterpret_cast<const uint4*>(D.xtab + x0);       // table padded to a multiple of 4 entries
     const uint32_t xe[4] = {xt.x, xt.y, xt.z, xt.w};
-    const int xbase = (int)(xe[0] >> 16) & ~3;
-    const int lastw = (S.img_stride >> 2) - 1;
-    const int wb = xbase >> 2;
-    const uint32_t* r0 = reinterpret_cast<const uint32_t*>(src + (long long)yo * S.img_stride);
-    const uint32_t* r1 = reinterpret_cast<const uint32_t*>(src + (long long)min(yo + 1, S.h - 1) * S.img_stride);
-    const int i0 = min(wb, lastw), i1 = min(wb + 1, lastw), i2 = min(wb + 2, lastw);
-    const uint32_t a0 = r0[i0], a1 = r0[i1], a2 = r0[i2];
-    const uint32_t b0 = r1[i0], b1 = r1[i1], b2 = r1[i2];
-    uint32_t out = 0;
+    uint8_t* dstf = const_cast<uint8_t*>(D.img) + (long long)f * D.img_fstride;
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        const int xo = xe[k] >> 16, c1 = xe[k] & 0xffff, c0 = 256 - c1;
-        const int bo = xo - xbase;                                         // 0..8: byte offset of the left tap
-        const bool hiw = bo >= 4;
-        const int sh = (bo & 3) * 8;
-        const uint32_t pa = __funnelshift_r(hiw ? a1 : a0, hiw ? a2 : a1, sh);   // bytes bo, bo+1 of row 0
-        const uint32_t pb = __funnelshift_r(hiw ? b1 : b0, hiw ? b2 : b1, sh);
-        const uint32_t h0 = c0 * (pa & 0xff) + c1 * ((pa >> 8) & 0xff);
-        const uint32_t h1 = c0 * (pb & 0xff) + c1 * ((pb >> 8) & 0xff);
-        const uint32_t v = (uint32_t)c0y * h0 + (uint32_t)c1y * h1;
-        out |= ((v + (1u << 15)) >> 16) << (8 * k);
+    for (int rr = 0; rr < 2; ++rr) {
+        const int y = ty0 + 2 * wrp + rr;
+        if (y >= D.h) break;
+        const uint32_t yt = D.ytab[y];
+        const int yo = yt >> 16, c1y = yt & 0xffff, c0y = 256 - c1y;
+        const uint8_t* r0 = &sp[yo - syb][0];
+        const uint8_t* r1 = &sp[min(yo + 1, S.h - 1) - syb][0];
+        uint32_t out = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int xr = (int)(xe[k] >> 16) - sxb, c1 = xe[k] & 0xffff, c0 = 256 - c1;
+            const uint32_t h0 = c0 * r0[xr] + c1 * r0[xr + 1];
+            const uint32_t h1 = c0 * r1[xr] + c1 * r1[xr + 1];
+            const uint32_t v = (uint32_t)c0y * h0 + (uint32_t)c1y * h1;
+            out |= ((v + (1u << 15)) >> 16) << (8 * k);
+        }
+        *reinterpret_cast<uint32_t*>(dstf + (long long)y * D.img_stride + x0) = out;   // rows padded to 128 B
     }
-    *reinterpret_cast<uint32_t*>(dst + x0) = out;       // rows are padded to 128 B: the tail store stays in-row
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -897,9 +908,9 @@ void afv_launch_extract(const AfvParams& P, afv_keypoint* d_kps, uint8_t* d_desc
     cudaMemsetAsync(P.counts, 0, sizeof(int) * 4 * AFV_MAX_LEVELS * P.B, st);
     cudaMemsetAsync(P.status, 0, sizeof(int) * P.B, st);
     for (int l = 1; l < P.nlevels; ++l) {
-        dim3 g((P.lv[l].w + 127) / 128, (P.lv[l].h + 7) / 8, P.B);
+        dim3 g((P.lv[l].w + 127) / 128, (P.lv[l].h + 15) / 16, P.B);
         AfvProfScope ps("k_resize", st);
-        k_resize<<<g, dim3(32, 8), 0, st>>>(P, l);
+        k_resize<<<g, 256, 0, st>>>(P, l);
         ++g_afv_launches;
     }
     { AfvProfScope ps("k_fast", st); k_fast<<<dim3(acc, P.B), 256, 0, st>>>(P); ++g_afv_launches; }
