@@ -171,7 +171,8 @@ def run_gpu(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        import datetime
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=180))
     pkg = load_pkg()
     lib = pkg.lib()
     B = args.batch
@@ -193,11 +194,11 @@ def run_gpu(args):
         d_pack = torch.empty(pack_bytes, dtype=torch.uint8, device=dev)
         gathered = [torch.empty(pack_bytes, dtype=torch.uint8, device=dev) for _ in range(world)] if rank == 0 else None
 
-    def device_step(src):
+    def device_step(src, collective=True):
         ex.extract_batch_device(src, out, stream)
         fm.search_for_initialization(out[0], out[1], out[2], out[3], d_pa, d_pb, None, BOUNDS, MAX_KPT_SIZE,
                                      window=100, matches12=m12, nmatches=nm, stream=stream)
-        if world > 1 and args.gather:
+        if world > 1 and args.gather and collective:
             pkg.sharding.pack_results(d_pack, out[3], nm, m12, out[0], out[1])
             pkg.sharding.gather_to_root(d_pack, gathered, world, rank)
 
@@ -300,7 +301,7 @@ def run_gpu(args):
         import ctypes as C
         lib.afv_profile_enable(1)
         for _ in range(3):
-            device_step(d_gray)
+            device_step(d_gray, collective=False)      # rank-0-only leg: no collective here
         torch.cuda.synchronize()
         names = C.create_string_buffer(32 * 32); kms = (C.c_float * 32)(); kcalls = (C.c_int * 32)()
         nk = lib.afv_profile_read(names, kms, kcalls, 32)
