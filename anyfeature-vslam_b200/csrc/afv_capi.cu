@@ -323,7 +323,7 @@ static int run_device(afv_extractor* ex, const uint8_t* d_gray, int B, int w, in
                                                  d_gray + (long long)b * frame_stride, stride, w, h, cudaMemcpyDeviceToDevice, st));
         }
     }
-    afv_launch_extract(P, d_kps, (uint8_t*)d_desc, d_kpsize, d_n_out, st);
+    { const int lrc = afv_launch_extract(P, d_kps, (uint8_t*)d_desc, d_kpsize, d_n_out, st); if (lrc) return lrc; }
     AFV_CUDA_CHECK(cudaGetLastError());
     ex->last_B = B; ex->last_stream = st;
     return AFV_OK;

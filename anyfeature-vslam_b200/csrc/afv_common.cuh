@@ -65,8 +65,8 @@ __host__ __device__ inline int afv_cnt_idx(int frame, int which, int level) {
 }
 
 // launch wrappers (afv_orb.cu)
-void afv_launch_extract(const AfvParams& P, afv_keypoint* d_kps, uint8_t* d_desc, float* d_kpsize,
-                        int* d_n_out, cudaStream_t st);
+int afv_launch_extract(const AfvParams& P, afv_keypoint* d_kps, uint8_t* d_desc, float* d_kpsize,
+                       int* d_n_out, cudaStream_t st);
 size_t afv_octree_smem_bytes(int mcap, int ncap);
 int afv_orb_configure(int max_det_cap, int max_keep_cap);   // sets smem attributes; returns 0 / cuda error
 

@@ -12,7 +12,33 @@
 // integer fixed point, explicit __f*_rn intrinsics (no contraction) and explicit __fmaf_rn where the pinned
 // binary fuses.  Results are bit-exact with the oracle; tests/test_extract_gpu.py checks that.
 #include "afv_common.cuh"
+#include <cuda.h>
 #include <stdio.h>
+#include <string.h>
+
+// ---- TMA (cp.async.bulk.tensor) + mbarrier primitives, inline PTX (sm_90+/sm_100a) -----------------------------
+struct AfvTmaps { CUtensorMap m[AFV_MAX_LEVELS]; };        // one 3-D map (x bytes, y rows, frame) per pyramid level
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                 :: "r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t phase) {
+    uint32_t ok = 0;
+    for (int spin = 0; !ok; ++spin) {
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                     : "=r"(ok) : "r"(smem_u32(bar)), "r"(phase) : "memory");
+        if (spin > (1 << 24)) __trap();                  // a lost TMA completion must not hang the box
+    }
+}
 
 static __constant__ __align__(16) int8_t c_pattern[1024] = {
 #include "orb_pattern.inc"
@@ -118,8 +144,9 @@ __device__ __forceinline__ void warp_push(bool pass, uint16_t val, uint16_t* lis
     if (pass) list[base + __popc(m & ((1u << lane) - 1))] = val;
 }
 
-__global__ void __launch_bounds__(256) k_fast(const __grid_constant__ AfvParams P) {
-    __shared__ __align__(16) uint32_t pixw[FT_PH][FT_WP];
+__global__ void __launch_bounds__(256) k_fast(const __grid_constant__ AfvParams P, const __grid_constant__ AfvTmaps TM) {
+    __shared__ __align__(128) uint32_t pixw[FT_PH][FT_WP];
+    __shared__ __align__(8) uint64_t tma_bar;
     __shared__ __align__(4) uint8_t score[FT_RH][FT_SW];
     __shared__ uint16_t slist[FT_RW * FT_RH];        // stage-1 survivors
     __shared__ uint16_t clist[FT_RW * FT_RH];        // corners
@@ -135,25 +162,22 @@ __global__ void __launch_bounds__(256) k_fast(const __grid_constant__ AfvParams 
     const uint8_t* img = L.img + (long long)f * L.img_fstride;
     const int t = P.fast_th;
 
-    if (tid == 0) { nstage1 = 0; ncorner = 0; nsurv = 0; }
-    // stage the pixel tile: data word q (pixels x0-4+4q ..) lives at pixw[r][q+1]; rows outside the image read as 0.
-    // warp w stages rows w, w+8, ...; lane = word slot (slots 32..35 by lanes 0..3)
-    for (int r = wrp; r < FT_PH; r += 8) {
-        const int gy = y0 - 4 + r;
-        const bool rowok = gy >= 0 && gy < L.h;
-        const uint8_t* rowp = img + (long long)gy * L.img_stride;
-#pragma unroll
-        for (int part = 0; part < 2; ++part) {
-            const int slot = part * 32 + lane;
-            if (slot >= FT_WP) break;
-            const int q = slot - 1, gx = x0 - 4 + q * 4;
-            uint32_t v = 0;
-            if (rowok && q >= 0 && q < FT_PW / 4 && gx >= 0 && gx < L.img_stride) v = *reinterpret_cast<const uint32_t*>(rowp + gx);
-            pixw[r][slot] = v;
-        }
+    // stage the pixel tile with ONE TMA box load: FT_WP*4 = 144 bytes x FT_PH rows of frame f, starting at
+    // (x0 - 8, y0 - 4) so data word q (pixels x0-4+4q ..) lands in pixw[r][q+1]; everything outside the level
+    // (left / top / right / bottom halo of border tiles) is zero-filled by the TMA unit.
+    if (tid == 0) {
+        nstage1 = 0; ncorner = 0; nsurv = 0;
+        mbar_init(&tma_bar, 1);
+    }
+    __syncthreads();
+    if (tid == 0) {
+        mbar_expect_tx(&tma_bar, FT_PH * FT_WP * 4);
+        tma_load_3d(&pixw[0][0], &TM.m[l], &tma_bar, x0 - 8, y0 - 4, f);
     }
     for (int i = tid; i < FT_RH * FT_SW / 4; i += 256) reinterpret_cast<uint32_t*>(&score[0][0])[i] = 0;
+    mbar_wait(&tma_bar, 0);
     __syncthreads();
+    (void)img; (void)wrp;
 
     const uint8_t* pb = reinterpret_cast<const uint8_t*>(&pixw[0][0]);
     constexpr int PITCH = FT_WP * 4;
@@ -902,8 +926,35 @@ int afv_orb_configure(int max_det_cap, int max_keep_cap) {
     return AFV_OK;
 }
 
-void afv_launch_extract(const AfvParams& P, afv_keypoint* d_kps, uint8_t* d_desc, float* d_kpsize,
-                        int* d_n_out, cudaStream_t st) {
+typedef CUresult (*afv_encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                        const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                        CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static afv_encode_tiled_fn g_encode = nullptr;
+
+// 3-D u8 tensor map of one level: (x, y, frame) with the k_fast staging box.
+static int make_level_tmap(CUtensorMap* m, const AfvLevel& L, int B) {
+    if (!g_encode) {
+        void* fn = nullptr; cudaDriverEntryPointQueryResult qr;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qr) != cudaSuccess || !fn) {
+            afv_set_error("cuTensorMapEncodeTiled not available from the driver"); return AFV_ERR_CUDA;
+        }
+        g_encode = (afv_encode_tiled_fn)fn;
+    }
+    const cuuint64_t gdim[3] = {(cuuint64_t)L.w, (cuuint64_t)L.h, (cuuint64_t)B};
+    const cuuint64_t gstr[2] = {(cuuint64_t)L.img_stride, (cuuint64_t)L.img_fstride};
+    const cuuint32_t box[3] = {FT_WP * 4, FT_PH, 1};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<uint8_t*>(L.img), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                          CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { afv_set_error("cuTensorMapEncodeTiled failed (%d) for a %dx%d level, stride %d", (int)r, L.w, L.h, L.img_stride); return AFV_ERR_CUDA; }
+    return AFV_OK;
+}
+
+int afv_launch_extract(const AfvParams& P, afv_keypoint* d_kps, uint8_t* d_desc, float* d_kpsize,
+                       int* d_n_out, cudaStream_t st) {
+    AfvTmaps TM;
+    memset(&TM, 0, sizeof(TM));
+    for (int l = 0; l < P.nlevels; ++l) { const int rc = make_level_tmap(&TM.m[l], P.lv[l], P.B); if (rc) return rc; }
     const int acc = P.ntiles;
     cudaMemsetAsync(P.counts, 0, sizeof(int) * 4 * AFV_MAX_LEVELS * P.B, st);
     cudaMemsetAsync(P.status, 0, sizeof(int) * P.B, st);
@@ -913,7 +964,7 @@ void afv_launch_extract(const AfvParams& P, afv_keypoint* d_kps, uint8_t* d_desc
         k_resize<<<g, 256, 0, st>>>(P, l);
         ++g_afv_launches;
     }
-    { AfvProfScope ps("k_fast", st); k_fast<<<dim3(acc, P.B), 256, 0, st>>>(P); ++g_afv_launches; }
+    { AfvProfScope ps("k_fast", st); k_fast<<<dim3(acc, P.B), 256, 0, st>>>(P, TM); ++g_afv_launches; }
     { AfvProfScope ps("k_harris_select", st); k_harris_select<<<dim3(P.nlevels, P.B), 256, 0, st>>>(P); ++g_afv_launches; }
     { AfvProfScope ps("k_octree", st);
       k_octree<<<dim3(P.nlevels, P.B), 256, afv_octree_smem_bytes(g_oct_mcap, g_oct_ncap), st>>>(P, g_oct_mcap, g_oct_ncap);
@@ -921,4 +972,5 @@ void afv_launch_extract(const AfvParams& P, afv_keypoint* d_kps, uint8_t* d_desc
     { AfvProfScope ps("k_blur", st); k_blur<<<dim3(acc, P.B), 256, 0, st>>>(P); ++g_afv_launches; }
     { AfvProfScope ps("k_describe", st);
       k_describe<<<dim3((P.out_cap + 7) / 8, P.B), 256, 0, st>>>(P, d_kps, d_desc, d_kpsize, d_n_out); ++g_afv_launches; }
+    return AFV_OK;
 }

@@ -97,27 +97,21 @@ class ClockSampler(threading.Thread):
 # CPU arm: the oracle port of the reference's per-frame path, all host threads (ctypes releases the GIL)
 # ---------------------------------------------------------------------------------------------------------
 def cpu_arm(frames, pair_b, nthreads, seconds_budget):
-    from concurrent.futures import ThreadPoolExecutor
+    """Returns (step(sample), sample, seconds per frame on one thread).  step() runs the oracle port of one bench step
+    (extract every frame of the sample + SearchForInitialization of consecutive frames) threaded in C (OpenMP)."""
     from oracle import pyoracle as po
     po.lib()
     n = len(frames)
 
-    def step(sample):
-        # extract every frame of the sample once, then match consecutive frames (same work as the GPU step)
-        with ThreadPoolExecutor(nthreads) as ex:
-            res = list(ex.map(lambda i: po.orb32_extract(frames[i], NFEAT)[:3], sample))
+    def step(sample, threads=nthreads):
+        fr = frames[sample[0]:sample[-1] + 1]
+        m = len(fr)
+        pa = np.arange(m, dtype=np.int32); pb = ((pa + 1) % m).astype(np.int32)
+        return po.extract_match_batch(fr, pa, pb, NFEAT, threads)
 
-            def match(t):
-                a, b = res[t], res[(t + 1) % len(res)]
-                prev = np.stack([a[0]["x"], a[0]["y"]], axis=1)
-                return po.search_for_initialization(0, a[0], a[1], b[0], b[1], b[2], BOUNDS, MAX_KPT_SIZE, prev,
-                                                    window=100, th_low=75.0, nnratio=0.9, check_ori=True)[0]
-            list(ex.map(match, range(len(res))))
-
-    # size the sample from a one-thread probe so a step stays within the budget
-    t0 = time.perf_counter(); step([0, 1]); t1 = time.perf_counter()
+    t0 = time.perf_counter(); step([0, 1], 1); t1 = time.perf_counter()
     per_frame = (t1 - t0) / 2
-    sample_n = int(max(nthreads, min(n, seconds_budget / per_frame * nthreads)))
+    sample_n = int(max(min(nthreads, n), min(n, seconds_budget / per_frame * nthreads)))
     sample = list(range(min(sample_n, n)))
     return step, sample, per_frame
 

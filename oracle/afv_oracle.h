@@ -115,6 +115,12 @@ int  orc_search_by_bow(int desc_type,
         const orc_keypoint* kf_f, int nf,
         float th_low, float nnratio, int check_ori, int* match_f /* nf: KF index or -1 */);
 
+/* One bench.py step on the CPU (OpenMP over frames / pairs): extraction of B frames + SearchForInitialization of the
+ * given pairs. Returns the total number of matches. Used only by bench.py's cpu_baseline / --impl reference legs. */
+long orc_orb32_extract_match_batch(const uint8_t* frames, int B, int w, int h, int nfeatures, int nlevels,
+                                   float scale_factor, float detect_th, const int* pair_a, const int* pair_b, int P,
+                                   int window, float th_low, float nnratio, int check_ori, int nthreads);
+
 /* rotation-consistency helpers (src/FeatureMatcher.cc:1579-1668) */
 int  orc_rot_bin(float angle1, float angle2);
 void orc_three_maxima(const int* hist_counts, int len, int* ind1, int* ind2, int* ind3);

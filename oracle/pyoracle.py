@@ -36,6 +36,7 @@ def lib():
         _LIB.orc_fast_atan2.restype = C.c_float
         _LIB.orc_fast_atan2.argtypes = [C.c_float, C.c_float]
         _LIB.orc_descriptor_distance.restype = C.c_float
+        _LIB.orc_orb32_extract_match_batch.restype = C.c_long
     return _LIB
 
 
@@ -185,3 +186,14 @@ def search_by_bow(desc_type, dkf, kkf, kf_segs, df, kf_f, f_segs, th_low=75.0, n
                                 _p(df), _p(b[0]), _p(b[1]), _p(b[2]), len(b[0]), _p(kf_f), nf,
                                 _f(th_low), _f(nnratio), int(bool(check_ori)), _p(out))
     return n, out[:nf].copy()
+
+
+def extract_match_batch(frames, pair_a, pair_b, nfeatures=1000, nthreads=1, window=100, th_low=75.0, nnratio=0.9, check_ori=True):
+    """One bench step on the CPU, threaded in C (OpenMP). Returns the total number of matches."""
+    frames = np.ascontiguousarray(frames, np.uint8)
+    B, h, w = frames.shape
+    pa = np.ascontiguousarray(pair_a, np.int32); pb = np.ascontiguousarray(pair_b, np.int32)
+    r = lib().orc_orb32_extract_match_batch(_p(frames), B, w, h, nfeatures, 8, _f(1.2), _f(20.0), _p(pa), _p(pb), len(pa),
+                                            int(window), _f(th_low), _f(nnratio), int(bool(check_ori)), int(nthreads))
+    assert r >= 0
+    return int(r)
