@@ -133,7 +133,8 @@ __device__ __forceinline__ bool has_arc9(uint32_t m) {
 // Two-stage segment test with compaction (keeps warps converged): stage 1 runs the two cheap antipodal-pair
 // rejections on every pixel of the score region and compacts the survivors (warp ballot + one shared atomic per
 // warp); stage 2 builds the two 16-bit brighter/darker masks only for survivors and compacts the corners.
-#define FT_WP 36                      // words per staged row: [pad][34 data words][pad]
+#define FT_WP 40                      // words per staged row: 160 B TMA box starting at x0-16 (16-B aligned)
+#define FT_XOFF 12                    // byte offset of pixel x0-4 inside a staged row
 __device__ __forceinline__ void warp_push(bool pass, uint16_t val, uint16_t* list, int* counter, int lane) {
     const unsigned m = __ballot_sync(0xffffffffu, pass);
     if (m == 0) return;
@@ -162,9 +163,10 @@ __global__ void __launch_bounds__(256) k_fast(const __grid_constant__ AfvParams 
     const uint8_t* img = L.img + (long long)f * L.img_fstride;
     const int t = P.fast_th;
 
-    // stage the pixel tile with ONE TMA box load: FT_WP*4 = 144 bytes x FT_PH rows of frame f, starting at
-    // (x0 - 8, y0 - 4) so data word q (pixels x0-4+4q ..) lands in pixw[r][q+1]; everything outside the level
-    // (left / top / right / bottom halo of border tiles) is zero-filled by the TMA unit.
+    // stage the pixel tile with ONE TMA box load: FT_WP*4 = 160 bytes x FT_PH rows of frame f, starting at
+    // (x0 - 16, y0 - 4): the inner coordinate of a u8 box must be 16-byte aligned (an unaligned start raises an
+    // illegal-instruction fault, tools/dbg/tma_dbg.cu), so pixel x0-4 sits at byte FT_XOFF of every staged row;
+    // everything outside the level (halo of border tiles) is zero-filled by the TMA unit.
     if (tid == 0) {
         nstage1 = 0; ncorner = 0; nsurv = 0;
         mbar_init(&tma_bar, 1);
@@ -172,7 +174,7 @@ __global__ void __launch_bounds__(256) k_fast(const __grid_constant__ AfvParams 
     __syncthreads();
     if (tid == 0) {
         mbar_expect_tx(&tma_bar, FT_PH * FT_WP * 4);
-        tma_load_3d(&pixw[0][0], &TM.m[l], &tma_bar, x0 - 8, y0 - 4, f);
+        tma_load_3d(&pixw[0][0], &TM.m[l], &tma_bar, x0 - 16, y0 - 4, f);
     }
     for (int i = tid; i < FT_RH * FT_SW / 4; i += 256) reinterpret_cast<uint32_t*>(&score[0][0])[i] = 0;
     mbar_wait(&tma_bar, 0);
@@ -197,7 +199,7 @@ __global__ void __launch_bounds__(256) k_fast(const __grid_constant__ AfvParams 
             half = item >= FT_RW; c = item - half * FT_RW;
             const int gx = x0 - 1 + c;
             if (gx >= 3 && gx < L.w - 3) {
-                const uint8_t* pc = pb + 4 + (c + 3) + (FT_HALF * half) * PITCH;   // window row k <-> region row FT_HALF*half + k - 3
+                const uint8_t* pc = pb + FT_XOFF + (c + 3) + (FT_HALF * half) * PITCH;   // window row k <-> region row FT_HALF*half + k - 3
                 // rows that are real centres: 3 <= gy < h-3 with gy = y0 - 1 + FT_HALF*half + j
                 const int gy0 = y0 - 1 + FT_HALF * half;
                 const int jlo = max(0, 3 - gy0), jhi = min(FT_HALF, L.h - 3 - gy0);
@@ -241,7 +243,7 @@ __global__ void __launch_bounds__(256) k_fast(const __grid_constant__ AfvParams 
         if (j < n1) {
             i = slist[j];
             const int r = i / FT_RW, c = i % FT_RW;
-            const uint8_t* p = pb + (r + 3) * PITCH + 4 + (c + 3);
+            const uint8_t* p = pb + (r + 3) * PITCH + FT_XOFF + (c + 3);
             const int v = p[0], hi = v + t, lo = v - t;
             uint32_t br = 0, dk = 0;
 #define FMASK(k, dx, dy) { const int q = p[(dy) * PITCH + (dx)]; br |= (uint32_t)(q > hi) << k; dk |= (uint32_t)(q < lo) << k; }
@@ -259,7 +261,7 @@ __global__ void __launch_bounds__(256) k_fast(const __grid_constant__ AfvParams 
     for (int j = tid; j < nc; j += 256) {
         const int i = clist[j];
         const int r = i / FT_RW, c = i % FT_RW;
-        const uint8_t* p = pb + (r + 3) * (FT_WP * 4) + 4 + (c + 3);
+        const uint8_t* p = pb + (r + 3) * (FT_WP * 4) + FT_XOFF + (c + 3);
         const int v = p[0];
         // d[k] = v - p[k] in [-255,255]: packed as (d, -d) in the two signed 16-bit halves so one __vmins2 chain
         // gives both min(d) (darker arcs) and min(-d) (brighter arcs); sliding minimum over 9 by doubling.
@@ -712,46 +714,56 @@ size_t afv_octree_smem_bytes(int mcap, int ncap) {
 __constant__ float c_g7[7] = {0x1.1f5f62p-4f, 0x1.0c70fcp-3f, 0x1.869472p-3f, 0x1.ba95cp-3f,
                               0x1.869472p-3f, 0x1.0c70fcp-3f, 0x1.1f5f62p-4f};
 
-// Staged input: rows y0-3 .. y0+BT_H+2, byte columns x0-4 .. x0+BT_W+3 as 34 aligned words per row.  Words that lie
-// inside the image are straight 32-bit loads (the row index is reflected once per row); only words that straddle the
-// left/right border take the per-byte REFLECT_101 gather.  Row pass: one thread = 4 outputs from 3 words; column
+// Staged input: rows y0-3 .. y0+BT_H+2, byte columns x0-16 .. x0+BT_W+27 (160 B, 16-B aligned start) by ONE TMA box
+// load; the TMA unit zero-fills outside the level, so border tiles then patch the few REFLECT_101 halo bytes they
+// need (<= 3 rows above/below, <= 3 columns left/right).  Row pass: one thread = 4 outputs from 3 words; column
 // pass: one thread = 4 columns x 4 rows from 10 float4 rows.
-#define BT_WW ((BT_W + 8) / 4)
+#define BT_WP 40                      // words per staged row
+#define BT_XOFF 16                    // byte offset of pixel x0 inside a staged row
 __device__ __forceinline__ uint32_t sat_u8(float v) {       // cv::saturate_cast<uchar>(float): round-half-even, clamp
     uint32_t r;
     asm("cvt.rni.sat.u8.f32 %0, %1;" : "=r"(r) : "f"(v));
     return r;
 }
-__global__ void __launch_bounds__(256) k_blur(const __grid_constant__ AfvParams P) {
-    __shared__ __align__(16) uint32_t in[BT_H + 6][BT_WW + 2];
+__global__ void __launch_bounds__(256) k_blur(const __grid_constant__ AfvParams P, const __grid_constant__ AfvTmaps TM) {
+    __shared__ __align__(128) uint32_t in[BT_H + 6][BT_WP];
     __shared__ __align__(16) float mid[BT_H + 6][BT_W];
+    __shared__ __align__(8) uint64_t tma_bar;
     const AfvTile ti = P.tiles[blockIdx.x];
     const AfvLevel& L = P.lv[ti.level];
     const int f = blockIdx.y, tid = threadIdx.x, lane = tid & 31, wrp = tid >> 5;
     const int x0 = ti.x0, y0 = ti.y0;
     const uint8_t* img = L.img + (long long)f * L.img_fstride;
-    for (int r = wrp; r < BT_H + 6; r += 8) {
-        const uint8_t* row = img + (long long)refl101(y0 - 3 + r, L.h) * L.img_stride;
-#pragma unroll
-        for (int part = 0; part < 2; ++part) {
-            const int q = part * 32 + lane;
-            if (q >= BT_WW) break;
-            const int gx = x0 - 4 + 4 * q;
-            uint32_t v;
-            if (gx >= 0 && gx + 3 < L.w) v = *reinterpret_cast<const uint32_t*>(row + gx);
-            else {
-                v = 0;
-#pragma unroll
-                for (int b2 = 0; b2 < 4; ++b2) v |= (uint32_t)row[refl101(gx + b2, L.w)] << (8 * b2);
+    if (tid == 0) mbar_init(&tma_bar, 1);
+    __syncthreads();
+    if (tid == 0) {
+        mbar_expect_tx(&tma_bar, (BT_H + 6) * BT_WP * 4);
+        tma_load_3d(&in[0][0], &TM.m[ti.level], &tma_bar, x0 - 16, y0 - 3, f);
+    }
+    mbar_wait(&tma_bar, 0);
+    // REFLECT_101 patch of the halo that fell outside the level (border tiles only; uniform branch)
+    const int xend = min(x0 + BT_W, L.w);                         // outputs exist for gx < xend, taps reach xend + 2
+    if (x0 == 0 || y0 == 0 || xend + 3 > L.w || y0 + BT_H + 3 > L.h) {
+        __syncthreads();
+        uint8_t* inb = reinterpret_cast<uint8_t*>(&in[0][0]);
+        for (int r = wrp; r < BT_H + 6; r += 8) {
+            const int gy = y0 - 3 + r;
+            if (gy > L.h + 2) break;
+            const uint8_t* row = img + (long long)refl101(gy, L.h) * L.img_stride;
+            uint8_t* dst = inb + r * (BT_WP * 4) + BT_XOFF - x0;     // dst[gx]
+            if (gy < 0 || gy >= L.h) {
+                for (int gx = x0 - 3 + lane; gx < xend + 3; gx += 32) dst[gx] = row[refl101(gx, L.w)];
+            } else {
+                if (x0 == 0 && lane < 3) dst[-1 - lane] = row[1 + lane];                       // gx = -1,-2,-3
+                if (xend + 3 > L.w && lane < 3 && L.w + lane < xend + 3) dst[L.w + lane] = row[L.w - 2 - lane];
             }
-            in[r][q] = v;
         }
     }
     __syncthreads();
     // row pass: outputs 4q..4q+3 need staged bytes 4q+1 .. 4q+10; warp w takes rows w, w+8, ..., lane = quad
     for (int r = wrp; r < BT_H + 6; r += 8) {
         const int q = lane;
-        const uint32_t w0 = in[r][q], w1 = in[r][q + 1], w2 = in[r][q + 2];
+        const uint32_t w0 = in[r][q + 3], w1 = in[r][q + 4], w2 = in[r][q + 5];      // staged bytes 4q+13 .. 4q+22
         float pf[10];
         pf[0] = (float)((w0 >> 8) & 0xff); pf[1] = (float)((w0 >> 16) & 0xff); pf[2] = (float)(w0 >> 24);
         pf[3] = (float)(w1 & 0xff); pf[4] = (float)((w1 >> 8) & 0xff); pf[5] = (float)((w1 >> 16) & 0xff); pf[6] = (float)(w1 >> 24);
@@ -932,7 +944,7 @@ typedef CUresult (*afv_encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuuin
 static afv_encode_tiled_fn g_encode = nullptr;
 
 // 3-D u8 tensor map of one level: (x, y, frame) with the k_fast staging box.
-static int make_level_tmap(CUtensorMap* m, const AfvLevel& L, int B) {
+static int make_level_tmap(CUtensorMap* m, const AfvLevel& L, int B, int box_w, int box_h) {
     if (!g_encode) {
         void* fn = nullptr; cudaDriverEntryPointQueryResult qr;
         if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qr) != cudaSuccess || !fn) {
@@ -942,7 +954,7 @@ static int make_level_tmap(CUtensorMap* m, const AfvLevel& L, int B) {
     }
     const cuuint64_t gdim[3] = {(cuuint64_t)L.w, (cuuint64_t)L.h, (cuuint64_t)B};
     const cuuint64_t gstr[2] = {(cuuint64_t)L.img_stride, (cuuint64_t)L.img_fstride};
-    const cuuint32_t box[3] = {FT_WP * 4, FT_PH, 1};
+    const cuuint32_t box[3] = {(cuuint32_t)box_w, (cuuint32_t)box_h, 1};
     const cuuint32_t estr[3] = {1, 1, 1};
     CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<uint8_t*>(L.img), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                           CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -952,9 +964,13 @@ static int make_level_tmap(CUtensorMap* m, const AfvLevel& L, int B) {
 
 int afv_launch_extract(const AfvParams& P, afv_keypoint* d_kps, uint8_t* d_desc, float* d_kpsize,
                        int* d_n_out, cudaStream_t st) {
-    AfvTmaps TM;
-    memset(&TM, 0, sizeof(TM));
-    for (int l = 0; l < P.nlevels; ++l) { const int rc = make_level_tmap(&TM.m[l], P.lv[l], P.B); if (rc) return rc; }
+    AfvTmaps TM, TMB;                         // k_fast / k_blur staging boxes
+    memset(&TM, 0, sizeof(TM)); memset(&TMB, 0, sizeof(TMB));
+    for (int l = 0; l < P.nlevels; ++l) {
+        int rc = make_level_tmap(&TM.m[l], P.lv[l], P.B, FT_WP * 4, FT_PH);
+        if (!rc) rc = make_level_tmap(&TMB.m[l], P.lv[l], P.B, BT_WP * 4, BT_H + 6);
+        if (rc) return rc;
+    }
     const int acc = P.ntiles;
     cudaMemsetAsync(P.counts, 0, sizeof(int) * 4 * AFV_MAX_LEVELS * P.B, st);
     cudaMemsetAsync(P.status, 0, sizeof(int) * P.B, st);
@@ -969,7 +985,7 @@ int afv_launch_extract(const AfvParams& P, afv_keypoint* d_kps, uint8_t* d_desc,
     { AfvProfScope ps("k_octree", st);
       k_octree<<<dim3(P.nlevels, P.B), 256, afv_octree_smem_bytes(g_oct_mcap, g_oct_ncap), st>>>(P, g_oct_mcap, g_oct_ncap);
       ++g_afv_launches; }
-    { AfvProfScope ps("k_blur", st); k_blur<<<dim3(acc, P.B), 256, 0, st>>>(P); ++g_afv_launches; }
+    { AfvProfScope ps("k_blur", st); k_blur<<<dim3(acc, P.B), 256, 0, st>>>(P, TMB); ++g_afv_launches; }
     { AfvProfScope ps("k_describe", st);
       k_describe<<<dim3((P.out_cap + 7) / 8, P.B), 256, 0, st>>>(P, d_kps, d_desc, d_kpsize, d_n_out); ++g_afv_launches; }
     return AFV_OK;

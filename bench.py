@@ -109,8 +109,9 @@ def cpu_arm(frames, pair_b, nthreads, seconds_budget):
         pa = np.arange(m, dtype=np.int32); pb = ((pa + 1) % m).astype(np.int32)
         return po.extract_match_batch(fr, pa, pb, NFEAT, threads)
 
-    t0 = time.perf_counter(); step([0, 1], 1); t1 = time.perf_counter()
-    per_frame = (t1 - t0) / 2
+    step([0, 1], 1)                                              # warm (library load, first-touch)
+    t0 = time.perf_counter(); step([0, 1, 2, 3], 1); t1 = time.perf_counter()
+    per_frame = (t1 - t0) / 4
     sample_n = int(max(min(nthreads, n), min(n, seconds_budget / per_frame * nthreads)))
     sample = list(range(min(sample_n, n)))
     return step, sample, per_frame

@@ -299,6 +299,7 @@ int orc_search_by_bow(int desc_type,
  * atomic counter): orb32 extraction of B frames + SearchForInitialization of frame pair_a[p] against pair_b[p].
  * Returns the total number of matches (a checksum so the work cannot be optimised away), -1 on error. */
 #include <pthread.h>
+#include <malloc.h>
 typedef struct {
     const uint8_t* frames; int B, w, h, nfeatures, nlevels; float scale_factor, detect_th;
     const int *pair_a, *pair_b; int P, window; float th_low, nnratio; int check_ori;
@@ -341,6 +342,10 @@ static void* orc_batch_worker(void* arg) {
 long orc_orb32_extract_match_batch(const uint8_t* frames, int B, int w, int h, int nfeatures, int nlevels,
                                    float scale_factor, float detect_th, const int* pair_a, const int* pair_b, int P,
                                    int window, float th_low, float nnratio, int check_ori, int nthreads) {
+    /* keep the per-frame scratch (pyramids, score maps: ~MBs) inside the per-thread heaps: with the default mmap /
+     * trim thresholds every frame would mmap+munmap them and 128 threads serialise on the kernel's mm lock */
+    mallopt(M_MMAP_THRESHOLD, 1 << 30);
+    mallopt(M_TRIM_THRESHOLD, 1 << 30);
     orc_batch_job J;
     memset(&J, 0, sizeof(J));
     J.frames = frames; J.B = B; J.w = w; J.h = h; J.nfeatures = nfeatures; J.nlevels = nlevels; J.scale_factor = scale_factor;
