@@ -75,6 +75,7 @@ struct afv_extractor {
     int max_batch, max_w, max_h;
     int cur_w, cur_h;                 // geometry the tables / params are currently built for
     cudaStream_t stream;
+    AfvAux aux;
     std::vector<void*> allocs;        // everything to cudaFree
     uint8_t* pyr[AFV_MAX_LEVELS];     // un-blurred arena per level (level 0 = staging copy of the input)
     uint8_t* blur[AFV_MAX_LEVELS];
@@ -226,6 +227,9 @@ extern "C" int afv_extractor_create(afv_extractor** out, int feature_id, int nfe
     ex->max_batch = max_batch; ex->max_w = max_w; ex->max_h = max_h; ex->cur_w = ex->cur_h = 0;
     ex->last_B = 0; ex->last_stream = nullptr;
     AFV_CUDA_CHECK(cudaStreamCreateWithFlags(&ex->stream, cudaStreamNonBlocking));
+    AFV_CUDA_CHECK(cudaStreamCreateWithFlags(&ex->aux.stream, cudaStreamNonBlocking));
+    AFV_CUDA_CHECK(cudaEventCreateWithFlags(&ex->aux.ev_pyr, cudaEventDisableTiming));
+    AFV_CUDA_CHECK(cudaEventCreateWithFlags(&ex->aux.ev_blur, cudaEventDisableTiming));
 
     features_per_level(nfeatures * 10, n_octaves, 1.2f, ex->q_orb);          // cv::ORB, maxFeatures = 10*nfeatures
     features_per_level(nfeatures, n_octaves, scale_factor, ex->q_ext);       // mnFeaturesPerLevel
@@ -288,6 +292,9 @@ extern "C" void afv_extractor_destroy(afv_extractor* ex) {
     if (!ex) return;
     cudaSetDevice(ex->device);
     if (ex->stream) { cudaStreamSynchronize(ex->stream); cudaStreamDestroy(ex->stream); }
+    if (ex->aux.stream) { cudaStreamSynchronize(ex->aux.stream); cudaStreamDestroy(ex->aux.stream); }
+    if (ex->aux.ev_pyr) cudaEventDestroy(ex->aux.ev_pyr);
+    if (ex->aux.ev_blur) cudaEventDestroy(ex->aux.ev_blur);
     for (void* p : ex->allocs) cudaFree(p);
     if (ex->h_status) cudaFreeHost(ex->h_status);
     if (ex->h_counts) cudaFreeHost(ex->h_counts);
@@ -323,7 +330,7 @@ static int run_device(afv_extractor* ex, const uint8_t* d_gray, int B, int w, in
                                                  d_gray + (long long)b * frame_stride, stride, w, h, cudaMemcpyDeviceToDevice, st));
         }
     }
-    { const int lrc = afv_launch_extract(P, d_kps, (uint8_t*)d_desc, d_kpsize, d_n_out, st); if (lrc) return lrc; }
+    { const int lrc = afv_launch_extract(P, d_kps, (uint8_t*)d_desc, d_kpsize, d_n_out, st, ex->aux); if (lrc) return lrc; }
     AFV_CUDA_CHECK(cudaGetLastError());
     ex->last_B = B; ex->last_stream = st;
     return AFV_OK;

@@ -65,8 +65,9 @@ __host__ __device__ inline int afv_cnt_idx(int frame, int which, int level) {
 }
 
 // launch wrappers (afv_orb.cu)
+struct AfvAux { cudaStream_t stream; cudaEvent_t ev_pyr, ev_blur; };   // side stream for kernels that only need the pyramid
 int afv_launch_extract(const AfvParams& P, afv_keypoint* d_kps, uint8_t* d_desc, float* d_kpsize,
-                       int* d_n_out, cudaStream_t st);
+                       int* d_n_out, cudaStream_t st, const AfvAux& aux);
 size_t afv_octree_smem_bytes(int mcap, int ncap);
 int afv_orb_configure(int max_det_cap, int max_keep_cap);   // sets smem attributes; returns 0 / cuda error
 

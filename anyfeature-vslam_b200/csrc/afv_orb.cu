@@ -963,7 +963,7 @@ static int make_level_tmap(CUtensorMap* m, const AfvLevel& L, int B, int box_w, 
 }
 
 int afv_launch_extract(const AfvParams& P, afv_keypoint* d_kps, uint8_t* d_desc, float* d_kpsize,
-                       int* d_n_out, cudaStream_t st) {
+                       int* d_n_out, cudaStream_t st, const AfvAux& aux) {
     AfvTmaps TM, TMB;                         // k_fast / k_blur staging boxes
     memset(&TM, 0, sizeof(TM)); memset(&TMB, 0, sizeof(TMB));
     for (int l = 0; l < P.nlevels; ++l) {
@@ -980,12 +980,18 @@ int afv_launch_extract(const AfvParams& P, afv_keypoint* d_kps, uint8_t* d_desc,
         k_resize<<<g, 256, 0, st>>>(P, l);
         ++g_afv_launches;
     }
+    // The blur only needs the pyramid: it runs on the auxiliary stream, overlapping the latency-bound selection /
+    // octree kernels of the main stream; k_describe joins both.
+    cudaEventRecord(aux.ev_pyr, st);
+    cudaStreamWaitEvent(aux.stream, aux.ev_pyr, 0);
+    { AfvProfScope ps("k_blur", aux.stream); k_blur<<<dim3(acc, P.B), 256, 0, aux.stream>>>(P, TMB); ++g_afv_launches; }
+    cudaEventRecord(aux.ev_blur, aux.stream);
     { AfvProfScope ps("k_fast", st); k_fast<<<dim3(acc, P.B), 256, 0, st>>>(P, TM); ++g_afv_launches; }
     { AfvProfScope ps("k_harris_select", st); k_harris_select<<<dim3(P.nlevels, P.B), 256, 0, st>>>(P); ++g_afv_launches; }
     { AfvProfScope ps("k_octree", st);
       k_octree<<<dim3(P.nlevels, P.B), 256, afv_octree_smem_bytes(g_oct_mcap, g_oct_ncap), st>>>(P, g_oct_mcap, g_oct_ncap);
       ++g_afv_launches; }
-    { AfvProfScope ps("k_blur", st); k_blur<<<dim3(acc, P.B), 256, 0, st>>>(P, TMB); ++g_afv_launches; }
+    cudaStreamWaitEvent(st, aux.ev_blur, 0);
     { AfvProfScope ps("k_describe", st);
       k_describe<<<dim3((P.out_cap + 7) / 8, P.B), 256, 0, st>>>(P, d_kps, d_desc, d_kpsize, d_n_out); ++g_afv_launches; }
     return AFV_OK;
