@@ -980,13 +980,13 @@ int afv_launch_extract(const AfvParams& P, afv_keypoint* d_kps, uint8_t* d_desc,
         k_resize<<<g, 256, 0, st>>>(P, l);
         ++g_afv_launches;
     }
-    // The blur only needs the pyramid: it runs on the auxiliary stream, overlapping the latency-bound selection /
-    // octree kernels of the main stream; k_describe joins both.
+    // The blur only needs the pyramid: it runs on the auxiliary stream next to the latency-bound selection / octree
+    // kernels of the main stream (it is released after k_fast, which saturates the SMs by itself); k_describe joins.
+    { AfvProfScope ps("k_fast", st); k_fast<<<dim3(acc, P.B), 256, 0, st>>>(P, TM); ++g_afv_launches; }
     cudaEventRecord(aux.ev_pyr, st);
     cudaStreamWaitEvent(aux.stream, aux.ev_pyr, 0);
     { AfvProfScope ps("k_blur", aux.stream); k_blur<<<dim3(acc, P.B), 256, 0, aux.stream>>>(P, TMB); ++g_afv_launches; }
     cudaEventRecord(aux.ev_blur, aux.stream);
-    { AfvProfScope ps("k_fast", st); k_fast<<<dim3(acc, P.B), 256, 0, st>>>(P, TM); ++g_afv_launches; }
     { AfvProfScope ps("k_harris_select", st); k_harris_select<<<dim3(P.nlevels, P.B), 256, 0, st>>>(P); ++g_afv_launches; }
     { AfvProfScope ps("k_octree", st);
       k_octree<<<dim3(P.nlevels, P.B), 256, afv_octree_smem_bytes(g_oct_mcap, g_oct_ncap), st>>>(P, g_oct_mcap, g_oct_ncap);

@@ -96,6 +96,18 @@ class ClockSampler(threading.Thread):
 # ---------------------------------------------------------------------------------------------------------
 # CPU arm: the oracle port of the reference's per-frame path, all host threads (ctypes releases the GIL)
 # ---------------------------------------------------------------------------------------------------------
+def host_threads():
+    """Usable host threads: min(logical CPUs, cgroup CPU quota) -- the GPU boxes cap the container at 16 CPUs."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        q, per = open("/sys/fs/cgroup/cpu.max").read().split()
+        if q != "max":
+            n = max(1, min(n, int(int(q) / int(per))))
+    except Exception:
+        pass
+    return n
+
+
 def cpu_arm(frames, pair_b, nthreads, seconds_budget):
     """Returns (step(sample), sample, seconds per frame on one thread).  step() runs the oracle port of one bench step
     (extract every frame of the sample + SearchForInitialization of consecutive frames) threaded in C (OpenMP)."""
@@ -128,7 +140,7 @@ def run_reference(args):
         pass
     P = _P(); P.synth = synth
     frames, pa, pb = make_frames(P, min(args.batch, 256), 0)
-    nthreads = os.cpu_count() or 1
+    nthreads = host_threads()
     step, sample, per_frame = cpu_arm(frames, pb, nthreads, seconds_budget=4.0)
     for _ in range(max(1, min(args.warmup, 1))):
         step(sample)
@@ -329,7 +341,7 @@ def run_gpu(args):
                     "kernel_ms_per_step": {k: round(v[0], 4) for k, v in kern.items()},
                     "step_algorithmic_gbs": B * (4 * P_PIX + 12 * Ccand + 60 * N) / (ms / args.steps * 1e-3) / 1e9}
         # ---- CPU baseline (oracle port) on this host, bounded sample
-        nthreads = os.cpu_count() or 1
+        nthreads = host_threads()
         step, sample, per_frame = cpu_arm(frames, pb, nthreads, seconds_budget=3.0)
         step(sample)
         t0 = time.perf_counter(); reps = 2
@@ -337,8 +349,8 @@ def run_gpu(args):
             step(sample)
         cpu_fps = len(sample) * reps / (time.perf_counter() - t0)
         cpu_baseline = {"value": cpu_fps, "unit": UNIT, "cores": nthreads, "kind": "port",
-                        "sample": "%d frames x %d passes of the same workload, oracle C port, %d threads (1 thread: %.1f fps)"
-                                  % (len(sample), reps, nthreads, 1.0 / per_frame)}
+                        "sample": "%d frames x %d passes of the same workload, oracle C port, %d threads = min(logical CPUs %d, cgroup quota) (1 thread: %.1f fps)"
+                                  % (len(sample), reps, nthreads, os.cpu_count() or 0, 1.0 / per_frame)}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
