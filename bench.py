@@ -336,8 +336,15 @@ def run_gpu(args):
         peak = float(peaks.get("hbm_gbs", 6650.0))
         dom_ms = kern[dom][0]
         achieved = alg.get(dom, 0.0) / (dom_ms * 1e-3) / 1e9
+        traffic = None
+        try:      # dram__bytes_read+write of the dominant kernel from the committed ncu --set full capture, per launch
+            tj = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+            if dom in tj["dram_bytes_per_frame"]:
+                traffic = tj["dram_bytes_per_frame"][dom] * B
+        except Exception:
+            pass
         roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                    "traffic": None, "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback",
+                    "traffic": traffic, "algorithmic_bytes": alg.get(dom), "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback",
                     "kernel_ms_per_step": {k: round(v[0], 4) for k, v in kern.items()},
                     "step_algorithmic_gbs": B * (4 * P_PIX + 12 * Ccand + 60 * N) / (ms / args.steps * 1e-3) / 1e9}
         # ---- CPU baseline (oracle port) on this host, bounded sample
