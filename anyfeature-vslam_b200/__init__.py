@@ -160,6 +160,18 @@ class FeatureExtractor:
         return buf[:n.value].copy()
 
 
+def gray_from_color(d_img, rgb=True, out=None, stream=None):
+    """Image::GetGrayImage on device: uint8 cuda tensor [B,H,W,C] (C = 3 or 4) -> [B,H,W].  rgb=True reproduces the
+    reference (CV_RGB2GRAY applied to imread's BGR data)."""
+    import torch
+    B, h, w, ch = d_img.shape
+    if out is None:
+        out = torch.empty((B, h, w), dtype=torch.uint8, device=d_img.device)
+    _check(lib().afv_gray_from_color(_vp(d_img), ch, int(bool(rgb)), B, w, h, d_img.stride(1), C.c_long(d_img.stride(0)), _vp(out),
+                                     out.stride(1), C.c_long(out.stride(0)), _stream_ptr(stream)))
+    return out
+
+
 def kps_from_device(t, n):
     """[cap,7] float32 device rows -> numpy structured afv_keypoint array of length n."""
     a = t[:n].contiguous().cpu().numpy()

@@ -761,3 +761,24 @@ extern "C" int afv_descriptor_distance(int desc_type, const void* d_a, const voi
     AFV_CUDA_CHECK(cudaGetLastError());
     return AFV_OK;
 }
+
+// ---- Image::GetGrayImage (K1): OpenCV 8-bit cvtColor, 15-bit fixed point ---------------------------------------
+__global__ void k_gray(const uint8_t* __restrict__ src, int ch, int c0, int c1, int c2, int w, int h, int sstride, long long sfs,
+                       uint8_t* __restrict__ dst, int dstride, long long dfs) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y, f = blockIdx.z;
+    if (x >= w || y >= h) return;
+    const uint8_t* p = src + f * sfs + (long long)y * sstride + (long long)x * ch;
+    dst[f * dfs + (long long)y * dstride + x] = (uint8_t)((p[0] * c0 + p[1] * c1 + p[2] * c2 + (1 << 14)) >> 15);
+}
+extern "C" int afv_gray_from_color(const uint8_t* d_src, int channels, int rgb, int B, int w, int h, int src_stride,
+                                   long src_frame_stride, uint8_t* d_gray, int gray_stride, long gray_frame_stride, void* cuda_stream) {
+    if (!d_src || !d_gray || (channels != 3 && channels != 4) || B < 1 || w < 1 || h < 1 || src_stride < w * channels || gray_stride < w) {
+        afv_set_error("afv_gray_from_color: bad argument"); return AFV_ERR_INVALID;
+    }
+    const int RY = 9798, GY = 19235, BY = 3735;
+    k_gray<<<dim3((w + 255) / 256, h, B), 256, 0, as_stream(cuda_stream)>>>(d_src, channels, rgb ? RY : BY, GY, rgb ? BY : RY, w, h, src_stride,
+                                                                           src_frame_stride, d_gray, gray_stride, gray_frame_stride);
+    ++g_afv_launches;
+    AFV_CUDA_CHECK(cudaGetLastError());
+    return AFV_OK;
+}

@@ -358,6 +358,25 @@ def run_gpu(args):
         cpu_baseline = {"value": cpu_fps, "unit": UNIT, "cores": nthreads, "kind": "port",
                         "sample": "%d frames x %d passes of the same workload, oracle C port, %d threads = min(logical CPUs %d, cgroup quota) (1 thread: %.1f fps)"
                                   % (len(sample), reps, nthreads, os.cpu_count() or 0, 1.0 / per_frame)}
+        # ---- extras: single-frame latency through the host API (the reference handles one frame per call) and the
+        # host->device bandwidth that bounds the e2e leg
+        ex1 = pkg.FeatureExtractor("orb32", nfeatures=NFEAT, device=local, max_batch=1, max_w=W, max_h=H)
+        for _ in range(5):
+            ex1(frames[0])
+        t0 = time.perf_counter()
+        for i in range(50):
+            ex1(frames[i % len(frames)])
+        single_ms = (time.perf_counter() - t0) / 50 * 1e3
+        ex1.close()
+        torch.cuda.synchronize()
+        g0 = torch.cuda.Event(enable_timing=True); g1 = torch.cuda.Event(enable_timing=True)
+        d_tmp = torch.empty_like(d_gray)
+        d_tmp.copy_(h_gray, non_blocking=True); torch.cuda.synchronize()
+        g0.record()
+        for _ in range(3):
+            d_tmp.copy_(h_gray, non_blocking=True)
+        g1.record(); torch.cuda.synchronize()
+        h2d_gbs = 3 * h_gray.numel() / (g0.elapsed_time(g1) * 1e-3) / 1e9
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -367,7 +386,7 @@ def run_gpu(args):
                        "l2": "inputs+intermediates (%.1f GB/step) larger than L2, no flush" % (B * 3.1e6 / 1e9),
                        "gather": bool(world > 1 and args.gather)},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": ms_e2e / args.steps, "pipeline": "%d chunks of %d frames on 2 streams, host sync after the last step only" % (nchunks, CH)},
+                    "ms_per_step": ms_e2e / args.steps, "h2d_gbs_measured": h2d_gbs, "single_frame_latency_ms": single_ms, "pipeline": "%d chunks of %d frames on 2 streams, host sync after the last step only" % (nchunks, CH)},
             "gpu_launches": int(launches),
             "clocks": sampler.summary() if sampler else None,
             "roofline": roofline,

@@ -82,6 +82,15 @@ int  afv_extractor_status(afv_extractor* ex);
  *          4: octree-kept list in node-list order (8 bytes each as in 3)                                   */
 int  afv_debug_read(afv_extractor* ex, int what, int frame, int level, void* out, long cap_bytes, long* n_bytes);
 
+/* Image::GetGrayImage (src/Image.cpp:30-53): interleaved 3- or 4-channel 8-bit image -> gray with OpenCV's 8-bit
+ * cvtColor arithmetic (R,G,B weights 9798/19235/3735, +2^14, >>15).  `rgb` != 0 selects CV_RGB(A)2GRAY (channel 0
+ * weighted as R), 0 selects CV_BGR(A)2GRAY.  NB the reference always passes rgb = true on imread's BGR data
+ * (Tracking::mbRGB is never assigned, src/Tracking.cc:1447 vs include/Tracking.h:230): pass rgb = 1 to reproduce it.
+ * Device buffers, B frames, asynchronous on `cuda_stream`. */
+int  afv_gray_from_color(const uint8_t* d_src, int channels, int rgb, int B, int w, int h, int src_stride,
+                         long src_frame_stride, uint8_t* d_gray, int gray_stride, long gray_frame_stride,
+                         void* cuda_stream);
+
 /* ---- FeatureMatcher (reference include/FeatureMatcher.h:36-118, src/FeatureMatcher.cc) ------------------
  * The reference methods take Frame/KeyFrame/MapPoint graphs; the ABI sits one step inside, on arrays:
  * (query descriptors, window / bucket / all candidates, train descriptors) -> best index, best and second

@@ -567,3 +567,15 @@ int orc_orb32_extract(const uint8_t* gray, int w, int h, int stride,
     if (n_candidates) *n_candidates = ncand;
     return rc;
 }
+
+/* ---------------------------------------------------------------- Image::GetGrayImage ------------------------- */
+/* reference src/Image.cpp:30-53 -> cv::cvtColor(CV_RGB2GRAY / CV_BGR2GRAY / ...A2GRAY), 8-bit: OpenCV's 15-bit fixed
+ * point (R,G,B = 9798,19235,3735; +2^14; >>15), pinned to cv2 4.13.0 in tests/test_oracle_golden.py. */
+void orc_gray_from_color(const uint8_t* src, int channels, int rgb, int w, int h, int sstride, uint8_t* dst, int dstride) {
+    const int c0 = rgb ? 9798 : 3735, c1 = 19235, c2 = rgb ? 3735 : 9798;
+    for (int y = 0; y < h; ++y)
+        for (int x = 0; x < w; ++x) {
+            const uint8_t* p = src + (long)y * sstride + (long)x * channels;
+            dst[(long)y * dstride + x] = (uint8_t)((p[0] * c0 + p[1] * c1 + p[2] * c2 + (1 << 14)) >> 15);
+        }
+}

@@ -71,6 +71,9 @@ int  orc_orb32_extract(const uint8_t* gray, int w, int h, int stride,
                        orc_keypoint* kps, uint8_t* desc, float* kpsize, int cap, int* n_out,
                        int* n_candidates /* optional: total cv::ORB::detect keypoints */);
 
+/* Image::GetGrayImage (src/Image.cpp:30-53): cvtColor 8-bit fixed point; rgb=1 -> channel 0 weighted as R. */
+void orc_gray_from_color(const uint8_t* src, int channels, int rgb, int w, int h, int sstride, uint8_t* dst, int dstride);
+
 /* ------------------------------------------------------------------ matcher restatement ---------- */
 /* DescriptorDistance_* (src/Feature_orb32.cpp:67-83, Feature_akaze61.cpp:75-77, Feature_brisk48.cpp:62-64,
  * Feature_sift128.cpp:132-134). desc_type uses include/Types.h:24-34 ids (0 orb,1 akaze61,2 brisk,5 sift). */

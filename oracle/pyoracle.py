@@ -197,3 +197,11 @@ def extract_match_batch(frames, pair_a, pair_b, nfeatures=1000, nthreads=1, wind
                                             int(window), _f(th_low), _f(nnratio), int(bool(check_ori)), int(nthreads))
     assert r >= 0
     return int(r)
+
+
+def gray_from_color(img, rgb=True):
+    img = np.ascontiguousarray(img, np.uint8)
+    h, w, ch = img.shape
+    out = np.zeros((h, w), np.uint8)
+    lib().orc_gray_from_color(_p(img), ch, int(bool(rgb)), w, h, w * ch, _p(out), w)
+    return out

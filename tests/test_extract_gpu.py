@@ -151,3 +151,46 @@ def test_edge_cases(pkg):
     rk, rd, rs, _ = po.orb32_extract(img, 1000)
     assert _same_kps(k, rk) and (d == rd).all()
     ex.close()
+
+
+def test_gray_conversion_kernel(pkg):
+    import torch
+    rng = np.random.default_rng(1)
+    for ch in (3, 4):
+        img = rng.integers(0, 256, (3, 120, 161, ch), dtype=np.uint8)
+        for rgb in (True, False):
+            g = pkg.gray_from_color(torch.from_numpy(img).cuda(), rgb=rgb)
+            torch.cuda.synchronize()
+            ref = np.stack([po.gray_from_color(img[i], rgb=rgb) for i in range(3)])
+            assert (g.cpu().numpy() == ref).all()
+
+
+def test_full_size_batch_properties(pkg, synth):
+    """BASELINE-size batch (256 frames of 640x480, 1000 kp): size-independent properties + oracle spot checks.
+    Frames i and i+128 are the same image at different arena slots -> identical outputs (no cross-frame leakage,
+    deterministic regardless of atomics order); every frame has nfeatures..cap keypoints in ascending octaves with
+    per-level counts within [quota, quota+3]; three sampled frames are bit-exact against the oracle."""
+    import torch
+    base = np.concatenate([synth.stream_frames(640, 480, 20 + s, 16)[0] for s in range(8)], axis=0)
+    frames = np.concatenate([base, base], axis=0)
+    ex = pkg.FeatureExtractor("orb32", nfeatures=1000, max_batch=256, max_w=640, max_h=480)
+    out = ex.alloc_device_outputs(256)
+    ex.extract_batch_device(torch.from_numpy(frames).cuda(), out)
+    torch.cuda.synchronize()
+    ex.status()
+    n = out[3].cpu().numpy()
+    kps = out[0].cpu().numpy(); desc = out[1].cpu().numpy()
+    assert (n[:128] == n[128:]).all()
+    q = po.features_per_level(1000)
+    for f in range(128):
+        m = int(n[f])
+        assert (kps[f, :m].view(np.uint8) == kps[f + 128, :m].view(np.uint8)).all() and (desc[f, :m] == desc[f + 128, :m]).all()
+        k = kps[f, :m].view(np.uint8).reshape(m, 28).view(pkg.KP_DTYPE).reshape(m)
+        assert 1000 <= m <= ex.cap and (np.diff(k["octave"]) >= 0).all()
+        cnt = np.bincount(k["octave"], minlength=8)
+        assert ((cnt >= q) & (cnt <= q + 3)).all()
+    for f in (0, 77, 200):
+        rk, rd, rs, _ = po.orb32_extract(frames[f], 1000)
+        m = int(n[f])
+        assert _same_kps(pkg.kps_from_device(out[0][f], m), rk) and (desc[f, :m] == rd).all()
+    ex.close()

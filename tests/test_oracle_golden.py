@@ -76,3 +76,20 @@ def test_octree_edge_cases():
     assert sorted(keep.tolist()) == list(range(50))          # every key ends alone in its node
     keep = po.octree(x, y, r, 640, 480, 8)
     assert 8 <= len(keep) <= 11 and len(set(keep.tolist())) == len(keep)
+
+
+def test_gray_conversion_matches_cv2_when_available():
+    cv2 = pytest.importorskip("cv2")
+    rng = np.random.default_rng(0)
+    img = rng.integers(0, 256, (97, 131, 3), dtype=np.uint8)
+    assert (po.gray_from_color(img, rgb=True) == cv2.cvtColor(img, cv2.COLOR_RGB2GRAY)).all()
+    assert (po.gray_from_color(img, rgb=False) == cv2.cvtColor(img, cv2.COLOR_BGR2GRAY)).all()
+    img4 = rng.integers(0, 256, (33, 47, 4), dtype=np.uint8)
+    assert (po.gray_from_color(img4, rgb=True) == cv2.cvtColor(img4, cv2.COLOR_RGBA2GRAY)).all()
+
+
+def test_gray_conversion_known_answers():
+    # committed known answers (cv2 4.13.0): weights 9798/19235/3735, +2^14, >>15
+    img = np.array([[[255, 0, 0], [0, 255, 0], [0, 0, 255], [255, 255, 255], [10, 200, 77], [128, 128, 128]]], np.uint8)
+    assert po.gray_from_color(img, rgb=True).tolist() == [[76, 150, 29, 255, 129, 128]]
+    assert po.gray_from_color(img, rgb=False).tolist() == [[29, 150, 76, 255, 142, 128]]
