@@ -252,11 +252,14 @@ def run_gpu(args):
     c_pa = d_pa[:CH].contiguous(); c_pb = d_pb[:CH].contiguous()            # pair pattern repeats every 16 frames
     h_out = [torch.empty(t.shape, dtype=t.dtype).pin_memory() for t in (out[0], out[1], out[3], m12, nm)]
 
+    chunk_counter = [0]
+
     def e2e_step():
         # streaming operation: every step copies its frames in and its results out; chunks alternate between the two
         # streams so copies of one chunk overlap kernels of the other, also across step boundaries (no host sync here)
         for c in range(nchunks):
-            k = c & 1
+            k = chunk_counter[0] & 1                           # alternate streams across chunks AND steps
+            chunk_counter[0] += 1
             st = streams[k]
             lo, hi = c * CH, (c + 1) * CH
             with torch.cuda.stream(st):
@@ -407,7 +410,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--batch", type=int, default=512, help="frames per step per GPU")
-    ap.add_argument("--e2e-chunk", type=int, default=256, help="frames per pipelined chunk in the e2e leg")
+    ap.add_argument("--e2e-chunk", type=int, default=512, help="frames per pipelined chunk in the e2e leg")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-gather", dest="gather", action="store_false")
     args = ap.parse_args()

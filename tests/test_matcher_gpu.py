@@ -194,3 +194,45 @@ def test_cpp_host_mirror_matches_python_path(pkg, synth, tmp_path):
     assert int(got["levels"]) == 8 and int(got["q0"]) == 217
     assert int(got["hash"]) == h
     ex.close()
+
+
+@pytest.mark.parametrize("desc_type,D", [(1, 61), (2, 48), (5, 512)])
+def test_search_for_initialization_other_descriptor_layouts(pkg, extracted, desc_type, D):
+    """akaze61 / brisk48 (Hamming over 61 / 48 bytes, unaligned rows) and sift128 (L2^2 on 128 floats) through the
+    same SearchForInitialization path: real orb keypoints, synthetic descriptors with planted correspondences."""
+    import torch
+    out, host, cap = extracted
+    rng = np.random.default_rng(40 + desc_type)
+    k1, _, s1 = host[0]; k2, _, s2 = host[1]
+    n1, n2 = len(k1), len(k2)
+    if desc_type == 5:
+        d2 = rng.normal(size=(n2, 128)).astype(np.float32); d2 /= np.linalg.norm(d2, axis=1, keepdims=True)
+        d1 = rng.normal(size=(n1, 128)).astype(np.float32); d1 /= np.linalg.norm(d1, axis=1, keepdims=True)
+        th = 0.5
+    else:
+        d2 = rng.integers(0, 256, (n2, D), dtype=np.uint8); d1 = rng.integers(0, 256, (n1, D), dtype=np.uint8)
+        th = 128.0 if desc_type == 1 else 120.0
+    # plant matches: query i looks like the nearest train keypoint (in position) with a little noise
+    for i in range(0, n1, 2):
+        j = int(np.argmin((k2["x"] - k1["x"][i]) ** 2 + (k2["y"] - k1["y"][i]) ** 2))
+        if desc_type == 5:
+            v = d2[j] + rng.normal(scale=0.03, size=128).astype(np.float32); d1[i] = (v / np.linalg.norm(v)).astype(np.float32)
+        else:
+            d1[i] = d2[j] ^ (rng.integers(0, 256, D, dtype=np.uint8) & rng.integers(0, 256, D, dtype=np.uint8) & rng.integers(0, 256, D, dtype=np.uint8))
+    Db = 512 if desc_type == 5 else D
+    kps = torch.zeros((2, cap, 7), dtype=torch.float32, device="cuda"); kps[0] = out[0][0]; kps[1] = out[0][1]
+    desc = torch.zeros((2, cap, Db), dtype=torch.uint8, device="cuda")
+    desc[0, :n1] = torch.from_numpy(d1.view(np.uint8).reshape(n1, Db)).cuda(); desc[1, :n2] = torch.from_numpy(d2.view(np.uint8).reshape(n2, Db)).cuda()
+    size = torch.zeros((2, cap), dtype=torch.float32, device="cuda"); size[0] = out[2][0]; size[1] = out[2][1]
+    n = torch.tensor([n1, n2], dtype=torch.int32, device="cuda")
+    pa = torch.tensor([0, 1], dtype=torch.int32, device="cuda"); pb = torch.tensor([1, 0], dtype=torch.int32, device="cuda")
+    pm = torch.zeros((2, cap, 2), dtype=torch.float32, device="cuda"); pm[0] = kps[0, :, :2]; pm[1] = kps[1, :, :2]
+    fm = pkg.FeatureMatcher(nnratio=0.9, check_ori=(desc_type != 5), desc_type=desc_type, th_low=th)
+    m12, nm = fm.search_for_initialization(kps, desc, size, n, pa, pb, pm, BOUNDS, MAXSZ, window=100)
+    torch.cuda.synchronize()
+    for p, (a, b, ka, da, kb, db, sb) in enumerate([(0, 1, k1, d1, k2, d2, s2), (1, 0, k2, d2, k1, d1, s1)]):
+        prev = np.stack([ka["x"], ka["y"]], axis=1)
+        rn, rm, rpm = po.search_for_initialization(desc_type, ka, da, kb, db, sb, BOUNDS, MAXSZ, prev, window=100, th_low=th,
+                                                   nnratio=0.9, check_ori=(desc_type != 5))
+        assert int(nm[p]) == rn and (m12[p, :len(ka)].cpu().numpy() == rm).all(), "pair %d" % p
+    assert int(nm[0]) > 40
