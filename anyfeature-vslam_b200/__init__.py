@@ -181,4 +181,4 @@ def kps_from_device(t, n):
 from . import matcher as matcher  # noqa: E402  (FeatureMatcher mirror)
 from . import synth as synth  # noqa: E402  (synthetic frame generator)
 from . import sharding as sharding  # noqa: E402  (multi-GPU host logic)
-from .matcher import FeatureMatcher  # noqa: E402,F401
+from .matcher import FeatureMatcher, Vocabulary  # noqa: E402,F401

@@ -782,3 +782,61 @@ extern "C" int afv_gray_from_color(const uint8_t* d_src, int channels, int rgb, 
     AFV_CUDA_CHECK(cudaGetLastError());
     return AFV_OK;
 }
+
+// ---- DBoW2 tree descent (Vocabulary::transform): one warp per feature, lanes over the children of the current node ----
+__device__ __forceinline__ double dbow_distance(int desc_type, const uint8_t* a, const uint8_t* b) {
+    if (desc_type == AFV_FEAT_SIFT128) {                 // FSift128::distance: float products accumulated in double
+        const float* x = (const float*)a; const float* y = (const float*)b;
+        double sqd = 0.;
+        for (int i = 0; i < 128; ++i) { const float d = x[i] - y[i]; sqd += (double)(d * d); }
+        return sqd;
+    }
+    const int nb = desc_type == AFV_FEAT_ORB32 ? 32 : desc_type == AFV_FEAT_AKAZE61 ? 56 : 48;   // FAkaze61 compares 7 x 8 bytes
+    int d = 0;
+    for (int i = 0; i < nb; ++i) d += __popc((uint32_t)(a[i] ^ b[i]));
+    return (double)d;
+}
+__global__ void __launch_bounds__(256) k_bow_transform(int desc_type, int D, const uint8_t* __restrict__ desc, int n,
+        const int* __restrict__ child_off, const int* __restrict__ child_ids, const uint8_t* __restrict__ node_desc,
+        const int* __restrict__ node_word, const double* __restrict__ node_weight, int depth_L, int levelsup,
+        int* __restrict__ word_id, double* __restrict__ weight, int* __restrict__ node_id) {
+    const int fi = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (fi >= n) return;
+    const uint8_t* f = desc + (long long)fi * D;
+    const int nid_level = depth_L - levelsup;
+    int nid = 0, final_id = 0, level = 0;
+    for (;;) {
+        const int c0 = child_off[final_id], c1 = child_off[final_id + 1];
+        if (c1 <= c0) break;                                            // leaf
+        ++level;
+        // (distance, child position) minimum: first minimum wins
+        double bd = 1e300; int bpos = 0x7fffffff;
+        for (int c = c0 + lane; c < c1; c += 32) {
+            const double d = dbow_distance(desc_type, f, node_desc + (long long)child_ids[c] * D);
+            if (d < bd) { bd = d; bpos = c; }
+        }
+#pragma unroll
+        for (int o = 16; o; o >>= 1) {
+            const double od = __shfl_xor_sync(0xffffffffu, bd, o); const int op = __shfl_xor_sync(0xffffffffu, bpos, o);
+            if (od < bd || (od == bd && op < bpos)) { bd = od; bpos = op; }
+        }
+        final_id = child_ids[bpos];
+        if (level == nid_level) nid = final_id;
+    }
+    if (lane == 0) { word_id[fi] = node_word[final_id]; weight[fi] = node_weight[final_id]; node_id[fi] = nid_level <= 0 ? 0 : nid; }
+}
+extern "C" int afv_bow_transform(int desc_type, const void* d_desc, int n, const int* d_child_off, const int* d_child_ids,
+                                 const void* d_node_desc, const int* d_node_word, const double* d_node_weight, int n_nodes, int depth_L,
+                                 int levelsup, int* d_word_id, double* d_weight, int* d_node_id, void* cuda_stream) {
+    const int D = desc_bytes(desc_type);
+    if (D < 0 || n < 0 || n_nodes < 1 || !d_child_off || !d_child_ids || !d_node_desc || !d_node_word || !d_node_weight) {
+        afv_set_error("afv_bow_transform: bad argument"); return AFV_ERR_INVALID;
+    }
+    if (n == 0) return AFV_OK;
+    if (!d_desc || !d_word_id || !d_weight || !d_node_id) { afv_set_error("afv_bow_transform: NULL argument"); return AFV_ERR_INVALID; }
+    k_bow_transform<<<(n + 7) / 8, 256, 0, as_stream(cuda_stream)>>>(desc_type, D, (const uint8_t*)d_desc, n, d_child_off, d_child_ids,
+        (const uint8_t*)d_node_desc, d_node_word, d_node_weight, depth_L, levelsup, d_word_id, d_weight, d_node_id);
+    ++g_afv_launches;
+    AFV_CUDA_CHECK(cudaGetLastError());
+    return AFV_OK;
+}

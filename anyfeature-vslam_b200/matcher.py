@@ -7,6 +7,8 @@ FeatureMatcher.matchingTh of settings/<feat>_settings.yaml.
 """
 import ctypes as C
 
+import numpy as np
+
 
 def _afv():
     from . import lib, _check, _vp, _stream_ptr
@@ -102,3 +104,42 @@ class FeatureMatcher:
         out = torch.empty(n, dtype=torch.float32, device=a.device)
         _check(lib.afv_descriptor_distance(int(desc_type), _vp(a), _vp(b), n, _vp(out), _sp(stream)))
         return out
+
+
+class Vocabulary:
+    """Mirror of the reference's Vocabulary::transform (src/Vocabulary.cpp:156-207) on a flat k-ary tree held on the
+    device (DBoW2 TemplatedVocabulary semantics, levelsup = 4).  `tree`: dict of numpy arrays child_off [N+1], child_ids,
+    node_desc [N,D], node_word [N] (-1 for inner nodes), node_weight [N] float64, and depth L."""
+
+    def __init__(self, desc_type, tree, device=0):
+        import torch
+        dev = torch.device("cuda", device)
+        self.desc_type = int(desc_type)
+        self.L = int(tree["L"])
+        t = lambda a, dt: torch.from_numpy(np.ascontiguousarray(a, dt)).to(dev)
+        self.child_off = t(tree["child_off"], np.int32); self.child_ids = t(tree["child_ids"], np.int32)
+        nd = np.ascontiguousarray(tree["node_desc"])
+        self.node_desc = torch.from_numpy(nd.view(np.uint8).reshape(nd.shape[0], -1)).to(dev)
+        self.node_word = t(tree["node_word"], np.int32); self.node_weight = t(tree["node_weight"], np.float64)
+        self.n_nodes = int(self.node_word.shape[0])
+
+    def transform(self, desc, levelsup=4, stream=None):
+        """desc: uint8 cuda tensor [n, D bytes]. Returns (word_id i32 [n], weight f64 [n], node_id i32 [n])."""
+        import torch
+        lib, _check, _vp, _sp = _afv()
+        n = desc.shape[0]
+        wid = torch.empty(max(n, 1), dtype=torch.int32, device=desc.device)
+        w = torch.empty(max(n, 1), dtype=torch.float64, device=desc.device)
+        nid = torch.empty(max(n, 1), dtype=torch.int32, device=desc.device)
+        _check(lib.afv_bow_transform(self.desc_type, _vp(desc), n, _vp(self.child_off), _vp(self.child_ids), _vp(self.node_desc),
+                                     _vp(self.node_word), _vp(self.node_weight), self.n_nodes, self.L, int(levelsup),
+                                     _vp(wid), _vp(w), _vp(nid), _sp(stream)))
+        return wid[:n], w[:n], nid[:n]
+
+    @staticmethod
+    def feature_vector_segments(node_id):
+        """FeatureVector (sorted node ids + CSR of ascending feature indices) from per-feature node ids (numpy)."""
+        node_id = np.asarray(node_id)
+        order = np.argsort(node_id, kind="stable")
+        ids, starts = np.unique(node_id[order], return_index=True)
+        return ids.astype(np.int32), np.append(starts, len(node_id)).astype(np.int32), order.astype(np.int32)

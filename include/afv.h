@@ -143,6 +143,19 @@ int  afv_search_by_bow(int desc_type,
                        float th_low, float nnratio, int check_orientation,
                        int* d_match_f, int* d_nmatches, void* cuda_stream);
 
+/* Vocabulary::transform (src/Vocabulary.cpp:156-207) -> DBoW2 TemplatedVocabulary::transform per feature
+ * (Thirdparty/DBoW2/include/DBoW2/TemplatedVocabulary.h:1346-1387): descend the k-ary tree from the root choosing the
+ * child with the smallest F<feat>::distance (first minimum wins; Thirdparty/DBoW2/src/FOrb.cpp:73-92 32 bytes,
+ * FAkaze61.cpp:85-100 only the first 56 of 61 bytes, FBrisk.cpp:78-100 48 bytes, FSift128.cpp:48-59 L2^2) until a
+ * leaf.  Tree as flat arrays: children of node i are child_ids[child_off[i] .. child_off[i+1]) (empty = leaf),
+ * node_desc[i] its descriptor, node_word[i] / node_weight[i] the word id / weight of leaves.  Outputs per feature:
+ * word id, weight, and the ancestor at level (depth L - levelsup) that keys the FeatureVector used by SearchByBoW
+ * (levelsup = 4 in the reference).  All device pointers. */
+int  afv_bow_transform(int desc_type, const void* d_desc, int n,
+                       const int* d_child_off, const int* d_child_ids, const void* d_node_desc,
+                       const int* d_node_word, const double* d_node_weight, int n_nodes, int depth_L, int levelsup,
+                       int* d_word_id, double* d_weight, int* d_node_id, void* cuda_stream);
+
 /* FeatureMatcher::DescriptorDistance (src/FeatureMatcher.cc:1508-1531) for n pairs (a[i], b[i]). */
 int  afv_descriptor_distance(int desc_type, const void* d_a, const void* d_b, int n, float* d_out,
                              void* cuda_stream);

@@ -124,6 +124,11 @@ long orc_orb32_extract_match_batch(const uint8_t* frames, int B, int w, int h, i
                                    float scale_factor, float detect_th, const int* pair_a, const int* pair_b, int P,
                                    int window, float th_low, float nnratio, int check_ori, int nthreads);
 
+/* DBoW2 tree descent per feature (Vocabulary::transform, src/Vocabulary.cpp:156-207). */
+void orc_bow_transform(int desc_type, const void* desc, int n, const int* child_off, const int* child_ids, const void* node_desc,
+                       const int* node_word, const double* node_weight, int depth_L, int levelsup,
+                       int* word_id, double* weight, int* node_id);
+
 /* rotation-consistency helpers (src/FeatureMatcher.cc:1579-1668) */
 int  orc_rot_bin(float angle1, float angle2);
 void orc_three_maxima(const int* hist_counts, int len, int* ind1, int* ind2, int* ind3);

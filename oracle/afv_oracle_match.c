@@ -294,6 +294,47 @@ int orc_search_by_bow(int desc_type,
     return nMatches;
 }
 
+/* ---------------------------------------------------------------- DBoW2 tree descent ---------------------- */
+/* TemplatedVocabulary::transform(feature, word_id, weight, nid, levelsup)
+ * (Thirdparty/DBoW2/include/DBoW2/TemplatedVocabulary.h:1346-1387) with the per-feature distances of
+ * Thirdparty/DBoW2/src/FOrb.cpp:73-92, FAkaze61.cpp:85-100 (56 of 61 bytes), FBrisk.cpp:78-100, FSift128.cpp:48-59. */
+static double orc_dbow_distance(int desc_type, const uint8_t* a, const uint8_t* b) {
+    if (desc_type == 5) {
+        const float *x = (const float*)a, *y = (const float*)b;
+        double sqd = 0.;
+        for (int i = 0; i < 128; ++i) sqd += (x[i] - y[i]) * (x[i] - y[i]);
+        return sqd;
+    }
+    const int nb = desc_type == 0 ? 32 : desc_type == 1 ? 56 : 48;
+    int d = 0;
+    for (int i = 0; i < nb; ++i) d += popc8((unsigned)(a[i] ^ b[i]));
+    return (double)d;
+}
+void orc_bow_transform(int desc_type, const void* desc, int n, const int* child_off, const int* child_ids, const void* node_desc,
+                       const int* node_word, const double* node_weight, int depth_L, int levelsup,
+                       int* word_id, double* weight, int* node_id) {
+    const int D = orc_descriptor_bytes(desc_type);
+    const int nid_level = depth_L - levelsup;
+    for (int i = 0; i < n; ++i) {
+        const uint8_t* f = (const uint8_t*)desc + (long)i * D;
+        int final_id = 0, level = 0, nid = 0;
+        while (child_off[final_id + 1] > child_off[final_id]) {
+            ++level;
+            const int c0 = child_off[final_id], c1 = child_off[final_id + 1];
+            int best = child_ids[c0];
+            double best_d = orc_dbow_distance(desc_type, f, (const uint8_t*)node_desc + (long)best * D);
+            for (int c = c0 + 1; c < c1; ++c) {
+                const int id = child_ids[c];
+                const double d = orc_dbow_distance(desc_type, f, (const uint8_t*)node_desc + (long)id * D);
+                if (d < best_d) { best_d = d; best = id; }
+            }
+            final_id = best;
+            if (level == nid_level) nid = final_id;
+        }
+        word_id[i] = node_word[final_id]; weight[i] = node_weight[final_id]; node_id[i] = nid_level <= 0 ? 0 : nid;
+    }
+}
+
 /* ---------------------------------------------------------------- batch driver for the CPU arm ------ */
 /* Same work as one bench.py step, all in C so host threads scale (pthreads pulling frames, then pairs, from an
  * atomic counter): orb32 extraction of B frames + SearchForInitialization of frame pair_a[p] against pair_b[p].

@@ -205,3 +205,24 @@ def gray_from_color(img, rgb=True):
     out = np.zeros((h, w), np.uint8)
     lib().orc_gray_from_color(_p(img), ch, int(bool(rgb)), w, h, w * ch, _p(out), w)
     return out
+
+
+def bow_transform(desc_type, desc, tree, levelsup=4):
+    """tree = dict(child_off, child_ids, node_desc, node_word, node_weight, L). Returns (word_id, weight, node_id)."""
+    desc = np.ascontiguousarray(desc)
+    n = len(desc)
+    co = np.ascontiguousarray(tree["child_off"], np.int32); ci = np.ascontiguousarray(tree["child_ids"], np.int32)
+    nd = np.ascontiguousarray(tree["node_desc"]); nw = np.ascontiguousarray(tree["node_word"], np.int32)
+    wt = np.ascontiguousarray(tree["node_weight"], np.float64)
+    wid = np.zeros(max(n, 1), np.int32); w = np.zeros(max(n, 1), np.float64); nid = np.zeros(max(n, 1), np.int32)
+    lib().orc_bow_transform(desc_type, _p(desc), n, _p(co), _p(ci), _p(nd), _p(nw), _p(wt), int(tree["L"]), int(levelsup),
+                            _p(wid), _p(w), _p(nid))
+    return wid[:n].copy(), w[:n].copy(), nid[:n].copy()
+
+
+def feature_vector_segments(node_id):
+    """DBoW2::FeatureVector as SearchByBoW consumes it: sorted node ids + CSR of feature indices (ascending)."""
+    node_id = np.asarray(node_id)
+    order = np.argsort(node_id, kind="stable")
+    ids, starts = np.unique(node_id[order], return_index=True)
+    return ids.astype(np.int32), np.append(starts, len(node_id)).astype(np.int32), order.astype(np.int32)

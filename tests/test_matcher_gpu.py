@@ -236,3 +236,39 @@ def test_search_for_initialization_other_descriptor_layouts(pkg, extracted, desc
                                                    nnratio=0.9, check_ori=(desc_type != 5))
         assert int(nm[p]) == rn and (m12[p, :len(ka)].cpu().numpy() == rm).all(), "pair %d" % p
     assert int(nm[0]) > 40
+
+
+@pytest.mark.parametrize("desc_type,D,fl", [(0, 32, False), (1, 61, False), (2, 48, False), (5, 128, True)])
+def test_bow_transform_and_search_by_bow_chain(pkg, extracted, desc_type, D, fl):
+    """Vocabulary::transform on the GPU == oracle (word, weight, FeatureVector node), then the FeatureVectors feed
+    SearchByBoW (orb only: real descriptors)."""
+    import torch
+    from tests_bow import make_tree
+    rng = np.random.default_rng(60 + desc_type)
+    tree = make_tree(rng, k=10, L=3, D=D, float_desc=fl)
+    out, host, cap = extracted
+    if desc_type == 0:
+        feats = host[0][1]
+    elif fl:
+        feats = rng.normal(size=(500, 128)).astype(np.float32)
+    else:
+        feats = rng.integers(0, 256, (500, D), dtype=np.uint8)
+    voc = pkg.Vocabulary(desc_type, tree)
+    dfe = torch.from_numpy(np.ascontiguousarray(feats).view(np.uint8).reshape(len(feats), -1)).cuda()
+    for levelsup in (1, 2, 4):
+        wid, w, nid = voc.transform(dfe, levelsup=levelsup)
+        torch.cuda.synchronize()
+        rw, rwt, rn = po.bow_transform(desc_type, feats, tree, levelsup=levelsup)
+        assert (wid.cpu().numpy() == rw).all() and (w.cpu().numpy() == rwt).all() and (nid.cpu().numpy() == rn).all()
+    if desc_type == 0:
+        k1, d1, s1 = host[0]; k2, d2, s2 = host[1]
+        segs = []
+        for f, d in ((0, d1), (1, d2)):
+            _, _, nid = voc.transform(out[1][f, :len(d)], levelsup=1)
+            segs.append(pkg.Vocabulary.feature_vector_segments(nid.cpu().numpy()))
+        rn, rmf = po.search_by_bow(0, d1, k1, segs[0], d2, k2, segs[1], th_low=75.0, nnratio=0.7, check_ori=True)
+        fm = pkg.FeatureMatcher(nnratio=0.7, check_ori=True, desc_type=0, th_low=75.0)
+        t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+        mf, nm = fm.search_by_bow(out[1][0, :len(k1)], out[0][0], [t(v) for v in segs[0]], out[1][1, :len(k2)], out[0][1], [t(v) for v in segs[1]])
+        torch.cuda.synchronize()
+        assert int(nm[0]) == rn and (mf.cpu().numpy() == rmf).all()

@@ -95,3 +95,20 @@ def test_search_by_bow_buckets(synth):
     idx = np.nonzero(mf >= 0)[0]
     assert n == len(idx) and n > 100
     assert len(set(mf[idx].tolist())) <= n
+
+
+def test_bow_transform_oracle_properties():
+    from tests_bow import make_tree
+    rng = np.random.default_rng(7)
+    tree = make_tree(rng, k=10, L=3, D=32)
+    leaves = np.nonzero(tree["node_word"] >= 0)[0]
+    # a feature equal to a leaf's descriptor whose ancestors are also nearest descends to that leaf (distance 0 at the end)
+    feats = tree["node_desc"][leaves[::37]]
+    wid, w, nid = po.bow_transform(0, feats, tree, levelsup=1)
+    assert (wid >= 0).all() and (w > 0).all()
+    # node ids at level L - levelsup are inner nodes of depth 2
+    assert ((nid >= 11) & (nid <= 110)).all()
+    # levelsup >= L -> root
+    assert (po.bow_transform(0, feats, tree, levelsup=4)[2] == 0).all()
+    ids, starts, order = po.feature_vector_segments(nid)
+    assert (np.diff(ids) > 0).all() and starts[-1] == len(nid)
