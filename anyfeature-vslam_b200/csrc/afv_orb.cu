@@ -830,28 +830,13 @@ __device__ __forceinline__ float fast_atan2_deg(float y, float x) {
     return a;
 }
 
-// Patch staging: a keypoint whose 37x37 footprint lies inside the level gets its two patches by TMA (un-blurred 31 rows
-// x 48 B for the moments, blurred 37 rows x 64 B for the BRIEF taps; box starts aligned down to 16 B) into the warp's
-// shared-memory slot, so the 31 + 16 scattered global loads per lane become two bulk copies; keypoints near the border
-// (REFLECT_101 / un-blurred padding semantics) keep the direct global path.
-#define DS_IMG_W 48
-#define DS_IMG_H 31
-#define DS_BLR_W 64
-#define DS_BLR_H 37
-#define DS_IMG_BYTES 1536            // 48*31 = 1488 rounded up to 128
-#define DS_BLR_BYTES 2432            // 64*37 = 2368 rounded up to 128
-struct AfvTmaps2 { CUtensorMap img[AFV_MAX_LEVELS]; CUtensorMap blr[AFV_MAX_LEVELS]; };
-
-__global__ void __launch_bounds__(256) k_describe(const __grid_constant__ AfvParams P, const __grid_constant__ AfvTmaps2 TM,
-                                                  afv_keypoint* __restrict__ kps, uint8_t* __restrict__ desc,
-                                                  float* __restrict__ kpsize, int* __restrict__ n_out) {
-    __shared__ __align__(128) uint8_t patch[8][DS_IMG_BYTES + DS_BLR_BYTES];
-    __shared__ __align__(8) uint64_t bars[8];
+__global__ void __launch_bounds__(256) k_describe(const __grid_constant__ AfvParams P, afv_keypoint* __restrict__ kps,
+                                                  uint8_t* __restrict__ desc, float* __restrict__ kpsize,
+                                                  int* __restrict__ n_out) {
     __shared__ uint32_t patw[8][32];         // patw[k][lane] = (x0,y0,x1,y1) int8 of test k of descriptor byte `lane`
     __shared__ int lvl_start[AFV_MAX_LEVELS + 1];
     const int f = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     { const int pl = tid & 31, pk = tid >> 5; patw[pk][pl] = *reinterpret_cast<const uint32_t*>(&c_pattern[pl * 32 + pk * 4]); }
-    if (tid < 8) mbar_init(&bars[tid], 1);
     if (tid == 0) {
         int acc = 0;
         for (int l = 0; l < P.nlevels; ++l) {
@@ -875,33 +860,17 @@ __global__ void __launch_bounds__(256) k_describe(const __grid_constant__ AfvPar
     const int x0 = kd.x & 0xfff, y0 = (kd.x >> 12) & 0xfff;
     const uint8_t* img = L.img + (long long)f * L.img_fstride;
     const uint8_t* blr = L.blur + (long long)f * L.fstride;
-    // whole footprint (radius 18 taps, radius 15 disc + lane 31's dummy column) inside the level -> TMA path
-    const bool staged = x0 >= 18 && y0 >= 18 && x0 + 18 < L.w && y0 + 18 < L.h;
-    const int xa = (x0 - 15) & ~15, xb = (x0 - 18) & ~15;
-    const uint8_t* pimg = &patch[warp][0];
-    const uint8_t* pblr = &patch[warp][DS_IMG_BYTES];
-    if (staged) {
-        if (lane == 0) {
-            mbar_expect_tx(&bars[warp], DS_IMG_W * DS_IMG_H + DS_BLR_W * DS_BLR_H);
-            tma_load_3d(const_cast<uint8_t*>(pimg), &TM.img[l], &bars[warp], xa, y0 - 15, f);
-            tma_load_3d(const_cast<uint8_t*>(pblr), &TM.blr[l], &bars[warp], xb, y0 - 18, f);
-        }
-        mbar_wait(&bars[warp], 0);
-    }
 
     // intensity-centroid moments over the radius-15 disc (cv::ORB ICAngles); lane = u + 15.  Fully unrolled so the
-    // 31 independent row loads are in flight together.
+    // 31 independent row loads are in flight together (the loop was latency-bound on one load per iteration).
     int m10 = 0, m01 = 0;
     const int u = lane - 15;
     const int au = u < 0 ? -u : u;
+    const bool inner = (x0 >= 15 && y0 >= 15 && x0 + 16 < L.w && y0 + 15 < L.h);
     {
         constexpr int UM[16] = {15, 15, 15, 15, 14, 14, 14, 13, 13, 12, 11, 10, 9, 8, 6, 3};
         int vals[31];
-        if (staged) {
-            const uint8_t* base = pimg + (x0 - 15 - xa) + lane;         // lane 31 reads one byte past the disc (masked below)
-#pragma unroll
-            for (int r = 0; r < 31; ++r) vals[r] = base[r * DS_IMG_W];
-        } else if (x0 >= 15 && y0 >= 15 && x0 + 16 < L.w && y0 + 15 < L.h) {
+        if (inner) {
             const uint8_t* base = img + (long long)(y0 - 15) * L.img_stride + x0 + u;
 #pragma unroll
             for (int r = 0; r < 31; ++r) vals[r] = base[(long long)r * L.img_stride];
@@ -928,7 +897,6 @@ __global__ void __launch_bounds__(256) k_describe(const __grid_constant__ AfvPar
     const int cx = __float2int_rn(__fmul_rn(fx, L.inv_scale)), cy = __float2int_rn(__fmul_rn(fy, L.inv_scale));
     const float ang = __fmul_rn(angle, 0x1.1df46ap-6f);            // (float)(CV_PI/180.f)
     const float a = (float)cos((double)ang), b = (float)sin((double)ang);
-    const bool use_patch = staged && cx == x0 && cy == y0;           // always true (the round trip returns the integer)
     const bool dinner = (cx >= 19 && cy >= 19 && cx + 19 < L.w && cy + 19 < L.h);
     uint32_t byte = 0;
 #pragma unroll
@@ -938,11 +906,9 @@ __global__ void __launch_bounds__(256) k_describe(const __grid_constant__ AfvPar
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
             const float px = (float)(int)(int8_t)(pw >> (16 * j)), py = (float)(int)(int8_t)(pw >> (16 * j + 8));
-            const int dx = __float2int_rn(__fsub_rn(__fmul_rn(px, a), __fmul_rn(py, b)));
-            const int dy = __float2int_rn(__fadd_rn(__fmul_rn(px, b), __fmul_rn(py, a)));
-            const int ix = cx + dx, iy = cy + dy;
-            if (use_patch) tv[j] = pblr[(dy + 18) * DS_BLR_W + (ix - xb)];
-            else if (dinner || (ix >= 0 && ix < L.w && iy >= 0 && iy < L.h)) tv[j] = blr[(long long)iy * L.stride + ix];
+            const int ix = cx + __float2int_rn(__fsub_rn(__fmul_rn(px, a), __fmul_rn(py, b)));
+            const int iy = cy + __float2int_rn(__fadd_rn(__fmul_rn(px, b), __fmul_rn(py, a)));
+            if (dinner || (ix >= 0 && ix < L.w && iy >= 0 && iy < L.h)) tv[j] = blr[(long long)iy * L.stride + ix];
             else tv[j] = img[(long long)refl101(iy, L.h) * L.img_stride + refl101(ix, L.w)];
         }
         byte |= (uint32_t)(tv[0] < tv[1]) << k;
@@ -978,7 +944,7 @@ typedef CUresult (*afv_encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuuin
 static afv_encode_tiled_fn g_encode = nullptr;
 
 // 3-D u8 tensor map of one level: (x, y, frame) with the k_fast staging box.
-static int make_level_tmap(CUtensorMap* m, const AfvLevel& L, int B, int box_w, int box_h, bool blurred = false) {
+static int make_level_tmap(CUtensorMap* m, const AfvLevel& L, int B, int box_w, int box_h) {
     if (!g_encode) {
         void* fn = nullptr; cudaDriverEntryPointQueryResult qr;
         if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qr) != cudaSuccess || !fn) {
@@ -987,10 +953,10 @@ static int make_level_tmap(CUtensorMap* m, const AfvLevel& L, int B, int box_w, 
         g_encode = (afv_encode_tiled_fn)fn;
     }
     const cuuint64_t gdim[3] = {(cuuint64_t)L.w, (cuuint64_t)L.h, (cuuint64_t)B};
-    const cuuint64_t gstr[2] = {(cuuint64_t)(blurred ? L.stride : L.img_stride), (cuuint64_t)(blurred ? L.fstride : L.img_fstride)};
+    const cuuint64_t gstr[2] = {(cuuint64_t)L.img_stride, (cuuint64_t)L.img_fstride};
     const cuuint32_t box[3] = {(cuuint32_t)box_w, (cuuint32_t)box_h, 1};
     const cuuint32_t estr[3] = {1, 1, 1};
-    CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, blurred ? (void*)L.blur : (void*)const_cast<uint8_t*>(L.img), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+    CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<uint8_t*>(L.img), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                           CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { afv_set_error("cuTensorMapEncodeTiled failed (%d) for a %dx%d level, stride %d", (int)r, L.w, L.h, L.img_stride); return AFV_ERR_CUDA; }
     return AFV_OK;
@@ -999,13 +965,10 @@ static int make_level_tmap(CUtensorMap* m, const AfvLevel& L, int B, int box_w, 
 int afv_launch_extract(const AfvParams& P, afv_keypoint* d_kps, uint8_t* d_desc, float* d_kpsize,
                        int* d_n_out, cudaStream_t st, const AfvAux& aux) {
     AfvTmaps TM, TMB;                         // k_fast / k_blur staging boxes
-    AfvTmaps2 TMD;                            // k_describe patches (un-blurred / blurred)
-    memset(&TM, 0, sizeof(TM)); memset(&TMB, 0, sizeof(TMB)); memset(&TMD, 0, sizeof(TMD));
+    memset(&TM, 0, sizeof(TM)); memset(&TMB, 0, sizeof(TMB));
     for (int l = 0; l < P.nlevels; ++l) {
         int rc = make_level_tmap(&TM.m[l], P.lv[l], P.B, FT_WP * 4, FT_PH);
         if (!rc) rc = make_level_tmap(&TMB.m[l], P.lv[l], P.B, BT_WP * 4, BT_H + 6);
-        if (!rc) rc = make_level_tmap(&TMD.img[l], P.lv[l], P.B, DS_IMG_W, DS_IMG_H);
-        if (!rc) rc = make_level_tmap(&TMD.blr[l], P.lv[l], P.B, DS_BLR_W, DS_BLR_H, true);
         if (rc) return rc;
     }
     const int acc = P.ntiles;
@@ -1030,6 +993,6 @@ int afv_launch_extract(const AfvParams& P, afv_keypoint* d_kps, uint8_t* d_desc,
       ++g_afv_launches; }
     cudaStreamWaitEvent(st, aux.ev_blur, 0);
     { AfvProfScope ps("k_describe", st);
-      k_describe<<<dim3((P.out_cap + 7) / 8, P.B), 256, 0, st>>>(P, TMD, d_kps, d_desc, d_kpsize, d_n_out); ++g_afv_launches; }
+      k_describe<<<dim3((P.out_cap + 7) / 8, P.B), 256, 0, st>>>(P, d_kps, d_desc, d_kpsize, d_n_out); ++g_afv_launches; }
     return AFV_OK;
 }
