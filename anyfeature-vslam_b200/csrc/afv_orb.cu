@@ -60,25 +60,24 @@ __device__ __forceinline__ int refl101(int i, int n) {
 // 4 packed table entries (offset << 16 | c1).
 #define RS_ROWS 24
 #define RS_PITCH 176
-__global__ void __launch_bounds__(256) k_resize(const __grid_constant__ AfvParams P, int l) {
-    __shared__ __align__(16) uint8_t sp[RS_ROWS][RS_PITCH];
+__global__ void __launch_bounds__(256) k_resize(const __grid_constant__ AfvParams P, const __grid_constant__ CUtensorMap tm_src, int l) {
+    __shared__ __align__(128) uint8_t sp[RS_ROWS][RS_PITCH];
+    __shared__ __align__(8) uint64_t tma_bar;
     const AfvLevel& D = P.lv[l];
     const AfvLevel& S = P.lv[l - 1];
     const int f = blockIdx.z, tid = threadIdx.x, lane = tid & 31, wrp = tid >> 5;
     const int tx0 = blockIdx.x * 128, ty0 = blockIdx.y * 16;
-    const uint8_t* src = S.img + (long long)f * S.img_fstride;
-    const int sxb = (int)(D.xtab[tx0] >> 16) & ~3;                 // first staged source column (word aligned)
+    const int sxb = (int)(D.xtab[tx0] >> 16) & ~15;                // first staged source column (16-B aligned for TMA)
     const int syb = (int)(D.ytab[ty0] >> 16);                      // first staged source row
-    const int lastw = (S.img_stride >> 2) - 1;
-    for (int r = wrp; r < RS_ROWS; r += 8) {
-        const uint32_t* row = reinterpret_cast<const uint32_t*>(src + (long long)min(syb + r, S.h - 1) * S.img_stride);
-#pragma unroll
-        for (int part = 0; part < 2; ++part) {
-            const int q = part * 32 + lane;
-            if (q >= RS_PITCH / 4) break;
-            reinterpret_cast<uint32_t*>(&sp[r][0])[q] = row[min((sxb >> 2) + q, lastw)];
-        }
+    // source footprint (<= 172 x 22 bytes incl. alignment slack) by one TMA box; rows / columns past the source are
+    // zero-filled and only ever multiplied by a zero coefficient (the tables clamp the last tap)
+    if (tid == 0) mbar_init(&tma_bar, 1);
+    __syncthreads();
+    if (tid == 0) {
+        mbar_expect_tx(&tma_bar, RS_ROWS * RS_PITCH);
+        tma_load_3d(&sp[0][0], &tm_src, &tma_bar, sxb, syb, f);
     }
+    mbar_wait(&tma_bar, 0);
     __syncthreads();
     const int x0 = tx0 + 4 * lane;
     if (x0 >= D.w) return;
@@ -976,8 +975,10 @@ int afv_launch_extract(const AfvParams& P, afv_keypoint* d_kps, uint8_t* d_desc,
     cudaMemsetAsync(P.status, 0, sizeof(int) * P.B, st);
     for (int l = 1; l < P.nlevels; ++l) {
         dim3 g((P.lv[l].w + 127) / 128, (P.lv[l].h + 15) / 16, P.B);
+        CUtensorMap tms;
+        { const int rc = make_level_tmap(&tms, P.lv[l - 1], P.B, RS_PITCH, RS_ROWS); if (rc) return rc; }
         AfvProfScope ps("k_resize", st);
-        k_resize<<<g, 256, 0, st>>>(P, l);
+        k_resize<<<g, 256, 0, st>>>(P, tms, l);
         ++g_afv_launches;
     }
     // The blur only needs the pyramid: it runs on the auxiliary stream next to the latency-bound selection / octree
