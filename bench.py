@@ -198,16 +198,29 @@ def run_gpu(args):
     if world > 1 and args.gather:
         # C5: fixed-capacity packed results gathered to rank 0 over NCCL/NVLink (n, nmatches, matches, kps, desc)
         _, pack_bytes = pkg.sharding.pack_layout(B, cap, 32)
-        d_pack = torch.empty(pack_bytes, dtype=torch.uint8, device=dev)
-        gathered = [torch.empty(pack_bytes, dtype=torch.uint8, device=dev) for _ in range(world)] if rank == 0 else None
+        # two pack / receive buffer sets: the gather of step i runs on NCCL's stream while step i+1 computes
+        d_pack = [torch.empty(pack_bytes, dtype=torch.uint8, device=dev) for _ in range(2)]
+        gathered = [[torch.empty(pack_bytes, dtype=torch.uint8, device=dev) for _ in range(world)] if rank == 0 else None for _ in range(2)]
+    pending = [None, None]
+    step_counter = [0]
 
     def device_step(src, collective=True):
         ex.extract_batch_device(src, out, stream)
         fm.search_for_initialization(out[0], out[1], out[2], out[3], d_pa, d_pb, None, BOUNDS, MAX_KPT_SIZE,
                                      window=100, matches12=m12, nmatches=nm, stream=stream)
         if world > 1 and args.gather and collective:
-            pkg.sharding.pack_results(d_pack, out[3], nm, m12, out[0], out[1])
-            pkg.sharding.gather_to_root(d_pack, gathered, world, rank)
+            k = step_counter[0] & 1
+            step_counter[0] += 1
+            if pending[k] is not None:
+                pending[k].wait()                              # buffer set k is free again
+            pkg.sharding.pack_results(d_pack[k], out[3], nm, m12, out[0], out[1])
+            pending[k] = dist.gather(d_pack[k], gathered[k], dst=0, async_op=True)
+
+    def drain_collectives():
+        for k in range(2):
+            if pending[k] is not None:
+                pending[k].wait()
+                pending[k] = None
 
     def barrier():
         if world > 1:
@@ -217,6 +230,7 @@ def run_gpu(args):
     # ---- warm-up (also the validity check: capacity flags, plausible match counts)
     for _ in range(max(args.warmup, 3)):
         device_step(d_gray)
+    drain_collectives()
     torch.cuda.synchronize()
     ex.status()
     n_host = out[3].cpu().numpy(); nm_host = nm.cpu().numpy()
@@ -232,6 +246,7 @@ def run_gpu(args):
     e0.record()
     for _ in range(args.steps):
         device_step(d_gray)
+    drain_collectives()                                    # every step's results have reached rank 0
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
@@ -387,7 +402,7 @@ def run_gpu(args):
             "config": {"workload": "orb32 640x480 synthetic batch, 1000 kp/frame, extract+SearchForInitialization on 1xB200 per rank (configs[1])",
                        "frames_per_step_per_gpu": B, "pairs_per_step_per_gpu": B, "parallelism": "frames sharded, dp%d" % world,
                        "l2": "inputs+intermediates (%.1f GB/step) larger than L2, no flush" % (B * 3.1e6 / 1e9),
-                       "gather": bool(world > 1 and args.gather)},
+                       "gather": bool(world > 1 and args.gather), "gather_mode": "NCCL gather of packed results to rank 0 every step, overlapped with the next step"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": ms_e2e / args.steps, "h2d_gbs_measured": h2d_gbs, "single_frame_latency_ms": single_ms, "pipeline": "%d chunks of %d frames on 2 streams, host sync after the last step only" % (nchunks, CH)},
             "gpu_launches": int(launches),
