@@ -633,6 +633,296 @@ extern "C" int afv_search_for_initialization(int desc_type, const afv_keypoint* 
     return AFV_OK;
 }
 
+// ---- SearchByProjection family: same two-kernel split as SearchForInitialization ------------------------------
+// k_proj_lists: CTA per problem, warp per query, train frame counting-sorted by grid column in shared memory; candidate =
+// grid cell in the query's cell range, size inside [min,max] (Frame::GetFeaturesInArea size gate, src/Frame.cc:365-368),
+// |dx|,|dy| < r.  k_proj_resolve: warp per problem, "occupied" flags in shared memory, queries in order.
+__host__ __device__ inline size_t prl_base_bytes(int cap) { return (((size_t)cap * (4 * 3 + 2 * 3)) + 15) & ~(size_t)15; }
+__host__ __device__ inline size_t prr_warp_bytes(int cap) { return (((size_t)cap * (4 + 2 + 1)) + 15) & ~(size_t)15; }
+struct ProjQMeta { int off, cnt; };
+
+template <bool BINARY>
+__global__ void __launch_bounds__(SFL_THREADS) k_proj_lists(int desc_type, int D, int Dpad, int stage_desc,
+        const uint8_t* __restrict__ qdesc, const float* __restrict__ qxy, const float* __restrict__ qr,
+        const float* __restrict__ qmin, const float* __restrict__ qmax, const int* __restrict__ q_start,
+        const afv_keypoint* __restrict__ kps, const uint8_t* __restrict__ desc, const float* __restrict__ kpsize,
+        const int* __restrict__ n_arr, int cap, const int* __restrict__ frame,
+        float minX, float minY, float invW, float invH, void* __restrict__ pool_v, int pool_cap, ProjQMeta* __restrict__ qmeta) {
+    extern __shared__ __align__(16) unsigned char sm[];
+    const int p = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int fb = frame[p];
+    const int n2 = min(n_arr[fb], cap);
+    const afv_keypoint* k2 = kps + (long long)fb * cap;
+    const uint8_t* d2 = desc + (long long)fb * cap * D;
+    const float* size2 = kpsize + (long long)fb * cap;
+    float* sx = reinterpret_cast<float*>(sm); float* sy = sx + cap; float* ssz = sy + cap;
+    unsigned short* scell = reinterpret_cast<unsigned short*>(ssz + cap);
+    unsigned short* sorig = scell + cap; unsigned short* tmpc = sorig + cap;
+    uint8_t* sdesc = sm + prl_base_bytes(cap);
+    __shared__ int colstart[AFV_GRID_COLS + 1], colfill[AFV_GRID_COLS];
+    __shared__ int s_pool;
+    const int nw = Dpad / 4;
+    const unsigned short NONE16 = 0xffff;
+    if (tid < AFV_GRID_COLS) { colstart[tid] = 0; colfill[tid] = 0; }
+    if (tid == 0) { s_pool = 0; colstart[AFV_GRID_COLS] = 0; }
+    __syncthreads();
+    for (int i = tid; i < n2; i += SFL_THREADS) {
+        const int c = grid_cell(k2[i].x, k2[i].y, minX, minY, invW, invH);
+        tmpc[i] = c >= 0 ? (unsigned short)c : NONE16;
+        if (c >= 0) atomicAdd(&colstart[c / AFV_GRID_ROWS + 1], 1);
+    }
+    __syncthreads();
+    if (wid == 0) {
+        int a0 = colstart[1 + lane], a1 = colstart[33 + lane];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { int t0 = __shfl_up_sync(0xffffffffu, a0, o), t1 = __shfl_up_sync(0xffffffffu, a1, o); if (lane >= o) { a0 += t0; a1 += t1; } }
+        const int tot0 = __shfl_sync(0xffffffffu, a0, 31);
+        colstart[1 + lane] = a0; colstart[33 + lane] = tot0 + a1;
+    }
+    __syncthreads();
+    for (int i = tid; i < n2; i += SFL_THREADS) {
+        const int c = tmpc[i];
+        if (c == NONE16) continue;
+        const int cx = c / AFV_GRID_ROWS;
+        const int slot = colstart[cx] + atomicAdd(&colfill[cx], 1);
+        sx[slot] = k2[i].x; sy[slot] = k2[i].y; ssz[slot] = size2[i];
+        scell[slot] = (unsigned short)((cx << 8) | (c % AFV_GRID_ROWS));
+        sorig[slot] = (unsigned short)i;
+    }
+    __syncthreads();
+    const int n2s = colstart[AFV_GRID_COLS];
+    if (stage_desc) {
+        for (int i = tid; i < n2s * nw; i += SFL_THREADS) {
+            const int r = i / nw, w = i % nw;
+            const uint8_t* row = d2 + (long long)sorig[r] * D;
+            uint32_t v;
+            if ((D & 3) == 0) v = reinterpret_cast<const uint32_t*>(row)[w];
+            else { v = 0; for (int b = 0; b < 4; ++b) { const int o = w * 4 + b; if (o < D) v |= (uint32_t)row[o] << (8 * b); } }
+            reinterpret_cast<uint32_t*>(sdesc)[(size_t)w * cap + r] = v;
+        }
+    }
+    __syncthreads();
+    const int q0 = q_start[p], q1 = q_start[p + 1];
+    for (int qi = q0 + wid; qi < q1; qi += SFL_THREADS / 32) {
+        SfiQuery q;
+        q.x = qxy[2 * qi]; q.y = qxy[2 * qi + 1];
+        const float r = qr[qi], smin = qmin[qi], smax = qmax[qi];
+        q.ok = window_cells(q.x, q.y, r, minX, minY, invW, invH, q.c0, q.c1, q.r0, q.r1);
+        int cnt = 0, off = 0;
+        if (q.ok) {
+            const int s0 = colstart[q.c0], s1 = colstart[q.c1 + 1];
+            auto is_cand = [&](int sl) {
+                const unsigned short cc = scell[sl];
+                const float sz = ssz[sl];
+                return !(sz < smin) && !(sz > smax) && sfi_in_window(q, cc >> 8, cc & 0xff, sx[sl], sy[sl], r);
+            };
+            for (int sb = s0; sb < s1; sb += 32) {
+                const int sl = sb + lane;
+                cnt += __popc(__ballot_sync(0xffffffffu, sl < s1 && is_cand(sl)));
+            }
+            if (cnt > 0) {
+                if (lane == 0) off = atomicAdd(&s_pool, cnt);
+                off = __shfl_sync(0xffffffffu, off, 0);
+                if (off + cnt > pool_cap) off = -1;
+            }
+            if (cnt > 0 && off >= 0) {
+                uint32_t qd[16];
+                const uint8_t* qrow = qdesc + (long long)qi * D;
+                if (BINARY) {
+                    if ((D & 3) == 0 && ((uintptr_t)qrow & 3) == 0) {
+#pragma unroll
+                        for (int w = 0; w < 16; ++w) if (w < nw) qd[w] = reinterpret_cast<const uint32_t*>(qrow)[w];
+                    } else {
+#pragma unroll
+                        for (int w = 0; w < 16; ++w) if (w < nw) { uint32_t v = 0; for (int b = 0; b < 4; ++b) { const int o = w * 4 + b; if (o < D) v |= (uint32_t)qrow[o] << (8 * b); } qd[w] = v; }
+                    }
+                }
+                int run = off;
+                for (int sb = s0; sb < s1; sb += 32) {
+                    const int sl = sb + lane;
+                    const bool pass = sl < s1 && is_cand(sl);
+                    const unsigned m = __ballot_sync(0xffffffffu, pass);
+                    if (pass) {
+                        const int i2 = sorig[sl];
+                        const int pos = run + __popc(m & ((1u << lane) - 1));
+                        if (BINARY) {
+                            int d = 0;
+                            if (stage_desc) {
+                                const uint32_t* y32 = reinterpret_cast<const uint32_t*>(sdesc) + sl;
+#pragma unroll
+                                for (int w = 0; w < 16; ++w) if (w < nw) d += __popc(qd[w] ^ y32[(size_t)w * cap]);
+                            } else d = hamming_bytes(qrow, d2 + (long long)i2 * D, D);
+                            reinterpret_cast<uint32_t*>(pool_v)[(long long)p * pool_cap + pos] = ((uint32_t)d << 20) | (uint32_t)i2;
+                        } else {
+                            const float dist = l2sqr128((const float*)qrow, (const float*)(d2 + (long long)i2 * D));
+                            reinterpret_cast<unsigned long long*>(pool_v)[(long long)p * pool_cap + pos] = make_key(dist, (uint32_t)i2);
+                        }
+                    }
+                    run += __popc(m);
+                }
+            }
+        }
+        if (lane == 0) { ProjQMeta m; m.off = off; m.cnt = cnt; qmeta[qi] = m; }
+    }
+}
+
+template <bool BINARY>
+__global__ void __launch_bounds__(SFR_WARPS * 32) k_proj_resolve(int desc_type, int D,
+        const uint8_t* __restrict__ qdesc, const float* __restrict__ qxy, const float* __restrict__ qr,
+        const float* __restrict__ qmin, const float* __restrict__ qmax, const int* __restrict__ q_start, int P,
+        const afv_keypoint* __restrict__ kps, const uint8_t* __restrict__ desc, const float* __restrict__ kpsize,
+        const int* __restrict__ n_arr, int cap, const int* __restrict__ frame, const uint8_t* __restrict__ occupied_in,
+        float minX, float minY, float invW, float invH, float th, float nnratio, int ratio_same_scale, float tol,
+        const void* __restrict__ pool_v, int pool_cap, const ProjQMeta* __restrict__ qmeta,
+        int* __restrict__ match_q, int* __restrict__ nmatches) {
+    extern __shared__ __align__(16) unsigned char sm[];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int p = blockIdx.x * SFR_WARPS + wid;
+    if (p >= P) return;
+    unsigned char* base = sm + (size_t)wid * prr_warp_bytes(cap);
+    float* tsize = reinterpret_cast<float*>(base);
+    unsigned short* tcell = reinterpret_cast<unsigned short*>(tsize + cap);
+    unsigned char* occ = reinterpret_cast<unsigned char*>(tcell + cap);
+    const int fb = frame[p];
+    const int n2 = min(n_arr[fb], cap);
+    const afv_keypoint* k2 = kps + (long long)fb * cap;
+    const uint8_t* d2 = desc + (long long)fb * cap * D;
+    const float* size2 = kpsize + (long long)fb * cap;
+    const unsigned short NONE16 = 0xffff;
+    for (int i = lane; i < n2; i += 32) {
+        tsize[i] = size2[i];
+        const int c = grid_cell(k2[i].x, k2[i].y, minX, minY, invW, invH);
+        tcell[i] = c >= 0 ? (unsigned short)(((c / AFV_GRID_ROWS) << 8) | (c % AFV_GRID_ROWS)) : NONE16;
+        occ[i] = occupied_in ? occupied_in[(long long)fb * cap + i] : 0;
+    }
+    __syncwarp();
+    const float invtol = __fdiv_rn(1.0f, tol);
+    int nm = 0;
+    const int q0 = q_start[p], q1 = q_start[p + 1];
+    for (int qi = q0; qi < q1; ++qi) {
+        const ProjQMeta q = qmeta[qi];
+        int bestIdx = -1;
+        if (q.cnt > 0) {
+            Top2 t; t.k1 = t.k2 = KEY_NONE;
+            if (q.off >= 0) {
+                for (int j0 = 0; j0 < q.cnt; j0 += 32) {
+                    const int j = j0 + lane;
+                    if (j >= q.cnt) continue;
+                    unsigned long long key;
+                    if (BINARY) {
+                        const uint32_t e = reinterpret_cast<const uint32_t*>(pool_v)[(long long)p * pool_cap + q.off + j];
+                        key = ((unsigned long long)__float_as_uint((float)(e >> 20)) << 32) | (e & 0xfffffu);
+                    } else key = reinterpret_cast<const unsigned long long*>(pool_v)[(long long)p * pool_cap + q.off + j];
+                    const int i2 = (int)((uint32_t)key & 0xfffffu);
+                    if (occ[i2]) continue;                                  // F.pts[idx] already holds a map point
+                    const unsigned short cc = tcell[i2];
+                    top2_push(t, make_key(key_dist(key), ((uint32_t)(cc >> 8) << 26) | ((uint32_t)(cc & 0xff) << 20) | (uint32_t)i2));
+                }
+            } else {
+                // exact fallback (pool exhausted): rescan the train frame with the same candidate definition
+                SfiQuery w;
+                w.x = qxy[2 * qi]; w.y = qxy[2 * qi + 1];
+                const float r = qr[qi], smin = qmin[qi], smax = qmax[qi];
+                w.ok = window_cells(w.x, w.y, r, minX, minY, invW, invH, w.c0, w.c1, w.r0, w.r1);
+                for (int i2 = lane; w.ok && i2 < n2; i2 += 32) {
+                    const unsigned short cc = tcell[i2];
+                    if (cc == NONE16 || occ[i2] || tsize[i2] < smin || tsize[i2] > smax) continue;
+                    if (!sfi_in_window(w, cc >> 8, cc & 0xff, k2[i2].x, k2[i2].y, r)) continue;
+                    const float dist = desc_distance(desc_type, qdesc + (long long)qi * D, d2 + (long long)i2 * D, D);
+                    top2_push(t, make_key(dist, ((uint32_t)(cc >> 8) << 26) | ((uint32_t)(cc & 0xff) << 20) | (uint32_t)i2));
+                }
+            }
+            top2_warp_reduce(t);
+            if (t.k1 != KEY_NONE) {
+                const float bestDist = key_dist(t.k1), bestDist2 = key_dist(t.k2);
+                const int bi = (int)((uint32_t)t.k1 & 0xfffffu);
+                if (bestDist <= th) {
+                    bool accept = true;
+                    if (ratio_same_scale) {                                 // :139-146
+                        const float bestSize = tsize[bi];
+                        const float bestSize2 = t.k2 != KEY_NONE ? tsize[(uint32_t)t.k2 & 0xfffffu] : -1.0f;
+                        const float ratio = __fdiv_rn(bestSize, bestSize2);
+                        if (ratio < tol && ratio > invtol && bestSize2 > 0.0f)
+                            if (bestDist > __fmul_rn(nnratio, bestDist2)) accept = false;
+                    }
+                    if (accept) bestIdx = bi;
+                }
+            }
+        }
+        if (bestIdx >= 0) { if (lane == 0) occ[bestIdx] = 1; ++nm; }
+        if (lane == 0) match_q[qi] = bestIdx;
+        __syncwarp();
+    }
+    if (lane == 0) nmatches[p] = nm;
+}
+
+extern "C" int afv_search_by_projection(int desc_type, const void* d_qdesc, const float* d_qxy, const float* d_qr,
+        const float* d_qmin_size, const float* d_qmax_size, const int* d_q_start, int P,
+        const afv_keypoint* d_kps, const void* d_desc, const float* d_kpsize, const int* d_n, int B, int cap, const int* d_frame,
+        const uint8_t* d_occupied, float min_x, float min_y, float max_x, float max_y, float th, float nnratio,
+        int ratio_same_scale_only, float size_tolerance, int* d_match_q, int* d_nmatches, void* cuda_stream) {
+    const int D = desc_bytes(desc_type);
+    if (D < 0 || !d_qdesc || !d_qxy || !d_qr || !d_qmin_size || !d_qmax_size || !d_q_start || !d_kps || !d_desc || !d_kpsize || !d_n ||
+        !d_frame || !d_match_q || !d_nmatches || B < 1 || P < 0 || cap < 1 || !(size_tolerance > 0.0f)) {
+        afv_set_error("afv_search_by_projection: bad argument"); return AFV_ERR_INVALID;
+    }
+    if (P == 0) return AFV_OK;
+    if (cap >= 65535) { afv_set_error("cap too large for the 16-bit indices"); return AFV_ERR_INVALID; }
+    cudaStream_t st = as_stream(cuda_stream);
+    const bool binary = desc_type != AFV_FEAT_SIFT128;
+    const int Dpad = (D + 3) & ~3;
+    const size_t baseA = prl_base_bytes(cap);
+    const int stage = binary && Dpad <= 64 && baseA + (size_t)cap * Dpad <= 200 * 1024;
+    const size_t smemA = baseA + (stage ? (size_t)cap * Dpad : 0);
+    const size_t smemB = prr_warp_bytes(cap) * SFR_WARPS;
+    if (smemA > 220 * 1024 || smemB > 220 * 1024) { afv_set_error("cap %d too large for the shared-memory staging", cap); return AFV_ERR_INVALID; }
+    static size_t confA[2] = {0, 0}, confB[2] = {0, 0};
+    if (smemA > confA[binary]) {
+        AFV_CUDA_CHECK(binary ? cudaFuncSetAttribute(k_proj_lists<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemA)
+                              : cudaFuncSetAttribute(k_proj_lists<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemA));
+        confA[binary] = smemA;
+    }
+    if (smemB > confB[binary]) {
+        AFV_CUDA_CHECK(binary ? cudaFuncSetAttribute(k_proj_resolve<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemB)
+                              : cudaFuncSetAttribute(k_proj_resolve<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemB));
+        confB[binary] = smemB;
+    }
+    int nq_total = 0;
+    AFV_CUDA_CHECK(cudaMemcpyAsync(&nq_total, d_q_start + P, sizeof(int), cudaMemcpyDeviceToHost, st));
+    AFV_CUDA_CHECK(cudaStreamSynchronize(st));
+    if (nq_total <= 0) { AFV_CUDA_CHECK(cudaMemsetAsync(d_nmatches, 0, sizeof(int) * P, st)); return AFV_OK; }
+    const int pool_cap = 64 * 1024;
+    const size_t esz = binary ? 4 : 8;
+    unsigned char* scratch = nullptr;
+    const size_t pool_bytes = (size_t)P * pool_cap * esz, meta_bytes = (size_t)nq_total * sizeof(ProjQMeta);
+    AFV_CUDA_CHECK(cudaMallocAsync((void**)&scratch, pool_bytes + meta_bytes + 256, st));
+    void* pool = scratch;
+    ProjQMeta* qmeta = reinterpret_cast<ProjQMeta*>(scratch + pool_bytes);
+    const float invW = (float)AFV_GRID_COLS / (max_x - min_x), invH = (float)AFV_GRID_ROWS / (max_y - min_y);
+    {
+        AfvProfScope ps("k_proj_lists", st);
+        if (binary) k_proj_lists<true><<<P, SFL_THREADS, smemA, st>>>(desc_type, D, Dpad, stage, (const uint8_t*)d_qdesc, d_qxy, d_qr, d_qmin_size, d_qmax_size,
+                d_q_start, d_kps, (const uint8_t*)d_desc, d_kpsize, d_n, cap, d_frame, min_x, min_y, invW, invH, pool, pool_cap, qmeta);
+        else k_proj_lists<false><<<P, SFL_THREADS, smemA, st>>>(desc_type, D, Dpad, stage, (const uint8_t*)d_qdesc, d_qxy, d_qr, d_qmin_size, d_qmax_size,
+                d_q_start, d_kps, (const uint8_t*)d_desc, d_kpsize, d_n, cap, d_frame, min_x, min_y, invW, invH, pool, pool_cap, qmeta);
+        ++g_afv_launches;
+    }
+    {
+        AfvProfScope ps("k_proj_resolve", st);
+        const int grid = (P + SFR_WARPS - 1) / SFR_WARPS;
+        if (binary) k_proj_resolve<true><<<grid, SFR_WARPS * 32, smemB, st>>>(desc_type, D, (const uint8_t*)d_qdesc, d_qxy, d_qr, d_qmin_size, d_qmax_size, d_q_start, P,
+                d_kps, (const uint8_t*)d_desc, d_kpsize, d_n, cap, d_frame, d_occupied, min_x, min_y, invW, invH, th, nnratio, ratio_same_scale_only,
+                size_tolerance, pool, pool_cap, qmeta, d_match_q, d_nmatches);
+        else k_proj_resolve<false><<<grid, SFR_WARPS * 32, smemB, st>>>(desc_type, D, (const uint8_t*)d_qdesc, d_qxy, d_qr, d_qmin_size, d_qmax_size, d_q_start, P,
+                d_kps, (const uint8_t*)d_desc, d_kpsize, d_n, cap, d_frame, d_occupied, min_x, min_y, invW, invH, th, nnratio, ratio_same_scale_only,
+                size_tolerance, pool, pool_cap, qmeta, d_match_q, d_nmatches);
+        ++g_afv_launches;
+    }
+    AFV_CUDA_CHECK(cudaGetLastError());
+    AFV_CUDA_CHECK(cudaFreeAsync(scratch, st));
+    return AFV_OK;
+}
+
 // ---- brute force N x M: one warp per query, lanes stride over train descriptors ----------------------------
 __global__ void __launch_bounds__(256) k_match_bf(int desc_type, int D, const uint8_t* __restrict__ q, int nq,
         const uint8_t* __restrict__ t, int nt, int* __restrict__ best, float* __restrict__ bestd, float* __restrict__ secondd) {

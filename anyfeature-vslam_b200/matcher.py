@@ -73,6 +73,26 @@ class FeatureMatcher:
                                     _vp(best), _vp(bd), _vp(sd), _vp(bs), _vp(ss), _sp(stream)))
         return best, bd, sd, bs, ss
 
+    # -- SearchByProjection family (src/FeatureMatcher.cc:73-154, :287-397), batched over problems ------------------
+    def search_by_projection(self, qdesc, qxy, qr, qmin, qmax, q_start, kps, desc, kpsize, n, frame, bounds, occupied=None,
+                             ratio_same_scale=True, size_tolerance=1.2, stream=None):
+        """qdesc [Q,D] u8, qxy [Q,2], qr/qmin/qmax [Q] f32, q_start [P+1] i32, frame [P] i32 (train frame of problem p in the
+        B x cap arrays), occupied [B,cap] u8 or None.  Returns (match_q [Q] i32 train index or -1, nmatches [P] i32)."""
+        import torch
+        lib, _check, _vp, _sp = _afv()
+        P = frame.shape[0]
+        Q = qdesc.shape[0]
+        B, cap = kps.shape[0], kps.shape[1]
+        match_q = torch.empty(max(Q, 1), dtype=torch.int32, device=kps.device)
+        nm = torch.empty(max(P, 1), dtype=torch.int32, device=kps.device)
+        minx, miny, maxx, maxy = bounds
+        _check(lib.afv_search_by_projection(self.desc_type, _vp(qdesc), _vp(qxy), _vp(qr), _vp(qmin), _vp(qmax), _vp(q_start), P,
+                                            _vp(kps), _vp(desc), _vp(kpsize), _vp(n), B, cap, _vp(frame), _vp(occupied),
+                                            C.c_float(minx), C.c_float(miny), C.c_float(maxx), C.c_float(maxy), C.c_float(self.th_low),
+                                            C.c_float(self.nnratio), int(bool(ratio_same_scale)), C.c_float(size_tolerance),
+                                            _vp(match_q), _vp(nm), _sp(stream)))
+        return match_q[:Q], nm[:P]
+
     def match_bruteforce(self, q, t, stream=None):
         import torch
         lib, _check, _vp, _sp = _afv()

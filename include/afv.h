@@ -129,6 +129,22 @@ int  afv_search_for_initialization(int desc_type, const afv_keypoint* d_kps, con
                                    int check_orientation, int* d_matches12, int* d_nmatches,
                                    void* cuda_stream);
 
+/* SearchByProjection family (src/FeatureMatcher.cc:73-154 TrackLocalMap, :287-397 Sim3 / relocalisation variants; the
+ * same core serves Fuse and SearchBySim3): P independent problems, problem p projects queries q_start[p]..q_start[p+1]
+ * (descriptor, projected position, search radius, accepted size range = predicted size / and * sizeTolerance) into train
+ * frame d_frame[p] of a B x cap extraction result.  Sequential semantics reproduced exactly: queries in order; a train
+ * keypoint that already holds a map point (d_occupied, or claimed by an earlier query of this call) is skipped;
+ * best / second distance with their keypoint sizes; accept if best <= th and, when ratio_same_scale_only != 0, reject
+ * when best and second are within the size tolerance of each other and best > nnratio * second (:139-146);
+ * ratio_same_scale_only == 0 gives the best-only rule of :381-386.  d_match_q[q] = train index or -1. */
+int  afv_search_by_projection(int desc_type, const void* d_qdesc, const float* d_qxy, const float* d_qr,
+                              const float* d_qmin_size, const float* d_qmax_size, const int* d_q_start, int P,
+                              const afv_keypoint* d_kps, const void* d_desc, const float* d_kpsize, const int* d_n,
+                              int B, int cap, const int* d_frame, const uint8_t* d_occupied,
+                              float min_x, float min_y, float max_x, float max_y,
+                              float th, float nnratio, int ratio_same_scale_only, float size_tolerance,
+                              int* d_match_q, int* d_nmatches, void* cuda_stream);
+
 /* Brute-force N x M best / second (upper bound of every matcher; also MapPoint::ComputeDistinctiveDescriptors'
  * distance matrix, src/MapPoint.cc:312-324). */
 int  afv_match_bruteforce(int desc_type, const void* d_q, int nq, const void* d_t, int nt,

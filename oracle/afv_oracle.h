@@ -124,6 +124,12 @@ long orc_orb32_extract_match_batch(const uint8_t* frames, int B, int w, int h, i
                                    float scale_factor, float detect_th, const int* pair_a, const int* pair_b, int P,
                                    int window, float th_low, float nnratio, int check_ori, int nthreads);
 
+/* SearchByProjection family on arrays (src/FeatureMatcher.cc:73-154 with ratio_same_scale=1, :287-397 with 0). */
+int orc_search_by_projection(int desc_type, const void* qdesc, const float* qxy, const float* qr, const float* qmin,
+        const float* qmax, int nq, const orc_keypoint* tk, const void* td, const float* tsize, int nt,
+        const uint8_t* occupied_in, float minX, float minY, float maxX, float maxY,
+        float th, float nnratio, int ratio_same_scale, float tol, int* match_q);
+
 /* DBoW2 tree descent per feature (Vocabulary::transform, src/Vocabulary.cpp:156-207). */
 void orc_bow_transform(int desc_type, const void* desc, int n, const int* child_off, const int* child_ids, const void* node_desc,
                        const int* node_word, const double* node_weight, int depth_L, int levelsup,

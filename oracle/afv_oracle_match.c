@@ -294,6 +294,52 @@ int orc_search_by_bow(int desc_type,
     return nMatches;
 }
 
+/* ---------------------------------------------------------------- SearchByProjection family --------------- */
+/* FeatureMatcher::SearchByProjection(F, vpMapPoints, th) (src/FeatureMatcher.cc:73-154) with ratio_same_scale = 1, and
+ * the best-only variant (:287-397) with ratio_same_scale = 0, on plain arrays: per query the projected position, the
+ * search radius and the accepted size range; a train keypoint that already holds a map point (occupied) is skipped and
+ * an accepted match occupies its keypoint for the later queries. Returns the number of matches. */
+int orc_search_by_projection(int desc_type, const void* qdesc, const float* qxy, const float* qr, const float* qmin,
+        const float* qmax, int nq, const orc_keypoint* tk, const void* td, const float* tsize, int nt,
+        const uint8_t* occupied_in, float minX, float minY, float maxX, float maxY,
+        float th, float nnratio, int ratio_same_scale, float tol, int* match_q) {
+    const int D = orc_descriptor_bytes(desc_type);
+    const float invW = (float)GRID_COLS / (maxX - minX), invH = (float)GRID_ROWS / (maxY - minY);
+    const float invtol = 1.0f / tol;
+    int* cs = (int*)malloc(sizeof(int) * (GRID_COLS * GRID_ROWS + 1));
+    int* ci = (int*)malloc(sizeof(int) * (nt + 1));
+    int* cand = (int*)malloc(sizeof(int) * (nt + 1));
+    uint8_t* occ = (uint8_t*)calloc((size_t)nt + 1, 1);
+    if (occupied_in) memcpy(occ, occupied_in, (size_t)nt);
+    orc_grid_build(tk, nt, minX, minY, invW, invH, cs, ci);
+    int nmatches = 0;
+    for (int i = 0; i < nq; ++i) {
+        match_q[i] = -1;
+        int nc = orc_features_in_area(tk, tsize, cs, ci, minX, minY, invW, invH, qxy[2 * i], qxy[2 * i + 1], qr[i], qmin[i], qmax[i], cand, nt);
+        if (nc == 0) continue;
+        const uint8_t* ref = (const uint8_t*)qdesc + (long)i * D;
+        float bestDist = FLT_MAX, bestDist2 = FLT_MAX, bestSize = -1.0f, bestSize2 = -1.0f;
+        int bestIdx = -1;
+        for (int c = 0; c < nc; ++c) {
+            const int idx = cand[c];
+            if (occ[idx]) continue;
+            const float d = orc_descriptor_distance(desc_type, ref, (const uint8_t*)td + (long)idx * D);
+            if (d < bestDist) { bestDist2 = bestDist; bestDist = d; bestIdx = idx; bestSize2 = bestSize; bestSize = tsize[idx]; }
+            else if (d < bestDist2) { bestDist2 = d; bestSize2 = tsize[idx]; }
+        }
+        if (bestDist <= th) {
+            if (ratio_same_scale) {
+                if ((bestSize / bestSize2 < tol) && (bestSize / bestSize2 > invtol) && (bestSize2 > 0.0f)) {
+                    if (bestDist > nnratio * bestDist2) continue;
+                }
+            }
+            match_q[i] = bestIdx; occ[bestIdx] = 1; nmatches++;
+        }
+    }
+    free(cs); free(ci); free(cand); free(occ);
+    return nmatches;
+}
+
 /* ---------------------------------------------------------------- DBoW2 tree descent ---------------------- */
 /* TemplatedVocabulary::transform(feature, word_id, weight, nid, levelsup)
  * (Thirdparty/DBoW2/include/DBoW2/TemplatedVocabulary.h:1346-1387) with the per-feature distances of

@@ -226,3 +226,19 @@ def feature_vector_segments(node_id):
     order = np.argsort(node_id, kind="stable")
     ids, starts = np.unique(node_id[order], return_index=True)
     return ids.astype(np.int32), np.append(starts, len(node_id)).astype(np.int32), order.astype(np.int32)
+
+
+def search_by_projection(desc_type, qdesc, qxy, qr, qmin, qmax, tk, td, tsize, bounds, occupied=None, th=75.0, nnratio=0.8,
+                         ratio_same_scale=True, tol=1.2):
+    qdesc = np.ascontiguousarray(qdesc); td = np.ascontiguousarray(td); tk = np.ascontiguousarray(tk)
+    qxy = np.ascontiguousarray(qxy, np.float32); qr = np.ascontiguousarray(qr, np.float32)
+    qmin = np.ascontiguousarray(qmin, np.float32); qmax = np.ascontiguousarray(qmax, np.float32)
+    tsize = np.ascontiguousarray(tsize, np.float32)
+    nq = len(qdesc)
+    out = np.zeros(max(nq, 1), np.int32)
+    occ = None if occupied is None else np.ascontiguousarray(occupied, np.uint8)
+    minX, minY, maxX, maxY = bounds
+    n = lib().orc_search_by_projection(desc_type, _p(qdesc), _p(qxy), _p(qr), _p(qmin), _p(qmax), nq, _p(tk), _p(td), _p(tsize), len(tk),
+                                       None if occ is None else _p(occ), _f(minX), _f(minY), _f(maxX), _f(maxY), _f(th), _f(nnratio),
+                                       int(bool(ratio_same_scale)), _f(tol), _p(out))
+    return n, out[:nq].copy()

@@ -272,3 +272,43 @@ def test_bow_transform_and_search_by_bow_chain(pkg, extracted, desc_type, D, fl)
         mf, nm = fm.search_by_bow(out[1][0, :len(k1)], out[0][0], [t(v) for v in segs[0]], out[1][1, :len(k2)], out[0][1], [t(v) for v in segs[1]])
         torch.cuda.synchronize()
         assert int(nm[0]) == rn and (mf.cpu().numpy() == rmf).all()
+
+
+@pytest.mark.parametrize("ratio_same_scale,nnratio", [(True, 0.8), (False, 0.9)])
+def test_search_by_projection_family(pkg, extracted, ratio_same_scale, nnratio):
+    """TrackLocalMap-style SearchByProjection (ratio only between same-scale best/second, :139-146) and the best-only
+    variant (:381-386), batched over problems, with pre-occupied train keypoints; sequential claiming reproduced."""
+    import torch
+    out, host, cap = extracted
+    rng = np.random.default_rng(90)
+    problems = [(0, 1), (2, 3), (5, 4)]                      # (query source frame, train frame)
+    qd, qxy, qr, qmin, qmax, qstart, occs = [], [], [], [], [], [0], np.zeros((len(host), cap), np.uint8)
+    refs = []
+    for (qa, tb) in problems:
+        kq, dq, sq = host[qa]; kt, dt, st = host[tb]
+        nq = len(kq)
+        xy = np.stack([kq["x"], kq["y"]], axis=1) + rng.uniform(-5, 5, (nq, 2)).astype(np.float32)
+        r = (rng.choice(np.array([3.0, 8.0, 20.0], np.float32), nq) * sq).astype(np.float32)
+        mn = (sq / np.float32(1.2)).astype(np.float32); mx = (sq * np.float32(1.2)).astype(np.float32)
+        # duplicate some queries so later ones must skip keypoints claimed by earlier ones
+        dup = rng.integers(0, nq, nq // 5)
+        dq2 = np.concatenate([dq, dq[dup]]); xy = np.concatenate([xy, xy[dup]]); r = np.concatenate([r, r[dup]])
+        mn = np.concatenate([mn, mn[dup]]); mx = np.concatenate([mx, mx[dup]])
+        occ = (rng.random(len(kt)) < 0.15).astype(np.uint8)
+        occs[tb, :len(kt)] = occ
+        qd.append(dq2); qxy.append(xy); qr.append(r); qmin.append(mn); qmax.append(mx); qstart.append(qstart[-1] + len(dq2))
+        refs.append(po.search_by_projection(0, dq2, xy, r, mn, mx, kt, dt, st, BOUNDS, occupied=occ, th=75.0, nnratio=nnratio,
+                                            ratio_same_scale=ratio_same_scale, tol=1.2))
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    fm = pkg.FeatureMatcher(nnratio=nnratio, desc_type=0, th_low=75.0)
+    mq, nm = fm.search_by_projection(t(np.concatenate(qd)), t(np.concatenate(qxy)), t(np.concatenate(qr)), t(np.concatenate(qmin)),
+                                     t(np.concatenate(qmax)), t(np.array(qstart, np.int32)), out[0], out[1], out[2], out[3],
+                                     t(np.array([p[1] for p in problems], np.int32)), BOUNDS, occupied=t(occs),
+                                     ratio_same_scale=ratio_same_scale, size_tolerance=1.2)
+    torch.cuda.synchronize()
+    mq = mq.cpu().numpy(); nm = nm.cpu().numpy()
+    for i, (rn, rm) in enumerate(refs):
+        assert nm[i] == rn and (mq[qstart[i]:qstart[i + 1]] == rm).all(), "problem %d" % i
+        assert rn > 100
+        got = rm[rm >= 0]
+        assert len(set(got.tolist())) == len(got)             # every train keypoint claimed at most once
