@@ -1130,3 +1130,48 @@ extern "C" int afv_bow_transform(int desc_type, const void* d_desc, int n, const
     AFV_CUDA_CHECK(cudaGetLastError());
     return AFV_OK;
 }
+
+// ---- MapPoint::ComputeDistinctiveDescriptors: one warp per map point ---------------------------------------------------
+#define DD_MAXN 256
+__global__ void __launch_bounds__(128) k_distinctive(int desc_type, int D, const uint8_t* __restrict__ desc, const int* __restrict__ obs,
+                                                     const int* __restrict__ seg_start, int M, int* __restrict__ best) {
+    __shared__ float rowbuf[4][DD_MAXN];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int m = blockIdx.x * 4 + wid;
+    if (m >= M) return;
+    const int s0 = seg_start[m], N = min(seg_start[m + 1] - s0, DD_MAXN);
+    float* row = rowbuf[wid];
+    float bestMedian = FLT_MAX; int bestIdx = N > 0 ? 0 : -1;
+    const int kth = (int)(0.5 * (double)(N - 1));                       // vDists[0.5*(N-1)]
+    for (int i = 0; i < N; ++i) {
+        const uint8_t* di = desc + (long long)obs[s0 + i] * D;
+        for (int j = lane; j < N; j += 32)
+            row[j] = j == i ? 0.0f : desc_distance(desc_type, j > i ? di : desc + (long long)obs[s0 + j] * D,
+                                                   j > i ? desc + (long long)obs[s0 + j] * D : di, D);   // Distances[i][j] = dist(min,max)
+        __syncwarp();
+        float median = FLT_MAX;
+        for (int j = lane; j < N; j += 32) {
+            const float v = row[j];
+            int rank = 0;
+            for (int l = 0; l < N; ++l) { const float w = row[l]; rank += (w < v) || (w == v && l < j); }
+            if (rank == kth) median = v;
+        }
+#pragma unroll
+        for (int o = 16; o; o >>= 1) median = fminf(median, __shfl_xor_sync(0xffffffffu, median, o));
+        if (median < bestMedian) { bestMedian = median; bestIdx = i; }
+        __syncwarp();
+    }
+    if (lane == 0) best[m] = bestIdx;
+}
+extern "C" int afv_distinctive_descriptors(int desc_type, const void* d_desc, const int* d_obs, const int* d_seg_start, int M,
+                                           int max_seg, int* d_best, void* cuda_stream) {
+    const int D = desc_bytes(desc_type);
+    if (D < 0 || M < 0 || (M > 0 && (!d_desc || !d_obs || !d_seg_start || !d_best)) || max_seg > DD_MAXN) {
+        afv_set_error("afv_distinctive_descriptors: bad argument (segments are limited to %d observations)", DD_MAXN); return AFV_ERR_INVALID;
+    }
+    if (M == 0) return AFV_OK;
+    k_distinctive<<<(M + 3) / 4, 128, 0, as_stream(cuda_stream)>>>(desc_type, D, (const uint8_t*)d_desc, d_obs, d_seg_start, M, d_best);
+    ++g_afv_launches;
+    AFV_CUDA_CHECK(cudaGetLastError());
+    return AFV_OK;
+}

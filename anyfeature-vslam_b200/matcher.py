@@ -115,6 +115,16 @@ class FeatureMatcher:
                                      int(self.check_ori), _vp(match_f), _vp(nm), _sp(stream)))
         return match_f[:nf], nm
 
+    # -- MapPoint::ComputeDistinctiveDescriptors (src/MapPoint.cc:279-348), batched over map points ----------------
+    @staticmethod
+    def distinctive_descriptors(desc_type, desc, obs, seg_start, max_seg, stream=None):
+        import torch
+        lib, _check, _vp, _sp = _afv()
+        M = seg_start.shape[0] - 1
+        best = torch.empty(max(M, 1), dtype=torch.int32, device=desc.device)
+        _check(lib.afv_distinctive_descriptors(int(desc_type), _vp(desc), _vp(obs), _vp(seg_start), M, int(max_seg), _vp(best), _sp(stream)))
+        return best[:M]
+
     # -- static DescriptorDistance (src/FeatureMatcher.cc:1508-1531) -------------------------------------
     @staticmethod
     def descriptor_distance(desc_type, a, b, stream=None):

@@ -172,6 +172,13 @@ int  afv_bow_transform(int desc_type, const void* d_desc, int n,
                        const int* d_node_word, const double* d_node_weight, int n_nodes, int depth_L, int levelsup,
                        int* d_word_id, double* d_weight, int* d_node_id, void* cuda_stream);
 
+/* MapPoint::ComputeDistinctiveDescriptors (src/MapPoint.cc:279-348), batched over M map points: map point m observes the
+ * descriptors d_desc[d_obs[s]] for s in [d_seg_start[m], d_seg_start[m+1]); all pairwise distances, per row the median
+ * sorted[0.5*(N-1)], and the first row with the smallest median wins.  d_best[m] = position inside the segment (-1 for an
+ * empty segment).  Segments longer than 256 observations are rejected (AFV_ERR_INVALID). */
+int  afv_distinctive_descriptors(int desc_type, const void* d_desc, const int* d_obs, const int* d_seg_start, int M,
+                                 int max_seg, int* d_best, void* cuda_stream);
+
 /* FeatureMatcher::DescriptorDistance (src/FeatureMatcher.cc:1508-1531) for n pairs (a[i], b[i]). */
 int  afv_descriptor_distance(int desc_type, const void* d_a, const void* d_b, int n, float* d_out,
                              void* cuda_stream);

@@ -130,6 +130,9 @@ int orc_search_by_projection(int desc_type, const void* qdesc, const float* qxy,
         const uint8_t* occupied_in, float minX, float minY, float maxX, float maxY,
         float th, float nnratio, int ratio_same_scale, float tol, int* match_q);
 
+/* MapPoint::ComputeDistinctiveDescriptors (src/MapPoint.cc:279-348) for one map point: index into obs[0..N). */
+int orc_distinctive_descriptor(int desc_type, const void* desc, const int* obs, int N);
+
 /* DBoW2 tree descent per feature (Vocabulary::transform, src/Vocabulary.cpp:156-207). */
 void orc_bow_transform(int desc_type, const void* desc, int n, const int* child_off, const int* child_ids, const void* node_desc,
                        const int* node_word, const double* node_weight, int depth_L, int levelsup,

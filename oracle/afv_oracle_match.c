@@ -340,6 +340,32 @@ int orc_search_by_projection(int desc_type, const void* qdesc, const float* qxy,
     return nmatches;
 }
 
+/* ---------------------------------------------------------------- ComputeDistinctiveDescriptors ----------- */
+/* MapPoint::ComputeDistinctiveDescriptors (src/MapPoint.cc:279-348): descriptor with the least median distance. */
+static int cmp_float_asc(const void* a, const void* b) { float x = *(const float*)a, y = *(const float*)b; return (x > y) - (x < y); }
+int orc_distinctive_descriptor(int desc_type, const void* desc, const int* obs, int N) {
+    if (N <= 0) return -1;
+    const int D = orc_descriptor_bytes(desc_type);
+    float* dist = (float*)malloc(sizeof(float) * (size_t)N * N);
+    for (int i = 0; i < N; ++i) {
+        dist[i * N + i] = 0.0f;
+        for (int j = i + 1; j < N; ++j) {
+            float d = orc_descriptor_distance(desc_type, (const uint8_t*)desc + (long)obs[i] * D, (const uint8_t*)desc + (long)obs[j] * D);
+            dist[i * N + j] = d; dist[j * N + i] = d;
+        }
+    }
+    float bestMedian = FLT_MAX; int bestIdx = 0;
+    float* v = (float*)malloc(sizeof(float) * N);
+    for (int i = 0; i < N; ++i) {
+        memcpy(v, dist + (size_t)i * N, sizeof(float) * N);
+        qsort(v, N, sizeof(float), cmp_float_asc);
+        float median = v[(int)(0.5 * (N - 1))];
+        if (median < bestMedian) { bestMedian = median; bestIdx = i; }
+    }
+    free(dist); free(v);
+    return bestIdx;
+}
+
 /* ---------------------------------------------------------------- DBoW2 tree descent ---------------------- */
 /* TemplatedVocabulary::transform(feature, word_id, weight, nid, levelsup)
  * (Thirdparty/DBoW2/include/DBoW2/TemplatedVocabulary.h:1346-1387) with the per-feature distances of

@@ -242,3 +242,8 @@ def search_by_projection(desc_type, qdesc, qxy, qr, qmin, qmax, tk, td, tsize, b
                                        None if occ is None else _p(occ), _f(minX), _f(minY), _f(maxX), _f(maxY), _f(th), _f(nnratio),
                                        int(bool(ratio_same_scale)), _f(tol), _p(out))
     return n, out[:nq].copy()
+
+
+def distinctive_descriptor(desc_type, desc, obs):
+    desc = np.ascontiguousarray(desc); obs = np.ascontiguousarray(obs, np.int32)
+    return int(lib().orc_distinctive_descriptor(desc_type, _p(desc), _p(obs), len(obs)))

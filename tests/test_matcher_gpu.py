@@ -312,3 +312,22 @@ def test_search_by_projection_family(pkg, extracted, ratio_same_scale, nnratio):
         assert rn > 100
         got = rm[rm >= 0]
         assert len(set(got.tolist())) == len(got)             # every train keypoint claimed at most once
+
+
+@pytest.mark.parametrize("desc_type,D", [(0, 32), (2, 48), (5, 512)])
+def test_distinctive_descriptors(pkg, desc_type, D):
+    import torch
+    rng = np.random.default_rng(70 + desc_type)
+    if desc_type == 5:
+        desc = rng.normal(size=(600, 128)).astype(np.float32)
+    else:
+        base = rng.integers(0, 256, (40, D), dtype=np.uint8)
+        desc = base[rng.integers(0, 40, 600)] ^ (rng.integers(0, 256, (600, D), dtype=np.uint8) & rng.integers(0, 256, (600, D), dtype=np.uint8) & rng.integers(0, 256, (600, D), dtype=np.uint8))
+    lens = [0, 1, 2, 3, 7, 31, 32, 33, 64, 100] + rng.integers(2, 40, 30).tolist()
+    seg = np.concatenate([[0], np.cumsum(lens)]).astype(np.int32)
+    obs = rng.integers(0, 600, seg[-1]).astype(np.int32)
+    ref = np.array([po.distinctive_descriptor(desc_type, desc, obs[seg[m]:seg[m + 1]]) for m in range(len(lens))], np.int32)
+    d = torch.from_numpy(np.ascontiguousarray(desc).view(np.uint8).reshape(600, -1)).cuda()
+    got = pkg.FeatureMatcher.distinctive_descriptors(desc_type, d, torch.from_numpy(obs).cuda(), torch.from_numpy(seg).cuda(), max(lens))
+    torch.cuda.synchronize()
+    assert (got.cpu().numpy() == ref).all()
