@@ -17,7 +17,6 @@ import json
 import os
 import subprocess
 import sys
-import threading
 import time
 
 import numpy as np
@@ -60,29 +59,43 @@ def make_frames(pkg, batch, rank, unique_streams=8, frames_per_stream=16):
     return np.ascontiguousarray(frames), idx.astype(np.int32), nxt.astype(np.int32)
 
 
-class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 50 ms (its own -lms loop) during the timed regions."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index):
-        super().__init__(daemon=True)
         self.gpu = gpu_index
+        self.proc = None
         self.samples = []
         self.stop_flag = False
 
-    def run(self):
-        while not self.stop_flag:
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-lms", "50"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return
+        try:
+            self.proc.terminate()
+            out, _ = self.proc.communicate(timeout=5)
+            for line in out.strip().splitlines():
+                v = [x.strip() for x in line.split(",")]
+                if len(v) >= 6:
+                    self.samples.append(v)
+        except Exception:
             try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits"],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.samples.append([v.strip() for v in out.split(",")])
+                self.proc.kill()
             except Exception:
                 pass
-            time.sleep(0.2)
+        self.proc = None
 
     def summary(self):
+        self.stop()
         if not self.samples:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
         sm = sorted(int(s[0]) for s in self.samples if s[0].isdigit())
@@ -306,7 +319,7 @@ def run_gpu(args):
     barrier()
     ms_e2e = max(f0.elapsed_time(f1), (time.perf_counter() - t_wall0) * 1e3)    # device events vs host wall clock: take the slower
     if sampler:
-        sampler.stop_flag = True
+        sampler.stop()
     h2d = int(h_gray.numel()); d2h = int(sum(t.numel() * t.element_size() for t in h_out))
     for e in exs:
         e.close()
@@ -422,7 +435,7 @@ def run_gpu(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--batch", type=int, default=512, help="frames per step per GPU")
     ap.add_argument("--e2e-chunk", type=int, default=512, help="frames per pipelined chunk in the e2e leg")
