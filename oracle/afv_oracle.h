@@ -142,6 +142,21 @@ void orc_bow_transform(int desc_type, const void* desc, int n, const int* child_
 int  orc_rot_bin(float angle1, float angle2);
 void orc_three_maxima(const int* hist_counts, int len, int* ind1, int* ind2, int* ind3);
 
+
+/* ---- sift128 (afv_oracle_sift.c; PARITY UNPINNED: SiftGPU is not vendored by the reference) ------------------- */
+float orc_sift_exp(float x);
+float orc_sift_exp2(float x);
+float orc_sift_atan2(float y, float x);
+void  orc_sift_sincos(float a, float* s, float* c);
+int   orc_sift_gauss_kernel(double sigma, float* taps, int max_r);
+void  orc_sift_sigmas(double* dsig);
+int   orc_sift_num_octaves(int w, int h);
+long  orc_sift_scale_space(const uint8_t* gray, int w, int h, int stride, int what, int oct, int idx, float* out, int* ow, int* oh);
+int   orc_sift_detect(const uint8_t* gray, int w, int h, int stride, int nfeatures, float* xyso, float* desc, int cap);
+int   orc_sift_ref_octave(float s);
+int   orc_sift128_extract(const uint8_t* gray, int w, int h, int stride, int nfeatures, int nlevels, float scale_factor,
+                          orc_keypoint* kps, float* desc, float* kpsize, int cap, int* n_out, int* n_detected);
+
 #ifdef __cplusplus
 }
 #endif

@@ -20,7 +20,7 @@ DESC_ORB, DESC_AKAZE61, DESC_BRISK, DESC_SIFT128 = 0, 1, 2, 5      # include/Typ
 
 def build(force=False):
     so = os.path.join(_DIR, "libafv_oracle.so")
-    srcs = [os.path.join(_DIR, f) for f in ("afv_oracle.c", "afv_oracle_match.c", "afv_oracle.h", "orb_pattern.inc")]
+    srcs = [os.path.join(_DIR, f) for f in ("afv_oracle.c", "afv_oracle_match.c", "afv_oracle_sift.c", "afv_oracle.h", "orb_pattern.inc")]
     if force or not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
         subprocess.check_call(["make", "-s", "-C", _DIR, "libafv_oracle.so"])
     return so
@@ -247,3 +247,39 @@ def search_by_projection(desc_type, qdesc, qxy, qr, qmin, qmax, tk, td, tsize, b
 def distinctive_descriptor(desc_type, desc, obs):
     desc = np.ascontiguousarray(desc); obs = np.ascontiguousarray(obs, np.int32)
     return int(lib().orc_distinctive_descriptor(desc_type, _p(desc), _p(obs), len(obs)))
+
+
+# ---- sift128 (oracle/afv_oracle_sift.c; PARITY UNPINNED, see its header) --------------------------------------------
+def sift_scale_space(gray, what, octave, idx):
+    gray = np.ascontiguousarray(gray, np.uint8)
+    h, w = gray.shape
+    ow = C.c_int(0); oh = C.c_int(0)
+    L = lib(); L.orc_sift_scale_space.restype = C.c_long
+    n = L.orc_sift_scale_space(_p(gray), w, h, w, int(what), int(octave), int(idx), None, C.byref(ow), C.byref(oh))
+    assert n > 0
+    out = np.zeros((oh.value, ow.value), np.float32)
+    L.orc_sift_scale_space(_p(gray), w, h, w, int(what), int(octave), int(idx), _p(out), C.byref(ow), C.byref(oh))
+    return out
+
+
+def sift_detect(gray, nfeatures, with_desc=True, cap=200000):
+    """SiftGPU-equivalent list after the -tc2 limit: (n,4) x,y,s,o and (n,128) descriptors."""
+    gray = np.ascontiguousarray(gray, np.uint8)
+    h, w = gray.shape
+    xyso = np.zeros((cap, 4), np.float32)
+    desc = np.zeros((cap, 128), np.float32) if with_desc else None
+    n = lib().orc_sift_detect(_p(gray), w, h, w, int(nfeatures), _p(xyso), _p(desc) if with_desc else None, cap)
+    assert n >= 0, n
+    return xyso[:n].copy(), (desc[:n].copy() if with_desc else None)
+
+
+def sift128_extract(gray, nfeatures, nlevels=8, scale_factor=2.0):
+    gray = np.ascontiguousarray(gray, np.uint8)
+    h, w = gray.shape
+    cap = nfeatures + 3 * nlevels + 64
+    kps = np.zeros(cap, KP_DTYPE); desc = np.zeros((cap, 128), np.float32); size = np.zeros(cap, np.float32)
+    n = C.c_int(0); nd = C.c_int(0)
+    rc = lib().orc_sift128_extract(_p(gray), w, h, w, int(nfeatures), int(nlevels), _f(scale_factor), _p(kps), _p(desc),
+                                   _p(size), cap, C.byref(n), C.byref(nd))
+    assert rc == 0, rc
+    return kps[:n.value].copy(), desc[:n.value].copy(), size[:n.value].copy(), nd.value
