@@ -15,6 +15,7 @@ OUT = os.path.join(HERE, "libafv_b200.so")
 SOURCES = [
     ("afv_orb.cu", ["--fmad=false"]),
     ("afv_match.cu", ["--fmad=false"]),
+    ("afv_sift.cu", ["--fmad=false"]),
     ("afv_capi.cu", ["--fmad=false"]),
 ]
 COMMON = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",

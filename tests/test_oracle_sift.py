@@ -1,0 +1,108 @@
+"""CPU tests of the sift128 ORACLE (oracle/afv_oracle_sift.c).  PARITY UNPINNED: SiftGPU is not vendored by the
+reference; the checks here are (a) the deterministic elementary functions, (b) structural invariants of the published
+algorithm, (c) a family check against cv2.SIFT keypoints stored by tools/make_golden_sift.py, (d) the reference-side
+post-processing (octave rule, octree quota, merge order, computeSize)."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+from oracle import pyoracle as po
+
+
+@pytest.fixture(scope="module")
+def frame(synth):
+    frames, _ = synth.stream_frames(640, 480, 0, 1)
+    return frames[0]
+
+
+def test_elementary_functions():
+    L = po.lib()
+    for f in (L.orc_sift_exp, L.orc_sift_exp2):
+        f.restype = C.c_float; f.argtypes = [C.c_float]
+    L.orc_sift_atan2.restype = C.c_float; L.orc_sift_atan2.argtypes = [C.c_float, C.c_float]
+    xs = np.linspace(-20, 0, 4001)
+    e = np.array([L.orc_sift_exp(float(x)) for x in xs])
+    assert np.max(np.abs(e - np.exp(xs)) / np.exp(xs)) < 5e-6
+    th = np.linspace(0, 2 * np.pi, 4001)[:-1]
+    a = np.array([L.orc_sift_atan2(float(np.sin(t)), float(np.cos(t))) for t in th])
+    assert np.max(np.abs(a - th)) < 2e-6
+    s = C.c_float(); c = C.c_float()
+    for t in th[::7]:
+        L.orc_sift_sincos(C.c_float(t), C.byref(s), C.byref(c))
+        assert abs(s.value - np.sin(t)) < 2e-6 and abs(c.value - np.cos(t)) < 2e-6
+
+
+def test_scale_space_structure(frame):
+    g0 = po.sift_scale_space(frame, 0, 0, 0)
+    g3 = po.sift_scale_space(frame, 0, 0, 3)
+    g1_0 = po.sift_scale_space(frame, 0, 1, 0)
+    assert g0.shape == (480, 640) and g1_0.shape == (240, 320)
+    assert (g1_0 == g3[::2, ::2]).all()                       # next octave = every 2nd pixel of level 2
+    d2 = po.sift_scale_space(frame, 1, 0, 2)
+    g2 = po.sift_scale_space(frame, 0, 0, 2)
+    assert (d2 == g3 - g2).all()
+    # level -1 has sigma 1.6: compare with a double-precision Gaussian of sqrt(1.6^2 - 0.5^2)
+    import scipy.ndimage as ndi
+    ref = ndi.gaussian_filter(frame.astype(np.float64) / 255.0, np.sqrt(1.6 ** 2 - 0.25), mode="nearest", truncate=4.5)
+    assert np.abs(ref - g0).max() < 2e-3
+
+
+def test_detect_invariants(frame):
+    xyso, desc = po.sift_detect(frame, 1000)
+    assert len(xyso) > 1000                                    # soft limit: the level that crosses it is kept whole
+    assert np.allclose(np.linalg.norm(desc, axis=1), 1.0, atol=1e-5)      # unit L2 (matchingTh 0.5 assumes it)
+    assert desc.min() >= 0 and desc.max() < 0.6
+    assert (xyso[:, 3] >= 0).all() and (xyso[:, 3] < 2 * np.pi).all()
+    assert (xyso[:, 2] > 1.5).all()
+    full, _ = po.sift_detect(frame, 10 ** 7, with_desc=False)
+    # -tc2 keeps a suffix of the list (coarsest levels), list order preserved
+    assert (full[len(full) - len(xyso):] == xyso).all()
+    # deterministic
+    again, d2 = po.sift_detect(frame, 1000)
+    assert (again == xyso).all() and (d2 == desc).all()
+
+
+def test_family_check_against_cv2(frame, golden_dir):
+    g = np.load(os.path.join(golden_dir, "sift_cv2_synth_640x480_s0_t0.npz"))
+    full, _ = po.sift_detect(frame, 10 ** 7, with_desc=False)
+    from scipy.spatial import cKDTree
+    tree = cKDTree(full[:, :2])
+    for o in (0, 1, 2):
+        m = g["octave"] == o
+        d, i = tree.query(g["xys"][m, :2])
+        hit = d < 1.0
+        assert hit.mean() > 0.8, (o, hit.mean())             # cv2's octave >= 0 extrema are found
+        ratio = g["xys"][m, 2][hit] / 2.0 / full[i[hit], 2]
+        assert abs(np.median(ratio) - 1.0) < 0.02             # and at the same scale (cv2 size = 2 sigma)
+
+
+def test_rotation_180(frame):
+    """The detector is symmetric under a 180 degree rotation (clamped borders, symmetric taps)."""
+    a, _ = po.sift_detect(frame, 10 ** 7, with_desc=False)
+    b, _ = po.sift_detect(np.ascontiguousarray(frame[::-1, ::-1]), 10 ** 7, with_desc=False)
+    h, w = frame.shape
+    pa = {(round(float(x), 2), round(float(y), 2)) for x, y in a[a[:, 2] < 3.2, :2]}
+    pb = {(round(float(w - 1 - x), 2), round(float(h - 1 - y), 2)) for x, y in b[b[:, 2] < 3.2, :2]}
+    assert len(pa & pb) > 0.98 * len(pa)
+
+
+def test_extract_postprocessing(frame):
+    kps, desc, size, nd = po.sift128_extract(frame, 1000)
+    xyso, dfull = po.sift_detect(frame, 1000)
+    assert nd == len(xyso)
+    q = po.features_per_level(1000, 8, 2.0)
+    assert list(q) == [502, 251, 125, 63, 31, 16, 8, 4]
+    oc = kps["octave"]
+    assert (np.diff(oc) >= 0).all()                            # mergeKeypointLevels: ascending level
+    for l in range(8):
+        assert (oc == l).sum() <= q[l] + 3
+    cid = kps["class_id"]
+    assert len(set(cid.tolist())) == len(cid)
+    assert (kps["x"] == xyso[cid, 0]).all() and (kps["size"] == xyso[cid, 2]).all() and (kps["angle"] == xyso[cid, 3]).all()
+    assert (desc == dfull[cid]).all()                          # computeDescriptors: row gather by class_id
+    assert (kps["response"] == 1.0).all()
+    expect_oct = np.floor(np.maximum(np.log2(kps["size"].astype(np.float64) / 1.6454), 0)).astype(int)
+    assert (oc == expect_oct).all()                            # src/Feature_sift128.cpp:92
+    assert np.allclose(size, 2.0 ** oc, rtol=1e-6)

@@ -1,0 +1,123 @@
+"""Parity of the CUDA sift128 extraction path (through the C ABI) against the CPU oracle
+(oracle/afv_oracle_sift.c; parity vs SiftGPU itself is UNPINNED, see that file's header).
+By construction the two share one arithmetic contract, so everything is compared bit for bit; the
+north-star tolerance (descriptors within 1e-5 L2) is asserted as well."""
+import numpy as np
+import pytest
+
+from oracle import pyoracle as po
+
+pytestmark = pytest.mark.gpu
+
+
+def _taps(ex, frames):
+    bad = []
+    for f, img in enumerate(frames):
+        no = po.lib().orc_sift_num_octaves(img.shape[1], img.shape[0])
+        for o in range(no):
+            for what, n in ((10, 6), (11, 5)):
+                for i in range(n):
+                    ref = po.sift_scale_space(img, what - 10, o, i)
+                    got = ex.debug_read(what, f, o * 8 + i, nbytes_cap=ref.size * 4 + 16).view(np.float32).reshape(ref.shape)
+                    if not (got.view(np.uint32) == ref.view(np.uint32)).all():
+                        bad.append("frame %d octave %d %s %d: %d px differ (max %.3g)" % (
+                            f, o, "G" if what == 10 else "DoG", i, int((got != ref).sum()), float(np.abs(got - ref).max())))
+    return bad
+
+
+def _check(pkg, frames, nfeatures, w, h, taps=True):
+    ex = pkg.FeatureExtractor("sift128", nfeatures=nfeatures, max_batch=len(frames), max_w=w, max_h=h)
+    kps, desc, size, n = ex.extract_batch(frames)
+    desc = desc.view(np.float32).reshape(len(frames), ex.cap, 128)
+    problems = []
+    for f, img in enumerate(frames):
+        rk, rd, rs, nd = po.sift128_extract(img, nfeatures)
+        xyso, _ = po.sift_detect(img, nfeatures, with_desc=False)
+        lst = ex.debug_read(12, f, 0, nbytes_cap=16 * (len(xyso) + 4096)).view(np.float32).reshape(-1, 4)
+        if lst.shape != xyso.shape or not (lst.view(np.uint32) == xyso.view(np.uint32)).all():
+            same = lst.shape == xyso.shape
+            problems.append("frame %d: detected list differs (ref %d, gpu %d%s)" % (
+                f, len(xyso), len(lst), ", %d rows differ" % int((lst != xyso).any(axis=1).sum()) if same else ""))
+        m = int(n[f])
+        if m != len(rk):
+            problems.append("frame %d: %d keypoints, oracle %d" % (f, m, len(rk)))
+            continue
+        for fld in rk.dtype.names:
+            if not (kps[f, :m][fld] == rk[fld]).all():
+                problems.append("frame %d: keypoint field %s differs in %d rows" % (f, fld, int((kps[f, :m][fld] != rk[fld]).sum())))
+        l2 = np.linalg.norm(desc[f, :m] - rd, axis=1)
+        if l2.max() > 1e-5:
+            problems.append("frame %d: descriptor L2 error %.3g > 1e-5" % (f, float(l2.max())))
+        if not (desc[f, :m].view(np.uint32) == rd.view(np.uint32)).all():
+            problems.append("frame %d: %d descriptor rows not bit-identical" % (f, int((desc[f, :m] != rd).any(axis=1).sum())))
+        if not (size[f, :m] == rs).all():
+            problems.append("frame %d: computeSize differs" % f)
+    if problems and taps:
+        problems += _taps(ex, frames)
+    ex.close()
+    assert not problems, "\n".join(problems[:40])
+
+
+def test_sift_640x480(pkg, synth):
+    frames, _ = synth.stream_frames(640, 480, 0, 2)
+    _check(pkg, frames, 1000, 640, 480)
+
+
+def test_sift_scale_space_taps(pkg, synth):
+    frames, _ = synth.stream_frames(640, 480, 3, 1)
+    ex = pkg.FeatureExtractor("sift128", nfeatures=1000, max_batch=1, max_w=640, max_h=480)
+    ex.extract_batch(frames)
+    bad = _taps(ex, frames)
+    ex.close()
+    assert not bad, "\n".join(bad[:20])
+
+
+def test_sift_1280x720_c3(pkg, synth):
+    """BASELINE configs[2]: sift128 1280x720, 2000 kp/frame."""
+    frames, _ = synth.stream_frames(1280, 720, 1, 2)
+    _check(pkg, frames, 2000, 1280, 720, taps=False)
+
+
+def test_sift_odd_size_and_smaller_than_max(pkg, synth):
+    frames, _ = synth.stream_frames(640, 480, 5, 1)
+    img = np.ascontiguousarray(frames[:, 7:7 + 333, 11:11 + 517])
+    _check(pkg, img, 500, 640, 480)
+
+
+def test_sift_blank_and_device_api(pkg, synth):
+    import torch
+    frames, _ = synth.stream_frames(640, 480, 2, 2)
+    frames[1][:] = 37                                          # featureless frame -> 0 keypoints
+    ex = pkg.FeatureExtractor("sift128", nfeatures=1000, max_batch=2, max_w=640, max_h=480)
+    d = torch.from_numpy(frames).cuda()
+    out = ex.alloc_device_outputs(2)
+    ex.extract_batch_device(d, out)
+    torch.cuda.synchronize()
+    ex.status()
+    n = out[3].cpu().numpy()
+    assert n[1] == 0
+    rk, rd, rs, _ = po.sift128_extract(frames[0], 1000)
+    assert n[0] == len(rk)
+    k = pkg.kps_from_device(out[0][0], int(n[0]))
+    assert all((k[f] == rk[f]).all() for f in rk.dtype.names)
+    dd = out[1][0, :int(n[0])].cpu().numpy().view(np.float32).reshape(-1, 128)
+    assert (dd == rd).all()
+    ex.close()
+
+
+def test_sift_l2_matcher_on_extracted(pkg, synth):
+    """C3: L2 matcher (DescriptorDistance_sift128, src/Feature_sift128.cpp:132-134) on real sift128 output:
+    brute force best / second between consecutive frames == oracle within 1e-5."""
+    import torch
+    frames, _ = synth.stream_frames(640, 480, 4, 2)
+    ex = pkg.FeatureExtractor("sift128", nfeatures=1000, max_batch=2, max_w=640, max_h=480)
+    kps, desc, size, n = ex.extract_batch(frames)
+    ex.close()
+    d0 = desc[0, :n[0]].view(np.float32).reshape(-1, 128); d1 = desc[1, :n[1]].view(np.float32).reshape(-1, 128)
+    fm = pkg.FeatureMatcher(nnratio=0.9, check_ori=False, desc_type=5, th_low=0.5)
+    best, bd, sd = fm.match_bruteforce(torch.from_numpy(d0.copy()).cuda(), torch.from_numpy(d1.copy()).cuda())
+    torch.cuda.synchronize()
+    rb, rbd, rsd = po.match_bruteforce(5, d0, d1)
+    assert (best.cpu().numpy() == rb).all()
+    assert np.allclose(bd.cpu().numpy(), rbd, rtol=1e-5, atol=1e-7) and np.allclose(sd.cpu().numpy(), rsd, rtol=1e-5, atol=1e-7)
+    assert (bd.cpu().numpy() < 0.5).mean() > 0.3               # consecutive synthetic frames do match
