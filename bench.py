@@ -25,12 +25,49 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-METRIC = "frames/sec (extract+match) orb32 640x480x1000kp"
 UNIT = "frames/s"
-W, H, NFEAT = 640, 480, 1000
-BOUNDS = (0.0, 0.0, float(W), float(H))
 MAX_KPT_SIZE = float(np.float32(1.2) ** np.float32(7))       # FeatureExtractor::GetMaxKeyPtSize
-P_PIX = 950532                                                  # sum of pyramid pixels at 640x480
+
+# BASELINE.json configs.  The default (what the driver runs, and what `metric` is quoted on) is c2 = configs[1];
+# c3 / c5 are the other single-GPU-sized configurations, selectable for the tables in README / DESIGN.
+WORKLOADS = {
+    "c2": dict(feature="orb32", w=640, h=480, nfeat=1000, batch=512, desc_bytes=32, desc_type=0, th_low=75.0,
+               metric="frames/sec (extract+match) orb32 640x480x1000kp",
+               name="orb32 640x480 synthetic batch, 1000 kp/frame, extract+SearchForInitialization on 1xB200 per rank (configs[1])"),
+    "c3": dict(feature="sift128", w=1280, h=720, nfeat=2000, batch=64, desc_bytes=512, desc_type=5, th_low=0.5,
+               metric="frames/sec (extract+match) sift128 1280x720x2000kp",
+               name="sift128 1280x720 synthetic batch, 2000 kp/frame, extract+SearchForInitialization (L2) on 1xB200 per rank (configs[2])"),
+    "c5": dict(feature="orb32", w=1280, h=720, nfeat=2000, batch=128, desc_bytes=32, desc_type=0, th_low=75.0,
+               metric="frames/sec (extract+match) orb32 1280x720x2000kp",
+               name="orb32 1280x720 synthetic 8-stream batch, 2000 kp/frame, streams sharded over ranks, NCCL gather (configs[4])"),
+}
+WL = dict(WORKLOADS["c2"])
+W, H, NFEAT = WL["w"], WL["h"], WL["nfeat"]
+METRIC = WL["metric"]
+BOUNDS = (0.0, 0.0, float(W), float(H))
+
+
+def select_workload(name, batch):
+    global WL, W, H, NFEAT, METRIC, BOUNDS
+    WL = dict(WORKLOADS[name])
+    W, H, NFEAT, METRIC = WL["w"], WL["h"], WL["nfeat"], WL["metric"]
+    BOUNDS = (0.0, 0.0, float(W), float(H))
+    return batch if batch else WL["batch"]
+
+
+def pyramid_pixels(w, h):
+    """Sum of cv::ORB pyramid pixels (8 levels, scale 1.2, cvRound geometry; 950 532 at 640x480, SURVEY 8a)."""
+    tot = 0
+    for l in range(8):
+        sc = float(np.float32(1.2) ** l) if l else 1.0
+        tot += int(np.rint(w / sc)) * int(np.rint(h / sc))
+    return tot
+
+
+def sift_pixels(w, h):
+    """Sum of octave pixels of the sift128 scale space (octave o = w>>o x h>>o)."""
+    m = min(w, h); lg = int(np.floor(np.log2(m))); no = max(1, min(8, lg - 3))
+    return sum((w >> o) * (h >> o) for o in range(no))
 
 
 def load_pkg():
@@ -132,6 +169,8 @@ def cpu_arm(frames, pair_b, nthreads, seconds_budget):
         fr = frames[sample[0]:sample[-1] + 1]
         m = len(fr)
         pa = np.arange(m, dtype=np.int32); pb = ((pa + 1) % m).astype(np.int32)
+        if WL["feature"] == "sift128":
+            return po.sift_extract_match_batch(fr, pa, pb, NFEAT, threads)
         return po.extract_match_batch(fr, pa, pb, NFEAT, threads)
 
     step([0, 1], 1)                                              # warm (library load, first-touch)
@@ -152,7 +191,7 @@ def run_reference(args):
     class _P:
         pass
     P = _P(); P.synth = synth
-    frames, pa, pb = make_frames(P, min(args.batch, 256), 0)
+    frames, pa, pb = make_frames(P, min(args.batch, 256 if WL["feature"] == "orb32" and W <= 640 else 32), 0)
     nthreads = host_threads()
     step, sample, per_frame = cpu_arm(frames, pb, nthreads, seconds_budget=4.0)
     for _ in range(max(1, min(args.warmup, 1))):
@@ -166,10 +205,9 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": {"workload": "orb32 640x480 synthetic batch, 1000 kp/frame, extract+SearchForInitialization (configs[1])",
-                   "frames_per_step": len(sample)},
+        "config": {"workload": WL["name"], "frames_per_step": len(sample)},
         "cpu_baseline": {"value": fps, "unit": UNIT, "cores": nthreads, "kind": "port",
-                         "sample": "%d frames/step x %d steps, oracle C port of the reference path (cv::ORB restated + octree + matcher), %d threads; 1 thread: %.1f fps"
+                         "sample": "%d frames/step x %d steps, oracle C port of the reference path (extractor restated + octree + matcher), %d threads; 1 thread: %.1f fps"
                                    % (len(sample), args.steps, nthreads, 1.0 / per_frame)},
         "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -197,9 +235,10 @@ def run_gpu(args):
     lib = pkg.lib()
     B = args.batch
     frames, pa, pb = make_frames(pkg, B, rank)
-    ex = pkg.FeatureExtractor("orb32", nfeatures=NFEAT, device=local, max_batch=B, max_w=W, max_h=H)
+    FEAT = WL["feature"]
+    ex = pkg.FeatureExtractor(FEAT, nfeatures=NFEAT, device=local, max_batch=B, max_w=W, max_h=H)
     cap = ex.cap
-    fm = pkg.FeatureMatcher(nnratio=0.9, check_ori=True, desc_type=0, th_low=75.0)
+    fm = pkg.FeatureMatcher(nnratio=0.9, check_ori=True, desc_type=WL["desc_type"], th_low=WL["th_low"])
     d_gray = torch.from_numpy(frames).to(dev)
     h_gray = torch.from_numpy(frames).pin_memory()
     d_pa = torch.from_numpy(pa).to(dev); d_pb = torch.from_numpy(pb).to(dev)
@@ -210,7 +249,7 @@ def run_gpu(args):
     gathered = None
     if world > 1 and args.gather:
         # C5: fixed-capacity packed results gathered to rank 0 over NCCL/NVLink (n, nmatches, matches, kps, desc)
-        _, pack_bytes = pkg.sharding.pack_layout(B, cap, 32)
+        _, pack_bytes = pkg.sharding.pack_layout(B, cap, WL["desc_bytes"])
         # two pack / receive buffer sets: the gather of step i runs on NCCL's stream while step i+1 computes
         d_pack = [torch.empty(pack_bytes, dtype=torch.uint8, device=dev) for _ in range(2)]
         gathered = [[torch.empty(pack_bytes, dtype=torch.uint8, device=dev) for _ in range(world)] if rank == 0 else None for _ in range(2)]
@@ -247,7 +286,8 @@ def run_gpu(args):
     torch.cuda.synchronize()
     ex.status()
     n_host = out[3].cpu().numpy(); nm_host = nm.cpu().numpy()
-    assert n_host.min() >= NFEAT and n_host.max() <= cap, "unexpected keypoint counts %d..%d" % (n_host.min(), n_host.max())
+    assert (n_host.min() >= NFEAT or FEAT != "orb32") and n_host.min() > 0 and n_host.max() <= cap, \
+        "unexpected keypoint counts %d..%d" % (n_host.min(), n_host.max())
 
     # ---- timed region 1: inputs resident in HBM (value)
     sampler = ClockSampler(local) if rank == 0 else None
@@ -272,7 +312,7 @@ def run_gpu(args):
     nchunks = (B + CH - 1) // CH
     assert B % CH == 0 and CH % 16 == 0, "batch must be a multiple of the e2e chunk (multiple of 16)"
     streams = [torch.cuda.Stream(device=dev) for _ in range(2)]
-    exs = [pkg.FeatureExtractor("orb32", nfeatures=NFEAT, device=local, max_batch=CH, max_w=W, max_h=H) for _ in range(2)]
+    exs = [pkg.FeatureExtractor(FEAT, nfeatures=NFEAT, device=local, max_batch=CH, max_w=W, max_h=H) for _ in range(2)]
     c_in = [torch.empty((CH, H, W), dtype=torch.uint8, device=dev) for _ in range(2)]
     c_out = [e.alloc_device_outputs(CH) for e in exs]
     c_m12 = [torch.empty((CH, cap), dtype=torch.int32, device=dev) for _ in range(2)]
@@ -347,10 +387,20 @@ def run_gpu(args):
         kern = {names.raw[32 * i:32 * i + 32].split(b"\0")[0].decode(): (kms[i] / 3.0, kcalls[i] // 3) for i in range(nk)}
         # algorithmic bytes per step of each kernel (DESIGN.md "kernels"): P = pyramid pixels, C = FAST candidates,
         # M = detect list, N = kept keypoints, all per frame
-        Ccand = float(np.mean([ex.debug_read(2, 0, l).size // 4 for l in range(8)])) * 8
         N = float(n_host.mean())
-        alg = {
-            "k_resize": B * (P_PIX - 179 * 134 + P_PIX - W * H),          # read levels 0..6, write levels 1..7
+        P_PIX = pyramid_pixels(W, H)
+        Ccand = 0.0
+        if FEAT == "orb32":
+            Ccand = float(np.mean([ex.debug_read(2, 0, l).size // 4 for l in range(8)])) * 8
+        S_PIX = sift_pixels(W, H)
+        alg_sift = {
+            # base step: u8 in, f32 out; 5 incremental steps per octave: read G, write G and DoG; decimation: read + write
+            "k_sift_blur": B * (5.0 * W * H + 12.0 * 5 * S_PIX + 8.0 * (S_PIX - W * H)),
+            "k_sift_detect": B * (3 * 4.0 * 4 * S_PIX),           # 3 DoG levels, each reads itself, both neighbours and G
+            "k_sift_describe": B * N * (4.0 * 45 * 45 + 512 + 28),
+        }
+        alg = alg_sift if FEAT == "sift128" else {
+            "k_resize": B * (2 * P_PIX - W * H - int(np.rint(W / 1.2 ** 7)) * int(np.rint(H / 1.2 ** 7))),   # read levels 0..6, write levels 1..7
             "k_fast": B * (P_PIX + 4 * Ccand),
             "k_harris_select": B * (4 * Ccand * 3 + 81 * Ccand * 0.5 + 8 * 8539),
             "k_octree": B * (8 * 8539 + 8 * N),
@@ -370,14 +420,14 @@ def run_gpu(args):
         traffic = None
         try:      # dram__bytes_read+write of the dominant kernel from the committed ncu --set full capture, per launch
             tj = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
-            if dom in tj["dram_bytes_per_frame"]:
+            if dom in tj["dram_bytes_per_frame"] and args.workload == "c2":
                 traffic = tj["dram_bytes_per_frame"][dom] * B
         except Exception:
             pass
         roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                     "traffic": traffic, "algorithmic_bytes": alg.get(dom), "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback",
                     "kernel_ms_per_step": {k: round(v[0], 4) for k, v in kern.items()},
-                    "step_algorithmic_gbs": B * (4 * P_PIX + 12 * Ccand + 60 * N) / (ms / args.steps * 1e-3) / 1e9}
+                    "step_algorithmic_gbs": (sum(alg_sift.values()) if FEAT == "sift128" else B * (4 * P_PIX + 12 * Ccand + 60 * N)) / (ms / args.steps * 1e-3) / 1e9}
         # ---- CPU baseline (oracle port) on this host, bounded sample
         nthreads = host_threads()
         step, sample, per_frame = cpu_arm(frames, pb, nthreads, seconds_budget=3.0)
@@ -391,7 +441,7 @@ def run_gpu(args):
                                   % (len(sample), reps, nthreads, os.cpu_count() or 0, 1.0 / per_frame)}
         # ---- extras: single-frame latency through the host API (the reference handles one frame per call) and the
         # host->device bandwidth that bounds the e2e leg
-        ex1 = pkg.FeatureExtractor("orb32", nfeatures=NFEAT, device=local, max_batch=1, max_w=W, max_h=H)
+        ex1 = pkg.FeatureExtractor(FEAT, nfeatures=NFEAT, device=local, max_batch=1, max_w=W, max_h=H)
         for _ in range(5):
             ex1(frames[0])
         t0 = time.perf_counter()
@@ -411,10 +461,10 @@ def run_gpu(args):
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "u8", "data": "synthetic",
-            "config": {"workload": "orb32 640x480 synthetic batch, 1000 kp/frame, extract+SearchForInitialization on 1xB200 per rank (configs[1])",
+            "dtype": "f32" if FEAT == "sift128" else "u8", "data": "synthetic",
+            "config": {"workload": WL["name"],
                        "frames_per_step_per_gpu": B, "pairs_per_step_per_gpu": B, "parallelism": "frames sharded, dp%d" % world,
-                       "l2": "inputs+intermediates (%.1f GB/step) larger than L2, no flush" % (B * 3.1e6 / 1e9),
+                       "l2": "inputs+intermediates (%.1f GB/step) larger than L2, no flush" % (B * (54e6 * W * H / 921600 if FEAT == "sift128" else 3.1e6 * W * H / 307200) / 1e9),
                        "gather": bool(world > 1 and args.gather), "gather_mode": "NCCL gather of packed results to rank 0 every step, overlapped with the next step"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": ms_e2e / args.steps, "h2d_gbs_measured": h2d_gbs, "single_frame_latency_ms": single_ms, "pipeline": "%d chunks of %d frames on 2 streams, host sync after the last step only" % (nchunks, CH)},
@@ -437,11 +487,13 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--batch", type=int, default=512, help="frames per step per GPU")
+    ap.add_argument("--batch", type=int, default=0, help="frames per step per GPU (default: 512 for c2, 64 for c3, 128 for c5)")
     ap.add_argument("--e2e-chunk", type=int, default=512, help="frames per pipelined chunk in the e2e leg")
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS), help="BASELINE.json config: c2 = configs[1] (headline), c3 = configs[2], c5 = configs[4]")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-gather", dest="gather", action="store_false")
     args = ap.parse_args()
+    args.batch = select_workload(args.workload, args.batch)
     if args.impl == "reference":
         return run_reference(args)
     return run_gpu(args)

@@ -156,6 +156,9 @@ int   orc_sift_detect(const uint8_t* gray, int w, int h, int stride, int nfeatur
 int   orc_sift_ref_octave(float s);
 int   orc_sift128_extract(const uint8_t* gray, int w, int h, int stride, int nfeatures, int nlevels, float scale_factor,
                           orc_keypoint* kps, float* desc, float* kpsize, int cap, int* n_out, int* n_detected);
+long  orc_sift128_extract_match_batch(const uint8_t* frames, int B, int w, int h, int nfeatures, int nlevels, float scale_factor,
+                                      const int* pair_a, const int* pair_b, int P, int window, float th_low, float nnratio,
+                                      int check_ori, int nthreads);
 
 #ifdef __cplusplus
 }

@@ -37,6 +37,7 @@ def lib():
         _LIB.orc_fast_atan2.argtypes = [C.c_float, C.c_float]
         _LIB.orc_descriptor_distance.restype = C.c_float
         _LIB.orc_orb32_extract_match_batch.restype = C.c_long
+        _LIB.orc_sift128_extract_match_batch.restype = C.c_long
     return _LIB
 
 
@@ -283,3 +284,15 @@ def sift128_extract(gray, nfeatures, nlevels=8, scale_factor=2.0):
                                    _p(size), cap, C.byref(n), C.byref(nd))
     assert rc == 0, rc
     return kps[:n.value].copy(), desc[:n.value].copy(), size[:n.value].copy(), nd.value
+
+
+def sift_extract_match_batch(frames, pair_a, pair_b, nfeatures=2000, nthreads=1, window=100, th_low=0.5, nnratio=0.9, check_ori=True):
+    """One bench step of the sift128 workload on the CPU (pthreads in C). Returns the total number of matches."""
+    frames = np.ascontiguousarray(frames, np.uint8)
+    B, h, w = frames.shape
+    pa = np.ascontiguousarray(pair_a, np.int32); pb = np.ascontiguousarray(pair_b, np.int32)
+    L = lib(); L.orc_sift128_extract_match_batch.restype = C.c_long
+    r = L.orc_sift128_extract_match_batch(_p(frames), B, w, h, int(nfeatures), 8, _f(2.0), _p(pa), _p(pb), len(pa),
+                                          int(window), _f(th_low), _f(nnratio), int(bool(check_ori)), int(nthreads))
+    assert r >= 0
+    return int(r)
