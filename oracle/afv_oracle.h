@@ -160,6 +160,17 @@ long  orc_sift128_extract_match_batch(const uint8_t* frames, int B, int w, int h
                                       const int* pair_a, const int* pair_b, int P, int window, float th_low, float nnratio,
                                       int check_ori, int nthreads);
 
+
+/* ---- akaze61 (afv_oracle_akaze.c; PARITY UNPINNED: libAKAZE is not vendored by the reference) -------------------- */
+int   orc_akaze_schedule(int w, int h, int omax, int nsub, int* lw, int* lh, int* octave, int* sigma_size, float* esigma,
+                         int* nsteps, float* tau);
+int   orc_akaze_gauss_taps(float sigma, float* taps);
+long  orc_akaze_scale_space(const uint8_t* gray, int w, int h, int stride, int omax, int nsub, int what, int level, float* out,
+                            int* ow, int* oh, float* kcontrast);
+int   orc_akaze_detect(const uint8_t* gray, int w, int h, int stride, int omax, int nsub, float dth, float* out5, int cap);
+int   orc_akaze61_extract(const uint8_t* gray, int w, int h, int stride, int nfeatures, int nlevels, float scale_factor,
+                          float detect_th, orc_keypoint* kps, uint8_t* desc, float* kpsize, int cap, int* n_out, int* n_detected);
+
 #ifdef __cplusplus
 }
 #endif

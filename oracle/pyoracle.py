@@ -20,7 +20,7 @@ DESC_ORB, DESC_AKAZE61, DESC_BRISK, DESC_SIFT128 = 0, 1, 2, 5      # include/Typ
 
 def build(force=False):
     so = os.path.join(_DIR, "libafv_oracle.so")
-    srcs = [os.path.join(_DIR, f) for f in ("afv_oracle.c", "afv_oracle_match.c", "afv_oracle_sift.c", "afv_oracle.h", "orb_pattern.inc")]
+    srcs = [os.path.join(_DIR, f) for f in ("afv_oracle.c", "afv_oracle_match.c", "afv_oracle_sift.c", "afv_oracle_akaze.c", "afv_oracle.h", "orb_pattern.inc")]
     if force or not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
         subprocess.check_call(["make", "-s", "-C", _DIR, "libafv_oracle.so"])
     return so
@@ -296,3 +296,39 @@ def sift_extract_match_batch(frames, pair_a, pair_b, nfeatures=2000, nthreads=1,
                                           int(window), _f(th_low), _f(nnratio), int(bool(check_ori)), int(nthreads))
     assert r >= 0
     return int(r)
+
+
+# ---- akaze61 (oracle/afv_oracle_akaze.c; PARITY UNPINNED, see its header) -------------------------------------------
+def akaze_scale_space(gray, what, level, omax=2, nsub=4):
+    """what: 0 Lt, 1 Lsmooth, 2 Lx, 3 Ly, 4 Ldet of evolution level `level`; returns (image, kcontrast)."""
+    gray = np.ascontiguousarray(gray, np.uint8)
+    h, w = gray.shape
+    ow = C.c_int(0); oh = C.c_int(0); kc = C.c_float(0)
+    L = lib(); L.orc_akaze_scale_space.restype = C.c_long
+    n = L.orc_akaze_scale_space(_p(gray), w, h, w, omax, nsub, int(what), int(level), None, C.byref(ow), C.byref(oh), C.byref(kc))
+    assert n > 0
+    out = np.zeros((oh.value, ow.value), np.float32)
+    L.orc_akaze_scale_space(_p(gray), w, h, w, omax, nsub, int(what), int(level), _p(out), C.byref(ow), C.byref(oh), C.byref(kc))
+    return out, kc.value
+
+
+def akaze_detect(gray, dth=5e-4, omax=2, nsub=4, cap=100000):
+    """Feature_Detection list: (n,5) x, y, size, response, class_id."""
+    gray = np.ascontiguousarray(gray, np.uint8)
+    h, w = gray.shape
+    out = np.zeros((cap, 5), np.float32)
+    n = lib().orc_akaze_detect(_p(gray), w, h, w, omax, nsub, _f(dth), _p(out), cap)
+    assert n >= 0, n
+    return out[:n].copy()
+
+
+def akaze61_extract(gray, nfeatures, nlevels=8, scale_factor=1.1892, detect_th=5e-4):
+    gray = np.ascontiguousarray(gray, np.uint8)
+    h, w = gray.shape
+    cap = nfeatures + 3 * nlevels + 64
+    kps = np.zeros(cap, KP_DTYPE); desc = np.zeros((cap, 61), np.uint8); size = np.zeros(cap, np.float32)
+    n = C.c_int(0); nd = C.c_int(0)
+    rc = lib().orc_akaze61_extract(_p(gray), w, h, w, int(nfeatures), int(nlevels), _f(scale_factor), _f(detect_th), _p(kps),
+                                   _p(desc), _p(size), cap, C.byref(n), C.byref(nd))
+    assert rc == 0, rc
+    return kps[:n.value].copy(), desc[:n.value].copy(), size[:n.value].copy(), nd.value
