@@ -5,6 +5,7 @@
 // and the INTER_LINEAR_EXACT coefficient tables; everything per frame runs in afv_orb.cu kernels.
 #include "afv_common.cuh"
 #include "afv_sift.h"
+#include "afv_akaze.h"
 #include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
@@ -94,7 +95,8 @@ struct afv_extractor {
     int last_B;
     cudaStream_t last_stream;
     AfvSift* sift;                    // sift128 state (feature_id == AFV_FEAT_SIFT128), else NULL
-    int desc_bytes;                   // bytes per descriptor row: 32 (orb32) / 512 (sift128: 128 floats)
+    AfvAkaze* akaze;                  // akaze61 state (feature_id == AFV_FEAT_AKAZE61), else NULL
+    int desc_bytes;                   // bytes per descriptor row: 32 (orb32) / 61 (akaze61) / 512 (sift128: 128 floats)
 };
 
 // reference src/FeatureExtractor.cpp:97-108 (same formula inside cv::ORB for its maxFeatures quota)
@@ -210,8 +212,8 @@ extern "C" int afv_extractor_create(afv_extractor** out, int feature_id, int nfe
                                     int max_batch, int max_w, int max_h) {
     if (!out) { afv_set_error("out is NULL"); return AFV_ERR_INVALID; }
     *out = nullptr;
-    if (feature_id != AFV_FEAT_ORB32 && feature_id != AFV_FEAT_SIFT128) {
-        afv_set_error("feature id %d: extractor not built (orb32 and sift128 only); matcher entry points accept akaze61/brisk48", feature_id);
+    if (feature_id != AFV_FEAT_ORB32 && feature_id != AFV_FEAT_SIFT128 && feature_id != AFV_FEAT_AKAZE61) {
+        afv_set_error("feature id %d: extractor not built (orb32, sift128, akaze61 only); matcher entry points accept brisk48", feature_id);
         return AFV_ERR_UNSUPPORTED;
     }
     if (feature_id == AFV_FEAT_SIFT128 && n_octaves > 15) { afv_set_error("sift128: at most 15 levels"); return AFV_ERR_INVALID; }
@@ -230,18 +232,22 @@ extern "C" int afv_extractor_create(afv_extractor** out, int feature_id, int nfe
     ex->scale_factor = scale_factor; ex->detect_th = detect_th;
     ex->max_batch = max_batch; ex->max_w = max_w; ex->max_h = max_h; ex->cur_w = ex->cur_h = 0;
     ex->last_B = 0; ex->last_stream = nullptr;
-    ex->sift = nullptr; ex->desc_bytes = feature_id == AFV_FEAT_SIFT128 ? 512 : 32;
+    ex->sift = nullptr; ex->akaze = nullptr;
+    ex->desc_bytes = feature_id == AFV_FEAT_SIFT128 ? 512 : feature_id == AFV_FEAT_AKAZE61 ? 61 : 32;
     ex->h_status = nullptr; ex->h_counts = nullptr; ex->aux.stream = nullptr; ex->aux.ev_pyr = nullptr; ex->aux.ev_blur = nullptr;
     AFV_CUDA_CHECK(cudaStreamCreateWithFlags(&ex->stream, cudaStreamNonBlocking));
-    if (feature_id == AFV_FEAT_SIFT128) {
+    if (feature_id == AFV_FEAT_SIFT128 || feature_id == AFV_FEAT_AKAZE61) {
+        // FeatureExtractor_akaze61 (reference src/Feature_akaze61.cpp:7-13): omax = n_octaves / 4, nsublevels = n_octaves / 2,
+        // dthreshold = detect_th.
         // FeatureExtractor_sift128 (reference src/Feature_sift128.cpp:9-62): SiftGPU arguments are fixed by the reference;
         // n_octaves / scale_factor only drive mnFeaturesPerLevel and computeSize (settings/sift128_settings.yaml: 8, 2.0)
         for (int l = 0; l < n_octaves; ++l) ex->ext_scale[l] = l == 0 ? 1.0f : ex->ext_scale[l - 1] * scale_factor;
         features_per_level(nfeatures, n_octaves, scale_factor, ex->q_ext);
-        int rc = afv_sift_create(&ex->sift, nfeatures, n_octaves, scale_factor, max_batch, max_w, max_h);
+        int rc = feature_id == AFV_FEAT_SIFT128 ? afv_sift_create(&ex->sift, nfeatures, n_octaves, scale_factor, max_batch, max_w, max_h)
+                                                : afv_akaze_create(&ex->akaze, nfeatures, n_octaves, scale_factor, detect_th, max_batch, max_w, max_h);
         const int ocap = nfeatures + 3 * n_octaves;
         if (rc == AFV_OK) rc = dev_alloc(ex, &ex->o_kps, (size_t)ocap * max_batch);
-        if (rc == AFV_OK) rc = dev_alloc(ex, &ex->o_desc, (size_t)ocap * 512 * max_batch);
+        if (rc == AFV_OK) rc = dev_alloc(ex, &ex->o_desc, (size_t)ocap * ex->desc_bytes * max_batch);
         if (rc == AFV_OK) rc = dev_alloc(ex, &ex->o_size, (size_t)ocap * max_batch);
         if (rc == AFV_OK) rc = dev_alloc(ex, &ex->o_n, (size_t)max_batch);
         if (rc != AFV_OK) { afv_extractor_destroy(ex); return rc; }
@@ -318,6 +324,7 @@ extern "C" void afv_extractor_destroy(afv_extractor* ex) {
     if (ex->aux.ev_blur) cudaEventDestroy(ex->aux.ev_blur);
     for (void* p : ex->allocs) cudaFree(p);
     if (ex->sift) afv_sift_destroy(ex->sift);
+    if (ex->akaze) afv_akaze_destroy(ex->akaze);
     if (ex->h_status) cudaFreeHost(ex->h_status);
     if (ex->h_counts) cudaFreeHost(ex->h_counts);
     delete ex;
@@ -339,8 +346,9 @@ static int run_device(afv_extractor* ex, const uint8_t* d_gray, int B, int w, in
                       bool gray_is_staged) {
     if (B < 1 || B > ex->max_batch) { afv_set_error("batch %d outside 1..%d", B, ex->max_batch); return AFV_ERR_INVALID; }
     if (cap < afv_extractor_output_cap(ex)) { afv_set_error("cap %d < required %d", cap, afv_extractor_output_cap(ex)); return AFV_ERR_INVALID; }
-    if (ex->sift) {
-        const int src = afv_sift_run(ex->sift, d_gray, B, w, h, stride, frame_stride, d_kps, (float*)d_desc, d_kpsize, cap, d_n_out, st);
+    if (ex->sift || ex->akaze) {
+        const int src = ex->sift ? afv_sift_run(ex->sift, d_gray, B, w, h, stride, frame_stride, d_kps, (float*)d_desc, d_kpsize, cap, d_n_out, st)
+                                 : afv_akaze_run(ex->akaze, d_gray, B, w, h, stride, frame_stride, d_kps, (uint8_t*)d_desc, d_kpsize, cap, d_n_out, st);
         if (src) return src;
         ex->last_B = B; ex->last_stream = st;
         return AFV_OK;
@@ -366,6 +374,7 @@ static int run_device(afv_extractor* ex, const uint8_t* d_gray, int B, int w, in
 
 static int check_status(afv_extractor* ex, int B, cudaStream_t st) {
     if (ex->sift) return afv_sift_status(ex->sift, B, st);
+    if (ex->akaze) return afv_akaze_status(ex->akaze, B, st);
     AFV_CUDA_CHECK(cudaMemcpyAsync(ex->h_status, ex->status, sizeof(int) * B, cudaMemcpyDeviceToHost, st));
     AFV_CUDA_CHECK(cudaStreamSynchronize(st));
     for (int b = 0; b < B; ++b)
@@ -403,9 +412,10 @@ extern "C" int afv_extract_batch(afv_extractor* ex, const uint8_t* gray, int B, 
     if (cap < ocap) { afv_set_error("cap %d < required %d", cap, ocap); return AFV_ERR_INVALID; }
     if (stride < w) { afv_set_error("stride < w"); return AFV_ERR_INVALID; }
     cudaStream_t st = ex->stream;
-    if (ex->sift) {
+    if (ex->sift || ex->akaze) {
         if (w > ex->max_w || h > ex->max_h) { afv_set_error("frame %dx%d larger than the extractor's configured maximum", w, h); return AFV_ERR_INVALID; }
-        uint8_t* stage = afv_sift_stage(ex->sift);
+        uint8_t* stage = ex->sift ? afv_sift_stage(ex->sift) : afv_akaze_stage(ex->akaze);
+        const size_t DB = (size_t)ex->desc_bytes;
         for (int b0 = 0; b0 < B; b0 += ex->max_batch) {
             const int nb = B - b0 < ex->max_batch ? B - b0 : ex->max_batch;
             if (frame_stride == (long)stride * h)
@@ -417,8 +427,8 @@ extern "C" int afv_extract_batch(afv_extractor* ex, const uint8_t* gray, int B, 
             if (rc) return rc;
             AFV_CUDA_CHECK(cudaMemcpy2DAsync(kps + (size_t)b0 * cap, (size_t)cap * sizeof(afv_keypoint), ex->o_kps, (size_t)ocap * sizeof(afv_keypoint),
                                              (size_t)ocap * sizeof(afv_keypoint), nb, cudaMemcpyDeviceToHost, st));
-            AFV_CUDA_CHECK(cudaMemcpy2DAsync((uint8_t*)desc + (size_t)b0 * cap * 512, (size_t)cap * 512, ex->o_desc, (size_t)ocap * 512,
-                                             (size_t)ocap * 512, nb, cudaMemcpyDeviceToHost, st));
+            AFV_CUDA_CHECK(cudaMemcpy2DAsync((uint8_t*)desc + (size_t)b0 * cap * DB, (size_t)cap * DB, ex->o_desc, (size_t)ocap * DB,
+                                             (size_t)ocap * DB, nb, cudaMemcpyDeviceToHost, st));
             if (kpsize)
                 AFV_CUDA_CHECK(cudaMemcpy2DAsync(kpsize + (size_t)b0 * cap, (size_t)cap * sizeof(float), ex->o_size, (size_t)ocap * sizeof(float),
                                                  (size_t)ocap * sizeof(float), nb, cudaMemcpyDeviceToHost, st));
@@ -463,11 +473,12 @@ extern "C" int afv_extract(afv_extractor* ex, const uint8_t* gray, int w, int h,
 }
 
 extern "C" int afv_debug_read(afv_extractor* ex, int what, int frame, int level, void* out, long cap_bytes, long* n_bytes) {
-    if (ex && ex->sift) {
+    if (ex && (ex->sift || ex->akaze)) {
         if (!out || !n_bytes || frame < 0 || frame >= ex->last_B) { afv_set_error("afv_debug_read: bad argument"); return AFV_ERR_INVALID; }
         AFV_CUDA_CHECK(cudaSetDevice(ex->device));
         AFV_CUDA_CHECK(cudaStreamSynchronize(ex->last_stream));
-        return afv_sift_debug_read(ex->sift, what, frame, level, out, cap_bytes, n_bytes);
+        return ex->sift ? afv_sift_debug_read(ex->sift, what, frame, level, out, cap_bytes, n_bytes)
+                        : afv_akaze_debug_read(ex->akaze, what, frame, level, out, cap_bytes, n_bytes);
     }
     if (!ex || !out || !n_bytes || level < 0 || level >= ex->nlevels || frame < 0 || frame >= ex->last_B) {
         afv_set_error("afv_debug_read: bad argument"); return AFV_ERR_INVALID;

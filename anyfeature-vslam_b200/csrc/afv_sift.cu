@@ -19,6 +19,7 @@
 //   k_sift_describe    warp per kept keypoint: 4x4x8 integer histogram, normalise / clamp / renormalise, merged output
 #include "afv_common.cuh"
 #include "afv_octree.cuh"
+#include "afv_blur.cuh"
 #include "afv_sift.h"
 #include <math.h>
 #include <stdio.h>
@@ -68,7 +69,6 @@ struct SiftParams {
 #define SIFT_ST_OCTREE_OVERFLOW 8
 #define SIFT_ST_OUT_OVERFLOW 4
 
-__constant__ float c_taps[6][16];
 
 // ---- deterministic elementary functions (same polynomials and operation order as the oracle) -----------------------
 __device__ __forceinline__ float sift_exp2(float t) {
@@ -133,87 +133,6 @@ __device__ __forceinline__ void sift_sincos(float a, float* sn, float* cs) {
 
 __device__ __forceinline__ float sift_sigma(float ls) { return (1.6f * 0x1.428a3p+0f) * sift_exp2(ls * (1.0f / 3.0f)); }
 __device__ __forceinline__ int sift_glevel(float ls) { return min(max((int)rintf(ls) + 1, 1), 3); }
-
-// ------------------------------------------------------------------------------------------------------
-// Gaussian step.  CTA = 128 x 32 outputs, 256 threads.  The (128+2R) x (32+2R) source footprint is staged with clamped
-// coordinates; row pass: one thread = 4 consecutive outputs from a (4+2R)-float register window (float4 LDS); column
-// pass: one thread = 8 consecutive rows of one column from an (8+2R) register window.  acc = t0*c; acc += tj*(l + r).
-// ------------------------------------------------------------------------------------------------------
-#define SB_W 128
-#define SB_H 32
-template <int R, bool U8>
-__global__ void __launch_bounds__(256) k_sift_blur(const void* __restrict__ src_, int sstride, long long sfstride,
-                                                   float* __restrict__ dst, float* __restrict__ dog, int w, int h,
-                                                   int stride, long long istride, int ki) {
-    constexpr int PW = (SB_W + 2 * R + 3) & ~3;          // staged row pitch (floats)
-    constexpr int PH = SB_H + 2 * R;
-    extern __shared__ __align__(16) float sm[];
-    float* in = sm;                                      // [PH][PW]
-    float* mid = sm + PH * PW;                           // [PH][SB_W]
-    const int tid = threadIdx.x, f = blockIdx.z;
-    const int tx0 = blockIdx.x * SB_W, ty0 = blockIdx.y * SB_H;
-    float tp[R + 1];
-#pragma unroll
-    for (int j = 0; j <= R; ++j) tp[j] = c_taps[ki][j];
-    if (U8) {
-        const uint8_t* s = reinterpret_cast<const uint8_t*>(src_) + (long long)f * sfstride;
-        for (int i = tid; i < PH * PW; i += 256) {
-            const int ry = i / PW, rx = i - ry * PW;
-            const int y = min(max(ty0 - R + ry, 0), h - 1), x = min(max(tx0 - R + rx, 0), w - 1);
-            in[i] = (float)s[(long long)y * sstride + x] / 255.0f;
-        }
-    } else {
-        const float* s = reinterpret_cast<const float*>(src_) + (long long)f * sfstride;
-        for (int i = tid; i < PH * PW; i += 256) {
-            const int ry = i / PW, rx = i - ry * PW;
-            const int y = min(max(ty0 - R + ry, 0), h - 1), x = min(max(tx0 - R + rx, 0), w - 1);
-            in[i] = s[(long long)y * sstride + x];
-        }
-    }
-    __syncthreads();
-    // row pass
-    for (int u = tid; u < PH * (SB_W / 4); u += 256) {
-        const int ry = u >> 5, xg = (u & 31) * 4;
-        constexpr int NW = (4 + 2 * R + 3) / 4;
-        float win[NW * 4];
-        const float4* p = reinterpret_cast<const float4*>(in + ry * PW + xg);
-#pragma unroll
-        for (int k = 0; k < NW; ++k) { const float4 v = p[k]; win[4 * k] = v.x; win[4 * k + 1] = v.y; win[4 * k + 2] = v.z; win[4 * k + 3] = v.w; }
-        float4 o;
-        float* op = reinterpret_cast<float*>(&o);
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            float acc = tp[0] * win[q + R];
-#pragma unroll
-            for (int j = 1; j <= R; ++j) acc = acc + tp[j] * (win[q + R - j] + win[q + R + j]);
-            op[q] = acc;
-        }
-        *reinterpret_cast<float4*>(mid + ry * SB_W + xg) = o;
-    }
-    __syncthreads();
-    // column pass
-    for (int u = tid; u < SB_W * (SB_H / 8); u += 256) {
-        const int x = u & 127, yg = (u >> 7) * 8;
-        const int gx = tx0 + x;
-        float win[8 + 2 * R];
-#pragma unroll
-        for (int k = 0; k < 8 + 2 * R; ++k) win[k] = mid[(yg + k) * SB_W + x];
-        if (gx < w) {
-#pragma unroll
-            for (int q = 0; q < 8; ++q) {
-                const int gy = ty0 + yg + q;
-                float acc = tp[0] * win[q + R];
-#pragma unroll
-                for (int j = 1; j <= R; ++j) acc = acc + tp[j] * (win[q + R - j] + win[q + R + j]);
-                if (gy < h) {
-                    const long long o = (long long)f * istride + (long long)gy * stride + gx;
-                    dst[o] = acc;
-                    if (!U8) dog[o] = acc - in[(yg + q + R) * PW + x + R];
-                }
-            }
-        }
-    }
-}
 
 __global__ void __launch_bounds__(256) k_sift_down(const float* __restrict__ src, int sstride, long long sistride,
                                                    float* __restrict__ dst, int w, int h, int stride, long long istride) {
@@ -682,6 +601,7 @@ struct AfvSift {
     int nfeatures, nlevels, max_batch, max_w, max_h, cur_w, cur_h;
     float scale_factor;
     int rad[6];
+    AfvBlurTaps taps[6];
     std::vector<void*> allocs;
     SiftParams P;
     float* g[SIFT_MAX_OCT]; float* d[SIFT_MAX_OCT];
@@ -720,21 +640,6 @@ static int sift_alloc(AfvSift* s, T** p, size_t n) {
     return AFV_OK;
 }
 
-template <int R, bool U8> static size_t blur_smem() {
-    return sizeof(float) * (size_t)(SB_H + 2 * R) * (((SB_W + 2 * R + 3) & ~3) + SB_W);
-}
-template <int R, bool U8> static int blur_cfg() {
-    AFV_CUDA_CHECK(cudaFuncSetAttribute(k_sift_blur<R, U8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)blur_smem<R, U8>()));
-    return AFV_OK;
-}
-template <int R, bool U8>
-static void blur_launch(const void* src, int sstride, long long sfstride, float* dst, float* dog, int w, int h, int stride,
-                        long long istride, int ki, int B, cudaStream_t st) {
-    dim3 g((w + SB_W - 1) / SB_W, (h + SB_H - 1) / SB_H, B);
-    k_sift_blur<R, U8><<<g, 256, blur_smem<R, U8>(), st>>>(src, sstride, sfstride, dst, dog, w, h, stride, istride, ki);
-    ++g_afv_launches;
-}
-
 // the five incremental steps have fixed radii (5, 7, 8, 10, 13) and the base step 7 for the SiftGPU sigmas
 static const int k_expected_rad[6] = {7, 5, 7, 8, 10, 13};
 
@@ -769,9 +674,16 @@ int afv_sift_create(AfvSift** out, int nfeatures, int nlevels, float scale_facto
         if (s->rad[i] != k_expected_rad[i]) { afv_set_error("sift128: internal: blur radius %d of step %d unexpected", s->rad[i], i); delete s; return AFV_ERR_INVALID; }
     }
     int rc = AFV_OK;
-    { cudaError_t e = cudaMemcpyToSymbol(c_taps, taps, sizeof(taps)); if (e != cudaSuccess) { afv_set_error("cudaMemcpyToSymbol: %s", cudaGetErrorString(e)); delete s; return AFV_ERR_CUDA; } }
-    if ((rc = blur_cfg<7, true>()) || (rc = blur_cfg<5, false>()) || (rc = blur_cfg<7, false>()) || (rc = blur_cfg<8, false>()) ||
-        (rc = blur_cfg<10, false>()) || (rc = blur_cfg<13, false>())) { delete s; return rc; }
+    for (int i = 0; i < 6; ++i) memcpy(s->taps[i].t, taps[i], sizeof(float) * 16);
+    {
+        cudaError_t e = afv_blur_cfg<7, 1>();
+        if (e == cudaSuccess) e = afv_blur_cfg<5, 0>();
+        if (e == cudaSuccess) e = afv_blur_cfg<7, 0>();
+        if (e == cudaSuccess) e = afv_blur_cfg<8, 0>();
+        if (e == cudaSuccess) e = afv_blur_cfg<10, 0>();
+        if (e == cudaSuccess) e = afv_blur_cfg<13, 0>();
+        if (e != cudaSuccess) { afv_set_error("cudaFuncSetAttribute(blur) failed: %s", cudaGetErrorString(e)); delete s; return AFV_ERR_CUDA; }
+    }
     s->max_no = sift_num_octaves(max_w, max_h);
     const size_t B = (size_t)max_batch;
     int ow = max_w, oh = max_h, key_cap = 0;
@@ -876,18 +788,18 @@ int afv_sift_run(AfvSift* s, const uint8_t* d_gray, int B, int w, int h, int str
         auto G = [&](int i) { return O.g + (long long)i * B * O.istride; };
         auto D = [&](int i) { return O.d + (long long)i * B * O.istride; };
         { AfvProfScope ps("k_sift_blur", st);
-        if (o == 0) blur_launch<7, true>(d_gray, stride, frame_stride, G(0), nullptr, O.w, O.h, O.stride, O.istride, 0, B, st);
+        if (o == 0) { afv_blur_launch<7, 1>(d_gray, stride, frame_stride, G(0), nullptr, O.w, O.h, O.stride, O.istride, s->taps[0], B, st); ++g_afv_launches; }
         else {
             const SiftOctG& Q = P.oc[o - 1];
             dim3 g((O.w + 63) / 64, (O.h + 3) / 4, B);
             k_sift_down<<<g, 256, 0, st>>>(Q.g + (long long)SIFT_S * B * Q.istride, Q.stride, Q.istride, G(0), O.w, O.h, O.stride, O.istride);
             ++g_afv_launches;
         }
-        blur_launch<5, false>(G(0), O.stride, O.istride, G(1), D(0), O.w, O.h, O.stride, O.istride, 1, B, st);
-        blur_launch<7, false>(G(1), O.stride, O.istride, G(2), D(1), O.w, O.h, O.stride, O.istride, 2, B, st);
-        blur_launch<8, false>(G(2), O.stride, O.istride, G(3), D(2), O.w, O.h, O.stride, O.istride, 3, B, st);
-        blur_launch<10, false>(G(3), O.stride, O.istride, G(4), D(3), O.w, O.h, O.stride, O.istride, 4, B, st);
-        blur_launch<13, false>(G(4), O.stride, O.istride, G(5), D(4), O.w, O.h, O.stride, O.istride, 5, B, st);
+        afv_blur_launch<5, 0>(G(0), O.stride, O.istride, G(1), D(0), O.w, O.h, O.stride, O.istride, s->taps[1], B, st); ++g_afv_launches;
+        afv_blur_launch<7, 0>(G(1), O.stride, O.istride, G(2), D(1), O.w, O.h, O.stride, O.istride, s->taps[2], B, st); ++g_afv_launches;
+        afv_blur_launch<8, 0>(G(2), O.stride, O.istride, G(3), D(2), O.w, O.h, O.stride, O.istride, s->taps[3], B, st); ++g_afv_launches;
+        afv_blur_launch<10, 0>(G(3), O.stride, O.istride, G(4), D(3), O.w, O.h, O.stride, O.istride, s->taps[4], B, st); ++g_afv_launches;
+        afv_blur_launch<13, 0>(G(4), O.stride, O.istride, G(5), D(4), O.w, O.h, O.stride, O.istride, s->taps[5], B, st); ++g_afv_launches;
         }
     }
     { AfvProfScope ps("k_sift_detect", st);

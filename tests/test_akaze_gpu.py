@@ -1,0 +1,108 @@
+"""Parity of the CUDA akaze61 extraction path (through the C ABI) against the CPU oracle (oracle/afv_oracle_akaze.c;
+parity vs libAKAZE itself is UNPINNED, see that file's header).  Bit-exact by construction: scale-space taps, contrast
+factor, Feature_Detection list, final keypoints, 486-bit descriptors, sizes."""
+import numpy as np
+import pytest
+
+from oracle import pyoracle as po
+
+pytestmark = pytest.mark.gpu
+
+
+def _taps(ex, frames):
+    bad = []
+    for f, img in enumerate(frames):
+        kc = ex.debug_read(26, f, 0, nbytes_cap=64).view(np.float32)[0]
+        _, rkc = po.akaze_scale_space(img, 0, 0)
+        if np.float32(rkc) != kc:
+            bad.append("frame %d: contrast factor %r, oracle %r" % (f, float(kc), float(rkc)))
+        for lv in range(8):
+            for what, name in ((0, "Lt"), (1, "Lsmooth"), (2, "Lx"), (3, "Ly"), (4, "Ldet")):
+                ref, _ = po.akaze_scale_space(img, what, lv)
+                got = ex.debug_read(20 + what, f, lv, nbytes_cap=ref.size * 4 + 16).view(np.float32).reshape(ref.shape)
+                if not (got.view(np.uint32) == ref.view(np.uint32)).all():
+                    bad.append("frame %d level %d %s: %d px differ (max %.3g)" % (f, lv, name, int((got != ref).sum()), float(np.abs(got - ref).max())))
+    return bad
+
+
+def _check(pkg, frames, nfeatures, w, h, taps=True):
+    ex = pkg.FeatureExtractor("akaze61", nfeatures=nfeatures, max_batch=len(frames), max_w=w, max_h=h)
+    kps, desc, size, n = ex.extract_batch(frames)
+    problems = []
+    for f, img in enumerate(frames):
+        rk, rd, rs, nd = po.akaze61_extract(img, nfeatures)
+        det = po.akaze_detect(img)
+        lst = ex.debug_read(25, f, 0, nbytes_cap=20 * (len(det) + 4096)).view(np.float32).reshape(-1, 5)
+        if lst.shape != det.shape or not (lst.view(np.uint32) == det.view(np.uint32)).all():
+            same = lst.shape == det.shape
+            problems.append("frame %d: Feature_Detection list differs (ref %d, gpu %d%s)" % (
+                f, len(det), len(lst), ", %d rows differ" % int((lst != det).any(axis=1).sum()) if same else ""))
+        m = int(n[f])
+        if m != len(rk):
+            problems.append("frame %d: %d keypoints, oracle %d" % (f, m, len(rk)))
+            continue
+        for fld in rk.dtype.names:
+            if not (kps[f, :m][fld] == rk[fld]).all():
+                problems.append("frame %d: keypoint field %s differs in %d rows" % (f, fld, int((kps[f, :m][fld] != rk[fld]).sum())))
+        if not (desc[f, :m] == rd).all():
+            problems.append("frame %d: %d descriptor rows differ" % (f, int((desc[f, :m] != rd).any(axis=1).sum())))
+        if not (size[f, :m] == rs).all():
+            problems.append("frame %d: computeSize differs" % f)
+    if problems and taps:
+        problems += _taps(ex, frames)
+    ex.close()
+    assert not problems, "\n".join(problems[:40])
+
+
+def test_akaze_640x480(pkg, synth):
+    frames, _ = synth.stream_frames(640, 480, 0, 2)
+    _check(pkg, frames, 1000, 640, 480)
+
+
+def test_akaze_scale_space_taps(pkg, synth):
+    frames, _ = synth.stream_frames(640, 480, 3, 1)
+    ex = pkg.FeatureExtractor("akaze61", nfeatures=1000, max_batch=1, max_w=640, max_h=480)
+    ex.extract_batch(frames)
+    bad = _taps(ex, frames)
+    ex.close()
+    assert not bad, "\n".join(bad[:20])
+
+
+def test_akaze_other_sizes(pkg, synth):
+    frames, _ = synth.stream_frames(1280, 720, 1, 1)
+    _check(pkg, frames, 2000, 1280, 720, taps=False)
+    f2, _ = synth.stream_frames(640, 480, 5, 1)
+    img = np.ascontiguousarray(f2[:, 6:6 + 334, 10:10 + 518])
+    _check(pkg, img, 500, 640, 480)
+
+
+def test_akaze_blank_device_api_and_matcher(pkg, synth):
+    """C4: akaze61 descriptors through the Hamming matcher (DescriptorDistance_akaze61, src/Feature_akaze61.cpp:75-77)."""
+    import torch
+    frames, _ = synth.stream_frames(640, 480, 2, 3)
+    frames[2][:] = 90
+    ex = pkg.FeatureExtractor("akaze61", nfeatures=1000, max_batch=3, max_w=640, max_h=480)
+    d = torch.from_numpy(frames).cuda()
+    out = ex.alloc_device_outputs(3)
+    ex.extract_batch_device(d, out)
+    torch.cuda.synchronize()
+    ex.status()
+    n = out[3].cpu().numpy()
+    assert n[2] == 0 and n[0] > 300 and n[1] > 300
+    ref = [po.akaze61_extract(frames[i], 1000) for i in range(2)]
+    for i in range(2):
+        k = pkg.kps_from_device(out[0][i], int(n[i]))
+        assert all((k[fld] == ref[i][0][fld]).all() for fld in k.dtype.names)
+        assert (out[1][i, :int(n[i])].cpu().numpy() == ref[i][1]).all()
+    fm = pkg.FeatureMatcher(nnratio=0.9, check_ori=False, desc_type=1, th_low=128.0)
+    pa = torch.tensor([0], dtype=torch.int32, device="cuda"); pb = torch.tensor([1], dtype=torch.int32, device="cuda")
+    max_size = float(np.float32(1.2) ** np.float32(7))
+    m12, nm = fm.search_for_initialization(out[0], out[1], out[2], out[3], pa, pb, None, (0.0, 0.0, 640.0, 480.0), max_size)
+    torch.cuda.synchronize()
+    rk0, rd0, rs0, _ = ref[0]; rk1, rd1, rs1, _ = ref[1]
+    prev = np.stack([rk0["x"], rk0["y"]], axis=1).astype(np.float32)
+    rn, rm12, _ = po.search_for_initialization(1, rk0, rd0, rk1, rd1, rs1, (0.0, 0.0, 640.0, 480.0), max_size, prev,
+                                               window=100, th_low=128.0, nnratio=0.9, check_ori=False)
+    assert int(nm[0]) == rn and rn > 20
+    assert (m12[0, :len(rk0)].cpu().numpy() == rm12).all()
+    ex.close()
