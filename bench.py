@@ -37,6 +37,10 @@ WORKLOADS = {
     "c3": dict(feature="sift128", w=1280, h=720, nfeat=2000, batch=64, desc_bytes=512, desc_type=5, th_low=0.5,
                metric="frames/sec (extract+match) sift128 1280x720x2000kp",
                name="sift128 1280x720 synthetic batch, 2000 kp/frame, extract+SearchForInitialization (L2) on 1xB200 per rank (configs[2])"),
+    "c4": dict(feature="akaze61", w=640, h=480, nfeat=1000, batch=256, desc_bytes=61, desc_type=1, th_low=128.0,
+               metric="frames/sec (extract+match) akaze61+brisk48-layout 640x480x1000kp",
+               name="akaze61 640x480 synthetic batch, 1000 kp/frame, extract + mixed Hamming SearchForInitialization (61-byte akaze61 "
+                    "and 48-byte brisk48 layout = first 384 MLDB bits; no brisk48 extractor: ETH brisk is not vendored) on 1xB200 per rank (configs[3])"),
     "c5": dict(feature="orb32", w=1280, h=720, nfeat=2000, batch=128, desc_bytes=32, desc_type=0, th_low=75.0,
                metric="frames/sec (extract+match) orb32 1280x720x2000kp",
                name="orb32 1280x720 synthetic 8-stream batch, 2000 kp/frame, streams sharded over ranks, NCCL gather (configs[4])"),
@@ -171,6 +175,8 @@ def cpu_arm(frames, pair_b, nthreads, seconds_budget):
         pa = np.arange(m, dtype=np.int32); pb = ((pa + 1) % m).astype(np.int32)
         if WL["feature"] == "sift128":
             return po.sift_extract_match_batch(fr, pa, pb, NFEAT, threads)
+        if WL["feature"] == "akaze61":
+            return po.akaze_extract_match_batch(fr, pa, pb, NFEAT, threads)
         return po.extract_match_batch(fr, pa, pb, NFEAT, threads)
 
     step([0, 1], 1)                                              # warm (library load, first-touch)
@@ -239,12 +245,17 @@ def run_gpu(args):
     ex = pkg.FeatureExtractor(FEAT, nfeatures=NFEAT, device=local, max_batch=B, max_w=W, max_h=H)
     cap = ex.cap
     fm = pkg.FeatureMatcher(nnratio=0.9, check_ori=True, desc_type=WL["desc_type"], th_low=WL["th_low"])
+    MIXED = FEAT == "akaze61"                                   # c4: second pass on the 48-byte brisk48 layout
+    fm48 = pkg.FeatureMatcher(nnratio=0.9, check_ori=True, desc_type=2, th_low=120.0) if MIXED else None
     d_gray = torch.from_numpy(frames).to(dev)
     h_gray = torch.from_numpy(frames).pin_memory()
     d_pa = torch.from_numpy(pa).to(dev); d_pb = torch.from_numpy(pb).to(dev)
     out = ex.alloc_device_outputs(B)
     m12 = torch.empty((B, cap), dtype=torch.int32, device=dev)
     nm = torch.empty((B,), dtype=torch.int32, device=dev)
+    d48 = torch.empty((B, cap, 48), dtype=torch.uint8, device=dev) if MIXED else None
+    m12b = torch.empty((B, cap), dtype=torch.int32, device=dev) if MIXED else None
+    nmb = torch.empty((B,), dtype=torch.int32, device=dev) if MIXED else None
     stream = torch.cuda.current_stream()
     gathered = None
     if world > 1 and args.gather:
@@ -260,6 +271,10 @@ def run_gpu(args):
         ex.extract_batch_device(src, out, stream)
         fm.search_for_initialization(out[0], out[1], out[2], out[3], d_pa, d_pb, None, BOUNDS, MAX_KPT_SIZE,
                                      window=100, matches12=m12, nmatches=nm, stream=stream)
+        if MIXED:
+            d48.copy_(out[1][:, :, :48])
+            fm48.search_for_initialization(out[0], d48, out[2], out[3], d_pa, d_pb, None, BOUNDS, MAX_KPT_SIZE,
+                                           window=100, matches12=m12b, nmatches=nmb, stream=stream)
         if world > 1 and args.gather and collective:
             k = step_counter[0] & 1
             step_counter[0] += 1
@@ -319,6 +334,10 @@ def run_gpu(args):
     c_nm = [torch.empty((CH,), dtype=torch.int32, device=dev) for _ in range(2)]
     c_pa = d_pa[:CH].contiguous(); c_pb = d_pb[:CH].contiguous()            # pair pattern repeats every 16 frames
     h_out = [torch.empty(t.shape, dtype=t.dtype).pin_memory() for t in (out[0], out[1], out[3], m12, nm)]
+    c_d48 = [torch.empty((CH, cap, 48), dtype=torch.uint8, device=dev) for _ in range(2)] if MIXED else None
+    c_m12b = [torch.empty((CH, cap), dtype=torch.int32, device=dev) for _ in range(2)] if MIXED else None
+    c_nmb = [torch.empty((CH,), dtype=torch.int32, device=dev) for _ in range(2)] if MIXED else None
+    h_out_b = [torch.empty(t.shape, dtype=t.dtype).pin_memory() for t in (m12b, nmb)] if MIXED else []
 
     chunk_counter = [0]
 
@@ -337,6 +356,12 @@ def run_gpu(args):
                                              MAX_KPT_SIZE, window=100, matches12=c_m12[k], nmatches=c_nm[k], stream=st)
                 for hdst, dsrc in zip(h_out, (c_out[k][0], c_out[k][1], c_out[k][3], c_m12[k], c_nm[k])):
                     hdst[lo:hi].copy_(dsrc, non_blocking=True)
+                if MIXED:
+                    c_d48[k].copy_(c_out[k][1][:, :, :48])
+                    fm48.search_for_initialization(c_out[k][0], c_d48[k], c_out[k][2], c_out[k][3], c_pa, c_pb, None, BOUNDS,
+                                                   MAX_KPT_SIZE, window=100, matches12=c_m12b[k], nmatches=c_nmb[k], stream=st)
+                    for hdst, dsrc in zip(h_out_b, (c_m12b[k], c_nmb[k])):
+                        hdst[lo:hi].copy_(dsrc, non_blocking=True)
 
     def e2e_drain():
         for st in streams:
@@ -360,7 +385,7 @@ def run_gpu(args):
     ms_e2e = max(f0.elapsed_time(f1), (time.perf_counter() - t_wall0) * 1e3)    # device events vs host wall clock: take the slower
     if sampler:
         sampler.stop()
-    h2d = int(h_gray.numel()); d2h = int(sum(t.numel() * t.element_size() for t in h_out))
+    h2d = int(h_gray.numel()); d2h = int(sum(t.numel() * t.element_size() for t in h_out + h_out_b))
     for e in exs:
         e.close()
 
@@ -399,7 +424,16 @@ def run_gpu(args):
             "k_sift_detect": B * (3 * 4.0 * 4 * S_PIX),           # 3 DoG levels, each reads itself, both neighbours and G
             "k_sift_describe": B * N * (4.0 * 45 * 45 + 512 + 28),
         }
-        alg = alg_sift if FEAT == "sift128" else {
+        px_f, px_h = float(W * H), float(W * H) / 4.0
+        alg_akaze = {
+            "k_akz_base": B * 22.0 * px_f,                        # 2 blurs of the u8 input, gradient magnitude, histogram
+            "k_akz_diffusion": B * (px_f * (3 * 16 + 10 * 12) + px_h * (4 * 16 + 22 * 12 + 8)),   # blur + flow + FED steps (3,3,4 | 4,5,6,7)
+            "k_akz_hessian": B * 36.0 * 4 * (px_f + px_h),        # deriv1 (4+8), deriv2 (8+12), extrema (4) per level
+            "k_akz_describe": B * N * (109 * 8 + 1241 * 12 + 61 + 28),
+        }
+        if FEAT == "akaze61":
+            alg_sift = alg_akaze
+        alg = alg_sift if FEAT in ("sift128", "akaze61") else {
             "k_resize": B * (2 * P_PIX - W * H - int(np.rint(W / 1.2 ** 7)) * int(np.rint(H / 1.2 ** 7))),   # read levels 0..6, write levels 1..7
             "k_fast": B * (P_PIX + 4 * Ccand),
             "k_harris_select": B * (4 * Ccand * 3 + 81 * Ccand * 0.5 + 8 * 8539),
@@ -427,7 +461,7 @@ def run_gpu(args):
         roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                     "traffic": traffic, "algorithmic_bytes": alg.get(dom), "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback",
                     "kernel_ms_per_step": {k: round(v[0], 4) for k, v in kern.items()},
-                    "step_algorithmic_gbs": (sum(alg_sift.values()) if FEAT == "sift128" else B * (4 * P_PIX + 12 * Ccand + 60 * N)) / (ms / args.steps * 1e-3) / 1e9}
+                    "step_algorithmic_gbs": (sum(alg_sift.values()) if FEAT in ("sift128", "akaze61") else B * (4 * P_PIX + 12 * Ccand + 60 * N)) / (ms / args.steps * 1e-3) / 1e9}
         # ---- CPU baseline (oracle port) on this host, bounded sample
         nthreads = host_threads()
         step, sample, per_frame = cpu_arm(frames, pb, nthreads, seconds_budget=3.0)
@@ -461,10 +495,10 @@ def run_gpu(args):
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32" if FEAT == "sift128" else "u8", "data": "synthetic",
+            "dtype": "u8" if FEAT == "orb32" else "f32", "data": "synthetic",
             "config": {"workload": WL["name"],
                        "frames_per_step_per_gpu": B, "pairs_per_step_per_gpu": B, "parallelism": "frames sharded, dp%d" % world,
-                       "l2": "inputs+intermediates (%.1f GB/step) larger than L2, no flush" % (B * (54e6 * W * H / 921600 if FEAT == "sift128" else 3.1e6 * W * H / 307200) / 1e9),
+                       "l2": "inputs+intermediates (%.1f GB/step) larger than L2, no flush" % (B * (54e6 * W * H / 921600 if FEAT == "sift128" else 36e6 * W * H / 307200 if FEAT == "akaze61" else 3.1e6 * W * H / 307200) / 1e9),
                        "gather": bool(world > 1 and args.gather), "gather_mode": "NCCL gather of packed results to rank 0 every step, overlapped with the next step"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": ms_e2e / args.steps, "h2d_gbs_measured": h2d_gbs, "single_frame_latency_ms": single_ms, "pipeline": "%d chunks of %d frames on 2 streams, host sync after the last step only" % (nchunks, CH)},
@@ -472,7 +506,8 @@ def run_gpu(args):
             "clocks": sampler.summary() if sampler else None,
             "roofline": roofline,
             "cpu_baseline": cpu_baseline,
-            "check": {"kps_per_frame": [int(n_host.min()), int(n_host.max())], "matches_per_pair_mean": float(nm_host.mean())},
+            "check": {"kps_per_frame": [int(n_host.min()), int(n_host.max())], "matches_per_pair_mean": float(nm_host.mean()),
+                      "matches48_per_pair_mean": float(nmb.float().mean()) if MIXED else None},
         }
         print(json.dumps(line))
     if world > 1:

@@ -20,7 +20,7 @@ DESC_ORB, DESC_AKAZE61, DESC_BRISK, DESC_SIFT128 = 0, 1, 2, 5      # include/Typ
 
 def build(force=False):
     so = os.path.join(_DIR, "libafv_oracle.so")
-    srcs = [os.path.join(_DIR, f) for f in ("afv_oracle.c", "afv_oracle_match.c", "afv_oracle_sift.c", "afv_oracle_akaze.c", "afv_oracle.h", "orb_pattern.inc")]
+    srcs = [os.path.join(_DIR, f) for f in ("afv_oracle.c", "afv_oracle_match.c", "afv_oracle_sift.c", "afv_oracle_akaze.c", "afv_oracle_batch.c", "afv_oracle.h", "orb_pattern.inc")]
     if force or not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
         subprocess.check_call(["make", "-s", "-C", _DIR, "libafv_oracle.so"])
     return so
@@ -332,3 +332,16 @@ def akaze61_extract(gray, nfeatures, nlevels=8, scale_factor=1.1892, detect_th=5
                                    _p(desc), _p(size), cap, C.byref(n), C.byref(nd))
     assert rc == 0, rc
     return kps[:n.value].copy(), desc[:n.value].copy(), size[:n.value].copy(), nd.value
+
+
+def akaze_extract_match_batch(frames, pair_a, pair_b, nfeatures=1000, nthreads=1, window=100, th_akaze=128.0, th_brisk=120.0,
+                              nnratio=0.9, check_ori=True):
+    """One bench step of the akaze61 (+ brisk48 layout) workload on the CPU (pthreads in C). Returns the total matches."""
+    frames = np.ascontiguousarray(frames, np.uint8)
+    B, h, w = frames.shape
+    pa = np.ascontiguousarray(pair_a, np.int32); pb = np.ascontiguousarray(pair_b, np.int32)
+    L = lib(); L.orc_akaze61_extract_match_batch.restype = C.c_long
+    r = L.orc_akaze61_extract_match_batch(_p(frames), B, w, h, int(nfeatures), 8, _f(1.1892), _f(5e-4), _p(pa), _p(pb), len(pa),
+                                          int(window), _f(th_akaze), _f(th_brisk), _f(nnratio), int(bool(check_ori)), int(nthreads))
+    assert r >= 0
+    return int(r)
