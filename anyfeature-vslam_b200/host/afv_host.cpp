@@ -102,18 +102,27 @@ float FeatureExtractor_orb32::GetKeypointSize(const KeyPoint& keypoint) const {
     return powf(settings->GetDetectorNominalScaleFactor(), float(GetKeypointOctave(keypoint)));
 }
 
-void FeatureExtractor_orb32::detectAndCompute(const Image& img, std::vector<KeyPoint>& keypoints, Mat& descriptors, std::vector<float>& sizes) {
+float FeatureExtractor_sift128::GetKeypointSize(const KeyPoint& keypoint) const {
+    return powf(settings->GetDetectorNominalScaleFactor(), float(GetKeypointOctave(keypoint)));
+}
+float FeatureExtractor_akaze61::GetKeypointSize(const KeyPoint& keypoint) const {
+    return powf(settings->GetDetectorNominalScaleFactor(), float(GetKeypointOctave(keypoint)));
+}
+
+// detectKeypoints + filterKeypoints + computeDescriptors + mergeKeypointLevels + computeSize of the subclass as ONE C-ABI call
+void FeatureExtractor::detectAndComputeABI(const Image& img, std::vector<KeyPoint>& keypoints, Mat& descriptors, std::vector<float>& sizes) {
     const Mat& g = img.grayImg;
-    ensureHandle(AFV_FEAT_ORB32, g.cols, g.rows, 1);
+    ensureHandle(featureId(), g.cols, g.rows, 1);
     const int cap = afv_extractor_output_cap(handle_);
+    const int dc = descCols(), dt = descType();
     keypoints.assign(cap, KeyPoint());
-    Mat d(cap, 32, afvcv::CV_8U);
+    Mat d(cap, dc, dt);
     sizes.assign(cap, 0.f);
     int n = 0;
     AFV_OK_OR_DIE(afv_extract(handle_, g.data(), g.cols, g.rows, (int)g.step(), reinterpret_cast<afv_keypoint*>(keypoints.data()), d.data(), sizes.data(), cap, &n));
     keypoints.resize(n); sizes.resize(n);
-    descriptors.create(n, 32, afvcv::CV_8U);
-    std::memcpy(descriptors.data(), d.data(), (size_t)n * 32);
+    descriptors.create(n, dc, dt);
+    std::memcpy(descriptors.data(), d.data(), (size_t)n * d.step());
 }
 
 void FeatureExtractor::extractBatch(const std::vector<const Image*>& imgs, std::vector<std::vector<KeyPoint>>& keypoints, std::vector<Mat>& descriptors,
@@ -121,18 +130,19 @@ void FeatureExtractor::extractBatch(const std::vector<const Image*>& imgs, std::
     const int B = (int)imgs.size();
     if (!B) return;
     const int w = imgs[0]->grayImg.cols, h = imgs[0]->grayImg.rows;
-    ensureHandle(AFV_FEAT_ORB32, w, h, B);
+    ensureHandle(featureId(), w, h, B);
     const int cap = afv_extractor_output_cap(handle_);
+    const size_t db = (size_t)descCols() * (descType() == afvcv::CV_32F ? 4 : 1);
     std::vector<uint8_t> gray((size_t)B * w * h);
     for (int b = 0; b < B; ++b) std::memcpy(gray.data() + (size_t)b * w * h, imgs[b]->grayImg.data(), (size_t)w * h);
-    std::vector<KeyPoint> k((size_t)B * cap); std::vector<uint8_t> d((size_t)B * cap * 32); std::vector<float> s((size_t)B * cap); std::vector<int> n(B);
+    std::vector<KeyPoint> k((size_t)B * cap); std::vector<uint8_t> d((size_t)B * cap * db); std::vector<float> s((size_t)B * cap); std::vector<int> n(B);
     AFV_OK_OR_DIE(afv_extract_batch(handle_, gray.data(), B, w, h, w, (long)w * h, reinterpret_cast<afv_keypoint*>(k.data()), d.data(), s.data(), cap, n.data()));
     keypoints.resize(B); descriptors.resize(B); sizes.resize(B);
     for (int b = 0; b < B; ++b) {
         keypoints[b].assign(k.begin() + (size_t)b * cap, k.begin() + (size_t)b * cap + n[b]);
         sizes[b].assign(s.begin() + (size_t)b * cap, s.begin() + (size_t)b * cap + n[b]);
-        descriptors[b].create(n[b], 32, afvcv::CV_8U);
-        std::memcpy(descriptors[b].data(), d.data() + (size_t)b * cap * 32, (size_t)n[b] * 32);
+        descriptors[b].create(n[b], descCols(), descType());
+        std::memcpy(descriptors[b].data(), d.data() + (size_t)b * cap * db, (size_t)n[b] * db);
     }
 }
 
@@ -146,8 +156,10 @@ std::shared_ptr<FeatureExtractor> getFeatureExtractor(const int& scaleNumFeature
     auto settings = std::make_shared<FeatureExtractorSettings>((KeypointType)id, (DescriptorType)id, yaml);
     switch (id) {
         case FEAT_ORB: return std::make_shared<FeatureExtractor_orb32>(nFeatures, settings);
+        case FEAT_SIFT128: return std::make_shared<FeatureExtractor_sift128>(nFeatures, settings);
+        case FEAT_AKAZE61: return std::make_shared<FeatureExtractor_akaze61>(nFeatures, settings);
         default:
-            std::fprintf(stderr, "getFeatureExtractor: feature '%s' has no B200 extractor yet (orb32 only)\n", feature.c_str());
+            std::fprintf(stderr, "getFeatureExtractor: feature '%s' has no B200 extractor (orb32, sift128, akaze61 are built)\n", feature.c_str());
             std::terminate();                                                         // include/Types.h:67-70 behaviour
     }
 }

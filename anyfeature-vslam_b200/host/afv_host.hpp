@@ -4,6 +4,8 @@
 //   FeatureExtractorSettings  include/FeatureExtractor.h:24-66, src/FeatureExtractor.cpp:21-56
 //   FeatureExtractor          include/FeatureExtractor.h:68-161 (operator() 6-arg / 3-arg, getters, protected virtuals)
 //   FeatureExtractor_orb32    include/Feature_orb32.h, src/Feature_orb32.cpp
+//   FeatureExtractor_sift128  include/Feature_sift128.h, src/Feature_sift128.cpp (CV_32F N x 128, angle in radians)
+//   FeatureExtractor_akaze61  include/Feature_akaze61.h, src/Feature_akaze61.cpp (CV_8U N x 61, octave := class_id)
 //   getFeatureExtractor       src/Tracking.cc:1505-1553 (factory, nfeatures clamp :1515-1520)
 //   FeatureMatcher            include/FeatureMatcher.h:36-118 (SearchForInitialization, static DescriptorDistance,
 //                             setDescriptorDistanceThresholds; TH_LOW/TH_HIGH statics)
@@ -75,6 +77,11 @@ protected:
     virtual int GetKeypointOctave(const KeyPoint& keypoint) const = 0;
     virtual float GetKeypointSize(const KeyPoint& keypoint) const = 0;
     virtual void detectAndCompute(const Image& img, std::vector<KeyPoint>& keypoints, Mat& descriptors, std::vector<float>& sizes) = 0;
+    // descriptor layout of the subclass: C-ABI feature id, row width, element type (CV_8U / CV_32F)
+    virtual int featureId() const = 0;
+    virtual int descCols() const = 0;
+    virtual int descType() const { return afvcv::CV_8U; }
+    void detectAndComputeABI(const Image& img, std::vector<KeyPoint>& keypoints, Mat& descriptors, std::vector<float>& sizes);
     afv_extractor* handle_ = nullptr;
     int handle_w_ = 0, handle_h_ = 0, handle_batch_ = 0;
     void ensureHandle(int feature_id, int w, int h, int batch);
@@ -86,7 +93,32 @@ public:
 protected:
     int GetKeypointOctave(const KeyPoint& keypoint) const override { return keypoint.octave; }
     float GetKeypointSize(const KeyPoint& keypoint) const override;
-    void detectAndCompute(const Image& img, std::vector<KeyPoint>& keypoints, Mat& descriptors, std::vector<float>& sizes) override;
+    void detectAndCompute(const Image& img, std::vector<KeyPoint>& keypoints, Mat& descriptors, std::vector<float>& sizes) override { detectAndComputeABI(img, keypoints, descriptors, sizes); }
+    int featureId() const override { return AFV_FEAT_ORB32; }
+    int descCols() const override { return 32; }
+};
+
+class FeatureExtractor_sift128 : public FeatureExtractor {           // src/Feature_sift128.cpp:9-134
+public:
+    FeatureExtractor_sift128(const int& nfeatures_, std::shared_ptr<FeatureExtractorSettings>& settings_) : FeatureExtractor(nfeatures_, settings_) {}
+protected:
+    int GetKeypointOctave(const KeyPoint& keypoint) const override { return keypoint.octave; }                       // :120-122
+    float GetKeypointSize(const KeyPoint& keypoint) const override;                                                  // :124-126
+    void detectAndCompute(const Image& img, std::vector<KeyPoint>& keypoints, Mat& descriptors, std::vector<float>& sizes) override { detectAndComputeABI(img, keypoints, descriptors, sizes); }
+    int featureId() const override { return AFV_FEAT_SIFT128; }
+    int descCols() const override { return 128; }
+    int descType() const override { return afvcv::CV_32F; }
+};
+
+class FeatureExtractor_akaze61 : public FeatureExtractor {           // src/Feature_akaze61.cpp:7-77
+public:
+    FeatureExtractor_akaze61(const int& nfeatures_, std::shared_ptr<FeatureExtractorSettings>& settings_) : FeatureExtractor(nfeatures_, settings_) {}
+protected:
+    int GetKeypointOctave(const KeyPoint& keypoint) const override { return keypoint.class_id; }                     // :63-65
+    float GetKeypointSize(const KeyPoint& keypoint) const override;                                                  // :67-69
+    void detectAndCompute(const Image& img, std::vector<KeyPoint>& keypoints, Mat& descriptors, std::vector<float>& sizes) override { detectAndComputeABI(img, keypoints, descriptors, sizes); }
+    int featureId() const override { return AFV_FEAT_AKAZE61; }
+    int descCols() const override { return 61; }
 };
 
 // Tracking::getFeatureExtractor (src/Tracking.cc:1505-1553): nfeatures scaled with resolution, clamped to [1000,2000]

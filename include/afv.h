@@ -24,7 +24,7 @@ extern "C" {
 #define AFV_ERR_NO_DEVICE   -2   /* CUDA device / driver unavailable: the product path has no CPU fallback */
 #define AFV_ERR_CUDA        -3   /* CUDA runtime error (see afv_last_error) */
 #define AFV_ERR_CAPACITY    -4   /* an internal or caller buffer capacity was exceeded (frame reported in text) */
-#define AFV_ERR_UNSUPPORTED -5   /* feature id not built in this round */
+#define AFV_ERR_UNSUPPORTED -5   /* feature id without an extractor (brisk48: ETH brisk v2 is not vendored, no oracle) */
 
 /* feature / descriptor ids == reference include/Types.h:11-45 and get_feature_id (:102-124) */
 #define AFV_FEAT_ORB32      0
@@ -43,7 +43,17 @@ typedef struct afv_extractor afv_extractor;
 
 /* Replaces the FeatureExtractor_<feat> constructor + FeatureExtractorSettings (nfeatures, numOctaves,
  * scaleFactor, detectionTh from settings/<feat>_settings.yaml).  max_batch/max_w/max_h size the device
- * arenas once (no allocation on the per-frame path). */
+ * arenas once (no allocation on the per-frame path).  Extractors built:
+ *   AFV_FEAT_ORB32   (src/Feature_orb32.cpp)   descriptors CV_8U  N x 32, pinned bit-exact to cv2 4.13.0's cv::ORB
+ *   AFV_FEAT_SIFT128 (src/Feature_sift128.cpp) descriptors CV_32F N x 128 (512-byte rows), angle in radians, class_id =
+ *                    row in the SiftGPU list; n_octaves / scale_factor only drive mnFeaturesPerLevel and computeSize
+ *                    (SiftGPU's own arguments are fixed by the reference, :13-52)
+ *   AFV_FEAT_AKAZE61 (src/Feature_akaze61.cpp) descriptors CV_8U  N x 61 (MLDB-486), octave = libAKAZE octave, class_id =
+ *                    evolution level (the reference's "octave", :63-65); omax = n_octaves/4, nsublevels = n_octaves/2,
+ *                    dthreshold = detect_th (:10-12); frame width and height must be even
+ * sift128 / akaze61 implement the published algorithms in the parameterisation the reference selects; SiftGPU / libAKAZE
+ * are not vendored by the reference, so parity with them is UNPINNED (oracle/afv_oracle_{sift,akaze}.c headers).
+ * AFV_FEAT_BRISK48 returns AFV_ERR_UNSUPPORTED. */
 int  afv_extractor_create(afv_extractor** out, int feature_id, int nfeatures, int n_octaves,
                           float scale_factor, float detect_th, int device,
                           int max_batch, int max_w, int max_h);
@@ -57,7 +67,8 @@ int  afv_extractor_levels(const afv_extractor* ex, float* scale_factors, int* fe
 
 /* FeatureExtractor::operator()(Image, keypoints, descriptors, ..., size) for ONE frame, host buffers
  * (src/FeatureExtractor.cpp:111-129).  gray: 8-bit single channel, `stride` bytes per row.
- * kps[cap], desc[cap*D] (D = 32 for orb32), kpsize[cap] (computeSize, :132-142; may be NULL). */
+ * kps[cap], desc[cap*D] (D = 32 bytes orb32, 61 bytes akaze61, 512 bytes = 128 floats sift128), kpsize[cap] (computeSize,
+ * :132-142; may be NULL). */
 int  afv_extract(afv_extractor* ex, const uint8_t* gray, int w, int h, int stride,
                  afv_keypoint* kps, void* desc, float* kpsize, int cap, int* n_out);
 
@@ -74,7 +85,10 @@ int  afv_extract_batch_device(afv_extractor* ex, const uint8_t* d_gray, int B, i
 /* Synchronises the last device batch and returns AFV_OK or AFV_ERR_CAPACITY. */
 int  afv_extractor_status(afv_extractor* ex);
 
-/* Stage taps for parity tests (device -> host copy of an intermediate of the LAST batch):
+/* Stage taps for parity tests (device -> host copy of an intermediate of the LAST batch).
+ * sift128: what = 10 Gaussian image / 11 DoG image (level = octave * 8 + index, float), 12 SiftGPU-order list after the -tc2
+ *          limit (x, y, s, o floats).  akaze61: what = 20..24 Lt / Lsmooth / Lx / Ly / Ldet of evolution level `level`,
+ *          25 Feature_Detection list (x, y, size, response, class_id floats), 26 contrast factor.  orb32:
  *   what = 0: pyramid level image (w_l*h_l bytes, tight)      1: blurred level image
  *          2: FAST+NMS candidates (uint32 x | y<<12 | score<<24, unordered)
  *          3: cv::ORB::detect-equivalent list after both retainBest culls (uint32 packed xy, float response

@@ -14,10 +14,11 @@ static bool read_pgm(const char* path, Image& im) {
     return (bool)f;
 }
 int main(int argc, char** argv) {
-    if (argc < 4) { std::fprintf(stderr, "usage: %s settings.yaml a.pgm b.pgm\n", argv[0]); return 2; }
+    if (argc < 4) { std::fprintf(stderr, "usage: %s settings.yaml a.pgm b.pgm [orb32|sift128|akaze61]\n", argv[0]); return 2; }
+    const std::string feature = argc > 4 ? argv[4] : "orb32";
     Image A, B;
     if (!read_pgm(argv[2], A) || !read_pgm(argv[3], B)) return 3;
-    auto ext = getFeatureExtractor(1, argv[1], "orb32", A.grayImg.cols, A.grayImg.rows);
+    auto ext = getFeatureExtractor(1, argv[1], feature, A.grayImg.cols, A.grayImg.rows);
     FeatureMatcher::setDescriptorDistanceThresholds(argv[1]);
     FrameView F[2];
     const Image* ims[2] = {&A, &B};
@@ -30,9 +31,9 @@ int main(int argc, char** argv) {
     for (size_t i = 0; i < prev.size(); ++i) prev[i] = F[0].mvKeysUn[i].pt;
     std::vector<int> m12;
     FeatureMatcher matcher(0.9f, true);
-    const int nm = matcher.SearchForInitialization(F[0], F[1], prev, m12, 100, DESC_ORB);
+    const int nm = matcher.SearchForInitialization(F[0], F[1], prev, m12, 100, (DescriptorType)get_feature_id(feature));
     unsigned long long h = 1469598103934665603ull;
-    for (int i = 0; i < 2; ++i) for (int r = 0; r < F[i].mDescriptors.rows; ++r) for (int c = 0; c < 32; ++c) { h ^= F[i].mDescriptors.ptr<uint8_t>(r)[c]; h *= 1099511628211ull; }
+    for (int i = 0; i < 2; ++i) for (int r = 0; r < F[i].mDescriptors.rows; ++r) for (size_t c = 0; c < F[i].mDescriptors.step(); ++c) { h ^= F[i].mDescriptors.ptr<uint8_t>(r)[c]; h *= 1099511628211ull; }
     for (int v : m12) { h ^= (unsigned)(v + 1); h *= 1099511628211ull; }
     std::printf("n0=%zu n1=%zu matches=%d levels=%d q0=%d hash=%llu\n", F[0].mvKeysUn.size(), F[1].mvKeysUn.size(), nm, ext->GetLevels(),
                 ext->GetFeaturesPerLevel()[0], h);

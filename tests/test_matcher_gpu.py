@@ -158,8 +158,9 @@ def test_empty_inputs(pkg):
     assert (b.cpu().numpy() == -1).all() and (bd.cpu().numpy() == np.finfo(np.float32).max).all()
 
 
-def test_cpp_host_mirror_matches_python_path(pkg, synth, tmp_path):
-    """FeatureExtractor_orb32::operator() + FeatureMatcher::SearchForInitialization through the C++ mirror."""
+@pytest.mark.parametrize("feature", ["orb32", "sift128", "akaze61"])
+def test_cpp_host_mirror_matches_python_path(pkg, synth, tmp_path, feature):
+    """FeatureExtractor_<feat>::operator() + FeatureMatcher::SearchForInitialization through the C++ mirror."""
     import os
     import subprocess
     import torch
@@ -172,15 +173,17 @@ def test_cpp_host_mirror_matches_python_path(pkg, synth, tmp_path):
         with open(p, "wb") as f:
             f.write(b"P5\n640 480\n255\n"); f.write(frames[i].tobytes())
         paths.append(str(p))
-    yaml = tmp_path / "orb32_settings.yaml"
-    yaml.write_text("%YAML:1.0\nFeatureExtractor.numOctaves: 8\nFeatureExtractor.scaleFactor: 1.2\nFeatureExtractor.detectionTh: 20.0\nFeatureMatcher.matchingTh: 75.0\n")
-    out = subprocess.check_output([os.path.join(root, "anyfeature-vslam_b200", "host", "host_api_test"), str(yaml)] + paths, text=True)
+    st = pkg.FEATURE_SETTINGS[feature]
+    yaml = tmp_path / ("%s_settings.yaml" % feature)
+    yaml.write_text("%%YAML:1.0\nFeatureExtractor.numOctaves: %d\nFeatureExtractor.scaleFactor: %r\nFeatureExtractor.detectionTh: %r\nFeatureMatcher.matchingTh: %r\n"
+                    % (st["n_octaves"], st["scale_factor"], st["detect_th"], st["matching_th"]))
+    out = subprocess.check_output([os.path.join(root, "anyfeature-vslam_b200", "host", "host_api_test"), str(yaml)] + paths + [feature], text=True)
     got = dict(kv.split("=") for kv in out.split())
-    ex = pkg.FeatureExtractor("orb32", nfeatures=1000, max_batch=2, max_w=640, max_h=480)
+    ex = pkg.FeatureExtractor(feature, nfeatures=1000, max_batch=2, max_w=640, max_h=480)
     k, d, s, n = ex.extract_batch(frames)
     o = ex.alloc_device_outputs(2)
     ex.extract_batch_device(torch.from_numpy(frames).cuda(), o)
-    fm = pkg.FeatureMatcher(nnratio=0.9, check_ori=True, desc_type=0, th_low=75.0)
+    fm = pkg.FeatureMatcher(nnratio=0.9, check_ori=True, desc_type=st["feature_id"], th_low=st["matching_th"])
     pa = torch.tensor([0], dtype=torch.int32, device="cuda"); pb = torch.tensor([1], dtype=torch.int32, device="cuda")
     m12, nm = fm.search_for_initialization(o[0], o[1], o[2], o[3], pa, pb, None, BOUNDS, MAXSZ, window=100)
     torch.cuda.synchronize()
@@ -191,7 +194,7 @@ def test_cpp_host_mirror_matches_python_path(pkg, synth, tmp_path):
     for v in m12[0, :int(n[0])].cpu().numpy().tolist():
         h = ((h ^ ((v + 1) & 0xffffffff)) * 1099511628211) & 0xffffffffffffffff
     assert int(got["n0"]) == int(n[0]) and int(got["n1"]) == int(n[1]) and int(got["matches"]) == int(nm[0])
-    assert int(got["levels"]) == 8 and int(got["q0"]) == 217
+    assert int(got["levels"]) == 8 and int(got["q0"]) == {"orb32": 217, "sift128": 502, "akaze61": 212}[feature]
     assert int(got["hash"]) == h
     ex.close()
 
