@@ -25,13 +25,14 @@
 #include "afv_akaze.h"
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include <vector>
 
 #define AKZ_MAX_LV 8
 #define AKZ_PI 3.14159265358979323846f
 #define AKZ_2PI 6.28318530717958647692f
-#define AKZ_LIST_CAP 8192
+#define AKZ_LIST_CAP 8192          // upper bound of the per-frame candidate list (shared memory of k_akz_select)
 
 struct AkzLevelG {
     int w, h, stride; long long istride;
@@ -54,6 +55,7 @@ struct AkzParams {
     float* okx; float* oky; uint32_t* oresp; int* oidx; unsigned short* knode; unsigned char* kquad;     // [B][key_cap]
     int* selinfo;                                      // [B][32]
     int* keep; int keep_cap; int* keepcnt; int oct_ncap;
+    int list_cap;                                      // capacity of k_akz_select's list for this geometry (<= AKZ_LIST_CAP)
 };
 
 #define AKZ_ST_CAND_OVERFLOW 1
@@ -138,15 +140,19 @@ __global__ void __launch_bounds__(256) k_akz_hist(const float* __restrict__ mag,
     for (int i = threadIdx.x; i < 304; i += 256) sh[i] = 0;
     __syncthreads();
     AKZ_PIX();
+    int nbin = -1;
     if (x >= 1 && x < w - 1 && y >= 1 && y < h - 1) {
         const float m = mag[f * ist + (long long)y * st + x];
         if (m != 0.0f) {
-            int nbin = (int)floorf(300.0f * (m / __uint_as_float(hmax[f])));
+            nbin = (int)floorf(300.0f * (m / __uint_as_float(hmax[f])));
             if (nbin == 300) nbin = 299;
-            atomicAdd(&sh[nbin], 1);
-            atomicAdd(&sh[300], 1);
         }
     }
+    // most magnitudes fall into a few low bins: one shared atomic per distinct bin per warp
+    const unsigned peers = __match_any_sync(0xffffffffu, nbin);
+    if (nbin >= 0 && (threadIdx.x & 31) == __ffs(peers) - 1) { atomicAdd(&sh[nbin], __popc(peers)); }
+    const unsigned valid = __ballot_sync(0xffffffffu, nbin >= 0);
+    if ((threadIdx.x & 31) == 0 && valid) atomicAdd(&sh[300], __popc(valid));
     __syncthreads();
     for (int i = threadIdx.x; i < 301; i += 256) if (sh[i]) atomicAdd(&hist[f * 304 + i], sh[i]);
 }
@@ -194,6 +200,64 @@ __global__ void __launch_bounds__(256) k_akz_nld(const float* __restrict__ Ld_, 
     if (y + 1 < h) ypos = (c0 + c[st]) * (Ld[st] - l0);
     if (y > 0) yneg = (c[-st] + c0) * (l0 - Ld[-st]);
     out[p] = l0 + (0.5f * tau) * ((xpos - xneg) + (ypos - yneg));
+}
+
+// ------------------------------------------------------------------------------------------------------
+// One whole FED cycle (NS explicit steps) of a level in ONE kernel: the Lt / conductivity footprint of a tile plus a halo of
+// NS cells is staged in shared memory once and the steps run back to back on a region that shrinks by one cell per step
+// (temporal blocking), so HBM sees one read of Lt and of the flow and one write instead of NS x (2 reads + 1 write).
+// Per-cell arithmetic and the one-sided image borders are those of k_akz_nld.
+// ------------------------------------------------------------------------------------------------------
+#define FED_SW 128
+#define FED_SH 48
+struct AkzTaus { float t[16]; };
+__global__ void __launch_bounds__(256) k_akz_fed(const float* __restrict__ Lin, const float* __restrict__ flow, float* __restrict__ Lout,
+                                                 int w, int h, int st, long long ist, int NS, const __grid_constant__ AkzTaus taus) {
+    extern __shared__ __align__(16) float fsm[];
+    float* A = fsm; float* Bf = fsm + FED_SH * FED_SW; float* C = Bf + FED_SH * FED_SW;
+    const int tid = threadIdx.x, lane = tid & 31, wrow = tid >> 5, f = blockIdx.z;
+    const int ow = FED_SW - 2 * NS, oh = FED_SH - 2 * NS;
+    const int gx0 = blockIdx.x * ow - NS, gy0 = blockIdx.y * oh - NS;
+    const float* Lf = Lin + f * ist; const float* Cf = flow + f * ist;
+    for (int i = tid; i < FED_SH * FED_SW; i += 256) {
+        const int r = i / FED_SW, c = i - r * FED_SW;
+        const int gy = gy0 + r, gx = gx0 + c;
+        const bool in = gx >= 0 && gx < w && gy >= 0 && gy < h;
+        A[i] = in ? Lf[(long long)gy * st + gx] : 0.f;
+        C[i] = in ? Cf[(long long)gy * st + gx] : 0.f;
+    }
+    __syncthreads();
+    float* src = A; float* dst = Bf;
+    for (int j = 0; j < NS; ++j) {
+        const float ht = 0.5f * taus.t[j];
+        for (int r = j + 1 + wrow; r < FED_SH - 1 - j; r += 8) {
+            const int gy = gy0 + r;
+            if (gy < 0 || gy >= h) continue;
+            for (int c = j + 1 + lane; c < FED_SW - 1 - j; c += 32) {
+                const int gx = gx0 + c;
+                if (gx < 0 || gx >= w) continue;
+                const int p = r * FED_SW + c;
+                const float l0 = src[p], c0 = C[p];
+                float xpos = 0.f, xneg = 0.f, ypos = 0.f, yneg = 0.f;
+                if (gx + 1 < w) xpos = (c0 + C[p + 1]) * (src[p + 1] - l0);
+                if (gx > 0) xneg = (C[p - 1] + c0) * (l0 - src[p - 1]);
+                if (gy + 1 < h) ypos = (c0 + C[p + FED_SW]) * (src[p + FED_SW] - l0);
+                if (gy > 0) yneg = (C[p - FED_SW] + c0) * (l0 - src[p - FED_SW]);
+                dst[p] = l0 + ht * ((xpos - xneg) + (ypos - yneg));
+            }
+        }
+        __syncthreads();
+        float* t = src; src = dst; dst = t;
+    }
+    float* Of = Lout + f * ist;
+    for (int r = NS + wrow; r < FED_SH - NS; r += 8) {
+        const int gy = gy0 + r;
+        if (gy >= h) continue;
+        for (int c = NS + lane; c < FED_SW - NS; c += 32) {
+            const int gx = gx0 + c;
+            if (gx < w) Of[(long long)gy * st + gx] = src[r * FED_SW + c];
+        }
+    }
 }
 
 // scaled Scharr value at (x, y): dir 0 = d/dx, 1 = d/dy (row pass then column pass of sepFilter2D, evaluated directly)
@@ -284,11 +348,12 @@ __global__ void __launch_bounds__(512) k_akz_sort(const __grid_constant__ AkzPar
 // ------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_akz_select(const __grid_constant__ AkzParams P) {
     extern __shared__ __align__(16) unsigned char sraw[];
+    const int LC = P.list_cap;
     float* ax = reinterpret_cast<float*>(sraw);
-    float* ay = ax + AKZ_LIST_CAP;
-    float* ar = ay + AKZ_LIST_CAP;
-    unsigned char* ac = reinterpret_cast<unsigned char*>(ar + AKZ_LIST_CAP);
-    unsigned char* aflag = ac + AKZ_LIST_CAP;
+    float* ay = ax + LC;
+    float* ar = ay + LC;
+    unsigned char* ac = reinterpret_cast<unsigned char*>(ar + LC);
+    unsigned char* aflag = ac + LC;
     __shared__ int s_first[2];
     __shared__ int lvcnt[16], lvoff[16], lvrun[16], wcnt[8][16];
     __shared__ int s_total;
@@ -324,9 +389,9 @@ __global__ void __launch_bounds__(256) k_akz_select(const __grid_constant__ AkzP
             if (tid == 0) {
                 s_first[it & 1] = 0x7fffffff;
                 if (replace) { ax[first] = px; ay[first] = py; ar[first] = v; ac[first] = (unsigned char)i; }
-                else if (append && n < AKZ_LIST_CAP) { ax[n] = px; ay[n] = py; ar[n] = v; ac[n] = (unsigned char)i; }
+                else if (append && n < LC) { ax[n] = px; ay[n] = py; ar[n] = v; ac[n] = (unsigned char)i; }
             }
-            if (append) { if (n < AKZ_LIST_CAP) ++n; else overflow = true; }
+            if (append) { if (n < LC) ++n; else overflow = true; }
             // the next iteration uses the other s_first slot; the barrier after its scan orders these writes
             __syncthreads();
         }
@@ -577,6 +642,7 @@ struct AfvAkaze {
     uint2* cand[AKZ_MAX_LV]; uint2* srt[AKZ_MAX_LV]; int cand_cap[AKZ_MAX_LV];
     float* scr[4];                      // full-resolution scratch images [B]
     uint8_t* gray_stage; int* h_status;
+    int unfused_fed;                    // AFV_AKAZE_UNFUSED_FED=1: one k_akz_nld launch per FED step (A/B check of k_akz_fed)
     size_t img_floats;                  // floats per full-resolution frame image (max geometry)
 };
 
@@ -640,6 +706,7 @@ int afv_akaze_create(AfvAkaze** out, int nfeatures, int nlevels, float scale_fac
     s->nfeatures = nfeatures; s->nlevels = nlevels; s->scale_factor = scale_factor; s->detect_th = detect_th;
     s->max_batch = max_batch; s->max_w = max_w; s->max_h = max_h; s->omax = omax; s->nsub = nsub;
     s->gray_stage = nullptr; s->h_status = nullptr;
+    { const char* e = getenv("AFV_AKAZE_UNFUSED_FED"); s->unfused_fed = e && e[0] == '1'; }
     memset(&s->taps16, 0, sizeof(AfvBlurTaps)); memset(&s->taps10, 0, sizeof(AfvBlurTaps));
     if (akz_gauss_taps(1.6f, s->taps16.t) != 4 || akz_gauss_taps(1.0f, s->taps10.t) != 2) { afv_set_error("akaze61: internal: unexpected blur radius"); delete s; return AFV_ERR_INVALID; }
     {
@@ -727,6 +794,7 @@ int afv_akaze_create(AfvAkaze** out, int nfeatures, int nlevels, float scale_fac
     if (rc == AFV_OK) {
         cudaError_t e = cudaMallocHost((void**)&s->h_status, sizeof(int) * B);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(k_akz_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 8192);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_akz_fed, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * FED_SH * FED_SW * (int)sizeof(float));
         if (e == cudaSuccess) e = cudaFuncSetAttribute(k_akz_select, cudaFuncAttributeMaxDynamicSharedMemorySize, 14 * AKZ_LIST_CAP);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(k_akz_octree, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)oct_work_bytes(P.oct_ncap));
         if (e != cudaSuccess) { afv_set_error("akaze61: setup failed: %s", cudaGetErrorString(e)); rc = AFV_ERR_CUDA; }
@@ -767,6 +835,9 @@ static int akz_configure(AfvAkaze* s, int w, int h, int B) {
         }
     }
     P.nl = n;
+    // list capacity: one entry per ~64 pixels of the input is an order of magnitude above what textured frames produce
+    // (640x480: ~2000 entries); smaller lists let several k_akz_select CTAs share an SM
+    { int lc = 1024; while (lc < (w * h) / 96 && lc < AKZ_LIST_CAP) lc <<= 1; P.list_cap = lc < P.key_cap ? lc : P.key_cap; }
     for (int i = 1; i < n; ++i) {
         const float e1 = 0.5f * (P.lv[i].esigma * P.lv[i].esigma), e0 = 0.5f * (P.lv[i - 1].esigma * P.lv[i - 1].esigma);
         float tau[64];
@@ -809,6 +880,13 @@ int afv_akaze_run(AfvAkaze* s, const uint8_t* d_gray, int B, int w, int h, int s
         }
         afv_blur_launch<2, 0>(cur, L.stride, L.istride, L.Lsm, nullptr, L.w, L.h, L.stride, L.istride, s->taps10, B, st); ++g_afv_launches;
         k_akz_flow<<<AKZ_GRID(L, B), 256, 0, st>>>(L.Lsm, s->scr[2], L.w, L.h, L.stride, L.istride, P.kcontrast, L.octave); ++g_afv_launches;
+        if (L.nsteps >= 1 && L.nsteps <= 12 && !s->unfused_fed) {
+            AkzTaus taus; memset(&taus, 0, sizeof(taus));
+            for (int j = 0; j < L.nsteps; ++j) taus.t[j] = L.tau[j];
+            const int ow = FED_SW - 2 * L.nsteps, oh = FED_SH - 2 * L.nsteps;
+            k_akz_fed<<<dim3((L.w + ow - 1) / ow, (L.h + oh - 1) / oh, B), 256, 3 * FED_SH * FED_SW * sizeof(float), st>>>(
+                cur, s->scr[2], L.Lt, L.w, L.h, L.stride, L.istride, L.nsteps, taus); ++g_afv_launches;
+        } else
         for (int j = 0; j < L.nsteps; ++j) {
             float* dst = j == L.nsteps - 1 ? L.Lt : (cur == s->scr[0] ? s->scr[1] : s->scr[0]);
             k_akz_nld<<<AKZ_GRID(L, B), 256, 0, st>>>(cur, s->scr[2], dst, L.w, L.h, L.stride, L.istride, L.tau[j]); ++g_afv_launches;
@@ -827,7 +905,7 @@ int afv_akaze_run(AfvAkaze* s, const uint8_t* d_gray, int B, int w, int h, int s
         k_akz_extrema<<<AKZ_GRID(L, B), 256, 0, st>>>(P, i); ++g_afv_launches;
     } }
     { AfvProfScope ps("k_akz_sort", st); k_akz_sort<<<dim3(P.nl, B), 512, 8 * 8192, st>>>(P); ++g_afv_launches; }
-    { AfvProfScope ps("k_akz_select", st); k_akz_select<<<B, 256, 14 * AKZ_LIST_CAP, st>>>(P); ++g_afv_launches; }
+    { AfvProfScope ps("k_akz_select", st); k_akz_select<<<B, 256, 14 * (size_t)P.list_cap, st>>>(P); ++g_afv_launches; }
     { AfvProfScope ps("k_akz_octree", st); k_akz_octree<<<dim3(P.nlevels, B), 256, oct_work_bytes(P.oct_ncap), st>>>(P); ++g_afv_launches; }
     { AfvProfScope ps("k_akz_describe", st);
       k_akz_describe<<<dim3((cap + 7) / 8, B), 256, 0, st>>>(P, d_kps, d_desc, d_kpsize, d_n_out); ++g_afv_launches; }

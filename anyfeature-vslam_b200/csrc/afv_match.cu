@@ -272,8 +272,10 @@ __device__ __forceinline__ void three_maxima(const int* cnt, int& ind1, int& ind
 #define SFL_THREADS 256
 #define SFR_WARPS 2
 #define SFR_QSTAGE 512
+#define SFR_RING 8            // candidate lists in flight per resolver warp (cp.async ring in shared memory)
+#define SFR_SLOT 256          // entries per ring slot; longer lists read their tail from global memory
 __host__ __device__ inline size_t sfl_base_bytes(int cap) { return (((size_t)cap * (4 * 2 + 2 * 4)) + 15) & ~(size_t)15; }
-__host__ __device__ inline size_t sfr_warp_bytes(int cap) { return ((((size_t)cap * (4 * 2 + 2 * 3 + 1)) + 15) & ~(size_t)15) + (size_t)SFR_QSTAGE * 16; }
+__host__ __device__ inline size_t sfr_warp_bytes(int cap) { return ((((size_t)cap * (4 * 2 + 2 * 3 + 1)) + 15) & ~(size_t)15) + (size_t)SFR_QSTAGE * 16 + (size_t)SFR_RING * SFR_SLOT * 8; }
 
 struct SfiQuery { float x, y; int c0, c1, r0, r1; bool ok; };
 struct SfiQMeta { int i1, off, cnt; float angle; };         // per query, written by k_sfi_lists
@@ -447,7 +449,8 @@ __global__ void __launch_bounds__(SFR_WARPS * 32) k_sfi_resolve(int desc_type, i
     unsigned short* m21 = reinterpret_cast<unsigned short*>(tang + cap);
     unsigned short* m12 = m21 + cap; unsigned short* tcell = m12 + cap;
     signed char* hbin = reinterpret_cast<signed char*>(tcell + cap);
-    SfiQMeta* qms = reinterpret_cast<SfiQMeta*>(base + sfr_warp_bytes(cap) - (size_t)SFR_QSTAGE * 16);
+    SfiQMeta* qms = reinterpret_cast<SfiQMeta*>(base + sfr_warp_bytes(cap) - (size_t)SFR_QSTAGE * 16 - (size_t)SFR_RING * SFR_SLOT * 8);
+    unsigned char* ring = base + sfr_warp_bytes(cap) - (size_t)SFR_RING * SFR_SLOT * 8;       // [SFR_RING][SFR_SLOT] u32 (Hamming) / u64 (L2)
     __shared__ int hist_all[SFR_WARPS][AFV_HISTO_LENGTH + 2];
     int* hist = hist_all[wid];
     const unsigned short NONE16 = 0xffff;
@@ -476,45 +479,53 @@ __global__ void __launch_bounds__(SFR_WARPS * 32) k_sfi_resolve(int desc_type, i
     __syncwarp();
     int nm = 0;                                                    // lane 0's copy is authoritative
 
-    // stage the query metadata (16 B each) so the sequential loop never waits on it, and prefetch the first 128
-    // candidates of query qi+1 while query qi is resolved
+    // stage the query metadata (16 B each) so the sequential loop never waits on it
     for (int i = lane; i < min(nq, SFR_QSTAGE); i += 32) qms[i] = qm[i];
     __syncwarp();
-    auto load_keys = [&](const SfiQMeta& m, int j0, unsigned long long* key) {
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const int j = j0 + u * 32 + lane;
-            key[u] = KEY_NONE;
-            if (m.off >= 0 && j < m.cnt) {
-                if (BINARY) {
-                    const uint32_t e = reinterpret_cast<const uint32_t*>(pool_v)[(long long)p * pool_cap + m.off + j];
-                    key[u] = ((unsigned long long)__float_as_uint((float)(e >> 20)) << 32) | (e & 0xfffffu);
-                } else key[u] = reinterpret_cast<const unsigned long long*>(pool_v)[(long long)p * pool_cap + m.off + j];
+    // The sequential loop must never wait on global memory: the candidate lists of the next SFR_RING-1 queries are in
+    // flight as cp.async copies into a shared-memory ring (one commit group per query) while the current one is reduced.
+    constexpr int ESZ = BINARY ? 4 : 8;
+    auto issue = [&](int qn) {
+        if (qn < nq) {
+            const SfiQMeta m = qn < SFR_QSTAGE ? qms[qn] : qm[qn];
+            if (m.off >= 0) {
+                const int c = min(m.cnt, SFR_SLOT);
+                const unsigned char* src = reinterpret_cast<const unsigned char*>(pool_v) + ((long long)p * pool_cap + m.off) * ESZ;
+                unsigned char* dst = ring + (size_t)(qn % SFR_RING) * SFR_SLOT * ESZ;
+                for (int j = lane; j < c; j += 32) {
+                    const unsigned sa = (unsigned)__cvta_generic_to_shared(dst + (size_t)j * ESZ);
+                    if (BINARY) asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"(sa), "l"(src + (size_t)j * 4) : "memory");
+                    else asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" :: "r"(sa), "l"(src + (size_t)j * 8) : "memory");
+                }
             }
         }
+        asm volatile("cp.async.commit_group;" ::: "memory");          // one group per query, empty ones included
     };
-    unsigned long long knext[4] = {KEY_NONE, KEY_NONE, KEY_NONE, KEY_NONE};
-    if (nq > 0) { const SfiQMeta m0 = qms[0]; load_keys(m0, 0, knext); }
+    auto entry_key = [&](const SfiQMeta& m, int qi_, int j) -> unsigned long long {
+        if (BINARY) {
+            const uint32_t e = j < SFR_SLOT ? reinterpret_cast<const uint32_t*>(ring + (size_t)(qi_ % SFR_RING) * SFR_SLOT * 4)[j]
+                                            : reinterpret_cast<const uint32_t*>(pool_v)[(long long)p * pool_cap + m.off + j];
+            return ((unsigned long long)__float_as_uint((float)(e >> 20)) << 32) | (e & 0xfffffu);
+        }
+        return j < SFR_SLOT ? reinterpret_cast<const unsigned long long*>(ring + (size_t)(qi_ % SFR_RING) * SFR_SLOT * 8)[j]
+                            : reinterpret_cast<const unsigned long long*>(pool_v)[(long long)p * pool_cap + m.off + j];
+    };
+    for (int k = 0; k < SFR_RING - 1; ++k) issue(k);
     for (int qi = 0; qi < nq; ++qi) {
         const SfiQMeta q = qi < SFR_QSTAGE ? qms[qi] : qm[qi];
-        unsigned long long key[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) key[u] = knext[u];
-        if (qi + 1 < nq) { const SfiQMeta mn = (qi + 1) < SFR_QSTAGE ? qms[qi + 1] : qm[qi + 1]; load_keys(mn, 0, knext); }
+        issue(qi + SFR_RING - 1);                                      // reuses the slot of query qi-1 (finished)
+        asm volatile("cp.async.wait_group %0;" :: "n"(SFR_RING - 1) : "memory");
+        __syncwarp();
         if (q.cnt == 0) continue;
         Top2 t; t.k1 = t.k2 = KEY_NONE;
         if (q.off >= 0) {
-            for (int j0 = 0; j0 < q.cnt; j0 += 128) {
-                if (j0 > 0) load_keys(q, j0, key);
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    if (key[u] == KEY_NONE) continue;
-                    const int i2 = (int)((uint32_t)key[u] & 0xfffffu);
-                    const float dist = key_dist(key[u]);
-                    if (matched[i2] <= dist) continue;              // :511-512
-                    const unsigned short cc = tcell[i2];
-                    top2_push(t, make_key(dist, ((uint32_t)(cc >> 8) << 26) | ((uint32_t)(cc & 0xff) << 20) | (uint32_t)i2));
-                }
+            for (int j = lane; j < q.cnt; j += 32) {
+                const unsigned long long key = entry_key(q, qi, j);
+                const int i2 = (int)((uint32_t)key & 0xfffffu);
+                const float dist = key_dist(key);
+                if (matched[i2] <= dist) continue;                  // :511-512
+                const unsigned short cc = tcell[i2];
+                top2_push(t, make_key(dist, ((uint32_t)(cc >> 8) << 26) | ((uint32_t)(cc & 0xff) << 20) | (uint32_t)i2));
             }
         } else {
             // exact fallback (candidate pool exhausted): rescan every train keypoint with the same candidate definition
