@@ -272,10 +272,8 @@ __device__ __forceinline__ void three_maxima(const int* cnt, int& ind1, int& ind
 #define SFL_THREADS 256
 #define SFR_WARPS 2
 #define SFR_QSTAGE 512
-#define SFR_RING 8            // candidate lists in flight per resolver warp (cp.async ring in shared memory)
-#define SFR_SLOT 256          // entries per ring slot; longer lists read their tail from global memory
 __host__ __device__ inline size_t sfl_base_bytes(int cap) { return (((size_t)cap * (4 * 2 + 2 * 4)) + 15) & ~(size_t)15; }
-__host__ __device__ inline size_t sfr_warp_bytes(int cap) { return ((((size_t)cap * (4 * 2 + 2 * 3 + 1)) + 15) & ~(size_t)15) + (size_t)SFR_QSTAGE * 16 + (size_t)SFR_RING * SFR_SLOT * 8; }
+
 
 struct SfiQuery { float x, y; int c0, c1, r0, r1; bool ok; };
 struct SfiQMeta { int i1, off, cnt; float angle; };         // per query, written by k_sfi_lists
@@ -432,8 +430,24 @@ __global__ void __launch_bounds__(SFL_THREADS) k_sfi_lists(int desc_type, int D,
     }
 }
 
+// k_sfi_resolve, v5: one CTA (8 warps) per frame pair.  What the sequential semantics really need per query is the first
+// two candidates, in (distance, reference enumeration order), that are not masked by the matching state (:511-512).  The
+// state-INDEPENDENT part of that -- the sorted order itself -- is produced ahead of the sequential loop: for a block of
+// SFR_QB queries all 8 warps extract the exact K smallest keys of each query's candidate list (K rounds of warp-min over
+// the list held in registers).  Warp 0 then walks the block in query order: K lanes test their entry against the state,
+// a ballot picks the first two survivors, lane 0 applies acceptance / stealing / histogram.  If fewer than two of the K
+// survive and the list is longer than K, that query falls back to the full scan (exact).  The sequential chain per query
+// drops from ~350 dependent instructions (list scan + 64-bit warp reduction) to ~50.
+#define SFR_THREADS 256
+#define SFR_QB 64            // queries per block (phase 1 parallel, phase 2 sequential)
+#define SFR_K 8              // sorted prefix length per query
+#define SFR_LMAX 256         // lists longer than this skip the prefix (full scan in phase 2)
+__host__ __device__ inline size_t sfr_cta_bytes(int cap) {
+    return ((((size_t)cap * (4 * 2 + 2 * 3 + 1)) + 15) & ~(size_t)15) + (size_t)SFR_QSTAGE * 16 + (size_t)SFR_QB * SFR_K * 8 + (size_t)SFR_QB * 4;
+}
+
 template <bool BINARY>
-__global__ void __launch_bounds__(SFR_WARPS * 32) k_sfi_resolve(int desc_type, int D,
+__global__ void __launch_bounds__(SFR_THREADS) k_sfi_resolve(int desc_type, int D,
         const afv_keypoint* __restrict__ kps, const uint8_t* __restrict__ desc, const float* __restrict__ kpsize,
         const int* __restrict__ n_arr, int cap, const int* __restrict__ pair_a, const int* __restrict__ pair_b, int P,
         float minX, float minY, float invW, float invH, float max_kpt_size,
@@ -441,18 +455,18 @@ __global__ void __launch_bounds__(SFR_WARPS * 32) k_sfi_resolve(int desc_type, i
         const void* __restrict__ pool_v, int pool_cap, const SfiQMeta* __restrict__ qmeta, const int* __restrict__ nq_arr,
         int* __restrict__ matches12, int* __restrict__ nmatches) {
     extern __shared__ __align__(16) unsigned char sm[];
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const int p = blockIdx.x * SFR_WARPS + wid;
-    if (p >= P) return;                                            // whole warp exits; no block-wide barriers below
-    unsigned char* base = sm + (size_t)wid * sfr_warp_bytes(cap);
-    float* matched = reinterpret_cast<float*>(base); float* tang = matched + cap;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int p = blockIdx.x;
+    float* matched = reinterpret_cast<float*>(sm); float* tang = matched + cap;
     unsigned short* m21 = reinterpret_cast<unsigned short*>(tang + cap);
     unsigned short* m12 = m21 + cap; unsigned short* tcell = m12 + cap;
     signed char* hbin = reinterpret_cast<signed char*>(tcell + cap);
-    SfiQMeta* qms = reinterpret_cast<SfiQMeta*>(base + sfr_warp_bytes(cap) - (size_t)SFR_QSTAGE * 16 - (size_t)SFR_RING * SFR_SLOT * 8);
-    unsigned char* ring = base + sfr_warp_bytes(cap) - (size_t)SFR_RING * SFR_SLOT * 8;       // [SFR_RING][SFR_SLOT] u32 (Hamming) / u64 (L2)
-    __shared__ int hist_all[SFR_WARPS][AFV_HISTO_LENGTH + 2];
-    int* hist = hist_all[wid];
+    unsigned char* tail = sm + ((((size_t)cap * (4 * 2 + 2 * 3 + 1)) + 15) & ~(size_t)15);
+    SfiQMeta* qms = reinterpret_cast<SfiQMeta*>(tail);
+    unsigned long long* topk = reinterpret_cast<unsigned long long*>(tail + (size_t)SFR_QSTAGE * 16);      // [SFR_QB][SFR_K]
+    int* tflag = reinterpret_cast<int*>(tail + (size_t)SFR_QSTAGE * 16 + (size_t)SFR_QB * SFR_K * 8);       // [SFR_QB] 1 = prefix valid
+    __shared__ int hist[AFV_HISTO_LENGTH + 2];
+    __shared__ int s_nm;
     const unsigned short NONE16 = 0xffff;
 
     const int fa = pair_a[p], fb = pair_b[p];
@@ -467,112 +481,140 @@ __global__ void __launch_bounds__(SFR_WARPS * 32) k_sfi_resolve(int desc_type, i
     const SfiQMeta* qm = qmeta + (long long)p * cap;
     const int nq = nq_arr[p];
 
-    for (int i = lane; i < n2; i += 32) {
+    for (int i = tid; i < n2; i += SFR_THREADS) {
         matched[i] = FLT_MAX; m21[i] = NONE16; tang[i] = k2[i].angle;
         const float sz = size2[i];
         const int c = grid_cell(k2[i].x, k2[i].y, minX, minY, invW, invH);
         const bool ok = c >= 0 && !(sz < 0.0f) && !(sz > max_kpt_size);
         tcell[i] = ok ? (unsigned short)(((c / AFV_GRID_ROWS) << 8) | (c % AFV_GRID_ROWS)) : NONE16;
     }
-    for (int i = lane; i < n1; i += 32) { m12[i] = NONE16; hbin[i] = -1; }
-    if (lane < AFV_HISTO_LENGTH) hist[lane] = 0;
-    __syncwarp();
-    int nm = 0;                                                    // lane 0's copy is authoritative
+    for (int i = tid; i < n1; i += SFR_THREADS) { m12[i] = NONE16; hbin[i] = -1; }
+    if (tid < AFV_HISTO_LENGTH) hist[tid] = 0;
+    for (int i = tid; i < min(nq, SFR_QSTAGE); i += SFR_THREADS) qms[i] = qm[i];
+    __syncthreads();
+    int nm = 0;                                                    // thread 0's copy is authoritative
 
-    // stage the query metadata (16 B each) so the sequential loop never waits on it
-    for (int i = lane; i < min(nq, SFR_QSTAGE); i += 32) qms[i] = qm[i];
-    __syncwarp();
-    // The sequential loop must never wait on global memory: the candidate lists of the next SFR_RING-1 queries are in
-    // flight as cp.async copies into a shared-memory ring (one commit group per query) while the current one is reduced.
-    constexpr int ESZ = BINARY ? 4 : 8;
-    auto issue = [&](int qn) {
-        if (qn < nq) {
-            const SfiQMeta m = qn < SFR_QSTAGE ? qms[qn] : qm[qn];
-            if (m.off >= 0) {
-                const int c = min(m.cnt, SFR_SLOT);
-                const unsigned char* src = reinterpret_cast<const unsigned char*>(pool_v) + ((long long)p * pool_cap + m.off) * ESZ;
-                unsigned char* dst = ring + (size_t)(qn % SFR_RING) * SFR_SLOT * ESZ;
-                for (int j = lane; j < c; j += 32) {
-                    const unsigned sa = (unsigned)__cvta_generic_to_shared(dst + (size_t)j * ESZ);
-                    if (BINARY) asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"(sa), "l"(src + (size_t)j * 4) : "memory");
-                    else asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" :: "r"(sa), "l"(src + (size_t)j * 8) : "memory");
+    auto pool_key = [&](const SfiQMeta& m, int j) -> unsigned long long {          // candidate j of a query as a (distance, order) key
+        unsigned long long k;
+        if (BINARY) {
+            const uint32_t e = reinterpret_cast<const uint32_t*>(pool_v)[(long long)p * pool_cap + m.off + j];
+            k = ((unsigned long long)__float_as_uint((float)(e >> 20)) << 32) | (e & 0xfffffu);
+        } else k = reinterpret_cast<const unsigned long long*>(pool_v)[(long long)p * pool_cap + m.off + j];
+        const int i2 = (int)((uint32_t)k & 0xfffffu);
+        const unsigned short cc = tcell[i2];
+        return (k & 0xffffffff00000000ull) | ((uint32_t)(cc >> 8) << 26) | ((uint32_t)(cc & 0xff) << 20) | (uint32_t)i2;
+    };
+
+    for (int qb = 0; qb < nq; qb += SFR_QB) {
+        const int nb = min(SFR_QB, nq - qb);
+        // ---- phase 1 (all warps): exact sorted prefix of every query of the block
+        for (int s = wid; s < nb; s += SFR_THREADS / 32) {
+            const int qi = qb + s;
+            const SfiQMeta m = qi < SFR_QSTAGE ? qms[qi] : qm[qi];
+            const bool ok = m.off >= 0 && m.cnt > 0 && m.cnt <= SFR_LMAX;
+            if (ok) {
+                unsigned long long key[SFR_LMAX / 32];
+#pragma unroll
+                for (int u = 0; u < SFR_LMAX / 32; ++u) { const int j = u * 32 + lane; key[u] = j < m.cnt ? pool_key(m, j) : KEY_NONE; }
+                for (int r = 0; r < SFR_K; ++r) {
+                    unsigned long long lmin = key[0];
+#pragma unroll
+                    for (int u = 1; u < SFR_LMAX / 32; ++u) lmin = key[u] < lmin ? key[u] : lmin;
+                    unsigned long long g = lmin;
+#pragma unroll
+                    for (int o = 16; o; o >>= 1) { const unsigned long long t = __shfl_xor_sync(0xffffffffu, g, o); g = t < g ? t : g; }
+                    if (lane == 0) topk[s * SFR_K + r] = g;
+                    if (g == KEY_NONE) { if (lane == 0) for (int r2 = r + 1; r2 < SFR_K; ++r2) topk[s * SFR_K + r2] = KEY_NONE; break; }
+#pragma unroll
+                    for (int u = 0; u < SFR_LMAX / 32; ++u) if (key[u] == g) key[u] = KEY_NONE;     // keys are unique (index bits)
                 }
             }
+            if (lane == 0) tflag[s] = ok ? 1 : 0;
         }
-        asm volatile("cp.async.commit_group;" ::: "memory");          // one group per query, empty ones included
-    };
-    auto entry_key = [&](const SfiQMeta& m, int qi_, int j) -> unsigned long long {
-        if (BINARY) {
-            const uint32_t e = j < SFR_SLOT ? reinterpret_cast<const uint32_t*>(ring + (size_t)(qi_ % SFR_RING) * SFR_SLOT * 4)[j]
-                                            : reinterpret_cast<const uint32_t*>(pool_v)[(long long)p * pool_cap + m.off + j];
-            return ((unsigned long long)__float_as_uint((float)(e >> 20)) << 32) | (e & 0xfffffu);
-        }
-        return j < SFR_SLOT ? reinterpret_cast<const unsigned long long*>(ring + (size_t)(qi_ % SFR_RING) * SFR_SLOT * 8)[j]
-                            : reinterpret_cast<const unsigned long long*>(pool_v)[(long long)p * pool_cap + m.off + j];
-    };
-    for (int k = 0; k < SFR_RING - 1; ++k) issue(k);
-    for (int qi = 0; qi < nq; ++qi) {
-        const SfiQMeta q = qi < SFR_QSTAGE ? qms[qi] : qm[qi];
-        issue(qi + SFR_RING - 1);                                      // reuses the slot of query qi-1 (finished)
-        asm volatile("cp.async.wait_group %0;" :: "n"(SFR_RING - 1) : "memory");
-        __syncwarp();
-        if (q.cnt == 0) continue;
-        Top2 t; t.k1 = t.k2 = KEY_NONE;
-        if (q.off >= 0) {
-            for (int j = lane; j < q.cnt; j += 32) {
-                const unsigned long long key = entry_key(q, qi, j);
-                const int i2 = (int)((uint32_t)key & 0xfffffu);
-                const float dist = key_dist(key);
-                if (matched[i2] <= dist) continue;                  // :511-512
-                const unsigned short cc = tcell[i2];
-                top2_push(t, make_key(dist, ((uint32_t)(cc >> 8) << 26) | ((uint32_t)(cc & 0xff) << 20) | (uint32_t)i2));
+        __syncthreads();
+        // ---- phase 2 (warp 0): the reference's sequential loop over the block
+        if (wid == 0) {
+            for (int s = 0; s < nb; ++s) {
+                const int qi = qb + s;
+                const SfiQMeta q = qi < SFR_QSTAGE ? qms[qi] : qm[qi];
+                if (q.cnt == 0) continue;
+                unsigned long long b1 = KEY_NONE, b2 = KEY_NONE;
+                bool done = false;
+                if (tflag[s]) {
+                    unsigned long long key = lane < SFR_K ? topk[s * SFR_K + lane] : KEY_NONE;
+                    bool unf = false;
+                    if (key != KEY_NONE) { const int i2 = (int)((uint32_t)key & 0xfffffu); unf = !(matched[i2] <= key_dist(key)); }   // :511-512
+                    unsigned msk = __ballot_sync(0xffffffffu, unf);
+                    if (__popc(msk) >= 2 || q.cnt <= SFR_K) {
+                        if (msk) { const int l1 = __ffs(msk) - 1; b1 = __shfl_sync(0xffffffffu, key, l1); msk &= msk - 1; }
+                        if (msk) { const int l2 = __ffs(msk) - 1; b2 = __shfl_sync(0xffffffffu, key, l2); }
+                        done = true;
+                    }
+                }
+                if (!done) {
+                    Top2 t; t.k1 = t.k2 = KEY_NONE;
+                    if (q.off >= 0) {
+                        for (int j = lane; j < q.cnt; j += 32) {
+                            const unsigned long long key = pool_key(q, j);
+                            if (matched[(int)((uint32_t)key & 0xfffffu)] <= key_dist(key)) continue;                // :511-512
+                            top2_push(t, key);
+                        }
+                    } else {
+                        // exact fallback (candidate pool exhausted): rescan every train keypoint with the same candidate definition
+                        SfiQuery w;
+                        w.x = pm ? pm[2 * q.i1] : k1[q.i1].x; w.y = pm ? pm[2 * q.i1 + 1] : k1[q.i1].y;
+                        w.ok = window_cells(w.x, w.y, window, minX, minY, invW, invH, w.c0, w.c1, w.r0, w.r1);
+                        for (int i2 = lane; w.ok && i2 < n2; i2 += 32) {
+                            const unsigned short cc = tcell[i2];
+                            if (cc == NONE16 || !sfi_in_window(w, cc >> 8, cc & 0xff, k2[i2].x, k2[i2].y, window)) continue;
+                            const float dist = desc_distance(desc_type, d1 + (long long)q.i1 * D, d2 + (long long)i2 * D, D);
+                            if (matched[i2] <= dist) continue;
+                            top2_push(t, make_key(dist, ((uint32_t)(cc >> 8) << 26) | ((uint32_t)(cc & 0xff) << 20) | (uint32_t)i2));
+                        }
+                    }
+                    top2_warp_reduce(t);
+                    b1 = t.k1; b2 = t.k2;
+                }
+                if (lane == 0 && b1 != KEY_NONE) {
+                    const float bestDist = key_dist(b1), bestDist2 = key_dist(b2);
+                    if (bestDist <= th_low && bestDist < __fmul_rn(bestDist2, nnratio)) {           // :526-528
+                        const int bestIdx2 = (int)((uint32_t)b1 & 0xfffffu);
+                        if (m21[bestIdx2] != NONE16) { m12[m21[bestIdx2]] = NONE16; nm--; }         // :530-534
+                        m12[q.i1] = (unsigned short)bestIdx2; m21[bestIdx2] = (unsigned short)q.i1; matched[bestIdx2] = bestDist; nm++;
+                        if (check_ori) { const int bin = rot_bin(q.angle, tang[bestIdx2]); hbin[q.i1] = (signed char)bin; hist[bin]++; }
+                    }
+                }
+                __syncwarp();
             }
-        } else {
-            // exact fallback (candidate pool exhausted): rescan every train keypoint with the same candidate definition
-            SfiQuery w;
-            w.x = pm ? pm[2 * q.i1] : k1[q.i1].x; w.y = pm ? pm[2 * q.i1 + 1] : k1[q.i1].y;
-            w.ok = window_cells(w.x, w.y, window, minX, minY, invW, invH, w.c0, w.c1, w.r0, w.r1);
-            for (int i2 = lane; w.ok && i2 < n2; i2 += 32) {
-                const unsigned short cc = tcell[i2];
-                if (cc == NONE16 || !sfi_in_window(w, cc >> 8, cc & 0xff, k2[i2].x, k2[i2].y, window)) continue;
-                const float dist = desc_distance(desc_type, d1 + (long long)q.i1 * D, d2 + (long long)i2 * D, D);
-                if (matched[i2] <= dist) continue;
-                top2_push(t, make_key(dist, ((uint32_t)(cc >> 8) << 26) | ((uint32_t)(cc & 0xff) << 20) | (uint32_t)i2));
-            }
         }
-        top2_warp_reduce(t);
-        if (lane == 0 && t.k1 != KEY_NONE) {
-            const float bestDist = key_dist(t.k1), bestDist2 = key_dist(t.k2);
-            if (bestDist <= th_low && bestDist < __fmul_rn(bestDist2, nnratio)) {           // :526-528
-                const int bestIdx2 = (int)((uint32_t)t.k1 & 0xfffffu);
-                if (m21[bestIdx2] != NONE16) { m12[m21[bestIdx2]] = NONE16; nm--; }         // :530-534
-                m12[q.i1] = (unsigned short)bestIdx2; m21[bestIdx2] = (unsigned short)q.i1; matched[bestIdx2] = bestDist; nm++;
-                if (check_ori) { const int bin = rot_bin(q.angle, tang[bestIdx2]); hbin[q.i1] = (signed char)bin; hist[bin]++; }
-            }
-        }
-        __syncwarp();
+        __syncthreads();
     }
-    if (check_ori) {
-        int kb0 = 0, kb1 = 0, kb2 = 0;
-        if (lane == 0) three_maxima(hist, kb0, kb1, kb2);
-        kb0 = __shfl_sync(0xffffffffu, kb0, 0); kb1 = __shfl_sync(0xffffffffu, kb1, 0); kb2 = __shfl_sync(0xffffffffu, kb2, 0);
-        int removed = 0;
-        for (int i = lane; i < n1; i += 32) {
-            const int b = hbin[i];
-            if (b < 0 || b == kb0 || b == kb1 || b == kb2) continue;
-            if (m12[i] != NONE16) { m12[i] = NONE16; ++removed; }
-        }
+    if (tid == 0) s_nm = nm;
+    __syncthreads();
+    if (wid == 0) {
+        nm = s_nm;
+        if (check_ori) {
+            int kb0 = 0, kb1 = 0, kb2 = 0;
+            if (lane == 0) three_maxima(hist, kb0, kb1, kb2);
+            kb0 = __shfl_sync(0xffffffffu, kb0, 0); kb1 = __shfl_sync(0xffffffffu, kb1, 0); kb2 = __shfl_sync(0xffffffffu, kb2, 0);
+            int removed = 0;
+            for (int i = lane; i < n1; i += 32) {
+                const int b = hbin[i];
+                if (b < 0 || b == kb0 || b == kb1 || b == kb2) continue;
+                if (m12[i] != NONE16) { m12[i] = NONE16; ++removed; }
+            }
 #pragma unroll
-        for (int o = 16; o; o >>= 1) removed += __shfl_xor_sync(0xffffffffu, removed, o);
-        nm -= removed;
-        __syncwarp();
+            for (int o = 16; o; o >>= 1) removed += __shfl_xor_sync(0xffffffffu, removed, o);
+            nm -= removed;
+        }
+        if (lane == 0) nmatches[p] = nm;
     }
-    for (int i = lane; i < n1; i += 32) {
+    __syncthreads();
+    for (int i = tid; i < n1; i += SFR_THREADS) {
         const int m = m12[i] == NONE16 ? -1 : (int)m12[i];
         m12g[i] = m;
         if (pm && m >= 0) { pm[2 * i] = k2[m].x; pm[2 * i + 1] = k2[m].y; }                 // :552-554
     }
-    if (lane == 0) nmatches[p] = nm;
 }
 
 extern "C" int afv_search_for_initialization(int desc_type, const afv_keypoint* d_kps, const void* d_desc,
@@ -591,7 +633,7 @@ extern "C" int afv_search_for_initialization(int desc_type, const afv_keypoint* 
     const size_t baseA = sfl_base_bytes(cap);
     const int stage = binary && Dpad <= 64 && baseA + (size_t)cap * Dpad <= 200 * 1024;
     const size_t smemA = baseA + (stage ? (size_t)cap * Dpad : 0);
-    const size_t smemB = sfr_warp_bytes(cap) * SFR_WARPS;
+    const size_t smemB = sfr_cta_bytes(cap);
     if (smemA > 220 * 1024 || smemB > 220 * 1024) { afv_set_error("cap %d too large for the shared-memory staging", cap); return AFV_ERR_INVALID; }
     static size_t confA[2] = {0, 0}, confB[2] = {0, 0};
     if (smemA > confA[binary]) {
@@ -632,10 +674,10 @@ extern "C" int afv_search_for_initialization(int desc_type, const afv_keypoint* 
     }
     {
         AfvProfScope ps("k_sfi_resolve", st);
-        const int grid = (P + SFR_WARPS - 1) / SFR_WARPS;
-        if (binary) k_sfi_resolve<true><<<grid, SFR_WARPS * 32, smemB, st>>>(desc_type, D, d_kps, (const uint8_t*)d_desc, d_kpsize, d_n, cap, d_pair_a, d_pair_b, P,
+        const int grid = P;
+        if (binary) k_sfi_resolve<true><<<grid, SFR_THREADS, smemB, st>>>(desc_type, D, d_kps, (const uint8_t*)d_desc, d_kpsize, d_n, cap, d_pair_a, d_pair_b, P,
                 min_x, min_y, invW, invH, max_kpt_size, d_prev_matched, (float)window, th_low, nnratio, check_orientation, pool, pool_cap, qmeta, nq, d_matches12, d_nmatches);
-        else k_sfi_resolve<false><<<grid, SFR_WARPS * 32, smemB, st>>>(desc_type, D, d_kps, (const uint8_t*)d_desc, d_kpsize, d_n, cap, d_pair_a, d_pair_b, P,
+        else k_sfi_resolve<false><<<grid, SFR_THREADS, smemB, st>>>(desc_type, D, d_kps, (const uint8_t*)d_desc, d_kpsize, d_n, cap, d_pair_a, d_pair_b, P,
                 min_x, min_y, invW, invH, max_kpt_size, d_prev_matched, (float)window, th_low, nnratio, check_orientation, pool, pool_cap, qmeta, nq, d_matches12, d_nmatches);
         ++g_afv_launches;
     }

@@ -440,7 +440,10 @@ def run_gpu(args):
             "k_octree": B * (8 * 8539 + 8 * N),
             "k_blur": B * (2 * P_PIX),
             "k_describe": B * N * (8 + 709 + 512 + 28 + 32 + 4),
-            "k_search_init": B * (2 * N * (32 + 12) + 4 * N + 4),
+            # matcher (compulsory traffic only; the candidate pool between the two kernels is an implementation intermediate):
+            # both frames' descriptors + keypoints in, query metadata out | metadata + train keypoints in, matches out
+            "k_sfi_lists": B * (2 * N * (WL["desc_bytes"] + 28) + 4 * N + 16 * float(ex.levels()[1][0])),
+            "k_sfi_resolve": B * (N * 28 + 16 * float(ex.levels()[1][0]) + 4 * N + 4),
         }
         dom = max(kern, key=lambda k: kern[k][0])
         peaks = {}
