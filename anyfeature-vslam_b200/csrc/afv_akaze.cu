@@ -642,6 +642,7 @@ struct AfvAkaze {
     uint2* cand[AKZ_MAX_LV]; uint2* srt[AKZ_MAX_LV]; int cand_cap[AKZ_MAX_LV];
     float* scr[4];                      // full-resolution scratch images [B]
     uint8_t* gray_stage; int* h_status;
+    int use_tma;                        // AFV_BLUR_NO_TMA=1: clamped-load staging on every blur tile (A/B check)
     int unfused_fed;                    // AFV_AKAZE_UNFUSED_FED=1: one k_akz_nld launch per FED step (A/B check of k_akz_fed)
     size_t img_floats;                  // floats per full-resolution frame image (max geometry)
 };
@@ -707,6 +708,7 @@ int afv_akaze_create(AfvAkaze** out, int nfeatures, int nlevels, float scale_fac
     s->max_batch = max_batch; s->max_w = max_w; s->max_h = max_h; s->omax = omax; s->nsub = nsub;
     s->gray_stage = nullptr; s->h_status = nullptr;
     { const char* e = getenv("AFV_AKAZE_UNFUSED_FED"); s->unfused_fed = e && e[0] == '1'; }
+    { const char* e = getenv("AFV_BLUR_NO_TMA"); s->use_tma = !(e && e[0] == '1'); }
     memset(&s->taps16, 0, sizeof(AfvBlurTaps)); memset(&s->taps10, 0, sizeof(AfvBlurTaps));
     if (akz_gauss_taps(1.6f, s->taps16.t) != 4 || akz_gauss_taps(1.0f, s->taps10.t) != 2) { afv_set_error("akaze61: internal: unexpected blur radius"); delete s; return AFV_ERR_INVALID; }
     {
@@ -878,7 +880,8 @@ int afv_akaze_run(AfvAkaze* s, const uint8_t* d_gray, int B, int w, int h, int s
             k_akz_half<<<AKZ_GRID(L, B), 256, 0, st>>>(Q.Lt, Q.stride, Q.istride, s->scr[0], L.w, L.h, L.stride, L.istride); ++g_afv_launches;
             cur = s->scr[0];
         }
-        afv_blur_launch<2, 0>(cur, L.stride, L.istride, L.Lsm, nullptr, L.w, L.h, L.stride, L.istride, s->taps10, B, st); ++g_afv_launches;
+        { CUtensorMap tm; const bool ok = s->use_tma && afv_blur_tmap(&tm, cur, L.w, L.h, L.stride, L.istride, B, 2);
+          afv_blur_launch<2, 0>(cur, L.stride, L.istride, L.Lsm, nullptr, L.w, L.h, L.stride, L.istride, s->taps10, B, st, ok ? &tm : nullptr, 0); ++g_afv_launches; }
         k_akz_flow<<<AKZ_GRID(L, B), 256, 0, st>>>(L.Lsm, s->scr[2], L.w, L.h, L.stride, L.istride, P.kcontrast, L.octave); ++g_afv_launches;
         if (L.nsteps >= 1 && L.nsteps <= 12 && !s->unfused_fed) {
             AkzTaus taus; memset(&taus, 0, sizeof(taus));

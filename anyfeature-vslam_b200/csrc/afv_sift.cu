@@ -23,6 +23,7 @@
 #include "afv_sift.h"
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include <vector>
 
@@ -602,6 +603,7 @@ struct AfvSift {
     float scale_factor;
     int rad[6];
     AfvBlurTaps taps[6];
+    int use_tma;                 // AFV_BLUR_NO_TMA=1 forces the clamped-load staging on every tile (A/B check)
     std::vector<void*> allocs;
     SiftParams P;
     float* g[SIFT_MAX_OCT]; float* d[SIFT_MAX_OCT];
@@ -660,6 +662,7 @@ int afv_sift_create(AfvSift** out, int nfeatures, int nlevels, float scale_facto
     s->nfeatures = nfeatures; s->nlevels = nlevels; s->scale_factor = scale_factor;
     s->max_batch = max_batch; s->max_w = max_w; s->max_h = max_h; s->cur_w = s->cur_h = 0;
     s->gray_stage = nullptr; s->h_status = nullptr;
+    { const char* e = getenv("AFV_BLUR_NO_TMA"); s->use_tma = !(e && e[0] == '1'); }
     // blur taps (same double arithmetic as the oracle)
     const double k = pow(2.0, 1.0 / SIFT_S), sigma0 = 1.6 * k, sigman = 0.5;
     double dsig[6];
@@ -795,11 +798,16 @@ int afv_sift_run(AfvSift* s, const uint8_t* d_gray, int B, int w, int h, int str
             k_sift_down<<<g, 256, 0, st>>>(Q.g + (long long)SIFT_S * B * Q.istride, Q.stride, Q.istride, G(0), O.w, O.h, O.stride, O.istride);
             ++g_afv_launches;
         }
-        afv_blur_launch<5, 0>(G(0), O.stride, O.istride, G(1), D(0), O.w, O.h, O.stride, O.istride, s->taps[1], B, st); ++g_afv_launches;
-        afv_blur_launch<7, 0>(G(1), O.stride, O.istride, G(2), D(1), O.w, O.h, O.stride, O.istride, s->taps[2], B, st); ++g_afv_launches;
-        afv_blur_launch<8, 0>(G(2), O.stride, O.istride, G(3), D(2), O.w, O.h, O.stride, O.istride, s->taps[3], B, st); ++g_afv_launches;
-        afv_blur_launch<10, 0>(G(3), O.stride, O.istride, G(4), D(3), O.w, O.h, O.stride, O.istride, s->taps[4], B, st); ++g_afv_launches;
-        afv_blur_launch<13, 0>(G(4), O.stride, O.istride, G(5), D(4), O.w, O.h, O.stride, O.istride, s->taps[5], B, st); ++g_afv_launches;
+        { CUtensorMap tm; const bool ok = s->use_tma && afv_blur_tmap(&tm, O.g, O.w, O.h, O.stride, O.istride, (long long)SIFT_NL * B, 5);
+          afv_blur_launch<5, 0>(G(0), O.stride, O.istride, G(1), D(0), O.w, O.h, O.stride, O.istride, s->taps[1], B, st, ok ? &tm : nullptr, 0 * B); ++g_afv_launches; }
+        { CUtensorMap tm; const bool ok = s->use_tma && afv_blur_tmap(&tm, O.g, O.w, O.h, O.stride, O.istride, (long long)SIFT_NL * B, 7);
+          afv_blur_launch<7, 0>(G(1), O.stride, O.istride, G(2), D(1), O.w, O.h, O.stride, O.istride, s->taps[2], B, st, ok ? &tm : nullptr, 1 * B); ++g_afv_launches; }
+        { CUtensorMap tm; const bool ok = s->use_tma && afv_blur_tmap(&tm, O.g, O.w, O.h, O.stride, O.istride, (long long)SIFT_NL * B, 8);
+          afv_blur_launch<8, 0>(G(2), O.stride, O.istride, G(3), D(2), O.w, O.h, O.stride, O.istride, s->taps[3], B, st, ok ? &tm : nullptr, 2 * B); ++g_afv_launches; }
+        { CUtensorMap tm; const bool ok = s->use_tma && afv_blur_tmap(&tm, O.g, O.w, O.h, O.stride, O.istride, (long long)SIFT_NL * B, 10);
+          afv_blur_launch<10, 0>(G(3), O.stride, O.istride, G(4), D(3), O.w, O.h, O.stride, O.istride, s->taps[4], B, st, ok ? &tm : nullptr, 3 * B); ++g_afv_launches; }
+        { CUtensorMap tm; const bool ok = s->use_tma && afv_blur_tmap(&tm, O.g, O.w, O.h, O.stride, O.istride, (long long)SIFT_NL * B, 13);
+          afv_blur_launch<13, 0>(G(4), O.stride, O.istride, G(5), D(4), O.w, O.h, O.stride, O.istride, s->taps[5], B, st, ok ? &tm : nullptr, 4 * B); ++g_afv_launches; }
         }
     }
     { AfvProfScope ps("k_sift_detect", st);
