@@ -292,6 +292,63 @@ __global__ void __launch_bounds__(256) k_akz_deriv2(const float* __restrict__ lx
     Lx[p] = lx0[p] * s1; Ly[p] = ly0[p] * s1;
 }
 
+// ------------------------------------------------------------------------------------------------------
+// Fused multiscale derivatives: one CTA = 64 x 32 outputs.  The smoothed level is staged once with a halo of 2*sc
+// (BORDER_REFLECT_101 resolved while staging), the un-scaled first derivatives are built in shared memory on the tile plus a
+// halo of sc -- for cells outside the image as the derivative AT THE REFLECTED POSITION, which is what the second sepFilter2D
+// of the reference sees -- and the second derivatives / Hessian determinant come from those.  Same per-value arithmetic as
+// k_akz_deriv1 + k_akz_deriv2 with ~3 global loads per pixel instead of ~32.
+// ------------------------------------------------------------------------------------------------------
+#define HS_TW 64
+#define HS_TH 32
+__host__ __device__ inline size_t akz_hess_smem(int sc) {
+    return sizeof(float) * ((size_t)(HS_TW + 4 * sc) * (HS_TH + 4 * sc) + 2 * (size_t)(HS_TW + 2 * sc) * (HS_TH + 2 * sc));
+}
+__global__ void __launch_bounds__(256) k_akz_hessian(const float* __restrict__ lsm, float* __restrict__ Lx, float* __restrict__ Ly,
+                                                     float* __restrict__ Ldet, int w, int h, int st, long long ist, int sc,
+                                                     float norm, float wc) {
+    extern __shared__ __align__(16) float hsm[];
+    const int SW = HS_TW + 4 * sc, SH = HS_TH + 4 * sc;          // staged smoothed level
+    const int DW = HS_TW + 2 * sc, DH = HS_TH + 2 * sc;          // first-derivative region
+    float* S = hsm; float* DX = hsm + SW * SH; float* DY = DX + DW * DH;
+    const int tid = threadIdx.x, f = blockIdx.z;
+    const int tx0 = blockIdx.x * HS_TW, ty0 = blockIdx.y * HS_TH;
+    const float* src = lsm + f * ist;
+    for (int i = tid; i < SW * SH; i += 256) {
+        const int r = i / SW, c = i - r * SW;
+        S[i] = src[(long long)akz_refl(ty0 - 2 * sc + r, h) * st + akz_refl(tx0 - 2 * sc + c, w)];
+    }
+    __syncthreads();
+    for (int i = tid; i < DW * DH; i += 256) {
+        const int r = i / DW, c = i - r * DW;
+        const int gy = ty0 - sc + r, gx = tx0 - sc + c;
+        if (gy > h - 1 + sc || gx > w - 1 + sc) continue;          // never read by an in-image output
+        const int sr = akz_refl(gy, h) - (ty0 - 2 * sc), sx = akz_refl(gx, w) - (tx0 - 2 * sc);
+        const float* r0 = S + (sr - sc) * SW; const float* r1 = S + sr * SW; const float* r2 = S + (sr + sc) * SW;
+        const int xm = sx - sc, xp = sx + sc;
+        DX[i] = norm * ((r0[xp] - r0[xm]) + (r2[xp] - r2[xm])) + wc * (r1[xp] - r1[xm]);
+        DY[i] = (norm * (r2[xm] + r2[xp]) + wc * r2[sx]) - (norm * (r0[xm] + r0[xp]) + wc * r0[sx]);
+    }
+    __syncthreads();
+    const float s1 = (float)sc, s2 = (float)(sc * sc);
+    for (int i = tid; i < HS_TW * HS_TH; i += 256) {
+        const int r = i / HS_TW, c = i - r * HS_TW;
+        const int gy = ty0 + r, gx = tx0 + c;
+        if (gy >= h || gx >= w) continue;
+        const int dr = r + sc, dc = c + sc;
+        const float* x0 = DX + (dr - sc) * DW; const float* x1 = DX + dr * DW; const float* x2 = DX + (dr + sc) * DW;
+        const float* y0 = DY + (dr - sc) * DW; const float* y2 = DY + (dr + sc) * DW;
+        const int cm = dc - sc, cp = dc + sc;
+        const float lxx = norm * ((x0[cp] - x0[cm]) + (x2[cp] - x2[cm])) + wc * (x1[cp] - x1[cm]);
+        const float lyy = (norm * (y2[cm] + y2[cp]) + wc * y2[dc]) - (norm * (y0[cm] + y0[cp]) + wc * y0[dc]);
+        const float lxy = (norm * (x2[cm] + x2[cp]) + wc * x2[dc]) - (norm * (x0[cm] + x0[cp]) + wc * x0[dc]);
+        const float a = lxx * s2, b = lyy * s2, cc = lxy * s2;
+        const long long p = f * ist + (long long)gy * st + gx;
+        Ldet[p] = a * b - cc * cc;
+        Lx[p] = x1[dc] * s1; Ly[p] = DY[dr * DW + dc] * s1;
+    }
+}
+
 __global__ void __launch_bounds__(256) k_akz_extrema(const __grid_constant__ AkzParams P, int i) {
     const AkzLevelG& L = P.lv[i];
     AKZ_PIX();
@@ -643,7 +700,8 @@ struct AfvAkaze {
     float* scr[4];                      // full-resolution scratch images [B]
     uint8_t* gray_stage; int* h_status;
     int use_tma;                        // AFV_BLUR_NO_TMA=1: clamped-load staging on every blur tile (A/B check)
-    int unfused_fed;                    // AFV_AKAZE_UNFUSED_FED=1: one k_akz_nld launch per FED step (A/B check of k_akz_fed)
+    int unfused_fed;                    // AFV_AKAZE_UNFUSED_FED=1: one k_akz_nld launch per FED step and the two-kernel derivative
+                                        // path (A/B check of k_akz_fed / k_akz_hessian)
     size_t img_floats;                  // floats per full-resolution frame image (max geometry)
 };
 
@@ -796,6 +854,7 @@ int afv_akaze_create(AfvAkaze** out, int nfeatures, int nlevels, float scale_fac
     if (rc == AFV_OK) {
         cudaError_t e = cudaMallocHost((void**)&s->h_status, sizeof(int) * B);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(k_akz_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 8192);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_akz_hessian, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)akz_hess_smem(8));
         if (e == cudaSuccess) e = cudaFuncSetAttribute(k_akz_fed, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * FED_SH * FED_SW * (int)sizeof(float));
         if (e == cudaSuccess) e = cudaFuncSetAttribute(k_akz_select, cudaFuncAttributeMaxDynamicSharedMemorySize, 14 * AKZ_LIST_CAP);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(k_akz_octree, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)oct_work_bytes(P.oct_ncap));
@@ -903,8 +962,13 @@ int afv_akaze_run(AfvAkaze* s, const uint8_t* d_gray, int B, int w, int h, int s
         const float wgt = 10.0f / 3.0f;
         const float norm = sc == 1 ? 3.0f / 16.0f * 0.5f : 1.0f / (2.0f * (float)sc * (wgt + 2.0f));
         const float wc = sc == 1 ? 10.0f / 16.0f * 0.5f : wgt * norm;
+        if (sc <= 8 && !s->unfused_fed) {
+            k_akz_hessian<<<dim3((L.w + HS_TW - 1) / HS_TW, (L.h + HS_TH - 1) / HS_TH, B), 256, akz_hess_smem(sc), st>>>(
+                L.Lsm, L.Lx, L.Ly, L.Ldet, L.w, L.h, L.stride, L.istride, sc, norm, wc); ++g_afv_launches;
+        } else {
         k_akz_deriv1<<<AKZ_GRID(L, B), 256, 0, st>>>(L.Lsm, s->scr[0], s->scr[1], L.w, L.h, L.stride, L.istride, sc, norm, wc); ++g_afv_launches;
         k_akz_deriv2<<<AKZ_GRID(L, B), 256, 0, st>>>(s->scr[0], s->scr[1], L.Lx, L.Ly, L.Ldet, L.w, L.h, L.stride, L.istride, sc, norm, wc); ++g_afv_launches;
+        }
         k_akz_extrema<<<AKZ_GRID(L, B), 256, 0, st>>>(P, i); ++g_afv_launches;
     } }
     { AfvProfScope ps("k_akz_sort", st); k_akz_sort<<<dim3(P.nl, B), 512, 8 * 8192, st>>>(P); ++g_afv_launches; }

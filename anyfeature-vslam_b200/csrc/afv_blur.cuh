@@ -11,7 +11,7 @@ struct AfvBlurTaps { float t[16]; };     // centre outward, t[0..R]
 // ------------------------------------------------------------------------------------------------------
 // Gaussian step.  CTA = 128 x 32 outputs, 256 threads.  The (128+2R) x (32+2R) source footprint is staged with clamped
 // coordinates; row pass: one thread = 4 consecutive outputs from a (4+2R)-float register window (float4 LDS); column
-// pass: one thread = 8 consecutive rows of one column from an (8+2R) register window.  acc = t0*c; acc += tj*(l + r).
+// pass: one thread = 8 consecutive rows of one column from an (8+2R) register window.  acc = t0*c; acc = fma(tj, l + r, acc).
 // ------------------------------------------------------------------------------------------------------
 #define SB_W 128
 #define SB_H 32
@@ -98,7 +98,7 @@ __global__ void __launch_bounds__(256) k_afv_blur(const void* __restrict__ src_,
         for (int q = 0; q < 4; ++q) {
             float acc = tp[0] * win[q + R4];
 #pragma unroll
-            for (int j = 1; j <= R; ++j) acc = acc + tp[j] * (win[q + R4 - j] + win[q + R4 + j]);
+            for (int j = 1; j <= R; ++j) acc = __fmaf_rn(tp[j], win[q + R4 - j] + win[q + R4 + j], acc);
             op[q] = acc;
         }
         *reinterpret_cast<float4*>(mid + ry * SB_W + xg) = o;
@@ -117,7 +117,7 @@ __global__ void __launch_bounds__(256) k_afv_blur(const void* __restrict__ src_,
                 const int gy = ty0 + yg + q;
                 float acc = tp[0] * win[q + R];
 #pragma unroll
-                for (int j = 1; j <= R; ++j) acc = acc + tp[j] * (win[q + R - j] + win[q + R + j]);
+                for (int j = 1; j <= R; ++j) acc = __fmaf_rn(tp[j], win[q + R - j] + win[q + R + j], acc);
                 if (gy < h) {
                     const long long o = (long long)f * istride + (long long)gy * stride + gx;
                     dst[o] = acc;

@@ -291,8 +291,11 @@ __global__ void __launch_bounds__(SFL_THREADS) k_sfi_lists(int desc_type, int D,
         const int* __restrict__ n_arr, int cap, const int* __restrict__ pair_a, const int* __restrict__ pair_b,
         float minX, float minY, float invW, float invH, float max_kpt_size,
         const float* __restrict__ prev_matched, float window,
-        void* __restrict__ pool_v, int pool_cap, SfiQMeta* __restrict__ qmeta, int* __restrict__ nq_out) {
+        void* __restrict__ pool_v, int pool_cap, SfiQMeta* __restrict__ qmeta, int* __restrict__ nq_out,
+        int* __restrict__ gpool, int nsplit) {
     extern __shared__ __align__(16) unsigned char sm[];
+    // blockIdx.y = slice of the pair's queries: with few pairs the queries of one pair are spread over nsplit CTAs (each
+    // re-sorts the train frame; list space comes from one global bump counter per pair)
     const int p = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int fa = pair_a[p], fb = pair_b[p];
     const int n1 = min(n_arr[fa], cap), n2 = min(n_arr[fb], cap);
@@ -341,7 +344,7 @@ __global__ void __launch_bounds__(SFL_THREADS) k_sfi_lists(int desc_type, int D,
             if (q) qlist[base + __popc(m & ((1u << lane) - 1))] = (unsigned short)i;
             base += __popc(m);
         }
-        if (lane == 0) { s_nq = base; nq_out[p] = base; }
+        if (lane == 0) { s_nq = base; if (blockIdx.y == 0) nq_out[p] = base; }
     }
     __syncthreads();
     for (int i = tid; i < n2; i += SFL_THREADS) {                   // scatter into column order
@@ -368,7 +371,7 @@ __global__ void __launch_bounds__(SFL_THREADS) k_sfi_lists(int desc_type, int D,
     }
     __syncthreads();
 
-    for (int qi = wid; qi < nq; qi += SFL_THREADS / 32) {
+    for (int qi = wid + (SFL_THREADS / 32) * blockIdx.y; qi < nq; qi += (SFL_THREADS / 32) * nsplit) {
         const int i1 = qlist[qi];
         SfiQuery q;
         q.x = pm ? pm[2 * i1] : k1[i1].x; q.y = pm ? pm[2 * i1 + 1] : k1[i1].y;
@@ -384,7 +387,7 @@ __global__ void __launch_bounds__(SFL_THREADS) k_sfi_lists(int desc_type, int D,
                 cnt += __popc(__ballot_sync(0xffffffffu, pass));
             }
             if (cnt > 0) {
-                if (lane == 0) off = atomicAdd(&s_pool, cnt);
+                if (lane == 0) off = atomicAdd(&gpool[p], cnt);
                 off = __shfl_sync(0xffffffffu, off, 0);
                 if (off + cnt > pool_cap) off = -1;                 // pool exhausted: the resolver rescans this query
             }
@@ -659,17 +662,21 @@ extern "C" int afv_search_for_initialization(int desc_type, const afv_keypoint* 
     const size_t esz = binary ? 4 : 8;
     unsigned char* scratch = nullptr;
     const size_t pool_bytes = (size_t)P * pool_cap * esz, meta_bytes = (size_t)P * cap * sizeof(SfiQMeta), nq_bytes = (size_t)P * sizeof(int);
-    AFV_CUDA_CHECK(cudaMallocAsync((void**)&scratch, pool_bytes + meta_bytes + nq_bytes + 256, st));
+    AFV_CUDA_CHECK(cudaMallocAsync((void**)&scratch, pool_bytes + meta_bytes + 2 * nq_bytes + 256, st));
     void* pool = scratch;
     SfiQMeta* qmeta = reinterpret_cast<SfiQMeta*>(scratch + pool_bytes);
     int* nq = reinterpret_cast<int*>(scratch + pool_bytes + meta_bytes);
+    int* gpool = nq + P;
+    AFV_CUDA_CHECK(cudaMemsetAsync(gpool, 0, nq_bytes, st));
+    int nsplit = 1;                                   // ~2 list CTAs per SM keep the chip busy when there are few pairs
+    while (nsplit < 8 && P * nsplit * 2 <= 296) nsplit *= 2;
     const float invW = (float)AFV_GRID_COLS / (max_x - min_x), invH = (float)AFV_GRID_ROWS / (max_y - min_y);
     {
         AfvProfScope ps("k_sfi_lists", st);
-        if (binary) k_sfi_lists<true><<<P, SFL_THREADS, smemA, st>>>(desc_type, D, Dpad, stage, d_kps, (const uint8_t*)d_desc, d_kpsize, d_n, cap,
-                d_pair_a, d_pair_b, min_x, min_y, invW, invH, max_kpt_size, d_prev_matched, (float)window, pool, pool_cap, qmeta, nq);
-        else k_sfi_lists<false><<<P, SFL_THREADS, smemA, st>>>(desc_type, D, Dpad, stage, d_kps, (const uint8_t*)d_desc, d_kpsize, d_n, cap,
-                d_pair_a, d_pair_b, min_x, min_y, invW, invH, max_kpt_size, d_prev_matched, (float)window, pool, pool_cap, qmeta, nq);
+        if (binary) k_sfi_lists<true><<<dim3(P, nsplit), SFL_THREADS, smemA, st>>>(desc_type, D, Dpad, stage, d_kps, (const uint8_t*)d_desc, d_kpsize, d_n, cap,
+                d_pair_a, d_pair_b, min_x, min_y, invW, invH, max_kpt_size, d_prev_matched, (float)window, pool, pool_cap, qmeta, nq, gpool, nsplit);
+        else k_sfi_lists<false><<<dim3(P, nsplit), SFL_THREADS, smemA, st>>>(desc_type, D, Dpad, stage, d_kps, (const uint8_t*)d_desc, d_kpsize, d_n, cap,
+                d_pair_a, d_pair_b, min_x, min_y, invW, invH, max_kpt_size, d_prev_matched, (float)window, pool, pool_cap, qmeta, nq, gpool, nsplit);
         ++g_afv_launches;
     }
     {

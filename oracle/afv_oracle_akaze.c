@@ -13,8 +13,8 @@
  * levels merged before Compute_Descriptors (:51-60), computeSize with powf(scaleFactor0, class_id) (:67-69).
  * cv2.AKAZE (OpenCV's port of libAKAZE by the same author) is used as a FAMILY CHECK in tests/test_oracle_akaze.py.
  *
- * Arithmetic contract (what the CUDA path reproduces bit for bit): IEEE float32, round to nearest, NO fused multiply-add,
- * operation order exactly as written; exp / atan2 / sin / cos are the polynomial forms shared with the sift128 oracle;
+ * Arithmetic contract (what the CUDA path reproduces bit for bit): IEEE float32, round to nearest, NO fused multiply-add
+ * except the explicit fmaf() of the Gaussian taps, operation order exactly as written; exp / atan2 / sin / cos are the polynomial forms shared with the sift128 oracle;
  * the orientation window sums are accumulated in 64-bit INTEGERS (responses quantised with rintf(v * 2^32)).
  */
 #include "afv_oracle.h"
@@ -110,7 +110,7 @@ int orc_akaze_gauss_taps(float sigma, float* taps /* centre outward */) {
     return r;
 }
 
-/* separable blur, rows then columns, BORDER_REPLICATE; acc = t0*c; acc += tj*(l + r) */
+/* separable blur, rows then columns, BORDER_REPLICATE; acc = t0*c; acc = fma(tj, l + r, acc) (fused, like the sift128 blur) */
 static void gauss_blur(const float* src, float* dst, float* tmp, int w, int h, float sigma) {
     float t[32];
     const int r = orc_akaze_gauss_taps(sigma, t);
@@ -118,14 +118,14 @@ static void gauss_blur(const float* src, float* dst, float* tmp, int w, int h, f
         for (int x = 0; x < w; ++x) {
             const float* s = src + (size_t)y * w;
             float acc = t[0] * s[x];
-            for (int j = 1; j <= r; ++j) acc = acc + t[j] * (s[clampi(x - j, 0, w - 1)] + s[clampi(x + j, 0, w - 1)]);
+            for (int j = 1; j <= r; ++j) acc = fmaf(t[j], s[clampi(x - j, 0, w - 1)] + s[clampi(x + j, 0, w - 1)], acc);
             tmp[(size_t)y * w + x] = acc;
         }
     for (int y = 0; y < h; ++y)
         for (int x = 0; x < w; ++x) {
             float acc = t[0] * tmp[(size_t)y * w + x];
             for (int j = 1; j <= r; ++j)
-                acc = acc + t[j] * (tmp[(size_t)clampi(y - j, 0, h - 1) * w + x] + tmp[(size_t)clampi(y + j, 0, h - 1) * w + x]);
+                acc = fmaf(t[j], tmp[(size_t)clampi(y - j, 0, h - 1) * w + x] + tmp[(size_t)clampi(y + j, 0, h - 1) * w + x], acc);
             dst[(size_t)y * w + x] = acc;
         }
 }

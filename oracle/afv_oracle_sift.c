@@ -18,7 +18,7 @@
  *   powf(scaleFactor0, octave), src/Feature_sift128.cpp:124-126).
  *
  * Arithmetic contract (what the CUDA path must reproduce bit for bit): IEEE float32, round-to-nearest, NO fused
- * multiply-add, operation order exactly as written here; exp / atan2 / sin / cos are the polynomial forms below (not
+ * multiply-add except the explicit fmaf() of the Gaussian taps, operation order exactly as written here; exp / atan2 / sin / cos are the polynomial forms below (not
  * libm); every histogram is accumulated in INTEGERS (contributions quantised with rintf(v * 2^20)), so the sums do not
  * depend on the order in which a parallel implementation adds them.
  */
@@ -136,14 +136,15 @@ int orc_sift_num_octaves(int w, int h) {
 
 static inline int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
 
-/* separable blur, rows then columns, clamp-to-edge; acc = t0*c; acc += tj*(l + r) for j = 1..r */
+/* separable blur, rows then columns, clamp-to-edge; acc = t0*c; acc = fma(tj, l + r, acc) for j = 1..r (the one place
+ * where the contract FUSES: one rounding per tap, and one FFMA instead of FMUL + FADD on the GPU) */
 static void blur_sep(const float* src, float* dst, float* tmp, int w, int h, const float* taps, int r) {
     for (int y = 0; y < h; ++y) {
         const float* s = src + (size_t)y * w;
         float* t = tmp + (size_t)y * w;
         for (int x = 0; x < w; ++x) {
             float acc = taps[0] * s[x];
-            for (int j = 1; j <= r; ++j) acc = acc + taps[j] * (s[clampi(x - j, 0, w - 1)] + s[clampi(x + j, 0, w - 1)]);
+            for (int j = 1; j <= r; ++j) acc = fmaf(taps[j], s[clampi(x - j, 0, w - 1)] + s[clampi(x + j, 0, w - 1)], acc);
             t[x] = acc;
         }
     }
@@ -152,7 +153,7 @@ static void blur_sep(const float* src, float* dst, float* tmp, int w, int h, con
         for (int x = 0; x < w; ++x) {
             float acc = taps[0] * tmp[(size_t)y * w + x];
             for (int j = 1; j <= r; ++j)
-                acc = acc + taps[j] * (tmp[(size_t)clampi(y - j, 0, h - 1) * w + x] + tmp[(size_t)clampi(y + j, 0, h - 1) * w + x]);
+                acc = fmaf(taps[j], tmp[(size_t)clampi(y - j, 0, h - 1) * w + x] + tmp[(size_t)clampi(y + j, 0, h - 1) * w + x], acc);
             d[x] = acc;
         }
     }
