@@ -457,8 +457,9 @@ def run_gpu(args):
         traffic = None
         try:      # dram__bytes_read+write of the dominant kernel from the committed ncu --set full capture, per launch
             tj = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
-            if dom in tj["dram_bytes_per_frame"] and args.workload == "c2":
-                traffic = tj["dram_bytes_per_frame"][dom] * B
+            tw = tj if args.workload == "c2" else tj.get(args.workload, {})
+            if dom in tw.get("dram_bytes_per_frame", {}):
+                traffic = tw["dram_bytes_per_frame"][dom] * B
         except Exception:
             pass
         roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
