@@ -236,6 +236,8 @@ def run_gpu(args):
     dev = torch.device("cuda", local)
     if world > 1:
         import datetime
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"             # keep stdout to the one JSON line (NCCL prints its version there)
         dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=180))
     pkg = load_pkg()
     lib = pkg.lib()
