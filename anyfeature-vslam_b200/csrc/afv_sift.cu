@@ -268,13 +268,7 @@ __global__ void __launch_bounds__(256) k_sift_orient(const __grid_constant__ Sif
         for (int j = -R; j <= R; ++j) {
             const int py = yi + j;
             if (py < 1 || py > h - 2) continue;
-            // circular window: conservative i interval of this row (+-1.5 px), the exact r2 test below decides
-            const float dyr = (float)py - yo;
-            const float rem = r2max - dyr * dyr;
-            if (rem < -1.0f) continue;
-            const int half = (int)ceilf(sqrtf(fmaxf(rem, 0.f)) + 1.5f);
-            const int ilo = max(-R, -half), ihi = min(R, half);
-            for (int i = ilo + lane; i <= ihi; i += 32) {
+            for (int i = -R + lane; i <= R; i += 32) {
                 const int px = xi + i;
                 if (px < 1 || px > w - 2) continue;
                 const float dx = (float)px - xo, dy = (float)py - yo;
@@ -504,26 +498,10 @@ __global__ void __launch_bounds__(256) k_sift_describe(const __grid_constant__ S
     const int R = (int)rintf(hw * 0x1.6a09e6p+0f * 2.5f);
     const float cw = cs / hw, sw_ = sn / hw;
     const int xi = (int)rintf(xo), yi = (int)rintf(yo);
-    const float ex = (float)xi - xo;                       // px - xo = i + ex
     for (int jj = -R; jj <= R; ++jj) {
         const int py = yi + jj;
         if (py < 1 || py > h - 2) continue;
-        // The accepted samples lie in the rotated square |cr| < 2.5, |rr| < 2.5.  For this row that is an interval of i;
-        // lanes only visit a conservative superset of it (+-1.5 px), the exact float test below still decides.
-        int ilo = -R, ihi = R;
-        {
-            const float dyf = (float)py - yo;
-            const float a0 = dyf * sw_, b0 = dyf * cw;         // cr = dx*cw + a0, rr = b0 - dx*sw_
-            if (fabsf(cw) > 1e-3f) {
-                const float t0 = (-2.5f - a0) / cw, t1 = (2.5f - a0) / cw;
-                ilo = max(ilo, (int)floorf(fminf(t0, t1) - ex - 1.5f)); ihi = min(ihi, (int)ceilf(fmaxf(t0, t1) - ex + 1.5f));
-            }
-            if (fabsf(sw_) > 1e-3f) {
-                const float t0 = (b0 - 2.5f) / sw_, t1 = (b0 + 2.5f) / sw_;
-                ilo = max(ilo, (int)floorf(fminf(t0, t1) - ex - 1.5f)); ihi = min(ihi, (int)ceilf(fmaxf(t0, t1) - ex + 1.5f));
-            }
-        }
-        for (int i = ilo + lane; i <= ihi; i += 32) {
+        for (int i = -R + lane; i <= R; i += 32) {
             const int px = xi + i;
             if (px < 1 || px > w - 2) continue;
             const float dx = (float)px - xo, dy = (float)py - yo;
