@@ -186,8 +186,7 @@ __global__ void __launch_bounds__(256) k_fast(const __grid_constant__ AfvParams 
     const unsigned t2 = 2u * (unsigned)t;
     // |p - v| > t  <=>  (unsigned)(p - v + t) > 2t
 #define FAR(p, v) ((unsigned)((int)(p) - (v) + t) > t2)
-    // stage 1: any arc of 9 contains one pixel of each antipodal pair -> both pairs (0,8) and (4,12) must have a far
-    // pixel.  One thread walks 9 rows of one column with a rolling 15-pixel register window (centre, 3 above, 3 below
+    // stage 1: sign-consistent compass test (below).  One thread walks 17 rows of one column with a rolling 15-pixel register window (centre, 3 above, 3 below
     // come from the window; only left/right are extra loads) and appends its survivors with one warp-aggregated atomic.
     static_assert(FT_RH == 2 * FT_HALF && FT_HALF <= 32, "two halves");
     for (int round = 0; round < 2; ++round) {
@@ -208,8 +207,12 @@ __global__ void __launch_bounds__(256) k_fast(const __grid_constant__ AfvParams 
                 for (int k = 0; k < FT_HALF + 6; ++k) col[k] = pc[k * PITCH];
 #pragma unroll
                 for (int j = 0; j < FT_HALF; ++j) {
-                    const int v = col[j + 3];
-                    const bool pass = ((FAR(col[j + 6], v) | FAR(col[j], v)) & (FAR(pc[(j + 3) * PITCH + 3], v) | FAR(pc[(j + 3) * PITCH - 3], v)));
+                    // an arc of 9 of the 16 circle pixels always contains two ADJACENT compass points (0, 4, 8, 12), so a
+                    // corner needs two adjacent compass points that are both brighter than v+t or both darker than v-t:
+                    // (dn|up) & (rt|lf) per sign covers exactly the four adjacent pairs
+                    const int v = col[j + 3], hi = v + t, lo = v - t;
+                    const int dn = col[j + 6], up = col[j], rt = pc[(j + 3) * PITCH + 3], lf = pc[(j + 3) * PITCH - 3];
+                    const bool pass = (((dn > hi) | (up > hi)) & ((rt > hi) | (lf > hi))) | (((dn < lo) | (up < lo)) & ((rt < lo) | (lf < lo)));
                     smask |= (uint32_t)pass << j;
                 }
                 const uint32_t rowmask = jhi > jlo ? (((jhi >= 32) ? 0xffffffffu : ((1u << jhi) - 1u)) & ~((1u << jlo) - 1u)) : 0u;
