@@ -172,6 +172,18 @@ def gray_from_color(d_img, rgb=True, out=None, stream=None):
     return out
 
 
+def undistort_keypoints(kps, n, K4, dist5, out=None, stream=None):
+    """Frame::UndistortKeyPoints (src/Frame.cc:403-433) on device keypoint rows [B,cap,7]; K4 = (fx, fy, cx, cy) and
+    dist5 = (k1, k2, p1, p2, k3) are host float32 values.  Returns the undistorted rows (mvKeysUn)."""
+    import torch
+    B, cap = kps.shape[0], kps.shape[1]
+    if out is None:
+        out = torch.zeros_like(kps)
+    K4 = np.ascontiguousarray(K4, np.float32); dist5 = np.ascontiguousarray(dist5, np.float32)
+    _check(lib().afv_undistort_keypoints(_vp(kps), _vp(n), B, cap, _vp(K4), _vp(dist5), _vp(out), _stream_ptr(stream)))
+    return out
+
+
 def kps_from_device(t, n):
     """[cap,7] float32 device rows -> numpy structured afv_keypoint array of length n."""
     a = t[:n].contiguous().cpu().numpy()

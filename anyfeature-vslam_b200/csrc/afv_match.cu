@@ -159,6 +159,44 @@ extern "C" int afv_grid_build(const afv_keypoint* d_kps, const int* d_n, int B, 
     return AFV_OK;
 }
 
+// ---- Frame::UndistortKeyPoints (src/Frame.cc:403-433) -> cv::undistortPoints(mat, mat, mK, mDistCoef, Mat(), mK) ---------
+// OpenCV's arithmetic, pinned bit for bit to cv2 4.13.0: double precision, x = (u - cx) / fx as a multiply by 1/fx, FIVE
+// fixed-point iterations of the inverse distortion model (k1 k2 p1 p2 k3; the default TermCriteria is count-only), then
+// u' = x fx + cx narrowed to float.  Thread per keypoint; every other cv::KeyPoint field is copied (Frame.cc:427-431).
+__global__ void __launch_bounds__(256) k_undistort(const afv_keypoint* __restrict__ kps, const int* __restrict__ n_arr, int cap,
+                                                   double fx, double fy, double cx, double cy, double k1, double k2, double p1,
+                                                   double p2, double k3, int identity, afv_keypoint* __restrict__ out) {
+    const int f = blockIdx.y, i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= min(n_arr[f], cap)) return;
+    afv_keypoint kp = kps[(long long)f * cap + i];
+    if (!identity) {
+        const double ifx = 1.0 / fx, ify = 1.0 / fy;
+        double x = ((double)kp.x - cx) * ifx, y = ((double)kp.y - cy) * ify;
+        const double x0 = x, y0 = y;
+        for (int j = 0; j < 5; ++j) {
+            const double r2 = x * x + y * y;
+            const double icdist = 1.0 / (1.0 + ((k3 * r2 + k2) * r2 + k1) * r2);
+            if (icdist < 0) { x = x0; y = y0; break; }
+            const double dX = 2.0 * p1 * x * y + p2 * (r2 + 2.0 * x * x);
+            const double dY = p1 * (r2 + 2.0 * y * y) + 2.0 * p2 * x * y;
+            x = (x0 - dX) * icdist; y = (y0 - dY) * icdist;
+        }
+        kp.x = (float)(x * fx + cx); kp.y = (float)(y * fy + cy);
+    }
+    out[(long long)f * cap + i] = kp;
+}
+
+extern "C" int afv_undistort_keypoints(const afv_keypoint* d_kps, const int* d_n, int B, int cap, const float* K4, const float* dist5,
+                                       afv_keypoint* d_kps_un, void* cuda_stream) {
+    if (!d_kps || !d_n || !K4 || !dist5 || !d_kps_un || B < 1 || cap < 1) { afv_set_error("afv_undistort_keypoints: bad argument"); return AFV_ERR_INVALID; }
+    const int identity = dist5[0] == 0.0f;                          // mDistCoef.at<float>(0) == 0.0 -> mvKeysUn = mvKeys (:405-409)
+    k_undistort<<<dim3((cap + 255) / 256, B), 256, 0, as_stream(cuda_stream)>>>(d_kps, d_n, cap, (double)K4[0], (double)K4[1], (double)K4[2],
+            (double)K4[3], (double)dist5[0], (double)dist5[1], (double)dist5[2], (double)dist5[3], (double)dist5[4], identity, d_kps_un);
+    ++g_afv_launches;
+    AFV_CUDA_CHECK(cudaGetLastError());
+    return AFV_OK;
+}
+
 // ---- stateless window search: one warp per query ---------------------------------------------------------
 __global__ void __launch_bounds__(256) k_match_window(int desc_type, int D, const uint8_t* __restrict__ q,
         const float* __restrict__ qxy, const float* __restrict__ qr, const float* __restrict__ qmin,

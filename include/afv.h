@@ -117,6 +117,14 @@ int  afv_grid_build(const afv_keypoint* d_kps, const int* d_n, int B, int cap,
                     float min_x, float min_y, float max_x, float max_y,
                     int* d_cell_start, int* d_cell_items, void* cuda_stream);
 
+/* Frame::UndistortKeyPoints (src/Frame.cc:403-433): cv::undistortPoints(pts, pts, mK, mDistCoef, Mat(), mK) on the keypoint
+ * positions of B frames (device, B x cap rows, n[b] valid), every other cv::KeyPoint field copied.  K4 = {fx, fy, cx, cy} and
+ * dist5 = {k1, k2, p1, p2, k3} are HOST float arrays (the reference keeps mK / mDistCoef as CV_32F).  dist5[0] == 0 copies the
+ * keypoints unchanged like the reference (:405-409).  Arithmetic pinned bit for bit to cv2 4.13.0 (double precision, 5 fixed
+ * iterations).  Chain afv_grid_build on the result for Frame::AssignFeaturesToGrid (:225-240). */
+int  afv_undistort_keypoints(const afv_keypoint* d_kps, const int* d_n, int B, int cap, const float* K4, const float* dist5,
+                             afv_keypoint* d_kps_un, void* cuda_stream);
+
 /* Data-parallel core of SearchByProjection (src/FeatureMatcher.cc:73-154) / GetFeaturesInArea
  * (src/Frame.cc:333-382): for each query (descriptor, window centre qxy, radius, size gate) the best and
  * second-best train keypoint inside the window, first-minimum-wins in (cell x, cell y, index) order.      */

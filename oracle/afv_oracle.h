@@ -138,6 +138,9 @@ void orc_bow_transform(int desc_type, const void* desc, int n, const int* child_
                        const int* node_word, const double* node_weight, int depth_L, int levelsup,
                        int* word_id, double* weight, int* node_id);
 
+/* Frame::UndistortKeyPoints (src/Frame.cc:403-433), pinned to cv2 4.13.0 undistortPoints. */
+void orc_undistort_keypoints(const orc_keypoint* kps, int n, const float* K4, const float* dist5, orc_keypoint* out);
+
 /* rotation-consistency helpers (src/FeatureMatcher.cc:1579-1668) */
 int  orc_rot_bin(float angle1, float angle2);
 void orc_three_maxima(const int* hist_counts, int len, int* ind1, int* ind2, int* ind3);

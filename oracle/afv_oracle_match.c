@@ -482,3 +482,32 @@ long orc_orb32_extract_match_batch(const uint8_t* frames, int B, int w, int h, i
     free(th); free(J.kps); free(J.desc); free(J.ksz); free(J.n);
     return total;
 }
+
+
+/* ---------------------------------------------------------------- Frame::UndistortKeyPoints -------------------- */
+/* reference src/Frame.cc:403-433 -> cv::undistortPoints(mat, mat, mK, mDistCoef, cv::Mat(), mK): OpenCV computes in double,
+ * normalises with 1/fx, runs 5 fixed iterations of the inverse distortion model (default TermCriteria is count-only) and
+ * re-projects with the same K.  Pinned to cv2 4.13.0 (tests/golden/undistort_cv2.npz, tools/make_golden_undistort.py). */
+void orc_undistort_keypoints(const orc_keypoint* kps, int n, const float* K4, const float* dist5, orc_keypoint* out) {
+    const int identity = dist5[0] == 0.0f;
+    const double fx = K4[0], fy = K4[1], cx = K4[2], cy = K4[3];
+    const double k1 = dist5[0], k2 = dist5[1], p1 = dist5[2], p2 = dist5[3], k3 = dist5[4];
+    const double ifx = 1.0 / fx, ify = 1.0 / fy;
+    for (int i = 0; i < n; ++i) {
+        orc_keypoint kp = kps[i];
+        if (!identity) {
+            double x = ((double)kp.x - cx) * ifx, y = ((double)kp.y - cy) * ify;
+            const double x0 = x, y0 = y;
+            for (int j = 0; j < 5; ++j) {
+                const double r2 = x * x + y * y;
+                const double icdist = 1.0 / (1.0 + ((k3 * r2 + k2) * r2 + k1) * r2);
+                if (icdist < 0) { x = x0; y = y0; break; }
+                const double dX = 2.0 * p1 * x * y + p2 * (r2 + 2.0 * x * x);
+                const double dY = p1 * (r2 + 2.0 * y * y) + 2.0 * p2 * x * y;
+                x = (x0 - dX) * icdist; y = (y0 - dY) * icdist;
+            }
+            kp.x = (float)(x * fx + cx); kp.y = (float)(y * fy + cy);
+        }
+        out[i] = kp;
+    }
+}

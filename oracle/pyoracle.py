@@ -345,3 +345,12 @@ def akaze_extract_match_batch(frames, pair_a, pair_b, nfeatures=1000, nthreads=1
                                           int(window), _f(th_akaze), _f(th_brisk), _f(nnratio), int(bool(check_ori)), int(nthreads))
     assert r >= 0
     return int(r)
+
+
+def undistort_keypoints(kps, K4, dist5):
+    """Frame::UndistortKeyPoints on a KP_DTYPE array; K4 = (fx, fy, cx, cy), dist5 = (k1, k2, p1, p2, k3) as float32."""
+    kps = np.ascontiguousarray(kps)
+    K4 = np.ascontiguousarray(K4, np.float32); dist5 = np.ascontiguousarray(dist5, np.float32)
+    out = np.zeros_like(kps)
+    lib().orc_undistort_keypoints(_p(kps), len(kps), _p(K4), _p(dist5), _p(out))
+    return out

@@ -42,13 +42,14 @@ def test_unsupported_feature_is_an_error_not_a_fallback():
     import __graft_entry__ as g
     pkg = g._load_pkg()
     h = C.c_void_p()
-    for fid in (1, 2):          # akaze61 / brisk48 extractors: libAKAZE / ETH brisk are not vendored, no oracle -> not built
-        rc = pkg.lib().afv_extractor_create(C.byref(h), fid, 1000, 8, C.c_float(1.5), C.c_float(34.0), 0, 1, 640, 480)
-        assert rc == -5 and not h.value
+    # brisk48: ETH brisk's 48-byte v2 pattern is not vendored by the reference, nothing to restate -> no extractor
+    rc = pkg.lib().afv_extractor_create(C.byref(h), 2, 1000, 8, C.c_float(1.5), C.c_float(34.0), 0, 1, 640, 480)
+    assert rc == -5 and not h.value
     import torch
-    if not torch.cuda.is_available():                       # sift128 is built, but never on the CPU
-        rc = pkg.lib().afv_extractor_create(C.byref(h), 5, 1000, 8, C.c_float(2.0), C.c_float(10.0), 0, 1, 640, 480)
-        assert rc == -2 and not h.value
+    if not torch.cuda.is_available():                       # sift128 / akaze61 are built, but never on the CPU
+        for fid, sf, th in ((5, 2.0, 10.0), (1, 1.1892, 5e-4)):
+            rc = pkg.lib().afv_extractor_create(C.byref(h), fid, 1000, 8, C.c_float(sf), C.c_float(th), 0, 1, 640, 480)
+            assert rc == -2 and not h.value
 
 
 def test_cpp_host_mirror_builds_and_links():

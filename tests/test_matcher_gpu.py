@@ -334,3 +334,24 @@ def test_distinctive_descriptors(pkg, desc_type, D):
     got = pkg.FeatureMatcher.distinctive_descriptors(desc_type, d, torch.from_numpy(obs).cuda(), torch.from_numpy(seg).cuda(), max(lens))
     torch.cuda.synchronize()
     assert (got.cpu().numpy() == ref).all()
+
+
+def test_undistort_keypoints_and_grid(pkg, extracted, golden_dir):
+    """Frame::UndistortKeyPoints on device rows == oracle (pinned to cv2) bit for bit, then AssignFeaturesToGrid on mvKeysUn."""
+    import os
+    import torch
+    out, host, cap = extracted
+    kps_d, n_d = out[0], out[3]
+    g = np.load(os.path.join(golden_dir, "undistort_cv2.npz"))
+    for i in range(3):
+        K4, D5 = g["K%d" % i], g["D%d" % i]
+        un = pkg.undistort_keypoints(kps_d, n_d, K4, D5)
+        torch.cuda.synchronize()
+        for b in range(kps_d.shape[0]):
+            m = len(host[b][0])
+            ref = po.undistort_keypoints(host[b][0], K4, D5)
+            got = pkg.kps_from_device(un[b], m)
+            assert all((got[f] == ref[f]).all() for f in ref.dtype.names)
+    cs, ci = pkg.FeatureMatcher.grid_build(un, n_d, BOUNDS)
+    torch.cuda.synchronize()
+    assert int(cs[0, -1]) <= int(n_d[0])

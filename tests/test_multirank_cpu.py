@@ -26,7 +26,7 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _worker(rank, world, port, B, cap, q):
+def _worker(rank, world, port, B, cap, q, D=32):
     os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     pkg = load_pkg()
@@ -36,8 +36,8 @@ def _worker(rank, world, port, B, cap, q):
     nm = torch.from_numpy(rng.integers(0, 200, B).astype(np.int32))
     m12 = torch.from_numpy(rng.integers(-1, cap, (B, cap)).astype(np.int32))
     kps = torch.from_numpy(rng.normal(size=(B, cap, 7)).astype(np.float32))
-    desc = torch.from_numpy(rng.integers(0, 256, (B, cap, 32), dtype=np.uint8))
-    _, total = sh.pack_layout(B, cap, 32)
+    desc = torch.from_numpy(rng.integers(0, 256, (B, cap, D), dtype=np.uint8))
+    _, total = sh.pack_layout(B, cap, D)
     pack = torch.empty(total, dtype=torch.uint8)
     sh.pack_results(pack, n, nm, m12, kps, desc)
     gathered = [torch.empty(total, dtype=torch.uint8) for _ in range(world)] if rank == 0 else None
@@ -45,23 +45,27 @@ def _worker(rank, world, port, B, cap, q):
     if rank == 0:
         ok = True
         for r in range(world):
-            u = sh.unpack_results(gathered[r].numpy(), B, cap, 32)
+            u = sh.unpack_results(gathered[r].numpy(), B, cap, D)
             rr = np.random.default_rng(100 + r)
             ok &= (u["n"] == rr.integers(0, cap, B).astype(np.int32)).all()
             ok &= (u["nmatches"] == rr.integers(0, 200, B).astype(np.int32)).all()
             ok &= (u["matches12"] == rr.integers(-1, cap, (B, cap)).astype(np.int32)).all()
             ok &= (u["kps"].view(np.float32).reshape(B, cap, 7) == rr.normal(size=(B, cap, 7)).astype(np.float32)).all()
-            ok &= (u["desc"] == rr.integers(0, 256, (B, cap, 32), dtype=np.uint8)).all()
+            ok &= (u["desc"] == rr.integers(0, 256, (B, cap, D), dtype=np.uint8)).all()
         q.put(bool(ok))
     dist.barrier()
     dist.destroy_process_group()
 
 
-def test_gather_packed_results_world2():
+import pytest
+
+
+@pytest.mark.parametrize("D", [32, 61, 512])          # orb32, akaze61 (unaligned rows), sift128 (128 floats)
+def test_gather_packed_results_world2(D):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, 3, 40, q)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, 3, 40, q, D)) for r in range(2)]
     for p in procs:
         p.start()
     for p in procs:

@@ -112,3 +112,18 @@ def test_bow_transform_oracle_properties():
     assert (po.bow_transform(0, feats, tree, levelsup=4)[2] == 0).all()
     ids, starts, order = po.feature_vector_segments(nid)
     assert (np.diff(ids) > 0).all() and starts[-1] == len(nid)
+
+
+def test_undistort_keypoints_matches_cv2_golden(golden_dir):
+    """Frame::UndistortKeyPoints (src/Frame.cc:403-433): the oracle is bit-identical with cv2 4.13.0's undistortPoints."""
+    import os
+    g = np.load(os.path.join(golden_dir, "undistort_cv2.npz"))
+    pts = g["pts"]
+    kps = np.zeros(len(pts), po.KP_DTYPE)
+    kps["x"] = pts[:, 0]; kps["y"] = pts[:, 1]; kps["size"] = 31.0; kps["angle"] = 12.5; kps["octave"] = 3; kps["class_id"] = -1
+    for i in range(3):
+        out = po.undistort_keypoints(kps, g["K%d" % i], g["D%d" % i])
+        assert (out["x"] == g["und%d" % i][:, 0]).all() and (out["y"] == g["und%d" % i][:, 1]).all()
+        for f in ("size", "angle", "response", "octave", "class_id"):
+            assert (out[f] == kps[f]).all()
+    assert (po.undistort_keypoints(kps, g["K2"], g["D2"])["x"] == kps["x"]).all()       # zero distortion: copy (:405-409)
