@@ -106,3 +106,35 @@ def test_akaze_blank_device_api_and_matcher(pkg, synth):
     assert int(nm[0]) == rn and rn > 20
     assert (m12[0, :len(rk0)].cpu().numpy() == rm12).all()
     ex.close()
+
+
+def test_akaze_full_size_batch_properties(pkg, synth):
+    """BASELINE configs[3] size (256 frames of 640x480, 1000 kp): frames i and i+128 are the same image in different arena
+    slots -> identical outputs; levels ascending, per-level counts within quota+3, octave = level // 4, 486-bit descriptors,
+    keypoints inside the image; two frames bit-exact against the oracle."""
+    import torch
+    base = np.concatenate([synth.stream_frames(640, 480, 60 + s, 16)[0] for s in range(8)], axis=0)
+    frames = np.concatenate([base, base], axis=0)
+    ex = pkg.FeatureExtractor("akaze61", nfeatures=1000, max_batch=256, max_w=640, max_h=480)
+    out = ex.alloc_device_outputs(256)
+    ex.extract_batch_device(torch.from_numpy(frames).cuda(), out)
+    torch.cuda.synchronize()
+    ex.status()
+    n = out[3].cpu().numpy()
+    kps = out[0].cpu().numpy(); desc = out[1].cpu().numpy()
+    assert (n[:128] == n[128:]).all() and n.min() > 300
+    q = po.features_per_level(1000, 8, 1.1892)
+    for f in range(128):
+        m = int(n[f])
+        assert (kps[f, :m].view(np.uint8) == kps[f + 128, :m].view(np.uint8)).all() and (desc[f, :m] == desc[f + 128, :m]).all()
+        k = kps[f, :m].view(np.uint8).reshape(m, 28).view(pkg.KP_DTYPE).reshape(m)
+        assert m <= ex.cap and (np.diff(k["class_id"]) >= 0).all() and (k["octave"] == k["class_id"] // 4).all()
+        assert (np.bincount(k["class_id"], minlength=8) <= q + 3).all()
+        assert (k["x"] >= 0).all() and (k["x"] < 640).all() and (k["y"] >= 0).all() and (k["y"] < 480).all()
+        assert (desc[f, :m, 60] >> 6 == 0).all() and (k["response"] > 5e-4).all()
+    for f in (3, 200):
+        rk, rd, rs, _ = po.akaze61_extract(frames[f], 1000)
+        m = int(n[f])
+        k = pkg.kps_from_device(out[0][f], m)
+        assert m == len(rk) and all((k[fld] == rk[fld]).all() for fld in rk.dtype.names) and (desc[f, :m] == rd).all()
+    ex.close()

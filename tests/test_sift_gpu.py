@@ -121,3 +121,38 @@ def test_sift_l2_matcher_on_extracted(pkg, synth):
     assert (best.cpu().numpy() == rb).all()
     assert np.allclose(bd.cpu().numpy(), rbd, rtol=1e-5, atol=1e-7) and np.allclose(sd.cpu().numpy(), rsd, rtol=1e-5, atol=1e-7)
     assert (bd.cpu().numpy() < 0.5).mean() > 0.3               # consecutive synthetic frames do match
+
+
+def test_sift_full_size_batch_properties(pkg, synth):
+    """BASELINE configs[2] size (64 frames of 1280x720, 2000 kp): size-independent properties + one oracle spot check.
+    Frames i and i+32 are the same image in different arena slots -> identical outputs (no cross-frame leakage,
+    deterministic regardless of atomics order); unit-norm descriptors; keypoints inside the image, ascending octaves,
+    per-octave counts within quota+3, octave rule of src/Feature_sift128.cpp:92, unique class_id."""
+    import torch
+    base = np.concatenate([synth.stream_frames(1280, 720, 40 + s, 8)[0] for s in range(4)], axis=0)
+    frames = np.concatenate([base, base], axis=0)
+    ex = pkg.FeatureExtractor("sift128", nfeatures=2000, max_batch=64, max_w=1280, max_h=720)
+    out = ex.alloc_device_outputs(64)
+    ex.extract_batch_device(torch.from_numpy(frames).cuda(), out)
+    torch.cuda.synchronize()
+    ex.status()
+    n = out[3].cpu().numpy()
+    kps = out[0].cpu().numpy(); desc = out[1].cpu().numpy().view(np.float32).reshape(64, ex.cap, 128)
+    assert (n[:32] == n[32:]).all() and n.min() > 500
+    q = po.features_per_level(2000, 8, 2.0)
+    for f in range(32):
+        m = int(n[f])
+        assert (kps[f, :m].view(np.uint8) == kps[f + 32, :m].view(np.uint8)).all()
+        assert (desc[f, :m].view(np.uint32) == desc[f + 32, :m].view(np.uint32)).all()
+        k = kps[f, :m].view(np.uint8).reshape(m, 28).view(pkg.KP_DTYPE).reshape(m)
+        assert m <= ex.cap and (np.diff(k["octave"]) >= 0).all()
+        assert (np.bincount(k["octave"], minlength=8) <= q + 3).all()
+        assert (k["x"] >= 0).all() and (k["x"] < 1280).all() and (k["y"] >= 0).all() and (k["y"] < 720).all()
+        assert (k["octave"] == np.floor(np.maximum(np.log2(k["size"].astype(np.float64) / 1.6454), 0)).astype(int)).all()
+        assert len(set(k["class_id"].tolist())) == m and (k["response"] == 1.0).all()
+        assert np.allclose(np.linalg.norm(desc[f, :m], axis=1), 1.0, atol=1e-5)
+    rk, rd, rs, _ = po.sift128_extract(frames[5], 2000)
+    m = int(n[5])
+    k = pkg.kps_from_device(out[0][5], m)
+    assert m == len(rk) and all((k[fld] == rk[fld]).all() for fld in rk.dtype.names) and (desc[5, :m] == rd).all()
+    ex.close()
