@@ -468,6 +468,7 @@ __global__ void __launch_bounds__(256) k_sift_octree(const __grid_constant__ Sif
 __global__ void __launch_bounds__(256) k_sift_describe(const __grid_constant__ SiftParams P, afv_keypoint* __restrict__ kps,
                                                        float* __restrict__ desc, float* __restrict__ kpsize, int* __restrict__ n_out) {
     __shared__ unsigned acc[8][128];
+    __shared__ unsigned squeue[8][64];
     const int f = blockIdx.y, lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
     const int j = blockIdx.x * 8 + wp;
     int total = 0, oc = -1, p = 0;
@@ -498,48 +499,74 @@ __global__ void __launch_bounds__(256) k_sift_describe(const __grid_constant__ S
     const int R = (int)rintf(hw * 0x1.6a09e6p+0f * 2.5f);
     const float cw = cs / hw, sw_ = sn / hw;
     const int xi = (int)rintf(xo), yi = (int)rintf(yo);
-    for (int jj = -R; jj <= R; ++jj) {
-        const int py = yi + jj;
-        if (py < 1 || py > h - 2) continue;
-        for (int i = -R + lane; i <= R; i += 32) {
-            const int px = xi + i;
-            if (px < 1 || px > w - 2) continue;
-            const float dx = (float)px - xo, dy = (float)py - yo;
-            const float cr = dx * cw + dy * sw_;
-            const float rr = dy * cw - dx * sw_;
-            const float cb = cr + 1.5f, rb = rr + 1.5f;
-            if (!(cb > -1.0f && cb < 4.0f && rb > -1.0f && rb < 4.0f)) continue;
-            const int c = py * st + px;
-            const float gx = G[c + 1] - G[c - 1], gy = G[c + st] - G[c - st];
-            const float mag = sqrtf(gx * gx + gy * gy);
-            float ang = sift_atan2(gy, gx) - ori;
-            if (ang < 0.f) ang = ang + SIFT_2PI;
-            const float ob = ang * (8.0f / SIFT_2PI);
-            const float wgt = sift_exp((cr * cr + rr * rr) * -0.125f);
-            const float m = mag * wgt;
-            const float c0f = floorf(cb), r0f = floorf(rb), o0f = floorf(ob);
-            const float fc = cb - c0f, fr = rb - r0f, fo = ob - o0f;
-            const int c0 = (int)c0f, r0 = (int)r0f, o0 = (int)o0f;
+    // Two phases per 32 window positions (ncu: with the test and the accumulation in one loop only 56 % of the lanes did the
+    // ~150-instruction accumulation, the rest had been rejected by the rotated-window test).  Phase 1: cheap test, survivors
+    // are pushed (ballot + prefix) into a per-warp queue; phase 2 runs whenever 32 survivors are queued, so the accumulation
+    // always executes with full warps.  Integer atomics: the changed order is exact.
+    auto accumulate = [&](unsigned e) {
+        const int i = (int)(e & 0xffu) - 128, jj = (int)(e >> 8) - 128;
+        const int px = xi + i, py = yi + jj;
+        const float dx = (float)px - xo, dy = (float)py - yo;
+        const float cr = dx * cw + dy * sw_;
+        const float rr = dy * cw - dx * sw_;
+        const float cb = cr + 1.5f, rb = rr + 1.5f;
+        const int c = py * st + px;
+        const float gx = G[c + 1] - G[c - 1], gy = G[c + st] - G[c - st];
+        const float mag = sqrtf(gx * gx + gy * gy);
+        float ang = sift_atan2(gy, gx) - ori;
+        if (ang < 0.f) ang = ang + SIFT_2PI;
+        const float ob = ang * (8.0f / SIFT_2PI);
+        const float wgt = sift_exp((cr * cr + rr * rr) * -0.125f);
+        const float m = mag * wgt;
+        const float c0f = floorf(cb), r0f = floorf(rb), o0f = floorf(ob);
+        const float fc = cb - c0f, fr = rb - r0f, fo = ob - o0f;
+        const int c0 = (int)c0f, r0 = (int)r0f, o0 = (int)o0f;
 #pragma unroll
-            for (int dr = 0; dr < 2; ++dr) {
-                const int r_ = r0 + dr;
-                if (r_ < 0 || r_ > 3) continue;
-                const float wr = m * (dr ? fr : 1.0f - fr);
+        for (int dr = 0; dr < 2; ++dr) {
+            const int r_ = r0 + dr;
+            if (r_ < 0 || r_ > 3) continue;
+            const float wr = m * (dr ? fr : 1.0f - fr);
 #pragma unroll
-                for (int dc = 0; dc < 2; ++dc) {
-                    const int c_ = c0 + dc;
-                    if (c_ < 0 || c_ > 3) continue;
-                    const float wc = wr * (dc ? fc : 1.0f - fc);
+            for (int dc = 0; dc < 2; ++dc) {
+                const int c_ = c0 + dc;
+                if (c_ < 0 || c_ > 3) continue;
+                const float wc = wr * (dc ? fc : 1.0f - fc);
 #pragma unroll
-                    for (int dq = 0; dq < 2; ++dq) {
-                        const int o_ = (o0 + dq) & 7;
-                        const float wo = wc * (dq ? fo : 1.0f - fo);
-                        atomicAdd(&acc[wp][(r_ * 4 + c_) * 8 + o_], (unsigned)rintf(wo * SIFT_QSCALE));
-                    }
+                for (int dq = 0; dq < 2; ++dq) {
+                    const int o_ = (o0 + dq) & 7;
+                    const float wo = wc * (dq ? fo : 1.0f - fo);
+                    atomicAdd(&acc[wp][(r_ * 4 + c_) * 8 + o_], (unsigned)rintf(wo * SIFT_QSCALE));
                 }
             }
         }
+    };
+    int qn = 0;                                            // queued survivors (warp-uniform)
+    for (int jj = -R; jj <= R; ++jj) {
+        const int py = yi + jj;
+        if (py < 1 || py > h - 2) continue;
+        for (int i0 = -R; i0 <= R; i0 += 32) {
+            const int i = i0 + lane, px = xi + i;
+            bool ok = i <= R && px >= 1 && px <= w - 2;
+            if (ok) {
+                const float dx = (float)px - xo, dy = (float)py - yo;
+                const float cb = (dx * cw + dy * sw_) + 1.5f, rb = (dy * cw - dx * sw_) + 1.5f;
+                ok = cb > -1.0f && cb < 4.0f && rb > -1.0f && rb < 4.0f;
+            }
+            const unsigned msk = __ballot_sync(0xffffffffu, ok);
+            if (ok) squeue[wp][qn + __popc(msk & ((1u << lane) - 1))] = (unsigned)(i + 128) | ((unsigned)(jj + 128) << 8);
+            qn += __popc(msk);
+            __syncwarp();
+            if (qn >= 32) {
+                accumulate(squeue[wp][lane]);
+                const unsigned rest = lane < qn - 32 ? squeue[wp][32 + lane] : 0u;
+                __syncwarp();
+                if (lane < qn - 32) squeue[wp][lane] = rest;
+                qn -= 32;
+                __syncwarp();
+            }
+        }
     }
+    if (lane < qn) accumulate(squeue[wp][lane]);
     __syncwarp();
     unsigned u[4];
     unsigned long long s1 = 0;
