@@ -637,7 +637,7 @@ __device__ __forceinline__ float fast_atan2_deg(float y, float x) {
     return a;
 }
 
-__global__ void __launch_bounds__(256) k_describe(const __grid_constant__ AfvParams P, afv_keypoint* __restrict__ kps,
+__global__ void __launch_bounds__(256, 5) k_describe(const __grid_constant__ AfvParams P, afv_keypoint* __restrict__ kps,
                                                   uint8_t* __restrict__ desc, float* __restrict__ kpsize,
                                                   int* __restrict__ n_out) {
     __shared__ uint32_t patw[8][32];         // patw[k][lane] = (x0,y0,x1,y1) int8 of test k of descriptor byte `lane`
