@@ -44,7 +44,6 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t phase) {
 static __constant__ __align__(16) int8_t c_pattern[1024] = {
 #include "orb_pattern.inc"
 };
-static __constant__ int c_umax[16] = {15, 15, 15, 15, 14, 14, 14, 13, 13, 12, 11, 10, 9, 8, 6, 3};
 
 __device__ __forceinline__ int refl101(int i, int n) {
     if (i < 0) i = -i;
@@ -160,7 +159,6 @@ __global__ void __launch_bounds__(256) k_fast(const __grid_constant__ AfvParams 
     const int f = blockIdx.y;
     const int x0 = ti.x0, y0 = ti.y0;
     const int tid = threadIdx.x, lane = tid & 31, wrp = tid >> 5;
-    const uint8_t* img = L.img + (long long)f * L.img_fstride;
     const int t = P.fast_th;
 
     // stage the pixel tile with ONE TMA box load: FT_WP*4 = 160 bytes x FT_PH rows of frame f, starting at
@@ -179,13 +177,10 @@ __global__ void __launch_bounds__(256) k_fast(const __grid_constant__ AfvParams 
     for (int i = tid; i < FT_RH * FT_SW / 4; i += 256) reinterpret_cast<uint32_t*>(&score[0][0])[i] = 0;
     mbar_wait(&tma_bar, 0);
     __syncthreads();
-    (void)img; (void)wrp;
+    (void)wrp;
 
     const uint8_t* pb = reinterpret_cast<const uint8_t*>(&pixw[0][0]);
     constexpr int PITCH = FT_WP * 4;
-    const unsigned t2 = 2u * (unsigned)t;
-    // |p - v| > t  <=>  (unsigned)(p - v + t) > 2t
-#define FAR(p, v) ((unsigned)((int)(p) - (v) + t) > t2)
     // stage 1: sign-consistent compass test (below).  One thread walks 17 rows of one column with a rolling 15-pixel register window (centre, 3 above, 3 below
     // come from the window; only left/right are extra loads) and appends its survivors with one warp-aggregated atomic.
     static_assert(FT_RH == 2 * FT_HALF && FT_HALF <= 32, "two halves");
@@ -256,7 +251,6 @@ __global__ void __launch_bounds__(256) k_fast(const __grid_constant__ AfvParams 
         }
         warp_push(corner, (uint16_t)i, clist, &ncorner, lane);
     }
-#undef FAR
     __syncthreads();
 
     // corner score = max over the 16 arcs of 9 of min|v - p| (same sign), minus 1 (OpenCV cornerScore<16>)

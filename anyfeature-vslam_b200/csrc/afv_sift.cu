@@ -286,7 +286,6 @@ __global__ void __launch_bounds__(256) k_sift_orient(const __grid_constant__ Sif
         }
         __syncwarp();
         for (int b = lane; b < 36; b += 32) {
-            const float* dummy = nullptr; (void)dummy;
             const float hm2 = (float)hist[wp][(b + 34) % 36], hp2 = (float)hist[wp][(b + 2) % 36];
             const float hm1 = (float)hist[wp][(b + 35) % 36], hp1 = (float)hist[wp][(b + 1) % 36];
             hsm[wp][b] = ((hm2 + hp2) * 0.0625f + (hm1 + hp1) * 0.25f) + (float)hist[wp][b] * 0.375f;
