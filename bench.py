@@ -269,23 +269,6 @@ def run_gpu(args):
     pending = [None, None]
     step_counter = [0]
 
-    # optional: two arena / output sets on two streams, steps alternate (--resident-streams 2): the latency-bound matcher
-    # kernels of step i overlap the issue-bound pixel kernels of step i+1.  Single-GPU measurement aid; default off.
-    alt = None
-    if args.resident_streams == 2 and world == 1 and not MIXED:
-        ex_b = pkg.FeatureExtractor(FEAT, nfeatures=NFEAT, device=local, max_batch=B, max_w=W, max_h=H)
-        alt = dict(ex=ex_b, out=ex_b.alloc_device_outputs(B), m12=torch.empty_like(m12), nm=torch.empty_like(nm),
-                   streams=[torch.cuda.Stream(device=dev) for _ in range(2)], i=0)
-
-    def device_step_alt(src):
-        k = alt["i"] & 1
-        alt["i"] += 1
-        st = alt["streams"][k]
-        e_, o_, m_, n_ = (ex, out, m12, nm) if k == 0 else (alt["ex"], alt["out"], alt["m12"], alt["nm"])
-        e_.extract_batch_device(src, o_, st)
-        fm.search_for_initialization(o_[0], o_[1], o_[2], o_[3], d_pa, d_pb, None, BOUNDS, MAX_KPT_SIZE,
-                                     window=100, matches12=m_, nmatches=n_, stream=st)
-
     def device_step(src, collective=True):
         ex.extract_batch_device(src, out, stream)
         fm.search_for_initialization(out[0], out[1], out[2], out[3], d_pa, d_pb, None, BOUNDS, MAX_KPT_SIZE,
@@ -331,22 +314,12 @@ def run_gpu(args):
     e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()
-    if alt is None:
-        for _ in range(args.steps):
-            device_step(d_gray)
-        drain_collectives()                                # every step's results have reached rank 0
-    else:
-        for st_ in alt["streams"]:
-            st_.wait_stream(stream)                        # both streams start after e0
-        for _ in range(args.steps):
-            device_step_alt(d_gray)
-        for st_ in alt["streams"]:
-            stream.wait_stream(st_)                        # e1 after the last kernel of both streams
+    for _ in range(args.steps):
+        device_step(d_gray)
+    drain_collectives()                                    # every step's results have reached rank 0
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
-    if alt is not None:
-        assert (alt["nm"].cpu().numpy() == nm_host).all() and (alt["out"][3].cpu().numpy() == n_host).all(), "two-stream results differ"
     launches = pkg.kernel_launches() - launches0
 
     # ---- timed region 2: end to end from pinned host frames, results read back to pinned host buffers (e2e).
@@ -532,7 +505,6 @@ def run_gpu(args):
             "config": {"workload": WL["name"],
                        "frames_per_step_per_gpu": B, "pairs_per_step_per_gpu": B, "parallelism": "frames sharded, dp%d" % world,
                        "l2": "inputs+intermediates (%.1f GB/step) larger than L2, no flush" % (B * (54e6 * W * H / 921600 if FEAT == "sift128" else 36e6 * W * H / 307200 if FEAT == "akaze61" else 3.1e6 * W * H / 307200) / 1e9),
-                       "resident_streams": 2 if alt is not None else 1,
                        "gather": bool(world > 1 and args.gather), "gather_mode": "NCCL gather of packed results to rank 0 every step, overlapped with the next step"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": ms_e2e / args.steps, "h2d_gbs_measured": h2d_gbs, "single_frame_latency_ms": single_ms, "pipeline": "%d chunks of %d frames on 2 streams, host sync after the last step only" % (nchunks, CH)},
@@ -561,8 +533,6 @@ def main():
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS), help="BASELINE.json config: c2 = configs[1] (headline), c3 = configs[2], c5 = configs[4]")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-gather", dest="gather", action="store_false")
-    ap.add_argument("--resident-streams", type=int, default=1, choices=[1, 2],
-                    help="2: alternate the resident-input steps between two streams / arena sets (single GPU, experiment)")
     args = ap.parse_args()
     args.batch = select_workload(args.workload, args.batch)
     if args.impl == "reference":
