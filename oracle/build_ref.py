@@ -1,0 +1,341 @@
+"""Builds oracle/_ref/libafv_ref.so: function bodies of the REFERENCE, compiled from the sources where they lie under
+/root/reference (never copied into the repo; the generated translation unit lives only in the git-ignored oracle/_ref/).
+
+The reference's hot path as a whole cannot be built here (every TU needs OpenCV C++ headers, Eigen, ...), but the in-repo
+parts of the path are plain C++ over cv::KeyPoint / cv::Mat / STL.  This script cuts those function definitions out of the
+reference sources by signature, puts them behind oracle/ref_shim.hpp and adds extern "C" drivers:
+  src/ORBextractor.cc   ExtractorNode::DivideNode, FeatureExtractor::DistributeOctTree            (:181-458)
+  src/Frame.cc          Frame::AssignFeaturesToGrid, GetFeaturesInArea, PosInGrid                 (:225-240, :333-394)
+  src/FeatureMatcher.cc SearchForInitialization, DescriptorDistance, rotation-histogram helpers   (:399-557, :1508-1531, :1579-1668)
+  src/Feature_{orb32,akaze61,brisk48,sift128}.cpp   DescriptorDistance_<feat>
+tests/test_oracle_vs_ref.py checks the oracle restatement against this library.  TEST INFRASTRUCTURE ONLY.
+"""
+import os
+import re
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REF = os.environ.get("AFV_REFERENCE", "/root/reference")
+OUT_DIR = os.path.join(HERE, "_ref")
+OUT_SO = os.path.join(OUT_DIR, "libafv_ref.so")
+
+
+def cut(path, signature_regex, all_matches=False):
+    """Text of the function definition(s) whose first line matches the regex, up to the matching closing brace."""
+    src = open(os.path.join(REF, path), errors="ignore").read()
+    out = []
+    for m in re.finditer(signature_regex, src, flags=re.M):
+        i = src.index("{", m.end() - 1) if src[m.end() - 1] != "{" else m.end() - 1
+        depth, j = 0, i
+        while True:
+            c = src[j]
+            if c == "{":
+                depth += 1
+            elif c == "}":
+                depth -= 1
+                if depth == 0:
+                    break
+            j += 1
+        out.append(src[m.start():j + 1])
+        if not all_matches:
+            break
+    if not out:
+        raise SystemExit("build_ref: no match for %r in %s" % (signature_regex, path))
+    return "\n\n".join(out)
+
+
+def cut_between(path, start_marker, end_marker):
+    """Text of a reference source between two literal markers (start inclusive, end exclusive)."""
+    src = open(os.path.join(REF, path), errors="ignore").read()
+    a = src.index(start_marker)
+    b = src.index(end_marker, a)
+    return src[a:b]
+
+
+DRIVERS = r'''
+// ---- deterministic heap for the reference code -------------------------------------------------------------------------
+// DistributeOctTree sorts (nKeys, ExtractorNode*) pairs (src/ORBextractor.cc:381): among nodes with equal key counts the
+// division order -- and with it the kept set (by a few keypoints) and the output order -- depends on HEAP ADDRESSES.  With
+// the stock allocator the compiled reference does not even agree with itself between two calls on the same input
+// (tests/test_oracle_vs_ref.py::test_reference_octree_depends_on_heap_addresses).  For the comparison with the oracle this
+// library therefore runs the unmodified reference code on a monotonic bump allocator (-Wl,-Bsymbolic binds the library's
+// operator new / delete to these definitions): a later allocation has a larger address, which is the canonical tie order the
+// oracle documents.  ref_set_bump(0) restores malloc.
+#include <sys/mman.h>
+#include <cstdlib>
+#include <functional>
+#include <new>
+static char* g_arena = nullptr; static size_t g_arena_off = 0; static const size_t ARENA = (size_t)4 << 30; static int g_bump = 1;
+static void arena_reset() {
+    if (!g_arena) g_arena = (char*)mmap(nullptr, ARENA, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS | MAP_NORESERVE, -1, 0);
+    else madvise(g_arena, g_arena_off, MADV_DONTNEED);
+    g_arena_off = 0;
+}
+static inline bool in_arena(void* p) { return g_arena && (char*)p >= g_arena && (char*)p < g_arena + ARENA; }
+void* operator new(size_t n) {
+    if (g_bump && g_arena) { const size_t a = (g_arena_off + 15) & ~(size_t)15; if (a + n <= ARENA) { g_arena_off = a + n; return g_arena + a; } }
+    void* p = malloc(n ? n : 1); if (!p) throw std::bad_alloc(); return p;
+}
+void operator delete(void* p) noexcept { if (p && !in_arena(p)) free(p); }
+void operator delete(void* p, size_t) noexcept { if (p && !in_arena(p)) free(p); }
+extern "C" void ref_set_bump(int on) { g_bump = on; }
+
+namespace ANYFEATURE_VSLAM {
+float Frame::mfGridElementWidthInv = 0, Frame::mfGridElementHeightInv = 0, Frame::mnMinX = 0, Frame::mnMaxX = 0, Frame::mnMinY = 0, Frame::mnMaxY = 0;
+Descriptor_Distance_Type FeatureMatcher::TH_HIGH = 0, FeatureMatcher::TH_LOW = 0;
+float FeatureMatcher::radiusScale = 1.0f;
+float FeatureExtractorSettings::scaleFactor0 = 1.2f;
+const int FeatureMatcher::HISTO_LENGTH = 30;                       // src/FeatureMatcher.cc:64
+}
+using namespace ANYFEATURE_VSLAM;
+struct kp7 { float x, y, size, angle, response; int octave, class_id; };
+static void fill_frame(Frame& F, const kp7* k, int n, void* desc, int dcols, int dtype, const float* ksize, float max_kpt_size) {
+    F.N = n; F.mvKeysUn.resize(n); F.keyPtsSize.assign(ksize, ksize + n); F.maxKeyPtSize = max_kpt_size;
+    for (int i = 0; i < n; ++i) { cv::KeyPoint p; p.pt.x = k[i].x; p.pt.y = k[i].y; p.size = k[i].size; p.angle = k[i].angle; p.response = k[i].response; p.octave = k[i].octave; p.class_id = k[i].class_id; F.mvKeysUn[i] = p; }
+    F.mDescriptors = cv::Mat(n, dcols, dtype, desc);
+    F.AssignFeaturesToGrid();
+}
+extern "C" {
+// FeatureExtractor::DistributeOctTree on keypoints (x, y, response); returns the kept keypoints' (x, y, response) in list order
+int ref_distribute_octree(const float* px, const float* py, const float* resp, int n, int minX, int maxX, int minY, int maxY, int N,
+                          float* ox, float* oy, float* oresp, int cap) {
+    if (g_bump) arena_reset();
+    int m = 0;
+    {
+        std::vector<cv::KeyPoint> v(n);
+        for (int i = 0; i < n; ++i) { v[i].pt.x = px[i]; v[i].pt.y = py[i]; v[i].response = resp[i]; v[i].class_id = i; }
+        FeatureExtractor fe;
+        std::vector<cv::KeyPoint> r = fe.DistributeOctTree(v, minX, maxX, minY, maxY, N, 0);
+        for (size_t i = 0; i < r.size() && (int)i < cap; ++i) { ox[i] = r[i].pt.x; oy[i] = r[i].pt.y; oresp[i] = (float)r[i].class_id; }
+        m = (int)r.size();
+    }
+    return m;
+}
+// FeatureMatcher::SearchForInitialization between two frames given as arrays; prev (n1 x 2) is updated like vbPrevMatched
+int ref_search_for_initialization(int desc_type, int dcols, int dtype, const kp7* k1, void* d1, const float* s1, int n1,
+                                  const kp7* k2, void* d2, const float* s2, int n2, float minX, float minY, float maxX, float maxY,
+                                  float max_kpt_size, float* prev, int window, float th_low, float nnratio, int check_ori, int* matches12) {
+    Frame::mnMinX = minX; Frame::mnMinY = minY; Frame::mnMaxX = maxX; Frame::mnMaxY = maxY;
+    Frame::mfGridElementWidthInv = static_cast<float>(FRAME_GRID_COLS) / (maxX - minX);      // src/Frame.cc:198-199
+    Frame::mfGridElementHeightInv = static_cast<float>(FRAME_GRID_ROWS) / (maxY - minY);
+    FeatureMatcher::TH_LOW = th_low; FeatureMatcher::TH_HIGH = th_low;
+    Frame F1, F2;
+    fill_frame(F1, k1, n1, d1, dcols, dtype, s1, max_kpt_size);
+    fill_frame(F2, k2, n2, d2, dcols, dtype, s2, max_kpt_size);
+    std::vector<cv::Point2f> pm(n1);
+    for (int i = 0; i < n1; ++i) { pm[i].x = prev[2 * i]; pm[i].y = prev[2 * i + 1]; }
+    std::vector<int> m12;
+    FeatureMatcher fm(nnratio, check_ori != 0);
+    const int nm = fm.SearchForInitialization(F1, F2, pm, m12, window, (DescriptorType)desc_type);
+    for (int i = 0; i < n1; ++i) { matches12[i] = m12[i]; prev[2 * i] = pm[i].x; prev[2 * i + 1] = pm[i].y; }
+    return nm;
+}
+// Frame::GetFeaturesInArea on one frame
+int ref_features_in_area(const kp7* k, const float* ksize, int n, float minX, float minY, float maxX, float maxY, float x, float y, float r,
+                         float min_size, float max_size, int* out, int cap) {
+    Frame::mnMinX = minX; Frame::mnMinY = minY; Frame::mnMaxX = maxX; Frame::mnMaxY = maxY;
+    Frame::mfGridElementWidthInv = static_cast<float>(FRAME_GRID_COLS) / (maxX - minX);
+    Frame::mfGridElementHeightInv = static_cast<float>(FRAME_GRID_ROWS) / (maxY - minY);
+    Frame F;
+    unsigned char dummy = 0;
+    fill_frame(F, k, n, &dummy, 1, 0, ksize, 0.f);
+    std::vector<size_t> v = F.GetFeaturesInArea(x, y, r, min_size, max_size);
+    for (size_t i = 0; i < v.size() && (int)i < cap; ++i) out[i] = (int)v[i];
+    return (int)v.size();
+}
+// FeatureMatcher::SearchByProjection(Frame&, vector<Pt>&, radiusTh) (TrackLocalMap): query i = a map point with descriptor,
+// projected position, predicted size and viewing cosine; occupied[idx] != 0 = keypoint idx already holds an observed map point.
+int ref_search_by_projection(int desc_type, int dcols, int dtype, void* qdesc, const float* qxy, const float* qsize, const float* qcos, int nq,
+                             const kp7* k, void* d, const float* ksize, int n, const unsigned char* occupied, float minX, float minY,
+                             float maxX, float maxY, float radius_th, float radius_scale, float size_tol, float th_high, float nnratio,
+                             int* match_q) {
+    Frame::mnMinX = minX; Frame::mnMinY = minY; Frame::mnMaxX = maxX; Frame::mnMaxY = maxY;
+    Frame::mfGridElementWidthInv = static_cast<float>(FRAME_GRID_COLS) / (maxX - minX);
+    Frame::mfGridElementHeightInv = static_cast<float>(FRAME_GRID_ROWS) / (maxY - minY);
+    FeatureMatcher::TH_HIGH = th_high; FeatureMatcher::TH_LOW = th_high; FeatureMatcher::radiusScale = radius_scale;
+    Frame F;
+    fill_frame(F, k, n, d, dcols, dtype, ksize, 0.f);
+    F.sizeTolerance = size_tol; F.invSizeTolerance = 1.0f / size_tol;       // src/Frame.cc:182-183
+    F.pts.assign(n, Pt()); F.mvuRight.assign(n, -1.0f);
+    Pt held = std::make_shared<MapPoint>();
+    for (int i = 0; i < n; ++i) if (occupied && occupied[i]) F.pts[i] = held;
+    std::vector<Pt> q(nq);
+    cv::Mat Q(nq, dcols, dtype, qdesc);
+    for (int i = 0; i < nq; ++i) {
+        q[i] = std::make_shared<MapPoint>();
+        q[i]->desc = Q.row(i); q[i]->descriptorType = (DescriptorType)desc_type; q[i]->trackSize = qsize[i]; q[i]->trackViewCos = qcos[i];
+        q[i]->mTrackProjX = qxy[2 * i]; q[i]->mTrackProjY = qxy[2 * i + 1];
+    }
+    FeatureMatcher fm(nnratio, true);
+    const int nm = fm.SearchByProjection(F, q, radius_th);
+    for (int i = 0; i < nq; ++i) match_q[i] = -1;
+    for (int idx = 0; idx < n; ++idx)
+        if (F.pts[idx] && F.pts[idx] != held)
+            for (int i = 0; i < nq; ++i) if (F.pts[idx] == q[i]) { match_q[i] = idx; break; }
+    return nm;
+}
+// FeatureMatcher::SearchByBoW(KF, F): FeatureVectors as (node ids, CSR starts, feature indices); every keyframe keypoint
+// holds a good map point.  match_f[f] = keyframe keypoint index matched to frame keypoint f, or -1.
+int ref_search_by_bow(int desc_type, int dcols, int dtype, const kp7* kkf, void* dkf, int nkf, const int* kf_node, const int* kf_start,
+                      const int* kf_idx, int kf_nodes, const kp7* kf_, void* df, int nf, const int* f_node, const int* f_start,
+                      const int* f_idx, int f_nodes, float th_low, float nnratio, int check_ori, int* match_f) {
+    FeatureMatcher::TH_LOW = th_low; FeatureMatcher::TH_HIGH = th_low;
+    Keyframe KF = std::make_shared<KeyFrame>();
+    KF->mvKeysUn.resize(nkf); KF->mappoints.resize(nkf);
+    for (int i = 0; i < nkf; ++i) {
+        cv::KeyPoint p; p.pt.x = kkf[i].x; p.pt.y = kkf[i].y; p.angle = kkf[i].angle; p.octave = kkf[i].octave; KF->mvKeysUn[i] = p;
+        KF->mappoints[i] = std::make_shared<MapPoint>(); KF->mappoints[i]->descriptorType = (DescriptorType)desc_type;
+    }
+    KF->mDescriptors = cv::Mat(nkf, dcols, dtype, dkf);
+    for (int s = 0; s < kf_nodes; ++s) for (int j = kf_start[s]; j < kf_start[s + 1]; ++j) KF->mFeatVec[(unsigned)kf_node[s]].push_back((unsigned)kf_idx[j]);
+    Frame F;
+    F.N = nf; F.mvKeys.resize(nf);
+    for (int i = 0; i < nf; ++i) { cv::KeyPoint p; p.pt.x = kf_[i].x; p.pt.y = kf_[i].y; p.angle = kf_[i].angle; p.octave = kf_[i].octave; F.mvKeys[i] = p; }
+    F.mDescriptors = cv::Mat(nf, dcols, dtype, df);
+    for (int s = 0; s < f_nodes; ++s) for (int j = f_start[s]; j < f_start[s + 1]; ++j) F.mFeatVec[(unsigned)f_node[s]].push_back((unsigned)f_idx[j]);
+    std::vector<Pt> matches;
+    FeatureMatcher fm(nnratio, check_ori != 0);
+    const int nm = fm.SearchByBoW(KF, F, matches);
+    for (int f = 0; f < nf; ++f) {
+        match_f[f] = -1;
+        if (matches[f]) for (int i = 0; i < nkf; ++i) if (KF->mappoints[i] == matches[f]) { match_f[f] = i; break; }
+    }
+    return nm;
+}
+// Vocabulary::transform (src/Vocabulary.cpp:156-207 -> TemplatedVocabulary::transform per feature, levelsup 4 in the reference):
+// the tree comes as CSR children lists + per-node descriptor / word id / weight (node 0 = root)
+}   // extern "C"
+template <class F, class MakeDesc>
+static void bow_run(int n, const int* child_off, const int* child_ids, int nnodes, const int* node_word, const double* node_weight, int L,
+                    int levelsup, MakeDesc mk_node, MakeDesc mk_feat, int* word_id, double* weight, int* node_id) {
+    DBoW2::TemplatedVocabulary<typename F::TDescriptor, F> V;
+    V.m_L = L; V.m_nodes.resize(nnodes);
+    for (int i = 0; i < nnodes; ++i) {
+        V.m_nodes[i].id = i; V.m_nodes[i].weight = node_weight[i]; V.m_nodes[i].word_id = node_word[i] < 0 ? 0 : node_word[i];
+        V.m_nodes[i].descriptor = mk_node(i);
+        for (int j = child_off[i]; j < child_off[i + 1]; ++j) V.m_nodes[i].children.push_back((DBoW2::NodeId)child_ids[j]);
+    }
+    for (int f = 0; f < n; ++f) {
+        DBoW2::WordId w = 0; DBoW2::WordValue wt = 0; DBoW2::NodeId nid = 0;
+        V.transform(mk_feat(f), w, wt, &nid, levelsup);
+        word_id[f] = (int)w; weight[f] = wt; node_id[f] = (int)nid;
+    }
+}
+extern "C" {
+int ref_bow_transform(int desc_type, void* desc, int n, const int* child_off, const int* child_ids, int nnodes, void* node_desc,
+                      const int* node_word, const double* node_weight, int L, int levelsup, int* word_id, double* weight, int* node_id) {
+    if (desc_type == 5) {
+        const float* nd = (const float*)node_desc; const float* fd = (const float*)desc;
+        auto mkn = [&](int i) { return std::vector<float>(nd + (size_t)i * 128, nd + (size_t)(i + 1) * 128); };
+        auto mkf = [&](int i) { return std::vector<float>(fd + (size_t)i * 128, fd + (size_t)(i + 1) * 128); };
+        bow_run<DBoW2::FSift128, std::function<std::vector<float>(int)>>(n, child_off, child_ids, nnodes, node_word, node_weight, L, levelsup, mkn, mkf, word_id, weight, node_id);
+        return 0;
+    }
+    const int D = desc_type == 0 ? 32 : desc_type == 1 ? 61 : 48;
+    // rows are copied into 8-byte aligned, zero-padded storage: the DBoW2 distances read uint64_t / int32_t words
+    const int Dp = (D + 7) & ~7;
+    std::vector<uint64_t> nbuf((size_t)nnodes * Dp / 8, 0), fbuf((size_t)(n > 0 ? n : 1) * Dp / 8, 0);
+    for (int i = 0; i < nnodes; ++i) memcpy((char*)nbuf.data() + (size_t)i * Dp, (char*)node_desc + (size_t)i * D, D);
+    for (int i = 0; i < n; ++i) memcpy((char*)fbuf.data() + (size_t)i * Dp, (char*)desc + (size_t)i * D, D);
+    auto mkn = [&](int i) { return cv::Mat(1, D, 0, (char*)nbuf.data() + (size_t)i * Dp); };
+    auto mkf = [&](int i) { return cv::Mat(1, D, 0, (char*)fbuf.data() + (size_t)i * Dp); };
+    typedef std::function<cv::Mat(int)> MK;
+    if (desc_type == 0) bow_run<DBoW2::FOrb, MK>(n, child_off, child_ids, nnodes, node_word, node_weight, L, levelsup, mkn, mkf, word_id, weight, node_id);
+    else if (desc_type == 1) bow_run<DBoW2::FAkaze61, MK>(n, child_off, child_ids, nnodes, node_word, node_weight, L, levelsup, mkn, mkf, word_id, weight, node_id);
+    else bow_run<DBoW2::FBrisk, MK>(n, child_off, child_ids, nnodes, node_word, node_weight, L, levelsup, mkn, mkf, word_id, weight, node_id);
+    return 0;
+}
+// FeatureExtractor constructor (src/FeatureExtractor.cpp:74-109: mvScaleFactor, mnFeaturesPerLevel) + computeSize (:132-142)
+int ref_extractor_tables(int nfeatures, int nlevels, float scale_factor, float* scale_factors, int* quota, float* size_norm) {
+    std::shared_ptr<FeatureExtractorSettings> st = std::make_shared<FeatureExtractorSettings>();
+    st->scaleFactor = scale_factor; st->nOctaves = nlevels; FeatureExtractorSettings::scaleFactor0 = scale_factor;
+    st->maxKeyPtSize0 = pow(1.2f, float(8 - 1.0)); st->maxKeyPtSize = st->maxKeyPtSize0; st->minKeyPtSize = 1.0f;   // :52-55
+    FeatureExtractor fe(nfeatures, st);
+    std::vector<cv::KeyPoint> k(nlevels);
+    for (int l = 0; l < nlevels; ++l) k[l].octave = l;
+    std::vector<float> sz;
+    fe.computeSize(sz, k);
+    for (int l = 0; l < nlevels; ++l) { scale_factors[l] = fe.mvScaleFactor[l]; quota[l] = fe.mnFeaturesPerLevel[l]; size_norm[l] = sz[l]; }
+    return nlevels;
+}
+// MapPoint::ComputeDistinctiveDescriptors on rows obs[0..n) of a descriptor matrix: returns the position (into obs) of the pick
+int ref_distinctive_descriptor(int desc_type, int dcols, int dtype, void* desc, const int* obs, int n) {
+    cv::Mat M(1 << 30, dcols, dtype, desc);
+    std::vector<cv::Mat> d;
+    for (int i = 0; i < n; ++i) d.push_back(M.row(obs[i]));
+    return ref_distinctive_core(d, (DescriptorType)desc_type);
+}
+float ref_descriptor_distance(int desc_type, int dcols, int dtype, void* a, void* b) {
+    return FeatureMatcher::DescriptorDistance(cv::Mat(1, dcols, dtype, a), cv::Mat(1, dcols, dtype, b), (DescriptorType)desc_type);
+}
+}
+'''
+
+
+def build(force=False):
+    if not os.path.isdir(REF):
+        return None                                        # e.g. on the GPU box: only the prebuilt library is used
+    os.makedirs(OUT_DIR, exist_ok=True)
+    gen = os.path.join(OUT_DIR, "ref_extract.cpp")
+    if not force and os.path.exists(OUT_SO) and os.path.getmtime(OUT_SO) > max(os.path.getmtime(__file__), os.path.getmtime(os.path.join(HERE, "ref_shim.hpp"))):
+        return OUT_SO
+    parts = ['#include "../ref_shim.hpp"', "namespace ANYFEATURE_VSLAM {"]
+    parts.append(cut("src/ORBextractor.cc", r"^void ExtractorNode::DivideNode\("))
+    parts.append(cut("src/ORBextractor.cc", r"^vector<cv::KeyPoint> FeatureExtractor::DistributeOctTree\("))
+    parts.append(cut("src/FeatureExtractor.cpp", r"^ANYFEATURE_VSLAM::FeatureExtractor::FeatureExtractor\(const int& nfeatures_"))
+    parts.append(cut("src/FeatureExtractor.cpp", r"^void ANYFEATURE_VSLAM::FeatureExtractor::computeSize\("))
+    parts.append(cut("src/Frame.cc", r"^void Frame::AssignFeaturesToGrid\(\)"))
+    parts.append(cut("src/Frame.cc", r"^vector<size_t> Frame::GetFeaturesInArea\("))
+    parts.append(cut("src/Frame.cc", r"^bool Frame::PosInGrid\("))
+    parts.append(cut("src/FeatureMatcher.cc", r"^int FeatureMatcher::SearchForInitialization\("))
+    parts.append(cut("src/FeatureMatcher.cc", r"^int FeatureMatcher::SearchByProjection\(Frame &F, const vector<Pt> &vpMapPoints, const float& radiusTh\)"))
+    parts.append(cut("src/FeatureMatcher.cc", r"^float FeatureMatcher::RadiusByViewingCos\("))
+    parts.append(cut("src/FeatureMatcher.cc", r"^int FeatureMatcher::SearchByBoW\(Keyframe pKF, Frame &F, vector<Pt> &vpMapPointMatches\)"))
+    parts.append(cut("src/FeatureMatcher.cc", r"^Descriptor_Distance_Type FeatureMatcher::DescriptorDistance\("))
+    parts.append(cut("src/FeatureMatcher.cc", r"^\s*vector<vector<int>> FeatureMatcher::initRotationHistogram\("))
+    parts.append(cut("src/FeatureMatcher.cc", r"^\s*void FeatureMatcher::updateRotationHistogram\("))
+    parts.append(cut("src/FeatureMatcher.cc", r"^\s*void FeatureMatcher::filterMatchesWithOrientation\(", all_matches=True))
+    parts.append(cut("src/FeatureMatcher.cc", r"^\s*void FeatureMatcher::computeThreeMaxima\("))
+    parts.append("}  // namespace ANYFEATURE_VSLAM")
+    for feat in ("orb32", "akaze61", "brisk48", "sift128"):
+        parts.append(cut("src/Feature_%s.cpp" % feat, r"^float ANYFEATURE_VSLAM::DescriptorDistance_%s\(" % feat))
+    # ---- MapPoint::ComputeDistinctiveDescriptors (src/MapPoint.cc:279-348): the distance matrix + least-median pick, i.e. the
+    # function body between the collection of the observed descriptors and the locked write-back
+    parts.append("namespace ANYFEATURE_VSLAM {\nint ref_distinctive_core(const std::vector<cv::Mat>& descriptors, DescriptorType descriptorType) {")
+    parts.append(cut_between("src/MapPoint.cc", "    // Compute distances between them", "    {\n        unique_lock<mutex> lock(mMutexFeatures);\n        mDescriptor = descriptors[BestIdx].clone();"))
+    parts.append("    return BestIdx;\n}\n}  // namespace ANYFEATURE_VSLAM")
+    # ---- DBoW2 (vendored by the reference under Thirdparty/DBoW2): tree descent + the per-feature distances it uses
+    parts.append("""
+#include <climits>
+namespace DBoW2 {
+typedef unsigned int WordId; typedef double WordValue; typedef unsigned int NodeId;
+template <class TDescriptor, class F> class TemplatedVocabulary {     // TemplatedVocabulary.h: the members transform() reads
+public:
+    struct Node { NodeId id; WordValue weight; std::vector<NodeId> children; NodeId parent; TDescriptor descriptor; WordId word_id;
+                  Node() : id(0), weight(0), parent(0), word_id(0) {} inline bool isLeaf() const { return children.empty(); } };
+    int m_L; std::vector<Node> m_nodes;
+    void transform(const TDescriptor& feature, WordId& word_id, WordValue& weight, NodeId* nid, int levelsup) const;
+};
+struct FOrb { typedef cv::Mat TDescriptor; static const int L = 32; static double distance(const TDescriptor& a, const TDescriptor& b); };
+struct FAkaze61 { typedef cv::Mat TDescriptor; static const int L = 61; static double distance(const TDescriptor& a, const TDescriptor& b); };
+struct FBrisk { typedef cv::Mat TDescriptor; static const int L = 48; static double distance(const TDescriptor& a, const TDescriptor& b); };
+struct FSift128 { typedef std::vector<float> TDescriptor; static const int L = 128; static double distance(const TDescriptor& a, const TDescriptor& b); };
+""")
+    parts.append(cut("Thirdparty/DBoW2/include/DBoW2/TemplatedVocabulary.h",
+                     r"^template<class TDescriptor, class F>\nvoid TemplatedVocabulary<TDescriptor,F>::transform\(const TDescriptor &feature, \n\s*WordId &word_id, WordValue &weight, NodeId \*nid, int levelsup\) const"))
+    parts.append(cut("Thirdparty/DBoW2/src/FOrb.cpp", r"^\s*double FOrb::distance\("))
+    parts.append(cut("Thirdparty/DBoW2/src/FAkaze61.cpp", r"^\s*double FAkaze61::distance\("))
+    parts.append(cut("Thirdparty/DBoW2/src/FBrisk.cpp", r"^\s*double FBrisk::distance\("))
+    parts.append(cut("Thirdparty/DBoW2/src/FSift128.cpp", r"^\s*double FSift128::distance\("))
+    parts.append("}  // namespace DBoW2")
+    parts.append(DRIVERS)
+    open(gen, "w").write("\n\n".join(parts) + "\n")
+    # same optimisation level family as the reference's CMakeLists.txt:16 (-O3 -march=native)
+    cmd = ["g++", "-std=c++17", "-O3", "-march=native", "-fPIC", "-shared", "-w", "-Wl,-Bsymbolic", "-o", OUT_SO, gen]
+    subprocess.check_call(cmd)
+    return OUT_SO
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv))

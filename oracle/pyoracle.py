@@ -354,3 +354,17 @@ def undistort_keypoints(kps, K4, dist5):
     out = np.zeros_like(kps)
     lib().orc_undistort_keypoints(_p(kps), len(kps), _p(K4), _p(dist5), _p(out))
     return out
+
+
+def features_in_area(kps, kpsize, bounds, x, y, r, min_size, max_size):
+    """Frame::AssignFeaturesToGrid + GetFeaturesInArea (src/Frame.cc:225-240, :333-382): indices in reference order."""
+    kps = np.ascontiguousarray(kps); kpsize = np.ascontiguousarray(kpsize, np.float32)
+    n = len(kps)
+    minX, minY, maxX, maxY = bounds
+    invW = np.float32(64.0) / (np.float32(maxX) - np.float32(minX)); invH = np.float32(48.0) / (np.float32(maxY) - np.float32(minY))
+    cs = np.zeros(64 * 48 + 1, np.int32); ci = np.zeros(max(n, 1), np.int32)
+    lib().orc_grid_build(_p(kps), n, _f(minX), _f(minY), _f(invW), _f(invH), _p(cs), _p(ci))
+    out = np.zeros(max(n, 1), np.int32)
+    m = lib().orc_features_in_area(_p(kps), _p(kpsize), _p(cs), _p(ci), _f(minX), _f(minY), _f(invW), _f(invH), _f(x), _f(y), _f(r),
+                                   _f(min_size), _f(max_size), _p(out), len(out))
+    return out[:m].copy()

@@ -1,0 +1,174 @@
+// ref_shim.hpp -- TEST INFRASTRUCTURE.  The smallest set of declarations that lets a handful of function bodies of the
+// REFERENCE (extracted at build time from /root/reference by oracle/build_ref.py, never copied into this repo) compile
+// without OpenCV / Eigen: cv::KeyPoint / Point / Mat look-alikes with the members those bodies touch, and skeleton
+// declarations of the reference classes they belong to (member names as in include/Frame.h, include/FeatureMatcher.h,
+// include/FeatureExtractor.h:164-175 of the reference).  cv::norm is this repo's restatement of OpenCV (third party).
+#pragma once
+#include <algorithm>
+#include <cassert>
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <iostream>
+#include <limits>
+#include <list>
+#include <map>
+#include <memory>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+static inline int cvRound(double v) { return (int)lrint(v); }       // OpenCV: round half to even
+namespace cv {
+template <typename T> struct Point_ { T x, y; Point_() : x(0), y(0) {} Point_(T x_, T y_) : x(x_), y(y_) {} };
+typedef Point_<int> Point2i;
+typedef Point_<float> Point2f;
+typedef Point2i Point;
+struct KeyPoint { Point2f pt; float size = 0, angle = -1, response = 0; int octave = 0, class_id = -1; };
+enum { NORM_L2SQR = 5, NORM_HAMMING = 6 };
+struct Mat {                                   // continuous row-major view; type 0 = CV_8U, 5 = CV_32F
+    int rows = 0, cols = 0, type_ = 0;
+    unsigned char* data = nullptr;
+    size_t step = 0;
+    Mat() {}
+    Mat(int r, int c, int t, void* d) : rows(r), cols(c), type_(t), data((unsigned char*)d), step((size_t)c * (t == 5 ? 4 : 1)) {}
+    Mat row(int i) const { Mat m(1, cols, type_, data + (size_t)i * step); return m; }
+    template <typename T> T* ptr(int r = 0) { return reinterpret_cast<T*>(data + (size_t)r * step); }
+    template <typename T> const T* ptr(int r = 0) const { return reinterpret_cast<const T*>(data + (size_t)r * step); }
+};
+// OpenCV: NORM_HAMMING = popcount of the xor over all bytes; NORM_L2SQR on CV_32F accumulates the squared differences in double
+inline double norm(const Mat& a, const Mat& b, int normType) {
+    if (normType == NORM_HAMMING) {
+        int d = 0;
+        for (int i = 0; i < a.cols; ++i) d += __builtin_popcount((unsigned)(a.data[i] ^ b.data[i]));
+        return (double)d;
+    }
+    const float* pa = a.ptr<float>(); const float* pb = b.ptr<float>();
+    double s = 0;
+    for (int i = 0; i < a.cols; ++i) { const double v = (double)pa[i] - (double)pb[i]; s += v * v; }
+    return s;
+}
+}  // namespace cv
+
+#define FRAME_GRID_ROWS 48
+#define FRAME_GRID_COLS 64
+
+namespace ANYFEATURE_VSLAM {
+using namespace std;
+using namespace cv;
+typedef float Descriptor_Distance_Type;
+using KeypointIndex = int;
+enum DescriptorType { DESC_ANYFEATNONBIN = 8, DESC_ANYFEATBIN = 7, DESC_R2D2 = 6, DESC_SIFT128 = 5, DESC_KAZE64 = 4, DESC_SURF64 = 3,
+                      DESC_BRISK = 2, DESC_AKAZE61 = 1, DESC_ORB = 0 };
+struct MapPoint {                                // include/MapPoint.h: the members SearchByProjection (src/FeatureMatcher.cc:73-154) touches
+    bool mbTrackInView = true, bad = false;
+    float trackSize = 1, trackViewCos = 1, mTrackProjX = 0, mTrackProjY = 0, mTrackProjXR = 0, trackSigma = 1;
+    cv::Mat desc; int nobs = 1;
+    bool isBad() const { return bad; }
+    cv::Mat GetDescriptor() const { return desc; }
+    int NumberOfObservations() const { return nobs; }
+    DescriptorType descriptorType = DESC_ORB;
+};
+typedef std::shared_ptr<MapPoint> Pt;
+
+// per-feature distances: orb32 / akaze61 / brisk48 / sift128 bodies are extracted from the reference; the rest is unused here
+float DescriptorDistance_orb32(const cv::Mat& a, const cv::Mat& b);
+float DescriptorDistance_akaze61(const cv::Mat& a, const cv::Mat& b);
+float DescriptorDistance_brisk48(const cv::Mat& a, const cv::Mat& b);
+float DescriptorDistance_sift128(const cv::Mat& a, const cv::Mat& b);
+inline float DescriptorDistance_anyFeatureNonBin(const cv::Mat&, const cv::Mat&) { return 0; }
+inline float DescriptorDistance_anyFeatureBin(const cv::Mat&, const cv::Mat&) { return 0; }
+inline float DescriptorDistance_r2d2_128(const cv::Mat&, const cv::Mat&) { return 0; }
+inline float DescriptorDistance_kaze64(const cv::Mat&, const cv::Mat&) { return 0; }
+inline float DescriptorDistance_surf64(const cv::Mat&, const cv::Mat&) { return 0; }
+
+namespace DBoW2_shim { typedef std::map<unsigned int, std::vector<unsigned int>> FeatureVector; }   // DBoW2::FeatureVector
+}  // namespace ANYFEATURE_VSLAM
+namespace DBoW2 { using ANYFEATURE_VSLAM::DBoW2_shim::FeatureVector; }
+namespace ANYFEATURE_VSLAM {
+
+class Frame {                                   // include/Frame.h: the members the extracted bodies use
+public:
+    int N = 0;
+    std::vector<cv::KeyPoint> mvKeysUn;
+    cv::Mat mDescriptors;
+    vector<float> keyPtsSize{};
+    float maxKeyPtSize{};
+    static float mfGridElementWidthInv, mfGridElementHeightInv, mnMinX, mnMaxX, mnMinY, mnMaxY;
+    std::vector<std::size_t> mGrid[FRAME_GRID_COLS][FRAME_GRID_ROWS];
+    std::vector<cv::KeyPoint> mvKeys;
+    DBoW2::FeatureVector mFeatVec;
+    std::vector<Pt> pts;                         // map point held by each keypoint
+    std::vector<float> mvuRight;                 // < 0 in the monocular case
+    float sizeTolerance{}, invSizeTolerance{};
+    float GetKeyPtSize(const KeypointIndex& idx) const { return keyPtsSize[idx]; }
+    void AssignFeaturesToGrid();
+    vector<size_t> GetFeaturesInArea(const float& x, const float& y, const float& r, const float& minSize, const float& maxSize) const;
+    bool PosInGrid(const cv::KeyPoint& kp, int& posX, int& posY);
+};
+
+class KeyFrame {                                // include/KeyFrame.h: what SearchByBoW(KF, F) reads
+public:
+    std::vector<Pt> mappoints;
+    std::vector<Pt> GetMapPointMatches() { return mappoints; }
+    DBoW2::FeatureVector mFeatVec;
+    cv::Mat mDescriptors;
+    std::vector<cv::KeyPoint> mvKeysUn;
+};
+typedef std::shared_ptr<KeyFrame> Keyframe;
+
+class FeatureMatcher {                          // include/FeatureMatcher.h:36-118
+public:
+    FeatureMatcher(float nnratio = 0.6, bool checkOri = true) : mfNNratio(nnratio), mbCheckOrientation(checkOri) {}
+    int SearchForInitialization(Frame& F1, Frame& F2, vector<cv::Point2f>& vbPrevMatched, vector<int>& vnMatches12, const int& windowSize,
+                                const DescriptorType& descriptorType);
+    static Descriptor_Distance_Type DescriptorDistance(const cv::Mat& a, const cv::Mat& b, const DescriptorType& descriptorType_);
+    int SearchByProjection(Frame& F, const vector<Pt>& vpMapPoints, const float& radiusTh);
+    int SearchByBoW(Keyframe pKF, Frame& F, vector<Pt>& vpMapPointMatches);
+    float RadiusByViewingCos(const float& viewCos);
+    static float radiusScale;
+    static Descriptor_Distance_Type TH_LOW, TH_HIGH;
+    static const int HISTO_LENGTH;
+    vector<vector<int>> initRotationHistogram(float& rotFactor, const int& histLength);
+    void updateRotationHistogram(vector<vector<int>>& rotHist, const KeypointIndex& idx, const cv::KeyPoint& keyPt, const cv::KeyPoint& refKeyPt,
+                                 const float& rotFactor, const int& histLength);
+    void filterMatchesWithOrientation(vector<vector<int>>& rotHist, vector<Pt>& points, int& nMatches);
+    void filterMatchesWithOrientation(vector<vector<int>>& rotHist, vector<int>& matches, int& nMatches);
+    void computeThreeMaxima(vector<vector<int>>& rotHist, int& ind1, int& ind2, int& ind3);
+    float mfNNratio; bool mbCheckOrientation;
+    const Descriptor_Distance_Type highestPossibleDistance{std::numeric_limits<Descriptor_Distance_Type>::max()};
+};
+
+class ExtractorNode {                           // include/FeatureExtractor.h:164-175
+public:
+    ExtractorNode() : bNoMore(false) {}
+    void DivideNode(ExtractorNode& n1, ExtractorNode& n2, ExtractorNode& n3, ExtractorNode& n4);
+    std::vector<cv::KeyPoint> vKeys;
+    cv::Point2i UL, UR, BL, BR;
+    std::list<ExtractorNode>::iterator lit;
+    bool bNoMore;
+};
+struct FeatureExtractorSettings {               // include/FeatureExtractor.h:24-66 (the fields the constructor / computeSize read)
+    float scaleFactor = 1.2f; int nOctaves = 8;
+    float maxKeyPtSize = 0, minKeyPtSize = 1.0f, maxKeyPtSize0 = 0;
+    static float scaleFactor0;
+    static float GetDetectorNominalScaleFactor() { return scaleFactor0; }
+};
+class FeatureExtractor {
+public:
+    FeatureExtractor() {}
+    FeatureExtractor(const int& nfeatures_, std::shared_ptr<FeatureExtractorSettings>& settings_);
+    virtual ~FeatureExtractor() {}
+    std::shared_ptr<FeatureExtractorSettings> settings{};
+    std::vector<float> mvScaleFactor, mvInvScaleFactor, mvLevelSigma2, mvInvLevelSigma2;
+    std::vector<cv::Mat> mvImagePyramid;
+    std::vector<int> mnFeaturesPerLevel;
+    void computeSize(std::vector<float>& keyPtsSize, const std::vector<cv::KeyPoint>& keypoints);
+    virtual int GetKeypointOctave(const cv::KeyPoint& keypoint) const { return keypoint.octave; }
+    virtual float GetKeypointSize(const cv::KeyPoint& keypoint) const {      // src/Feature_orb32.cpp:59-61 (same in every Feature_*)
+        return powf(settings->GetDetectorNominalScaleFactor(), float(GetKeypointOctave(keypoint))); }
+    int nfeatures = 1000;
+    std::vector<cv::KeyPoint> DistributeOctTree(const std::vector<cv::KeyPoint>& vToDistributeKeys, const int& minX, const int& maxX,
+                                                const int& minY, const int& maxY, const int& N, const int& level) const;
+};
+}  // namespace ANYFEATURE_VSLAM

@@ -1,0 +1,288 @@
+"""The oracle's restatement of the IN-REPO parts of the reference path, checked against the reference's OWN code:
+oracle/build_ref.py cuts DistributeOctTree / DivideNode, Frame::AssignFeaturesToGrid / GetFeaturesInArea / PosInGrid,
+FeatureMatcher::SearchForInitialization / DescriptorDistance / the rotation-histogram helpers and the per-feature
+DescriptorDistance_* out of /root/reference at build time and compiles them behind oracle/ref_shim.hpp into
+oracle/_ref/libafv_ref.so (git-ignored; it travels to the GPU box as a binary).  Skipped when that library is absent."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+from oracle import pyoracle as po
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF_SO = os.path.join(ROOT, "oracle", "_ref", "libafv_ref.so")
+
+
+@pytest.fixture(scope="module")
+def ref():
+    if not os.path.exists(REF_SO):
+        from oracle import build_ref
+        if build_ref.build() is None:
+            pytest.skip("oracle/_ref/libafv_ref.so not built and /root/reference not present")
+    lib = C.CDLL(REF_SO)
+    lib.ref_descriptor_distance.restype = C.c_float
+    return lib
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def _ref_octree(ref, px, py, resp, w, h, N):
+    n = len(px)
+    ox = np.zeros(n + 8, np.float32); oy = np.zeros(n + 8, np.float32); oi = np.zeros(n + 8, np.float32)
+    m = ref.ref_distribute_octree(_p(px), _p(py), _p(resp), n, 0, int(w), 0, int(h), int(N), _p(ox), _p(oy), _p(oi), n + 8)
+    return oi[:m].astype(np.int64)
+
+
+def test_distribute_octree_on_real_detect_lists(ref, synth):
+    """orb32 detect lists (cv::ORB::detect-equivalent, per level) of three frames, both quotas."""
+    checked = 0
+    for stream, (w, h) in ((0, (640, 480)), (3, (640, 480)), (1, (1280, 720))):
+        img = synth.stream_frames(w, h, stream, 1)[0][0]
+        levels, ls = po.pyramid(img)
+        for nfeat in (1000, 2000):
+            q_orb = po.features_per_level(nfeat * 10); q_ext = po.features_per_level(nfeat)
+            for l in range(8):
+                dx, dy, hr, _ = po.detect_level(levels[l], 20, q_orb[l])
+                px = dx.astype(np.float32) * ls[l]; py = dy.astype(np.float32) * ls[l]
+                keep = po.octree(px, py, hr, w, h, q_ext[l])
+                rk = _ref_octree(ref, px, py, hr, w, h, q_ext[l])
+                assert len(keep) == len(rk) and (np.asarray(keep) == rk).all(), (stream, nfeat, l)
+                checked += 1
+    assert checked == 48
+
+
+def test_distribute_octree_random_and_equal_responses(ref):
+    """Random clouds incl. equal responses (sift128: every response is 1) and duplicate positions."""
+    rng = np.random.default_rng(5)
+    for trial in range(60):
+        n = int(rng.integers(1, 4000))
+        w, h = ((640, 480), (1280, 720), (752, 480))[trial % 3]
+        px = rng.uniform(0, w - 1e-3, n).astype(np.float32); py = rng.uniform(0, h - 1e-3, n).astype(np.float32)
+        if trial % 4 == 0:
+            px = np.minimum(np.round(px), w - 1); py = np.minimum(np.round(py), h - 1)   # integer grid -> duplicates, boundary hits
+            # (x == w would index past vpIniNodes in the reference, src/ORBextractor.cc:268: keypoints never lie there)
+        resp = np.ones(n, np.float32) if trial % 2 else rng.uniform(0, 1, n).astype(np.float32)
+        N = int(rng.integers(1, 1200))
+        keep = po.octree(px, py, resp, w, h, N)
+        rk = _ref_octree(ref, px, py, resp, w, h, N)
+        assert len(keep) == len(rk) and (np.asarray(keep) == rk).all(), trial
+
+
+def test_reference_octree_depends_on_heap_addresses(ref, synth):
+    """Documented property of the REFERENCE, not of this repo: DistributeOctTree sorts (nKeys, ExtractorNode*) pairs
+    (src/ORBextractor.cc:381), so with the stock allocator ties are broken by heap addresses -- the kept set differs by a few
+    keypoints and the order changes from call to call.  Same count, same quota; the oracle (and the CUDA path) use the
+    canonical order "later-created node = larger address", which is what the reference does on a monotonic heap."""
+    img = synth.stream_frames(640, 480, 0, 1)[0][0]
+    levels, ls = po.pyramid(img)
+    q_orb = po.features_per_level(10000); q_ext = po.features_per_level(1000)
+    dx, dy, hr, _ = po.detect_level(levels[0], 20, q_orb[0])
+    px = dx.astype(np.float32); py = dy.astype(np.float32)
+    canon = _ref_octree(ref, px, py, hr, 640, 480, q_ext[0])
+    ref.ref_set_bump(0)
+    try:
+        runs = [_ref_octree(ref, px, py, hr, 640, 480, q_ext[0]) for _ in range(4)]
+    finally:
+        ref.ref_set_bump(1)
+    for r in runs:
+        assert len(r) == len(canon)                                        # the count never depends on the heap
+        assert len(set(r.tolist()) ^ set(canon.tolist())) <= 0.15 * len(canon)   # the set only by a few tie cases
+    again = _ref_octree(ref, px, py, hr, 640, 480, q_ext[0])
+    assert (again == canon).all()                                          # deterministic on the monotonic heap
+
+
+def _kp7(k):
+    return np.ascontiguousarray(k).view(np.uint8).reshape(len(k), 28)
+
+
+@pytest.mark.parametrize("feature", ["orb32", "akaze61", "sift128"])
+def test_search_for_initialization_vs_reference_code(ref, synth, feature):
+    frames, _ = synth.stream_frames(640, 480, 9, 3)
+    if feature == "orb32":
+        ex = lambda im: po.orb32_extract(im, 1000)[:3]; dt, dcols, dtype, th = 0, 32, 0, 75.0
+    elif feature == "akaze61":
+        ex = lambda im: po.akaze61_extract(im, 1000)[:3]; dt, dcols, dtype, th = 1, 61, 0, 128.0
+    else:
+        ex = lambda im: po.sift128_extract(im, 1000)[:3]; dt, dcols, dtype, th = 5, 128, 5, 0.5
+    E = [ex(f) for f in frames]
+    bounds = (0.0, 0.0, 640.0, 480.0)
+    max_size = float(np.float32(1.2) ** np.float32(7))
+    for check_ori in (True, False):
+        k0, d0, s0 = E[0]
+        prev = np.stack([k0["x"], k0["y"]], axis=1).astype(np.float32)
+        prev_ref = prev.copy()
+        for j in (1, 2):                                          # second call chains the updated vbPrevMatched
+            k1, d1, s1 = E[j]
+            n_o, m_o, prev = po.search_for_initialization(dt, k0, d0, k1, d1, s1, bounds, max_size, prev, window=100,
+                                                          th_low=th, nnratio=0.9, check_ori=check_ori)
+            m_r = np.zeros(len(k0), np.int32)
+            d0c = np.ascontiguousarray(d0); d1c = np.ascontiguousarray(d1)
+            n_r = ref.ref_search_for_initialization(dt, dcols, dtype, _p(_kp7(k0)), _p(d0c), _p(np.ascontiguousarray(s0)), len(k0),
+                                                    _p(_kp7(k1)), _p(d1c), _p(np.ascontiguousarray(s1)), len(k1),
+                                                    C.c_float(0.0), C.c_float(0.0), C.c_float(640.0), C.c_float(480.0), C.c_float(max_size),
+                                                    _p(prev_ref), 100, C.c_float(th), C.c_float(0.9), int(check_ori), _p(m_r))
+            assert n_o == n_r and n_r > 20, (feature, j, n_o, n_r)
+            assert (m_o == m_r).all() and (prev == prev_ref).all()
+
+
+def test_features_in_area_vs_reference_code(ref, synth):
+    img = synth.stream_frames(640, 480, 2, 1)[0][0]
+    k, d, s, _ = po.orb32_extract(img, 1000)
+    rng = np.random.default_rng(1)
+    for _ in range(300):
+        x, y = float(rng.uniform(-50, 700)), float(rng.uniform(-50, 530))
+        r = float(rng.choice([5.0, 15.0, 40.0, 100.0])); lo = float(rng.choice([0.0, 1.0, 1.3])); hi = float(rng.choice([1.5, 2.5, 3.6]))
+        out = np.zeros(len(k) + 8, np.int32)
+        m = ref.ref_features_in_area(_p(_kp7(k)), _p(np.ascontiguousarray(s)), len(k), C.c_float(0.0), C.c_float(0.0), C.c_float(640.0),
+                                     C.c_float(480.0), C.c_float(x), C.c_float(y), C.c_float(r), C.c_float(lo), C.c_float(hi), _p(out), len(out))
+        got = po.features_in_area(k, s, (0.0, 0.0, 640.0, 480.0), x, y, r, lo, hi)
+        assert list(got) == out[:m].tolist()
+
+
+def test_descriptor_distance_vs_reference_code(ref):
+    rng = np.random.default_rng(2)
+    for dt, dcols, dtype in ((0, 32, 0), (1, 61, 0), (2, 48, 0), (5, 128, 5)):
+        for _ in range(200):
+            if dtype == 0:
+                a = rng.integers(0, 256, dcols, dtype=np.uint8); b = rng.integers(0, 256, dcols, dtype=np.uint8)
+            else:
+                a = rng.normal(size=dcols).astype(np.float32); b = rng.normal(size=dcols).astype(np.float32)
+                a /= np.linalg.norm(a); b /= np.linalg.norm(b)
+            r = ref.ref_descriptor_distance(dt, dcols, dtype, _p(a), _p(b))
+            o = po.descriptor_distance(dt, a, b)
+            assert (r == o) if dtype == 0 else abs(r - o) <= 1e-6 * max(r, 1e-9), (dt, r, o)
+
+
+@pytest.mark.parametrize("feature", ["orb32", "akaze61"])
+def test_search_by_projection_vs_reference_code(ref, synth, feature):
+    """FeatureMatcher::SearchByProjection(Frame&, vector<Pt>&, radiusTh) (src/FeatureMatcher.cc:73-154, TrackLocalMap): map
+    points = keypoints of frame 0 projected with a small error into frame 1; some train keypoints already hold map points."""
+    frames, offs = synth.stream_frames(640, 480, 12, 2)
+    if feature == "orb32":
+        ex = lambda im: po.orb32_extract(im, 1000)[:3]; dt, dcols, th, tol = 0, 32, 75.0, np.float32(1.2)
+    else:
+        ex = lambda im: po.akaze61_extract(im, 1000)[:3]; dt, dcols, th, tol = 1, 61, 128.0, np.float32(1.1892)
+    (k0, d0, s0), (k1, d1, s1) = ex(frames[0]), ex(frames[1])
+    rng = np.random.default_rng(4)
+    shift = (offs[1] - offs[0]).astype(np.float32)
+    nq = len(k0)
+    qxy = np.stack([k0["x"] - shift[0], k0["y"] - shift[1]], axis=1).astype(np.float32) + rng.normal(0, 1.5, (nq, 2)).astype(np.float32)
+    qsize = s0.astype(np.float32)
+    qcos = rng.choice(np.array([0.9995, 0.95], np.float32), nq)
+    occupied = (rng.random(len(k1)) < 0.15).astype(np.uint8)
+    radius_th, radius_scale = np.float32(1.0), np.float32(1.0)
+    rcos = np.where(qcos > np.float32(0.998), np.float32(2.5), np.float32(4.0)).astype(np.float32)
+    qr = ((radius_scale * radius_th) * rcos) * qsize                  # :88, evaluated left to right in float
+    qmin = qsize / tol; qmax = qsize * tol                             # :91-92
+    for nnratio in (0.8, 0.6):
+        n_o, m_o = po.search_by_projection(dt, d0, qxy, qr, qmin, qmax, k1, d1, s1, (0.0, 0.0, 640.0, 480.0), occupied=occupied,
+                                           th=th, nnratio=nnratio, ratio_same_scale=True, tol=float(tol))
+        m_r = np.zeros(nq, np.int32)
+        d0c = np.ascontiguousarray(d0); d1c = np.ascontiguousarray(d1)
+        n_r = ref.ref_search_by_projection(dt, dcols, 0, _p(d0c), _p(qxy), _p(qsize), _p(qcos), nq, _p(_kp7(k1)), _p(d1c),
+                                           _p(np.ascontiguousarray(s1)), len(k1), _p(occupied), C.c_float(0.0), C.c_float(0.0),
+                                           C.c_float(640.0), C.c_float(480.0), C.c_float(radius_th), C.c_float(radius_scale),
+                                           C.c_float(tol), C.c_float(th), C.c_float(nnratio), _p(m_r))
+        assert n_o == n_r and n_r > 100, (feature, n_o, n_r)
+        assert (m_o == m_r).all()
+
+
+@pytest.mark.parametrize("check_ori", [True, False])
+def test_search_by_bow_vs_reference_code(ref, synth, check_ori):
+    """FeatureMatcher::SearchByBoW(KF, F) (src/FeatureMatcher.cc:186-283) on synthetic FeatureVectors (bucket = coarse
+    position hash, so true matches share a node; node id sets differ between the two frames -> lower_bound jumps)."""
+    frames, offs = synth.stream_frames(640, 480, 0, 2)
+    (k1, d1, s1, _), (k2, d2, s2, _) = po.orb32_extract(frames[0], 1000), po.orb32_extract(frames[1], 1000)
+    dx, dy = (offs[1] - offs[0]).tolist()
+
+    def segs(k, shift):
+        node = ((k["x"] + shift[0]) // 80).astype(np.int32) * 10 + ((k["y"] + shift[1]) // 80).astype(np.int32)
+        order = np.argsort(node, kind="stable")
+        ids, starts = np.unique(node[order], return_index=True)
+        return ids.astype(np.int32), np.append(starts, len(k)).astype(np.int32), order.astype(np.int32)
+    a, b = segs(k1, (0, 0)), segs(k2, (dx, dy))
+    n_o, mf_o = po.search_by_bow(0, d1, k1, a, d2, k2, b, th_low=75.0, nnratio=0.7, check_ori=check_ori)
+    mf_r = np.zeros(len(k2), np.int32)
+    d1c = np.ascontiguousarray(d1); d2c = np.ascontiguousarray(d2)
+    n_r = ref.ref_search_by_bow(0, 32, 0, _p(_kp7(k1)), _p(d1c), len(k1), _p(a[0]), _p(a[1]), _p(a[2]), len(a[0]),
+                                _p(_kp7(k2)), _p(d2c), len(k2), _p(b[0]), _p(b[1]), _p(b[2]), len(b[0]),
+                                C.c_float(75.0), C.c_float(0.7), int(check_ori), _p(mf_r))
+    assert n_o == n_r and n_r > 100
+    assert (mf_o == mf_r).all()
+
+
+@pytest.mark.parametrize("desc_type,D,float_desc", [(0, 32, False), (1, 61, False), (2, 48, False), (5, 128, True)])
+def test_bow_transform_vs_dbow2_code(ref, desc_type, D, float_desc):
+    """Vocabulary::transform -> DBoW2 TemplatedVocabulary::transform (Thirdparty/DBoW2, vendored by the reference) with the
+    feature classes' own distance functions (FOrb, FAkaze61 -- which only compares floor(61/8)*8 = 56 bytes --, FBrisk,
+    FSift128) on a synthetic k-ary tree, levelsup 4 (reference), 1 and > L."""
+    from bow_tree import make_tree
+    rng = np.random.default_rng(11)
+    tree = make_tree(rng, k=10, L=3, D=D, float_desc=float_desc)
+    nn = len(tree["node_word"])
+    if float_desc:
+        feats = (tree["node_desc"][rng.integers(1, nn, 400)] + rng.normal(scale=0.2, size=(400, 128))).astype(np.float32)
+    else:
+        base = tree["node_desc"][rng.integers(1, nn, 400)]
+        feats = base ^ np.packbits((rng.random((400, D, 8)) < 0.08).astype(np.uint8), axis=2).reshape(400, D)
+    feats = np.ascontiguousarray(feats)
+    for levelsup in (4, 1, 2):
+        wid, w, nid = po.bow_transform(desc_type, feats, tree, levelsup=levelsup)
+        rw = np.zeros(400, np.int32); rwt = np.zeros(400, np.float64); rn = np.zeros(400, np.int32)
+        co = np.ascontiguousarray(tree["child_off"], np.int32); ci = np.ascontiguousarray(tree["child_ids"], np.int32)
+        nd = np.ascontiguousarray(tree["node_desc"]); nw = np.ascontiguousarray(tree["node_word"], np.int32)
+        wt = np.ascontiguousarray(tree["node_weight"], np.float64)
+        ref.ref_bow_transform(desc_type, _p(feats), 400, _p(co), _p(ci), nn, _p(nd), _p(nw), _p(wt), int(tree["L"]), levelsup,
+                              _p(rw), _p(rwt), _p(rn))
+        assert (wid == rw).all() and (w == rwt).all() and (nid == rn).all(), (desc_type, levelsup)
+
+
+@pytest.mark.parametrize("nfeatures,nlevels,sf", [(1000, 8, 1.2), (2000, 8, 1.2), (1000, 8, 2.0), (2000, 8, 2.0), (1000, 8, 1.1892), (1500, 8, 1.5)])
+def test_extractor_tables_vs_reference_code(ref, nfeatures, nlevels, sf):
+    """mnFeaturesPerLevel / mvScaleFactor of the FeatureExtractor constructor (src/FeatureExtractor.cpp:74-109) and computeSize
+    (:132-142) from the reference's own code == the oracle (and, through tests/test_extract_gpu.py, the CUDA library)."""
+    sc = np.zeros(nlevels, np.float32); q = np.zeros(nlevels, np.int32); sn = np.zeros(nlevels, np.float32)
+    ref.ref_extractor_tables(nfeatures, nlevels, C.c_float(sf), _p(sc), _p(q), _p(sn))
+    assert (po.features_per_level(nfeatures, nlevels, sf) == q).all()
+    s = np.float32(1.0); want = []
+    for l in range(nlevels):
+        want.append(s); s = np.float32(s * np.float32(sf))
+    assert (np.array(want, np.float32) == sc).all()
+    assert sn[0] == 1.0 and (np.diff(sn) > 0).all()           # the size table is compared on real frames in the next test
+
+
+def test_compute_size_vs_reference_code(ref, synth):
+    frames, _ = synth.stream_frames(640, 480, 4, 1)
+    for feat, sf, fn in (("orb32", 1.2, lambda im: po.orb32_extract(im, 1000)), ("sift128", 2.0, lambda im: po.sift128_extract(im, 1000)),
+                         ("akaze61", 1.1892, lambda im: po.akaze61_extract(im, 1000))):
+        k, d, size, _ = fn(frames[0])
+        sc = np.zeros(8, np.float32); q = np.zeros(8, np.int32); sn = np.zeros(8, np.float32)
+        ref.ref_extractor_tables(1000, 8, C.c_float(sf), _p(sc), _p(q), _p(sn))
+        lvl = k["class_id"] if feat == "akaze61" else k["octave"]                # GetKeypointOctave of the subclass
+        assert (size == sn[lvl]).all(), feat
+
+
+@pytest.mark.parametrize("desc_type,D,dtype", [(0, 32, 0), (1, 61, 0), (2, 48, 0), (5, 128, 5)])
+def test_distinctive_descriptor_vs_reference_code(ref, desc_type, D, dtype):
+    """MapPoint::ComputeDistinctiveDescriptors (src/MapPoint.cc:279-348): least-median-distance descriptor, first minimum wins,
+    median index 0.5*(N-1) truncated -- the reference's own loop vs the oracle, for 1..40 observations."""
+    rng = np.random.default_rng(13)
+    for trial in range(120):
+        n = int(rng.integers(1, 41))
+        if dtype == 0:
+            centre = rng.integers(0, 256, D, dtype=np.uint8)
+            desc = centre ^ np.packbits((rng.random((64, D, 8)) < 0.15).astype(np.uint8), axis=2).reshape(64, D)
+            if trial % 5 == 0:
+                desc[3] = desc[1]                                   # exact ties
+        else:
+            desc = rng.normal(size=(64, D)).astype(np.float32)
+            desc /= np.linalg.norm(desc, axis=1, keepdims=True)
+        desc = np.ascontiguousarray(desc)
+        obs = rng.choice(64, n, replace=False).astype(np.int32)
+        r = ref.ref_distinctive_descriptor(desc_type, D, dtype, _p(desc), _p(obs), n)
+        o = po.distinctive_descriptor(desc_type, desc, obs)
+        assert r == o, (desc_type, trial, n, r, o)
