@@ -266,6 +266,13 @@ int ref_distinctive_descriptor(int desc_type, int dcols, int dtype, void* desc, 
     for (int i = 0; i < n; ++i) d.push_back(M.row(obs[i]));
     return ref_distinctive_core(d, (DescriptorType)desc_type);
 }
+// computeOrbDescriptor of the reference header on a (blurred) level image
+void ref_orb_descriptor(unsigned char* img, int w, int h, int stride, float x, float y, float angle_deg, unsigned char* desc32) {
+    cv::Mat M(h, w, 0, img); M.step = (size_t)stride;
+    cv::KeyPoint kp; kp.pt.x = x; kp.pt.y = y; kp.angle = angle_deg;
+    computeOrbDescriptor(kp, M, (const cv::Point*)bit_pattern_31_, desc32);
+}
+const int* ref_orb_pattern() { return bit_pattern_31_; }
 float ref_descriptor_distance(int desc_type, int dcols, int dtype, void* a, void* b) {
     return FeatureMatcher::DescriptorDistance(cv::Mat(1, dcols, dtype, a), cv::Mat(1, dcols, dtype, b), (DescriptorType)desc_type);
 }
@@ -281,6 +288,10 @@ def build(force=False):
     if not force and os.path.exists(OUT_SO) and os.path.getmtime(OUT_SO) > max(os.path.getmtime(__file__), os.path.getmtime(os.path.join(HERE, "ref_shim.hpp"))):
         return OUT_SO
     parts = ['#include "../ref_shim.hpp"', "namespace ANYFEATURE_VSLAM {"]
+    # steered BRIEF of the reference header (include/FeatureExtractor.h:177-217) and its 256 x 4 pattern table (:219-477)
+    parts.append("const float factorPI = (float)(CV_PI/180.f);")
+    parts.append(cut("include/FeatureExtractor.h", r"^\s*static void computeOrbDescriptor\("))
+    parts.append(cut("include/FeatureExtractor.h", r"^\s*static int bit_pattern_31_\[256\*4\] =") + ";")
     parts.append(cut("src/ORBextractor.cc", r"^void ExtractorNode::DivideNode\("))
     parts.append(cut("src/ORBextractor.cc", r"^vector<cv::KeyPoint> FeatureExtractor::DistributeOctTree\("))
     parts.append(cut("src/FeatureExtractor.cpp", r"^ANYFEATURE_VSLAM::FeatureExtractor::FeatureExtractor\(const int& nfeatures_"))

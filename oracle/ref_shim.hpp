@@ -19,6 +19,8 @@
 #include <vector>
 
 static inline int cvRound(double v) { return (int)lrint(v); }       // OpenCV: round half to even
+typedef unsigned char uchar;
+#define CV_PI 3.1415926535897932384626433832795
 namespace cv {
 template <typename T> struct Point_ { T x, y; Point_() : x(0), y(0) {} Point_(T x_, T y_) : x(x_), y(y_) {} };
 typedef Point_<int> Point2i;
@@ -33,6 +35,8 @@ struct Mat {                                   // continuous row-major view; typ
     Mat() {}
     Mat(int r, int c, int t, void* d) : rows(r), cols(c), type_(t), data((unsigned char*)d), step((size_t)c * (t == 5 ? 4 : 1)) {}
     Mat row(int i) const { Mat m(1, cols, type_, data + (size_t)i * step); return m; }
+    template <typename T> T& at(int r, int c) { return reinterpret_cast<T*>(data + (size_t)r * step)[c]; }
+    template <typename T> const T& at(int r, int c) const { return reinterpret_cast<const T*>(data + (size_t)r * step)[c]; }
     template <typename T> T* ptr(int r = 0) { return reinterpret_cast<T*>(data + (size_t)r * step); }
     template <typename T> const T* ptr(int r = 0) const { return reinterpret_cast<const T*>(data + (size_t)r * step); }
 };

@@ -286,3 +286,25 @@ def test_distinctive_descriptor_vs_reference_code(ref, desc_type, D, dtype):
         r = ref.ref_distinctive_descriptor(desc_type, D, dtype, _p(desc), _p(obs), n)
         o = po.distinctive_descriptor(desc_type, desc, obs)
         assert r == o, (desc_type, trial, n, r, o)
+
+
+def test_steered_brief_vs_reference_header(ref, synth):
+    """The reference header's own computeOrbDescriptor + bit_pattern_31_ (include/FeatureExtractor.h:177-477) on the blurred
+    level == the oracle's rBRIEF (which is pinned to cv::ORB::compute): same pattern table, same rotation / rounding."""
+    ref.ref_orb_pattern.restype = C.POINTER(C.c_int)
+    pat = np.ctypeslib.as_array(ref.ref_orb_pattern(), shape=(1024,)).astype(np.int8)
+    import re
+    inc = re.sub(r"/\*.*?\*/", "", open(os.path.join(ROOT, "oracle", "orb_pattern.inc")).read(), flags=re.S)
+    mine = np.array([int(t) for t in re.findall(r"-?\d+", inc)], np.int8)
+    assert (pat == mine).all()
+    img = synth.stream_frames(640, 480, 6, 1)[0][0]
+    blur = po.blur7(img)
+    rng = np.random.default_rng(3)
+    L = po.lib()
+    for _ in range(2000):
+        x, y = int(rng.integers(25, 615)), int(rng.integers(25, 455))
+        ang = float(np.float32(rng.uniform(0, 360)))
+        a = np.zeros(32, np.uint8); b = np.zeros(32, np.uint8)
+        ref.ref_orb_descriptor(_p(blur), 640, 480, 640, C.c_float(x), C.c_float(y), C.c_float(ang), _p(a))
+        L.orc_rbrief32(_p(img), _p(blur), 640, 480, 640, x, y, C.c_float(ang), _p(b))
+        assert (a == b).all(), (x, y, ang)
