@@ -273,6 +273,40 @@ void ref_orb_descriptor(unsigned char* img, int w, int h, int stride, float x, f
     computeOrbDescriptor(kp, M, (const cv::Point*)bit_pattern_31_, desc32);
 }
 const int* ref_orb_pattern() { return bit_pattern_31_; }
+// FeatureMatcher::SearchByProjection(CurrentFrame, LastFrame, radiusTh, bMono) (TrackWithMotionModel, :1291-1402): identity
+// poses, fx = fy = 1, cx = cy = 0 and world points (u, v, 1) make the projection of last-frame map point i land exactly on
+// qxy[i]; LastFrame.GetKeyPtSize(i) = qsize[i].  match_q[i] = current-frame keypoint matched to query i, or -1.
+int ref_search_by_projection_frames(int desc_type, int dcols, int dtype, void* qdesc, const float* qxy, const float* qsize, const float* qangle,
+                                    int nq, const kp7* k, void* d, const float* ksize, int n, const unsigned char* occupied, float minX,
+                                    float minY, float maxX, float maxY, float radius_th, float radius_scale, float size_tol, float th_high,
+                                    int check_ori, int* match_q) {
+    Frame::mnMinX = minX; Frame::mnMinY = minY; Frame::mnMaxX = maxX; Frame::mnMaxY = maxY;
+    Frame::mfGridElementWidthInv = static_cast<float>(FRAME_GRID_COLS) / (maxX - minX);
+    Frame::mfGridElementHeightInv = static_cast<float>(FRAME_GRID_ROWS) / (maxY - minY);
+    FeatureMatcher::TH_HIGH = th_high; FeatureMatcher::TH_LOW = th_high; FeatureMatcher::radiusScale = radius_scale;
+    Frame Cur;
+    fill_frame(Cur, k, n, d, dcols, dtype, ksize, 0.f);
+    Cur.sizeTolerance = size_tol; Cur.invSizeTolerance = 1.0f / size_tol;
+    Cur.pts.assign(n, Pt()); Cur.mvuRight.assign(n, -1.0f);
+    Pt held = std::make_shared<MapPoint>();
+    for (int i = 0; i < n; ++i) if (occupied && occupied[i]) Cur.pts[i] = held;
+    Frame Last;
+    Last.N = nq; Last.mvKeysUn.resize(nq); Last.keyPtsSize.assign(qsize, qsize + nq); Last.pts.resize(nq); Last.mvbOutlier.assign(nq, false);
+    cv::Mat Q(nq, dcols, dtype, qdesc);
+    for (int i = 0; i < nq; ++i) {
+        Last.mvKeysUn[i].angle = qangle[i];
+        Last.pts[i] = std::make_shared<MapPoint>();
+        Last.pts[i]->desc = Q.row(i); Last.pts[i]->descriptorType = (DescriptorType)desc_type;
+        Last.pts[i]->worldPos.v[0] = qxy[2 * i]; Last.pts[i]->worldPos.v[1] = qxy[2 * i + 1]; Last.pts[i]->worldPos.v[2] = 1.0f;
+    }
+    FeatureMatcher fm(0.9f, check_ori != 0);
+    const int nm = fm.SearchByProjection(Cur, Last, radius_th, true);
+    for (int i = 0; i < nq; ++i) match_q[i] = -1;
+    for (int idx = 0; idx < n; ++idx)
+        if (Cur.pts[idx] && Cur.pts[idx] != held)
+            for (int i = 0; i < nq; ++i) if (Cur.pts[idx] == Last.pts[i]) { match_q[i] = idx; break; }
+    return nm;
+}
 float ref_descriptor_distance(int desc_type, int dcols, int dtype, void* a, void* b) {
     return FeatureMatcher::DescriptorDistance(cv::Mat(1, dcols, dtype, a), cv::Mat(1, dcols, dtype, b), (DescriptorType)desc_type);
 }
@@ -302,6 +336,7 @@ def build(force=False):
     parts.append(cut("src/FeatureMatcher.cc", r"^int FeatureMatcher::SearchForInitialization\("))
     parts.append(cut("src/FeatureMatcher.cc", r"^int FeatureMatcher::SearchByProjection\(Frame &F, const vector<Pt> &vpMapPoints, const float& radiusTh\)"))
     parts.append(cut("src/FeatureMatcher.cc", r"^float FeatureMatcher::RadiusByViewingCos\("))
+    parts.append(cut("src/FeatureMatcher.cc", r"^int FeatureMatcher::SearchByProjection\(Frame &CurrentFrame, const Frame &LastFrame, const float& radiusTh, const bool bMono\)"))
     parts.append(cut("src/FeatureMatcher.cc", r"^int FeatureMatcher::SearchByBoW\(Keyframe pKF, Frame &F, vector<Pt> &vpMapPointMatches\)"))
     parts.append(cut("src/FeatureMatcher.cc", r"^Descriptor_Distance_Type FeatureMatcher::DescriptorDistance\("))
     parts.append(cut("src/FeatureMatcher.cc", r"^\s*vector<vector<int>> FeatureMatcher::initRotationHistogram\("))

@@ -64,10 +64,30 @@ typedef float Descriptor_Distance_Type;
 using KeypointIndex = int;
 enum DescriptorType { DESC_ANYFEATNONBIN = 8, DESC_ANYFEATBIN = 7, DESC_R2D2 = 6, DESC_SIFT128 = 5, DESC_KAZE64 = 4, DESC_SURF64 = 3,
                       DESC_BRISK = 2, DESC_AKAZE61 = 1, DESC_ORB = 0 };
+// the few Eigen fixed-size operations the projection prologue of SearchByProjection (src/FeatureMatcher.cc:1299-1308) uses
+struct vec3f { float v[3] = {0, 0, 0}; float operator()(int i) const { return v[i]; } float& operator()(int i) { return v[i]; } };
+inline vec3f operator+(const vec3f& a, const vec3f& b) { vec3f r; for (int i = 0; i < 3; ++i) r.v[i] = a.v[i] + b.v[i]; return r; }
+struct mat3f {
+    float m[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
+    mat3f transpose() const { mat3f r; for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) r.m[i][j] = m[j][i]; return r; }
+    mat3f operator-() const { mat3f r; for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) r.m[i][j] = -m[i][j]; return r; }
+    vec3f operator*(const vec3f& x) const { vec3f r; for (int i = 0; i < 3; ++i) r.v[i] = (m[i][0] * x.v[0] + m[i][1] * x.v[1]) + m[i][2] * x.v[2]; return r; }
+};
+template <int R, int C> struct blk_t { typedef mat3f type; };
+template <> struct blk_t<3, 1> { typedef vec3f type; };
+struct mat4f {
+    float m[4][4] = {{1, 0, 0, 0}, {0, 1, 0, 0}, {0, 0, 1, 0}, {0, 0, 0, 1}};
+    template <int R, int C> typename blk_t<R, C>::type block(int r, int c) const;
+};
+template <> inline mat3f mat4f::block<3, 3>(int r, int c) const { mat3f o; for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) o.m[i][j] = m[r + i][c + j]; return o; }
+template <> inline vec3f mat4f::block<3, 1>(int r, int c) const { vec3f o; for (int i = 0; i < 3; ++i) o.v[i] = m[r + i][c]; return o; }
+
 struct MapPoint {                                // include/MapPoint.h: the members SearchByProjection (src/FeatureMatcher.cc:73-154) touches
     bool mbTrackInView = true, bad = false;
     float trackSize = 1, trackViewCos = 1, mTrackProjX = 0, mTrackProjY = 0, mTrackProjXR = 0, trackSigma = 1;
     cv::Mat desc; int nobs = 1;
+    vec3f worldPos;
+    vec3f GetWorldPos() const { return worldPos; }
     bool isBad() const { return bad; }
     cv::Mat GetDescriptor() const { return desc; }
     int NumberOfObservations() const { return nobs; }
@@ -101,6 +121,8 @@ public:
     static float mfGridElementWidthInv, mfGridElementHeightInv, mnMinX, mnMaxX, mnMinY, mnMaxY;
     std::vector<std::size_t> mGrid[FRAME_GRID_COLS][FRAME_GRID_ROWS];
     std::vector<cv::KeyPoint> mvKeys;
+    mat4f Tcw; float fx = 1, fy = 1, cx = 0, cy = 0, mbf = 0, mb = 0;
+    std::vector<bool> mvbOutlier;
     DBoW2::FeatureVector mFeatVec;
     std::vector<Pt> pts;                         // map point held by each keypoint
     std::vector<float> mvuRight;                 // < 0 in the monocular case
@@ -129,6 +151,7 @@ public:
     static Descriptor_Distance_Type DescriptorDistance(const cv::Mat& a, const cv::Mat& b, const DescriptorType& descriptorType_);
     int SearchByProjection(Frame& F, const vector<Pt>& vpMapPoints, const float& radiusTh);
     int SearchByBoW(Keyframe pKF, Frame& F, vector<Pt>& vpMapPointMatches);
+    int SearchByProjection(Frame& CurrentFrame, const Frame& LastFrame, const float& radiusTh, const bool bMono);
     float RadiusByViewingCos(const float& viewCos);
     static float radiusScale;
     static Descriptor_Distance_Type TH_LOW, TH_HIGH;

@@ -308,3 +308,40 @@ def test_steered_brief_vs_reference_header(ref, synth):
         ref.ref_orb_descriptor(_p(blur), 640, 480, 640, C.c_float(x), C.c_float(y), C.c_float(ang), _p(a))
         L.orc_rbrief32(_p(img), _p(blur), 640, 480, 640, x, y, C.c_float(ang), _p(b))
         assert (a == b).all(), (x, y, ang)
+
+
+@pytest.mark.parametrize("feature", ["orb32", "akaze61"])
+def test_search_by_projection_frames_vs_reference_code(ref, synth, feature):
+    """FeatureMatcher::SearchByProjection(CurrentFrame, LastFrame, th, bMono) (src/FeatureMatcher.cc:1291-1402, best-only rule,
+    no ratio test) with the orientation filter off == the oracle's ratio_same_scale=False variant.  Identity poses and unit
+    intrinsics make the reference's own projection arithmetic land exactly on the query positions."""
+    frames, offs = synth.stream_frames(640, 480, 14, 2)
+    if feature == "orb32":
+        ex = lambda im: po.orb32_extract(im, 1000)[:3]; dt, dcols, th, tol = 0, 32, 75.0, np.float32(1.2)
+    else:
+        ex = lambda im: po.akaze61_extract(im, 1000)[:3]; dt, dcols, th, tol = 1, 61, 128.0, np.float32(1.1892)
+    (k0, d0, s0), (k1, d1, s1) = ex(frames[0]), ex(frames[1])
+    rng = np.random.default_rng(6)
+    shift = (offs[1] - offs[0]).astype(np.float32)
+    nq = len(k0)
+    qxy = np.stack([k0["x"] - shift[0], k0["y"] - shift[1]], axis=1).astype(np.float32) + rng.normal(0, 2.0, (nq, 2)).astype(np.float32)
+    # the reference skips map points that project outside the image bounds before the window search (:1331-1334); that test
+    # belongs to the caller of the C ABI (INTEGRATION.md), so only in-bounds projections are handed to both sides
+    inb = (qxy[:, 0] >= 0) & (qxy[:, 0] <= 640) & (qxy[:, 1] >= 0) & (qxy[:, 1] <= 480)
+    qxy = np.ascontiguousarray(qxy[inb]); d0 = np.ascontiguousarray(d0[inb]); k0 = k0[inb]; s0 = s0[inb]; nq = int(inb.sum())
+    qsize = s0.astype(np.float32)
+    occupied = (rng.random(len(k1)) < 0.1).astype(np.uint8)
+    radius_th, radius_scale = np.float32(7.0), np.float32(1.0)
+    qr = (radius_scale * radius_th) * qsize                            # :1339
+    qmin = qsize / tol; qmax = qsize * tol                             # :1348
+    n_o, m_o = po.search_by_projection(dt, d0, qxy, qr, qmin, qmax, k1, d1, s1, (0.0, 0.0, 640.0, 480.0), occupied=occupied,
+                                       th=th, nnratio=0.9, ratio_same_scale=False, tol=float(tol))
+    m_r = np.zeros(nq, np.int32)
+    d0c = np.ascontiguousarray(d0); d1c = np.ascontiguousarray(d1)
+    ang = np.ascontiguousarray(k0["angle"], np.float32)
+    n_r = ref.ref_search_by_projection_frames(dt, dcols, 0, _p(d0c), _p(qxy), _p(qsize), _p(ang), nq, _p(_kp7(k1)), _p(d1c),
+                                              _p(np.ascontiguousarray(s1)), len(k1), _p(occupied), C.c_float(0.0), C.c_float(0.0),
+                                              C.c_float(640.0), C.c_float(480.0), C.c_float(radius_th), C.c_float(radius_scale),
+                                              C.c_float(tol), C.c_float(th), 0, _p(m_r))
+    assert n_o == n_r and n_r > 100
+    assert (m_o == m_r).all()
