@@ -1,4 +1,4 @@
-"""anyfeature-vslam_b200 -- B200-native feature front end (orb32 extract + FeatureMatcher kernels).
+"""anyfeature-vslam_b200 -- B200-native feature front end (orb32 / sift128 / akaze61 extract + FeatureMatcher kernels).
 
 Python host side above the C ABI (include/afv.h), used by tests/ and bench.py.  It mirrors the reference's
 FeatureExtractor / FeatureMatcher call surface on arrays (numpy for host buffers, torch tensors for device

@@ -1,9 +1,11 @@
 #!/usr/bin/env python3
-"""bench.py -- frames/sec of the orb32 extract+match hot path on B200 (BASELINE.json metric).
+"""bench.py -- frames/sec of the extract+match hot path on B200 (BASELINE.json metric).
 
-One "step" = one pass of the hot path over one batch of B synthetic 640x480 frames (1000 kp/frame):
-orb32 extraction of all B frames (CUDA, batched) + FeatureMatcher::SearchForInitialization of every frame
-against its successor in the same stream (B pairs, wrap-around inside a stream).
+One "step" = one pass of the hot path over one batch of B synthetic frames: extraction of all B frames (CUDA, batched) +
+FeatureMatcher::SearchForInitialization of every frame against its successor in the same stream (B pairs, wrap-around
+inside a stream).  Default workload = BASELINE configs[1] (c2: orb32, 640x480, 1000 kp/frame, B = 512), the configuration the
+metric is quoted on; --workload c3 / c4 / c5 select sift128 1280x720 (L2 matcher), akaze61 640x480 (mixed 61/48-byte Hamming
+matcher) and orb32 1280x720 (the sharded NCCL-gather configuration).
 
   python bench.py --gpus 1 --steps K --warmup W          # this repo's arm
   python bench.py --impl reference ...                   # CPU arm: the oracle port of the reference's path
