@@ -307,6 +307,56 @@ int ref_search_by_projection_frames(int desc_type, int dcols, int dtype, void* q
             for (int i = 0; i < nq; ++i) if (Cur.pts[idx] == Last.pts[i]) { match_q[i] = idx; break; }
     return nm;
 }
+// FeatureExtractor_sift128::detectAndCompute + computeSize of the reference on a prepared SiftGPU feature list (x, y, s, o, desc)
+int ref_sift128_glue(const float* xyso, const float* desc, int n, int w, int h, int nfeatures, int nlevels, float scale_factor,
+                     kp7* okps, float* odesc, float* osize, int cap) {
+    if (g_bump) arena_reset();                               // DistributeOctTree runs inside: monotonic heap (see above)
+    std::shared_ptr<FeatureExtractorSettings> st = std::make_shared<FeatureExtractorSettings>();
+    st->scaleFactor = scale_factor; st->nOctaves = nlevels; FeatureExtractorSettings::scaleFactor0 = scale_factor; st->detectTh = 10.0f;
+    st->maxKeyPtSize0 = pow(1.2f, float(8 - 1.0)); st->maxKeyPtSize = st->maxKeyPtSize0; st->minKeyPtSize = 1.0f;
+    FeatureExtractor_sift128 fe(nfeatures, st);
+    fe.sift->keys.resize(n); fe.sift->desc.assign(desc, desc + (size_t)n * 128);
+    for (int i = 0; i < n; ++i) { fe.sift->keys[i].x = xyso[4 * i]; fe.sift->keys[i].y = xyso[4 * i + 1]; fe.sift->keys[i].s = xyso[4 * i + 2]; fe.sift->keys[i].o = xyso[4 * i + 3]; }
+    Image img; unsigned char dummy = 0; img.grayImg = cv::Mat(h, w, CV_8U, &dummy);
+    std::vector<cv::KeyPoint> k; cv::Mat d; std::vector<float> sz;
+    fe.detectAndCompute(img, k, d);
+    fe.computeSize(sz, k);
+    const int m = (int)k.size();
+    for (int i = 0; i < m && i < cap; ++i) {
+        okps[i].x = k[i].pt.x; okps[i].y = k[i].pt.y; okps[i].size = k[i].size; okps[i].angle = k[i].angle; okps[i].response = k[i].response;
+        okps[i].octave = k[i].octave; okps[i].class_id = k[i].class_id; osize[i] = sz[i];
+        memcpy(odesc + (size_t)i * 128, d.ptr<float>(i), 512);
+    }
+    return m;
+}
+// FeatureExtractor_akaze61::detectAndCompute + computeSize on a prepared Feature_Detection list; descriptors / angles of every
+// detected keypoint come as a table (what libAKAZE::Compute_Descriptors would produce for it)
+int ref_akaze61_glue(const kp7* det, const float* det_angle, const unsigned char* det_desc, int n, int w, int h, int nfeatures, int nlevels,
+                     float scale_factor, float detect_th, kp7* okps, unsigned char* odesc, float* osize, int cap) {
+    if (g_bump) arena_reset();
+    std::shared_ptr<FeatureExtractorSettings> st = std::make_shared<FeatureExtractorSettings>();
+    st->scaleFactor = scale_factor; st->nOctaves = nlevels; FeatureExtractorSettings::scaleFactor0 = scale_factor; st->detectTh = detect_th;
+    st->maxKeyPtSize0 = pow(1.2f, float(8 - 1.0)); st->maxKeyPtSize = st->maxKeyPtSize0; st->minKeyPtSize = 1.0f;
+    FeatureExtractor_akaze61 fe(nfeatures, st);
+    fe.evolution->detected.resize(n); fe.evolution->table_angle.assign(det_angle, det_angle + n);
+    fe.evolution->table_desc.assign(det_desc, det_desc + (size_t)n * 61);
+    for (int i = 0; i < n; ++i) {
+        cv::KeyPoint p; p.pt.x = det[i].x; p.pt.y = det[i].y; p.size = det[i].size; p.angle = 0; p.response = det[i].response; p.octave = det[i].octave; p.class_id = det[i].class_id;
+        fe.evolution->detected[i] = p;
+    }
+    fe.evolution->table_kp = fe.evolution->detected;
+    Image img; unsigned char dummy = 0; img.grayImg = cv::Mat(h, w, CV_8U, &dummy);
+    std::vector<cv::KeyPoint> k; cv::Mat d; std::vector<float> sz;
+    fe.detectAndCompute(img, k, d);
+    fe.computeSize(sz, k);
+    const int m = (int)k.size();
+    for (int i = 0; i < m && i < cap; ++i) {
+        okps[i].x = k[i].pt.x; okps[i].y = k[i].pt.y; okps[i].size = k[i].size; okps[i].angle = k[i].angle; okps[i].response = k[i].response;
+        okps[i].octave = k[i].octave; okps[i].class_id = k[i].class_id; osize[i] = sz[i];
+        memcpy(odesc + (size_t)i * 61, d.data + (size_t)i * 61, 61);
+    }
+    return m;
+}
 float ref_descriptor_distance(int desc_type, int dcols, int dtype, void* a, void* b) {
     return FeatureMatcher::DescriptorDistance(cv::Mat(1, dcols, dtype, a), cv::Mat(1, dcols, dtype, b), (DescriptorType)desc_type);
 }
@@ -344,6 +394,13 @@ def build(force=False):
     parts.append(cut("src/FeatureMatcher.cc", r"^\s*void FeatureMatcher::filterMatchesWithOrientation\(", all_matches=True))
     parts.append(cut("src/FeatureMatcher.cc", r"^\s*void FeatureMatcher::computeThreeMaxima\("))
     parts.append("}  // namespace ANYFEATURE_VSLAM")
+    # ---- the reference-side glue of the sift128 / akaze61 extractors (everything around the un-vendored third-party library)
+    parts.append(cut("src/FeatureExtractor.cpp", r"^void ANYFEATURE_VSLAM::FeatureExtractor::filterKeypoints_notScaled\("))
+    parts.append(cut("src/FeatureExtractor.cpp", r"^void ANYFEATURE_VSLAM::FeatureExtractor::mergeKeypointLevels\("))
+    for feat in ("sift128", "akaze61"):
+        for fn in ("detectAndCompute", "detectKeypoints", "computeDescriptors", "filterKeypoints", "GetKeypointOctave", "GetKeypointSize"):
+            rt = {"GetKeypointOctave": "int", "GetKeypointSize": "float"}.get(fn, "void")
+            parts.append(cut("src/Feature_%s.cpp" % feat, r"^%s ANYFEATURE_VSLAM::FeatureExtractor_%s::%s\(" % (rt, feat, fn)))
     for feat in ("orb32", "akaze61", "brisk48", "sift128"):
         parts.append(cut("src/Feature_%s.cpp" % feat, r"^float ANYFEATURE_VSLAM::DescriptorDistance_%s\(" % feat))
     # ---- MapPoint::ComputeDistinctiveDescriptors (src/MapPoint.cc:279-348): the distance matrix + least-median pick, i.e. the

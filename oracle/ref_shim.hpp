@@ -21,6 +21,10 @@
 static inline int cvRound(double v) { return (int)lrint(v); }       // OpenCV: round half to even
 typedef unsigned char uchar;
 #define CV_PI 3.1415926535897932384626433832795
+#define CV_8U 0
+#define CV_32F 5
+#define GL_LUMINANCE 0x1909
+#define GL_UNSIGNED_BYTE 0x1401
 namespace cv {
 template <typename T> struct Point_ { T x, y; Point_() : x(0), y(0) {} Point_(T x_, T y_) : x(x_), y(y_) {} };
 typedef Point_<int> Point2i;
@@ -32,14 +36,28 @@ struct Mat {                                   // continuous row-major view; typ
     int rows = 0, cols = 0, type_ = 0;
     unsigned char* data = nullptr;
     size_t step = 0;
+    std::shared_ptr<std::vector<unsigned char>> own;      // set when the matrix owns its storage
     Mat() {}
     Mat(int r, int c, int t, void* d) : rows(r), cols(c), type_(t), data((unsigned char*)d), step((size_t)c * (t == 5 ? 4 : 1)) {}
+    Mat(int r, int c, int t) { create(r, c, t); }
+    void create(int r, int c, int t) {
+        rows = r; cols = c; type_ = t; step = (size_t)c * (t == 5 ? 4 : 1);
+        own = std::make_shared<std::vector<unsigned char>>((size_t)r * step + 8, 0); data = own->data();
+    }
+    void release() { rows = cols = 0; data = nullptr; own.reset(); }
     Mat row(int i) const { Mat m(1, cols, type_, data + (size_t)i * step); return m; }
     template <typename T> T& at(int r, int c) { return reinterpret_cast<T*>(data + (size_t)r * step)[c]; }
     template <typename T> const T& at(int r, int c) const { return reinterpret_cast<const T*>(data + (size_t)r * step)[c]; }
     template <typename T> T* ptr(int r = 0) { return reinterpret_cast<T*>(data + (size_t)r * step); }
     template <typename T> const T* ptr(int r = 0) const { return reinterpret_cast<const T*>(data + (size_t)r * step); }
 };
+inline void vconcat(const std::vector<Mat>& src, Mat& dst) {      // row-wise concatenation of equally wide matrices
+    int rows = 0, cols = 0, type = 0;
+    for (const Mat& m : src) { rows += m.rows; if (m.rows) { cols = m.cols; type = m.type_; } }
+    dst.create(rows, cols, type);
+    size_t off = 0;
+    for (const Mat& m : src) { if (m.rows) memcpy(dst.data + off, m.data, (size_t)m.rows * m.step); off += (size_t)m.rows * m.step; }
+}
 // OpenCV: NORM_HAMMING = popcount of the xor over all bytes; NORM_L2SQR on CV_32F accumulates the squared differences in double
 inline double norm(const Mat& a, const Mat& b, int normType) {
     if (normType == NORM_HAMMING) {
@@ -175,7 +193,39 @@ public:
     std::list<ExtractorNode>::iterator lit;
     bool bNoMore;
 };
+class Image { public: cv::Mat img{}, grayImg{}, mask{}; };           // include/Image.h:12-27 (data members)
+
+// SiftGPU look-alike (third party, not vendored): hands back a prepared feature list
+struct SiftGPU {
+    struct SiftKeypoint { float x, y, s, o; };
+    std::vector<SiftKeypoint> keys; std::vector<float> desc;
+    int RunSIFT(int, int, const void*, unsigned, unsigned) { return 1; }
+    int GetFeatureNum() { return (int)keys.size(); }
+    void GetFeatureVector(SiftKeypoint* k, float* d) {
+        if (k) std::copy(keys.begin(), keys.end(), k);
+        if (d) std::copy(desc.begin(), desc.end(), d);
+    }
+};
+// libAKAZE look-alike (third party, not vendored): prepared detection list; descriptors / orientation by keypoint identity
+struct AKAZEOptions { int omax = 4, nsublevels = 4, img_width = 0, img_height = 0; float dthreshold = 0.001f; };
+namespace libAKAZE {
+struct AKAZE {
+    std::vector<cv::KeyPoint> detected;                              // Feature_Detection output
+    std::vector<cv::KeyPoint> table_kp; std::vector<float> table_angle; std::vector<unsigned char> table_desc;   // per detected keypoint
+    void Feature_Detection(std::vector<cv::KeyPoint>& kpts) { kpts = detected; }
+    void Compute_Descriptors(std::vector<cv::KeyPoint>& kpts, cv::Mat& desc) {
+        desc.create((int)kpts.size(), 61, CV_8U);
+        for (size_t i = 0; i < kpts.size(); ++i)
+            for (size_t j = 0; j < table_kp.size(); ++j)
+                if (table_kp[j].pt.x == kpts[i].pt.x && table_kp[j].pt.y == kpts[i].pt.y && table_kp[j].class_id == kpts[i].class_id) {
+                    kpts[i].angle = table_angle[j]; memcpy(desc.data + i * 61, table_desc.data() + j * 61, 61); break;
+                }
+    }
+};
+}
+
 struct FeatureExtractorSettings {               // include/FeatureExtractor.h:24-66 (the fields the constructor / computeSize read)
+    float detectTh = 0;
     float scaleFactor = 1.2f; int nOctaves = 8;
     float maxKeyPtSize = 0, minKeyPtSize = 1.0f, maxKeyPtSize0 = 0;
     static float scaleFactor0;
@@ -191,11 +241,42 @@ public:
     std::vector<cv::Mat> mvImagePyramid;
     std::vector<int> mnFeaturesPerLevel;
     void computeSize(std::vector<float>& keyPtsSize, const std::vector<cv::KeyPoint>& keypoints);
+    // hooks of include/FeatureExtractor.h:114-134 with the reference's signatures
+    virtual void detectAndCompute(const Image& img, std::vector<cv::KeyPoint>& keypoints, cv::Mat& descriptors) {}
+    virtual void detectKeypoints(std::map<int, std::vector<cv::KeyPoint>>& keypoints_level, const Image& img, const float& detectTh, const int& nOctaves) const {}
+    virtual void computeDescriptors(std::map<int, cv::Mat>& descriptors_level, std::map<int, std::vector<cv::KeyPoint>>& keypoints_level, const Image& img) const {}
+    virtual void mergeKeypointLevels(std::vector<cv::KeyPoint>& keypoints, cv::Mat& descriptors, std::map<int, cv::Mat>& descriptors_level,
+                                     std::map<int, std::vector<cv::KeyPoint>>& keypoints_level) const;
+    virtual void filterKeypoints(std::map<int, std::vector<cv::KeyPoint>>& keypoints_level, const cv::Mat& image, const cv::Mat& mask) const {}
+    void filterKeypoints_notScaled(std::map<int, std::vector<cv::KeyPoint>>& keypoints_level, const cv::Mat& image, const cv::Mat& mask) const;
     virtual int GetKeypointOctave(const cv::KeyPoint& keypoint) const { return keypoint.octave; }
     virtual float GetKeypointSize(const cv::KeyPoint& keypoint) const {      // src/Feature_orb32.cpp:59-61 (same in every Feature_*)
         return powf(settings->GetDetectorNominalScaleFactor(), float(GetKeypointOctave(keypoint))); }
     int nfeatures = 1000;
     std::vector<cv::KeyPoint> DistributeOctTree(const std::vector<cv::KeyPoint>& vToDistributeKeys, const int& minX, const int& maxX,
                                                 const int& minY, const int& maxY, const int& N, const int& level) const;
+};
+class FeatureExtractor_sift128 : public FeatureExtractor {          // include/Feature_sift128.h (constructor replaced: no GL context)
+public:
+    std::shared_ptr<SiftGPU> sift;
+    FeatureExtractor_sift128(const int& nfeatures_, std::shared_ptr<FeatureExtractorSettings>& settings_) : FeatureExtractor(nfeatures_, settings_), sift(std::make_shared<SiftGPU>()) {}
+    void detectAndCompute(const Image& img, std::vector<cv::KeyPoint>& keypoints, cv::Mat& descriptors) override;
+    void detectKeypoints(std::map<int, std::vector<cv::KeyPoint>>& keypoints_level, const Image& img, const float& detectTh, const int& nOctaves) const override;
+    void computeDescriptors(std::map<int, cv::Mat>& descriptors_level, std::map<int, std::vector<cv::KeyPoint>>& keypoints_level, const Image& img) const override;
+    void filterKeypoints(std::map<int, std::vector<cv::KeyPoint>>& keypoints_level, const cv::Mat& image, const cv::Mat& mask) const override;
+    int GetKeypointOctave(const cv::KeyPoint& keypoint) const override;
+    float GetKeypointSize(const cv::KeyPoint& keypoint) const override;
+};
+class FeatureExtractor_akaze61 : public FeatureExtractor {          // include/Feature_akaze61.h (constructor replaced)
+public:
+    std::shared_ptr<libAKAZE::AKAZE> evolution{};
+    AKAZEOptions akazeOptions{};
+    FeatureExtractor_akaze61(const int& nfeatures_, std::shared_ptr<FeatureExtractorSettings>& settings_) : FeatureExtractor(nfeatures_, settings_), evolution(std::make_shared<libAKAZE::AKAZE>()) {}
+    void detectAndCompute(const Image& img, std::vector<cv::KeyPoint>& keypoints, cv::Mat& descriptors) override;
+    void detectKeypoints(std::map<int, std::vector<cv::KeyPoint>>& keypoints_level, const Image& img, const float& detectTh, const int& nOctaves) const override;
+    void computeDescriptors(std::map<int, cv::Mat>& descriptors_level, std::map<int, std::vector<cv::KeyPoint>>& keypoints_level, const Image& img) const override;
+    void filterKeypoints(std::map<int, std::vector<cv::KeyPoint>>& keypoints_level, const cv::Mat& image, const cv::Mat& mask) const override;
+    int GetKeypointOctave(const cv::KeyPoint& keypoint) const override;
+    float GetKeypointSize(const cv::KeyPoint& keypoint) const override;
 };
 }  // namespace ANYFEATURE_VSLAM

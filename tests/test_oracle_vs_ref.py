@@ -75,7 +75,8 @@ def test_distribute_octree_random_and_equal_responses(ref):
 def test_reference_octree_depends_on_heap_addresses(ref, synth):
     """Documented property of the REFERENCE, not of this repo: DistributeOctTree sorts (nKeys, ExtractorNode*) pairs
     (src/ORBextractor.cc:381), so with the stock allocator ties are broken by heap addresses -- the kept set differs by a few
-    keypoints and the order changes from call to call.  Same count, same quota; the oracle (and the CUDA path) use the
+    keypoints and the order changes from call to call (the count can move by 1-3 as well: 881 vs 882 keypoints were seen on a
+    sift128 frame).  The oracle (and the CUDA path) use the
     canonical order "later-created node = larger address", which is what the reference does on a monotonic heap."""
     img = synth.stream_frames(640, 480, 0, 1)[0][0]
     levels, ls = po.pyramid(img)
@@ -89,7 +90,7 @@ def test_reference_octree_depends_on_heap_addresses(ref, synth):
     finally:
         ref.ref_set_bump(1)
     for r in runs:
-        assert len(r) == len(canon)                                        # the count never depends on the heap
+        assert abs(len(r) - len(canon)) <= 3                               # the last division adds 1..3 nodes: even the count can move
         assert len(set(r.tolist()) ^ set(canon.tolist())) <= 0.15 * len(canon)   # the set only by a few tie cases
     again = _ref_octree(ref, px, py, hr, 640, 480, q_ext[0])
     assert (again == canon).all()                                          # deterministic on the monotonic heap
@@ -345,3 +346,47 @@ def test_search_by_projection_frames_vs_reference_code(ref, synth, feature):
                                               C.c_float(tol), C.c_float(th), 0, _p(m_r))
     assert n_o == n_r and n_r > 100
     assert (m_o == m_r).all()
+
+
+def test_sift128_glue_vs_reference_code(ref, synth):
+    """Everything FeatureExtractor_sift128 does around SiftGPU (src/Feature_sift128.cpp:64-134: octave = int(log2(s/1.6454)),
+    response 1, class_id = list row, octree per octave, descriptor row gather, merge, computeSize), executed by the reference's
+    own code on the oracle's SiftGPU-equivalent feature list == the oracle's full extraction."""
+    for stream, (w, h), nfeat in ((0, (640, 480), 1000), (1, (1280, 720), 2000)):
+        img = synth.stream_frames(w, h, stream, 1)[0][0]
+        xyso, desc = po.sift_detect(img, nfeat)
+        rk, rd, rs, _ = po.sift128_extract(img, nfeat)
+        cap = len(xyso) + 8
+        ok = np.zeros(cap, po.KP_DTYPE); od = np.zeros((cap, 128), np.float32); osz = np.zeros(cap, np.float32)
+        m = ref.ref_sift128_glue(_p(np.ascontiguousarray(xyso)), _p(np.ascontiguousarray(desc)), len(xyso), w, h, nfeat, 8, C.c_float(2.0),
+                                 _p(ok), _p(od), _p(osz), cap)
+        assert m == len(rk)
+        for f in rk.dtype.names:
+            assert (ok[:m][f] == rk[f]).all(), f
+        assert (od[:m] == rd).all() and (osz[:m] == rs).all()
+
+
+def test_akaze61_glue_vs_reference_code(ref, synth):
+    """Everything FeatureExtractor_akaze61 does around libAKAZE (src/Feature_akaze61.cpp:15-73: levels keyed by class_id, octree
+    per level, all levels merged before Compute_Descriptors, computeSize), executed by the reference's own code on the oracle's
+    Feature_Detection list == the oracle's full extraction."""
+    img = synth.stream_frames(640, 480, 2, 1)[0][0]
+    ak, ad, _, _ = po.akaze61_extract(img, 200000)                  # quota above the count: every detected keypoint, with angle + descriptor
+    det = np.zeros(len(ak), po.KP_DTYPE)
+    for f in ("x", "y", "size", "response", "octave", "class_id"):
+        det[f] = ak[f]
+    order = np.lexsort((np.arange(len(ak)),))                       # Feature_Detection order is restored from the raw detector tap
+    raw = po.akaze_detect(img)
+    assert len(raw) == len(ak)
+    key = {(float(a), float(b), int(c)): i for i, (a, b, c) in enumerate(zip(ak["x"], ak["y"], ak["class_id"]))}
+    idx = np.array([key[(float(a), float(b), int(c))] for a, b, c in zip(raw[:, 0], raw[:, 1], raw[:, 4])])
+    det = np.ascontiguousarray(det[idx]); ang = np.ascontiguousarray(ak["angle"][idx], np.float32); dd = np.ascontiguousarray(ad[idx])
+    for nfeat in (1000, 400):
+        rk, rd, rs, _ = po.akaze61_extract(img, nfeat)
+        cap = len(det) + 8
+        ok = np.zeros(cap, po.KP_DTYPE); od = np.zeros((cap, 61), np.uint8); osz = np.zeros(cap, np.float32)
+        m = ref.ref_akaze61_glue(_p(det), _p(ang), _p(dd), len(det), 640, 480, nfeat, 8, C.c_float(1.1892), C.c_float(5e-4), _p(ok), _p(od), _p(osz), cap)
+        assert m == len(rk)
+        for f in rk.dtype.names:
+            assert (ok[:m][f] == rk[f]).all(), f
+        assert (od[:m] == rd).all() and (osz[:m] == rs).all()
