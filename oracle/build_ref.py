@@ -86,6 +86,11 @@ float Frame::mfGridElementWidthInv = 0, Frame::mfGridElementHeightInv = 0, Frame
 Descriptor_Distance_Type FeatureMatcher::TH_HIGH = 0, FeatureMatcher::TH_LOW = 0;
 float FeatureMatcher::radiusScale = 1.0f;
 float FeatureExtractorSettings::scaleFactor0 = 1.2f;
+}
+std::vector<cv::KeyPoint>* cv::ORB::g_detect = nullptr;
+void (*cv::ORB::g_compute)(const cv::KeyPoint*, int, unsigned char*) = nullptr;
+int cv::ORB::g_last[4] = {0, 0, 0, 0};
+namespace ANYFEATURE_VSLAM {
 const int FeatureMatcher::HISTO_LENGTH = 30;                       // src/FeatureMatcher.cc:64
 }
 using namespace ANYFEATURE_VSLAM;
@@ -357,6 +362,34 @@ int ref_akaze61_glue(const kp7* det, const float* det_angle, const unsigned char
     }
     return m;
 }
+// FeatureExtractor_orb32: initializeExtractor + detectAndCompute + computeSize of the reference.  det = cv::ORB::detect output
+// (the tests pass cv2's real one), compute_cb = ORB.compute on the keypoints the glue selects (the tests call cv2's real one).
+// orb_params receives the (maxFeatures, edgeThreshold, fastThreshold, nLevels) the reference configured cv::ORB with.
+int ref_orb32_glue(const kp7* det, int n, int w, int h, int nfeatures, int nlevels, float scale_factor, float detect_th,
+                   void (*compute_cb)(const cv::KeyPoint*, int, unsigned char*), kp7* okps, unsigned char* odesc, float* osize, int cap,
+                   int* orb_params) {
+    if (g_bump) arena_reset();
+    std::shared_ptr<FeatureExtractorSettings> st = std::make_shared<FeatureExtractorSettings>();
+    st->scaleFactor = scale_factor; st->nOctaves = nlevels; FeatureExtractorSettings::scaleFactor0 = scale_factor; st->detectTh = detect_th;
+    st->maxKeyPtSize0 = pow(1.2f, float(8 - 1.0)); st->maxKeyPtSize = st->maxKeyPtSize0; st->minKeyPtSize = 1.0f;
+    std::vector<cv::KeyPoint> dv(n);
+    for (int i = 0; i < n; ++i) { dv[i].pt.x = det[i].x; dv[i].pt.y = det[i].y; dv[i].size = det[i].size; dv[i].angle = det[i].angle; dv[i].response = det[i].response; dv[i].octave = det[i].octave; dv[i].class_id = det[i].class_id; }
+    cv::ORB::g_detect = &dv; cv::ORB::g_compute = compute_cb;
+    FeatureExtractor_orb32 fe(nfeatures, st);
+    Image img; unsigned char dummy = 0; img.grayImg = cv::Mat(h, w, CV_8U, &dummy);
+    fe.initializeExtractor(img);
+    std::vector<cv::KeyPoint> k; cv::Mat d; std::vector<float> sz;
+    fe.detectAndCompute(img, k, d);
+    fe.computeSize(sz, k);
+    for (int i = 0; i < 4; ++i) orb_params[i] = cv::ORB::g_last[i];
+    const int m = (int)k.size();
+    for (int i = 0; i < m && i < cap; ++i) {
+        okps[i].x = k[i].pt.x; okps[i].y = k[i].pt.y; okps[i].size = k[i].size; okps[i].angle = k[i].angle; okps[i].response = k[i].response;
+        okps[i].octave = k[i].octave; okps[i].class_id = k[i].class_id; osize[i] = sz[i];
+        memcpy(odesc + (size_t)i * 32, d.data + (size_t)i * 32, 32);
+    }
+    return m;
+}
 float ref_descriptor_distance(int desc_type, int dcols, int dtype, void* a, void* b) {
     return FeatureMatcher::DescriptorDistance(cv::Mat(1, dcols, dtype, a), cv::Mat(1, dcols, dtype, b), (DescriptorType)desc_type);
 }
@@ -397,7 +430,9 @@ def build(force=False):
     # ---- the reference-side glue of the sift128 / akaze61 extractors (everything around the un-vendored third-party library)
     parts.append(cut("src/FeatureExtractor.cpp", r"^void ANYFEATURE_VSLAM::FeatureExtractor::filterKeypoints_notScaled\("))
     parts.append(cut("src/FeatureExtractor.cpp", r"^void ANYFEATURE_VSLAM::FeatureExtractor::mergeKeypointLevels\("))
-    for feat in ("sift128", "akaze61"):
+    parts.append(cut("src/Feature_orb32.cpp", r"^ANYFEATURE_VSLAM::FeatureExtractor_orb32::FeatureExtractor_orb32\("))
+    parts.append(cut("src/Feature_orb32.cpp", r"^void ANYFEATURE_VSLAM::FeatureExtractor_orb32::initializeExtractor\("))
+    for feat in ("orb32", "sift128", "akaze61"):
         for fn in ("detectAndCompute", "detectKeypoints", "computeDescriptors", "filterKeypoints", "GetKeypointOctave", "GetKeypointSize"):
             rt = {"GetKeypointOctave": "int", "GetKeypointSize": "float"}.get(fn, "void")
             parts.append(cut("src/Feature_%s.cpp" % feat, r"^%s ANYFEATURE_VSLAM::FeatureExtractor_%s::%s\(" % (rt, feat, fn)))

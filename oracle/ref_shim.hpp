@@ -195,6 +195,25 @@ public:
 };
 class Image { public: cv::Mat img{}, grayImg{}, mask{}; };           // include/Image.h:12-27 (data members)
 
+// cv::ORB look-alike: records the parameters the reference sets; detect() hands back a prepared list (cv2's real output in the
+// tests), compute() calls back into the test harness (which runs cv2's real ORB.compute on exactly those keypoints)
+}  // namespace ANYFEATURE_VSLAM
+namespace cv {
+template <typename T> using Ptr = std::shared_ptr<T>;
+struct ORB {
+    int maxFeatures = 500, edgeThreshold = 31, fastThreshold = 20, nLevels = 8;
+    static std::vector<KeyPoint>* g_detect;                                        // prepared detect() output
+    static void (*g_compute)(const KeyPoint* kps, int n, unsigned char* desc32);   // harness callback
+    static int g_last[4];
+    static Ptr<ORB> create() { return std::make_shared<ORB>(); }
+    void setMaxFeatures(int v) { maxFeatures = v; } void setEdgeThreshold(int v) { edgeThreshold = v; }
+    void setFastThreshold(int v) { fastThreshold = v; } void setNLevels(int v) { nLevels = v; }
+    void detect(const Mat&, std::vector<KeyPoint>& k) { g_last[0] = maxFeatures; g_last[1] = edgeThreshold; g_last[2] = fastThreshold; g_last[3] = nLevels; k = *g_detect; }
+    void compute(const Mat&, std::vector<KeyPoint>& k, Mat& desc) { desc.create((int)k.size(), 32, 0); if (!k.empty()) g_compute(k.data(), (int)k.size(), desc.data); }
+};
+}
+namespace ANYFEATURE_VSLAM {
+
 // SiftGPU look-alike (third party, not vendored): hands back a prepared feature list
 struct SiftGPU {
     struct SiftKeypoint { float x, y, s, o; };
@@ -255,6 +274,18 @@ public:
     int nfeatures = 1000;
     std::vector<cv::KeyPoint> DistributeOctTree(const std::vector<cv::KeyPoint>& vToDistributeKeys, const int& minX, const int& maxX,
                                                 const int& minY, const int& maxY, const int& N, const int& level) const;
+};
+class FeatureExtractor_orb32 : public FeatureExtractor {            // include/Feature_orb32.h
+public:
+    cv::Ptr<cv::ORB> orb32_extractor;
+    FeatureExtractor_orb32(const int& nfeatures_, std::shared_ptr<FeatureExtractorSettings>& settings_);
+    void detectAndCompute(const Image& img, std::vector<cv::KeyPoint>& keypoints, cv::Mat& descriptors) override;
+    void initializeExtractor(const Image& img);
+    void detectKeypoints(std::map<int, std::vector<cv::KeyPoint>>& keypoints_level, const Image& img, const float& detectTh, const int& nOctaves) const override;
+    void computeDescriptors(std::map<int, cv::Mat>& descriptors_level, std::map<int, std::vector<cv::KeyPoint>>& keypoints_level, const Image& img) const override;
+    void filterKeypoints(std::map<int, std::vector<cv::KeyPoint>>& keypoints_level, const cv::Mat& image, const cv::Mat& mask) const override;
+    int GetKeypointOctave(const cv::KeyPoint& keypoint) const override;
+    float GetKeypointSize(const cv::KeyPoint& keypoint) const override;
 };
 class FeatureExtractor_sift128 : public FeatureExtractor {          // include/Feature_sift128.h (constructor replaced: no GL context)
 public:

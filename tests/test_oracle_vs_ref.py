@@ -390,3 +390,38 @@ def test_akaze61_glue_vs_reference_code(ref, synth):
         for f in rk.dtype.names:
             assert (ok[:m][f] == rk[f]).all(), f
         assert (od[:m] == rd).all() and (osz[:m] == rs).all()
+
+
+def test_orb32_pipeline_from_real_parts(ref, synth):
+    """The orb32 path assembled from its REAL parts == the oracle: cv2 4.13.0 runs the OpenCV stages (ORB.detect, ORB.compute per
+    level) and the reference's own compiled code (FeatureExtractor_orb32::initializeExtractor / detectAndCompute, the base class's
+    filterKeypoints_notScaled -> DistributeOctTree, mergeKeypointLevels, computeSize) runs everything else, calling back into
+    cv2 for compute() on exactly the keypoints it selects.  Also checks the parameters the reference configures cv::ORB with."""
+    cv2 = pytest.importorskip("cv2")
+    cv2.setNumThreads(1)
+    KPC = np.dtype([("x", "<f4"), ("y", "<f4"), ("size", "<f4"), ("angle", "<f4"), ("response", "<f4"), ("octave", "<i4"), ("class_id", "<i4")])
+    for stream, (w, h), nfeat in ((0, (640, 480), 1000), (7, (640, 480), 1000), (1, (1280, 720), 2000)):
+        img = synth.stream_frames(w, h, stream, 1)[0][0]
+        orb = cv2.ORB_create(); orb.setMaxFeatures(nfeat * 10); orb.setEdgeThreshold(0); orb.setFastThreshold(20); orb.setNLevels(8)
+        det_cv = orb.detect(img)
+        det = np.zeros(len(det_cv), KPC)
+        for i, k in enumerate(det_cv):
+            det[i] = (k.pt[0], k.pt[1], k.size, k.angle, k.response, k.octave, k.class_id)
+
+        @C.CFUNCTYPE(None, C.c_void_p, C.c_int, C.c_void_p)
+        def compute_cb(kps_ptr, n, desc_ptr):
+            a = np.ctypeslib.as_array(C.cast(kps_ptr, C.POINTER(C.c_uint8)), shape=(n * 28,)).view(KPC)
+            kl = [cv2.KeyPoint(float(k["x"]), float(k["y"]), float(k["size"]), float(k["angle"]), float(k["response"]), int(k["octave"]), int(k["class_id"])) for k in a]
+            sel, d = orb.compute(img, kl)
+            assert len(sel) == n
+            np.ctypeslib.as_array(C.cast(desc_ptr, C.POINTER(C.c_uint8)), shape=(n * 32,))[:] = d.reshape(-1)
+
+        cap = nfeat + 64
+        ok = np.zeros(cap, po.KP_DTYPE); od = np.zeros((cap, 32), np.uint8); osz = np.zeros(cap, np.float32); params = np.zeros(4, np.int32)
+        m = ref.ref_orb32_glue(_p(det), len(det), w, h, nfeat, 8, C.c_float(1.2), C.c_float(20.0), compute_cb, _p(ok), _p(od), _p(osz), cap, _p(params))
+        assert params.tolist() == [nfeat * 10, 0, 20, 8]               # src/Feature_orb32.cpp:20-34
+        rk, rd, rs, _ = po.orb32_extract(img, nfeat)
+        assert m == len(rk)
+        for f in rk.dtype.names:
+            assert (ok[:m][f] == rk[f]).all(), (stream, f)
+        assert (od[:m] == rd).all() and (osz[:m] == rs).all()
