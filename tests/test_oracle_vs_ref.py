@@ -392,7 +392,7 @@ def test_akaze61_glue_vs_reference_code(ref, synth):
         assert (od[:m] == rd).all() and (osz[:m] == rs).all()
 
 
-def test_orb32_pipeline_from_real_parts(ref, synth):
+def test_orb32_pipeline_from_real_parts(ref, synth, golden_dir):
     """The orb32 path assembled from its REAL parts == the oracle: cv2 4.13.0 runs the OpenCV stages (ORB.detect, ORB.compute per
     level) and the reference's own compiled code (FeatureExtractor_orb32::initializeExtractor / detectAndCompute, the base class's
     filterKeypoints_notScaled -> DistributeOctTree, mergeKeypointLevels, computeSize) runs everything else, calling back into
@@ -400,8 +400,15 @@ def test_orb32_pipeline_from_real_parts(ref, synth):
     cv2 = pytest.importorskip("cv2")
     cv2.setNumThreads(1)
     KPC = np.dtype([("x", "<f4"), ("y", "<f4"), ("size", "<f4"), ("angle", "<f4"), ("response", "<f4"), ("octave", "<i4"), ("class_id", "<i4")])
-    for stream, (w, h), nfeat in ((0, (640, 480), 1000), (7, (640, 480), 1000), (1, (1280, 720), 2000)):
-        img = synth.stream_frames(w, h, stream, 1)[0][0]
+    cases = [(synth.stream_frames(w, h, stream, 1)[0][0], nfeat) for stream, (w, h), nfeat in
+             ((0, (640, 480), 1000), (7, (640, 480), 1000), (1, (1280, 720), 2000))]
+    # BASELINE configs[0]: the reference's own toy sequence (gray images stored in the golden fixtures), 1000 and 2000 features
+    for name in ("toy0.npz", "toy2.npz"):
+        g = np.load(os.path.join(golden_dir, name))
+        cases += [(np.ascontiguousarray(g["gray"]), 1000), (np.ascontiguousarray(g["gray"]), 2000)]
+    for img, nfeat in cases:
+        h, w = img.shape
+        stream = (w, h, nfeat)
         orb = cv2.ORB_create(); orb.setMaxFeatures(nfeat * 10); orb.setEdgeThreshold(0); orb.setFastThreshold(20); orb.setNLevels(8)
         det_cv = orb.detect(img)
         det = np.zeros(len(det_cv), KPC)
