@@ -189,6 +189,92 @@ def cpu_arm(frames, pair_b, nthreads, seconds_budget):
     return step, sample, per_frame
 
 
+# ---------------------------------------------------------------------------------------------------------
+# CPU arm from the reference's REAL parts (orb32 workloads): the cv2 4.13.0 binary runs the OpenCV stages exactly as
+# src/Feature_orb32.cpp calls them (a fresh cv::ORB per frame, detect, one compute per level) and oracle/_ref/libafv_ref.so -- the
+# reference's own C++ compiled from its sources by oracle/build_ref.py -- runs everything else (per-level DistributeOctTree,
+# merge, computeSize, Frame grid, FeatureMatcher::SearchForInitialization).  One work unit = one stream of 16 consecutive
+# frames (extraction + the 16 wrap-around pairs), units fan out over a process pool (cv2.setNumThreads(1) per process).
+# ---------------------------------------------------------------------------------------------------------
+REF_SO = os.path.join(ROOT, "oracle", "_ref", "libafv_ref.so")
+_KPC = np.dtype([("x", "<f4"), ("y", "<f4"), ("size", "<f4"), ("angle", "<f4"), ("response", "<f4"), ("octave", "<i4"), ("class_id", "<i4")])
+
+
+def _real_parts_unit(job):
+    """Worker: (frames u8 [n,h,w], nfeat) -> (number of keypoints, number of matches) for the n frames / n wrap-around pairs."""
+    import ctypes as C
+    import cv2
+    frames, nfeat = job
+    cv2.setNumThreads(1)
+    ref = C.CDLL(REF_SO)
+    n, h, w = frames.shape
+    cap = nfeat + 64
+    res = []
+    for i in range(n):
+        img = frames[i]
+        orb = cv2.ORB_create(); orb.setMaxFeatures(nfeat * 10); orb.setEdgeThreshold(0)       # initializeExtractor, every frame
+        orb.setFastThreshold(20); orb.setNLevels(8)
+        det_cv = orb.detect(img)
+        det = np.zeros(len(det_cv), _KPC)
+        for j, k in enumerate(det_cv):
+            det[j] = (k.pt[0], k.pt[1], k.size, k.angle, k.response, k.octave, k.class_id)
+
+        @C.CFUNCTYPE(None, C.c_void_p, C.c_int, C.c_void_p)
+        def compute_cb(kps_ptr, m, desc_ptr):
+            a = np.ctypeslib.as_array(C.cast(kps_ptr, C.POINTER(C.c_uint8)), shape=(m * 28,)).view(_KPC)
+            kl = [cv2.KeyPoint(float(k["x"]), float(k["y"]), float(k["size"]), float(k["angle"]), float(k["response"]), int(k["octave"]), int(k["class_id"])) for k in a]
+            _, d = orb.compute(img, kl)
+            np.ctypeslib.as_array(C.cast(desc_ptr, C.POINTER(C.c_uint8)), shape=(m * 32,))[:] = d.reshape(-1)
+
+        ok = np.zeros(cap, _KPC); od = np.zeros((cap, 32), np.uint8); osz = np.zeros(cap, np.float32); params = np.zeros(4, np.int32)
+        m = ref.ref_orb32_glue(det.ctypes.data_as(C.c_void_p), len(det), w, h, nfeat, 8, C.c_float(1.2), C.c_float(20.0), compute_cb,
+                               ok.ctypes.data_as(C.c_void_p), od.ctypes.data_as(C.c_void_p), osz.ctypes.data_as(C.c_void_p), cap,
+                               params.ctypes.data_as(C.c_void_p))
+        res.append((ok[:m].copy(), od[:m].copy(), osz[:m].copy()))
+    nkp = sum(len(r[0]) for r in res)
+    nmatch = 0
+    for i in range(n):
+        k0, d0, s0 = res[i]; k1, d1, s1 = res[(i + 1) % n]
+        prev = np.ascontiguousarray(np.stack([k0["x"], k0["y"]], axis=1), np.float32)
+        m12 = np.zeros(max(len(k0), 1), np.int32)
+        nmatch += ref.ref_search_for_initialization(0, 32, 0, k0.ctypes.data_as(C.c_void_p), d0.ctypes.data_as(C.c_void_p), s0.ctypes.data_as(C.c_void_p),
+                                                    len(k0), k1.ctypes.data_as(C.c_void_p), d1.ctypes.data_as(C.c_void_p), s1.ctypes.data_as(C.c_void_p), len(k1),
+                                                    C.c_float(0.0), C.c_float(0.0), C.c_float(float(w)), C.c_float(float(h)), C.c_float(MAX_KPT_SIZE),
+                                                    prev.ctypes.data_as(C.c_void_p), 100, C.c_float(75.0), C.c_float(0.9), 1, m12.ctypes.data_as(C.c_void_p))
+    return nkp, nmatch
+
+
+def run_reference_real_parts(args, frames, nthreads):
+    """Returns (fps, ms_per_step, sample description) or None when cv2 / oracle/_ref are not available."""
+    try:
+        import cv2  # noqa: F401
+        import multiprocessing as mp
+        if not os.path.exists(REF_SO):
+            return None
+        per = 16
+        nunits = max(1, min(len(frames) // per, 2 * nthreads))
+        jobs = [(np.ascontiguousarray(frames[u * per:(u + 1) * per]), NFEAT) for u in range(nunits)]
+        ctx = mp.get_context("spawn")
+        with ctx.Pool(min(nthreads, nunits)) as pool:
+            pool.map(_real_parts_unit, jobs[:min(nthreads, nunits)])                 # warm-up: imports, library load, first touch
+            t0 = time.perf_counter()
+            tot = None
+            for _ in range(args.steps):
+                tot = pool.map(_real_parts_unit, jobs)
+            dt = time.perf_counter() - t0
+        nfr = nunits * per
+        nkp = sum(t[0] for t in tot); nm = sum(t[1] for t in tot)
+        if nkp < nfr * NFEAT:                                                          # every frame yields >= nfeatures keypoints
+            return None
+        desc = ("%d frames/step x %d steps; the reference's real parts: cv2 %s ORB.detect / ORB.compute per level (fresh cv::ORB per frame) + "
+                "the reference's own compiled C++ (oracle/_ref: DistributeOctTree, merge, computeSize, Frame grid, SearchForInitialization); "
+                "%d processes x 1 thread; %.1f matches/pair" % (nfr, args.steps, __import__("cv2").__version__, min(nthreads, nunits), nm / float(nfr)))
+        return nfr * args.steps / dt, dt / args.steps * 1e3, desc, nfr
+    except Exception as e:                                                             # never fail the arm: fall back to the port
+        sys.stderr.write("real-parts reference arm unavailable (%r): using the oracle port\n" % (e,))
+        return None
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -201,6 +287,21 @@ def run_reference(args):
     P = _P(); P.synth = synth
     frames, pa, pb = make_frames(P, min(args.batch, 256 if WL["feature"] == "orb32" and W <= 640 else 32), 0)
     nthreads = host_threads()
+    if WL["feature"] == "orb32" and args.real_parts:
+        rp = run_reference_real_parts(args, frames, nthreads)
+        if rp is not None:
+            fps, ms_step, desc, nfr = rp
+            line = {
+                "impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+                "config": {"workload": WL["name"], "frames_per_step": nfr},
+                "cpu_baseline": {"value": fps, "unit": UNIT, "cores": nthreads, "kind": "reference", "sample": desc},
+                "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0,
+            }
+            print(json.dumps(line))
+            return 0
     step, sample, per_frame = cpu_arm(frames, pb, nthreads, seconds_budget=4.0)
     for _ in range(max(1, min(args.warmup, 1))):
         step(sample)
@@ -535,6 +636,10 @@ def main():
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS), help="BASELINE.json config: c2 = configs[1] (headline), c3 = configs[2], c5 = configs[4]")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-gather", dest="gather", action="store_false")
+    ap.add_argument("--real-parts", action="store_true",
+                    help="--impl reference, orb32 workloads: time the pipeline assembled from the reference's real parts (cv2 binary + "
+                         "oracle/_ref) instead of the oracle C port.  Informational: it is SLOWER than the port (per-level ORB.compute "
+                         "rebuilds the pyramid 8 times, Python marshals the cv::KeyPoint lists), so the port stays the default baseline")
     args = ap.parse_args()
     args.batch = select_workload(args.workload, args.batch)
     if args.impl == "reference":
