@@ -68,10 +68,14 @@ def _vp(x):
 
 
 def _stream_ptr(stream):
+    """cudaStream_t for the C ABI.  torch's default stream has handle 0, which the extractor entry points read as "use the
+    extractor's own non-blocking stream" -- unordered against torch work on the default stream that produced the inputs.  The
+    legacy default stream is therefore passed explicitly as cudaStreamLegacy (0x1), which keeps the call ordered after it."""
     if stream is None:
         import torch
         stream = torch.cuda.current_stream()
-    return C.c_void_p(stream.cuda_stream)
+    h = stream.cuda_stream
+    return C.c_void_p(h if h else 1)
 
 
 class FeatureExtractor:

@@ -77,6 +77,7 @@ struct afv_extractor {
     int max_batch, max_w, max_h;
     int cur_w, cur_h;                 // geometry the tables / params are currently built for
     cudaStream_t stream;
+    cudaEvent_t ev_order;             // orders the private stream after the legacy default stream (NULL-stream calls)
     AfvAux aux;
     std::vector<void*> allocs;        // everything to cudaFree
     uint8_t* pyr[AFV_MAX_LEVELS];     // un-blurred arena per level (level 0 = staging copy of the input)
@@ -92,6 +93,7 @@ struct afv_extractor {
     int q_orb[AFV_MAX_LEVELS], q_ext[AFV_MAX_LEVELS];
     float scale[AFV_MAX_LEVELS], size_norm[AFV_MAX_LEVELS], ext_scale[AFV_MAX_LEVELS];
     AfvParams P;
+    int oct_mcap, oct_ncap;           // this extractor's k_octree capacities
     int last_B;
     cudaStream_t last_stream;
     AfvSift* sift;                    // sift128 state (feature_id == AFV_FEAT_SIFT128), else NULL
@@ -167,6 +169,7 @@ static int configure_geometry(afv_extractor* ex, int w, int h) {
     if (P.n_ini < 1) { afv_set_error("portrait frames with w/h < 0.5 are not supported (reference divides by zero)"); return AFV_ERR_INVALID; }
     P.hX = (float)w / (float)P.n_ini;
     P.counts = ex->counts; P.status = ex->status;
+    P.oct_mcap = ex->oct_mcap; P.oct_ncap = ex->oct_ncap;
     for (int l = 0; l < ex->nlevels; ++l) {
         AfvLevel& L = P.lv[l];
         L.w = lw[l]; L.h = lh[l];
@@ -232,10 +235,11 @@ extern "C" int afv_extractor_create(afv_extractor** out, int feature_id, int nfe
     ex->scale_factor = scale_factor; ex->detect_th = detect_th;
     ex->max_batch = max_batch; ex->max_w = max_w; ex->max_h = max_h; ex->cur_w = ex->cur_h = 0;
     ex->last_B = 0; ex->last_stream = nullptr;
-    ex->sift = nullptr; ex->akaze = nullptr;
+    ex->sift = nullptr; ex->akaze = nullptr; ex->ev_order = nullptr; ex->stream = nullptr;
     ex->desc_bytes = feature_id == AFV_FEAT_SIFT128 ? 512 : feature_id == AFV_FEAT_AKAZE61 ? 61 : 32;
     ex->h_status = nullptr; ex->h_counts = nullptr; ex->aux.stream = nullptr; ex->aux.ev_pyr = nullptr; ex->aux.ev_blur = nullptr;
     AFV_CUDA_CHECK(cudaStreamCreateWithFlags(&ex->stream, cudaStreamNonBlocking));
+    AFV_CUDA_CHECK(cudaEventCreateWithFlags(&ex->ev_order, cudaEventDisableTiming));
     if (feature_id == AFV_FEAT_SIFT128 || feature_id == AFV_FEAT_AKAZE61) {
         // FeatureExtractor_akaze61 (reference src/Feature_akaze61.cpp:7-13): omax = n_octaves / 4, nsublevels = n_octaves / 2,
         // dthreshold = detect_th.
@@ -308,7 +312,7 @@ extern "C" int afv_extractor_create(afv_extractor** out, int feature_id, int nfe
     if (rc == AFV_OK) {
         int mdet = 0, mkeep = 0;
         for (int l = 0; l < n_octaves; ++l) { if (ex->det_cap[l] > mdet) mdet = ex->det_cap[l]; if (ex->keep_cap[l] > mkeep) mkeep = ex->keep_cap[l]; }
-        rc = afv_orb_configure(mdet, mkeep);
+        rc = afv_orb_configure(mdet, mkeep, &ex->oct_mcap, &ex->oct_ncap);
     }
     if (rc != AFV_OK) { afv_extractor_destroy(ex); return rc; }
     *out = ex;
@@ -320,6 +324,7 @@ extern "C" void afv_extractor_destroy(afv_extractor* ex) {
     cudaSetDevice(ex->device);
     if (ex->stream) { cudaStreamSynchronize(ex->stream); cudaStreamDestroy(ex->stream); }
     if (ex->aux.stream) { cudaStreamSynchronize(ex->aux.stream); cudaStreamDestroy(ex->aux.stream); }
+    if (ex->ev_order) cudaEventDestroy(ex->ev_order);
     if (ex->aux.ev_pyr) cudaEventDestroy(ex->aux.ev_pyr);
     if (ex->aux.ev_blur) cudaEventDestroy(ex->aux.ev_blur);
     for (void* p : ex->allocs) cudaFree(p);
@@ -391,6 +396,12 @@ extern "C" int afv_extract_batch_device(afv_extractor* ex, const uint8_t* d_gray
     if (!ex || !d_gray || !d_kps || !d_desc || !d_n_out) { afv_set_error("NULL argument"); return AFV_ERR_INVALID; }
     AFV_CUDA_CHECK(cudaSetDevice(ex->device));
     cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : ex->stream;
+    if (!cuda_stream) {
+        // the private stream is cudaStreamNonBlocking: order it after whatever the legacy default stream has queued (the
+        // usual producer of d_gray and of freshly zeroed output buffers) so NULL never races with the caller's work
+        AFV_CUDA_CHECK(cudaEventRecord(ex->ev_order, cudaStreamLegacy));
+        AFV_CUDA_CHECK(cudaStreamWaitEvent(ex->stream, ex->ev_order, 0));
+    }
     int rc = run_device(ex, d_gray, B, w, h, stride, frame_stride, d_kps, d_desc, d_kpsize, cap, d_n_out, st, false);
     if (rc) return rc;
     if (!cuda_stream) return check_status(ex, B, st);

@@ -47,6 +47,7 @@ struct AfvParams {
     int fast_th;
     int n_ini; float hX;      // octree roots (reference src/ORBextractor.cc:243-245)
     int out_cap;              // per-frame output capacity (caller's cap)
+    int oct_mcap, oct_ncap;   // k_octree capacities of THIS extractor (keys / nodes held in shared memory)
     int* counts;              // [frame][4][AFV_MAX_LEVELS]: 0 = #candidates, 1 = #det, 2 = #kept, 3 = spare
     int* status;              // [frame] bit flags (AFV_ST_*)
     AfvLevel lv[AFV_MAX_LEVELS];
@@ -69,7 +70,7 @@ struct AfvAux { cudaStream_t stream; cudaEvent_t ev_pyr, ev_blur; };   // side s
 int afv_launch_extract(const AfvParams& P, afv_keypoint* d_kps, uint8_t* d_desc, float* d_kpsize,
                        int* d_n_out, cudaStream_t st, const AfvAux& aux);
 size_t afv_octree_smem_bytes(int mcap, int ncap);
-int afv_orb_configure(int max_det_cap, int max_keep_cap);   // sets smem attributes; returns 0 / cuda error
+int afv_orb_configure(int max_det_cap, int max_keep_cap, int* mcap_out, int* ncap_out);   // raises the smem attribute; returns 0 / error
 
 // matcher launches (afv_match.cu) are called directly from afv_capi.cu through the C ABI.
 

@@ -728,14 +728,27 @@ __global__ void __launch_bounds__(256, 5) k_describe(const __grid_constant__ Afv
 // ------------------------------------------------------------------------------------------------------
 // host-side launch sequence for one batch (all on one stream, no host synchronisation inside)
 // ------------------------------------------------------------------------------------------------------
-static int g_oct_mcap = 0, g_oct_ncap = 0;
+// Octree capacities belong to the extractor (AfvParams::oct_mcap / oct_ncap): the reference builds two extractors with
+// different nfeatures (src/Tracking.cc:78,84).  The dynamic shared-memory attribute of k_octree is per device and only
+// ever raised to the running maximum, so an earlier, larger extractor keeps working after a smaller one is created.
+#include <mutex>
+static std::mutex g_oct_mu;
+static size_t g_oct_smem_set[64] = {0};                  // per device
 
-int afv_orb_configure(int max_det_cap, int max_keep_cap) {
-    g_oct_mcap = max_det_cap;
-    g_oct_ncap = max_keep_cap + 8;
-    size_t smem = afv_octree_smem_bytes(g_oct_mcap, g_oct_ncap);
+int afv_orb_configure(int max_det_cap, int max_keep_cap, int* mcap_out, int* ncap_out) {
+    const int mcap = max_det_cap, ncap = max_keep_cap + 8;
+    size_t smem = afv_octree_smem_bytes(mcap, ncap);
     if (smem > 227 * 1024) { afv_set_error("octree shared memory %zu B exceeds 227 KB (nfeatures too large)", smem); return AFV_ERR_INVALID; }
-    AFV_CUDA_CHECK(cudaFuncSetAttribute(k_octree, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int dev = 0;
+    AFV_CUDA_CHECK(cudaGetDevice(&dev));
+    {
+        std::lock_guard<std::mutex> lk(g_oct_mu);
+        if (dev < 0 || dev >= 64 || smem > g_oct_smem_set[dev]) {
+            AFV_CUDA_CHECK(cudaFuncSetAttribute(k_octree, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            if (dev >= 0 && dev < 64) g_oct_smem_set[dev] = smem;
+        }
+    }
+    *mcap_out = mcap; *ncap_out = ncap;
     return AFV_OK;
 }
 
@@ -792,7 +805,7 @@ int afv_launch_extract(const AfvParams& P, afv_keypoint* d_kps, uint8_t* d_desc,
     cudaEventRecord(aux.ev_blur, aux.stream);
     { AfvProfScope ps("k_harris_select", st); k_harris_select<<<dim3(P.nlevels, P.B), 256, 0, st>>>(P); ++g_afv_launches; }
     { AfvProfScope ps("k_octree", st);
-      k_octree<<<dim3(P.nlevels, P.B), 256, afv_octree_smem_bytes(g_oct_mcap, g_oct_ncap), st>>>(P, g_oct_mcap, g_oct_ncap);
+      k_octree<<<dim3(P.nlevels, P.B), 256, afv_octree_smem_bytes(P.oct_mcap, P.oct_ncap), st>>>(P, P.oct_mcap, P.oct_ncap);
       ++g_afv_launches; }
     cudaStreamWaitEvent(st, aux.ev_blur, 0);
     { AfvProfScope ps("k_describe", st);

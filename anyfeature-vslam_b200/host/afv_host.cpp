@@ -147,10 +147,13 @@ void FeatureExtractor::extractBatch(const std::vector<const Image*>& imgs, std::
 }
 
 std::shared_ptr<FeatureExtractor> getFeatureExtractor(const int& scaleNumFeaturesMonocular, const std::string& yaml, const std::string& feature, int imWidth, int imHeight) {
-    const int nFeatures0 = 1000;                                                      // src/Tracking.cc:1515-1520
-    int nFeatures = int(float(nFeatures0) * float(imWidth * imHeight) / float(640 * 480));
-    if (nFeatures < 1000) nFeatures = 1000;
+    // src/Tracking.cc:1514-1520: linear interpolation between 1000 features at 640x480 and 2000 at 1241x376 (double
+    // arithmetic on a float pixel count, truncated to int), clamped to [1000, 2000], then scaled
+    const int numFeatures0 = 1000;
+    const int w = imWidth, h = imHeight;
+    int nFeatures = ((2000.0 - 1000.0) / (1241.0 * 376.0 - 640.0 * 480.0)) * (float(w * h) - 640.0 * 480.0) + numFeatures0;
     if (nFeatures > 2000) nFeatures = 2000;
+    else if (nFeatures < 1000) nFeatures = 1000;
     nFeatures *= scaleNumFeaturesMonocular;
     const int id = get_feature_id(feature);
     auto settings = std::make_shared<FeatureExtractorSettings>((KeypointType)id, (DescriptorType)id, yaml);

@@ -77,8 +77,10 @@ int  afv_extract(afv_extractor* ex, const uint8_t* gray, int w, int h, int strid
 int  afv_extract_batch(afv_extractor* ex, const uint8_t* gray, int B, int w, int h, int stride,
                        long frame_stride, afv_keypoint* kps, void* desc, float* kpsize, int cap, int* n_out);
 
-/* Same with DEVICE buffers, asynchronous on `cuda_stream` (a cudaStream_t; NULL = the extractor's own
- * stream, synchronised before return).  Capacity overflows are reported by afv_extractor_status(). */
+/* Same with DEVICE buffers, asynchronous on `cuda_stream` (a cudaStream_t).  NULL = the extractor's own non-blocking
+ * stream, ordered after everything already queued on the legacy default stream and synchronised before return; to run
+ * ON the legacy default stream pass cudaStreamLegacy ((void*)0x1).  Capacity overflows are reported by
+ * afv_extractor_status(). */
 int  afv_extract_batch_device(afv_extractor* ex, const uint8_t* d_gray, int B, int w, int h, int stride,
                               long frame_stride, afv_keypoint* d_kps, void* d_desc, float* d_kpsize,
                               int cap, int* d_n_out, void* cuda_stream);
