@@ -115,7 +115,6 @@ __global__ void __launch_bounds__(256) k_resize(const __grid_constant__ AfvParam
 #define FT_RW (FT_W + 2)
 #define FT_RH (FT_H + 2)
 #define FT_SW 132
-#define FT_HALF (FT_RH / 2)           // rows walked by one stage-1 thread
 
 __device__ __forceinline__ bool has_arc9(uint32_t m) {
     m |= m << 16;
@@ -181,38 +180,64 @@ __global__ void __launch_bounds__(256) k_fast(const __grid_constant__ AfvParams 
 
     const uint8_t* pb = reinterpret_cast<const uint8_t*>(&pixw[0][0]);
     constexpr int PITCH = FT_WP * 4;
-    // stage 1: sign-consistent compass test (below).  One thread walks 17 rows of one column with a rolling 15-pixel register window (centre, 3 above, 3 below
-    // come from the window; only left/right are extra loads) and appends its survivors with one warp-aggregated atomic.
-    static_assert(FT_RH == 2 * FT_HALF && FT_HALF <= 32, "two halves");
-    for (int round = 0; round < 2; ++round) {
-        if (round == 1 && tid >= 32) break;                      // items 256..259 live in warp 0
-        const int item = round * 256 + tid;
-        uint32_t smask = 0;
-        int c = 0, half = 0;
-        if (item < 2 * FT_RW) {
-            half = item >= FT_RW; c = item - half * FT_RW;
-            const int gx = x0 - 1 + c;
-            if (gx >= 3 && gx < L.w - 3) {
-                const uint8_t* pc = pb + FT_XOFF + (c + 3) + (FT_HALF * half) * PITCH;   // window row k <-> region row FT_HALF*half + k - 3
-                // rows that are real centres: 3 <= gy < h-3 with gy = y0 - 1 + FT_HALF*half + j
-                const int gy0 = y0 - 1 + FT_HALF * half;
-                const int jlo = max(0, 3 - gy0), jhi = min(FT_HALF, L.h - 3 - gy0);
-                int col[FT_HALF + 6];
+    // stage 1: sign-consistent compass test on FOUR pixels per thread and row, two pixels per 32-bit register.
+    // An arc of 9 of the 16 circle pixels always contains two ADJACENT compass points (0, 4, 8, 12), so a corner needs two
+    // adjacent compass points that are both brighter than v+t or both darker than v-t: (dn|up) & (rt|lf) per sign.
+    // A staged word w = (p0,p1,p2,p3) is split into E = (p0,p2) and O = (p1,p3), one pixel per 16-bit half.  With
+    // C = (0x8000 + t) in both halves, bit 15 of a half of (E + C) - x is CLEAR iff x > v + t and bit 15 of x + (C - E) is
+    // CLEAR iff x < v - t (all halves stay in [0x7f01, 0x81fe]: no carry between halves), so one IADD does a compare for two
+    // pixels and the pass condition is five LOP3s.  A thread owns one word column and FS1_ROWS rows and keeps the E / O words of
+    // its column in a rolling register window (up / down neighbours); left / right neighbours come from the adjacent words.
+    constexpr int FS1_ROWS = 5, FS1_WC0 = 3, FS1_NWC = 34, FS1_CH = 7;       // words 3..36 = staged bytes 12..147 cover the region
+    static_assert(FS1_ROWS * FS1_CH >= FT_RH && FS1_NWC * FS1_CH <= 256, "stage-1 work split");
+    static_assert(FT_XOFF + 3 == 15 && FS1_WC0 * 4 <= 15 && (FS1_WC0 + FS1_NWC) * 4 > 15 + FT_RW - 1, "word columns cover the region");
+    {
+        uint32_t smask = 0;                                        // bit 4*j + k: row j of the chunk, nibble bit k (see below)
+        int wc = 0, ch = 0;
+        if (tid < FS1_NWC * FS1_CH) {
+            ch = tid / FS1_NWC; wc = FS1_WC0 + tid - ch * FS1_NWC;
+            const uint32_t C2 = (0x8000u + (uint32_t)t) * 0x10001u, G = 0x80008000u;
+            uint32_t E[FS1_ROWS + 6], O[FS1_ROWS + 6];
 #pragma unroll
-                for (int k = 0; k < FT_HALF + 6; ++k) col[k] = pc[k * PITCH];
-#pragma unroll
-                for (int j = 0; j < FT_HALF; ++j) {
-                    // an arc of 9 of the 16 circle pixels always contains two ADJACENT compass points (0, 4, 8, 12), so a
-                    // corner needs two adjacent compass points that are both brighter than v+t or both darker than v-t:
-                    // (dn|up) & (rt|lf) per sign covers exactly the four adjacent pairs
-                    const int v = col[j + 3], hi = v + t, lo = v - t;
-                    const int dn = col[j + 6], up = col[j], rt = pc[(j + 3) * PITCH + 3], lf = pc[(j + 3) * PITCH - 3];
-                    const bool pass = (((dn > hi) | (up > hi)) & ((rt > hi) | (lf > hi))) | (((dn < lo) | (up < lo)) & ((rt < lo) | (lf < lo)));
-                    smask |= (uint32_t)pass << j;
-                }
-                const uint32_t rowmask = jhi > jlo ? (((jhi >= 32) ? 0xffffffffu : ((1u << jhi) - 1u)) & ~((1u << jlo) - 1u)) : 0u;
-                smask &= rowmask;
+            for (int k = 0; k < FS1_ROWS + 6; ++k) {               // staged rows ch*FS1_ROWS + k (region row + 3 = staged row)
+                const uint32_t w = pixw[min(ch * FS1_ROWS + k, FT_PH - 1)][wc];
+                E[k] = w & 0x00ff00ffu; O[k] = __byte_perm(w, 0, 0x4341);
             }
+#pragma unroll
+            for (int j = 0; j < FS1_ROWS; ++j) {
+                const int rs = min(ch * FS1_ROWS + j + 3, FT_PH - 1);
+                const uint32_t wm = pixw[rs][wc - 1], wp = pixw[rs][wc + 1];
+                const uint32_t Em = wm & 0x00ff00ffu, Om = __byte_perm(wm, 0, 0x4341);
+                const uint32_t Ep = wp & 0x00ff00ffu, Op = __byte_perm(wp, 0, 0x4341);
+                // pixels (p0,p2): left = (p-3,p-1) = Om, right = (p3,p5) = (O.hi, Op.lo); pixels (p1,p3): left = (p-2,p0) = (Em.hi, E.lo), right = (p4,p6) = Ep
+                const uint32_t lfA = Om, rtA = __byte_perm(O[j + 3], Op, 0x5432);
+                const uint32_t lfB = __byte_perm(Em, E[j + 3], 0x5432), rtB = Ep;
+                // bright pair exists iff min(max(dn,up), max(rt,lf)) > v + t; dark pair iff max(min(dn,up), min(rt,lf)) < v - t
+                const uint32_t K1a = E[j + 3] + C2, K2a = C2 - E[j + 3];
+                const uint32_t bA = __vmins2(__vmaxs2(E[j + 6], E[j]), __vmaxs2(rtA, lfA));
+                const uint32_t dA = __vmaxs2(__vmins2(E[j + 6], E[j]), __vmins2(rtA, lfA));
+                const uint32_t K1b = O[j + 3] + C2, K2b = C2 - O[j + 3];
+                const uint32_t bB = __vmins2(__vmaxs2(O[j + 6], O[j]), __vmaxs2(rtB, lfB));
+                const uint32_t dB = __vmaxs2(__vmins2(O[j + 6], O[j]), __vmins2(rtB, lfB));
+                const uint32_t pa = ~((K1a - bA) & (dA + K2a)) & G, pbm = ~((K1b - bB) & (dB + K2b)) & G;   // pass flags at bits 15 / 31
+                // nibble: bit 0 = p0, bit 1 = p1, bit 2 = p2, bit 3 = p3
+                const uint32_t nib = ((pa >> 15) & 1u) | ((pbm >> 14) & 2u) | ((pa >> 29) & 4u) | ((pbm >> 28) & 8u);
+                smask |= nib << (4 * j);
+            }
+            // validity: region columns c = 4*wc + k - 15 in [0, FT_RW) with 3 <= gx < w-3; region rows r = ch*FS1_ROWS + j < FT_RH with 3 <= gy < h-3
+            uint32_t cm = 0;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int c = 4 * wc + k - 15, gx = x0 - 1 + c;
+                if (c >= 0 && c < FT_RW && gx >= 3 && gx < L.w - 3) cm |= 1u << k;
+            }
+            uint32_t vm = 0;
+#pragma unroll
+            for (int j = 0; j < FS1_ROWS; ++j) {
+                const int r = ch * FS1_ROWS + j, gy = y0 - 1 + r;
+                if (r < FT_RH && gy >= 3 && gy < L.h - 3) vm |= cm << (4 * j);
+            }
+            smask &= vm;
         }
         const int cnt = __popc(smask);
         int incl = cnt;
@@ -225,14 +250,20 @@ __global__ void __launch_bounds__(256) k_fast(const __grid_constant__ AfvParams 
             base = __shfl_sync(0xffffffffu, base, 31);
         }
         int o = base + incl - cnt;
+        const int i0 = ch * FS1_ROWS * FT_RW + 4 * wc - 15;
         while (smask) {
-            const int j = __ffs(smask) - 1;
+            const int bpos = __ffs(smask) - 1;
             smask &= smask - 1;
-            slist[o++] = (uint16_t)((FT_HALF * half + j) * FT_RW + c);
+            slist[o++] = (uint16_t)(i0 + (bpos >> 2) * FT_RW + (bpos & 3));
         }
     }
     __syncthreads();
-    // stage 2: full 16-point masks for the survivors
+    // stage 2: corner score of every stage-1 survivor = max over the 16 arcs of 9 of min|v - p| (same sign), minus 1 (OpenCV
+    // cornerScore<16>); the pixel is a FAST-9 corner at threshold t iff that maximum exceeds t, so no separate segment test is
+    // needed.  d[k] = v - p[k] in [-255,255] packed as (d, -d) in the two signed 16-bit halves: one __vmins2 chain gives both
+    // min(d) (darker arcs) and min(-d) (brighter arcs); sliding minimum over 9 by doubling.
+    // NB: the scalar form max(min9(d), -max9(d)) is MISCOMPILED by nvcc 12.9 / ptxas for sm_100a (3-input VIMNMX3 with a
+    // negated operand; repro in tools/dbg/minmax_dbg.cu) - keep this formulation.
     const int n1 = nstage1;
     for (int j0 = 0; j0 < n1; j0 += 256) {
         const int j = j0 + tid;
@@ -242,45 +273,28 @@ __global__ void __launch_bounds__(256) k_fast(const __grid_constant__ AfvParams 
             i = slist[j];
             const int r = i / FT_RW, c = i % FT_RW;
             const uint8_t* p = pb + (r + 3) * PITCH + FT_XOFF + (c + 3);
-            const int v = p[0], hi = v + t, lo = v - t;
-            uint32_t br = 0, dk = 0;
-#define FMASK(k, dx, dy) { const int q = p[(dy) * PITCH + (dx)]; br |= (uint32_t)(q > hi) << k; dk |= (uint32_t)(q < lo) << k; }
-            CIRC16(FMASK)
-#undef FMASK
-            corner = has_arc9(br) || has_arc9(dk);
+            const int v = p[0];
+            uint32_t e[16];
+#define FDIFF(k, dx, dy) { const int dv = v - (int)p[(dy) * PITCH + (dx)]; e[k] = ((uint32_t)dv & 0xffffu) | ((uint32_t)(-dv) << 16); }
+            CIRC16(FDIFF)
+#undef FDIFF
+            uint32_t m2[16], m4[16];
+#pragma unroll
+            for (int k = 0; k < 16; ++k) m2[k] = __vmins2(e[k], e[(k + 1) & 15]);
+#pragma unroll
+            for (int k = 0; k < 16; ++k) m4[k] = __vmins2(m2[k], m2[(k + 2) & 15]);
+            uint32_t acc = 0x80008000u;
+#pragma unroll
+            for (int k = 0; k < 16; ++k) acc = __vmaxs2(acc, __vmins2(__vmins2(m4[k], m4[(k + 4) & 15]), e[(k + 8) & 15]));
+            const int bd = (int)(short)(acc & 0xffffu), bb = (int)(short)(acc >> 16);
+            const int best = bd > bb ? bd : bb;
+            corner = best > t;
+            if (corner) score[r][c] = (uint8_t)(best - 1);
         }
         warp_push(corner, (uint16_t)i, clist, &ncorner, lane);
     }
     __syncthreads();
-
-    // corner score = max over the 16 arcs of 9 of min|v - p| (same sign), minus 1 (OpenCV cornerScore<16>)
     const int nc = ncorner;
-    for (int j = tid; j < nc; j += 256) {
-        const int i = clist[j];
-        const int r = i / FT_RW, c = i % FT_RW;
-        const uint8_t* p = pb + (r + 3) * (FT_WP * 4) + FT_XOFF + (c + 3);
-        const int v = p[0];
-        // d[k] = v - p[k] in [-255,255]: packed as (d, -d) in the two signed 16-bit halves so one __vmins2 chain
-        // gives both min(d) (darker arcs) and min(-d) (brighter arcs); sliding minimum over 9 by doubling.
-        // NB: the scalar form max(min9(d), -max9(d)) is MISCOMPILED by nvcc 12.9 / ptxas for sm_100a (3-input
-        // VIMNMX3 with a negated operand; repro in tools/dbg/minmax_dbg.cu) - keep this formulation.
-        uint32_t e[16];
-#define FDIFF(k, dx, dy) { const int dv = v - (int)p[(dy) * (FT_WP * 4) + (dx)]; e[k] = ((uint32_t)dv & 0xffffu) | ((uint32_t)(-dv) << 16); }
-        CIRC16(FDIFF)
-#undef FDIFF
-        uint32_t m2[16], m4[16];
-#pragma unroll
-        for (int k = 0; k < 16; ++k) m2[k] = __vmins2(e[k], e[(k + 1) & 15]);
-#pragma unroll
-        for (int k = 0; k < 16; ++k) m4[k] = __vmins2(m2[k], m2[(k + 2) & 15]);
-        uint32_t acc = 0x80008000u;
-#pragma unroll
-        for (int k = 0; k < 16; ++k) acc = __vmaxs2(acc, __vmins2(__vmins2(m4[k], m4[(k + 4) & 15]), e[(k + 8) & 15]));
-        const int bd = (int)(short)(acc & 0xffffu), bb = (int)(short)(acc >> 16);
-        const int best = bd > bb ? bd : bb;
-        score[r][c] = (uint8_t)(best - 1);
-    }
-    __syncthreads();
 
     // 3x3 non-max suppression (strictly greater than all 8 neighbours), interior of the tile only
     for (int j = tid; j < nc; j += 256) {

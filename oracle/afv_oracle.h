@@ -177,6 +177,22 @@ long  orc_akaze61_extract_match_batch(const uint8_t* frames, int B, int w, int h
                                       float detect_th, const int* pair_a, const int* pair_b, int P, int window, float th_akaze,
                                       float th_brisk, float nnratio, int check_ori, int nthreads);
 
+/* ---- brisk48 (afv_oracle_brisk.c; PARITY UNPINNED vs ETH brisk v2, detector / orientation / 512-bit core semi-pinned to
+ * cv2 4.13.0's cv::BRISK) ------------------------------------------------------------------------------------------ */
+#define ORC_BRISK_SEQUENTIAL 0   /* lazy score cache exactly as the authors' implementation (cv2-comparable) */
+#define ORC_BRISK_DENSE      1   /* order-independent contract implemented by the CUDA path */
+void  orc_resize_area_u8(const uint8_t* src, int sw, int sh, int sstride, uint8_t* dst, int dw, int dh, int dstride);
+long  orc_brisk_layer(const uint8_t* gray, int w, int h, int stride, int octaves, int what, int layer, uint8_t* out, int* ow, int* oh);
+int   orc_brisk_detect(const uint8_t* gray, int w, int h, int stride, int threshold, int octaves, int mode, float* out5, int cap);
+int   orc_brisk_describe(const uint8_t* gray, int w, int h, int stride, orc_keypoint* kps, int n, int nbytes, int libm_angle,
+                         uint8_t* desc, int* kept_index);
+int   orc_brisk_scale_index(float size);
+int   orc_brisk_size_list(unsigned* out64);
+double orc_brisk_atan2(double y, double x);
+int   orc_brisk48_extract(const uint8_t* gray, int w, int h, int stride, int nfeatures, int nlevels, float scale_factor,
+                          float detect_th, int mode, orc_keypoint* kps, uint8_t* desc, float* kpsize, int cap, int* n_out,
+                          int* n_detected);
+
 #ifdef __cplusplus
 }
 #endif

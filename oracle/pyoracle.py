@@ -20,7 +20,7 @@ DESC_ORB, DESC_AKAZE61, DESC_BRISK, DESC_SIFT128 = 0, 1, 2, 5      # include/Typ
 
 def build(force=False):
     so = os.path.join(_DIR, "libafv_oracle.so")
-    srcs = [os.path.join(_DIR, f) for f in ("afv_oracle.c", "afv_oracle_match.c", "afv_oracle_sift.c", "afv_oracle_akaze.c", "afv_oracle_batch.c", "afv_oracle.h", "orb_pattern.inc")]
+    srcs = [os.path.join(_DIR, f) for f in ("afv_oracle.c", "afv_oracle_match.c", "afv_oracle_sift.c", "afv_oracle_akaze.c", "afv_oracle_brisk.c", "afv_oracle_batch.c", "afv_oracle.h", "orb_pattern.inc")]
     if force or not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
         subprocess.check_call(["make", "-s", "-C", _DIR, "libafv_oracle.so"])
     return so
@@ -368,3 +368,68 @@ def features_in_area(kps, kpsize, bounds, x, y, r, min_size, max_size):
     m = lib().orc_features_in_area(_p(kps), _p(kpsize), _p(cs), _p(ci), _f(minX), _f(minY), _f(invW), _f(invH), _f(x), _f(y), _f(r),
                                    _f(min_size), _f(max_size), _p(out), len(out))
     return out[:m].copy()
+
+
+# ---- brisk48 (oracle/afv_oracle_brisk.c; PARITY UNPINNED vs ETH brisk v2, semi-pinned to cv2.BRISK, see its header) ----
+BRISK_SEQUENTIAL, BRISK_DENSE = 0, 1
+
+
+def resize_area(img, dw, dh):
+    img = np.ascontiguousarray(img, np.uint8)
+    h, w = img.shape
+    out = np.zeros((dh, dw), np.uint8)
+    lib().orc_resize_area_u8(_p(img), w, h, w, _p(out), dw, dh, dw)
+    return out
+
+
+def brisk_layer(gray, what, layer, octaves=4):
+    """what = 0: pyramid layer image, 1: true AGAST 9-16 score image (0 below 1)."""
+    gray = np.ascontiguousarray(gray, np.uint8)
+    h, w = gray.shape
+    ow = C.c_int(0); oh = C.c_int(0)
+    L = lib(); L.orc_brisk_layer.restype = C.c_long
+    n = L.orc_brisk_layer(_p(gray), w, h, w, int(octaves), int(what), int(layer), None, C.byref(ow), C.byref(oh))
+    if n < 0:
+        raise ValueError("layer %d not built" % layer)
+    out = np.zeros((oh.value, ow.value), np.uint8)
+    L.orc_brisk_layer(_p(gray), w, h, w, int(octaves), int(what), int(layer), _p(out), C.byref(ow), C.byref(oh))
+    return out
+
+
+def brisk_detect(gray, threshold=34, octaves=4, mode=BRISK_DENSE, cap=200000):
+    """BriskFeatureDetector(threshold, octaves).detect: rows (x, y, size, response, layer) in detection order."""
+    gray = np.ascontiguousarray(gray, np.uint8)
+    h, w = gray.shape
+    out = np.zeros((cap, 5), np.float32)
+    n = lib().orc_brisk_detect(_p(gray), w, h, w, int(threshold), int(octaves), int(mode), _p(out), cap)
+    if n < 0:
+        raise RuntimeError("orc_brisk_detect failed / capacity (%d)" % n)
+    return out[:n].copy()
+
+
+def brisk_describe(gray, kps, nbytes=48, libm_angle=False):
+    """BriskDescriptorExtractor.compute on a KP_DTYPE array: returns (kept keypoints with angle, descriptors, kept index)."""
+    gray = np.ascontiguousarray(gray, np.uint8)
+    h, w = gray.shape
+    k = np.ascontiguousarray(kps, KP_DTYPE).copy()
+    desc = np.zeros((max(len(k), 1), nbytes), np.uint8)
+    idx = np.zeros(max(len(k), 1), np.int32)
+    m = lib().orc_brisk_describe(_p(gray), w, h, w, _p(k), len(k), int(nbytes), int(bool(libm_angle)), _p(desc), _p(idx))
+    return k[:m], desc[:m], idx[:m]
+
+
+def brisk_scale_index(size):
+    return int(lib().orc_brisk_scale_index(_f(size)))
+
+
+def brisk48_extract(gray, nfeatures, nlevels=8, scale_factor=1.5, detect_th=34.0, mode=BRISK_DENSE):
+    gray = np.ascontiguousarray(gray, np.uint8)
+    h, w = gray.shape
+    cap = nfeatures + 3 * nlevels + 64
+    kps = np.zeros(cap, KP_DTYPE); desc = np.zeros((cap, 48), np.uint8); size = np.zeros(cap, np.float32)
+    n = C.c_int(0); nd = C.c_int(0)
+    rc = lib().orc_brisk48_extract(_p(gray), w, h, w, int(nfeatures), int(nlevels), _f(scale_factor), _f(detect_th), int(mode),
+                                   _p(kps), _p(desc), _p(size), cap, C.byref(n), C.byref(nd))
+    if rc:
+        raise RuntimeError("orc_brisk48_extract failed (%d)" % rc)
+    return kps[:n.value], desc[:n.value], size[:n.value], nd.value
