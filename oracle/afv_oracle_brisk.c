@@ -547,7 +547,7 @@ static int brk_detect(brk_space* S, int threshold, int mode, brk_kp** out) {
         for (int y = 3; y < L->h - 3; ++y)
             for (int x = 3; x < L->w - 3; ++x) {
                 const int s = brk_score_9_16(L->img, L->w, x, y);
-                if (mode == 1 && s >= 1) L->scores[(size_t)y * L->w + x] = (uint8_t)(s > 255 ? 255 : s);
+                if (mode >= 1 && s >= 1) L->scores[(size_t)y * L->w + x] = (uint8_t)(s > 255 ? 255 : s);
                 if (s >= threshold) {
                     if (an[i] == acap) { acap *= 2; ax[i] = (int*)realloc(ax[i], sizeof(int) * 2 * (size_t)acap); }
                     ax[i][2 * an[i]] = x; ax[i][2 * an[i] + 1] = y; ++an[i];
@@ -570,6 +570,7 @@ static int brk_detect(brk_space* S, int threshold, int mode, brk_kp** out) {
         brk_layer* L = &S->L[i];
         brk_layer Lmax = *L;                       /* view used by isMax2D */
         if (mode == 1) Lmax.scores = thr[i];
+        if (mode == 2) { L->dense = 1; }
         for (int k = 0; k < an[i]; ++k) {
             const int px = ax[i][2 * k], py = ax[i][2 * k + 1];
             if (!brk_is_max2d(&Lmax, px, py)) continue;
@@ -727,7 +728,7 @@ static int brk_smoothed(const uint8_t* image, int imagecols, const int* integral
     if (dx + dy > 2) {
         const uint8_t* ptr = image + x_left + imagecols * y_top;
         ret_val = A * (int)(*ptr); ptr += dx + 1;
-        ret_val += B * (int)(*ptr); ptr += dy * imagecols + 1;
+        ret_val += B * (int)(*ptr); ptr += (dy + 1) * imagecols;
         ret_val += C * (int)(*ptr); ptr -= dx + 1;
         ret_val += D * (int)(*ptr);
         const int* pi = integral + x_left + integralcols * y_top + 1;
@@ -845,7 +846,8 @@ int orc_brisk_describe(const uint8_t* gray, int w, int h, int stride, orc_keypoi
             direction0 += delta_t * g_long[p].wdx / 1024;
             direction1 += delta_t * g_long[p].wdy / 1024;
         }
-        if (libm_angle) kp.angle = (float)(atan2f((float)direction1, (float)direction0) / M_PI * 180.0);
+        if (libm_angle == 2) kp.angle = (float)(atan2((double)(float)direction1, (double)(float)direction0) / M_PI * 180.0);
+        else if (libm_angle) kp.angle = (float)(atan2f((float)direction1, (float)direction0) / M_PI * 180.0);
         else kp.angle = (float)(orc_brisk_atan2((double)(float)direction1, (double)(float)direction0) / M_PI * 180.0);
         int theta;
         if (kp.angle == -1) theta = 0;

@@ -414,7 +414,7 @@ def brisk_describe(gray, kps, nbytes=48, libm_angle=False):
     k = np.ascontiguousarray(kps, KP_DTYPE).copy()
     desc = np.zeros((max(len(k), 1), nbytes), np.uint8)
     idx = np.zeros(max(len(k), 1), np.int32)
-    m = lib().orc_brisk_describe(_p(gray), w, h, w, _p(k), len(k), int(nbytes), int(bool(libm_angle)), _p(desc), _p(idx))
+    m = lib().orc_brisk_describe(_p(gray), w, h, w, _p(k), len(k), int(nbytes), int(libm_angle), _p(desc), _p(idx))
     return k[:m], desc[:m], idx[:m]
 
 
