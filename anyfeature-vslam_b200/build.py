@@ -17,6 +17,7 @@ SOURCES = [
     ("afv_match.cu", ["--fmad=false"]),
     ("afv_sift.cu", ["--fmad=false"]),
     ("afv_akaze.cu", ["--fmad=false"]),
+    ("afv_brisk.cu", ["--fmad=false"]),
     ("afv_capi.cu", ["--fmad=false"]),
 ]
 COMMON = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
