@@ -108,6 +108,9 @@ float FeatureExtractor_sift128::GetKeypointSize(const KeyPoint& keypoint) const 
 float FeatureExtractor_akaze61::GetKeypointSize(const KeyPoint& keypoint) const {
     return powf(settings->GetDetectorNominalScaleFactor(), float(GetKeypointOctave(keypoint)));
 }
+float FeatureExtractor_brisk48::GetKeypointSize(const KeyPoint& keypoint) const {
+    return powf(settings->GetDetectorNominalScaleFactor(), float(GetKeypointOctave(keypoint)));
+}
 
 // detectKeypoints + filterKeypoints + computeDescriptors + mergeKeypointLevels + computeSize of the subclass as ONE C-ABI call
 void FeatureExtractor::detectAndComputeABI(const Image& img, std::vector<KeyPoint>& keypoints, Mat& descriptors, std::vector<float>& sizes) {
@@ -161,8 +164,9 @@ std::shared_ptr<FeatureExtractor> getFeatureExtractor(const int& scaleNumFeature
         case FEAT_ORB: return std::make_shared<FeatureExtractor_orb32>(nFeatures, settings);
         case FEAT_SIFT128: return std::make_shared<FeatureExtractor_sift128>(nFeatures, settings);
         case FEAT_AKAZE61: return std::make_shared<FeatureExtractor_akaze61>(nFeatures, settings);
+        case FEAT_BRISK: return std::make_shared<FeatureExtractor_brisk48>(nFeatures, settings);
         default:
-            std::fprintf(stderr, "getFeatureExtractor: feature '%s' has no B200 extractor (orb32, sift128, akaze61 are built)\n", feature.c_str());
+            std::fprintf(stderr, "getFeatureExtractor: feature '%s' has no B200 extractor (orb32, akaze61, brisk48, sift128 are built)\n", feature.c_str());
             std::terminate();                                                         // include/Types.h:67-70 behaviour
     }
 }

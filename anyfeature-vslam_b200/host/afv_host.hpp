@@ -6,6 +6,7 @@
 //   FeatureExtractor_orb32    include/Feature_orb32.h, src/Feature_orb32.cpp
 //   FeatureExtractor_sift128  include/Feature_sift128.h, src/Feature_sift128.cpp (CV_32F N x 128, angle in radians)
 //   FeatureExtractor_akaze61  include/Feature_akaze61.h, src/Feature_akaze61.cpp (CV_8U N x 61, octave := class_id)
+//   FeatureExtractor_brisk48  include/Feature_brisk48.h, src/Feature_brisk48.cpp (CV_8U N x 48, octave = BRISK layer 0..7)
 //   getFeatureExtractor       src/Tracking.cc:1505-1553 (factory, nfeatures clamp :1515-1520)
 //   FeatureMatcher            include/FeatureMatcher.h:36-118 (SearchForInitialization, static DescriptorDistance,
 //                             setDescriptorDistanceThresholds; TH_LOW/TH_HIGH statics)
@@ -119,6 +120,17 @@ protected:
     void detectAndCompute(const Image& img, std::vector<KeyPoint>& keypoints, Mat& descriptors, std::vector<float>& sizes) override { detectAndComputeABI(img, keypoints, descriptors, sizes); }
     int featureId() const override { return AFV_FEAT_AKAZE61; }
     int descCols() const override { return 61; }
+};
+
+class FeatureExtractor_brisk48 : public FeatureExtractor {           // src/Feature_brisk48.cpp:7-64 (CV_8U N x 48, octave = BRISK layer)
+public:
+    FeatureExtractor_brisk48(const int& nfeatures_, std::shared_ptr<FeatureExtractorSettings>& settings_) : FeatureExtractor(nfeatures_, settings_) {}
+protected:
+    int GetKeypointOctave(const KeyPoint& keypoint) const override { return keypoint.octave; }                       // :50-52
+    float GetKeypointSize(const KeyPoint& keypoint) const override;                                                  // :54-56
+    void detectAndCompute(const Image& img, std::vector<KeyPoint>& keypoints, Mat& descriptors, std::vector<float>& sizes) override { detectAndComputeABI(img, keypoints, descriptors, sizes); }
+    int featureId() const override { return AFV_FEAT_BRISK48; }
+    int descCols() const override { return 48; }
 };
 
 // Tracking::getFeatureExtractor (src/Tracking.cc:1505-1553): nfeatures scaled with resolution, clamped to [1000,2000]

@@ -40,9 +40,9 @@ WORKLOADS = {
                metric="frames/sec (extract+match) sift128 1280x720x2000kp",
                name="sift128 1280x720 synthetic batch, 2000 kp/frame, extract+SearchForInitialization (L2) on 1xB200 per rank (configs[2])"),
     "c4": dict(feature="akaze61", w=640, h=480, nfeat=1000, batch=256, desc_bytes=61, desc_type=1, th_low=128.0,
-               metric="frames/sec (extract+match) akaze61+brisk48-layout 640x480x1000kp",
-               name="akaze61 640x480 synthetic batch, 1000 kp/frame, extract + mixed Hamming SearchForInitialization (61-byte akaze61 "
-                    "and 48-byte brisk48 layout = first 384 MLDB bits; no brisk48 extractor: ETH brisk is not vendored) on 1xB200 per rank (configs[3])"),
+               metric="frames/sec (extract+match) akaze61+brisk48 640x480x1000kp",
+               name="akaze61 + brisk48 640x480 synthetic batch, 1000 kp/frame: BOTH extractors on every frame, each followed by its own "
+                    "Hamming SearchForInitialization (61-byte akaze61, 48-byte brisk48) on 1xB200 per rank (configs[3])"),
     "c5": dict(feature="orb32", w=1280, h=720, nfeat=2000, batch=128, desc_bytes=32, desc_type=0, th_low=75.0,
                metric="frames/sec (extract+match) orb32 1280x720x2000kp",
                name="orb32 1280x720 synthetic 8-stream batch, 2000 kp/frame, streams sharded over ranks, NCCL gather (configs[4])"),
@@ -350,15 +350,16 @@ def run_gpu(args):
     ex = pkg.FeatureExtractor(FEAT, nfeatures=NFEAT, device=local, max_batch=B, max_w=W, max_h=H)
     cap = ex.cap
     fm = pkg.FeatureMatcher(nnratio=0.9, check_ori=True, desc_type=WL["desc_type"], th_low=WL["th_low"])
-    MIXED = FEAT == "akaze61"                                   # c4: second pass on the 48-byte brisk48 layout
+    MIXED = FEAT == "akaze61"                                   # c4: the brisk48 extractor + its 48-byte Hamming matcher run on the same frames
     fm48 = pkg.FeatureMatcher(nnratio=0.9, check_ori=True, desc_type=2, th_low=120.0) if MIXED else None
+    ex2 = pkg.FeatureExtractor("brisk48", nfeatures=NFEAT, device=local, max_batch=B, max_w=W, max_h=H) if MIXED else None
+    out2 = ex2.alloc_device_outputs(B) if MIXED else None
     d_gray = torch.from_numpy(frames).to(dev)
     h_gray = torch.from_numpy(frames).pin_memory()
     d_pa = torch.from_numpy(pa).to(dev); d_pb = torch.from_numpy(pb).to(dev)
     out = ex.alloc_device_outputs(B)
     m12 = torch.empty((B, cap), dtype=torch.int32, device=dev)
     nm = torch.empty((B,), dtype=torch.int32, device=dev)
-    d48 = torch.empty((B, cap, 48), dtype=torch.uint8, device=dev) if MIXED else None
     m12b = torch.empty((B, cap), dtype=torch.int32, device=dev) if MIXED else None
     nmb = torch.empty((B,), dtype=torch.int32, device=dev) if MIXED else None
     stream = torch.cuda.current_stream()
@@ -377,8 +378,8 @@ def run_gpu(args):
         fm.search_for_initialization(out[0], out[1], out[2], out[3], d_pa, d_pb, None, BOUNDS, MAX_KPT_SIZE,
                                      window=100, matches12=m12, nmatches=nm, stream=stream)
         if MIXED:
-            d48.copy_(out[1][:, :, :48])
-            fm48.search_for_initialization(out[0], d48, out[2], out[3], d_pa, d_pb, None, BOUNDS, MAX_KPT_SIZE,
+            ex2.extract_batch_device(src, out2, stream)
+            fm48.search_for_initialization(out2[0], out2[1], out2[2], out2[3], d_pa, d_pb, None, BOUNDS, MAX_KPT_SIZE,
                                            window=100, matches12=m12b, nmatches=nmb, stream=stream)
         if world > 1 and args.gather and collective:
             k = step_counter[0] & 1
@@ -405,6 +406,8 @@ def run_gpu(args):
     drain_collectives()
     torch.cuda.synchronize()
     ex.status()
+    if MIXED:
+        ex2.status()
     n_host = out[3].cpu().numpy(); nm_host = nm.cpu().numpy()
     assert (n_host.min() >= NFEAT or FEAT != "orb32") and n_host.min() > 0 and n_host.max() <= cap, \
         "unexpected keypoint counts %d..%d" % (n_host.min(), n_host.max())
@@ -439,10 +442,11 @@ def run_gpu(args):
     c_nm = [torch.empty((CH,), dtype=torch.int32, device=dev) for _ in range(2)]
     c_pa = d_pa[:CH].contiguous(); c_pb = d_pb[:CH].contiguous()            # pair pattern repeats every 16 frames
     h_out = [torch.empty(t.shape, dtype=t.dtype).pin_memory() for t in (out[0], out[1], out[3], m12, nm)]
-    c_d48 = [torch.empty((CH, cap, 48), dtype=torch.uint8, device=dev) for _ in range(2)] if MIXED else None
+    exs2 = [pkg.FeatureExtractor("brisk48", nfeatures=NFEAT, device=local, max_batch=CH, max_w=W, max_h=H) for _ in range(2)] if MIXED else None
+    c_out2 = [e.alloc_device_outputs(CH) for e in exs2] if MIXED else None
     c_m12b = [torch.empty((CH, cap), dtype=torch.int32, device=dev) for _ in range(2)] if MIXED else None
     c_nmb = [torch.empty((CH,), dtype=torch.int32, device=dev) for _ in range(2)] if MIXED else None
-    h_out_b = [torch.empty(t.shape, dtype=t.dtype).pin_memory() for t in (m12b, nmb)] if MIXED else []
+    h_out_b = [torch.empty(t.shape, dtype=t.dtype).pin_memory() for t in (out2[0], out2[1], out2[3], m12b, nmb)] if MIXED else []
 
     chunk_counter = [0]
 
@@ -462,10 +466,10 @@ def run_gpu(args):
                 for hdst, dsrc in zip(h_out, (c_out[k][0], c_out[k][1], c_out[k][3], c_m12[k], c_nm[k])):
                     hdst[lo:hi].copy_(dsrc, non_blocking=True)
                 if MIXED:
-                    c_d48[k].copy_(c_out[k][1][:, :, :48])
-                    fm48.search_for_initialization(c_out[k][0], c_d48[k], c_out[k][2], c_out[k][3], c_pa, c_pb, None, BOUNDS,
+                    exs2[k].extract_batch_device(c_in[k], c_out2[k], st)
+                    fm48.search_for_initialization(c_out2[k][0], c_out2[k][1], c_out2[k][2], c_out2[k][3], c_pa, c_pb, None, BOUNDS,
                                                    MAX_KPT_SIZE, window=100, matches12=c_m12b[k], nmatches=c_nmb[k], stream=st)
-                    for hdst, dsrc in zip(h_out_b, (c_m12b[k], c_nmb[k])):
+                    for hdst, dsrc in zip(h_out_b, (c_out2[k][0], c_out2[k][1], c_out2[k][3], c_m12b[k], c_nmb[k])):
                         hdst[lo:hi].copy_(dsrc, non_blocking=True)
 
     def e2e_drain():
@@ -491,7 +495,10 @@ def run_gpu(args):
     if sampler:
         sampler.stop()
     h2d = int(h_gray.numel()); d2h = int(sum(t.numel() * t.element_size() for t in h_out + h_out_b))
-    for e in exs:
+    if MIXED:
+        assert (h_out_b[2].numpy() == out2[3].cpu().numpy()).all() and (h_out_b[1].numpy() == out2[1].cpu().numpy()).all(), \
+            "e2e brisk48 results differ from the device-resident results"
+    for e in exs + (exs2 or []):
         e.close()
 
     # ---- max over ranks
@@ -537,6 +544,18 @@ def run_gpu(args):
             "k_akz_describe": B * N * (109 * 8 + 1241 * 12 + 61 + 28),
         }
         if FEAT == "akaze61":
+            # brisk48 (second extractor of c4): layer pixels S_B, N2 kept keypoints
+            lw_, lh_ = [W, 2 * (W // 3)], [H, 2 * (H // 3)]
+            for i_ in range(2, 8):
+                lw_.append(lw_[i_ - 2] // 2); lh_.append(lh_[i_ - 2] // 2)
+            S_B = float(sum(a * b for a, b in zip(lw_, lh_)))
+            N2 = float(out2[3].float().mean())
+            alg_akaze.update({
+                "k_brk_resize": B * (2.0 * (S_B - W * H) + W * H),
+                "k_brk_score": B * 2.0 * S_B,                         # read every layer, write its score image
+                "k_brk_integral": B * (W * H + 3 * 4.0 * (W + 1) * (H + 1)),
+                "k_brk_describe": B * N2 * (2 * 60 * (4 + 12 * 4) + 28 + 48),
+            })
             alg_sift = alg_akaze
         alg = alg_sift if FEAT in ("sift128", "akaze61") else {
             "k_resize": B * (2 * P_PIX - W * H - int(np.rint(W / 1.2 ** 7)) * int(np.rint(H / 1.2 ** 7))),   # read levels 0..6, write levels 1..7
@@ -616,6 +635,7 @@ def run_gpu(args):
             "roofline": roofline,
             "cpu_baseline": cpu_baseline,
             "check": {"kps_per_frame": [int(n_host.min()), int(n_host.max())], "matches_per_pair_mean": float(nm_host.mean()),
+                      "brisk48_kps_per_frame": [int(out2[3].min()), int(out2[3].max())] if MIXED else None,
                       "matches48_per_pair_mean": float(nmb.float().mean()) if MIXED else None},
         }
         print(json.dumps(line))
@@ -623,6 +643,8 @@ def run_gpu(args):
         dist.barrier()
         dist.destroy_process_group()
     ex.close()
+    if ex2 is not None:
+        ex2.close()
     return 0
 
 

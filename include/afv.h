@@ -24,7 +24,7 @@ extern "C" {
 #define AFV_ERR_NO_DEVICE   -2   /* CUDA device / driver unavailable: the product path has no CPU fallback */
 #define AFV_ERR_CUDA        -3   /* CUDA runtime error (see afv_last_error) */
 #define AFV_ERR_CAPACITY    -4   /* an internal or caller buffer capacity was exceeded (frame reported in text) */
-#define AFV_ERR_UNSUPPORTED -5   /* feature id without an extractor (brisk48: ETH brisk v2 is not vendored, no oracle) */
+#define AFV_ERR_UNSUPPORTED -5   /* feature id without an extractor (surf64, kaze64, r2d2_128, anyFeat*) */
 
 /* feature / descriptor ids == reference include/Types.h:11-45 and get_feature_id (:102-124) */
 #define AFV_FEAT_ORB32      0
@@ -51,9 +51,13 @@ typedef struct afv_extractor afv_extractor;
  *   AFV_FEAT_AKAZE61 (src/Feature_akaze61.cpp) descriptors CV_8U  N x 61 (MLDB-486), octave = libAKAZE octave, class_id =
  *                    evolution level (the reference's "octave", :63-65); omax = n_octaves/4, nsublevels = n_octaves/2,
  *                    dthreshold = detect_th (:10-12); frame width and height must be even
- * sift128 / akaze61 implement the published algorithms in the parameterisation the reference selects; SiftGPU / libAKAZE
- * are not vendored by the reference, so parity with them is UNPINNED (oracle/afv_oracle_{sift,akaze}.c headers).
- * AFV_FEAT_BRISK48 returns AFV_ERR_UNSUPPORTED. */
+ *   AFV_FEAT_BRISK48 (src/Feature_brisk48.cpp) descriptors CV_8U  N x 48, octave = BRISK layer 0 .. 2*(n_octaves/2)-1 (:29-30),
+ *                    angle in degrees, class_id -1; detector = BriskFeatureDetector(int(detect_th), n_octaves / 2, true) (:24-26),
+ *                    keypoints whose sampling pattern leaves the image are removed by the descriptor stage like brisk's compute()
+ * sift128 / akaze61 / brisk48 implement the published algorithms in the parameterisation the reference selects; SiftGPU /
+ * libAKAZE / ETH brisk are not vendored by the reference, so parity with them is UNPINNED (oracle/afv_oracle_{sift,akaze,brisk}.c
+ * headers; the brisk48 detector, orientation and 512-bit descriptor core are pinned to cv2.BRISK, the 48-byte pair table is a
+ * documented stand-in). */
 int  afv_extractor_create(afv_extractor** out, int feature_id, int nfeatures, int n_octaves,
                           float scale_factor, float detect_th, int device,
                           int max_batch, int max_w, int max_h);
@@ -67,7 +71,7 @@ int  afv_extractor_levels(const afv_extractor* ex, float* scale_factors, int* fe
 
 /* FeatureExtractor::operator()(Image, keypoints, descriptors, ..., size) for ONE frame, host buffers
  * (src/FeatureExtractor.cpp:111-129).  gray: 8-bit single channel, `stride` bytes per row.
- * kps[cap], desc[cap*D] (D = 32 bytes orb32, 61 bytes akaze61, 512 bytes = 128 floats sift128), kpsize[cap] (computeSize,
+ * kps[cap], desc[cap*D] (D = 32 bytes orb32, 61 bytes akaze61, 48 bytes brisk48, 512 bytes = 128 floats sift128), kpsize[cap] (computeSize,
  * :132-142; may be NULL). */
 int  afv_extract(afv_extractor* ex, const uint8_t* gray, int w, int h, int stride,
                  afv_keypoint* kps, void* desc, float* kpsize, int cap, int* n_out);
@@ -90,7 +94,8 @@ int  afv_extractor_status(afv_extractor* ex);
 /* Stage taps for parity tests (device -> host copy of an intermediate of the LAST batch).
  * sift128: what = 10 Gaussian image / 11 DoG image (level = octave * 8 + index, float), 12 SiftGPU-order list after the -tc2
  *          limit (x, y, s, o floats).  akaze61: what = 20..24 Lt / Lsmooth / Lx / Ly / Ldet of evolution level `level`,
- *          25 Feature_Detection list (x, y, size, response, class_id floats), 26 contrast factor.  orb32:
+ *          25 Feature_Detection list (x, y, size, response, class_id floats), 26 contrast factor.  brisk48: what = 30 layer image,
+ *          31 AGAST 9-16 score image of layer `level` (u8), 32 detect list (x, y, size, response, layer floats).  orb32:
  *   what = 0: pyramid level image (w_l*h_l bytes, tight)      1: blurred level image
  *          2: FAST+NMS candidates (uint32 x | y<<12 | score<<24, unordered)
  *          3: cv::ORB::detect-equivalent list after both retainBest culls (uint32 packed xy, float response

@@ -34,6 +34,7 @@
  */
 #include "afv_oracle.h"
 #include <math.h>
+#include <pthread.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -634,17 +635,17 @@ static int cmp_pairdist(const void* a, const void* b) {
     return x[1] < y[1] ? -1 : (x[1] > y[1] ? 1 : 0);
 }
 
-static void brk_build_pattern(void) {
-    if (g_pat) return;
+static void brk_build_pattern_once(void);
+static pthread_once_t g_pat_once = PTHREAD_ONCE_INIT;
+static void brk_build_pattern(void) { pthread_once(&g_pat_once, brk_build_pattern_once); }      /* thread-safe (batch CPU arm) */
+static void brk_build_pattern_once(void) {
     const float f = 0.85f * 1.0f;
     const float rList[5] = {(float)(f * 0.), (float)(f * 2.9), (float)(f * 4.9), (float)(f * 7.4), (float)(f * 10.8)};
     const int nList[5] = {1, 10, 14, 15, 20};
     const float dMax = 5.85f, dMin = 8.2f;
     brk_pp* pat = (brk_pp*)malloc(sizeof(brk_pp) * (size_t)BRK_POINTS * BRK_SCALES * BRK_NROT);
-    const float lb_scale = (float)(log((double)30.f) / log(2.0));          /* std::log(float) = logf; see below */
-    const float lb_scale2 = (float)((double)logf(30.f) / log(2.0));
-    (void)lb_scale;
-    const float lb_scale_step = lb_scale2 / (float)BRK_SCALES;
+    const float lb_scale = (float)((double)logf(30.f) / log(2.0));          /* std::log(scalerange_) on a float is logf */
+    const float lb_scale_step = lb_scale / (float)BRK_SCALES;
     const float sigma_scale = 1.3f;
     brk_pp* it = pat;
     for (unsigned scale = 0; scale < BRK_SCALES; ++scale) {

@@ -14,7 +14,7 @@ static bool read_pgm(const char* path, Image& im) {
     return (bool)f;
 }
 int main(int argc, char** argv) {
-    if (argc < 4) { std::fprintf(stderr, "usage: %s settings.yaml a.pgm b.pgm [orb32|sift128|akaze61]\n", argv[0]); return 2; }
+    if (argc < 4) { std::fprintf(stderr, "usage: %s settings.yaml a.pgm b.pgm [orb32|sift128|akaze61|brisk48]\n", argv[0]); return 2; }
     const std::string feature = argc > 4 ? argv[4] : "orb32";
     Image A, B;
     if (!read_pgm(argv[2], A) || !read_pgm(argv[3], B)) return 3;

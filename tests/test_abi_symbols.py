@@ -42,12 +42,12 @@ def test_unsupported_feature_is_an_error_not_a_fallback():
     import __graft_entry__ as g
     pkg = g._load_pkg()
     h = C.c_void_p()
-    # brisk48: ETH brisk's 48-byte v2 pattern is not vendored by the reference, nothing to restate -> no extractor
-    rc = pkg.lib().afv_extractor_create(C.byref(h), 2, 1000, 8, C.c_float(1.5), C.c_float(34.0), 0, 1, 640, 480)
+    # surf64 (feature id 3): no extractor in this library -> an error code, never a substitute
+    rc = pkg.lib().afv_extractor_create(C.byref(h), 3, 1000, 8, C.c_float(1.5), C.c_float(34.0), 0, 1, 640, 480)
     assert rc == -5 and not h.value
     import torch
-    if not torch.cuda.is_available():                       # sift128 / akaze61 are built, but never on the CPU
-        for fid, sf, th in ((5, 2.0, 10.0), (1, 1.1892, 5e-4)):
+    if not torch.cuda.is_available():                       # sift128 / akaze61 / brisk48 are built, but never on the CPU
+        for fid, sf, th in ((5, 2.0, 10.0), (1, 1.1892, 5e-4), (2, 1.5, 34.0)):
             rc = pkg.lib().afv_extractor_create(C.byref(h), fid, 1000, 8, C.c_float(sf), C.c_float(th), 0, 1, 640, 480)
             assert rc == -2 and not h.value
 

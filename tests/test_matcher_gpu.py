@@ -158,7 +158,7 @@ def test_empty_inputs(pkg):
     assert (b.cpu().numpy() == -1).all() and (bd.cpu().numpy() == np.finfo(np.float32).max).all()
 
 
-@pytest.mark.parametrize("feature", ["orb32", "sift128", "akaze61"])
+@pytest.mark.parametrize("feature", ["orb32", "sift128", "akaze61", "brisk48"])
 def test_cpp_host_mirror_matches_python_path(pkg, synth, tmp_path, feature):
     """FeatureExtractor_<feat>::operator() + FeatureMatcher::SearchForInitialization through the C++ mirror."""
     import os
@@ -194,7 +194,7 @@ def test_cpp_host_mirror_matches_python_path(pkg, synth, tmp_path, feature):
     for v in m12[0, :int(n[0])].cpu().numpy().tolist():
         h = ((h ^ ((v + 1) & 0xffffffff)) * 1099511628211) & 0xffffffffffffffff
     assert int(got["n0"]) == int(n[0]) and int(got["n1"]) == int(n[1]) and int(got["matches"]) == int(nm[0])
-    assert int(got["levels"]) == 8 and int(got["q0"]) == {"orb32": 217, "sift128": 502, "akaze61": 212}[feature]
+    assert int(got["levels"]) == 8 and int(got["q0"]) == {"orb32": 217, "sift128": 502, "akaze61": 212, "brisk48": 347}[feature]
     assert int(got["hash"]) == h
     ex.close()
 
