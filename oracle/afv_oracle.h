@@ -130,6 +130,26 @@ int orc_search_by_projection(int desc_type, const void* qdesc, const float* qxy,
         const uint8_t* occupied_in, float minX, float minY, float maxX, float maxY,
         float th, float nnratio, int ratio_same_scale, float tol, int* match_q);
 
+/* All projection-type searches of the reference after their projection prologue (options select the variant: see the table
+ * above the definition in afv_oracle_match.c); qr < 0 skips a query; qangle != NULL adds the orientation histogram;
+ * tinf1d != NULL adds Fuse's monocular reprojection gate; claim = accepted matches occupy their train keypoint. */
+int orc_search_by_projection_ex(int desc_type, const void* qdesc, const float* qxy, const float* qr, const float* qmin,
+        const float* qmax, const float* qangle, int nq, const orc_keypoint* tk, const void* td, const float* tsize,
+        const float* tinf1d, int nt, const uint8_t* occupied_in, int claim, float minX, float minY, float maxX, float maxY,
+        float th, float nnratio, int ratio_same_scale, float tol, int* match_q);
+/* SearchBySim3 (src/FeatureMatcher.cc:1066-1287): two stateless directed searches + agreement; match12[i1] = i2 or -1. */
+int orc_search_by_sim3(int desc_type,
+        const void* q1desc, const float* q1xy, const float* q1r, const float* q1min, const float* q1max, int n1,
+        const void* q2desc, const float* q2xy, const float* q2r, const float* q2min, const float* q2max, int n2,
+        const orc_keypoint* k1, const void* d1, const float* size1, const orc_keypoint* k2, const void* d2, const float* size2,
+        float minX, float minY, float maxX, float maxY, float th_high, int* match12);
+/* BoW merge-join searches on per-feature node ids: mode 0 SearchByBoW(KF,F) (:186-283), 1 SearchByBoW(KF,KF) (:561-660),
+ * 2 SearchForTriangulation (:662-790, monocular). */
+int orc_bow_match(int mode, int desc_type,
+        const orc_keypoint* k1, const void* d1, const int* node1, const uint8_t* valid1, int n1,
+        const orc_keypoint* k2, const void* d2, const int* node2, const uint8_t* valid2, int n2,
+        float th_low, float nnratio, int check_ori, const float* F12, float ex, float ey, const float* sigma2_2, int* out);
+
 /* MapPoint::ComputeDistinctiveDescriptors (src/MapPoint.cc:279-348) for one map point: index into obs[0..N). */
 int orc_distinctive_descriptor(int desc_type, const void* desc, const int* obs, int N);
 

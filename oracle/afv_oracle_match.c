@@ -511,3 +511,206 @@ void orc_undistort_keypoints(const orc_keypoint* kps, int n, const float* K4, co
         out[i] = kp;
     }
 }
+
+/* ---------------------------------------------------------------- SearchByProjection family, all variants -- */
+/* One restatement with the options that distinguish the reference's projection-type searches (everything after the
+ * projection prologue, which stays with the caller: queries arrive as projected position, radius and accepted size range):
+ *   :73-154   TrackLocalMap        occupied + claim, ratio rule when best / second have the same scale (ratio_same_scale = 1)
+ *   :287-397  Sim3 (loop closing)  occupied (vpMatched) + claim, best only, th = TH_LOW
+ *   :1291-1402 TrackWithMotionModel occupied + claim, best only, th = TH_HIGH, orientation histogram (qangle)
+ *   :1406-1506 relocalisation      occupied (CurrentFrame.pts) + claim, best only, th = reloc threshold, orientation histogram
+ *   :794-942  Fuse (local mapping) NO occupied test, NO claim, best only, th = TH_LOW, reprojection gate
+ *                                  e2 * GetKeyPt1DInf(idx) > 5.99 (monocular branch, :905-915) -> tinf1d
+ *   :944-1064 Fuse (loop closing)  NO occupied test, NO claim, best only
+ *   :1066-1287 SearchBySim3        two such stateless best-only searches (th = TH_HIGH) + agreement (orc_search_by_sim3)
+ * A query with qr < 0 is skipped (the reference's `continue`s of the projection prologue).  match_q[i] = train index or -1.
+ * With an orientation histogram the entries are the TRAIN indices (points[j] = NULL, :1601-1612): the match of that train
+ * keypoint is removed.  Returns the number of matches left. */
+int orc_search_by_projection_ex(int desc_type, const void* qdesc, const float* qxy, const float* qr, const float* qmin,
+        const float* qmax, const float* qangle, int nq, const orc_keypoint* tk, const void* td, const float* tsize,
+        const float* tinf1d, int nt, const uint8_t* occupied_in, int claim, float minX, float minY, float maxX, float maxY,
+        float th, float nnratio, int ratio_same_scale, float tol, int* match_q) {
+    const int D = orc_descriptor_bytes(desc_type);
+    const float invW = (float)GRID_COLS / (maxX - minX), invH = (float)GRID_ROWS / (maxY - minY);
+    const float invtol = 1.0f / tol;
+    int* cs = (int*)malloc(sizeof(int) * (GRID_COLS * GRID_ROWS + 1));
+    int* ci = (int*)malloc(sizeof(int) * (nt + 1));
+    int* cand = (int*)malloc(sizeof(int) * (nt + 1));
+    int* bin_of_q = (int*)malloc(sizeof(int) * (nq + 1));
+    uint8_t* occ = (uint8_t*)calloc((size_t)nt + 1, 1);
+    int hist_cnt[HISTO_LENGTH] = {0};
+    if (occupied_in) memcpy(occ, occupied_in, (size_t)nt);
+    orc_grid_build(tk, nt, minX, minY, invW, invH, cs, ci);
+    int nmatches = 0;
+    for (int i = 0; i < nq; ++i) {
+        match_q[i] = -1; bin_of_q[i] = -1;
+        if (qr[i] < 0.0f) continue;
+        int nc = orc_features_in_area(tk, tsize, cs, ci, minX, minY, invW, invH, qxy[2 * i], qxy[2 * i + 1], qr[i], qmin[i], qmax[i], cand, nt);
+        if (nc == 0) continue;
+        const uint8_t* ref = (const uint8_t*)qdesc + (long)i * D;
+        float bestDist = FLT_MAX, bestDist2 = FLT_MAX, bestSize = -1.0f, bestSize2 = -1.0f;
+        int bestIdx = -1;
+        for (int c = 0; c < nc; ++c) {
+            const int idx = cand[c];
+            if (occ[idx]) continue;
+            if (tinf1d) {                                        /* Fuse, monocular branch (:905-915) */
+                const float ex = qxy[2 * i] - tk[idx].x, ey = qxy[2 * i + 1] - tk[idx].y;
+                const float e2 = ex * ex + ey * ey;
+                if (e2 * tinf1d[idx] > 5.99) continue;
+            }
+            const float d = orc_descriptor_distance(desc_type, ref, (const uint8_t*)td + (long)idx * D);
+            if (d < bestDist) { bestDist2 = bestDist; bestDist = d; bestIdx = idx; bestSize2 = bestSize; bestSize = tsize[idx]; }
+            else if (d < bestDist2) { bestDist2 = d; bestSize2 = tsize[idx]; }
+        }
+        if (bestDist <= th) {
+            if (ratio_same_scale) {
+                if ((bestSize / bestSize2 < tol) && (bestSize / bestSize2 > invtol) && (bestSize2 > 0.0f)) {
+                    if (bestDist > nnratio * bestDist2) continue;
+                }
+            }
+            match_q[i] = bestIdx; nmatches++;
+            if (claim) occ[bestIdx] = 1;
+            if (qangle) { const int bin = orc_rot_bin(qangle[i], tk[bestIdx].angle); bin_of_q[i] = bin; hist_cnt[bin]++; }
+        }
+    }
+    if (qangle) {
+        int i1m, i2m, i3m;
+        orc_three_maxima(hist_cnt, HISTO_LENGTH, &i1m, &i2m, &i3m);
+        for (int i = 0; i < nq; ++i) {
+            const int b = bin_of_q[i];
+            if (b < 0 || b == i1m || b == i2m || b == i3m) continue;
+            match_q[i] = -1; nmatches--;
+        }
+    }
+    free(cs); free(ci); free(cand); free(occ); free(bin_of_q);
+    return nmatches;
+}
+
+/* FeatureMatcher::SearchBySim3 (src/FeatureMatcher.cc:1066-1287) after the projection prologue: direction 1 -> 2 projects the
+ * map points of KF1's keypoints into KF2 (queries indexed by KF1 keypoint, qr < 0 = skipped), direction 2 -> 1 likewise; both are
+ * stateless best-only searches with th = TH_HIGH; a pair is accepted when both directions agree (:1270-1284).
+ * match12[i1] = i2 or -1.  Returns nFound. */
+int orc_search_by_sim3(int desc_type,
+        const void* q1desc, const float* q1xy, const float* q1r, const float* q1min, const float* q1max, int n1,
+        const void* q2desc, const float* q2xy, const float* q2r, const float* q2min, const float* q2max, int n2,
+        const orc_keypoint* k1, const void* d1, const float* size1, const orc_keypoint* k2, const void* d2, const float* size2,
+        float minX, float minY, float maxX, float maxY, float th_high, int* match12) {
+    int* m1 = (int*)malloc(sizeof(int) * (n1 + 1)); int* m2 = (int*)malloc(sizeof(int) * (n2 + 1));
+    orc_search_by_projection_ex(desc_type, q1desc, q1xy, q1r, q1min, q1max, NULL, n1, k2, d2, size2, NULL, n2, NULL, 0, minX, minY, maxX, maxY,
+                                th_high, 1.0f, 0, 1.0f, m1);
+    orc_search_by_projection_ex(desc_type, q2desc, q2xy, q2r, q2min, q2max, NULL, n2, k1, d1, size1, NULL, n1, NULL, 0, minX, minY, maxX, maxY,
+                                th_high, 1.0f, 0, 1.0f, m2);
+    int nFound = 0;
+    for (int i1 = 0; i1 < n1; ++i1) {
+        match12[i1] = -1;
+        const int idx2 = m1[i1];
+        if (idx2 >= 0 && m2[idx2] == i1) { match12[i1] = idx2; nFound++; }
+    }
+    free(m1); free(m2);
+    return nFound;
+}
+
+/* ---------------------------------------------------------------- BoW merge-join searches on per-feature node ids ----
+ * The FeatureVector of a frame is given as the node id of every feature (what Vocabulary::transform returns per feature,
+ * src/Vocabulary.cpp:200-204; < 0 = feature not in the vector): DBoW2's map<node, vector<feature>> lists the features of a node
+ * in increasing feature index, nodes ascending, which is the (node, index) order used here.
+ *   mode 0  SearchByBoW(KF, F)   src/FeatureMatcher.cc:186-283: frame-1 features need valid1 (map point present and good, :216-222),
+ *           frame-2 features already matched are skipped (:232-233), best <= th_low and best < nnratio * second;
+ *           out[i2] = i1 (vpMapPointMatches is indexed by the FRAME feature), orientation entries are frame-2 indices
+ *   mode 1  SearchByBoW(KF, KF)  :561-660: valid1 / valid2 gates, vbMatched2, best < th_low (strict, :630) and the ratio;
+ *           out[i1] = i2, orientation entries are frame-1 indices
+ *   mode 2  SearchForTriangulation :662-790 (monocular): only features WITHOUT a map point on both sides (valid = "has map point"),
+ *           candidates with dist > th_low or dist > best are skipped, epipole distance gate (:744-751), epipolar line gate
+ *           (CheckDistEpipolarLine :165-183); vbMatched2 is never set by the reference, so frame-1 features are independent;
+ *           out[i1] = i2.  F12 row-major, (ex, ey) the epipole in image 2, sigma2_2 = GetKeyPt1DSigma2 of frame 2.
+ * Returns the number of matches. */
+typedef struct { int node, idx; } bow_ent;
+static int cmp_bow_ent(const void* a, const void* b) {
+    const bow_ent* x = (const bow_ent*)a; const bow_ent* y = (const bow_ent*)b;
+    if (x->node != y->node) return x->node < y->node ? -1 : 1;
+    return x->idx < y->idx ? -1 : (x->idx > y->idx ? 1 : 0);
+}
+int orc_bow_match(int mode, int desc_type,
+        const orc_keypoint* k1, const void* d1, const int* node1, const uint8_t* valid1, int n1,
+        const orc_keypoint* k2, const void* d2, const int* node2, const uint8_t* valid2, int n2,
+        float th_low, float nnratio, int check_ori, const float* F12, float ex, float ey, const float* sigma2_2, int* out) {
+    const int D = orc_descriptor_bytes(desc_type);
+    bow_ent* e1 = (bow_ent*)malloc(sizeof(bow_ent) * (n1 + 1)); bow_ent* e2 = (bow_ent*)malloc(sizeof(bow_ent) * (n2 + 1));
+    int m1 = 0, m2 = 0;
+    for (int i = 0; i < n1; ++i) if (node1[i] >= 0) { e1[m1].node = node1[i]; e1[m1].idx = i; ++m1; }
+    for (int i = 0; i < n2; ++i) if (node2[i] >= 0) { e2[m2].node = node2[i]; e2[m2].idx = i; ++m2; }
+    qsort(e1, (size_t)m1, sizeof(bow_ent), cmp_bow_ent); qsort(e2, (size_t)m2, sizeof(bow_ent), cmp_bow_ent);
+    const int nout = mode == 0 ? n2 : n1;
+    int* bin_of = (int*)malloc(sizeof(int) * (nout + 1));
+    uint8_t* matched2 = (uint8_t*)calloc((size_t)n2 + 1, 1);
+    int hist_cnt[HISTO_LENGTH] = {0};
+    for (int i = 0; i < nout; ++i) { out[i] = -1; bin_of[i] = -1; }
+    int nMatches = 0, a = 0, b = 0;
+    while (a < m1 && b < m2) {
+        if (e1[a].node == e2[b].node) {
+            int a1 = a, b1 = b;
+            while (a1 < m1 && e1[a1].node == e1[a].node) ++a1;
+            while (b1 < m2 && e2[b1].node == e2[b].node) ++b1;
+            for (int ia = a; ia < a1; ++ia) {
+                const int idx1 = e1[ia].idx;
+                const uint8_t* ref = (const uint8_t*)d1 + (long)idx1 * D;
+                if (mode == 2) {
+                    if (valid1 && valid1[idx1]) continue;                       /* already a map point (:701-704) */
+                    float bestDist = th_low; int bestIdx2 = -1;
+                    for (int ib = b; ib < b1; ++ib) {
+                        const int idx2 = e2[ib].idx;
+                        if (valid2 && valid2[idx2]) continue;                   /* :722-724 (vbMatched2 is never set) */
+                        const float dist = orc_descriptor_distance(desc_type, ref, (const uint8_t*)d2 + (long)idx2 * D);
+                        if (dist > th_low || dist > bestDist) continue;
+                        const float distex = ex - k2[idx2].x, distey = ey - k2[idx2].y;
+                        if (distex * distex + distey * distey < 100.0f * sqrtf(sigma2_2[idx2])) continue;
+                        /* CheckDistEpipolarLine */
+                        const float la = k1[idx1].x * F12[0] + k1[idx1].y * F12[3] + F12[6];
+                        const float lb = k1[idx1].x * F12[1] + k1[idx1].y * F12[4] + F12[7];
+                        const float lc = k1[idx1].x * F12[2] + k1[idx1].y * F12[5] + F12[8];
+                        const float num = la * k2[idx2].x + lb * k2[idx2].y + lc;
+                        const float den = la * la + lb * lb;
+                        if (den == 0) continue;
+                        const float dsqr = num * num / den;
+                        if (dsqr < 3.84f * sigma2_2[idx2]) { bestIdx2 = idx2; bestDist = dist; }
+                    }
+                    if (bestIdx2 >= 0) { out[idx1] = bestIdx2; nMatches++; }
+                    continue;
+                }
+                if (valid1 && !valid1[idx1]) continue;
+                float bd1 = FLT_MAX, bd2 = FLT_MAX; int best2 = -1;
+                for (int ib = b; ib < b1; ++ib) {
+                    const int idx2 = e2[ib].idx;
+                    if (matched2[idx2]) continue;
+                    if (mode == 1 && valid2 && !valid2[idx2]) continue;
+                    const float dist = orc_descriptor_distance(desc_type, ref, (const uint8_t*)d2 + (long)idx2 * D);
+                    if (dist < bd1) { bd2 = bd1; bd1 = dist; best2 = idx2; }
+                    else if (dist < bd2) bd2 = dist;
+                }
+                const int pass_th = mode == 0 ? (bd1 <= th_low) : (bd1 < th_low);
+                if (pass_th && bd1 < nnratio * bd2) {
+                    matched2[best2] = 1; nMatches++;
+                    const int oi = mode == 0 ? best2 : idx1;
+                    out[oi] = mode == 0 ? idx1 : best2;
+                    if (check_ori) { const int bin = orc_rot_bin(k1[idx1].angle, k2[best2].angle); bin_of[oi] = bin; hist_cnt[bin]++; }
+                }
+            }
+            a = a1; b = b1;
+        } else if (e1[a].node < e2[b].node) {
+            while (a < m1 && e1[a].node < e2[b].node) ++a;
+        } else {
+            while (b < m2 && e2[b].node < e1[a].node) ++b;
+        }
+    }
+    if (check_ori && mode != 2) {
+        int i1m, i2m, i3m;
+        orc_three_maxima(hist_cnt, HISTO_LENGTH, &i1m, &i2m, &i3m);
+        for (int i = 0; i < nout; ++i) {
+            const int bn = bin_of[i];
+            if (bn < 0 || bn == i1m || bn == i2m || bn == i3m) continue;
+            out[i] = -1; nMatches--;
+        }
+    }
+    free(e1); free(e2); free(bin_of); free(matched2);
+    return nMatches;
+}

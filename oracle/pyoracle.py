@@ -433,3 +433,52 @@ def brisk48_extract(gray, nfeatures, nlevels=8, scale_factor=1.5, detect_th=34.0
     if rc:
         raise RuntimeError("orc_brisk48_extract failed (%d)" % rc)
     return kps[:n.value], desc[:n.value], size[:n.value], nd.value
+
+
+# ---- the remaining FeatureMatcher searches (rows a19 / a20) on arrays --------------------------------------------------
+def search_by_projection_ex(desc_type, qdesc, qxy, qr, qmin, qmax, tk, td, tsize, bounds, qangle=None, tinf1d=None, occupied=None,
+                            claim=True, th=75.0, nnratio=0.8, ratio_same_scale=False, tol=1.2):
+    """All projection-type searches after their projection prologue (see orc_search_by_projection_ex)."""
+    qdesc = np.ascontiguousarray(qdesc); td = np.ascontiguousarray(td); tk = np.ascontiguousarray(tk)
+    qxy = np.ascontiguousarray(qxy, np.float32); qr = np.ascontiguousarray(qr, np.float32)
+    qmin = np.ascontiguousarray(qmin, np.float32); qmax = np.ascontiguousarray(qmax, np.float32)
+    tsize = np.ascontiguousarray(tsize, np.float32)
+    qa = None if qangle is None else np.ascontiguousarray(qangle, np.float32)
+    ti = None if tinf1d is None else np.ascontiguousarray(tinf1d, np.float32)
+    occ = None if occupied is None else np.ascontiguousarray(occupied, np.uint8)
+    nq = len(qdesc)
+    out = np.zeros(max(nq, 1), np.int32)
+    minX, minY, maxX, maxY = bounds
+    n = lib().orc_search_by_projection_ex(desc_type, _p(qdesc), _p(qxy), _p(qr), _p(qmin), _p(qmax), None if qa is None else _p(qa), nq,
+                                          _p(tk), _p(td), _p(tsize), None if ti is None else _p(ti), len(tk), None if occ is None else _p(occ),
+                                          int(bool(claim)), _f(minX), _f(minY), _f(maxX), _f(maxY), _f(th), _f(nnratio),
+                                          int(bool(ratio_same_scale)), _f(tol), _p(out))
+    return n, out[:nq].copy()
+
+
+def search_by_sim3(desc_type, k1, d1, size1, q1xy, q1r, q1min, q1max, k2, d2, size2, q2xy, q2r, q2min, q2max, bounds, th_high):
+    """SearchBySim3: direction 1 -> 2 queries are KF1's keypoints (descriptor d1[i], projected to q1xy[i] in KF2), and vice versa."""
+    k1 = np.ascontiguousarray(k1); k2 = np.ascontiguousarray(k2); d1 = np.ascontiguousarray(d1); d2 = np.ascontiguousarray(d2)
+    f = lambda a: np.ascontiguousarray(a, np.float32)
+    size1, q1xy, q1r, q1min, q1max, size2, q2xy, q2r, q2min, q2max = map(f, (size1, q1xy, q1r, q1min, q1max, size2, q2xy, q2r, q2min, q2max))
+    out = np.zeros(max(len(k1), 1), np.int32)
+    minX, minY, maxX, maxY = bounds
+    n = lib().orc_search_by_sim3(desc_type, _p(d1), _p(q1xy), _p(q1r), _p(q1min), _p(q1max), len(k1), _p(d2), _p(q2xy), _p(q2r), _p(q2min), _p(q2max),
+                                 len(k2), _p(k1), _p(d1), _p(size1), _p(k2), _p(d2), _p(size2), _f(minX), _f(minY), _f(maxX), _f(maxY), _f(th_high), _p(out))
+    return n, out[:len(k1)].copy()
+
+
+def bow_match(mode, desc_type, k1, d1, node1, valid1, k2, d2, node2, valid2, th_low=75.0, nnratio=0.7, check_ori=True, F12=None, epipole=(0.0, 0.0),
+              sigma2_2=None):
+    """mode 0 SearchByBoW(KF,F) -> out[i2] = i1; 1 SearchByBoW(KF,KF) -> out[i1] = i2; 2 SearchForTriangulation -> out[i1] = i2."""
+    k1 = np.ascontiguousarray(k1); k2 = np.ascontiguousarray(k2); d1 = np.ascontiguousarray(d1); d2 = np.ascontiguousarray(d2)
+    node1 = np.ascontiguousarray(node1, np.int32); node2 = np.ascontiguousarray(node2, np.int32)
+    v1 = None if valid1 is None else np.ascontiguousarray(valid1, np.uint8); v2 = None if valid2 is None else np.ascontiguousarray(valid2, np.uint8)
+    F = np.zeros(9, np.float32) if F12 is None else np.ascontiguousarray(F12, np.float32).reshape(9)
+    s2 = np.ones(len(k2), np.float32) if sigma2_2 is None else np.ascontiguousarray(sigma2_2, np.float32)
+    nout = len(k2) if mode == 0 else len(k1)
+    out = np.zeros(max(nout, 1), np.int32)
+    n = lib().orc_bow_match(int(mode), desc_type, _p(k1), _p(d1), _p(node1), None if v1 is None else _p(v1), len(k1), _p(k2), _p(d2), _p(node2),
+                            None if v2 is None else _p(v2), len(k2), _f(th_low), _f(nnratio), int(bool(check_ori)), _p(F), _f(epipole[0]),
+                            _f(epipole[1]), _p(s2), _p(out))
+    return n, out[:nout].copy()

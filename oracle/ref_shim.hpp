@@ -14,6 +14,7 @@
 #include <list>
 #include <map>
 #include <memory>
+#include <set>
 #include <string>
 #include <unordered_map>
 #include <vector>
@@ -83,14 +84,24 @@ using KeypointIndex = int;
 enum DescriptorType { DESC_ANYFEATNONBIN = 8, DESC_ANYFEATBIN = 7, DESC_R2D2 = 6, DESC_SIFT128 = 5, DESC_KAZE64 = 4, DESC_SURF64 = 3,
                       DESC_BRISK = 2, DESC_AKAZE61 = 1, DESC_ORB = 0 };
 // the few Eigen fixed-size operations the projection prologue of SearchByProjection (src/FeatureMatcher.cc:1299-1308) uses
-struct vec3f { float v[3] = {0, 0, 0}; float operator()(int i) const { return v[i]; } float& operator()(int i) { return v[i]; } };
+struct vec3f {
+    float v[3] = {0, 0, 0}; float operator()(int i) const { return v[i]; } float& operator()(int i) { return v[i]; }
+    float dot(const vec3f& o) const { return (v[0] * o.v[0] + v[1] * o.v[1]) + v[2] * o.v[2]; }
+    float norm() const { return std::sqrt(dot(*this)); }
+};
 inline vec3f operator+(const vec3f& a, const vec3f& b) { vec3f r; for (int i = 0; i < 3; ++i) r.v[i] = a.v[i] + b.v[i]; return r; }
+inline vec3f operator-(const vec3f& a, const vec3f& b) { vec3f r; for (int i = 0; i < 3; ++i) r.v[i] = a.v[i] - b.v[i]; return r; }
 struct mat3f {
     float m[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
     mat3f transpose() const { mat3f r; for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) r.m[i][j] = m[j][i]; return r; }
     mat3f operator-() const { mat3f r; for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) r.m[i][j] = -m[i][j]; return r; }
     vec3f operator*(const vec3f& x) const { vec3f r; for (int i = 0; i < 3; ++i) r.v[i] = (m[i][0] * x.v[0] + m[i][1] * x.v[1]) + m[i][2] * x.v[2]; return r; }
+    vec3f row(int i) const { vec3f r; for (int j = 0; j < 3; ++j) r.v[j] = m[i][j]; return r; }
+    float operator()(int i, int j) const { return m[i][j]; }
+    mat3f operator/(float s) const { mat3f r; for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) r.m[i][j] = m[i][j] / s; return r; }
 };
+inline mat3f operator*(float s, const mat3f& a) { mat3f r; for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) r.m[i][j] = s * a.m[i][j]; return r; }
+inline mat3f operator*(double s, const mat3f& a) { mat3f r; for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) r.m[i][j] = (float)(s * a.m[i][j]); return r; }
 template <int R, int C> struct blk_t { typedef mat3f type; };
 template <> struct blk_t<3, 1> { typedef vec3f type; };
 struct mat4f {
@@ -100,8 +111,20 @@ struct mat4f {
 template <> inline mat3f mat4f::block<3, 3>(int r, int c) const { mat3f o; for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) o.m[i][j] = m[r + i][c + j]; return o; }
 template <> inline vec3f mat4f::block<3, 1>(int r, int c) const { vec3f o; for (int i = 0; i < 3; ++i) o.v[i] = m[r + i][c]; return o; }
 
-struct MapPoint {                                // include/MapPoint.h: the members SearchByProjection (src/FeatureMatcher.cc:73-154) touches
+class KeyFrame;
+struct MapPoint {                                // include/MapPoint.h: the members the extracted FeatureMatcher bodies touch
     bool mbTrackInView = true, bad = false;
+    // Fuse / Sim3 / relocalisation searches: invariance range, normal, predicted size, bookkeeping the bodies call
+    float minDist = 0.0f, maxDist = 3.0e38f; vec3f normal; bool inKF = false; int idxInKF2 = -1;
+    MapPoint* replacedBy = nullptr; int addedObsIdx = -1;
+    float GetMaxDistanceInvariance() const { return maxDist; }
+    float GetMinDistanceInvariance() const { return minDist; }
+    vec3f GetNormal() const { return normal; }
+    float PredictSize(const float&) const { return trackSize; }
+    bool IsInKeyFrame(const std::shared_ptr<KeyFrame>&) const { return inKF; }
+    int GetIndexInKeyFrame(const std::shared_ptr<KeyFrame>&) const { return idxInKF2; }
+    void Replace(const std::shared_ptr<MapPoint>& p) { replacedBy = p.get(); bad = true; }
+    void AddObservation(const std::shared_ptr<KeyFrame>&, size_t idx) { addedObsIdx = (int)idx; idxInKF2 = (int)idx; nobs++; }
     float trackSize = 1, trackViewCos = 1, mTrackProjX = 0, mTrackProjY = 0, mTrackProjXR = 0, trackSigma = 1;
     cv::Mat desc; int nobs = 1;
     vec3f worldPos;
@@ -151,13 +174,32 @@ public:
     bool PosInGrid(const cv::KeyPoint& kp, int& posX, int& posY);
 };
 
-class KeyFrame {                                // include/KeyFrame.h: what SearchByBoW(KF, F) reads
+class KeyFrame {                                // include/KeyFrame.h: what the extracted FeatureMatcher bodies read / call
 public:
     std::vector<Pt> mappoints;
     std::vector<Pt> GetMapPointMatches() { return mappoints; }
+    Pt GetMapPoint(const size_t& idx) { return mappoints[idx]; }
+    std::set<Pt> GetMapPoints() { std::set<Pt> s; for (auto& p : mappoints) if (p && !p->isBad()) s.insert(p); return s; }
+    void AddMapPoint(Pt pMP, const size_t& idx) { mappoints[idx] = pMP; }
     DBoW2::FeatureVector mFeatVec;
     cv::Mat mDescriptors;
     std::vector<cv::KeyPoint> mvKeysUn;
+    int N = 0;
+    float fx = 1, fy = 1, cx = 0, cy = 0, mbf = 0;
+    std::vector<float> mvuRight, keyPtsSize, sigma2_1d, inf_1d;
+    float sizeTolerance{};
+    mat3f Rcw; vec3f tcw, Ow;
+    mat3f GetRotation() { return Rcw; }
+    vec3f GetTranslation() { return tcw; }
+    vec3f GetCameraCenter() { return Ow; }
+    float GetKeyPtSize(const KeypointIndex& i) const { return keyPtsSize[i]; }
+    float GetKeyPt1DSigma2(const KeypointIndex& i) const { return sigma2_1d[i]; }
+    float GetKeyPt1DInf(const KeypointIndex& i) const { return inf_1d[i]; }
+    float mnMinX = 0, mnMinY = 0, mnMaxX = 0, mnMaxY = 0, mfGridElementWidthInv = 0, mfGridElementHeightInv = 0;
+    int mnGridCols = FRAME_GRID_COLS, mnGridRows = FRAME_GRID_ROWS;
+    std::vector<std::vector<std::vector<size_t>>> mGrid;
+    vector<size_t> GetFeaturesInArea(const float& x, const float& y, const float& r) const;
+    bool IsInImage(const float& x, const float& y) const;
 };
 typedef std::shared_ptr<KeyFrame> Keyframe;
 
@@ -170,9 +212,18 @@ public:
     int SearchByProjection(Frame& F, const vector<Pt>& vpMapPoints, const float& radiusTh);
     int SearchByBoW(Keyframe pKF, Frame& F, vector<Pt>& vpMapPointMatches);
     int SearchByProjection(Frame& CurrentFrame, const Frame& LastFrame, const float& radiusTh, const bool bMono);
+    int SearchByProjection(Frame& CurrentFrame, Keyframe pKF, const std::set<Pt>& sAlreadyFound, const float& radiusTh, const bool& useHighMatchingThreshold);
+    int SearchByProjection(Keyframe pKF, const mat4f& Scw, const std::vector<Pt>& vpPoints, std::vector<Pt>& vpMatched, const float& radiusTh);
+    int SearchByBoW(Keyframe pKF1, Keyframe pKF2, std::vector<Pt>& vpMatches12);
+    int SearchForTriangulation(Keyframe pKF1, Keyframe pKF2, const mat3f& F12, std::vector<pair<size_t, size_t>>& vMatchedPairs, const bool bOnlyStereo,
+                               const DescriptorType& descriptorType);
+    int SearchBySim3(Keyframe pKF1, Keyframe pKF2, std::vector<Pt>& vpMatches12, const float& s12, const mat3f& R12, const vec3f& t12, const float& radiusTh);
+    int Fuse(Keyframe pKF, const vector<Pt>& vpMapPoints, const float& radiusTh);
+    int Fuse(Keyframe pKF, const mat4f& Scw, const std::vector<Pt>& vpPoints, const float& radiusTh, vector<Pt>& vpReplacePoint);
+    bool CheckDistEpipolarLine(const cv::KeyPoint& kp1, const cv::KeyPoint& kp2, const mat3f& F12, const Keyframe pKF, const float& sigma2_kp2);
     float RadiusByViewingCos(const float& viewCos);
     static float radiusScale;
-    static Descriptor_Distance_Type TH_LOW, TH_HIGH;
+    static Descriptor_Distance_Type TH_LOW, TH_HIGH, descDistTh_high_reloc, descDistTh_low_reloc;
     static const int HISTO_LENGTH;
     vector<vector<int>> initRotationHistogram(float& rotFactor, const int& histLength);
     void updateRotationHistogram(vector<vector<int>>& rotHist, const KeypointIndex& idx, const cv::KeyPoint& keyPt, const cv::KeyPoint& refKeyPt,

@@ -432,3 +432,165 @@ def test_orb32_pipeline_from_real_parts(ref, synth, golden_dir):
         for f in rk.dtype.names:
             assert (ok[:m][f] == rk[f]).all(), (stream, f)
         assert (od[:m] == rd).all() and (osz[:m] == rs).all()
+
+
+# ---- rows a19 / a20: the remaining FeatureMatcher searches, oracle restatement == the reference's own compiled bodies ----------
+def _two_frames(synth, feature, stream=12):
+    frames, offs = synth.stream_frames(640, 480, stream, 2)
+    if feature == "orb32":
+        ex = lambda im: po.orb32_extract(im, 1000)[:3]; cfg = (0, 32, 0, 75.0, np.float32(1.2))
+    elif feature == "akaze61":
+        ex = lambda im: po.akaze61_extract(im, 1000)[:3]; cfg = (1, 61, 0, 128.0, np.float32(1.1892))
+    else:
+        ex = lambda im: po.brisk48_extract(im, 1000)[:3]; cfg = (2, 48, 0, 120.0, np.float32(1.5))
+    return ex(frames[0]), ex(frames[1]), (offs[1] - offs[0]).astype(np.float32), cfg
+
+
+def _proj_queries(k0, s0, shift, tol, rng, radius_th, skip_frac=0.1):
+    nq = len(k0)
+    qxy = np.stack([k0["x"] - shift[0], k0["y"] - shift[1]], axis=1).astype(np.float32) + rng.normal(0, 1.5, (nq, 2)).astype(np.float32)
+    qxy = np.clip(qxy, 1.0, [638.0, 478.0]).astype(np.float32)       # the prologue's IsInImage test passes for every query
+    qsize = s0.astype(np.float32)
+    qskip = (rng.random(nq) < skip_frac).astype(np.uint8)
+    qr = ((np.float32(1.0) * np.float32(radius_th)) * qsize).astype(np.float32)       # radiusScale * radiusTh * predictedSize
+    qr_o = np.where(qskip > 0, np.float32(-1.0), qr).astype(np.float32)
+    return qxy, qsize, qskip, qr_o, (qsize / tol).astype(np.float32), (qsize * tol).astype(np.float32)
+
+
+@pytest.mark.parametrize("feature", ["orb32", "brisk48"])
+def test_search_by_projection_sim3_vs_reference_code(ref, synth, feature):
+    """SearchByProjection(pKF, Scw, vpPoints, vpMatched, th) (src/FeatureMatcher.cc:287-397)."""
+    (k0, d0, s0), (k1, d1, s1), shift, (dt, dcols, dtype, th, tol) = _two_frames(synth, feature)
+    rng = np.random.default_rng(11)
+    qxy, qsize, qskip, qr, qmin, qmax = _proj_queries(k0, s0, shift, tol, rng, 4.0)
+    occupied = (rng.random(len(k1)) < 0.2).astype(np.uint8)
+    n_o, m_o = po.search_by_projection_ex(dt, d0, qxy, qr, qmin, qmax, k1, d1, s1, (0.0, 0.0, 640.0, 480.0), occupied=occupied, claim=True,
+                                          th=th, ratio_same_scale=False, tol=float(tol))
+    m_r = np.zeros(len(k0), np.int32)
+    d0c = np.ascontiguousarray(d0); d1c = np.ascontiguousarray(d1)
+    n_r = ref.ref_search_by_projection_sim3(dt, dcols, dtype, _p(d0c), _p(qxy), _p(qsize), _p(qskip), len(k0), _p(_kp7(k1)), _p(d1c),
+                                            _p(np.ascontiguousarray(s1)), len(k1), _p(occupied), C.c_float(0.0), C.c_float(0.0), C.c_float(640.0),
+                                            C.c_float(480.0), C.c_float(4.0), C.c_float(tol), C.c_float(th), _p(m_r))
+    assert n_o == n_r and n_r > 100, (feature, n_o, n_r)
+    assert (m_o == m_r).all()
+
+
+@pytest.mark.parametrize("feature,check_ori", [("orb32", True), ("orb32", False), ("akaze61", True)])
+def test_search_by_projection_reloc_vs_reference_code(ref, synth, feature, check_ori):
+    """SearchByProjection(CurrentFrame, pKF, sAlreadyFound, th, useHigh) (:1406-1506): orientation histogram on train indices."""
+    (k0, d0, s0), (k1, d1, s1), shift, (dt, dcols, dtype, th, tol) = _two_frames(synth, feature, stream=14)
+    rng = np.random.default_rng(12)
+    qxy, qsize, qskip, qr, qmin, qmax = _proj_queries(k0, s0, shift, tol, rng, 3.0)
+    qangle = k0["angle"].astype(np.float32).copy()
+    qangle[rng.random(len(k0)) < 0.3] += np.float32(95.0)              # a third of the matches land in other histogram bins
+    qangle = np.mod(qangle, np.float32(360.0)).astype(np.float32)
+    occupied = (rng.random(len(k1)) < 0.1).astype(np.uint8)
+    n_o, m_o = po.search_by_projection_ex(dt, d0, qxy, qr, qmin, qmax, k1, d1, s1, (0.0, 0.0, 640.0, 480.0), qangle=qangle if check_ori else None,
+                                          occupied=occupied, claim=True, th=th, ratio_same_scale=False, tol=float(tol))
+    m_r = np.zeros(len(k0), np.int32)
+    d0c = np.ascontiguousarray(d0); d1c = np.ascontiguousarray(d1)
+    n_r = ref.ref_search_by_projection_reloc(dt, dcols, dtype, _p(d0c), _p(qxy), _p(qsize), _p(qangle), _p(qskip), len(k0), _p(_kp7(k1)), _p(d1c),
+                                             _p(np.ascontiguousarray(s1)), len(k1), _p(occupied), C.c_float(0.0), C.c_float(0.0), C.c_float(640.0),
+                                             C.c_float(480.0), C.c_float(3.0), C.c_float(tol), C.c_float(th), int(check_ori), _p(m_r))
+    assert n_o == n_r and n_r > 100, (feature, n_o, n_r)
+    assert (m_o == m_r).all()
+
+
+@pytest.mark.parametrize("variant,feature", [(1, "orb32"), (2, "orb32"), (1, "akaze61"), (2, "brisk48")])
+def test_fuse_vs_reference_code(ref, synth, variant, feature):
+    """Fuse(pKF, vpMapPoints, th) (:794-942, monocular reprojection gate e2 * inf > 5.99) and Fuse(pKF, Scw, ...) (:944-1064):
+    the search is stateless (no occupied test, no claim); the keypoint each map point lands on is compared."""
+    (k0, d0, s0), (k1, d1, s1), shift, (dt, dcols, dtype, th, tol) = _two_frames(synth, feature, stream=15)
+    rng = np.random.default_rng(13)
+    qxy, qsize, qskip, qr, qmin, qmax = _proj_queries(k0, s0, shift, tol, rng, 3.0)
+    has_mp = (rng.random(len(k1)) < 0.5).astype(np.uint8)
+    inf1d = (np.float32(1.0) / (s1.astype(np.float32) ** 2)).astype(np.float32)            # GetKeyPt1DInf: 1 / size^2 (computeSigma)
+    n_o, m_o = po.search_by_projection_ex(dt, d0, qxy, qr, qmin, qmax, k1, d1, s1, (0.0, 0.0, 640.0, 480.0), tinf1d=inf1d if variant == 1 else None,
+                                          occupied=None, claim=False, th=th, ratio_same_scale=False, tol=float(tol))
+    m_r = np.zeros(len(k0), np.int32)
+    d0c = np.ascontiguousarray(d0); d1c = np.ascontiguousarray(d1)
+    n_r = ref.ref_fuse(variant, dt, dcols, dtype, _p(d0c), _p(qxy), _p(qsize), _p(qskip), len(k0), _p(_kp7(k1)), _p(d1c), _p(np.ascontiguousarray(s1)),
+                       _p(inf1d), len(k1), _p(has_mp), C.c_float(0.0), C.c_float(0.0), C.c_float(640.0), C.c_float(480.0), C.c_float(3.0),
+                       C.c_float(tol), C.c_float(th), _p(m_r))
+    assert n_o == n_r and n_r > 100, (variant, feature, n_o, n_r)
+    assert (m_o == m_r).all()
+    if variant == 1:                                                  # the gate really removes candidates
+        n_nogate, _ = po.search_by_projection_ex(dt, d0, qxy, qr, qmin, qmax, k1, d1, s1, (0.0, 0.0, 640.0, 480.0), claim=False, th=th, tol=float(tol))
+        assert n_nogate > n_o
+
+
+@pytest.mark.parametrize("feature", ["orb32", "akaze61"])
+def test_search_by_sim3_vs_reference_code(ref, synth, feature):
+    """SearchBySim3 (:1066-1287): two directed best-only searches with TH_HIGH + agreement."""
+    (k0, d0, s0), (k1, d1, s1), shift, (dt, dcols, dtype, th, tol) = _two_frames(synth, feature, stream=16)
+    rng = np.random.default_rng(14)
+    q1xy, q1size, q1skip, q1r, q1min, q1max = _proj_queries(k0, s0, shift, tol, rng, 3.0, skip_frac=0.3)
+    q2xy, q2size, q2skip, q2r, q2min, q2max = _proj_queries(k1, s1, -shift, tol, rng, 3.0, skip_frac=0.3)
+    n_o, m_o = po.search_by_sim3(dt, k0, d0, s0, q1xy, q1r, q1min, q1max, k1, d1, s1, q2xy, q2r, q2min, q2max, (0.0, 0.0, 640.0, 480.0), th)
+    m_r = np.zeros(len(k0), np.int32)
+    d0c = np.ascontiguousarray(d0); d1c = np.ascontiguousarray(d1)
+    n_r = ref.ref_search_by_sim3(dt, dcols, dtype, _p(_kp7(k0)), _p(d0c), _p(np.ascontiguousarray(s0)), _p(q1xy), _p(q1size), _p(q1skip), len(k0),
+                                 _p(_kp7(k1)), _p(d1c), _p(np.ascontiguousarray(s1)), _p(q2xy), _p(q2size), _p(q2skip), len(k1),
+                                 C.c_float(0.0), C.c_float(0.0), C.c_float(640.0), C.c_float(480.0), C.c_float(3.0), C.c_float(tol), C.c_float(th), _p(m_r))
+    assert n_o == n_r and n_r > 50, (feature, n_o, n_r)
+    assert (m_o == m_r).all()
+
+
+def _nodes(k, shift, rng, drop=0.05):
+    node = ((k["x"] + shift[0]) // 80).astype(np.int32) * 10 + ((k["y"] + shift[1]) // 80).astype(np.int32)
+    node[rng.random(len(k)) < drop] = -1                              # features outside the FeatureVector
+    return node.astype(np.int32)
+
+
+@pytest.mark.parametrize("feature,check_ori", [("orb32", True), ("orb32", False), ("brisk48", True)])
+def test_search_by_bow_kfkf_vs_reference_code(ref, synth, feature, check_ori):
+    """SearchByBoW(pKF1, pKF2, vpMatches12) (:561-660): strict < TH_LOW, vbMatched2, map-point gates on both sides."""
+    (k0, d0, s0), (k1, d1, s1), shift, (dt, dcols, dtype, th, tol) = _two_frames(synth, feature, stream=17)
+    rng = np.random.default_rng(15)
+    n1, n2 = _nodes(k0, (0, 0), rng), _nodes(k1, shift, rng)
+    v1 = (rng.random(len(k0)) < 0.8).astype(np.uint8); v2 = (rng.random(len(k1)) < 0.8).astype(np.uint8)
+    for nnratio in (0.75, 0.9):
+        n_o, m_o = po.bow_match(1, dt, k0, d0, n1, v1, k1, d1, n2, v2, th_low=th, nnratio=nnratio, check_ori=check_ori)
+        m_r = np.zeros(len(k0), np.int32)
+        d0c = np.ascontiguousarray(d0); d1c = np.ascontiguousarray(d1)
+        n_r = ref.ref_search_by_bow_kfkf(dt, dcols, dtype, _p(_kp7(k0)), _p(d0c), _p(n1), _p(v1), len(k0), _p(_kp7(k1)), _p(d1c), _p(n2), _p(v2), len(k1),
+                                         C.c_float(th), C.c_float(nnratio), int(check_ori), _p(m_r))
+        assert n_o == n_r and n_r > 50, (feature, n_o, n_r)
+        assert (m_o == m_r).all()
+    # mode 0 of the same routine == the (KF, F) restatement that is already pinned to the reference's SearchByBoW(KF, F)
+    node_a, node_b = _nodes(k0, (0, 0), rng, 0.0), _nodes(k1, shift, rng, 0.0)
+
+    def segs(node):
+        order = np.argsort(node, kind="stable"); ids, starts = np.unique(node[order], return_index=True)
+        return ids.astype(np.int32), np.append(starts, len(node)).astype(np.int32), order.astype(np.int32)
+    n_a, mf_a = po.search_by_bow(dt, d0, k0, segs(node_a), d1, k1, segs(node_b), th_low=th, nnratio=0.7, check_ori=check_ori)
+    n_b, mf_b = po.bow_match(0, dt, k0, d0, node_a, None, k1, d1, node_b, None, th_low=th, nnratio=0.7, check_ori=check_ori)
+    assert n_a == n_b and (mf_a == mf_b).all()
+
+
+@pytest.mark.parametrize("feature", ["orb32", "akaze61"])
+def test_search_for_triangulation_vs_reference_code(ref, synth, feature):
+    """SearchForTriangulation (:662-790) incl. CheckDistEpipolarLine (:165-183) for a pure image translation: F12 = [t]x."""
+    (k0, d0, s0), (k1, d1, s1), shift, (dt, dcols, dtype, th, tol) = _two_frames(synth, feature, stream=18)
+    rng = np.random.default_rng(16)
+    n1, n2 = _nodes(k0, (0, 0), rng), _nodes(k1, shift, rng)
+    h1 = (rng.random(len(k0)) < 0.3).astype(np.uint8); h2 = (rng.random(len(k1)) < 0.3).astype(np.uint8)
+    # frame 1 = frame 0 shifted by `shift` pixels: x2 = x1 - shift; epipolar lines are parallel to the shift direction:
+    # l = F12^T-style product of the reference (a = x F00 + y F10 + F20, ...) with F = [[0, 0, ty], [0, 0, -tx], [-ty, tx, 0]]
+    tx, ty = float(-shift[0]), float(-shift[1])
+    F12 = np.array([[0, 0, ty], [0, 0, -tx], [-ty, tx, 0]], np.float32)
+    F12 = F12 / np.float32(max(1.0, np.hypot(tx, ty)))
+    sigma2 = (s1.astype(np.float32) ** 2).astype(np.float32)
+    epi = (-500.0, 240.0)
+    n_o, m_o = po.bow_match(2, dt, k0, d0, n1, h1, k1, d1, n2, h2, th_low=th, F12=F12, epipole=epi, sigma2_2=sigma2)
+    m_r = np.zeros(len(k0), np.int32)
+    d0c = np.ascontiguousarray(d0); d1c = np.ascontiguousarray(d1)
+    n_r = ref.ref_search_for_triangulation(dt, dcols, dtype, _p(_kp7(k0)), _p(d0c), _p(n1), _p(h1), len(k0), _p(_kp7(k1)), _p(d1c), _p(n2), _p(h2),
+                                           _p(sigma2), len(k1), _p(np.ascontiguousarray(F12.reshape(9))), C.c_float(epi[0]), C.c_float(epi[1]),
+                                           C.c_float(th), _p(m_r))
+    assert n_o == n_r and n_r > 50, (feature, n_o, n_r)
+    assert (m_o == m_r).all()
+    # an epipole inside the image suppresses the candidates around it (:744-751)
+    n_in, m_in = po.bow_match(2, dt, k0, d0, n1, h1, k1, d1, n2, h2, th_low=th, F12=F12, epipole=(320.0, 240.0), sigma2_2=sigma2)
+    near = (np.hypot(k1["x"] - 320.0, k1["y"] - 240.0) ** 2 < 100.0 * s1)
+    assert n_in <= n_o and not near[m_in[m_in >= 0]].any()
