@@ -10,6 +10,7 @@
 //   * loops whose iterations depend on earlier ones ("already matched", match stealing) stay sequential over
 //     queries inside one CTA per frame pair, with all candidate work of a query done in parallel.
 #include "afv_common.cuh"
+#include <atomic>
 #include <float.h>
 
 #define NCELLS (AFV_GRID_COLS * AFV_GRID_ROWS)
@@ -676,24 +677,19 @@ extern "C" int afv_search_for_initialization(int desc_type, const afv_keypoint* 
     const size_t smemA = baseA + (stage ? (size_t)cap * Dpad : 0);
     const size_t smemB = sfr_cta_bytes(cap);
     if (smemA > 220 * 1024 || smemB > 220 * 1024) { afv_set_error("cap %d too large for the shared-memory staging", cap); return AFV_ERR_INVALID; }
-    static size_t confA[2] = {0, 0}, confB[2] = {0, 0};
-    if (smemA > confA[binary]) {
-        AFV_CUDA_CHECK(binary ? cudaFuncSetAttribute(k_sfi_lists<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemA)
-                              : cudaFuncSetAttribute(k_sfi_lists<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemA));
-        confA[binary] = smemA;
-    }
-    if (smemB > confB[binary]) {
-        AFV_CUDA_CHECK(binary ? cudaFuncSetAttribute(k_sfi_resolve<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemB)
-                              : cudaFuncSetAttribute(k_sfi_resolve<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemB));
-        confB[binary] = smemB;
-    }
-    static bool pool_cfg = false;
-    if (!pool_cfg) {        // keep freed scratch cached in the stream-ordered pool instead of returning it to the OS
+    // the opt-in shared-memory size is a per-device function attribute: set on every call (cheap, idempotent, thread-safe)
+    AFV_CUDA_CHECK(binary ? cudaFuncSetAttribute(k_sfi_lists<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemA)
+                          : cudaFuncSetAttribute(k_sfi_lists<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemA));
+    AFV_CUDA_CHECK(binary ? cudaFuncSetAttribute(k_sfi_resolve<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemB)
+                          : cudaFuncSetAttribute(k_sfi_resolve<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemB));
+    {       // keep freed scratch cached in the stream-ordered pool of THIS device instead of returning it to the OS (once per device)
+        static std::atomic<unsigned long long> pool_cfg_mask{0};
         int dev = 0; cudaMemPool_t mp;
-        if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetDefaultMemPool(&mp, dev) == cudaSuccess) {
+        if (cudaGetDevice(&dev) == cudaSuccess && dev >= 0 && dev < 64 && !(pool_cfg_mask.load() & (1ull << dev)) &&
+            cudaDeviceGetDefaultMemPool(&mp, dev) == cudaSuccess) {
             unsigned long long thr = ~0ull; cudaMemPoolSetAttribute(mp, cudaMemPoolAttrReleaseThreshold, &thr);
+            pool_cfg_mask.fetch_or(1ull << dev);
         }
-        pool_cfg = true;
     }
     // candidate pool: entries per pair (u32 for Hamming: dist<<20 | index; u64 for L2: float bits<<32 | index)
     const int pool_cap = 64 * 1024;
@@ -744,11 +740,12 @@ __global__ void __launch_bounds__(SFL_THREADS) k_proj_lists(int desc_type, int D
         const uint8_t* __restrict__ qdesc, const float* __restrict__ qxy, const float* __restrict__ qr,
         const float* __restrict__ qmin, const float* __restrict__ qmax, const int* __restrict__ q_start,
         const afv_keypoint* __restrict__ kps, const uint8_t* __restrict__ desc, const float* __restrict__ kpsize,
-        const int* __restrict__ n_arr, int cap, const int* __restrict__ frame,
+        const int* __restrict__ n_arr, int cap, const int* __restrict__ frame, const float* __restrict__ tinf1d,
         float minX, float minY, float invW, float invH, void* __restrict__ pool_v, int pool_cap, ProjQMeta* __restrict__ qmeta) {
     extern __shared__ __align__(16) unsigned char sm[];
     const int p = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int fb = frame[p];
+    const float* inf2 = tinf1d ? tinf1d + (long long)fb * cap : nullptr;
     const int n2 = min(n_arr[fb], cap);
     const afv_keypoint* k2 = kps + (long long)fb * cap;
     const uint8_t* d2 = desc + (long long)fb * cap * D;
@@ -805,14 +802,20 @@ __global__ void __launch_bounds__(SFL_THREADS) k_proj_lists(int desc_type, int D
         SfiQuery q;
         q.x = qxy[2 * qi]; q.y = qxy[2 * qi + 1];
         const float r = qr[qi], smin = qmin[qi], smax = qmax[qi];
-        q.ok = window_cells(q.x, q.y, r, minX, minY, invW, invH, q.c0, q.c1, q.r0, q.r1);
+        q.ok = !(r < 0.0f) && window_cells(q.x, q.y, r, minX, minY, invW, invH, q.c0, q.c1, q.r0, q.r1);   // r < 0: query skipped by the caller's prologue
         int cnt = 0, off = 0;
         if (q.ok) {
             const int s0 = colstart[q.c0], s1 = colstart[q.c1 + 1];
             auto is_cand = [&](int sl) {
                 const unsigned short cc = scell[sl];
                 const float sz = ssz[sl];
-                return !(sz < smin) && !(sz > smax) && sfi_in_window(q, cc >> 8, cc & 0xff, sx[sl], sy[sl], r);
+                if (!(!(sz < smin) && !(sz > smax) && sfi_in_window(q, cc >> 8, cc & 0xff, sx[sl], sy[sl], r))) return false;
+                if (inf2) {                                      // Fuse, monocular reprojection gate (src/FeatureMatcher.cc:905-915)
+                    const float ex = __fsub_rn(q.x, sx[sl]), ey = __fsub_rn(q.y, sy[sl]);
+                    const float e2 = __fadd_rn(__fmul_rn(ex, ex), __fmul_rn(ey, ey));
+                    if ((double)__fmul_rn(e2, inf2[sorig[sl]]) > 5.99) return false;
+                }
+                return true;
             };
             for (int sb = s0; sb < s1; sb += 32) {
                 const int sl = sb + lane;
@@ -870,10 +873,13 @@ __global__ void __launch_bounds__(SFR_WARPS * 32) k_proj_resolve(int desc_type, 
         const float* __restrict__ qmin, const float* __restrict__ qmax, const int* __restrict__ q_start, int P,
         const afv_keypoint* __restrict__ kps, const uint8_t* __restrict__ desc, const float* __restrict__ kpsize,
         const int* __restrict__ n_arr, int cap, const int* __restrict__ frame, const uint8_t* __restrict__ occupied_in,
+        const float* __restrict__ tinf1d, const float* __restrict__ qangle, int claim,
         float minX, float minY, float invW, float invH, float th, float nnratio, int ratio_same_scale, float tol,
-        const void* __restrict__ pool_v, int pool_cap, const ProjQMeta* __restrict__ qmeta,
+        const void* __restrict__ pool_v, int pool_cap, ProjQMeta* __restrict__ qmeta,
         int* __restrict__ match_q, int* __restrict__ nmatches) {
     extern __shared__ __align__(16) unsigned char sm[];
+    __shared__ int s_hist[SFR_WARPS][32];
+    __shared__ int s_keep[SFR_WARPS][3];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int p = blockIdx.x * SFR_WARPS + wid;
     if (p >= P) return;
@@ -893,8 +899,10 @@ __global__ void __launch_bounds__(SFR_WARPS * 32) k_proj_resolve(int desc_type, 
         tcell[i] = c >= 0 ? (unsigned short)(((c / AFV_GRID_ROWS) << 8) | (c % AFV_GRID_ROWS)) : NONE16;
         occ[i] = occupied_in ? occupied_in[(long long)fb * cap + i] : 0;
     }
+    s_hist[wid][lane] = 0;
     __syncwarp();
     const float invtol = __fdiv_rn(1.0f, tol);
+    const float* inf2 = tinf1d ? tinf1d + (long long)fb * cap : nullptr;
     int nm = 0;
     const int q0 = q_start[p], q1 = q_start[p + 1];
     for (int qi = q0; qi < q1; ++qi) {
@@ -921,11 +929,15 @@ __global__ void __launch_bounds__(SFR_WARPS * 32) k_proj_resolve(int desc_type, 
                 SfiQuery w;
                 w.x = qxy[2 * qi]; w.y = qxy[2 * qi + 1];
                 const float r = qr[qi], smin = qmin[qi], smax = qmax[qi];
-                w.ok = window_cells(w.x, w.y, r, minX, minY, invW, invH, w.c0, w.c1, w.r0, w.r1);
+                w.ok = !(r < 0.0f) && window_cells(w.x, w.y, r, minX, minY, invW, invH, w.c0, w.c1, w.r0, w.r1);
                 for (int i2 = lane; w.ok && i2 < n2; i2 += 32) {
                     const unsigned short cc = tcell[i2];
                     if (cc == NONE16 || occ[i2] || tsize[i2] < smin || tsize[i2] > smax) continue;
                     if (!sfi_in_window(w, cc >> 8, cc & 0xff, k2[i2].x, k2[i2].y, r)) continue;
+                    if (inf2) {
+                        const float ex = __fsub_rn(w.x, k2[i2].x), ey = __fsub_rn(w.y, k2[i2].y);
+                        if ((double)__fmul_rn(__fadd_rn(__fmul_rn(ex, ex), __fmul_rn(ey, ey)), inf2[i2]) > 5.99) continue;
+                    }
                     const float dist = desc_distance(desc_type, qdesc + (long long)qi * D, d2 + (long long)i2 * D, D);
                     top2_push(t, make_key(dist, ((uint32_t)(cc >> 8) << 26) | ((uint32_t)(cc & 0xff) << 20) | (uint32_t)i2));
                 }
@@ -947,18 +959,48 @@ __global__ void __launch_bounds__(SFR_WARPS * 32) k_proj_resolve(int desc_type, 
                 }
             }
         }
-        if (bestIdx >= 0) { if (lane == 0) occ[bestIdx] = 1; ++nm; }
+        if (bestIdx >= 0) {
+            ++nm;
+            if (lane == 0) {
+                if (claim) occ[bestIdx] = 1;
+                if (qangle) {                                    // updateRotationHistogram(rotHist, bestIdx, query keypoint, train keypoint)
+                    const int bin = rot_bin(qangle[qi], k2[bestIdx].angle);
+                    s_hist[wid][bin]++; qmeta[qi].off = bin;     // the list offset of this query is not needed any more
+                }
+            }
+        }
         if (lane == 0) match_q[qi] = bestIdx;
         __syncwarp();
+    }
+    if (qangle) {                                                // filterMatchesWithOrientation (:1601-1612)
+        if (lane == 0) three_maxima(s_hist[wid], s_keep[wid][0], s_keep[wid][1], s_keep[wid][2]);
+        __syncwarp();
+        int removed = 0;
+        for (int qi = q0 + lane; qi < q1; qi += 32) {
+            if (match_q[qi] < 0) continue;
+            const int bn = qmeta[qi].off;
+            if (bn == s_keep[wid][0] || bn == s_keep[wid][1] || bn == s_keep[wid][2]) continue;
+            match_q[qi] = -1; ++removed;
+        }
+#pragma unroll
+        for (int o = 16; o; o >>= 1) removed += __shfl_xor_sync(0xffffffffu, removed, o);
+        nm -= removed;
     }
     if (lane == 0) nmatches[p] = nm;
 }
 
-extern "C" int afv_search_by_projection(int desc_type, const void* d_qdesc, const float* d_qxy, const float* d_qr,
-        const float* d_qmin_size, const float* d_qmax_size, const int* d_q_start, int P,
-        const afv_keypoint* d_kps, const void* d_desc, const float* d_kpsize, const int* d_n, int B, int cap, const int* d_frame,
-        const uint8_t* d_occupied, float min_x, float min_y, float max_x, float max_y, float th, float nnratio,
-        int ratio_same_scale_only, float size_tolerance, int* d_match_q, int* d_nmatches, void* cuda_stream) {
+static const int PROJ_POOL_CAP = 64 * 1024;
+extern "C" size_t afv_search_by_projection_workspace_bytes(int desc_type, int P, int nq_total) {
+    const size_t esz = desc_type != AFV_FEAT_SIFT128 ? 4 : 8;
+    return (size_t)(P > 0 ? P : 0) * PROJ_POOL_CAP * esz + (size_t)(nq_total > 0 ? nq_total : 0) * sizeof(ProjQMeta) + 256;
+}
+
+extern "C" int afv_search_by_projection_ex(int desc_type, const void* d_qdesc, const float* d_qxy, const float* d_qr,
+        const float* d_qmin_size, const float* d_qmax_size, const float* d_qangle, const int* d_q_start, int P, int nq_total,
+        const afv_keypoint* d_kps, const void* d_desc, const float* d_kpsize, const float* d_inf1d, const int* d_n, int B, int cap,
+        const int* d_frame, const uint8_t* d_occupied, int claim, float min_x, float min_y, float max_x, float max_y, float th,
+        float nnratio, int ratio_same_scale_only, float size_tolerance, int* d_match_q, int* d_nmatches,
+        void* d_workspace, size_t workspace_bytes, void* cuda_stream) {
     const int D = desc_bytes(desc_type);
     if (D < 0 || !d_qdesc || !d_qxy || !d_qr || !d_qmin_size || !d_qmax_size || !d_q_start || !d_kps || !d_desc || !d_kpsize || !d_n ||
         !d_frame || !d_match_q || !d_nmatches || B < 1 || P < 0 || cap < 1 || !(size_tolerance > 0.0f)) {
@@ -974,50 +1016,286 @@ extern "C" int afv_search_by_projection(int desc_type, const void* d_qdesc, cons
     const size_t smemA = baseA + (stage ? (size_t)cap * Dpad : 0);
     const size_t smemB = prr_warp_bytes(cap) * SFR_WARPS;
     if (smemA > 220 * 1024 || smemB > 220 * 1024) { afv_set_error("cap %d too large for the shared-memory staging", cap); return AFV_ERR_INVALID; }
-    static size_t confA[2] = {0, 0}, confB[2] = {0, 0};
-    if (smemA > confA[binary]) {
-        AFV_CUDA_CHECK(binary ? cudaFuncSetAttribute(k_proj_lists<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemA)
-                              : cudaFuncSetAttribute(k_proj_lists<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemA));
-        confA[binary] = smemA;
+    // the opt-in shared-memory size is a per-device function attribute: set it on every call (cheap, idempotent, thread-safe)
+    AFV_CUDA_CHECK(binary ? cudaFuncSetAttribute(k_proj_lists<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemA)
+                          : cudaFuncSetAttribute(k_proj_lists<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemA));
+    AFV_CUDA_CHECK(binary ? cudaFuncSetAttribute(k_proj_resolve<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemB)
+                          : cudaFuncSetAttribute(k_proj_resolve<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemB));
+    if (nq_total < 0) {                               // query count unknown to the host: read it back (the only synchronising path)
+        AFV_CUDA_CHECK(cudaMemcpyAsync(&nq_total, d_q_start + P, sizeof(int), cudaMemcpyDeviceToHost, st));
+        AFV_CUDA_CHECK(cudaStreamSynchronize(st));
     }
-    if (smemB > confB[binary]) {
-        AFV_CUDA_CHECK(binary ? cudaFuncSetAttribute(k_proj_resolve<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemB)
-                              : cudaFuncSetAttribute(k_proj_resolve<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemB));
-        confB[binary] = smemB;
-    }
-    int nq_total = 0;
-    AFV_CUDA_CHECK(cudaMemcpyAsync(&nq_total, d_q_start + P, sizeof(int), cudaMemcpyDeviceToHost, st));
-    AFV_CUDA_CHECK(cudaStreamSynchronize(st));
     if (nq_total <= 0) { AFV_CUDA_CHECK(cudaMemsetAsync(d_nmatches, 0, sizeof(int) * P, st)); return AFV_OK; }
-    const int pool_cap = 64 * 1024;
+    const int pool_cap = PROJ_POOL_CAP;
     const size_t esz = binary ? 4 : 8;
-    unsigned char* scratch = nullptr;
-    const size_t pool_bytes = (size_t)P * pool_cap * esz, meta_bytes = (size_t)nq_total * sizeof(ProjQMeta);
-    AFV_CUDA_CHECK(cudaMallocAsync((void**)&scratch, pool_bytes + meta_bytes + 256, st));
+    const size_t pool_bytes = (size_t)P * pool_cap * esz, need = afv_search_by_projection_workspace_bytes(desc_type, P, nq_total);
+    unsigned char* scratch = (unsigned char*)d_workspace;
+    if (scratch && workspace_bytes < need) { afv_set_error("afv_search_by_projection: workspace %zu B < required %zu B", workspace_bytes, need); return AFV_ERR_INVALID; }
+    if (!scratch) AFV_CUDA_CHECK(cudaMallocAsync((void**)&scratch, need, st));
     void* pool = scratch;
     ProjQMeta* qmeta = reinterpret_cast<ProjQMeta*>(scratch + pool_bytes);
     const float invW = (float)AFV_GRID_COLS / (max_x - min_x), invH = (float)AFV_GRID_ROWS / (max_y - min_y);
     {
         AfvProfScope ps("k_proj_lists", st);
         if (binary) k_proj_lists<true><<<P, SFL_THREADS, smemA, st>>>(desc_type, D, Dpad, stage, (const uint8_t*)d_qdesc, d_qxy, d_qr, d_qmin_size, d_qmax_size,
-                d_q_start, d_kps, (const uint8_t*)d_desc, d_kpsize, d_n, cap, d_frame, min_x, min_y, invW, invH, pool, pool_cap, qmeta);
+                d_q_start, d_kps, (const uint8_t*)d_desc, d_kpsize, d_n, cap, d_frame, d_inf1d, min_x, min_y, invW, invH, pool, pool_cap, qmeta);
         else k_proj_lists<false><<<P, SFL_THREADS, smemA, st>>>(desc_type, D, Dpad, stage, (const uint8_t*)d_qdesc, d_qxy, d_qr, d_qmin_size, d_qmax_size,
-                d_q_start, d_kps, (const uint8_t*)d_desc, d_kpsize, d_n, cap, d_frame, min_x, min_y, invW, invH, pool, pool_cap, qmeta);
+                d_q_start, d_kps, (const uint8_t*)d_desc, d_kpsize, d_n, cap, d_frame, d_inf1d, min_x, min_y, invW, invH, pool, pool_cap, qmeta);
         ++g_afv_launches;
     }
     {
         AfvProfScope ps("k_proj_resolve", st);
         const int grid = (P + SFR_WARPS - 1) / SFR_WARPS;
         if (binary) k_proj_resolve<true><<<grid, SFR_WARPS * 32, smemB, st>>>(desc_type, D, (const uint8_t*)d_qdesc, d_qxy, d_qr, d_qmin_size, d_qmax_size, d_q_start, P,
-                d_kps, (const uint8_t*)d_desc, d_kpsize, d_n, cap, d_frame, d_occupied, min_x, min_y, invW, invH, th, nnratio, ratio_same_scale_only,
-                size_tolerance, pool, pool_cap, qmeta, d_match_q, d_nmatches);
+                d_kps, (const uint8_t*)d_desc, d_kpsize, d_n, cap, d_frame, d_occupied, d_inf1d, d_qangle, claim, min_x, min_y, invW, invH, th, nnratio,
+                ratio_same_scale_only, size_tolerance, pool, pool_cap, qmeta, d_match_q, d_nmatches);
         else k_proj_resolve<false><<<grid, SFR_WARPS * 32, smemB, st>>>(desc_type, D, (const uint8_t*)d_qdesc, d_qxy, d_qr, d_qmin_size, d_qmax_size, d_q_start, P,
-                d_kps, (const uint8_t*)d_desc, d_kpsize, d_n, cap, d_frame, d_occupied, min_x, min_y, invW, invH, th, nnratio, ratio_same_scale_only,
-                size_tolerance, pool, pool_cap, qmeta, d_match_q, d_nmatches);
+                d_kps, (const uint8_t*)d_desc, d_kpsize, d_n, cap, d_frame, d_occupied, d_inf1d, d_qangle, claim, min_x, min_y, invW, invH, th, nnratio,
+                ratio_same_scale_only, size_tolerance, pool, pool_cap, qmeta, d_match_q, d_nmatches);
         ++g_afv_launches;
     }
     AFV_CUDA_CHECK(cudaGetLastError());
-    AFV_CUDA_CHECK(cudaFreeAsync(scratch, st));
+    if (!d_workspace) AFV_CUDA_CHECK(cudaFreeAsync(scratch, st));
+    return AFV_OK;
+}
+
+extern "C" int afv_search_by_projection(int desc_type, const void* d_qdesc, const float* d_qxy, const float* d_qr,
+        const float* d_qmin_size, const float* d_qmax_size, const int* d_q_start, int P,
+        const afv_keypoint* d_kps, const void* d_desc, const float* d_kpsize, const int* d_n, int B, int cap, const int* d_frame,
+        const uint8_t* d_occupied, float min_x, float min_y, float max_x, float max_y, float th, float nnratio,
+        int ratio_same_scale_only, float size_tolerance, int* d_match_q, int* d_nmatches, void* cuda_stream) {
+    return afv_search_by_projection_ex(desc_type, d_qdesc, d_qxy, d_qr, d_qmin_size, d_qmax_size, nullptr, d_q_start, P, -1, d_kps, d_desc, d_kpsize,
+                                       nullptr, d_n, B, cap, d_frame, d_occupied, 1, min_x, min_y, max_x, max_y, th, nnratio, ratio_same_scale_only,
+                                       size_tolerance, d_match_q, d_nmatches, nullptr, 0, cuda_stream);
+}
+
+// ---- SearchBySim3 (src/FeatureMatcher.cc:1066-1287): two stateless directed searches + agreement -------------------------
+__global__ void k_sim3_agree(const int* __restrict__ m1, const int* __restrict__ q_start1, const int* __restrict__ m2,
+                             const int* __restrict__ q_start2, int P, int* __restrict__ match12, int* __restrict__ nfound) {
+    const int p = blockIdx.x;
+    if (p >= P) return;
+    __shared__ int s_cnt;
+    if (threadIdx.x == 0) s_cnt = 0;
+    __syncthreads();
+    const int a0 = q_start1[p], a1 = q_start1[p + 1], b0 = q_start2[p], b1 = q_start2[p + 1];
+    int local = 0;
+    for (int i = a0 + threadIdx.x; i < a1; i += blockDim.x) {
+        const int idx2 = m1[i];
+        int out = -1;
+        if (idx2 >= 0 && b0 + idx2 < b1 && m2[b0 + idx2] == i - a0) { out = idx2; ++local; }
+        match12[i] = out;
+    }
+    atomicAdd(&s_cnt, local);
+    __syncthreads();
+    if (threadIdx.x == 0) nfound[p] = s_cnt;
+}
+
+extern "C" int afv_search_by_sim3(int desc_type,
+        const void* d_q1desc, const float* d_q1xy, const float* d_q1r, const float* d_q1min, const float* d_q1max, const int* d_q_start1, int nq1_total,
+        const void* d_q2desc, const float* d_q2xy, const float* d_q2r, const float* d_q2min, const float* d_q2max, const int* d_q_start2, int nq2_total,
+        int P, const afv_keypoint* d_kps, const void* d_desc, const float* d_kpsize, const int* d_n, int B, int cap,
+        const int* d_frame1, const int* d_frame2, float min_x, float min_y, float max_x, float max_y, float th_high,
+        int* d_match12, int* d_nfound, void* cuda_stream) {
+    if (P < 0 || nq1_total < 0 || nq2_total < 0 || !d_match12 || !d_nfound || !d_q_start1 || !d_q_start2) { afv_set_error("afv_search_by_sim3: bad argument"); return AFV_ERR_INVALID; }
+    if (P == 0) return AFV_OK;
+    cudaStream_t st = as_stream(cuda_stream);
+    int* tmp = nullptr;
+    AFV_CUDA_CHECK(cudaMallocAsync((void**)&tmp, sizeof(int) * ((size_t)nq1_total + nq2_total + 2 * (size_t)P + 4), st));
+    int* m1 = tmp; int* m2 = tmp + nq1_total; int* c1 = m2 + nq2_total; int* c2 = c1 + P;
+    // direction 1 -> 2: the map points of frame1's keypoints searched in frame2, and vice versa; no occupied flags, no claims
+    int rc = afv_search_by_projection_ex(desc_type, d_q1desc, d_q1xy, d_q1r, d_q1min, d_q1max, nullptr, d_q_start1, P, nq1_total, d_kps, d_desc, d_kpsize,
+                                         nullptr, d_n, B, cap, d_frame2, nullptr, 0, min_x, min_y, max_x, max_y, th_high, 1.0f, 0, 1.0f, m1, c1, nullptr, 0, cuda_stream);
+    if (rc == AFV_OK)
+        rc = afv_search_by_projection_ex(desc_type, d_q2desc, d_q2xy, d_q2r, d_q2min, d_q2max, nullptr, d_q_start2, P, nq2_total, d_kps, d_desc, d_kpsize,
+                                         nullptr, d_n, B, cap, d_frame1, nullptr, 0, min_x, min_y, max_x, max_y, th_high, 1.0f, 0, 1.0f, m2, c2, nullptr, 0, cuda_stream);
+    if (rc == AFV_OK) {
+        if (nq1_total == 0) AFV_CUDA_CHECK(cudaMemsetAsync(d_nfound, 0, sizeof(int) * P, st));
+        else { k_sim3_agree<<<P, 256, 0, st>>>(m1, d_q_start1, m2, d_q_start2, P, d_match12, d_nfound); ++g_afv_launches; AFV_CUDA_CHECK(cudaGetLastError()); }
+    }
+    AFV_CUDA_CHECK(cudaFreeAsync(tmp, st));
+    return rc;
+}
+
+// ---- BoW merge-join searches on per-feature node ids, batched over frame pairs --------------------------------------------
+// mode 0 SearchByBoW(KF, F) (:186-283), 1 SearchByBoW(KF, KF) (:561-660), 2 SearchForTriangulation (:662-790, monocular).
+// One CTA per pair: both frames' (node, feature) keys are bitonic-sorted in shared memory (= DBoW2's FeatureVector order: nodes
+// ascending, features of a node in increasing index); the sequential "already matched" state of the reference only couples the
+// features of ONE node, so the shared nodes are independent and go to the 8 warps round-robin; inside a node the frame-1
+// features are taken in order and the lanes share the node's frame-2 features.
+#define BOW_THREADS 256
+template <int MODE>
+__global__ void __launch_bounds__(BOW_THREADS) k_bow_match(int desc_type, int D, const afv_keypoint* __restrict__ kps, const uint8_t* __restrict__ desc,
+        const int* __restrict__ n_arr, int cap, int capp, const int* __restrict__ node_id, const uint8_t* __restrict__ valid,
+        const int* __restrict__ pair_a, const int* __restrict__ pair_b, float th_low, float nnratio, int check_ori,
+        const float* __restrict__ F12s, const float* __restrict__ epis, const float* __restrict__ sigma2,
+        int* __restrict__ match, int* __restrict__ nmatches) {
+    extern __shared__ __align__(16) unsigned char sm[];
+    unsigned long long* key1 = reinterpret_cast<unsigned long long*>(sm);         // [capp]
+    unsigned long long* key2 = key1 + capp;                                       // [capp]
+    int* seg = reinterpret_cast<int*>(key2 + capp);                               // [capp + 1] segment starts of list 1
+    unsigned char* matched2 = reinterpret_cast<unsigned char*>(seg + capp + 1);   // [cap]
+    unsigned char* bin_of = matched2 + cap;                                       // [cap]
+    __shared__ int hist[32], s_m1, s_m2, s_nseg, s_nm, keepbin[3];
+    const int p = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int fa = pair_a[p], fb = pair_b[p];
+    const int n1 = min(n_arr[fa], cap), n2 = min(n_arr[fb], cap);
+    const afv_keypoint* k1 = kps + (long long)fa * cap; const afv_keypoint* k2 = kps + (long long)fb * cap;
+    const uint8_t* d1 = desc + (long long)fa * cap * D; const uint8_t* d2 = desc + (long long)fb * cap * D;
+    const int* nd1 = node_id + (long long)fa * cap; const int* nd2 = node_id + (long long)fb * cap;
+    const uint8_t* v1 = valid ? valid + (long long)fa * cap : nullptr; const uint8_t* v2 = valid ? valid + (long long)fb * cap : nullptr;
+    int* out = match + (long long)p * cap;
+    if (tid < 32) hist[tid] = 0;
+    if (tid == 0) { s_m1 = 0; s_m2 = 0; s_nseg = 0; s_nm = 0; }
+    __syncthreads();
+    int c1 = 0, c2 = 0;
+    for (int i = tid; i < capp; i += BOW_THREADS) {
+        unsigned long long a = ~0ull, b = ~0ull;
+        if (i < n1 && nd1[i] >= 0) { a = ((unsigned long long)(unsigned)nd1[i] << 32) | (unsigned)i; ++c1; }
+        if (i < n2 && nd2[i] >= 0) { b = ((unsigned long long)(unsigned)nd2[i] << 32) | (unsigned)i; ++c2; }
+        key1[i] = a; key2[i] = b;
+        if (i < cap) { matched2[i] = 0; bin_of[i] = 0xff; out[i] = -1; }
+    }
+    atomicAdd(&s_m1, c1); atomicAdd(&s_m2, c2);
+    __syncthreads();
+    for (int k = 2; k <= capp; k <<= 1)
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int t = tid; t < capp; t += BOW_THREADS) {
+                const int txj = t ^ j;
+                if (txj > t) {
+                    const bool up = (t & k) == 0;
+                    unsigned long long a = key1[t], b = key1[txj];
+                    if ((a > b) == up) { key1[t] = b; key1[txj] = a; }
+                    a = key2[t]; b = key2[txj];
+                    if ((a > b) == up) { key2[t] = b; key2[txj] = a; }
+                }
+            }
+            __syncthreads();
+        }
+    const int m1 = s_m1, m2 = s_m2;
+    // segment heads of list 1 (ordered compaction by one warp: m1 <= 4096 entries)
+    if (wid == 0) {
+        int base = 0;
+        for (int t0 = 0; t0 < m1; t0 += 32) {
+            const int t = t0 + lane;
+            const bool head = t < m1 && (t == 0 || (key1[t] >> 32) != (key1[t - 1] >> 32));
+            const unsigned m = __ballot_sync(0xffffffffu, head);
+            if (head) seg[base + __popc(m & ((1u << lane) - 1))] = t;
+            base += __popc(m);
+        }
+        if (lane == 0) { seg[base] = m1; s_nseg = base; }
+    }
+    __syncthreads();
+    const int nseg = s_nseg;
+    float F[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, ex = 0.f, ey = 0.f;
+    const float* sg2 = nullptr;
+    if (MODE == 2) {
+        for (int i = 0; i < 9; ++i) F[i] = F12s[(long long)p * 9 + i];
+        ex = epis[2 * p]; ey = epis[2 * p + 1];
+        sg2 = sigma2 + (long long)fb * cap;
+    }
+    int nm = 0;
+    for (int s = wid; s < nseg; s += BOW_THREADS / 32) {
+        const int a0 = seg[s], a1 = seg[s + 1];
+        const unsigned node = (unsigned)(key1[a0] >> 32);
+        // lower bound of (node, 0) in list 2
+        int lo = 0, hi = m2;
+        const unsigned long long target = (unsigned long long)node << 32;
+        while (lo < hi) { const int mid = (lo + hi) >> 1; if (key2[mid] < target) lo = mid + 1; else hi = mid; }
+        if (lo >= m2 || (unsigned)(key2[lo] >> 32) != node) continue;
+        const int b0 = lo;
+        int b1 = b0;
+        { int l2 = b0, h2 = m2; const unsigned long long t2 = ((unsigned long long)node + 1ull) << 32;
+          while (l2 < h2) { const int mid = (l2 + h2) >> 1; if (key2[mid] < t2) l2 = mid + 1; else h2 = mid; }
+          b1 = l2; }
+        for (int ia = a0; ia < a1; ++ia) {
+            const int idx1 = (int)(unsigned)(key1[ia] & 0xffffffffu);
+            if (MODE == 2) { if (v1 && v1[idx1]) continue; }
+            else if (v1 && !v1[idx1]) continue;
+            const uint8_t* ref = d1 + (long long)idx1 * D;
+            Top2 t; t.k1 = t.k2 = KEY_NONE;
+            for (int ib = b0 + lane; ib < b1; ib += 32) {
+                const int idx2 = (int)(unsigned)(key2[ib] & 0xffffffffu);
+                if (MODE == 2) {
+                    if (v2 && v2[idx2]) continue;
+                    const float dist = desc_distance(desc_type, ref, d2 + (long long)idx2 * D, D);
+                    if (dist > th_low) continue;
+                    const float distex = __fsub_rn(ex, k2[idx2].x), distey = __fsub_rn(ey, k2[idx2].y);
+                    if (__fadd_rn(__fmul_rn(distex, distex), __fmul_rn(distey, distey)) < __fmul_rn(100.0f, __fsqrt_rn(sg2[idx2]))) continue;
+                    const float x1 = k1[idx1].x, y1 = k1[idx1].y, x2 = k2[idx2].x, y2 = k2[idx2].y;
+                    const float la = __fadd_rn(__fadd_rn(__fmul_rn(x1, F[0]), __fmul_rn(y1, F[3])), F[6]);
+                    const float lb = __fadd_rn(__fadd_rn(__fmul_rn(x1, F[1]), __fmul_rn(y1, F[4])), F[7]);
+                    const float lc = __fadd_rn(__fadd_rn(__fmul_rn(x1, F[2]), __fmul_rn(y1, F[5])), F[8]);
+                    const float num = __fadd_rn(__fadd_rn(__fmul_rn(la, x2), __fmul_rn(lb, y2)), lc);
+                    const float den = __fadd_rn(__fmul_rn(la, la), __fmul_rn(lb, lb));
+                    if (den == 0.0f) continue;
+                    const float dsqr = __fdiv_rn(__fmul_rn(num, num), den);
+                    if (!(dsqr < __fmul_rn(3.84f, sg2[idx2]))) continue;
+                    // smallest distance wins, the LAST of equal distances (candidates with dist > best are skipped, :733)
+                    top2_push(t, make_key(dist, (uint32_t)(b1 - 1 - ib)));
+                } else {
+                    if (matched2[idx2]) continue;
+                    if (MODE == 1 && v2 && !v2[idx2]) continue;
+                    top2_push(t, make_key(desc_distance(desc_type, ref, d2 + (long long)idx2 * D, D), (uint32_t)(ib - b0)));
+                }
+            }
+            top2_warp_reduce(t);
+            if (lane == 0 && t.k1 != KEY_NONE) {
+                const float bd1 = key_dist(t.k1), bd2 = key_dist(t.k2);
+                if (MODE == 2) {
+                    const int ib = b1 - 1 - (int)(uint32_t)t.k1;
+                    out[idx1] = (int)(unsigned)(key2[ib] & 0xffffffffu); ++nm;
+                } else {
+                    const bool pass_th = MODE == 0 ? (bd1 <= th_low) : (bd1 < th_low);
+                    if (pass_th && bd1 < __fmul_rn(nnratio, bd2)) {
+                        const int best2 = (int)(unsigned)(key2[b0 + (int)(uint32_t)t.k1] & 0xffffffffu);
+                        matched2[best2] = 1; ++nm;
+                        const int oi = MODE == 0 ? best2 : idx1;
+                        out[oi] = MODE == 0 ? idx1 : best2;
+                        if (check_ori) { const int bin = rot_bin(k1[idx1].angle, k2[best2].angle); bin_of[oi] = (unsigned char)bin; atomicAdd(&hist[bin], 1); }
+                    }
+                }
+            }
+            __syncwarp();
+        }
+    }
+    if (lane == 0 && nm) atomicAdd(&s_nm, nm);
+    __syncthreads();
+    if (check_ori && MODE != 2) {
+        if (tid == 0) three_maxima(hist, keepbin[0], keepbin[1], keepbin[2]);
+        __syncthreads();
+        int removed = 0;
+        const int nout = MODE == 0 ? n2 : n1;
+        for (int i = tid; i < nout; i += BOW_THREADS) {
+            const int bn = bin_of[i];
+            if (bn == 0xff || bn == keepbin[0] || bn == keepbin[1] || bn == keepbin[2]) continue;
+            out[i] = -1; ++removed;
+        }
+        if (removed) atomicSub(&s_nm, removed);
+        __syncthreads();
+    }
+    if (tid == 0) nmatches[p] = s_nm;
+}
+
+extern "C" int afv_bow_match(int mode, int desc_type, const afv_keypoint* d_kps, const void* d_desc, const int* d_n, int B, int cap,
+        const int* d_node_id, const uint8_t* d_valid, const int* d_pair_a, const int* d_pair_b, int P, float th_low, float nnratio,
+        int check_orientation, const float* d_F12, const float* d_epipole, const float* d_sigma2, int* d_match, int* d_nmatches, void* cuda_stream) {
+    const int D = desc_bytes(desc_type);
+    if (D < 0 || mode < 0 || mode > 2 || !d_kps || !d_desc || !d_n || !d_node_id || !d_pair_a || !d_pair_b || !d_match || !d_nmatches || B < 1 || P < 0 || cap < 1 ||
+        (mode == 2 && (!d_F12 || !d_epipole || !d_sigma2))) { afv_set_error("afv_bow_match: bad argument"); return AFV_ERR_INVALID; }
+    if (P == 0) return AFV_OK;
+    int capp = 1;
+    while (capp < cap) capp <<= 1;
+    const size_t smem = (size_t)capp * 16 + (size_t)(capp + 1) * 4 + (size_t)cap * 2 + 16;
+    if (smem > 200 * 1024) { afv_set_error("afv_bow_match: cap %d too large for the shared-memory sort", cap); return AFV_ERR_INVALID; }
+    cudaStream_t st = as_stream(cuda_stream);
+    AfvProfScope ps("k_bow_match", st);
+#define BOW_LAUNCH(M) do { AFV_CUDA_CHECK(cudaFuncSetAttribute(k_bow_match<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        k_bow_match<M><<<P, BOW_THREADS, smem, st>>>(desc_type, D, d_kps, (const uint8_t*)d_desc, d_n, cap, capp, d_node_id, d_valid, d_pair_a, d_pair_b, \
+            th_low, nnratio, check_orientation, d_F12, d_epipole, d_sigma2, d_match, d_nmatches); } while (0)
+    if (mode == 0) BOW_LAUNCH(0); else if (mode == 1) BOW_LAUNCH(1); else BOW_LAUNCH(2);
+#undef BOW_LAUNCH
+    ++g_afv_launches;
+    AFV_CUDA_CHECK(cudaGetLastError());
     return AFV_OK;
 }
 

@@ -93,6 +93,75 @@ class FeatureMatcher:
                                             _vp(match_q), _vp(nm), _sp(stream)))
         return match_q[:Q], nm[:P]
 
+    def search_by_projection_ex(self, qdesc, qxy, qr, qmin, qmax, q_start, kps, desc, kpsize, n, frame, bounds, qangle=None, inf1d=None,
+                                occupied=None, claim=True, ratio_same_scale=False, size_tolerance=1.2, th=None, nq_total=None,
+                                workspace=None, stream=None):
+        """Every projection-type search of the reference after its projection prologue (include/afv.h lists the option set of each
+        reference method).  qr < 0 skips a query; qangle [Q] adds the orientation histogram; inf1d [B,cap] adds Fuse's reprojection
+        gate.  Returns (match_q [Q] i32 train index or -1, nmatches [P] i32)."""
+        import torch
+        lib, _check, _vp, _sp = _afv()
+        P = frame.shape[0]
+        Q = qdesc.shape[0]
+        B, cap = kps.shape[0], kps.shape[1]
+        match_q = torch.empty(max(Q, 1), dtype=torch.int32, device=kps.device)
+        nm = torch.empty(max(P, 1), dtype=torch.int32, device=kps.device)
+        minx, miny, maxx, maxy = bounds
+        ws_ptr, ws_bytes = (None, 0) if workspace is None else (_vp(workspace), workspace.numel() * workspace.element_size())
+        lib.afv_search_by_projection_workspace_bytes.restype = C.c_size_t
+        _check(lib.afv_search_by_projection_ex(self.desc_type, _vp(qdesc), _vp(qxy), _vp(qr), _vp(qmin), _vp(qmax), _vp(qangle), _vp(q_start), P,
+                                               int(Q if nq_total is None else nq_total), _vp(kps), _vp(desc), _vp(kpsize), _vp(inf1d), _vp(n), B, cap,
+                                               _vp(frame), _vp(occupied), int(bool(claim)), C.c_float(minx), C.c_float(miny), C.c_float(maxx),
+                                               C.c_float(maxy), C.c_float(self.th_low if th is None else th), C.c_float(self.nnratio),
+                                               int(bool(ratio_same_scale)), C.c_float(size_tolerance), _vp(match_q), _vp(nm), ws_ptr,
+                                               C.c_size_t(ws_bytes), _sp(stream)))
+        return match_q[:Q], nm[:P]
+
+    # the reference's method names on top of the generic search (arrays after the projection prologue)
+    def fuse(self, qdesc, qxy, qr, qmin, qmax, q_start, kps, desc, kpsize, n, frame, bounds, inf1d=None, size_tolerance=1.2, stream=None):
+        """Fuse (src/FeatureMatcher.cc:794-942 with inf1d = GetKeyPt1DInf, :944-1064 without): keypoint each map point lands on."""
+        return self.search_by_projection_ex(qdesc, qxy, qr, qmin, qmax, q_start, kps, desc, kpsize, n, frame, bounds, inf1d=inf1d, occupied=None,
+                                            claim=False, ratio_same_scale=False, size_tolerance=size_tolerance, stream=stream)
+
+    def search_by_projection_reloc(self, qdesc, qxy, qr, qmin, qmax, qangle, q_start, kps, desc, kpsize, n, frame, bounds, occupied=None,
+                                   size_tolerance=1.2, stream=None):
+        """SearchByProjection(CurrentFrame, pKF, sAlreadyFound, th, useHigh) (:1406-1506) / (CurrentFrame, LastFrame) (:1291-1402)."""
+        return self.search_by_projection_ex(qdesc, qxy, qr, qmin, qmax, q_start, kps, desc, kpsize, n, frame, bounds,
+                                            qangle=qangle if self.check_ori else None, occupied=occupied, claim=True, ratio_same_scale=False,
+                                            size_tolerance=size_tolerance, stream=stream)
+
+    def search_by_sim3(self, q1, q2, kps, desc, kpsize, n, frame1, frame2, bounds, stream=None):
+        """SearchBySim3 (:1066-1287).  q1 / q2 = (qdesc, qxy, qr, qmin, qmax, q_start) of the two directions; query j of problem p is
+        keypoint j of frame1[p] (resp. frame2[p]).  Returns (match12 [Q1] i32, nfound [P] i32)."""
+        import torch
+        lib, _check, _vp, _sp = _afv()
+        P = frame1.shape[0]
+        B, cap = kps.shape[0], kps.shape[1]
+        Q1, Q2 = q1[0].shape[0], q2[0].shape[0]
+        m12 = torch.empty(max(Q1, 1), dtype=torch.int32, device=kps.device)
+        nf = torch.empty(max(P, 1), dtype=torch.int32, device=kps.device)
+        minx, miny, maxx, maxy = bounds
+        _check(lib.afv_search_by_sim3(self.desc_type, _vp(q1[0]), _vp(q1[1]), _vp(q1[2]), _vp(q1[3]), _vp(q1[4]), _vp(q1[5]), Q1,
+                                      _vp(q2[0]), _vp(q2[1]), _vp(q2[2]), _vp(q2[3]), _vp(q2[4]), _vp(q2[5]), Q2, P, _vp(kps), _vp(desc), _vp(kpsize),
+                                      _vp(n), B, cap, _vp(frame1), _vp(frame2), C.c_float(minx), C.c_float(miny), C.c_float(maxx), C.c_float(maxy),
+                                      C.c_float(self.th_low), _vp(m12), _vp(nf), _sp(stream)))
+        return m12[:Q1], nf[:P]
+
+    def bow_match(self, mode, kps, desc, n, node_id, valid, pair_a, pair_b, F12=None, epipole=None, sigma2=None, stream=None):
+        """mode 0 SearchByBoW(KF,F) (:186-283, match[p][i2] = i1), 1 SearchByBoW(KF,KF) (:561-660, match[p][i1] = i2),
+        2 SearchForTriangulation (:662-790, match[p][i1] = i2).  node_id [B,cap] i32 (afv_bow_transform's node ids, < 0 = none),
+        valid [B,cap] u8 or None.  Returns (match [P,cap] i32, nmatches [P] i32)."""
+        import torch
+        lib, _check, _vp, _sp = _afv()
+        B, cap = kps.shape[0], kps.shape[1]
+        P = pair_a.shape[0]
+        match = torch.empty((max(P, 1), cap), dtype=torch.int32, device=kps.device)
+        nm = torch.empty(max(P, 1), dtype=torch.int32, device=kps.device)
+        _check(lib.afv_bow_match(int(mode), self.desc_type, _vp(kps), _vp(desc), _vp(n), B, cap, _vp(node_id), _vp(valid), _vp(pair_a), _vp(pair_b), P,
+                                 C.c_float(self.th_low), C.c_float(self.nnratio), int(self.check_ori), _vp(F12), _vp(epipole), _vp(sigma2),
+                                 _vp(match), _vp(nm), _sp(stream)))
+        return match[:P], nm[:P]
+
     def match_bruteforce(self, q, t, stream=None):
         import torch
         lib, _check, _vp, _sp = _afv()

@@ -158,8 +158,9 @@ int  afv_search_for_initialization(int desc_type, const afv_keypoint* d_kps, con
                                    int check_orientation, int* d_matches12, int* d_nmatches,
                                    void* cuda_stream);
 
-/* SearchByProjection family (src/FeatureMatcher.cc:73-154 TrackLocalMap, :287-397 Sim3 / relocalisation variants; the
- * same core serves Fuse and SearchBySim3): P independent problems, problem p projects queries q_start[p]..q_start[p+1]
+/* SearchByProjection, the two classic variants (src/FeatureMatcher.cc:73-154 TrackLocalMap, :287-397 Sim3); kept as the short form
+ * of afv_search_by_projection_ex below (it reads the query count back from the device, i.e. it synchronises the stream once):
+ * P independent problems, problem p projects queries q_start[p]..q_start[p+1]
  * (descriptor, projected position, search radius, accepted size range = predicted size / and * sizeTolerance) into train
  * frame d_frame[p] of a B x cap extraction result.  Sequential semantics reproduced exactly: queries in order; a train
  * keypoint that already holds a map point (d_occupied, or claimed by an earlier query of this call) is skipped;
@@ -174,12 +175,63 @@ int  afv_search_by_projection(int desc_type, const void* d_qdesc, const float* d
                               float th, float nnratio, int ratio_same_scale_only, float size_tolerance,
                               int* d_match_q, int* d_nmatches, void* cuda_stream);
 
+/* Every projection-type search of the reference AFTER its projection prologue (the caller keeps the few lines that project a
+ * map point and read its predicted size; queries arrive as projected position, radius, accepted size range, descriptor):
+ *   reference method (src/FeatureMatcher.cc)            occupied  claim  ratio_same_scale  d_qangle  d_inf1d   th
+ *   SearchByProjection(F, vpMapPoints)        :73-154   F.pts     1      1                 NULL      NULL      TH_HIGH
+ *   SearchByProjection(pKF, Scw, ..) Sim3     :287-397  vpMatched 1      0                 NULL      NULL      TH_LOW
+ *   SearchByProjection(Cur, Last) motion      :1291-1402 Cur.pts  1      0                 Last angles NULL    TH_HIGH
+ *   SearchByProjection(Cur, pKF, ..) reloc    :1406-1506 Cur.pts  1      0                 KF angles NULL      reloc th
+ *   Fuse(pKF, vpMapPoints)                    :794-942  NULL      0      0                 NULL      GetKeyPt1DInf  TH_LOW
+ *   Fuse(pKF, Scw, ..)                        :944-1064 NULL      0      0                 NULL      NULL      TH_LOW
+ * (Fuse returns the keypoint every map point lands on; the add / replace decision on the map graph stays with the caller.)
+ * d_qr[q] < 0 marks a query the prologue skipped.  d_qangle != NULL adds the orientation histogram (:1579-1668) over the accepted
+ * matches and removes the matches outside the three dominant bins; d_inf1d ([B][cap]) adds Fuse's monocular reprojection gate
+ * e2 * inf > 5.99 (:905-915).  nq_total = d_q_start[P] when the host knows it (no synchronisation), -1 to read it back.
+ * d_workspace (afv_search_by_projection_workspace_bytes) may be NULL: stream-ordered allocation inside the call. */
+size_t afv_search_by_projection_workspace_bytes(int desc_type, int P, int nq_total);
+int  afv_search_by_projection_ex(int desc_type, const void* d_qdesc, const float* d_qxy, const float* d_qr,
+                                 const float* d_qmin_size, const float* d_qmax_size, const float* d_qangle, const int* d_q_start, int P,
+                                 int nq_total, const afv_keypoint* d_kps, const void* d_desc, const float* d_kpsize, const float* d_inf1d,
+                                 const int* d_n, int B, int cap, const int* d_frame, const uint8_t* d_occupied, int claim,
+                                 float min_x, float min_y, float max_x, float max_y, float th, float nnratio,
+                                 int ratio_same_scale_only, float size_tolerance, int* d_match_q, int* d_nmatches,
+                                 void* d_workspace, size_t workspace_bytes, void* cuda_stream);
+
+/* FeatureMatcher::SearchBySim3 (src/FeatureMatcher.cc:1066-1287) after its projection prologue, P keyframe pairs: direction 1
+ * projects the map points of frame1's keypoints into frame2 (problem p = queries q_start1[p]..q_start1[p+1], query j = keypoint j
+ * of frame d_frame1[p]; d_qr < 0 = no map point / already matched / outside), direction 2 likewise; both are stateless best-only
+ * searches with th_high; match12[q_start1[p] + i1] = i2 where both directions agree (:1270-1284), else -1. */
+int  afv_search_by_sim3(int desc_type,
+                        const void* d_q1desc, const float* d_q1xy, const float* d_q1r, const float* d_q1min, const float* d_q1max,
+                        const int* d_q_start1, int nq1_total,
+                        const void* d_q2desc, const float* d_q2xy, const float* d_q2r, const float* d_q2min, const float* d_q2max,
+                        const int* d_q_start2, int nq2_total, int P,
+                        const afv_keypoint* d_kps, const void* d_desc, const float* d_kpsize, const int* d_n, int B, int cap,
+                        const int* d_frame1, const int* d_frame2, float min_x, float min_y, float max_x, float max_y, float th_high,
+                        int* d_match12, int* d_nfound, void* cuda_stream);
+
+/* BoW merge-join searches on per-feature node ids (what afv_bow_transform returns per feature; < 0 = not in the FeatureVector),
+ * batched over P frame pairs (frame1 = d_pair_a[p], frame2 = d_pair_b[p]) of a B x cap extraction result:
+ *   mode 0  SearchByBoW(KF, F)  (:186-283): d_valid[frame1] = keypoint holds a good map point (:216-222); d_match[p][i2] = i1
+ *   mode 1  SearchByBoW(KF, KF) (:561-660): d_valid on both frames, strict best < th_low (:630);       d_match[p][i1] = i2
+ *   mode 2  SearchForTriangulation (:662-790, monocular): d_valid = keypoint already HAS a map point (skipped on both sides),
+ *           epipole gate (:744-751) and CheckDistEpipolarLine (:165-183) with d_F12[p] (row-major), d_epipole[p] = (ex, ey) in
+ *           image 2 and d_sigma2 ([B][cap]) = GetKeyPt1DSigma2;                                         d_match[p][i1] = i2
+ * d_valid may be NULL (mode 0 / 1: every keypoint valid; mode 2: no keypoint has a map point).  d_match is P x cap. */
+int  afv_bow_match(int mode, int desc_type, const afv_keypoint* d_kps, const void* d_desc, const int* d_n, int B, int cap,
+                   const int* d_node_id, const uint8_t* d_valid, const int* d_pair_a, const int* d_pair_b, int P,
+                   float th_low, float nnratio, int check_orientation, const float* d_F12, const float* d_epipole,
+                   const float* d_sigma2, int* d_match, int* d_nmatches, void* cuda_stream);
+
 /* Brute-force N x M best / second (upper bound of every matcher; also MapPoint::ComputeDistinctiveDescriptors'
  * distance matrix, src/MapPoint.cc:312-324). */
 int  afv_match_bruteforce(int desc_type, const void* d_q, int nq, const void* d_t, int nt,
                           int* d_best, float* d_bestd, float* d_secondd, void* cuda_stream);
 
-/* SearchByBoW(KF,F) (src/FeatureMatcher.cc:186-283) on FeatureVector segments (sorted node ids + CSR). */
+/* SearchByBoW(KF,F) (src/FeatureMatcher.cc:186-283) on FeatureVector segments (sorted node ids + CSR) for ONE pair.  kf_idx
+ * must list only keyframe features that hold a good map point (the reference skips the others, :216-222); afv_bow_match is the
+ * batched form with explicit validity masks. */
 int  afv_search_by_bow(int desc_type,
                        const void* d_dkf, const afv_keypoint* d_kkf,
                        const int* d_kf_node, const int* d_kf_start, const int* d_kf_idx, int kf_nodes,

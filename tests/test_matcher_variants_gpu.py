@@ -1,0 +1,177 @@
+"""CUDA == oracle for the remaining FeatureMatcher searches, one test per reference method:
+SearchByProjection Sim3 (:287-397), relocalisation (:1406-1506) / motion model (:1291-1402), Fuse x2 (:794-1064), SearchBySim3
+(:1066-1287), SearchByBoW(KF,F) and (KF,KF) (:186-283, :561-660), SearchForTriangulation (:662-790).  The oracle functions
+used here are themselves checked against the reference's own compiled bodies in tests/test_oracle_vs_ref.py."""
+import numpy as np
+import pytest
+
+from oracle import pyoracle as po
+
+pytestmark = pytest.mark.gpu
+BOUNDS = (0.0, 0.0, 640.0, 480.0)
+
+
+@pytest.fixture(scope="module", params=["orb32", "brisk48"])
+def extracted(request, pkg, synth):
+    import torch
+    feat = request.param
+    st = pkg.FEATURE_SETTINGS[feat]
+    frames = np.concatenate([synth.stream_frames(640, 480, s, 4)[0] for s in (20, 25)], axis=0)
+    ex = pkg.FeatureExtractor(feat, nfeatures=1000, max_batch=len(frames), max_w=640, max_h=480)
+    out = ex.alloc_device_outputs(len(frames))
+    ex.extract_batch_device(torch.from_numpy(frames).cuda(), out)
+    torch.cuda.synchronize()
+    ex.status()
+    n = out[3].cpu().numpy()
+    host = []
+    for f in range(len(frames)):
+        m = int(n[f])
+        host.append((pkg.kps_from_device(out[0][f], m), out[1][f, :m].cpu().numpy(), out[2][f, :m].cpu().numpy()))
+    yield out, host, ex.cap, st["feature_id"], float(st["matching_th"]), np.float32(st["scale_factor"])
+    ex.close()
+
+
+def _t(a):
+    import torch
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def _queries(host, problems, rng, tol, radius, skip_frac=0.1, dup=True):
+    qd, qxy, qr, qmin, qmax, qang, qstart = [], [], [], [], [], [], [0]
+    for (qa, tb) in problems:
+        kq, dq, sq = host[qa]
+        nq = len(kq)
+        xy = (np.stack([kq["x"], kq["y"]], axis=1) + rng.uniform(-4, 4, (nq, 2))).astype(np.float32)
+        r = (np.float32(radius) * sq).astype(np.float32)
+        r[rng.random(nq) < skip_frac] = -1.0
+        mn = (sq / tol).astype(np.float32); mx = (sq * tol).astype(np.float32)
+        ang = np.mod(kq["angle"] + np.where(rng.random(nq) < 0.3, 95.0, 0.0), 360.0).astype(np.float32)
+        d = dq
+        if dup:
+            ii = rng.integers(0, nq, nq // 5)
+            d = np.concatenate([dq, dq[ii]]); xy = np.concatenate([xy, xy[ii]]); r = np.concatenate([r, r[ii]])
+            mn = np.concatenate([mn, mn[ii]]); mx = np.concatenate([mx, mx[ii]]); ang = np.concatenate([ang, ang[ii]])
+        qd.append(d); qxy.append(xy); qr.append(r); qmin.append(mn); qmax.append(mx); qang.append(ang); qstart.append(qstart[-1] + len(d))
+    return qd, qxy, qr, qmin, qmax, qang, qstart
+
+
+@pytest.mark.parametrize("variant", ["sim3", "reloc", "reloc_noori", "fuse1", "fuse2"])
+def test_projection_variants(pkg, extracted, variant):
+    out, host, cap, dt, th, tol = extracted
+    rng = np.random.default_rng(100)
+    problems = [(0, 1), (2, 3), (5, 4), (6, 7)]
+    qd, qxy, qr, qmin, qmax, qang, qstart = _queries(host, problems, rng, tol, 6.0)
+    nfr = len(host)
+    occs = np.zeros((nfr, cap), np.uint8); infs = np.zeros((nfr, cap), np.float32)
+    for f in range(nfr):
+        occs[f, :len(host[f][0])] = (rng.random(len(host[f][0])) < 0.15)
+        infs[f, :len(host[f][0])] = np.float32(1.0) / (host[f][2] ** 2)
+    use_occ = variant in ("sim3", "reloc", "reloc_noori"); claim = use_occ
+    use_ang = variant == "reloc"; use_inf = variant == "fuse1"
+    refs = []
+    for i, (qa, tb) in enumerate(problems):
+        kt, dtt, stt = host[tb]
+        refs.append(po.search_by_projection_ex(dt, qd[i], qxy[i], qr[i], qmin[i], qmax[i], kt, dtt, stt, BOUNDS, qangle=qang[i] if use_ang else None,
+                                               tinf1d=infs[tb, :len(kt)] if use_inf else None, occupied=occs[tb, :len(kt)] if use_occ else None,
+                                               claim=claim, th=th, ratio_same_scale=False, tol=float(tol)))
+    fm = pkg.FeatureMatcher(nnratio=0.8, check_ori=use_ang, desc_type=dt, th_low=th)
+    mq, nm = fm.search_by_projection_ex(_t(np.concatenate(qd)), _t(np.concatenate(qxy)), _t(np.concatenate(qr)), _t(np.concatenate(qmin)),
+                                        _t(np.concatenate(qmax)), _t(np.array(qstart, np.int32)), out[0], out[1], out[2], out[3],
+                                        _t(np.array([p[1] for p in problems], np.int32)), BOUNDS, qangle=_t(np.concatenate(qang)) if use_ang else None,
+                                        inf1d=_t(infs) if use_inf else None, occupied=_t(occs) if use_occ else None, claim=claim,
+                                        ratio_same_scale=False, size_tolerance=float(tol))
+    import torch
+    torch.cuda.synchronize()
+    mq = mq.cpu().numpy(); nm = nm.cpu().numpy()
+    for i, (rn, rm) in enumerate(refs):
+        assert nm[i] == rn and (mq[qstart[i]:qstart[i + 1]] == rm).all(), "%s problem %d: %d vs %d" % (variant, i, nm[i], rn)
+        assert rn > 100
+        if claim:
+            got = rm[rm >= 0]; assert len(set(got.tolist())) == len(got)
+    if variant in ("fuse1", "fuse2"):                                  # stateless: duplicated queries land on the same keypoint
+        assert any(len(set(rm[rm >= 0].tolist())) < (rm >= 0).sum() for _, rm in refs)
+
+
+def test_search_by_sim3(pkg, extracted):
+    out, host, cap, dt, th, tol = extracted
+    rng = np.random.default_rng(101)
+    pairs = [(0, 1), (2, 3), (5, 4)]
+    q1 = _queries(host, pairs, rng, tol, 5.0, skip_frac=0.3, dup=False)
+    q2 = _queries(host, [(b, a) for a, b in pairs], rng, tol, 5.0, skip_frac=0.3, dup=False)
+    refs = []
+    for i, (a, b) in enumerate(pairs):
+        ka, da, sa = host[a]; kb, db, sb = host[b]
+        refs.append(po.search_by_sim3(dt, ka, da, sa, q1[1][i], q1[2][i], q1[3][i], q1[4][i], kb, db, sb, q2[1][i], q2[2][i], q2[3][i], q2[4][i], BOUNDS, th))
+    fm = pkg.FeatureMatcher(nnratio=0.8, desc_type=dt, th_low=th)
+    pack = lambda q: (_t(np.concatenate(q[0])), _t(np.concatenate(q[1])), _t(np.concatenate(q[2])), _t(np.concatenate(q[3])), _t(np.concatenate(q[4])),
+                      _t(np.array(q[6], np.int32)))
+    m12, nf = fm.search_by_sim3(pack(q1), pack(q2), out[0], out[1], out[2], out[3], _t(np.array([p[0] for p in pairs], np.int32)),
+                                _t(np.array([p[1] for p in pairs], np.int32)), BOUNDS)
+    import torch
+    torch.cuda.synchronize()
+    m12 = m12.cpu().numpy(); nf = nf.cpu().numpy()
+    for i, (rn, rm) in enumerate(refs):
+        assert nf[i] == rn and rn > 30 and (m12[q1[6][i]:q1[6][i + 1]] == rm).all(), "pair %d" % i
+
+
+def _node_ids(host, cap, rng, drop=0.05):
+    nfr = len(host)
+    nodes = np.full((nfr, cap), -1, np.int32)
+    for f in range(nfr):
+        k = host[f][0]
+        nd = ((k["x"] // 80).astype(np.int32) * 10 + (k["y"] // 80).astype(np.int32)) * 7 + 3
+        nd[rng.random(len(k)) < drop] = -1
+        nodes[f, :len(k)] = nd
+    return nodes
+
+
+@pytest.mark.parametrize("mode,check_ori", [(0, True), (0, False), (1, True), (1, False)])
+def test_search_by_bow_batched(pkg, extracted, mode, check_ori):
+    out, host, cap, dt, th, tol = extracted
+    rng = np.random.default_rng(102 + mode)
+    nodes = _node_ids(host, cap, rng)
+    valid = (rng.random((len(host), cap)) < 0.8).astype(np.uint8)
+    pairs = [(0, 1), (1, 2), (2, 3), (4, 5), (6, 7), (3, 3)]
+    fm = pkg.FeatureMatcher(nnratio=0.75, check_ori=check_ori, desc_type=dt, th_low=th)
+    m, nm = fm.bow_match(mode, out[0], out[1], out[3], _t(nodes), _t(valid), _t(np.array([p[0] for p in pairs], np.int32)),
+                         _t(np.array([p[1] for p in pairs], np.int32)))
+    import torch
+    torch.cuda.synchronize()
+    m = m.cpu().numpy(); nm = nm.cpu().numpy()
+    for i, (a, b) in enumerate(pairs):
+        ka, da, _ = host[a]; kb, db, _ = host[b]
+        rn, rm = po.bow_match(mode, dt, ka, da, nodes[a, :len(ka)], valid[a, :len(ka)], kb, db, nodes[b, :len(kb)], valid[b, :len(kb)],
+                              th_low=th, nnratio=0.75, check_ori=check_ori)
+        assert nm[i] == rn and (m[i, :len(rm)] == rm).all() and (m[i, len(rm):] == -1).all(), "mode %d pair %d: %d vs %d" % (mode, i, nm[i], rn)
+        assert rn > 30
+
+
+def test_search_for_triangulation(pkg, extracted):
+    out, host, cap, dt, th, tol = extracted
+    rng = np.random.default_rng(104)
+    nodes = _node_ids(host, cap, rng)
+    has_mp = (rng.random((len(host), cap)) < 0.3).astype(np.uint8)
+    sigma2 = np.ones((len(host), cap), np.float32)
+    for f in range(len(host)):
+        sigma2[f, :len(host[f][0])] = host[f][2] ** 2
+    pairs = [(0, 1), (1, 2), (4, 5), (6, 7)]
+    F12 = np.zeros((len(pairs), 9), np.float32); epi = np.zeros((len(pairs), 2), np.float32)
+    for i in range(len(pairs)):
+        ang = rng.uniform(0, np.pi)
+        tx, ty = np.cos(ang), np.sin(ang)
+        F12[i] = np.array([[0, 0, ty], [0, 0, -tx], [-ty, tx, 0]], np.float32).reshape(9) + rng.normal(0, 1e-4, 9).astype(np.float32)
+        epi[i] = (rng.uniform(-300, 900), rng.uniform(-200, 700))
+    fm = pkg.FeatureMatcher(nnratio=0.6, check_ori=False, desc_type=dt, th_low=th)
+    m, nm = fm.bow_match(2, out[0], out[1], out[3], _t(nodes), _t(has_mp), _t(np.array([p[0] for p in pairs], np.int32)),
+                         _t(np.array([p[1] for p in pairs], np.int32)), F12=_t(F12), epipole=_t(epi), sigma2=_t(sigma2))
+    import torch
+    torch.cuda.synchronize()
+    m = m.cpu().numpy(); nm = nm.cpu().numpy()
+    tot = 0
+    for i, (a, b) in enumerate(pairs):
+        ka, da, _ = host[a]; kb, db, _ = host[b]
+        rn, rm = po.bow_match(2, dt, ka, da, nodes[a, :len(ka)], has_mp[a, :len(ka)], kb, db, nodes[b, :len(kb)], has_mp[b, :len(kb)], th_low=th,
+                              F12=F12[i], epipole=tuple(epi[i].tolist()), sigma2_2=sigma2[b, :len(kb)])
+        assert nm[i] == rn and (m[i, :len(rm)] == rm).all(), "pair %d: %d vs %d" % (i, nm[i], rn)
+        tot += rn
+    assert tot > 40
