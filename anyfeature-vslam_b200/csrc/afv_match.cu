@@ -270,6 +270,113 @@ extern "C" int afv_match_window(int desc_type, const void* d_q, const float* d_q
     return AFV_OK;
 }
 
+// ---- windowed matcher batched over frame pairs (the throughput form of the SearchByProjection / GetFeaturesInArea core) ----
+// One CTA per pair: the train frame (positions, sizes, descriptors) and its prebuilt grid (afv_grid_build = the reference's
+// Frame::AssignFeaturesToGrid, done once per frame) are staged in shared memory with coalesced loads -- these loads ARE the
+// algorithmic HBM traffic of the pair -- then one THREAD per query walks its cell-column ranges in the reference's enumeration
+// order (cell x, cell y, index ascending), so "first minimum wins" needs no tie handling.  Small windows are HBM / latency bound
+// (a few candidates per query), large ones POPC bound (see bench.py --workload m1).  Measured alternatives that were SLOWER on
+// B200 (profiles/r02_matcher.md): enumerate -> flat candidate list -> uniform distance pass -> per-query reduce (2 - 3.5x slower:
+// double enumeration + block barriers), and 4 lanes per query over interleaved cell columns (1.0 - 1.3x slower: same number of
+// warp iterations, the longest column of a warp sets the pace).
+#define MWP_THREADS 512
+template <int NW>                               // descriptor words: 8 orb32, 12 brisk48, 16 akaze61 (61 bytes zero-padded)
+__global__ void __launch_bounds__(MWP_THREADS) k_match_window_pairs(int D, const afv_keypoint* __restrict__ kps, const uint8_t* __restrict__ desc,
+        const float* __restrict__ kpsize, const int* __restrict__ n_arr, int cap, const int* __restrict__ cell_start,
+        const int* __restrict__ cell_items, const int* __restrict__ pair_a, const int* __restrict__ pair_b,
+        const float* __restrict__ qxy, const float* __restrict__ qr, float r_all, const float* __restrict__ qmin, const float* __restrict__ qmax,
+        float minX, float minY, float invW, float invH, int* __restrict__ best, float* __restrict__ bestd, float* __restrict__ secondd) {
+    extern __shared__ __align__(16) unsigned char sm[];
+    uint32_t* sdesc = reinterpret_cast<uint32_t*>(sm);                                  // [NW][cap] word-major
+    float2* sxy = reinterpret_cast<float2*>(sdesc + (size_t)NW * cap);                  // [cap]
+    float* ssz = reinterpret_cast<float*>(sxy + cap);                                   // [cap]
+    unsigned short* scs = reinterpret_cast<unsigned short*>(ssz + cap);                 // [NCELLS + 1]
+    unsigned short* sci = scs + ((NCELLS + 1 + 7) & ~7);                                // [cap]
+    const int p = blockIdx.x, tid = threadIdx.x;
+    const int fa = pair_a[p], fb = pair_b[p];
+    const int n1 = min(n_arr[fa], cap), n2 = min(n_arr[fb], cap);
+    const afv_keypoint* k1 = kps + (long long)fa * cap; const afv_keypoint* k2 = kps + (long long)fb * cap;
+    const uint8_t* d1 = desc + (long long)fa * cap * D; const uint8_t* d2 = desc + (long long)fb * cap * D;
+    const float* sz2 = kpsize + (long long)fb * cap;
+    const int* cs = cell_start + (long long)fb * (NCELLS + 1); const int* ci = cell_items + (long long)fb * cap;
+    // ---- stage the train frame
+    if ((D & 3) == 0) {
+        const uint32_t* w2 = reinterpret_cast<const uint32_t*>(d2);
+        for (int i = tid; i < n2 * NW; i += MWP_THREADS) { const int r = i / NW, w = i - r * NW; sdesc[(size_t)w * cap + r] = w2[i]; }
+    } else {
+        for (int i = tid; i < n2 * NW; i += MWP_THREADS) {
+            const int r = i / NW, w = i - r * NW;
+            uint32_t v = 0;
+            for (int b = 0; b < 4; ++b) { const int o = w * 4 + b; if (o < D) v |= (uint32_t)d2[(long long)r * D + o] << (8 * b); }
+            sdesc[(size_t)w * cap + r] = v;
+        }
+    }
+    for (int i = tid; i < n2; i += MWP_THREADS) { sxy[i] = make_float2(k2[i].x, k2[i].y); ssz[i] = sz2[i]; sci[i] = (unsigned short)ci[i]; }
+    for (int i = tid; i <= NCELLS; i += MWP_THREADS) scs[i] = (unsigned short)cs[i];
+    __syncthreads();
+    // ---- one thread per query
+    for (int qi = tid; qi < n1; qi += MWP_THREADS) {
+        const long long qo = (long long)p * cap + qi;
+        const float x = qxy ? qxy[2 * qo] : k1[qi].x, y = qxy ? qxy[2 * qo + 1] : k1[qi].y;
+        const float r = qr ? qr[qo] : r_all;
+        const float smin = qmin ? qmin[qo] : -FLT_MAX, smax = qmax ? qmax[qo] : FLT_MAX;
+        uint32_t q[NW];
+        if ((D & 3) == 0) {
+            const uint32_t* row = reinterpret_cast<const uint32_t*>(d1 + (long long)qi * D);
+#pragma unroll
+            for (int w = 0; w < NW; ++w) q[w] = row[w];
+        } else {
+#pragma unroll
+            for (int w = 0; w < NW; ++w) { uint32_t v = 0; for (int b = 0; b < 4; ++b) { const int o = w * 4 + b; if (o < D) v |= (uint32_t)d1[(long long)qi * D + o] << (8 * b); } q[w] = v; }
+        }
+        int bi = -1, b1 = 0x7fffffff, b2 = 0x7fffffff;
+        int c0, c1, r0, r1;
+        if (!(r < 0.0f) && window_cells(x, y, r, minX, minY, invW, invH, c0, c1, r0, r1)) {
+            for (int ix = c0; ix <= c1; ++ix) {
+                const int sb = scs[ix * AFV_GRID_ROWS + r0], se = scs[ix * AFV_GRID_ROWS + r1 + 1];
+                for (int j = sb; j < se; ++j) {
+                    const int idx = sci[j];
+                    const float sz = ssz[idx];
+                    if (sz < smin || sz > smax) continue;
+                    const float2 t = sxy[idx];
+                    if (!(fabsf(__fsub_rn(t.x, x)) < r && fabsf(__fsub_rn(t.y, y)) < r)) continue;
+                    int d = 0;
+#pragma unroll
+                    for (int w = 0; w < NW; ++w) d += __popc(q[w] ^ sdesc[(size_t)w * cap + idx]);
+                    if (d < b1) { b2 = b1; b1 = d; bi = idx; } else if (d < b2) b2 = d;
+                }
+            }
+        }
+        best[qo] = bi;
+        bestd[qo] = b1 == 0x7fffffff ? FLT_MAX : (float)b1;
+        secondd[qo] = b2 == 0x7fffffff ? FLT_MAX : (float)b2;
+    }
+}
+
+extern "C" int afv_match_window_pairs(int desc_type, const afv_keypoint* d_kps, const void* d_desc, const float* d_kpsize, const int* d_n,
+        int B, int cap, const int* d_cell_start, const int* d_cell_items, const int* d_pair_a, const int* d_pair_b, int P,
+        const float* d_qxy, const float* d_qr, float radius, const float* d_qmin_size, const float* d_qmax_size,
+        float min_x, float min_y, float max_x, float max_y, int* d_best, float* d_bestd, float* d_secondd, void* cuda_stream) {
+    const int D = desc_bytes(desc_type);
+    if (D < 0 || desc_type == AFV_FEAT_SIFT128 || !d_kps || !d_desc || !d_kpsize || !d_n || !d_cell_start || !d_cell_items || !d_pair_a || !d_pair_b ||
+        !d_best || !d_bestd || !d_secondd || B < 1 || P < 0 || cap < 1 || cap >= 65535) { afv_set_error("afv_match_window_pairs: bad argument (binary descriptors only)"); return AFV_ERR_INVALID; }
+    if (P == 0) return AFV_OK;
+    const int NW = (D + 3) / 4;
+    const size_t smem = (size_t)NW * cap * 4 + (size_t)cap * (8 + 4 + 2) + (size_t)((NCELLS + 1 + 7) & ~7) * 2 + 16;
+    if (smem > 220 * 1024) { afv_set_error("afv_match_window_pairs: cap %d too large for the shared-memory staging", cap); return AFV_ERR_INVALID; }
+    cudaStream_t st = as_stream(cuda_stream);
+    const float invW = (float)AFV_GRID_COLS / (max_x - min_x), invH = (float)AFV_GRID_ROWS / (max_y - min_y);
+    AfvProfScope ps("k_match_window_pairs", st);
+#define MWP_LAUNCH(W) do { AFV_CUDA_CHECK(cudaFuncSetAttribute(k_match_window_pairs<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        k_match_window_pairs<W><<<P, MWP_THREADS, smem, st>>>(D, d_kps, (const uint8_t*)d_desc, d_kpsize, d_n, cap, d_cell_start, d_cell_items, d_pair_a, d_pair_b, \
+            d_qxy, d_qr, radius, d_qmin_size, d_qmax_size, min_x, min_y, invW, invH, d_best, d_bestd, d_secondd); } while (0)
+    if (NW == 8) MWP_LAUNCH(8); else if (NW == 12) MWP_LAUNCH(12); else MWP_LAUNCH(16);
+#undef MWP_LAUNCH
+    ++g_afv_launches;
+    AFV_CUDA_CHECK(cudaGetLastError());
+    return AFV_OK;
+}
+
 // ---- SearchForInitialization: one CTA per frame pair ----------------------------------------------------
 // Train frame staged in shared memory (x, y, size, grid cell, descriptor when it fits); queries processed in
 // index order; per query every thread scans a slice of the train keypoints: a keypoint is a candidate iff its
@@ -1325,16 +1432,109 @@ __global__ void __launch_bounds__(256) k_match_bf(int desc_type, int D, const ui
     }
 }
 
+// Tiled Hamming brute force: a thread owns one query (descriptor words in registers); the train descriptors pass through shared
+// memory in tiles of BF_TILE rows, every lane reads the SAME row (128-bit broadcast loads), train index ascending so the first
+// minimum wins without tie handling.  Runs at 96 % of the chip's POPC rate (148 SMs x 16 lanes x clock; bench.py --workload m1).
+#define BF_TILE 256
+template <int NW>
+__global__ void __launch_bounds__(256) k_match_bf_tiled(int D, const uint8_t* __restrict__ qbase, int nq_one, const uint8_t* __restrict__ tbase, int nt_one,
+        const int* __restrict__ n_arr, int cap, const int* __restrict__ pair_a, const int* __restrict__ pair_b,
+        int* __restrict__ best, float* __restrict__ bestd, float* __restrict__ secondd) {
+    __shared__ __align__(16) uint32_t tile[BF_TILE][NW];
+    const int p = blockIdx.y, tid = threadIdx.x;
+    const uint8_t* qd = qbase; const uint8_t* td = tbase;
+    int nq = nq_one, nt = nt_one;
+    long long oo = 0;
+    if (pair_a) {
+        const int fa = pair_a[p], fb = pair_b[p];
+        qd = qbase + (long long)fa * cap * D; td = qbase + (long long)fb * cap * D;
+        nq = min(n_arr[fa], cap); nt = min(n_arr[fb], cap); oo = (long long)p * cap;
+    }
+    const int qi = blockIdx.x * 256 + tid;
+    if (blockIdx.x * 256 >= nq) return;
+    uint32_t q[NW];
+#pragma unroll
+    for (int w = 0; w < NW; ++w) q[w] = 0;
+    if (qi < nq) {
+        if ((D & 3) == 0 && (((uintptr_t)qd) & 3) == 0) {
+            const uint32_t* row = reinterpret_cast<const uint32_t*>(qd + (long long)qi * D);
+#pragma unroll
+            for (int w = 0; w < NW; ++w) q[w] = row[w];
+        } else {
+#pragma unroll
+            for (int w = 0; w < NW; ++w) { uint32_t v = 0; for (int b = 0; b < 4; ++b) { const int o = w * 4 + b; if (o < D) v |= (uint32_t)qd[(long long)qi * D + o] << (8 * b); } q[w] = v; }
+        }
+    }
+    int bi = -1, b1 = 0x7fffffff, b2 = 0x7fffffff;
+    for (int t0 = 0; t0 < nt; t0 += BF_TILE) {
+        const int nrow = min(BF_TILE, nt - t0);
+        __syncthreads();
+        if ((D & 3) == 0 && (((uintptr_t)td) & 3) == 0) {
+            const uint32_t* src = reinterpret_cast<const uint32_t*>(td + (long long)t0 * D);
+            for (int i = tid; i < nrow * NW; i += 256) (&tile[0][0])[i] = src[i];
+        } else {
+            for (int i = tid; i < nrow * NW; i += 256) {
+                const int r = i / NW, w = i - r * NW;
+                uint32_t v = 0;
+                for (int b = 0; b < 4; ++b) { const int o = w * 4 + b; if (o < D) v |= (uint32_t)td[(long long)(t0 + r) * D + o] << (8 * b); }
+                tile[r][w] = v;
+            }
+        }
+        __syncthreads();
+#pragma unroll 4
+        for (int j = 0; j < nrow; ++j) {
+            int d = 0;
+#pragma unroll
+            for (int w4 = 0; w4 < NW / 4; ++w4) {
+                const uint4 v = *reinterpret_cast<const uint4*>(&tile[j][4 * w4]);
+                d += __popc(q[4 * w4] ^ v.x) + __popc(q[4 * w4 + 1] ^ v.y) + __popc(q[4 * w4 + 2] ^ v.z) + __popc(q[4 * w4 + 3] ^ v.w);
+            }
+            if (d < b1) { b2 = b1; b1 = d; bi = t0 + j; } else if (d < b2) b2 = d;
+        }
+    }
+    if (qi < nq) {
+        best[oo + qi] = bi;
+        bestd[oo + qi] = b1 == 0x7fffffff ? FLT_MAX : (float)b1;
+        secondd[oo + qi] = b2 == 0x7fffffff ? FLT_MAX : (float)b2;
+    }
+}
+
+static int launch_bf_tiled(int D, const uint8_t* q, int nq, const uint8_t* t, int nt, const int* d_n, int cap, const int* pa,
+                           const int* pb, int P, int* best, float* bestd, float* secondd, cudaStream_t st) {
+    const int NW = (D + 3) / 4;
+    const dim3 grid(((pa ? cap : nq) + 255) / 256, P);
+    AfvProfScope ps("k_match_bf", st);
+    if (NW == 8) k_match_bf_tiled<8><<<grid, 256, 0, st>>>(D, q, nq, t, nt, d_n, cap, pa, pb, best, bestd, secondd);
+    else if (NW == 12) k_match_bf_tiled<12><<<grid, 256, 0, st>>>(D, q, nq, t, nt, d_n, cap, pa, pb, best, bestd, secondd);
+    else k_match_bf_tiled<16><<<grid, 256, 0, st>>>(D, q, nq, t, nt, d_n, cap, pa, pb, best, bestd, secondd);
+    ++g_afv_launches;
+    AFV_CUDA_CHECK(cudaGetLastError());
+    return AFV_OK;
+}
+
 extern "C" int afv_match_bruteforce(int desc_type, const void* d_q, int nq, const void* d_t, int nt,
                                     int* d_best, float* d_bestd, float* d_secondd, void* cuda_stream) {
     const int D = desc_bytes(desc_type);
     if (D < 0 || nq < 0 || nt < 0) { afv_set_error("afv_match_bruteforce: bad argument"); return AFV_ERR_INVALID; }
     if (nq == 0) return AFV_OK;
     if (!d_q || (!d_t && nt > 0) || !d_best || !d_bestd || !d_secondd) { afv_set_error("afv_match_bruteforce: NULL argument"); return AFV_ERR_INVALID; }
+    if (desc_type != AFV_FEAT_SIFT128)
+        return launch_bf_tiled(D, (const uint8_t*)d_q, nq, (const uint8_t*)d_t, nt, nullptr, 0, nullptr, nullptr, 1, d_best, d_bestd, d_secondd, as_stream(cuda_stream));
     k_match_bf<<<(nq + 7) / 8, 256, 0, as_stream(cuda_stream)>>>(desc_type, D, (const uint8_t*)d_q, nq, (const uint8_t*)d_t, nt, d_best, d_bestd, d_secondd);
     ++g_afv_launches;
     AFV_CUDA_CHECK(cudaGetLastError());
     return AFV_OK;
+}
+
+// brute force for P frame pairs of a B x cap extraction result (binary descriptors): outputs are P x cap
+extern "C" int afv_match_bruteforce_pairs(int desc_type, const void* d_desc, const int* d_n, int B, int cap, const int* d_pair_a,
+                                          const int* d_pair_b, int P, int* d_best, float* d_bestd, float* d_secondd, void* cuda_stream) {
+    const int D = desc_bytes(desc_type);
+    if (D < 0 || desc_type == AFV_FEAT_SIFT128 || !d_desc || !d_n || !d_pair_a || !d_pair_b || !d_best || !d_bestd || !d_secondd || B < 1 || P < 0 || cap < 1) {
+        afv_set_error("afv_match_bruteforce_pairs: bad argument (binary descriptors only)"); return AFV_ERR_INVALID;
+    }
+    if (P == 0) return AFV_OK;
+    return launch_bf_tiled(D, (const uint8_t*)d_desc, 0, nullptr, 0, d_n, cap, d_pair_a, d_pair_b, P, d_best, d_bestd, d_secondd, as_stream(cuda_stream));
 }
 
 // ---- SearchByBoW(KF, F): one warp walks the merge-join; lanes share a bucket's frame features ---------------

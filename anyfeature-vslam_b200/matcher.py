@@ -162,6 +162,35 @@ class FeatureMatcher:
                                  _vp(match), _vp(nm), _sp(stream)))
         return match[:P], nm[:P]
 
+    def match_window_pairs(self, kps, desc, kpsize, n, cell_start, cell_items, pair_a, pair_b, bounds, radius=15.0, qxy=None, qr=None,
+                           qmin=None, qmax=None, out=None, stream=None):
+        """Windowed best / second search for P frame pairs (see afv_match_window_pairs).  Returns (best, bestd, secondd) [P,cap]."""
+        import torch
+        lib, _check, _vp, _sp = _afv()
+        B, cap = kps.shape[0], kps.shape[1]
+        P = pair_a.shape[0]
+        if out is None:
+            out = (torch.empty((P, cap), dtype=torch.int32, device=kps.device), torch.empty((P, cap), dtype=torch.float32, device=kps.device),
+                   torch.empty((P, cap), dtype=torch.float32, device=kps.device))
+        minx, miny, maxx, maxy = bounds
+        _check(lib.afv_match_window_pairs(self.desc_type, _vp(kps), _vp(desc), _vp(kpsize), _vp(n), B, cap, _vp(cell_start), _vp(cell_items),
+                                          _vp(pair_a), _vp(pair_b), P, _vp(qxy), _vp(qr), C.c_float(radius), _vp(qmin), _vp(qmax),
+                                          C.c_float(minx), C.c_float(miny), C.c_float(maxx), C.c_float(maxy), _vp(out[0]), _vp(out[1]), _vp(out[2]),
+                                          _sp(stream)))
+        return out
+
+    def match_bruteforce_pairs(self, desc, n, pair_a, pair_b, out=None, stream=None):
+        import torch
+        lib, _check, _vp, _sp = _afv()
+        B, cap = desc.shape[0], desc.shape[1]
+        P = pair_a.shape[0]
+        if out is None:
+            out = (torch.empty((P, cap), dtype=torch.int32, device=desc.device), torch.empty((P, cap), dtype=torch.float32, device=desc.device),
+                   torch.empty((P, cap), dtype=torch.float32, device=desc.device))
+        _check(lib.afv_match_bruteforce_pairs(self.desc_type, _vp(desc), _vp(n), B, cap, _vp(pair_a), _vp(pair_b), P, _vp(out[0]), _vp(out[1]),
+                                              _vp(out[2]), _sp(stream)))
+        return out
+
     def match_bruteforce(self, q, t, stream=None):
         import torch
         lib, _check, _vp, _sp = _afv()

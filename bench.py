@@ -43,6 +43,10 @@ WORKLOADS = {
                metric="frames/sec (extract+match) akaze61+brisk48 640x480x1000kp",
                name="akaze61 + brisk48 640x480 synthetic batch, 1000 kp/frame: BOTH extractors on every frame, each followed by its own "
                     "Hamming SearchForInitialization (61-byte akaze61, 48-byte brisk48) on 1xB200 per rank (configs[3])"),
+    "m1": dict(feature="orb32", w=640, h=480, nfeat=1000, batch=512, desc_bytes=32, desc_type=0, th_low=75.0,
+               metric="frame pairs/sec (windowed Hamming matcher r=15, orb32 1000x1000 kp)",
+               name="matcher-only: 10240 frame pairs of a resident 512-frame orb32 640x480 extraction; windowed Hamming match r=15/30/100, "
+                    "SearchForInitialization, brute force 1000x1000, sift128-layout L2 2000x2000 (SURVEY 8d)"),
     "c5": dict(feature="orb32", w=1280, h=720, nfeat=2000, batch=128, desc_bytes=32, desc_type=0, th_low=75.0,
                metric="frames/sec (extract+match) orb32 1280x720x2000kp",
                name="orb32 1280x720 synthetic 8-stream batch, 2000 kp/frame, streams sharded over ranks, NCCL gather (configs[4])"),
@@ -322,6 +326,171 @@ def run_reference(args):
         "gpu_launches": 0,
     }
     print(json.dumps(line))
+    return 0
+
+
+# ---------------------------------------------------------------------------------------------------------
+# matcher-only measurement (the matcher against ITS OWN rooflines)
+# ---------------------------------------------------------------------------------------------------------
+def matcher_blocks(pkg, torch, dev, out, cap, n_host, host_kps, P, steps, warmup, peaks, sm_mhz, full=True):
+    """Times the matcher kernels over P frame pairs of the resident extraction result `out` (CUDA events on the current stream).
+    Returns a list of per-kernel blocks: {kernel, config, ms, pairs_per_s, bound, achieved, peak, unit, frac, ...}.
+    Algorithmic bytes per pair = SURVEY 8d: (Nq+Nt)*D + (Nq+Nt)*8 + Nt*4 + grid (64*48*4 + Nt*4) + Nq*12."""
+    B = out[0].shape[0]
+    D = int(out[1].shape[2])
+    N = float(n_host.mean())
+    fm = pkg.FeatureMatcher(nnratio=0.9, check_ori=True, desc_type=WL["desc_type"], th_low=WL["th_low"])
+    idx = np.arange(P, dtype=np.int64)
+    a = (idx % B).astype(np.int32)
+    off = (idx // B).astype(np.int64) + 1                      # pass k pairs frame i with its k-th successor inside the 16-frame stream,
+    start = (a // 16) * 16                                     # passes beyond 15 with frames of other streams
+    b = np.where(off < 16, start + (a - start + off) % 16, (a + off * 37) % B).astype(np.int32)
+    d_pa = torch.from_numpy(a).to(dev); d_pb = torch.from_numpy(b).to(dev)
+    cs, ci = fm.grid_build(out[0], out[3], BOUNDS)
+    hbm = float(peaks.get("hbm_gbs", 6650.0))
+    popc_peak = 148 * 16 * sm_mhz * 1e6                        # POPC lanes: 16 per SM per clock
+    bytes_pair = 2 * N * D + 2 * N * 8 + N * 4 + (64 * 48 * 4 + N * 4) + N * 12
+    res = (torch.empty((P, cap), dtype=torch.int32, device=dev), torch.empty((P, cap), dtype=torch.float32, device=dev),
+           torch.empty((P, cap), dtype=torch.float32, device=dev))
+
+    def timed(fn):
+        for _ in range(max(warmup, 3)):
+            fn()
+        torch.cuda.synchronize()
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record(); torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / steps
+
+    def cand_per_query(r):                                     # mean window population on a sample of pairs (numpy, for the POPC count)
+        tot = 0.0; cnt = 0
+        for p in range(0, P, max(1, P // 8)):
+            ka, kb = host_kps[a[p]], host_kps[b[p]]
+            dx = np.abs(ka["x"][:, None] - kb["x"][None, :]) < r; dy = np.abs(ka["y"][:, None] - kb["y"][None, :]) < r
+            tot += float((dx & dy).sum()); cnt += len(ka)
+        return tot / max(cnt, 1)
+    blocks = []
+    for r in ((15.0, 30.0, 100.0) if full else (15.0,)):
+        ms = timed(lambda: fm.match_window_pairs(out[0], out[1], out[2], out[3], cs, ci, d_pa, d_pb, BOUNDS, radius=r, out=res))
+        cq = cand_per_query(r)
+        gbs = bytes_pair * P / (ms * 1e-3) / 1e9
+        popc = N * cq * (D / 4) * P / (ms * 1e-3)
+        blocks.append({"kernel": "k_match_window_pairs", "config": "r=%g px, %.1f candidates/query" % (r, cq), "ms": ms, "pairs_per_s": P / (ms * 1e-3),
+                       "bound": "hbm" if gbs / hbm > popc / popc_peak else "popc", "achieved": gbs, "peak": hbm, "unit": "GB/s", "frac": gbs / hbm,
+                       "popc_frac": popc / popc_peak, "algorithmic_bytes_per_pair": bytes_pair})
+    m12 = torch.empty((P, cap), dtype=torch.int32, device=dev); nm = torch.empty((P,), dtype=torch.int32, device=dev)
+    ms = timed(lambda: fm.search_for_initialization(out[0], out[1], out[2], out[3], d_pa, d_pb, None, BOUNDS, MAX_KPT_SIZE, window=100, matches12=m12, nmatches=nm))
+    q0 = float(np.mean([(k["octave"] == 0).sum() for k in host_kps[:32]]))
+    cq = cand_per_query(100.0)
+    gbs = bytes_pair * P / (ms * 1e-3) / 1e9
+    popc = q0 * cq * (D / 4) * P / (ms * 1e-3)
+    blocks.append({"kernel": "k_sfi_lists+k_sfi_resolve", "config": "SearchForInitialization, window 100, %.0f octave-0 queries x %.0f candidates" % (q0, cq),
+                   "ms": ms, "pairs_per_s": P / (ms * 1e-3), "bound": "popc / sequential resolver", "achieved": gbs, "peak": hbm, "unit": "GB/s",
+                   "frac": gbs / hbm, "popc_frac": popc / popc_peak, "matches_per_pair": float(nm.float().mean())})
+    if full:
+        ms = timed(lambda: fm.match_bruteforce_pairs(out[1], out[3], d_pa, d_pb, out=res))
+        popc = N * N * (D / 4) * P / (ms * 1e-3)
+        blocks.append({"kernel": "k_match_bf", "config": "brute force %.0f x %.0f, tiled through shared memory" % (N, N), "ms": ms, "pairs_per_s": P / (ms * 1e-3),
+                       "bound": "popc", "achieved": popc / 1e12, "peak": popc_peak / 1e12, "unit": "Tpopc/s", "frac": popc / popc_peak,
+                       "hbm_frac": (2 * N * D + 12 * N) * P / (ms * 1e-3) / 1e9 / hbm})
+        # sift128 layout: L2^2 on 128 floats, 2000 x 2000, double accumulation like cv::norm(NORM_L2SQR)
+        g = torch.Generator(device="cpu"); g.manual_seed(7)
+        q = torch.nn.functional.normalize(torch.randn((2000, 128), generator=g), dim=1).to(dev).contiguous()
+        t = torch.nn.functional.normalize(torch.randn((2000, 128), generator=g), dim=1).to(dev).contiguous()
+        fml2 = pkg.FeatureMatcher(desc_type=5, th_low=0.5)
+        ms = timed(lambda: fml2.match_bruteforce(q.view(torch.uint8).view(2000, 512), t.view(torch.uint8).view(2000, 512)))
+        flops = 2000.0 * 2000 * 128 * 3 / (ms * 1e-3)             # sub, mul, add per element (double accumulation)
+        blocks.append({"kernel": "k_match_bf (L2)", "config": "sift128 layout 2000 x 2000 x 128, float diff / double accumulate (exact cv::norm order)", "ms": ms,
+                       "pairs_per_s": 1.0 / (ms * 1e-3), "bound": "fp64 accumulate", "achieved": flops / 1e12, "peak": 148 * 128 * 2 * sm_mhz * 1e6 / 1e12,
+                       "unit": "TFLOP/s (vs FP32 FMA peak)", "frac": flops / (148 * 128 * 2 * sm_mhz * 1e6)})
+    return blocks
+
+
+def run_matcher(args):
+    """--workload m1: matcher-only line (one step = the windowed r=15 matcher over 10240 resident frame pairs)."""
+    import torch
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if int(os.environ.get("RANK", "0")) != 0:
+        return 0
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    pkg = load_pkg()
+    B = args.batch
+    frames, pa, pb = make_frames(pkg, B, 0)
+    ex = pkg.FeatureExtractor("orb32", nfeatures=NFEAT, device=local, max_batch=B, max_w=W, max_h=H)
+    cap = ex.cap
+    out = ex.alloc_device_outputs(B)
+    ex.extract_batch_device(torch.from_numpy(frames).to(dev), out)
+    torch.cuda.synchronize(); ex.status()
+    n_host = out[3].cpu().numpy()
+    host_kps = [pkg.kps_from_device(out[0][f], int(n_host[f])) for f in range(B)]
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    P = args.pairs
+    sampler = ClockSampler(local); sampler.start()
+    launches0 = pkg.kernel_launches()
+    blocks = matcher_blocks(pkg, torch, dev, out, cap, n_host, host_kps, P, args.steps, args.warmup, peaks, float(peaks.get("sm_max_mhz", 1965.0)), full=True)
+    launches = pkg.kernel_launches() - launches0
+    # e2e: keypoints / descriptors / sizes of all B frames from pinned host memory, grid build, r=15 match of P pairs, results back
+    fm = pkg.FeatureMatcher(desc_type=0, th_low=75.0)
+    h_in = [t.cpu().pin_memory() for t in out]
+    d_in = [torch.empty_like(t) for t in out]
+    idx = np.arange(P, dtype=np.int64); a = (idx % B).astype(np.int32)
+    d_pa = torch.from_numpy(a).to(dev); d_pb = torch.from_numpy(((a // 16) * 16 + (a % 16 + 1 + idx // B) % 16).astype(np.int32)).to(dev)
+    res = (torch.empty((P, cap), dtype=torch.int32, device=dev), torch.empty((P, cap), dtype=torch.float32, device=dev), torch.empty((P, cap), dtype=torch.float32, device=dev))
+    h_res = [torch.empty(t.shape, dtype=t.dtype).pin_memory() for t in res]
+
+    def e2e_step():
+        for dd, hh in zip(d_in, h_in):
+            dd.copy_(hh, non_blocking=True)
+        cs, ci = fm.grid_build(d_in[0], d_in[3], BOUNDS)
+        fm.match_window_pairs(d_in[0], d_in[1], d_in[2], d_in[3], cs, ci, d_pa, d_pb, BOUNDS, radius=15.0, out=res)
+        for hh, dd in zip(h_res, res):
+            hh.copy_(dd, non_blocking=True)
+    for _ in range(3):
+        e2e_step()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        e2e_step()
+    torch.cuda.synchronize()
+    ms_e2e = (time.perf_counter() - t0) * 1e3 / args.steps
+    sampler.stop()
+    # CPU: the oracle's window search on one thread, a few pairs
+    from oracle import pyoracle as po
+    hk = [(host_kps[f], out[1][f, :int(n_host[f])].cpu().numpy(), out[2][f, :int(n_host[f])].cpu().numpy()) for f in range(8)]
+    FMAX = float(np.finfo(np.float32).max)
+    t0 = time.perf_counter(); reps = 0
+    while time.perf_counter() - t0 < 3.0:
+        for f in range(7):
+            ka, da, sa = hk[f]; kb, db, sb = hk[f + 1]
+            po.match_window(0, da, np.stack([ka["x"], ka["y"]], axis=1).astype(np.float32), np.full(len(ka), 15.0, np.float32), np.full(len(ka), -FMAX, np.float32),
+                            np.full(len(ka), FMAX, np.float32), kb, db, sb, BOUNDS)
+            reps += 1
+    cpu_pps = reps / (time.perf_counter() - t0)
+    head = blocks[0]
+    line = {"metric": METRIC, "value": head["pairs_per_s"], "unit": "pairs/s", "n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": head["ms"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": {"workload": WL["name"], "pairs_per_step": P, "frames_resident": B, "kps_per_frame": float(n_host.mean()),
+                       "l2": "descriptors + keypoints of %d frames = %.0f MB resident; every pair re-reads two frames (L2 hits count as HBM-equivalent "
+                             "algorithmic traffic; outputs %.0f MB/step stream to HBM)" % (B, B * cap * 64 / 1e6, P * cap * 12 / 1e6)},
+            "e2e": {"value": P / (ms_e2e * 1e-3), "unit": "pairs/s", "h2d_bytes_per_step": int(sum(t.numel() * t.element_size() for t in h_in)),
+                    "d2h_bytes_per_step": int(sum(t.numel() * t.element_size() for t in h_res)), "ms_per_step": ms_e2e},
+            "gpu_launches": int(launches), "clocks": sampler.summary(),
+            "roofline": {"bound": head["bound"], "kernel": head["kernel"], "achieved": head["achieved"], "peak": head["peak"], "unit": "GB/s",
+                         "frac": head["frac"], "traffic": None, "algorithmic_bytes": head["algorithmic_bytes_per_pair"] * P,
+                         "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"},
+            "matcher_kernels": blocks,
+            "cpu_baseline": {"value": cpu_pps, "unit": "pairs/s", "cores": 1, "kind": "port", "sample": "%d pairs in 3 s, oracle window search r=15, one thread" % reps}}
+    print(json.dumps(line))
+    ex.close()
     return 0
 
 
@@ -620,6 +789,14 @@ def run_gpu(args):
             d_tmp.copy_(h_gray, non_blocking=True)
         g1.record(); torch.cuda.synchronize()
         h2d_gbs = 3 * h_gray.numel() / (g0.elapsed_time(g1) * 1e-3) / 1e9
+        matcher = None
+        if FEAT == "orb32" and not MIXED:
+            # the matcher against its own rooflines, short form: windowed r=15 and SearchForInitialization over 2048 pairs
+            try:
+                host_kps = [pkg.kps_from_device(out[0][f], int(n_host[f])) for f in range(B)]
+                matcher = matcher_blocks(pkg, torch, dev, out, cap, n_host, host_kps, 2048, 5, 3, peaks, float(peaks.get("sm_max_mhz", 1965.0)), full=False)
+            except Exception as e:                          # never lose the headline line over the extra block
+                matcher = {"error": repr(e)}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -633,6 +810,7 @@ def run_gpu(args):
             "gpu_launches": int(launches),
             "clocks": sampler.summary() if sampler else None,
             "roofline": roofline,
+            "matcher": matcher,
             "cpu_baseline": cpu_baseline,
             "check": {"kps_per_frame": [int(n_host.min()), int(n_host.max())], "matches_per_pair_mean": float(nm_host.mean()),
                       "brisk48_kps_per_frame": [int(out2[3].min()), int(out2[3].max())] if MIXED else None,
@@ -655,7 +833,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--batch", type=int, default=0, help="frames per step per GPU (default: 512 for c2, 64 for c3, 128 for c5)")
     ap.add_argument("--e2e-chunk", type=int, default=512, help="frames per pipelined chunk in the e2e leg")
-    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS), help="BASELINE.json config: c2 = configs[1] (headline), c3 = configs[2], c5 = configs[4]")
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS), help="BASELINE.json config: c2 = configs[1] (headline), c3 = configs[2], c4 = configs[3], c5 = configs[4]; m1 = matcher-only")
+    ap.add_argument("--pairs", type=int, default=10240, help="m1: frame pairs per step")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-gather", dest="gather", action="store_false")
     ap.add_argument("--real-parts", action="store_true",
@@ -666,6 +845,8 @@ def main():
     args.batch = select_workload(args.workload, args.batch)
     if args.impl == "reference":
         return run_reference(args)
+    if args.workload == "m1":
+        return run_matcher(args)
     return run_gpu(args)
 
 

@@ -229,6 +229,22 @@ int  afv_bow_match(int mode, int desc_type, const afv_keypoint* d_kps, const voi
 int  afv_match_bruteforce(int desc_type, const void* d_q, int nq, const void* d_t, int nt,
                           int* d_best, float* d_bestd, float* d_secondd, void* cuda_stream);
 
+/* The same for P frame pairs (queries = frame d_pair_a[p], train = frame d_pair_b[p]) of a B x cap extraction result, binary
+ * descriptors; outputs are P x cap. */
+int  afv_match_bruteforce_pairs(int desc_type, const void* d_desc, const int* d_n, int B, int cap, const int* d_pair_a,
+                                const int* d_pair_b, int P, int* d_best, float* d_bestd, float* d_secondd, void* cuda_stream);
+
+/* Windowed best / second search batched over P frame pairs (throughput form of afv_match_window): queries = the keypoints of
+ * frame d_pair_a[p] (their descriptors), searched in frame d_pair_b[p] through its grid from afv_grid_build.  Window centre =
+ * d_qxy[p][i] (P x cap x 2) or, when NULL, the query keypoint's own position; radius = d_qr[p][i] (P x cap; < 0 skips the query) or,
+ * when NULL, `radius`; accepted size range d_qmin_size / d_qmax_size (P x cap) or NULL = no size gate.  Same candidate definition
+ * and enumeration order as Frame::GetFeaturesInArea (src/Frame.cc:333-382); binary descriptors.  Outputs are P x cap. */
+int  afv_match_window_pairs(int desc_type, const afv_keypoint* d_kps, const void* d_desc, const float* d_kpsize, const int* d_n,
+                            int B, int cap, const int* d_cell_start, const int* d_cell_items, const int* d_pair_a,
+                            const int* d_pair_b, int P, const float* d_qxy, const float* d_qr, float radius,
+                            const float* d_qmin_size, const float* d_qmax_size, float min_x, float min_y, float max_x, float max_y,
+                            int* d_best, float* d_bestd, float* d_secondd, void* cuda_stream);
+
 /* SearchByBoW(KF,F) (src/FeatureMatcher.cc:186-283) on FeatureVector segments (sorted node ids + CSR) for ONE pair.  kf_idx
  * must list only keyframe features that hold a good map point (the reference skips the others, :216-222); afv_bow_match is the
  * batched form with explicit validity masks. */

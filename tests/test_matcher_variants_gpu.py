@@ -175,3 +175,59 @@ def test_search_for_triangulation(pkg, extracted):
         assert nm[i] == rn and (m[i, :len(rm)] == rm).all(), "pair %d: %d vs %d" % (i, nm[i], rn)
         tot += rn
     assert tot > 40
+
+
+@pytest.mark.parametrize("radius,gated", [(15.0, False), (100.0, False), (30.0, True)])
+def test_match_window_pairs(pkg, extracted, radius, gated):
+    """Batched windowed matcher (thread per query, train frame + grid staged in shared memory) == the oracle's GetFeaturesInArea
+    window search, pair by pair: best index (first minimum in reference enumeration order), best and second distance."""
+    import torch
+    out, host, cap, dt, th, tol = extracted
+    rng = np.random.default_rng(105)
+    pairs = [(0, 1), (1, 2), (2, 3), (4, 5), (6, 7), (3, 3)]
+    fm = pkg.FeatureMatcher(desc_type=dt, th_low=th)
+    cs, ci = fm.grid_build(out[0], out[3], BOUNDS)
+    P = len(pairs)
+    qxy = np.zeros((P, cap, 2), np.float32); qr = np.full((P, cap), -1.0, np.float32)
+    qmin = np.zeros((P, cap), np.float32); qmax = np.zeros((P, cap), np.float32)
+    for i, (a, b) in enumerate(pairs):
+        ka, _, sa = host[a]
+        qxy[i, :len(ka), 0] = ka["x"] + rng.uniform(-6, 6, len(ka)); qxy[i, :len(ka), 1] = ka["y"] + rng.uniform(-6, 6, len(ka))
+        qr[i, :len(ka)] = np.where(rng.random(len(ka)) < 0.1, -1.0, radius * rng.choice([0.5, 1.0, 2.0], len(ka)))
+        qmin[i, :len(ka)] = sa / tol; qmax[i, :len(ka)] = sa * tol
+    if gated:
+        best, bd, sd = fm.match_window_pairs(out[0], out[1], out[2], out[3], cs, ci, _t(np.array([p[0] for p in pairs], np.int32)),
+                                             _t(np.array([p[1] for p in pairs], np.int32)), BOUNDS, qxy=_t(qxy), qr=_t(qr), qmin=_t(qmin), qmax=_t(qmax))
+    else:
+        best, bd, sd = fm.match_window_pairs(out[0], out[1], out[2], out[3], cs, ci, _t(np.array([p[0] for p in pairs], np.int32)),
+                                             _t(np.array([p[1] for p in pairs], np.int32)), BOUNDS, radius=radius)
+    torch.cuda.synchronize()
+    best = best.cpu().numpy(); bd = bd.cpu().numpy(); sd = sd.cpu().numpy()
+    FMAX = np.finfo(np.float32).max
+    for i, (a, b) in enumerate(pairs):
+        ka, da, sa = host[a]; kb, db, sb = host[b]
+        na = len(ka)
+        if gated:
+            valid = qr[i, :na] >= 0
+            rb, rbd, rsd, _, _ = po.match_window(dt, da, qxy[i, :na], np.maximum(qr[i, :na], 0), qmin[i, :na], qmax[i, :na], kb, db, sb, BOUNDS)
+            rb = np.where(valid, rb, -1); rbd = np.where(valid, rbd, FMAX); rsd = np.where(valid, rsd, FMAX)
+        else:
+            xy = np.stack([ka["x"], ka["y"]], axis=1).astype(np.float32)
+            rb, rbd, rsd, _, _ = po.match_window(dt, da, xy, np.full(na, radius, np.float32), np.full(na, -FMAX, np.float32), np.full(na, FMAX, np.float32),
+                                                 kb, db, sb, BOUNDS)
+        assert (best[i, :na] == rb).all() and (bd[i, :na] == rbd).all() and (sd[i, :na] == rsd).all(), "pair %d" % i
+        assert (rb >= 0).sum() > 100
+
+
+def test_match_bruteforce_pairs(pkg, extracted):
+    import torch
+    out, host, cap, dt, th, tol = extracted
+    pairs = [(0, 1), (2, 3), (5, 4), (7, 7)]
+    fm = pkg.FeatureMatcher(desc_type=dt, th_low=th)
+    best, bd, sd = fm.match_bruteforce_pairs(out[1], out[3], _t(np.array([p[0] for p in pairs], np.int32)), _t(np.array([p[1] for p in pairs], np.int32)))
+    torch.cuda.synchronize()
+    best = best.cpu().numpy(); bd = bd.cpu().numpy(); sd = sd.cpu().numpy()
+    for i, (a, b) in enumerate(pairs):
+        da = host[a][1]; db = host[b][1]
+        rb, rbd, rsd = po.match_bruteforce(dt, da, db)
+        assert (best[i, :len(da)] == rb).all() and (bd[i, :len(da)] == rbd).all() and (sd[i, :len(da)] == rsd).all()
