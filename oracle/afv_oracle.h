@@ -213,6 +213,17 @@ int   orc_brisk48_extract(const uint8_t* gray, int w, int h, int stride, int nfe
                           float detect_th, int mode, orc_keypoint* kps, uint8_t* desc, float* kpsize, int cap, int* n_out,
                           int* n_detected);
 
+/* ---- vanilla ORB-SLAM2 extractor (afv_oracle_orbslam2.c; reference src/ORBextractor.cc:460-676 built with VANILLA_ORB_SLAM2):
+ * control flow checked against the reference's compiled code, OpenCV stages pinned to cv2 4.13.0 ---------------------------- */
+void  orc_resize_linear_u8(const uint8_t* src, int sw, int sh, int sstride, uint8_t* dst, int dw, int dh, int dstride);
+void  orc_gaussblur7_fixed_u8(const uint8_t* img, int w, int h, int stride, uint8_t* out, int ostride);
+int   orc_orbslam2_geometry(int w, int h, int nlevels, float scale_factor, int* lw, int* lh, float* sf, float* isf);
+int   orc_orbslam2_detect_level(const uint8_t* img, int cols, int rows, int stride, int ini_th, int min_th,
+                                int* xs, int* ys, int* scores, int cap);
+void  orc_orbslam2_descriptor(const uint8_t* blur, int stride, int cx, int cy, float angle_deg, uint8_t* desc32);
+int   orc_orbslam2_extract(const uint8_t* gray, int w, int h, int stride, int nfeatures, int nlevels, float scale_factor,
+                           int ini_th, int min_th, orc_keypoint* kps, uint8_t* desc, float* kpsize, int cap, int* n_out);
+
 #ifdef __cplusplus
 }
 #endif

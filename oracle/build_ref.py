@@ -87,6 +87,7 @@ Descriptor_Distance_Type FeatureMatcher::TH_HIGH = 0, FeatureMatcher::TH_LOW = 0
 float FeatureMatcher::radiusScale = 1.0f;
 float FeatureExtractorSettings::scaleFactor0 = 1.2f;
 }
+cv::VanillaCallbacks cv::g_vanilla = {nullptr, nullptr, nullptr, nullptr};
 std::vector<cv::KeyPoint>* cv::ORB::g_detect = nullptr;
 void (*cv::ORB::g_compute)(const cv::KeyPoint*, int, unsigned char*) = nullptr;
 int cv::ORB::g_last[4] = {0, 0, 0, 0};
@@ -558,6 +559,37 @@ int ref_search_for_triangulation(int desc_type, int dcols, int dtype, const kp7*
     for (auto& pr : pairs) match12[pr.first] = (int)pr.second;
     return nm;
 }
+// vanilla ORB-SLAM2 FeatureExtractor::operator()(..., vanillaOrbslam) (src/ORBextractor.cc:568-645) on one gray frame; the OpenCV
+// functions it calls (FAST, resize INTER_LINEAR, GaussianBlur, fastAtan2) are the harness callbacks (the tests pass cv2's real ones)
+int ref_orbslam2_extract(const unsigned char* gray, int w, int h, int nfeatures, int nlevels, float scale_factor, int ini_th, int min_th,
+                         int (*fast_cb)(const unsigned char*, int, int, int, int, float*, int),
+                         void (*resize_cb)(const unsigned char*, int, int, int, unsigned char*, int, int, int),
+                         void (*blur_cb)(unsigned char*, int, int, int), float (*atan2_cb)(float, float),
+                         kp7* okps, unsigned char* odesc, float* osize, int cap) {
+    if (g_bump) arena_reset();
+    cv::g_vanilla.fast = fast_cb; cv::g_vanilla.resize = resize_cb; cv::g_vanilla.blur = blur_cb; cv::g_vanilla.atan2 = atan2_cb;
+    std::shared_ptr<FeatureExtractorSettings> st = std::make_shared<FeatureExtractorSettings>();
+    st->scaleFactor = scale_factor; st->nOctaves = nlevels; FeatureExtractorSettings::scaleFactor0 = scale_factor;
+    st->iniThFAST = ini_th; st->minThFAST = min_th; st->detectTh = (float)ini_th;
+    st->maxKeyPtSize0 = pow(1.2f, float(8 - 1.0)); st->maxKeyPtSize = st->maxKeyPtSize0; st->minKeyPtSize = 1.0f;      // src/FeatureExtractor.cpp:52-55
+    int m = 0;
+    {
+        FeatureExtractor fe;
+        fe.initVanilla(nfeatures, st);
+        Image img; img.grayImg = cv::Mat(h, w, CV_8U, (void*)gray);
+        std::vector<cv::KeyPoint> k; cv::Mat d; std::vector<float> sz; std::vector<mat2f> s2, inf;
+        fe(img, k, d, s2, inf, sz, true);
+        // second call: computeSize then sees the settings' maxKeyPtSize / minKeyPtSize as the first frame left them (steady state)
+        fe(img, k, d, s2, inf, sz, true);
+        m = (int)k.size();
+        for (int i = 0; i < m && i < cap; ++i) {
+            okps[i].x = k[i].pt.x; okps[i].y = k[i].pt.y; okps[i].size = k[i].size; okps[i].angle = k[i].angle; okps[i].response = k[i].response;
+            okps[i].octave = k[i].octave; okps[i].class_id = k[i].class_id; osize[i] = sz[i];
+            memcpy(odesc + (size_t)i * 32, d.data + (size_t)i * d.step, 32);
+        }
+    }
+    return m;
+}
 float ref_descriptor_distance(int desc_type, int dcols, int dtype, void* a, void* b) {
     return FeatureMatcher::DescriptorDistance(cv::Mat(1, dcols, dtype, a), cv::Mat(1, dcols, dtype, b), (DescriptorType)desc_type);
 }
@@ -605,7 +637,19 @@ def build(force=False):
     parts.append(cut("src/FeatureMatcher.cc", r"^\s*void FeatureMatcher::updateRotationHistogram\("))
     parts.append(cut("src/FeatureMatcher.cc", r"^\s*void FeatureMatcher::filterMatchesWithOrientation\(", all_matches=True))
     parts.append(cut("src/FeatureMatcher.cc", r"^\s*void FeatureMatcher::computeThreeMaxima\("))
+    # ---- vanilla ORB-SLAM2 extractor: src/ORBextractor.cc:79-177 and :460-676 as built with VANILLA_ORB_SLAM2.  The
+    # constructor is cut and turned into a member function (the shim's class already has the default build's constructor).
+    ctor = cut("src/ORBextractor.cc", r"^\s*FeatureExtractor::FeatureExtractor\(const int& nfeatures_, shared_ptr<FeatureExtractorSettings>& settings_\):\s*\n\s*nfeatures\(nfeatures_\), settings\(settings_\)")
+    body = ctor[ctor.index("{") + 1:]
+    parts.append("void FeatureExtractor::initVanilla(const int& nfeatures_, shared_ptr<FeatureExtractorSettings>& settings_)\n{\n    nfeatures = nfeatures_; settings = settings_;" + body)
+    parts.append(cut("src/ORBextractor.cc", r"^static float IC_Angle\("))
+    parts.append(cut("src/ORBextractor.cc", r"^static void computeOrientation\("))
+    parts.append(cut("src/ORBextractor.cc", r"^void FeatureExtractor::ComputeKeyPointsOctTree\("))
+    parts.append(cut("src/ORBextractor.cc", r"^static void computeDescriptorsORB\("))
+    parts.append(cut("src/ORBextractor.cc", r"^void FeatureExtractor::operator\(\)\(const Image & img, vector<KeyPoint>& _keypoints, OutputArray _descriptors,"))
+    parts.append(cut("src/ORBextractor.cc", r"^void FeatureExtractor::ComputePyramid\("))
     parts.append("}  // namespace ANYFEATURE_VSLAM")
+    parts.append(cut("src/FeatureExtractor.cpp", r"^void ANYFEATURE_VSLAM::FeatureExtractor::computeSigma\("))
     # ---- the reference-side glue of the sift128 / akaze61 extractors (everything around the un-vendored third-party library)
     parts.append(cut("src/FeatureExtractor.cpp", r"^void ANYFEATURE_VSLAM::FeatureExtractor::filterKeypoints_notScaled\("))
     parts.append(cut("src/FeatureExtractor.cpp", r"^void ANYFEATURE_VSLAM::FeatureExtractor::mergeKeypointLevels\("))

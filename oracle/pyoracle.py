@@ -20,7 +20,7 @@ DESC_ORB, DESC_AKAZE61, DESC_BRISK, DESC_SIFT128 = 0, 1, 2, 5      # include/Typ
 
 def build(force=False):
     so = os.path.join(_DIR, "libafv_oracle.so")
-    srcs = [os.path.join(_DIR, f) for f in ("afv_oracle.c", "afv_oracle_match.c", "afv_oracle_sift.c", "afv_oracle_akaze.c", "afv_oracle_brisk.c", "afv_oracle_batch.c", "afv_oracle.h", "orb_pattern.inc")]
+    srcs = [os.path.join(_DIR, f) for f in ("afv_oracle.c", "afv_oracle_match.c", "afv_oracle_sift.c", "afv_oracle_akaze.c", "afv_oracle_brisk.c", "afv_oracle_orbslam2.c", "afv_oracle_batch.c", "afv_oracle.h", "orb_pattern.inc")]
     if force or not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
         subprocess.check_call(["make", "-s", "-C", _DIR, "libafv_oracle.so"])
     return so
@@ -482,3 +482,57 @@ def bow_match(mode, desc_type, k1, d1, node1, valid1, k2, d2, node2, valid2, th_
                             None if v2 is None else _p(v2), len(k2), _f(th_low), _f(nnratio), int(bool(check_ori)), _p(F), _f(epipole[0]),
                             _f(epipole[1]), _p(s2), _p(out))
     return n, out[:nout].copy()
+
+
+# ---- vanilla ORB-SLAM2 extractor (src/ORBextractor.cc:460-676 built with VANILLA_ORB_SLAM2) --------------------------------
+def resize_linear(img, dw, dh):
+    img = np.ascontiguousarray(img, np.uint8)
+    h, w = img.shape
+    out = np.zeros((dh, dw), np.uint8)
+    lib().orc_resize_linear_u8(_p(img), w, h, w, _p(out), dw, dh, dw)
+    return out
+
+
+def gaussblur7_fixed(img):
+    img = np.ascontiguousarray(img, np.uint8)
+    h, w = img.shape
+    out = np.zeros_like(img)
+    lib().orc_gaussblur7_fixed_u8(_p(img), w, h, w, _p(out), w)
+    return out
+
+
+def orbslam2_geometry(w, h, nlevels=8, sf=1.2):
+    lw = np.zeros(nlevels, np.int32); lh = np.zeros(nlevels, np.int32)
+    s = np.zeros(nlevels, np.float32); i = np.zeros(nlevels, np.float32)
+    assert lib().orc_orbslam2_geometry(w, h, nlevels, _f(sf), _p(lw), _p(lh), _p(s), _p(i)) == 0
+    return lw, lh, s, i
+
+
+def orbslam2_pyramid(gray, nlevels=8, sf=1.2):
+    lw, lh, _, _ = orbslam2_geometry(gray.shape[1], gray.shape[0], nlevels, sf)
+    pyr = [np.ascontiguousarray(gray, np.uint8)]
+    for l in range(1, nlevels):
+        pyr.append(resize_linear(pyr[-1], int(lw[l]), int(lh[l])))
+    return pyr
+
+
+def orbslam2_detect_level(img, ini_th=20, min_th=7):
+    img = np.ascontiguousarray(img, np.uint8)
+    h, w = img.shape
+    cap = w * h // 4 + 16
+    xs = np.zeros(cap, np.int32); ys = np.zeros(cap, np.int32); sc = np.zeros(cap, np.int32)
+    n = lib().orc_orbslam2_detect_level(_p(img), w, h, w, int(ini_th), int(min_th), _p(xs), _p(ys), _p(sc), cap)
+    assert 0 <= n <= cap, n
+    return xs[:n].copy(), ys[:n].copy(), sc[:n].copy()
+
+
+def orbslam2_extract(gray, nfeatures=1000, nlevels=8, scale_factor=1.2, ini_th=20, min_th=7, cap=None):
+    gray = np.ascontiguousarray(gray, np.uint8)
+    h, w = gray.shape
+    cap = cap or nfeatures + 3 * nlevels + 64
+    kps = np.zeros(cap, KP_DTYPE); desc = np.zeros((cap, 32), np.uint8); ksz = np.zeros(cap, np.float32)
+    n = C.c_int(0)
+    rc = lib().orc_orbslam2_extract(_p(gray), w, h, w, nfeatures, nlevels, _f(scale_factor), int(ini_th), int(min_th),
+                                    _p(kps), _p(desc), _p(ksz), cap, C.byref(n))
+    assert rc == 0, rc
+    return kps[:n.value].copy(), desc[:n.value].copy(), ksz[:n.value].copy()

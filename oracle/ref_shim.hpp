@@ -27,7 +27,12 @@ typedef unsigned char uchar;
 #define GL_LUMINANCE 0x1909
 #define GL_UNSIGNED_BYTE 0x1401
 namespace cv {
-template <typename T> struct Point_ { T x, y; Point_() : x(0), y(0) {} Point_(T x_, T y_) : x(x_), y(y_) {} };
+template <typename T> struct Point_ { T x, y; Point_() : x(0), y(0) {} Point_(T x_, T y_) : x(x_), y(y_) {}
+    Point_& operator*=(float s) { x = (T)(x * s); y = (T)(y * s); return *this; } };
+struct Size { int width = 0, height = 0; Size() {} Size(int w, int h) : width(w), height(h) {} };
+struct Rect { int x = 0, y = 0, width = 0, height = 0; Rect(int x_, int y_, int w, int h) : x(x_), y(y_), width(w), height(h) {} };
+enum { BORDER_REFLECT_101 = 4, BORDER_ISOLATED = 16, INTER_LINEAR = 1 };
+#define CV_8UC1 0
 typedef Point_<int> Point2i;
 typedef Point_<float> Point2f;
 typedef Point2i Point;
@@ -47,6 +52,28 @@ struct Mat {                                   // continuous row-major view; typ
     }
     void release() { rows = cols = 0; data = nullptr; own.reset(); }
     Mat row(int i) const { Mat m(1, cols, type_, data + (size_t)i * step); return m; }
+    // the pieces of cv::Mat the vanilla ORB-SLAM2 extractor bodies (src/ORBextractor.cc:460-676) use: ROI views share the storage
+    Mat(Size sz, int t) { create(sz.height, sz.width, t); }
+    Mat view(int r0, int r1, int c0, int c1) const { Mat m(r1 - r0, c1 - c0, type_, data + (size_t)r0 * step + (size_t)c0 * (type_ == 5 ? 4 : 1)); m.step = step; m.own = own; return m; }
+    Mat rowRange(int a, int b) const { return view(a, b, 0, cols); }
+    Mat colRange(int a, int b) const { return view(0, rows, a, b); }
+    Mat operator()(const Rect& r) const { return view(r.y, r.y + r.height, r.x, r.x + r.width); }
+    Mat clone() const { Mat m(rows, cols, type_); for (int i = 0; i < rows; ++i) memcpy(m.data + (size_t)i * m.step, data + (size_t)i * step, m.step); return m; }
+    bool empty() const { return data == nullptr || rows == 0 || cols == 0; }
+    int type() const { return type_; }
+    size_t step1() const { return step / (type_ == 5 ? 4 : 1); }
+    Mat getMat() const { return *this; }
+    // Mat::zeros returns an expression in OpenCV: assigned to a header of the same size / type it clears the EXISTING storage
+    // (computeDescriptorsORB, src/ORBextractor.cc:561, relies on that: its argument is a row range of the output matrix)
+    struct Zeros { int r, c, t; };
+    static Zeros zeros(int r, int c, int t) { return Zeros{r, c, t}; }
+    Mat& operator=(const Zeros& z) {
+        if (data && rows == z.r && cols == z.c && type_ == z.t) { for (int i = 0; i < rows; ++i) memset(data + (size_t)i * step, 0, (size_t)cols * (type_ == 5 ? 4 : 1)); }
+        else create(z.r, z.c, z.t);
+        return *this;
+    }
+    unsigned char* ptr(int r = 0) { return data + (size_t)r * step; }
+    const unsigned char* ptr(int r = 0) const { return data + (size_t)r * step; }
     template <typename T> T& at(int r, int c) { return reinterpret_cast<T*>(data + (size_t)r * step)[c]; }
     template <typename T> const T& at(int r, int c) const { return reinterpret_cast<const T*>(data + (size_t)r * step)[c]; }
     template <typename T> T* ptr(int r = 0) { return reinterpret_cast<T*>(data + (size_t)r * step); }
@@ -71,7 +98,39 @@ inline double norm(const Mat& a, const Mat& b, int normType) {
     for (int i = 0; i < a.cols; ++i) { const double v = (double)pa[i] - (double)pb[i]; s += v * v; }
     return s;
 }
+typedef Mat& OutputArray;
+// OpenCV functions the vanilla extractor calls: the tests plug the REAL cv2 4.13.0 functions in through these callbacks
+struct VanillaCallbacks {
+    int (*fast)(const unsigned char* data, int rows, int cols, int step, int threshold, float* xys, int cap);   // cv::FAST(img, kps, th, true)
+    void (*resize)(const unsigned char* src, int srows, int scols, int sstep, unsigned char* dst, int drows, int dcols, int dstep);   // INTER_LINEAR
+    void (*blur)(unsigned char* data, int rows, int cols, int step);                                        // GaussianBlur 7x7, sigma 2, REFLECT_101
+    float (*atan2)(float y, float x);                                                                       // cv::fastAtan2
+};
+extern VanillaCallbacks g_vanilla;
+inline void FAST(const Mat& img, std::vector<KeyPoint>& kps, int threshold, bool nonmax) {
+    (void)nonmax;
+    std::vector<float> buf((size_t)img.rows * img.cols * 3 + 3);
+    const int n = g_vanilla.fast(img.data, img.rows, img.cols, (int)img.step, threshold, buf.data(), img.rows * img.cols);
+    kps.resize(n);
+    for (int i = 0; i < n; ++i) { kps[i] = KeyPoint(); kps[i].pt.x = buf[3 * i]; kps[i].pt.y = buf[3 * i + 1]; kps[i].response = buf[3 * i + 2]; kps[i].size = 7.f; }
+}
+inline void resize(const Mat& src, Mat& dst, Size sz, double, double, int) {
+    if (dst.rows != sz.height || dst.cols != sz.width) dst.create(sz.height, sz.width, src.type_);     // cv::Mat::create keeps a fitting ROI
+    g_vanilla.resize(src.data, src.rows, src.cols, (int)src.step, dst.data, dst.rows, dst.cols, (int)dst.step);
+}
+inline void GaussianBlur(const Mat& src, Mat& dst, Size, double, double, int) { (void)src; g_vanilla.blur(dst.data, dst.rows, dst.cols, (int)dst.step); }   // in place in the reference
+inline float fastAtan2(float y, float x) { return g_vanilla.atan2(y, x); }
+inline int borderInterpolate101(int p, int len) { if (len == 1) return 0; while (p < 0 || p >= len) { if (p < 0) p = -p; else p = 2 * len - 2 - p; } return p; }
+// copyMakeBorder(BORDER_REFLECT_101 [+ ISOLATED]) into a destination of the final size; src may already be the centre ROI of dst
+inline void copyMakeBorder(const Mat& src, Mat& dst, int top, int bottom, int left, int right, int) {
+    if (dst.rows != src.rows + top + bottom || dst.cols != src.cols + left + right) dst.create(src.rows + top + bottom, src.cols + left + right, src.type_);
+    Mat s = src.clone();
+    for (int y = 0; y < dst.rows; ++y) for (int x = 0; x < dst.cols; ++x)
+        dst.data[(size_t)y * dst.step + x] = s.data[(size_t)borderInterpolate101(y - top, s.rows) * s.step + borderInterpolate101(x - left, s.cols)];
+}
 }  // namespace cv
+static inline int cvFloor(double v) { return (int)floor(v); }
+static inline int cvCeil(double v) { return (int)ceil(v); }
 
 #define FRAME_GRID_ROWS 48
 #define FRAME_GRID_COLS 64
@@ -296,14 +355,37 @@ struct AKAZE {
 
 struct FeatureExtractorSettings {               // include/FeatureExtractor.h:24-66 (the fields the constructor / computeSize read)
     float detectTh = 0;
+    int iniThFAST = 20, minThFAST = 7;
     float scaleFactor = 1.2f; int nOctaves = 8;
     float maxKeyPtSize = 0, minKeyPtSize = 1.0f, maxKeyPtSize0 = 0;
     static float scaleFactor0;
     static float GetDetectorNominalScaleFactor() { return scaleFactor0; }
 };
+// include/Types.h: mat2f (Eigen::Matrix2f) and CovarianceMethod as computeSigma / the vanilla operator() use them
+struct mat2f {
+    float m[2][2] = {{0, 0}, {0, 0}};
+    float& operator()(int i, int j) { return m[i][j]; } float operator()(int i, int j) const { return m[i][j]; }
+    static mat2f Identity() { mat2f r; r.m[0][0] = r.m[1][1] = 1.0f; return r; }
+};
+inline mat2f operator*(float s, const mat2f& a) { mat2f r; for (int i = 0; i < 2; ++i) for (int j = 0; j < 2; ++j) r.m[i][j] = s * a.m[i][j]; return r; }
+enum CovarianceMethod { NONE = 0, SIZE = 1 };
+// src/ORBextractor.cc:68-72 with VANILLA_ORB_SLAM2 defined
+const int PATCH_SIZE = 31;
+const int HALF_PATCH_SIZE = 15;
+const int EDGE_THRESHOLD = 19;
 class FeatureExtractor {
 public:
     FeatureExtractor() {}
+    // vanilla ORB-SLAM2 members (include/FeatureExtractor.h:74-82, :140-158); initVanilla = the VANILLA constructor body (:79-136)
+    void initVanilla(const int& nfeatures_, std::shared_ptr<FeatureExtractorSettings>& settings_);
+    void operator()(const Image& img, std::vector<cv::KeyPoint>& keypoints, cv::OutputArray descriptors, std::vector<mat2f>& keyPtsSigma2,
+                    std::vector<mat2f>& keyPtsInf, std::vector<float>& keyPtsSize, const bool& vanillaOrbslam);
+    void ComputePyramid(cv::Mat image);
+    void ComputeKeyPointsOctTree(std::vector<std::vector<cv::KeyPoint>>& allKeypoints, const cv::Mat& mask);
+    void computeSigma(std::vector<mat2f>& keyPtsSigma2, std::vector<mat2f>& keyPtsInf, const std::vector<float>& keyPtsSize,
+                      const std::vector<cv::KeyPoint>& keypoints, const Image& img, const CovarianceMethod& method);
+    std::vector<cv::Point> pattern;
+    std::vector<int> umax;
     FeatureExtractor(const int& nfeatures_, std::shared_ptr<FeatureExtractorSettings>& settings_);
     virtual ~FeatureExtractor() {}
     std::shared_ptr<FeatureExtractorSettings> settings{};
