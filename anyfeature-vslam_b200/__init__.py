@@ -17,7 +17,8 @@ LIB_PATH = os.path.join(_HERE, "libafv_b200.so")
 KP_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("size", "<f4"), ("angle", "<f4"),
                      ("response", "<f4"), ("octave", "<i4"), ("class_id", "<i4")])
 FEAT_ORB32, FEAT_AKAZE61, FEAT_BRISK48, FEAT_SIFT128 = 0, 1, 2, 5       # reference include/Types.h:35-45
-DESC_BYTES = {0: 32, 1: 61, 2: 48, 5: 512}
+FEAT_ORB32_VANILLA = 100                                                 # extractor built with VANILLA_ORB_SLAM2 (include/Definitions.h:8)
+DESC_BYTES = {0: 32, 1: 61, 2: 48, 5: 512, 100: 32}
 
 # settings/<feat>_settings.yaml of the reference (numOctaves, scaleFactor, detectionTh, matchingTh)
 FEATURE_SETTINGS = {
@@ -25,6 +26,8 @@ FEATURE_SETTINGS = {
     "akaze61": dict(feature_id=1, n_octaves=8, scale_factor=1.1892, detect_th=0.0005, matching_th=128.0),
     "brisk48": dict(feature_id=2, n_octaves=8, scale_factor=1.5, detect_th=34.0, matching_th=120.0),
     "sift128": dict(feature_id=5, n_octaves=8, scale_factor=2.0, detect_th=10.0, matching_th=0.5),
+    # vanilla ORB-SLAM2 build: the settings constructor pins scaleFactor 1.2, 8 octaves, iniThFAST 20 (src/FeatureExtractor.cpp:40-46)
+    "orbslam2": dict(feature_id=100, n_octaves=8, scale_factor=1.2, detect_th=20.0, matching_th=75.0),
 }
 
 
@@ -186,6 +189,24 @@ def undistort_keypoints(kps, n, K4, dist5, out=None, stream=None):
     K4 = np.ascontiguousarray(K4, np.float32); dist5 = np.ascontiguousarray(dist5, np.float32)
     _check(lib().afv_undistort_keypoints(_vp(kps), _vp(n), B, cap, _vp(K4), _vp(dist5), _vp(out), _stream_ptr(stream)))
     return out
+
+
+def is_in_frustum(Pw, normal, min_dist, max_dist, ref_size, ref_sigma, ref_dist, pose16, cam5, bounds4, cos_limit=0.5,
+                  radius_factor=1.0, size_tol=1.5, stream=None):
+    """Frame::isInFrustum (src/Frame.cc:276-331) for M map points (float32 cuda tensors [M,3] / [M]) against one frame, fused with
+    SearchByProjection's window prologue.  pose16 / cam5 / bounds4 are host values.  Returns device tensors
+    (in_view [M] uint8, proj [M,3], track [M,3], qr [M], qmin [M], qmax [M])."""
+    import torch
+    M = Pw.shape[0]
+    dev = Pw.device
+    iv = torch.zeros(M, dtype=torch.uint8, device=dev)
+    proj = torch.zeros((M, 3), dtype=torch.float32, device=dev); track = torch.zeros((M, 3), dtype=torch.float32, device=dev)
+    qr = torch.zeros(M, dtype=torch.float32, device=dev); qmin = torch.zeros_like(qr); qmax = torch.zeros_like(qr)
+    f32 = lambda a: np.ascontiguousarray(a, np.float32)
+    _check(lib().afv_is_in_frustum(_vp(Pw), _vp(normal), _vp(min_dist), _vp(max_dist), _vp(ref_size), _vp(ref_sigma), _vp(ref_dist), M,
+                                   _vp(f32(pose16)), _vp(f32(cam5)), _vp(f32(bounds4)), C.c_float(cos_limit), C.c_float(radius_factor),
+                                   C.c_float(size_tol), _vp(iv), _vp(proj), _vp(track), _vp(qr), _vp(qmin), _vp(qmax), _stream_ptr(stream)))
+    return iv, proj, track, qr, qmin, qmax
 
 
 def kps_from_device(t, n):

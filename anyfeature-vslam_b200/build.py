@@ -18,6 +18,7 @@ SOURCES = [
     ("afv_sift.cu", ["--fmad=false"]),
     ("afv_akaze.cu", ["--fmad=false"]),
     ("afv_brisk.cu", ["--fmad=false"]),
+    ("afv_orbslam2.cu", ["--fmad=false"]),
     ("afv_capi.cu", ["--fmad=false"]),
 ]
 COMMON = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",

@@ -7,6 +7,7 @@
 #include "afv_sift.h"
 #include "afv_akaze.h"
 #include "afv_brisk.h"
+#include "afv_orbslam2.h"
 #include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
@@ -100,6 +101,7 @@ struct afv_extractor {
     AfvSift* sift;                    // sift128 state (feature_id == AFV_FEAT_SIFT128), else NULL
     AfvAkaze* akaze;                  // akaze61 state (feature_id == AFV_FEAT_AKAZE61), else NULL
     AfvBrisk* brisk;                  // brisk48 state (feature_id == AFV_FEAT_BRISK48), else NULL
+    AfvOs2* os2;                      // vanilla ORB-SLAM2 state (feature_id == AFV_FEAT_ORB32_VANILLA), else NULL
     int desc_bytes;                   // bytes per descriptor row: 32 (orb32) / 61 (akaze61) / 512 (sift128: 128 floats)
 };
 
@@ -217,7 +219,8 @@ extern "C" int afv_extractor_create(afv_extractor** out, int feature_id, int nfe
                                     int max_batch, int max_w, int max_h) {
     if (!out) { afv_set_error("out is NULL"); return AFV_ERR_INVALID; }
     *out = nullptr;
-    if (feature_id != AFV_FEAT_ORB32 && feature_id != AFV_FEAT_SIFT128 && feature_id != AFV_FEAT_AKAZE61 && feature_id != AFV_FEAT_BRISK48) {
+    if (feature_id != AFV_FEAT_ORB32 && feature_id != AFV_FEAT_SIFT128 && feature_id != AFV_FEAT_AKAZE61 && feature_id != AFV_FEAT_BRISK48 &&
+        feature_id != AFV_FEAT_ORB32_VANILLA) {
         afv_set_error("feature id %d: no extractor for this feature (orb32, akaze61, brisk48, sift128 are built)", feature_id);
         return AFV_ERR_UNSUPPORTED;
     }
@@ -237,12 +240,13 @@ extern "C" int afv_extractor_create(afv_extractor** out, int feature_id, int nfe
     ex->scale_factor = scale_factor; ex->detect_th = detect_th;
     ex->max_batch = max_batch; ex->max_w = max_w; ex->max_h = max_h; ex->cur_w = ex->cur_h = 0;
     ex->last_B = 0; ex->last_stream = nullptr;
-    ex->sift = nullptr; ex->akaze = nullptr; ex->brisk = nullptr; ex->ev_order = nullptr; ex->stream = nullptr;
+    ex->sift = nullptr; ex->akaze = nullptr; ex->brisk = nullptr; ex->os2 = nullptr; ex->ev_order = nullptr; ex->stream = nullptr;
     ex->desc_bytes = feature_id == AFV_FEAT_SIFT128 ? 512 : feature_id == AFV_FEAT_AKAZE61 ? 61 : feature_id == AFV_FEAT_BRISK48 ? 48 : 32;
     ex->h_status = nullptr; ex->h_counts = nullptr; ex->aux.stream = nullptr; ex->aux.ev_pyr = nullptr; ex->aux.ev_blur = nullptr;
     AFV_CUDA_CHECK(cudaStreamCreateWithFlags(&ex->stream, cudaStreamNonBlocking));
     AFV_CUDA_CHECK(cudaEventCreateWithFlags(&ex->ev_order, cudaEventDisableTiming));
-    if (feature_id == AFV_FEAT_SIFT128 || feature_id == AFV_FEAT_AKAZE61 || feature_id == AFV_FEAT_BRISK48) {
+    if (feature_id == AFV_FEAT_SIFT128 || feature_id == AFV_FEAT_AKAZE61 || feature_id == AFV_FEAT_BRISK48 || feature_id == AFV_FEAT_ORB32_VANILLA) {
+        // vanilla ORB-SLAM2 (reference src/ORBextractor.cc:79-136 constructor, :568-645 operator()): iniThFAST = int(detect_th), minThFAST = 7
         // FeatureExtractor_brisk48 (reference src/Feature_brisk48.cpp:20-48): BriskFeatureDetector(int(detect_th), n_octaves / 2, true).
         // FeatureExtractor_akaze61 (reference src/Feature_akaze61.cpp:7-13): omax = n_octaves / 4, nsublevels = n_octaves / 2,
         // dthreshold = detect_th.
@@ -252,6 +256,7 @@ extern "C" int afv_extractor_create(afv_extractor** out, int feature_id, int nfe
         features_per_level(nfeatures, n_octaves, scale_factor, ex->q_ext);
         int rc = feature_id == AFV_FEAT_SIFT128 ? afv_sift_create(&ex->sift, nfeatures, n_octaves, scale_factor, max_batch, max_w, max_h)
                : feature_id == AFV_FEAT_BRISK48 ? afv_brisk_create(&ex->brisk, nfeatures, n_octaves, scale_factor, detect_th, max_batch, max_w, max_h)
+               : feature_id == AFV_FEAT_ORB32_VANILLA ? afv_os2_create(&ex->os2, nfeatures, n_octaves, scale_factor, detect_th, max_batch, max_w, max_h)
                                                 : afv_akaze_create(&ex->akaze, nfeatures, n_octaves, scale_factor, detect_th, max_batch, max_w, max_h);
         const int ocap = nfeatures + 3 * n_octaves;
         if (rc == AFV_OK) rc = dev_alloc(ex, &ex->o_kps, (size_t)ocap * max_batch);
@@ -335,6 +340,7 @@ extern "C" void afv_extractor_destroy(afv_extractor* ex) {
     if (ex->sift) afv_sift_destroy(ex->sift);
     if (ex->akaze) afv_akaze_destroy(ex->akaze);
     if (ex->brisk) afv_brisk_destroy(ex->brisk);
+    if (ex->os2) afv_os2_destroy(ex->os2);
     if (ex->h_status) cudaFreeHost(ex->h_status);
     if (ex->h_counts) cudaFreeHost(ex->h_counts);
     delete ex;
@@ -356,8 +362,9 @@ static int run_device(afv_extractor* ex, const uint8_t* d_gray, int B, int w, in
                       bool gray_is_staged) {
     if (B < 1 || B > ex->max_batch) { afv_set_error("batch %d outside 1..%d", B, ex->max_batch); return AFV_ERR_INVALID; }
     if (cap < afv_extractor_output_cap(ex)) { afv_set_error("cap %d < required %d", cap, afv_extractor_output_cap(ex)); return AFV_ERR_INVALID; }
-    if (ex->sift || ex->akaze || ex->brisk) {
-        const int src = ex->sift ? afv_sift_run(ex->sift, d_gray, B, w, h, stride, frame_stride, d_kps, (float*)d_desc, d_kpsize, cap, d_n_out, st)
+    if (ex->sift || ex->akaze || ex->brisk || ex->os2) {
+        const int src = ex->os2 ? afv_os2_run(ex->os2, d_gray, B, w, h, stride, frame_stride, d_kps, (uint8_t*)d_desc, d_kpsize, cap, d_n_out, st)
+                      : ex->sift ? afv_sift_run(ex->sift, d_gray, B, w, h, stride, frame_stride, d_kps, (float*)d_desc, d_kpsize, cap, d_n_out, st)
                       : ex->brisk ? afv_brisk_run(ex->brisk, d_gray, B, w, h, stride, frame_stride, d_kps, (uint8_t*)d_desc, d_kpsize, cap, d_n_out, st)
                                  : afv_akaze_run(ex->akaze, d_gray, B, w, h, stride, frame_stride, d_kps, (uint8_t*)d_desc, d_kpsize, cap, d_n_out, st);
         if (src) return src;
@@ -387,6 +394,7 @@ static int check_status(afv_extractor* ex, int B, cudaStream_t st) {
     if (ex->sift) return afv_sift_status(ex->sift, B, st);
     if (ex->akaze) return afv_akaze_status(ex->akaze, B, st);
     if (ex->brisk) return afv_brisk_status(ex->brisk, B, st);
+    if (ex->os2) return afv_os2_status(ex->os2, B, st);
     AFV_CUDA_CHECK(cudaMemcpyAsync(ex->h_status, ex->status, sizeof(int) * B, cudaMemcpyDeviceToHost, st));
     AFV_CUDA_CHECK(cudaStreamSynchronize(st));
     for (int b = 0; b < B; ++b)
@@ -430,9 +438,9 @@ extern "C" int afv_extract_batch(afv_extractor* ex, const uint8_t* gray, int B, 
     if (cap < ocap) { afv_set_error("cap %d < required %d", cap, ocap); return AFV_ERR_INVALID; }
     if (stride < w) { afv_set_error("stride < w"); return AFV_ERR_INVALID; }
     cudaStream_t st = ex->stream;
-    if (ex->sift || ex->akaze || ex->brisk) {
+    if (ex->sift || ex->akaze || ex->brisk || ex->os2) {
         if (w > ex->max_w || h > ex->max_h) { afv_set_error("frame %dx%d larger than the extractor's configured maximum", w, h); return AFV_ERR_INVALID; }
-        uint8_t* stage = ex->sift ? afv_sift_stage(ex->sift) : ex->brisk ? afv_brisk_stage(ex->brisk) : afv_akaze_stage(ex->akaze);
+        uint8_t* stage = ex->os2 ? afv_os2_stage(ex->os2) : ex->sift ? afv_sift_stage(ex->sift) : ex->brisk ? afv_brisk_stage(ex->brisk) : afv_akaze_stage(ex->akaze);
         const size_t DB = (size_t)ex->desc_bytes;
         for (int b0 = 0; b0 < B; b0 += ex->max_batch) {
             const int nb = B - b0 < ex->max_batch ? B - b0 : ex->max_batch;
@@ -491,11 +499,12 @@ extern "C" int afv_extract(afv_extractor* ex, const uint8_t* gray, int w, int h,
 }
 
 extern "C" int afv_debug_read(afv_extractor* ex, int what, int frame, int level, void* out, long cap_bytes, long* n_bytes) {
-    if (ex && (ex->sift || ex->akaze || ex->brisk)) {
+    if (ex && (ex->sift || ex->akaze || ex->brisk || ex->os2)) {
         if (!out || !n_bytes || frame < 0 || frame >= ex->last_B) { afv_set_error("afv_debug_read: bad argument"); return AFV_ERR_INVALID; }
         AFV_CUDA_CHECK(cudaSetDevice(ex->device));
         AFV_CUDA_CHECK(cudaStreamSynchronize(ex->last_stream));
-        return ex->sift ? afv_sift_debug_read(ex->sift, what, frame, level, out, cap_bytes, n_bytes)
+        return ex->os2 ? afv_os2_debug_read(ex->os2, what, frame, level, out, cap_bytes, n_bytes)
+             : ex->sift ? afv_sift_debug_read(ex->sift, what, frame, level, out, cap_bytes, n_bytes)
              : ex->brisk ? afv_brisk_debug_read(ex->brisk, what, frame, level, out, cap_bytes, n_bytes)
                         : afv_akaze_debug_read(ex->akaze, what, frame, level, out, cap_bytes, n_bytes);
     }

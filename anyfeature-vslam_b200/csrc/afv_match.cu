@@ -198,6 +198,70 @@ extern "C" int afv_undistort_keypoints(const afv_keypoint* d_kps, const int* d_n
     return AFV_OK;
 }
 
+// ---- Frame::isInFrustum (src/Frame.cc:276-331) + the window prologue of SearchByProjection (src/FeatureMatcher.cc:86-95) ----
+// Thread per map point.  IEEE float32, every operation rounded once (explicit intrinsics; the TU is also built --fmad=false),
+// 3-term sums left to right: the arithmetic contract of oracle/afv_oracle_match.c::orc_is_in_frustum (the reference evaluates
+// the same expressions through Eigen under -march=native, i.e. to ~1e-6 relative of this, not to the bit).
+struct AfvPose { float R[9], t[3], c[3], fx, fy, cx, cy, mbf, minX, maxX, minY, maxY; };
+__global__ void __launch_bounds__(256) k_in_frustum(const float* __restrict__ Pw, const float* __restrict__ nrm, const float* __restrict__ mind,
+        const float* __restrict__ maxd, const float* __restrict__ rsz, const float* __restrict__ rsg, const float* __restrict__ rds, int M,
+        const AfvPose S, float cos_limit, float radius_factor, float size_tol, uint8_t* __restrict__ in_view, float* __restrict__ proj3,
+        float* __restrict__ track3, float* __restrict__ qr, float* __restrict__ qmin, float* __restrict__ qmax) {
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= M) return;
+    const float P0 = Pw[3 * i], P1 = Pw[3 * i + 1], P2 = Pw[3 * i + 2];
+    float u = 0.f, v = 0.f, ur = 0.f, tsz = 0.f, tsg = 0.f, vc = 0.f, r = -1.0f, lo = 0.f, hi = 0.f;
+    bool ok = false;
+    float Pc[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k)
+        Pc[k] = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(S.R[3 * k], P0), __fmul_rn(S.R[3 * k + 1], P1)), __fmul_rn(S.R[3 * k + 2], P2)), S.t[k]);
+    if (!(Pc[2] < 0.0f)) {
+        const float invz = __fdiv_rn(1.0f, Pc[2]);
+        const float uu = __fadd_rn(__fmul_rn(__fmul_rn(S.fx, Pc[0]), invz), S.cx);
+        const float vv = __fadd_rn(__fmul_rn(__fmul_rn(S.fy, Pc[1]), invz), S.cy);
+        if (!(uu < S.minX || uu > S.maxX) && !(vv < S.minY || vv > S.maxY)) {
+            const float a = __fsub_rn(P0, S.c[0]), b = __fsub_rn(P1, S.c[1]), c = __fsub_rn(P2, S.c[2]);
+            const float dist = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(a, a), __fmul_rn(b, b)), __fmul_rn(c, c)));
+            if (!(dist < mind[i] || dist > maxd[i])) {
+                const float dot = __fadd_rn(__fadd_rn(__fmul_rn(a, nrm[3 * i]), __fmul_rn(b, nrm[3 * i + 1])), __fmul_rn(c, nrm[3 * i + 2]));
+                const float viewCos = __fdiv_rn(dot, dist);
+                if (!(viewCos < cos_limit)) {
+                    ok = true; u = uu; v = vv; ur = __fsub_rn(uu, __fmul_rn(S.mbf, invz));
+                    tsz = __fdiv_rn(__fmul_rn(rsz[i], rds[i]), dist); tsg = __fdiv_rn(__fmul_rn(rsg[i], rds[i]), dist); vc = viewCos;
+                    const float rv = (double)viewCos > 0.998 ? 2.5f : 4.0f;
+                    r = __fmul_rn(__fmul_rn(radius_factor, rv), tsz); lo = __fdiv_rn(tsz, size_tol); hi = __fmul_rn(tsz, size_tol);
+                }
+            }
+        }
+    }
+    in_view[i] = ok ? 1 : 0;
+    proj3[3 * i] = u; proj3[3 * i + 1] = v; proj3[3 * i + 2] = ur;
+    track3[3 * i] = tsz; track3[3 * i + 1] = tsg; track3[3 * i + 2] = vc;
+    if (qr) { qr[i] = r; qmin[i] = lo; qmax[i] = hi; }
+}
+
+extern "C" int afv_is_in_frustum(const float* d_Pw, const float* d_normal, const float* d_min_dist, const float* d_max_dist,
+                                 const float* d_ref_size, const float* d_ref_sigma, const float* d_ref_dist, int M, const float* pose16,
+                                 const float* cam5, const float* bounds4, float viewing_cos_limit, float radius_factor, float size_tolerance,
+                                 uint8_t* d_in_view, float* d_proj3, float* d_track3, float* d_qr, float* d_qmin, float* d_qmax,
+                                 void* cuda_stream) {
+    if (M == 0) return AFV_OK;                                           // empty local map: nothing to do (pointers may be NULL)
+    if (!d_Pw || !d_normal || !d_min_dist || !d_max_dist || !d_ref_size || !d_ref_sigma || !d_ref_dist || !pose16 || !cam5 || !bounds4 ||
+        !d_in_view || !d_proj3 || !d_track3 || M < 0 || (d_qr && (!d_qmin || !d_qmax))) { afv_set_error("afv_is_in_frustum: bad argument"); return AFV_ERR_INVALID; }
+    (void)cudaGetLastError();            // a stale error left by another library in this thread must not be reported as this launch's
+    AfvPose S;
+    for (int i = 0; i < 9; ++i) S.R[i] = pose16[i];
+    for (int i = 0; i < 3; ++i) { S.t[i] = pose16[9 + i]; S.c[i] = pose16[12 + i]; }
+    S.fx = cam5[0]; S.fy = cam5[1]; S.cx = cam5[2]; S.cy = cam5[3]; S.mbf = cam5[4];
+    S.minX = bounds4[0]; S.maxX = bounds4[1]; S.minY = bounds4[2]; S.maxY = bounds4[3];
+    k_in_frustum<<<(M + 255) / 256, 256, 0, as_stream(cuda_stream)>>>(d_Pw, d_normal, d_min_dist, d_max_dist, d_ref_size, d_ref_sigma, d_ref_dist, M, S,
+            viewing_cos_limit, radius_factor, size_tolerance, d_in_view, d_proj3, d_track3, d_qr, d_qmin, d_qmax);
+    ++g_afv_launches;
+    AFV_CUDA_CHECK(cudaGetLastError());
+    return AFV_OK;
+}
+
 // ---- stateless window search: one warp per query ---------------------------------------------------------
 __global__ void __launch_bounds__(256) k_match_window(int desc_type, int D, const uint8_t* __restrict__ q,
         const float* __restrict__ qxy, const float* __restrict__ qr, const float* __restrict__ qmin,

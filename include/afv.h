@@ -31,6 +31,9 @@ extern "C" {
 #define AFV_FEAT_AKAZE61    1
 #define AFV_FEAT_BRISK48    2
 #define AFV_FEAT_SIFT128    5
+/* extractor-only id (descriptor type stays AFV_FEAT_ORB32 for the matcher): the reference's FeatureExtractor built with
+ * VANILLA_ORB_SLAM2 (include/Definitions.h:8), i.e. operator()(..., vanillaOrbslam) of src/ORBextractor.cc:568-645 */
+#define AFV_FEAT_ORB32_VANILLA 100
 
 /* == cv::KeyPoint POD (28 bytes, same field order): what the reference's operator() fills
  * (include/FeatureExtractor.h:84-93). */
@@ -54,6 +57,10 @@ typedef struct afv_extractor afv_extractor;
  *   AFV_FEAT_BRISK48 (src/Feature_brisk48.cpp) descriptors CV_8U  N x 48, octave = BRISK layer 0 .. 2*(n_octaves/2)-1 (:29-30),
  *                    angle in degrees, class_id -1; detector = BriskFeatureDetector(int(detect_th), n_octaves / 2, true) (:24-26),
  *                    keypoints whose sampling pattern leaves the image are removed by the descriptor stage like brisk's compute()
+   AFV_FEAT_ORB32_VANILLA (src/ORBextractor.cc:79-177, :460-676; Frame::ExtractFeatures src/Frame.cc:245-246) descriptors CV_8U N x 32:
+ *                    INTER_LINEAR pyramid, FAST(iniThFAST = int(detect_th)) per 30-px cell with the minThFAST = 7 fallback, octree over
+ *                    the 16-px border rectangle, IC angle, fixed-point GaussianBlur, steered BRIEF; size = mvScaleFactor[octave],
+ *                    response = FAST score; every pyramid level must be at least 62 x 62.  OpenCV stages pinned to cv2 4.13.0
  * sift128 / akaze61 / brisk48 implement the published algorithms in the parameterisation the reference selects; SiftGPU /
  * libAKAZE / ETH brisk are not vendored by the reference, so parity with them is UNPINNED (oracle/afv_oracle_{sift,akaze,brisk}.c
  * headers; the brisk48 detector, orientation and 512-bit descriptor core are pinned to cv2.BRISK, the 48-byte pair table is a
@@ -95,7 +102,9 @@ int  afv_extractor_status(afv_extractor* ex);
  * sift128: what = 10 Gaussian image / 11 DoG image (level = octave * 8 + index, float), 12 SiftGPU-order list after the -tc2
  *          limit (x, y, s, o floats).  akaze61: what = 20..24 Lt / Lsmooth / Lx / Ly / Ldet of evolution level `level`,
  *          25 Feature_Detection list (x, y, size, response, class_id floats), 26 contrast factor.  brisk48: what = 30 layer image,
- *          31 AGAST 9-16 score image of layer `level` (u8), 32 detect list (x, y, size, response, layer floats).  orb32:
+ *          31 AGAST 9-16 score image of layer `level` (u8), 32 detect list (x, y, size, response, layer floats).  vanilla ORB-SLAM2: what = 40 level image,
+ *          41 blurred level, 42 FAST score map, 43 detect list in push order (uint32 (x-16) | (y-16) << 12 | score << 24), 44 octree
+ *          keep list (8 bytes as in 4, level coordinates, FAST score as float).  orb32:
  *   what = 0: pyramid level image (w_l*h_l bytes, tight)      1: blurred level image
  *          2: FAST+NMS candidates (uint32 x | y<<12 | score<<24, unordered)
  *          3: cv::ORB::detect-equivalent list after both retainBest culls (uint32 packed xy, float response
@@ -131,6 +140,22 @@ int  afv_grid_build(const afv_keypoint* d_kps, const int* d_n, int B, int cap,
  * iterations).  Chain afv_grid_build on the result for Frame::AssignFeaturesToGrid (:225-240). */
 int  afv_undistort_keypoints(const afv_keypoint* d_kps, const int* d_n, int B, int cap, const float* K4, const float* dist5,
                              afv_keypoint* d_kps_un, void* cuda_stream);
+
+/* Frame::isInFrustum (src/Frame.cc:276-331) for M map points against one frame, fused with the window prologue of
+ * SearchByProjection(F, vpMapPoints, radiusTh) (src/FeatureMatcher.cc:86-95) so the result feeds afv_search_by_projection_ex directly.
+ * Device arrays per map point: world position (M x 3), mean viewing normal (M x 3), GetMin/MaxDistanceInvariance, and the
+ * PredictSize / PredictSigma inputs refSize, refSigma, refDistance (src/MapPoint.cc:432-442).  HOST arrays: pose16 = {Rcw row-major
+ * (9), tcw (3), twc = camera centre (3), unused}, cam5 = {fx, fy, cx, cy, mbf}, bounds4 = {mnMinX, mnMaxX, mnMinY, mnMaxY}.
+ * Outputs: d_in_view[M] (mbTrackInView), d_proj3 = (mTrackProjX, mTrackProjY, mTrackProjXR), d_track3 = (trackSize, trackSigma,
+ * trackViewCos); optional (all three or none) d_qr = radius_factor * RadiusByViewingCos(viewCos) * trackSize with radius_factor =
+ * radiusScale * radiusTh (-1 for a point out of view = skipped query), d_qmin / d_qmax = trackSize / and * size_tolerance.
+ * Floating point: IEEE float32, one rounding per operation, 3-term sums left to right; the reference evaluates the same
+ * expressions through Eigen built -march=native, so a reference build agrees to ~1e-6 relative (tests: 1e-5), not to the bit. */
+int  afv_is_in_frustum(const float* d_Pw, const float* d_normal, const float* d_min_dist, const float* d_max_dist,
+                       const float* d_ref_size, const float* d_ref_sigma, const float* d_ref_dist, int M, const float* pose16,
+                       const float* cam5, const float* bounds4, float viewing_cos_limit, float radius_factor, float size_tolerance,
+                       uint8_t* d_in_view, float* d_proj3, float* d_track3, float* d_qr, float* d_qmin, float* d_qmax,
+                       void* cuda_stream);
 
 /* Data-parallel core of SearchByProjection (src/FeatureMatcher.cc:73-154) / GetFeaturesInArea
  * (src/Frame.cc:333-382): for each query (descriptor, window centre qxy, radius, size gate) the best and

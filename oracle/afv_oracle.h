@@ -224,6 +224,12 @@ void  orc_orbslam2_descriptor(const uint8_t* blur, int stride, int cx, int cy, f
 int   orc_orbslam2_extract(const uint8_t* gray, int w, int h, int stride, int nfeatures, int nlevels, float scale_factor,
                            int ini_th, int min_th, orc_keypoint* kps, uint8_t* desc, float* kpsize, int cap, int* n_out);
 
+/* Frame::isInFrustum (src/Frame.cc:276-331) + the window prologue of SearchByProjection (src/FeatureMatcher.cc:86-95), M map points. */
+void  orc_is_in_frustum(const float* Pw, const float* normal, const float* min_dist, const float* max_dist, const float* ref_size,
+                        const float* ref_sigma, const float* ref_dist, int M, const float* pose16, const float* cam5, const float* bounds4,
+                        float viewing_cos_limit, float radius_factor, float size_tol, uint8_t* in_view, float* proj3, float* track3,
+                        float* qr, float* qmin, float* qmax);
+
 #ifdef __cplusplus
 }
 #endif

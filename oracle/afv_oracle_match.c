@@ -714,3 +714,48 @@ int orc_bow_match(int mode, int desc_type,
     free(e1); free(e2); free(bin_of); free(matched2);
     return nMatches;
 }
+
+/* ---------------------------------------------------------------- Frame::isInFrustum ---------------------------------------- */
+/* Frame::isInFrustum (src/Frame.cc:276-331) for M map points against one frame pose, followed by the window prologue of
+ * SearchByProjection(F, vpMapPoints, radiusTh) (src/FeatureMatcher.cc:86-93).  IEEE float32 without contraction; 3-term sums are
+ * evaluated left to right ((a0*b0 + a1*b1) + a2*b2) -- the reference uses Eigen (not vendored) compiled with -march=native, whose
+ * evaluation order / FMA use is not defined by the reference sources, so agreement with a reference BUILD is to ~1e-6 relative, not
+ * to the bit (tests use 1e-5).  pose16 = {Rcw row-major (9), tcw (3), twc (3), pad}; cam = {fx, fy, cx, cy, mbf};
+ * bounds = {mnMinX, mnMaxX, mnMinY, mnMaxY}.  Outputs per point: in_view, proj = (mTrackProjX, mTrackProjY, mTrackProjXR),
+ * track = (trackSize, trackSigma, trackViewCos); optional query arrays for the projection search: qr = radius_factor *
+ * RadiusByViewingCos(viewCos) * trackSize (-1 when not in view), qmin = trackSize / tol, qmax = trackSize * tol. */
+void orc_is_in_frustum(const float* Pw, const float* normal, const float* min_dist, const float* max_dist, const float* ref_size,
+                       const float* ref_sigma, const float* ref_dist, int M, const float* pose16, const float* cam5, const float* bounds4,
+                       float viewing_cos_limit, float radius_factor, float size_tol, uint8_t* in_view, float* proj3, float* track3,
+                       float* qr, float* qmin, float* qmax) {
+    const float* R = pose16; const float* t = pose16 + 9; const float* c = pose16 + 12;
+    for (int i = 0; i < M; ++i) {
+        const float* P = Pw + 3 * i;
+        in_view[i] = 0;
+        if (qr) { qr[i] = -1.0f; qmin[i] = 0.0f; qmax[i] = 0.0f; }
+        for (int k = 0; k < 3; ++k) { proj3[3 * i + k] = 0.0f; track3[3 * i + k] = 0.0f; }
+        float Pc[3];
+        for (int r = 0; r < 3; ++r) Pc[r] = ((R[3 * r] * P[0] + R[3 * r + 1] * P[1]) + R[3 * r + 2] * P[2]) + t[r];
+        if (Pc[2] < 0.0f) continue;
+        const float invz = 1.0f / Pc[2];
+        const float u = cam5[0] * Pc[0] * invz + cam5[2];
+        const float v = cam5[1] * Pc[1] * invz + cam5[3];
+        if (u < bounds4[0] || u > bounds4[1]) continue;
+        if (v < bounds4[2] || v > bounds4[3]) continue;
+        const float PO[3] = {P[0] - c[0], P[1] - c[1], P[2] - c[2]};
+        const float dist = sqrtf((PO[0] * PO[0] + PO[1] * PO[1]) + PO[2] * PO[2]);
+        if (dist < min_dist[i] || dist > max_dist[i]) continue;
+        const float* Pn = normal + 3 * i;
+        const float viewCos = ((PO[0] * Pn[0] + PO[1] * Pn[1]) + PO[2] * Pn[2]) / dist;
+        if (viewCos < viewing_cos_limit) continue;
+        in_view[i] = 1;
+        proj3[3 * i] = u; proj3[3 * i + 1] = v; proj3[3 * i + 2] = u - cam5[4] * invz;
+        const float tsz = ref_size[i] * ref_dist[i] / dist;
+        track3[3 * i] = tsz; track3[3 * i + 1] = ref_sigma[i] * ref_dist[i] / dist; track3[3 * i + 2] = viewCos;
+        if (qr) {
+            const float rv = (double)viewCos > 0.998 ? 2.5f : 4.0f;                /* RadiusByViewingCos (src/FeatureMatcher.cc:156-162) */
+            qr[i] = radius_factor * rv * tsz;                                      /* radiusScale * radiusTh * ... * predictedSize (:91) */
+            qmin[i] = tsz / size_tol; qmax[i] = tsz * size_tol;                    /* :95 */
+        }
+    }
+}

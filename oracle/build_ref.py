@@ -590,6 +590,25 @@ int ref_orbslam2_extract(const unsigned char* gray, int w, int h, int nfeatures,
     }
     return m;
 }
+// Frame::isInFrustum (src/Frame.cc:276-331) for M map points; Eigen is replaced by the shim's left-to-right float look-alikes
+void ref_is_in_frustum(const float* Pw, const float* normal, const float* min_dist, const float* max_dist, const float* ref_size,
+                       const float* ref_sigma, const float* ref_dist, int M, const float* pose16, const float* cam5, const float* bounds4,
+                       float viewing_cos_limit, unsigned char* in_view, float* proj3, float* track3) {
+    Frame::mnMinX = bounds4[0]; Frame::mnMaxX = bounds4[1]; Frame::mnMinY = bounds4[2]; Frame::mnMaxY = bounds4[3];
+    Frame F;
+    for (int i = 0; i < 3; ++i) { for (int j = 0; j < 3; ++j) F.Rcw.m[i][j] = pose16[3 * i + j]; F.tcw.v[i] = pose16[9 + i]; F.twc.v[i] = pose16[12 + i]; }
+    F.fx = cam5[0]; F.fy = cam5[1]; F.cx = cam5[2]; F.cy = cam5[3]; F.mbf = cam5[4];
+    for (int i = 0; i < M; ++i) {
+        Pt p = std::make_shared<MapPoint>();
+        for (int k = 0; k < 3; ++k) { p->worldPos.v[k] = Pw[3 * i + k]; p->normal.v[k] = normal[3 * i + k]; }
+        p->minDist = min_dist[i]; p->maxDist = max_dist[i]; p->realPredict = true;
+        p->refSize = ref_size[i]; p->refSigma = ref_sigma[i]; p->refDistance = ref_dist[i];
+        p->mTrackProjX = p->mTrackProjY = p->mTrackProjXR = 0; p->trackSize = p->trackSigma = p->trackViewCos = 0;
+        in_view[i] = F.isInFrustum(p, viewing_cos_limit) ? 1 : 0;
+        proj3[3 * i] = p->mTrackProjX; proj3[3 * i + 1] = p->mTrackProjY; proj3[3 * i + 2] = p->mTrackProjXR;
+        track3[3 * i] = p->trackSize; track3[3 * i + 1] = p->trackSigma; track3[3 * i + 2] = p->trackViewCos;
+    }
+}
 float ref_descriptor_distance(int desc_type, int dcols, int dtype, void* a, void* b) {
     return FeatureMatcher::DescriptorDistance(cv::Mat(1, dcols, dtype, a), cv::Mat(1, dcols, dtype, b), (DescriptorType)desc_type);
 }
@@ -616,6 +635,9 @@ def build(force=False):
     parts.append(cut("src/Frame.cc", r"^void Frame::AssignFeaturesToGrid\(\)"))
     parts.append(cut("src/Frame.cc", r"^vector<size_t> Frame::GetFeaturesInArea\("))
     parts.append(cut("src/Frame.cc", r"^bool Frame::PosInGrid\("))
+    parts.append(cut("src/Frame.cc", r"^bool Frame::isInFrustum\("))
+    parts.append(cut("src/MapPoint.cc", r"^float MapPoint::PredictSize\(").replace("MapPoint::PredictSize(", "MapPoint::PredictSizeRef("))
+    parts.append(cut("src/MapPoint.cc", r"^float MapPoint::PredictSigma\(").replace("MapPoint::PredictSigma(", "MapPoint::PredictSigmaRef("))
     parts.append(cut("src/FeatureMatcher.cc", r"^int FeatureMatcher::SearchForInitialization\("))
     parts.append(cut("src/FeatureMatcher.cc", r"^int FeatureMatcher::SearchByProjection\(Frame &F, const vector<Pt> &vpMapPoints, const float& radiusTh\)"))
     parts.append(cut("src/FeatureMatcher.cc", r"^float FeatureMatcher::RadiusByViewingCos\("))

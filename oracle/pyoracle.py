@@ -536,3 +536,17 @@ def orbslam2_extract(gray, nfeatures=1000, nlevels=8, scale_factor=1.2, ini_th=2
                                     _p(kps), _p(desc), _p(ksz), cap, C.byref(n))
     assert rc == 0, rc
     return kps[:n.value].copy(), desc[:n.value].copy(), ksz[:n.value].copy()
+
+
+def is_in_frustum(Pw, normal, min_dist, max_dist, ref_size, ref_sigma, ref_dist, pose16, cam5, bounds4, cos_limit=0.5,
+                  radius_factor=1.0, size_tol=1.5):
+    """Frame::isInFrustum (src/Frame.cc:276-331) + SearchByProjection's window prologue; returns in_view, proj3, track3, qr, qmin, qmax."""
+    f32 = lambda a: np.ascontiguousarray(a, np.float32)
+    Pw, normal = f32(Pw), f32(normal)
+    M = len(Pw)
+    iv = np.zeros(M, np.uint8); proj = np.zeros((M, 3), np.float32); track = np.zeros((M, 3), np.float32)
+    qr = np.zeros(M, np.float32); qmin = np.zeros(M, np.float32); qmax = np.zeros(M, np.float32)
+    lib().orc_is_in_frustum(_p(Pw), _p(normal), _p(f32(min_dist)), _p(f32(max_dist)), _p(f32(ref_size)), _p(f32(ref_sigma)), _p(f32(ref_dist)),
+                            M, _p(f32(pose16)), _p(f32(cam5)), _p(f32(bounds4)), _f(cos_limit), _f(radius_factor), _f(size_tol),
+                            _p(iv), _p(proj), _p(track), _p(qr), _p(qmin), _p(qmax))
+    return iv, proj, track, qr, qmin, qmax

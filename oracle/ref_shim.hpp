@@ -14,6 +14,7 @@
 #include <list>
 #include <map>
 #include <memory>
+#include <mutex>
 #include <set>
 #include <string>
 #include <unordered_map>
@@ -179,7 +180,12 @@ struct MapPoint {                                // include/MapPoint.h: the memb
     float GetMaxDistanceInvariance() const { return maxDist; }
     float GetMinDistanceInvariance() const { return minDist; }
     vec3f GetNormal() const { return normal; }
-    float PredictSize(const float&) const { return trackSize; }
+    // PredictSize / PredictSigma: the searches' test set-up presets trackSize; with realPredict the reference's own bodies
+    // (src/MapPoint.cc:432-442, cut as PredictSizeRef / PredictSigmaRef) run on refSize / refSigma / refDistance
+    bool realPredict = false; float refSize = 1, refSigma = 1, refDistance = 1; std::mutex mMutexPos;
+    float PredictSizeRef(const float& currentDist); float PredictSigmaRef(const float& currentDist);
+    float PredictSize(const float& d) { return realPredict ? PredictSizeRef(d) : trackSize; }
+    float PredictSigma(const float& d) { return realPredict ? PredictSigmaRef(d) : trackSigma; }
     bool IsInKeyFrame(const std::shared_ptr<KeyFrame>&) const { return inKF; }
     int GetIndexInKeyFrame(const std::shared_ptr<KeyFrame>&) const { return idxInKF2; }
     void Replace(const std::shared_ptr<MapPoint>& p) { replacedBy = p.get(); bad = true; }
@@ -222,6 +228,8 @@ public:
     std::vector<std::size_t> mGrid[FRAME_GRID_COLS][FRAME_GRID_ROWS];
     std::vector<cv::KeyPoint> mvKeys;
     mat4f Tcw; float fx = 1, fy = 1, cx = 0, cy = 0, mbf = 0, mb = 0;
+    mat3f Rcw; vec3f tcw, twc;                   // SetPose / UpdatePoseMatrices members isInFrustum reads (src/Frame.cc:262-274)
+    bool isInFrustum(Pt pMP, float viewingCosLimit);
     std::vector<bool> mvbOutlier;
     DBoW2::FeatureVector mFeatVec;
     std::vector<Pt> pts;                         // map point held by each keypoint

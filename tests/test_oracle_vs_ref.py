@@ -594,3 +594,25 @@ def test_search_for_triangulation_vs_reference_code(ref, synth, feature):
     n_in, m_in = po.bow_match(2, dt, k0, d0, n1, h1, k1, d1, n2, h2, th_low=th, F12=F12, epipole=(320.0, 240.0), sigma2_2=sigma2)
     near = (np.hypot(k1["x"] - 320.0, k1["y"] - 240.0) ** 2 < 100.0 * s1)
     assert n_in <= n_o and not near[m_in[m_in >= 0]].any()
+
+
+def test_is_in_frustum_vs_reference_code(ref):
+    """Frame::isInFrustum + MapPoint::PredictSize / PredictSigma (src/Frame.cc:276-331, src/MapPoint.cc:432-442), compiled from the
+    reference with the shim's Eigen look-alikes, against the oracle: identical decisions and values."""
+    from frustum_case import make_case
+    seen = set()
+    for seed in range(4):
+        c = make_case(seed)
+        M = len(c["Pw"])
+        iv, proj, track, qr, qmin, qmax = po.is_in_frustum(cos_limit=0.5, radius_factor=1.5, size_tol=1.5, **c)
+        riv = np.zeros(M, np.uint8); rproj = np.zeros((M, 3), np.float32); rtrack = np.zeros((M, 3), np.float32)
+        ref.ref_is_in_frustum(_p(c["Pw"]), _p(c["normal"]), _p(c["min_dist"]), _p(c["max_dist"]), _p(c["ref_size"]), _p(c["ref_sigma"]),
+                              _p(c["ref_dist"]), M, _p(c["pose16"]), _p(c["cam5"]), _p(c["bounds4"]), C.c_float(0.5), _p(riv), _p(rproj), _p(rtrack))
+        assert (iv == riv).all()
+        v = iv.astype(bool)
+        assert 0.05 < v.mean() < 0.9
+        assert (proj[v] == rproj[v]).all() and (track[v] == rtrack[v]).all()
+        assert (qr[~v] == -1).all() and (qr[v] > 0).all()
+        assert np.allclose(qmin[v], track[v, 0] / 1.5, rtol=1e-6) and np.allclose(qmax[v], track[v, 0] * 1.5, rtol=1e-6)
+        seen |= set(np.round(qr[v] / (1.5 * track[v, 0]), 3).tolist())
+    assert seen == {2.5, 4.0}                                     # both RadiusByViewingCos branches
