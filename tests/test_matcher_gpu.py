@@ -196,7 +196,100 @@ def test_cpp_host_mirror_matches_python_path(pkg, synth, tmp_path, feature):
     assert int(got["n0"]) == int(n[0]) and int(got["n1"]) == int(n[1]) and int(got["matches"]) == int(nm[0])
     assert int(got["levels"]) == 8 and int(got["q0"]) == {"orb32": 217, "sift128": 502, "akaze61": 212, "brisk48": 347}[feature]
     assert int(got["hash"]) == h
+    assert int(got["pyr_default"]) == 800             # mvImagePyramid: 8 empty levels in the default build, like the reference
+    _check_cpp_mirror_against_oracle(pkg, got, feature, st, frames, k, d, s, n, ex, o)
     ex.close()
+
+
+def _fnv_ints(v):
+    h = 1469598103934665603
+    for x in np.asarray(v).tolist():
+        h = ((h ^ ((x + 1) & 0xffffffff)) * 1099511628211) & 0xffffffffffffffff
+    return h
+
+
+def _fnv_bytes(a, h=1469598103934665603):
+    for b in np.ascontiguousarray(a).view(np.uint8).reshape(-1).tolist():
+        h = ((h ^ b) * 1099511628211) & 0xffffffffffffffff
+    return h
+
+
+def _check_cpp_mirror_against_oracle(pkg, got, feature, st, frames, k, d, s, n, ex, o):
+    """Every other method of the C++ mirror (tests/cpp/host_api_test.cpp) against the ORACLE on the same inputs."""
+    import torch
+    from oracle import pyoracle as po
+    dt, th = st["feature_id"], float(st["matching_th"])
+    n0, n1 = int(n[0]), int(n[1])
+    k0, d0, s0 = k[0, :n0], d[0, :n0], s[0, :n0]
+    k1, d1, s1 = k[1, :n1], d[1, :n1], s[1, :n1]
+    if dt == 5:
+        d0 = d0.view(np.float32); d1 = d1.view(np.float32)
+    f32 = np.float32
+
+    def queries(kq, sq, dx, dy):
+        xy = np.stack([kq["x"] + f32(dx), kq["y"] + f32(dy)], axis=1).astype(np.float32)
+        r = (f32(6.0) * sq).astype(np.float32); r[9::10] = -1.0
+        return xy, r, (sq / f32(1.2)).astype(np.float32), (sq * f32(1.2)).astype(np.float32), kq["angle"].astype(np.float32)
+
+    qxy, qr, qmin, qmax, qang = queries(k0, s0, 1.5, -2.0)
+    occ = (np.arange(n1) % 7 == 0).astype(np.uint8)
+    for name, ratio, ang in (("proj_local", True, False), ("proj_sim3", False, False), ("proj_motion", False, True), ("proj_reloc", False, True)):
+        rn, rm = po.search_by_projection_ex(dt, d0, qxy, qr, qmin, qmax, k1, d1, s1, BOUNDS, qangle=qang if ang else None, occupied=occ, claim=True,
+                                            th=th, nnratio=0.8, ratio_same_scale=ratio, tol=1.2)
+        assert int(got[name]) == rn and int(got[name + "_h"]) == _fnv_ints(rm), name
+        assert int(got[name + "_occ"]) == int(occ.sum()) + rn and rn > 50
+    inf = (f32(1.0) / (s1 * s1)).astype(np.float32)
+    for gate in (1, 0):
+        rn, rm = po.search_by_projection_ex(dt, d0, qxy, qr, qmin, qmax, k1, d1, s1, BOUNDS, tinf1d=inf if gate else None, claim=False, th=th,
+                                            nnratio=0.8, ratio_same_scale=False, tol=1.2)
+        assert int(got["fuse%d" % gate]) == rn and int(got["fuse%d_h" % gate]) == _fnv_ints(rm), gate
+    q2 = queries(k1, s1, -1.5, 2.0)
+    rn, rm = po.search_by_sim3(dt, k0, d0, s0, qxy, qr, qmin, qmax, k1, d1, s1, q2[0], q2[1], q2[2], q2[3], BOUNDS, th)
+    assert int(got["sim3"]) == rn and int(got["sim3_h"]) == _fnv_ints(rm) and rn > 50
+    if dt != 5:
+        node0 = (d0[:, 0] % 24).astype(np.int32); node1 = (d1[:, 0] % 24).astype(np.int32)
+        v0 = (np.arange(n0) % 5 != 0).astype(np.uint8); v1 = (np.arange(n1) % 4 != 0).astype(np.uint8)
+        rn, rm = po.bow_match(0, dt, k0, d0, node0, v0, k1, d1, node1, None, th_low=th, nnratio=0.7, check_ori=True)
+        assert int(got["bow_kf_f"]) == rn and int(got["bow_kf_f_h"]) == _fnv_ints(rm) and rn > 20
+        rn, rm = po.bow_match(1, dt, k0, d0, node0, v0, k1, d1, node1, v1, th_low=th, nnratio=0.7, check_ori=True)
+        assert int(got["bow_kf_kf"]) == rn and int(got["bow_kf_kf_h"]) == _fnv_ints(rm) and rn > 20
+        h0 = (np.arange(n0) % 3 == 0).astype(np.uint8); h1 = (np.arange(n1) % 3 == 1).astype(np.uint8)
+        rn, rm = po.bow_match(2, dt, k0, d0, node0, h0, k1, d1, node1, h1, th_low=th, nnratio=0.6, check_ori=False,
+                              F12=[0, 0, 0, 0, 0, -1, 0, 1, 0], epipole=(1.0e6, 240.0), sigma2_2=(s1 * s1).astype(np.float32))
+        hp = 1469598103934665603
+        for i1 in np.nonzero(rm >= 0)[0].tolist():
+            for v in (i1, int(rm[i1])):
+                hp = ((hp ^ v) * 1099511628211) & 0xffffffffffffffff
+        assert int(got["triang"]) == rn and int(got["triang_h"]) == hp
+    un = po.undistort_keypoints(k0, [520.0, 520.0, 320.0, 240.0], [-0.28, 0.07, 0.0002, 0.00002, 0.0])
+    assert int(got["undist_h"]) == _fnv_bytes(un)
+    cs, ci = pkg.FeatureMatcher.grid_build(o[0], o[3], BOUNDS)
+    torch.cuda.synchronize()
+    cs1 = cs[1].cpu().numpy(); ci1 = ci[1].cpu().numpy()[:n1]
+    assert int(got["grid_items"]) == int(cs1[-1]) and int(got["grid_h"]) == _fnv_bytes(ci1[:int(cs1[-1])], _fnv_bytes(cs1))
+    idx = np.arange(n0)
+    depth = (f32(2.0) + (idx % 5).astype(np.float32)); depth[::9] *= -1
+    Pw = np.stack([(k0["x"] - f32(320)) / f32(520) * depth, (k0["y"] - f32(240)) / f32(520) * depth, depth], axis=1).astype(np.float32)
+    nrm = np.tile(np.array([0, 0, 1], np.float32), (n0, 1))
+    maxd = np.where(idx % 11 == 0, 1.0, 100.0).astype(np.float32)
+    pose = np.zeros(16, np.float32); pose[[0, 4, 8]] = 1
+    iv, proj, track, fr, fmin, fmax = po.is_in_frustum(Pw, nrm, np.full(n0, 0.1, np.float32), maxd, s0, np.ones(n0, np.float32), np.full(n0, 3.0, np.float32),
+                                                       pose, [520, 520, 320, 240, 0], [0, 640, 0, 480], cos_limit=0.5, radius_factor=3.0, size_tol=1.2)
+    uv = proj[:, :2].copy()
+    assert int(got["frustum_in"]) == int(iv.sum()) and 0 < iv.sum() < n0
+    assert int(got["frustum_h"]) == _fnv_bytes(fr, _fnv_bytes(uv, _fnv_bytes(iv)))
+    rn, rm = po.search_by_projection_ex(dt, d0, uv, fr, fmin, fmax, k1, d1, s1, BOUNDS, claim=True, th=th, nnratio=0.8, ratio_same_scale=True, tol=1.2)
+    assert int(got["local_points"]) == rn and int(got["local_points_h"]) == _fnv_ints(rm)
+    if feature == "orb32":
+        vk, vd, vs = po.orbslam2_extract(frames[0], 1000)
+        assert int(got["vanilla_n"]) == len(vk) and int(got["vanilla_h"]) == _fnv_bytes(vd, _fnv_bytes(vk))
+        l3 = po.orbslam2_pyramid(frames[0])[3]
+        assert got["pyr3"] == "%dx%d" % (l3.shape[1], l3.shape[0]) and int(got["pyr3_h"]) == _fnv_bytes(l3)
+        ex1 = pkg.FeatureExtractor("orb32", nfeatures=1000, max_batch=1, max_w=640, max_h=480)
+        kk, _, _ = ex1(frames[0])
+        nd = sum(len(ex1.debug_read(3, 0, l)) // 8 for l in range(8)); nk = sum(len(ex1.debug_read(4, 0, l)) // 8 for l in range(8))
+        assert int(got["hook_detect"]) == nd and int(got["hook_kept"]) == nk == len(kk) == int(got["hook_n"]) and nd > 5 * nk
+        ex1.close()
 
 
 @pytest.mark.parametrize("desc_type,D", [(1, 61), (2, 48), (5, 512)])
