@@ -10,6 +10,7 @@
 //   * loops whose iterations depend on earlier ones ("already matched", match stealing) stay sequential over
 //     queries inside one CTA per frame pair, with all candidate work of a query done in parallel.
 #include "afv_common.cuh"
+#include <algorithm>
 #include <atomic>
 #include <float.h>
 
@@ -257,6 +258,41 @@ extern "C" int afv_is_in_frustum(const float* d_Pw, const float* d_normal, const
     S.minX = bounds4[0]; S.maxX = bounds4[1]; S.minY = bounds4[2]; S.maxY = bounds4[3];
     k_in_frustum<<<(M + 255) / 256, 256, 0, as_stream(cuda_stream)>>>(d_Pw, d_normal, d_min_dist, d_max_dist, d_ref_size, d_ref_sigma, d_ref_dist, M, S,
             viewing_cos_limit, radius_factor, size_tolerance, d_in_view, d_proj3, d_track3, d_qr, d_qmin, d_qmax);
+    ++g_afv_launches;
+    AFV_CUDA_CHECK(cudaGetLastError());
+    return AFV_OK;
+}
+
+// ---- packed per-rank results for the multi-GPU gather: n[B] | nmatches[B] | matches12[B][cap] | kps[B][cap] |
+// desc[B][cap][D] copied into one contiguous message by ONE launch (the five tensors are 4-byte aligned: 32-bit copies) ------------
+struct AfvPackSeg { const uint32_t* src; long long off_w, nw; };            // destination offset / length in 32-bit words
+struct AfvPackSegs { AfvPackSeg s[5]; long long total_w; };
+__global__ void __launch_bounds__(256) k_pack_results(const AfvPackSegs S, uint32_t* __restrict__ dst) {
+    const long long stride = (long long)gridDim.x * 256;
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < S.total_w; i += stride) {
+        int k = 0;
+#pragma unroll
+        for (int j = 1; j < 5; ++j) k += i >= S.s[j].off_w;
+        dst[i] = S.s[k].src[i - S.s[k].off_w];
+    }
+}
+extern "C" size_t afv_pack_results_bytes(int B, int cap, int desc_bytes) {
+    return (size_t)B * 8 + (size_t)B * cap * (4 + 28) + (((size_t)B * cap * desc_bytes + 3) & ~(size_t)3);
+}
+extern "C" int afv_pack_results(const int* d_n, const int* d_nmatches, const int* d_matches12, const afv_keypoint* d_kps, const void* d_desc,
+                                int B, int cap, int desc_bytes, void* d_pack, void* cuda_stream) {
+    if (!d_n || !d_nmatches || !d_matches12 || !d_kps || !d_desc || !d_pack || B < 1 || cap < 1 || desc_bytes < 1 || ((uintptr_t)d_desc & 3) || ((uintptr_t)d_pack & 3)) {
+        afv_set_error("afv_pack_results: bad argument"); return AFV_ERR_INVALID;
+    }
+    AfvPackSegs S;
+    const long long nw[5] = {B, B, (long long)B * cap, (long long)B * cap * 7, ((long long)B * cap * desc_bytes + 3) / 4};
+    const void* src[5] = {d_n, d_nmatches, d_matches12, d_kps, d_desc};
+    long long off = 0;
+    for (int i = 0; i < 5; ++i) { S.s[i].src = (const uint32_t*)src[i]; S.s[i].off_w = off; S.s[i].nw = nw[i]; off += nw[i]; }
+    S.total_w = off;
+    (void)cudaGetLastError();
+    const int blocks = (int)std::min<long long>((off + 255) / 256, 148 * 16);
+    k_pack_results<<<blocks, 256, 0, as_stream(cuda_stream)>>>(S, (uint32_t*)d_pack);
     ++g_afv_launches;
     AFV_CUDA_CHECK(cudaGetLastError());
     return AFV_OK;

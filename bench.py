@@ -497,6 +497,156 @@ def run_matcher(args):
 # ---------------------------------------------------------------------------------------------------------
 # GPU arm
 # ---------------------------------------------------------------------------------------------------------
+C5_STREAMS, C5_FRAMES_PER_STREAM, C5_W, C5_H, C5_NFEAT = 8, 128, 1280, 720, 2000
+
+
+def c5_rank_frames(pkg, world, rank, frames_per_stream=C5_FRAMES_PER_STREAM, unique=16, w=C5_W, h=C5_H):
+    """BASELINE configs[4] / SURVEY 8e: 8 FIXED streams, stream i lives on rank i % world (sharding.streams_of_rank); every stream is
+    `frames_per_stream` frames long (16 unique synthetic frames, repeated).  Returns (frames u8 [B,h,w], pair_a, pair_b, stream ids)."""
+    mine = pkg.sharding.streams_of_rank(C5_STREAMS, world, rank)
+    reps = (frames_per_stream + unique - 1) // unique
+    parts = [np.concatenate([pkg.synth.stream_frames(w, h, s, unique)[0]] * reps, axis=0)[:frames_per_stream] for s in mine]
+    frames = np.ascontiguousarray(np.concatenate(parts, axis=0))
+    idx = np.arange(len(frames))
+    start = (idx // unique) * unique
+    nxt = np.minimum(start + (idx - start + 1) % unique, len(frames) - 1)
+    return frames, idx.astype(np.int32), nxt.astype(np.int32), mine
+
+
+def c5_strong(pkg, torch, dist, rank, world, local, steps, warmup, frames_per_stream=C5_FRAMES_PER_STREAM):
+    """The configuration the north star names for N GPUs: orb32 1280x720 / 2000 kp, 8 fixed streams x 128 frames = 1024 frames per
+    step in TOTAL (strong scaling), streams partitioned over the ranks, extraction + SearchForInitialization per rank with no data-path
+    collective, then the packed results (afv_pack_results) gathered to rank 0 over NCCL.  Inside warm-up rank 0 unpacks EVERY rank's
+    gathered message (sharding.unpack_results) and compares it with that rank's own checksums; the sum of the checksums over all ranks
+    is independent of N and printed so runs at 1 / 2 / 4 / 8 GPUs can be compared.  Returns the result block (rank 0) or None."""
+    dev = torch.device("cuda", local)
+    sh = pkg.sharding
+    frames, pa, pb, mine = c5_rank_frames(pkg, world, rank, frames_per_stream)
+    B = len(frames)
+    ex = pkg.FeatureExtractor("orb32", nfeatures=C5_NFEAT, device=local, max_batch=B, max_w=C5_W, max_h=C5_H)
+    cap = ex.cap
+    fm = pkg.FeatureMatcher(nnratio=0.9, check_ori=True, desc_type=0, th_low=75.0)
+    bounds = (0.0, 0.0, float(C5_W), float(C5_H))
+    h_gray = torch.from_numpy(frames).pin_memory()
+    d_gray = h_gray.to(dev)
+    d_pa = torch.from_numpy(pa).to(dev); d_pb = torch.from_numpy(pb).to(dev)
+    out = ex.alloc_device_outputs(B)
+    m12 = torch.empty((B, cap), dtype=torch.int32, device=dev); nm = torch.empty((B,), dtype=torch.int32, device=dev)
+    _, pack_bytes = sh.pack_layout(B, cap, 32)
+    d_pack = [torch.empty(pack_bytes, dtype=torch.uint8, device=dev) for _ in range(2)]
+    gathered = [[torch.empty(pack_bytes, dtype=torch.uint8, device=dev) for _ in range(world)] if rank == 0 else None for _ in range(2)]
+    h_gathered = torch.empty((world, pack_bytes), dtype=torch.uint8).pin_memory() if rank == 0 else None
+    pending = [None, None]
+    cnt = [0]
+    stream = torch.cuda.current_stream()
+
+    def step(src):
+        ex.extract_batch_device(src, out, stream)
+        fm.search_for_initialization(out[0], out[1], out[2], out[3], d_pa, d_pb, None, bounds, MAX_KPT_SIZE, window=100, matches12=m12, nmatches=nm, stream=stream)
+        k = cnt[0] & 1; cnt[0] += 1
+        if pending[k] is not None:
+            pending[k].wait()
+        sh.pack_results(d_pack[k], out[3], nm, m12, out[0], out[1])
+        if world > 1:
+            pending[k] = dist.gather(d_pack[k], gathered[k], dst=0, async_op=True)
+        return k
+
+    def drain():
+        for k in range(2):
+            if pending[k] is not None:
+                pending[k].wait(); pending[k] = None
+
+    def checksums(n_, nm_, m12_, desc_):
+        """order-independent over frames, position-dependent inside a frame: catches a swapped, truncated or shifted message"""
+        nn = np.asarray(n_, np.int64); w = np.arange(1, 33, dtype=np.int64)
+        dsum = 0
+        for f in range(len(nn)):
+            dsum += int((np.asarray(desc_[f, :nn[f]], np.int64) * w).sum())
+        msum = int(sum(int(np.asarray(m12_[f, :nn[f]], np.int64).sum()) for f in range(len(nn))))
+        return np.array([int(nn.sum()), int(np.asarray(nm_, np.int64).sum()), msum, dsum], np.int64)
+
+    for _ in range(max(warmup, 3)):
+        k_last = step(d_gray)
+    drain(); torch.cuda.synchronize()
+    ex.status()
+    mine_chk = checksums(out[3].cpu().numpy(), nm.cpu().numpy(), m12.cpu().numpy(), out[1].cpu().numpy())
+    all_chk = torch.zeros((world, 4), dtype=torch.int64, device=dev)
+    my_t = torch.from_numpy(mine_chk).to(dev)
+    if world > 1:
+        dist.all_gather_into_tensor(all_chk, my_t)
+    else:
+        all_chk[0] = my_t
+    validated = 0
+    mismatch = []
+    if rank == 0:
+        for r in range(world):
+            src = gathered[k_last][r] if world > 1 else d_pack[k_last]
+            h_gathered[r].copy_(src)
+        torch.cuda.synchronize()
+        for r in range(world):
+            u = sh.unpack_results(h_gathered[r].numpy(), B, cap, 32)
+            got = checksums(u["n"], u["nmatches"], u["matches12"], u["desc"])
+            # no assert here: a rank-0-only exception would leave the other ranks waiting in the next collective
+            if (got == all_chk[r].cpu().numpy()).all() and u["n"].min() >= C5_NFEAT and u["n"].max() <= cap:
+                validated += 1
+            else:
+                mismatch.append(r)
+    total_chk = all_chk.sum(dim=0).cpu().numpy().tolist()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    barrier(); e0.record()
+    for _ in range(steps):
+        step(d_gray)
+    drain(); e1.record(); barrier()
+    ms = e0.elapsed_time(e1)
+    # end to end: frames from pinned host memory every step, gathered messages read back to pinned host memory on rank 0
+    d_in = torch.empty_like(d_gray)
+
+    def e2e_step():
+        d_in.copy_(h_gray, non_blocking=True)
+        k = step(d_in)
+        if world > 1:
+            pending[k].wait(); pending[k] = None
+        if rank == 0:
+            for r in range(world):
+                h_gathered[r].copy_(gathered[k][r] if world > 1 else d_pack[k], non_blocking=True)
+    e2e_step(); drain(); torch.cuda.synchronize()
+    f0 = torch.cuda.Event(enable_timing=True); f1 = torch.cuda.Event(enable_timing=True)
+    barrier(); t0 = time.perf_counter(); f0.record()
+    for _ in range(steps):
+        e2e_step()
+    drain(); f1.record(); barrier()
+    ms_e2e = max(f0.elapsed_time(f1), (time.perf_counter() - t0) * 1e3)
+    # host -> device ceiling with every rank copying at once (what bounds the e2e leg when several GPUs share one host)
+    g0 = torch.cuda.Event(enable_timing=True); g1 = torch.cuda.Event(enable_timing=True)
+    barrier(); g0.record()
+    for _ in range(4):
+        d_in.copy_(h_gray, non_blocking=True)
+    g1.record(); barrier()
+    ms_h2d = g0.elapsed_time(g1)
+    t = torch.tensor([ms, ms_e2e, ms_h2d], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, ms_e2e, ms_h2d = float(t[0]), float(t[1]), float(t[2])
+    ex.close()
+    if rank != 0:
+        return None
+    total = B * world
+    return {"workload": WORKLOADS["c5"]["name"], "scaling": "strong", "frames_per_step_total": total, "streams": C5_STREAMS,
+            "frames_per_stream": frames_per_stream, "streams_of_rank0": mine, "frames_per_step_per_gpu": B,
+            "value": total * steps / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms / steps,
+            "e2e": {"value": total * steps / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e / steps, "h2d_bytes_per_step_per_gpu": int(h_gray.numel()),
+                    "d2h_bytes_per_step_rank0": int(world * pack_bytes),
+                    "pipeline": "H2D, kernels, gather and D2H of a step in sequence on one stream (no overlap across steps)"},
+            "h2d_gbs_aggregate_all_ranks_concurrent": 4.0 * h_gray.numel() * world / (ms_h2d * 1e-3) / 1e9,
+            "gather_bytes_per_step": int((world - 1) * pack_bytes), "validated_ranks": validated, "mismatching_ranks": mismatch,
+            "checksum_all_ranks": total_chk, "checksum_note": "[keypoints, matches, sum of match indices, weighted descriptor sum] summed over all ranks: independent of n_gpus"}
+
+
 def run_gpu(args):
     import torch
     import torch.distributed as dist
@@ -508,13 +658,18 @@ def run_gpu(args):
     dev = torch.device("cuda", local)
     if world > 1:
         import datetime
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"             # keep stdout to the one JSON line (NCCL prints its version there)
         dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=180))
     pkg = load_pkg()
     lib = pkg.lib()
     B = args.batch
-    frames, pa, pb = make_frames(pkg, B, rank)
+    STRONG = args.workload == "c5"
+    if STRONG:
+        # configs[4]: 8 FIXED streams partitioned over the ranks (stream i -> rank i % world), total work independent of n_gpus
+        frames, pa, pb, _ = c5_rank_frames(pkg, world, rank, args.c5_frames)
+        B = args.batch = len(frames)
+        args.e2e_chunk = min(args.e2e_chunk, B)
+    else:
+        frames, pa, pb = make_frames(pkg, B, rank)
     FEAT = WL["feature"]
     ex = pkg.FeatureExtractor(FEAT, nfeatures=NFEAT, device=local, max_batch=B, max_w=W, max_h=H)
     cap = ex.cap
@@ -679,6 +834,13 @@ def run_gpu(args):
     value = total_frames / (ms * 1e-3)
     e2e_value = total_frames / (ms_e2e * 1e-3)
 
+    # ---- the north star's multi-GPU configuration (8 fixed streams, strong scaling, validated gather) as an extra block of the line
+    c5_block = None
+    if args.c5_block and FEAT == "orb32" and not MIXED:
+        try:
+            c5_block = c5_strong(pkg, torch, dist, rank, world, local, min(args.steps, 10), 3, args.c5_frames)
+        except Exception as e:
+            c5_block = {"error": repr(e)}
     line = None
     if rank == 0:
         # ---- per-kernel event timing on instrumented extra steps (same inputs), dominant kernel -> roofline
@@ -799,7 +961,7 @@ def run_gpu(args):
                 matcher = {"error": repr(e)}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong" if STRONG else "weak", "vs_baseline": None,
             "dtype": "u8" if FEAT == "orb32" else "f32", "data": "synthetic",
             "config": {"workload": WL["name"],
                        "frames_per_step_per_gpu": B, "pairs_per_step_per_gpu": B, "parallelism": "frames sharded, dp%d" % world,
@@ -811,6 +973,7 @@ def run_gpu(args):
             "clocks": sampler.summary() if sampler else None,
             "roofline": roofline,
             "matcher": matcher,
+            "c5": c5_block,
             "cpu_baseline": cpu_baseline,
             "check": {"kps_per_frame": [int(n_host.min()), int(n_host.max())], "matches_per_pair_mean": float(nm_host.mean()),
                       "brisk48_kps_per_frame": [int(out2[3].min()), int(out2[3].max())] if MIXED else None,
@@ -837,6 +1000,9 @@ def main():
     ap.add_argument("--pairs", type=int, default=10240, help="m1: frame pairs per step")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-gather", dest="gather", action="store_false")
+    ap.add_argument("--no-c5-block", dest="c5_block", action="store_false",
+                    help="skip the extra c5 block (8 fixed 1280x720 streams partitioned over the ranks, strong scaling, validated NCCL gather)")
+    ap.add_argument("--c5-frames", type=int, default=C5_FRAMES_PER_STREAM, help="frames per stream of the c5 configuration (BASELINE: 128)")
     ap.add_argument("--real-parts", action="store_true",
                     help="--impl reference, orb32 workloads: time the pipeline assembled from the reference's real parts (cv2 binary + "
                          "oracle/_ref) instead of the oracle C port.  Informational: it is SLOWER than the port (per-level ORB.compute "

@@ -305,6 +305,14 @@ int  afv_distinctive_descriptors(int desc_type, const void* d_desc, const int* d
 int  afv_descriptor_distance(int desc_type, const void* d_a, const void* d_b, int n, float* d_out,
                              void* cuda_stream);
 
+/* Multi-GPU result exchange (BASELINE configs[4]): one rank's fixed-capacity results as ONE contiguous message
+ *   n[B] i32 | nmatches[B] i32 | matches12[B][cap] i32 | kps[B][cap] (28 B) | desc[B][cap][desc_bytes] (padded to 4 bytes)
+ * written by a single launch; the host side gathers the messages with NCCL (anyfeature-vslam_b200/sharding.py).  The last byte of an
+ * unaligned descriptor block (B * cap * desc_bytes not a multiple of 4) is read up to 3 bytes past the array: allocate accordingly. */
+size_t afv_pack_results_bytes(int B, int cap, int desc_bytes);
+int    afv_pack_results(const int* d_n, const int* d_nmatches, const int* d_matches12, const afv_keypoint* d_kps, const void* d_desc,
+                        int B, int cap, int desc_bytes, void* d_pack, void* cuda_stream);
+
 /* ---- misc ------------------------------------------------------------------------------------------------ */
 const char* afv_last_error(void);
 /* number of kernels this library has launched since load (bench.py's gpu_launches) */

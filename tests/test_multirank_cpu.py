@@ -91,3 +91,24 @@ def test_bench_frames_differ_across_ranks_and_pairs_stay_in_stream():
     f1, _, _ = b.make_frames(pkg, 32, 1, unique_streams=2, frames_per_stream=16)
     assert f0.shape == (32, 480, 640) and (f0 != f1).any()
     assert (pa == np.arange(32)).all() and (pb // 16 == pa // 16).all() and ((pb - pa) % 16 == 1).all()
+
+
+def test_c5_strong_partition_is_fixed_work():
+    """bench.py's c5 data plan: 8 fixed streams, stream i on rank i % world, total frames independent of world, pairs
+    stay inside their stream, and the union over ranks is the same set of streams for every world size."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("afv_bench", os.path.join(os.path.dirname(os.path.dirname(__file__)), "bench.py"))
+    b = importlib.util.module_from_spec(spec); spec.loader.exec_module(b)
+    pkg = load_pkg()
+    ref = None
+    for world in (1, 2, 4, 8):
+        per_rank = [b.c5_rank_frames(pkg, world, r, frames_per_stream=8, unique=4, w=96, h=64) for r in range(world)]
+        assert sum(len(f) for f, _, _, _ in per_rank) == 8 * 8
+        assert sorted(sum((m for _, _, _, m in per_rank), [])) == list(range(8))
+        crc = 0
+        for f, pa, pb, mine in per_rank:
+            assert len(f) == 8 * len(mine) and (pa == np.arange(len(f))).all()
+            assert (pb // 4 == pa // 4).all() and (pb // 8 == pa // 8).all()          # next frame of the same 4-cycle of the same stream
+            crc += int(f.astype(np.int64).sum())
+        ref = crc if ref is None else ref
+        assert crc == ref
