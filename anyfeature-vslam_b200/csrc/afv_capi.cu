@@ -48,6 +48,7 @@ void afv_prof_end(cudaStream_t st) {
     if (!g_prof_on || g_prof_recs.empty()) return;
     cudaEventRecord(g_prof_recs.back().e1, st);
 }
+bool afv_prof_is_on() { return g_prof_on; }
 extern "C" int afv_profile_enable(int on) { g_prof_on = on != 0; return AFV_OK; }
 // Synchronises, sums the recorded launches per kernel name and clears the records.
 // names: max_n x 32 chars; ms / calls: max_n.  Returns the number of distinct kernels.
@@ -267,7 +268,12 @@ extern "C" int afv_extractor_create(afv_extractor** out, int feature_id, int nfe
         *out = ex;
         return AFV_OK;
     }
-    AFV_CUDA_CHECK(cudaStreamCreateWithFlags(&ex->aux.stream, cudaStreamNonBlocking));
+    {   // the side stream carries the latency-bound selection kernels (k_harris_select, k_octree): highest priority, so their few
+        // CTAs are placed ahead of the hundreds of thousands of blur tiles queued on the caller's stream
+        int prio_least = 0, prio_greatest = 0;
+        AFV_CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest));
+        AFV_CUDA_CHECK(cudaStreamCreateWithPriority(&ex->aux.stream, cudaStreamNonBlocking, prio_greatest));
+    }
     AFV_CUDA_CHECK(cudaEventCreateWithFlags(&ex->aux.ev_pyr, cudaEventDisableTiming));
     AFV_CUDA_CHECK(cudaEventCreateWithFlags(&ex->aux.ev_blur, cudaEventDisableTiming));
 

@@ -78,6 +78,7 @@ extern long long g_afv_launches;
 // optional per-kernel CUDA-event timing (bench.py's roofline leg): AFV_PROF_BEGIN/END bracket one launch
 void afv_prof_begin(const char* name, cudaStream_t st);
 void afv_prof_end(cudaStream_t st);
+bool afv_prof_is_on();
 struct AfvProfScope { cudaStream_t st; AfvProfScope(const char* n, cudaStream_t s) : st(s) { afv_prof_begin(n, s); } ~AfvProfScope() { afv_prof_end(st); } };
 void afv_set_error(const char* fmt, ...);
 #define AFV_CUDA_CHECK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { \

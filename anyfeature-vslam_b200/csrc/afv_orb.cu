@@ -54,11 +54,12 @@ __device__ __forceinline__ int refl101(int i, int n) {
 // ------------------------------------------------------------------------------------------------------
 // K2: pyramid level from the previous one.  thread = 4 consecutive output pixels (one 32-bit store).
 // ------------------------------------------------------------------------------------------------------
-// One CTA = 128x16 output pixels.  The source footprint (<= 160 x 22 bytes at scale 1.2) is staged in shared memory
+// One CTA = 128x32 output pixels.  The source footprint (<= 160 x 41 bytes at scale 1.2) is staged in shared memory
 // with aligned 32-bit loads; taps are byte LDS with 32-bit addressing (the global-pointer version spent most of its
 // instructions on 64-bit address arithmetic).  Thread = 4 columns x 2 rows; coefficients come as one 128-bit load of
-// 4 packed table entries (offset << 16 | c1).
-#define RS_ROWS 24
+// 4 packed table entries (offset << 16 | c1).  (128 x 16 tiles spent a quarter of their instructions on the per-CTA prologue.)
+#define RS_ROWS 44                    // source rows of 32 output rows at scale 1.2 (38.4) + the second tap + slack
+#define RS_OUT_H 32
 #define RS_PITCH 176
 __global__ void __launch_bounds__(256) k_resize(const __grid_constant__ AfvParams P, const __grid_constant__ CUtensorMap tm_src, int l) {
     __shared__ __align__(128) uint8_t sp[RS_ROWS][RS_PITCH];
@@ -66,7 +67,7 @@ __global__ void __launch_bounds__(256) k_resize(const __grid_constant__ AfvParam
     const AfvLevel& D = P.lv[l];
     const AfvLevel& S = P.lv[l - 1];
     const int f = blockIdx.z, tid = threadIdx.x, lane = tid & 31, wrp = tid >> 5;
-    const int tx0 = blockIdx.x * 128, ty0 = blockIdx.y * 16;
+    const int tx0 = blockIdx.x * 128, ty0 = blockIdx.y * RS_OUT_H;
     const int sxb = (int)(D.xtab[tx0] >> 16) & ~15;                // first staged source column (16-B aligned for TMA)
     const int syb = (int)(D.ytab[ty0] >> 16);                      // first staged source row
     // source footprint (<= 172 x 22 bytes incl. alignment slack) by one TMA box; rows / columns past the source are
@@ -85,8 +86,8 @@ __global__ void __launch_bounds__(256) k_resize(const __grid_constant__ AfvParam
     const uint32_t xe[4] = {xt.x, xt.y, xt.z, xt.w};
     uint8_t* dstf = const_cast<uint8_t*>(D.img) + (long long)f * D.img_fstride;
 #pragma unroll
-    for (int rr = 0; rr < 2; ++rr) {
-        const int y = ty0 + 2 * wrp + rr;
+    for (int rr = 0; rr < RS_OUT_H / 8; ++rr) {
+        const int y = ty0 + (RS_OUT_H / 8) * wrp + rr;
         if (y >= D.h) break;
         const uint32_t yt = D.ytab[y];
         const int yo = yt >> 16, c1y = yt & 0xffff, c0y = 256 - c1y;
@@ -146,7 +147,7 @@ __device__ __forceinline__ void warp_push(bool pass, uint16_t val, uint16_t* lis
 __global__ void __launch_bounds__(256) k_fast(const __grid_constant__ AfvParams P, const __grid_constant__ AfvTmaps TM) {
     __shared__ __align__(128) uint32_t pixw[FT_PH][FT_WP];
     __shared__ __align__(8) uint64_t tma_bar;
-    __shared__ __align__(4) uint8_t score[FT_RH][FT_SW];
+    __shared__ __align__(16) uint8_t score[FT_RH][FT_SW + 4];          // 34 x 136 = 289 x 16 bytes: zeroed with 128-bit stores
     __shared__ uint16_t slist[FT_RW * FT_RH];        // stage-1 survivors
     __shared__ uint16_t clist[FT_RW * FT_RH];        // corners
     __shared__ uint32_t surv[(FT_W / 2) * (FT_H / 2) + 64];
@@ -173,7 +174,8 @@ __global__ void __launch_bounds__(256) k_fast(const __grid_constant__ AfvParams 
         mbar_expect_tx(&tma_bar, FT_PH * FT_WP * 4);
         tma_load_3d(&pixw[0][0], &TM.m[l], &tma_bar, x0 - 16, y0 - 4, f);
     }
-    for (int i = tid; i < FT_RH * FT_SW / 4; i += 256) reinterpret_cast<uint32_t*>(&score[0][0])[i] = 0;
+    static_assert((FT_RH * (FT_SW + 4)) % 16 == 0, "score tile is a whole number of uint4");
+    for (int i = tid; i < FT_RH * (FT_SW + 4) / 16; i += 256) reinterpret_cast<uint4*>(&score[0][0])[i] = make_uint4(0, 0, 0, 0);
     mbar_wait(&tma_bar, 0);
     __syncthreads();
     (void)wrp;
@@ -225,17 +227,26 @@ __global__ void __launch_bounds__(256) k_fast(const __grid_constant__ AfvParams 
                 smask |= nib << (4 * j);
             }
             // validity: region columns c = 4*wc + k - 15 in [0, FT_RW) with 3 <= gx < w-3; region rows r = ch*FS1_ROWS + j < FT_RH with 3 <= gy < h-3
-            uint32_t cm = 0;
+            // region columns 4*wc - 15 + k: only the first and the last word column hold columns outside [0, FT_RW)
+            uint32_t cm = wc == FS1_WC0 ? 0x8u : (wc == FS1_WC0 + FS1_NWC - 1 ? 0x1u : 0xfu);
+            static_assert(4 * FS1_WC0 - 15 + 3 == 0 && 4 * (FS1_WC0 + FS1_NWC - 1) - 15 == FT_RW - 1, "edge word columns");
+            uint32_t vm;
+            if (x0 >= 4 && y0 >= 4 && x0 + FT_W + 4 <= L.w && y0 + FT_H + 4 <= L.h) {      // interior tile (uniform): no image-bound tests
+                vm = cm * 0x11111u;
+                if (ch == FS1_CH - 1) vm &= (1u << (4 * (FT_RH - (FS1_CH - 1) * FS1_ROWS))) - 1u;      // rows >= FT_RH of the last chunk
+            } else {
+                cm = 0;
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const int c = 4 * wc + k - 15, gx = x0 - 1 + c;
-                if (c >= 0 && c < FT_RW && gx >= 3 && gx < L.w - 3) cm |= 1u << k;
-            }
-            uint32_t vm = 0;
+                for (int k = 0; k < 4; ++k) {
+                    const int c = 4 * wc + k - 15, gx = x0 - 1 + c;
+                    if (c >= 0 && c < FT_RW && gx >= 3 && gx < L.w - 3) cm |= 1u << k;
+                }
+                vm = 0;
 #pragma unroll
-            for (int j = 0; j < FS1_ROWS; ++j) {
-                const int r = ch * FS1_ROWS + j, gy = y0 - 1 + r;
-                if (r < FT_RH && gy >= 3 && gy < L.h - 3) vm |= cm << (4 * j);
+                for (int j = 0; j < FS1_ROWS; ++j) {
+                    const int r = ch * FS1_ROWS + j, gy = y0 - 1 + r;
+                    if (r < FT_RH && gy >= 3 && gy < L.h - 3) vm |= cm << (4 * j);
+                }
             }
             smask &= vm;
         }
@@ -251,11 +262,10 @@ __global__ void __launch_bounds__(256) k_fast(const __grid_constant__ AfvParams 
         }
         int o = base + incl - cnt;
         const int i0 = ch * FS1_ROWS * FT_RW + 4 * wc - 15;
-        while (smask) {
-            const int bpos = __ffs(smask) - 1;
-            smask &= smask - 1;
-            slist[o++] = (uint16_t)(i0 + (bpos >> 2) * FT_RW + (bpos & 3));
-        }
+        // predicated, fully unrolled writer (a per-lane `while (smask)` loop ran at 5 of 32 lanes and cost 12 % of the kernel)
+#pragma unroll
+        for (int b = 0; b < 4 * FS1_ROWS; ++b)
+            if (smask & (1u << b)) slist[o++] = (uint16_t)(i0 + (b >> 2) * FT_RW + (b & 3));
     }
     __syncthreads();
     // stage 2: corner score of every stage-1 survivor = max over the 16 arcs of 9 of min|v - p| (same sign), minus 1 (OpenCV
@@ -275,7 +285,12 @@ __global__ void __launch_bounds__(256) k_fast(const __grid_constant__ AfvParams 
             const uint8_t* p = pb + (r + 3) * PITCH + FT_XOFF + (c + 3);
             const int v = p[0];
             uint32_t e[16];
-#define FDIFF(k, dx, dy) { const int dv = v - (int)p[(dy) * PITCH + (dx)]; e[k] = ((uint32_t)dv & 0xffffu) | ((uint32_t)(-dv) << 16); }
+            // e[k] = (256 + v - p_k) | (256 - v + p_k) << 16 as ONE multiply-add per circle pixel: p * 0xffff = (p << 16) - p, added to
+            // A = (256 + v) | (256 - v) << 16; both halves stay in [1, 511], so there is no borrow between them.  The bias of 256 is common
+            // to every half and drops out of the min / max chain (removed from the result below).  The kernel is ALU-pipe bound
+            // (ncu: ALU 76 %): IMAD issues on the FMA pipe, the sub / and / neg / shift-or form cost 4 ALU instructions per pixel.
+            const uint32_t A = (uint32_t)(256 + v) | ((uint32_t)(256 - v) << 16);
+#define FDIFF(k, dx, dy) e[k] = (uint32_t)p[(dy) * PITCH + (dx)] * 0xffffu + A;
             CIRC16(FDIFF)
 #undef FDIFF
             uint32_t m2[16], m4[16];
@@ -283,10 +298,10 @@ __global__ void __launch_bounds__(256) k_fast(const __grid_constant__ AfvParams 
             for (int k = 0; k < 16; ++k) m2[k] = __vmins2(e[k], e[(k + 1) & 15]);
 #pragma unroll
             for (int k = 0; k < 16; ++k) m4[k] = __vmins2(m2[k], m2[(k + 2) & 15]);
-            uint32_t acc = 0x80008000u;
+            uint32_t acc = 0;
 #pragma unroll
             for (int k = 0; k < 16; ++k) acc = __vmaxs2(acc, __vmins2(__vmins2(m4[k], m4[(k + 4) & 15]), e[(k + 8) & 15]));
-            const int bd = (int)(short)(acc & 0xffffu), bb = (int)(short)(acc >> 16);
+            const int bd = (int)(acc & 0xffffu) - 256, bb = (int)(acc >> 16) - 256;
             const int best = bd > bb ? bd : bb;
             corner = best > t;
             if (corner) score[r][c] = (uint8_t)(best - 1);
@@ -297,15 +312,27 @@ __global__ void __launch_bounds__(256) k_fast(const __grid_constant__ AfvParams 
     const int nc = ncorner;
 
     // 3x3 non-max suppression (strictly greater than all 8 neighbours), interior of the tile only
-    for (int j = tid; j < nc; j += 256) {
-        const int i = clist[j];
-        const int r = i / FT_RW, c = i % FT_RW;
-        if (r < 1 || r > FT_H || c < 1 || c > FT_W) continue;
-        const int s = score[r][c];
-        if (s > score[r][c - 1] && s > score[r][c + 1] && s > score[r - 1][c - 1] && s > score[r - 1][c] &&
-            s > score[r - 1][c + 1] && s > score[r + 1][c - 1] && s > score[r + 1][c] && s > score[r + 1][c + 1]) {
-            const int gx = x0 - 1 + c, gy = y0 - 1 + r;
-            surv[atomicAdd(&nsurv, 1)] = (uint32_t)gx | ((uint32_t)gy << 12) | ((uint32_t)s << 24);
+    for (int j0 = 0; j0 < nc; j0 += 256) {
+        const int j = j0 + tid;
+        bool keep = false;
+        uint32_t val = 0;
+        if (j < nc) {
+            const int i = clist[j];
+            const int r = i / FT_RW, c = i % FT_RW;
+            if (r >= 1 && r <= FT_H && c >= 1 && c <= FT_W) {
+                const int s = score[r][c];
+                keep = s > score[r][c - 1] && s > score[r][c + 1] && s > score[r - 1][c - 1] && s > score[r - 1][c] &&
+                       s > score[r - 1][c + 1] && s > score[r + 1][c - 1] && s > score[r + 1][c] && s > score[r + 1][c + 1];
+                val = (uint32_t)(x0 - 1 + c) | ((uint32_t)(y0 - 1 + r) << 12) | ((uint32_t)s << 24);
+            }
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, keep);               // one shared atomic per warp
+        if (m) {
+            int base = 0;
+            const int leader = __ffs(m) - 1;
+            if (lane == leader) base = atomicAdd(&nsurv, __popc(m));
+            base = __shfl_sync(0xffffffffu, base, leader);
+            if (keep) surv[base + __popc(m & ((1u << lane) - 1))] = val;
         }
     }
     __syncthreads();
@@ -373,8 +400,24 @@ __device__ float harris7(const uint8_t* img, int w, int h, int stride, int x0, i
     return __fmul_rn(r, s4);
 }
 
+// Suffix sums of a 256-bin histogram by the 256 threads of the CTA: S[b] = sum of hist[b..255] (the serial walk from bin 255 down by
+// one thread cost ~10 us per pass: the kernel is latency bound and runs 5 such selections per (frame, level)).
+__device__ __forceinline__ int suffix_sum_256(const int* hist, int* wsum, int tid) {
+    const int lane = tid & 31, wid = tid >> 5;
+    int v = hist[tid];
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_down_sync(0xffffffffu, v, o); if (lane + o < 32) v += t; }
+    if (lane == 0) wsum[wid] = v;
+    __syncthreads();
+#pragma unroll
+    for (int w = 1; w < 8; ++w) if (wid + w < 8) v += wsum[wid + w];
+    __syncthreads();
+    return v;
+}
+
 __global__ void __launch_bounds__(256) k_harris_select(const __grid_constant__ AfvParams P) {
     __shared__ int hist[256];
+    __shared__ int wsum[8];
     __shared__ int s_thr, s_np, s_k, s_m;
     __shared__ uint32_t s_prefix, s_mask;
     const int l = blockIdx.x, f = blockIdx.y, tid = threadIdx.x;
@@ -390,20 +433,21 @@ __global__ void __launch_bounds__(256) k_harris_select(const __grid_constant__ A
     __syncthreads();
     for (int i = tid; i < cnt; i += 256) atomicAdd(&hist[cand[i] >> 24], 1);
     __syncthreads();
-    if (tid == 0) {
+    {
+        // retainBest(2q) on the FAST score: threshold = the largest score s with #(score >= s) >= 2q (ties of the 2q-th all stay)
         const int n2 = 2 * L.q_orb;
-        int thr = 0, np = cnt;
+        const int S = suffix_sum_256(hist, wsum, tid);                   // S(tid) = #(score >= tid), non-increasing in tid
+        if (tid == 0) { s_thr = 0; s_np = cnt; }
+        __syncthreads();
         if (cnt > n2) {
-            if (n2 == 0) { thr = 256; np = 0; }
+            if (n2 == 0) { if (tid == 0) { s_thr = 256; s_np = 0; } }
             else {
-                int acc = 0, s = 255;
-                for (; s >= 0; --s) { acc += hist[s]; if (acc >= n2) break; }
-                thr = s; np = acc;
+                const int S1 = S - hist[tid];                             // S(tid + 1)
+                if (S >= n2 && S1 < n2) { s_thr = tid; s_np = S; }       // exactly one thread
             }
         }
-        s_thr = thr; s_np = np;
+        __syncthreads();
     }
-    __syncthreads();
     const int thr = s_thr, np = s_np;
     for (int i = tid; i < cnt; i += 256) {
         const uint32_t c = cand[i];
@@ -427,12 +471,16 @@ __global__ void __launch_bounds__(256) k_harris_select(const __grid_constant__ A
                     if ((key & mask) == prefix) atomicAdd(&hist[(key >> (8 * pass)) & 255], 1);
                 }
                 __syncthreads();
-                if (tid == 0) {
-                    int k = s_k, acc = 0, dgt = 255;
-                    for (; dgt >= 0; --dgt) { if (acc + hist[dgt] >= k) break; acc += hist[dgt]; }
-                    s_k = k - acc;
-                    s_prefix = prefix | ((uint32_t)dgt << (8 * pass));
-                    s_mask = mask | (0xffu << (8 * pass));
+                {
+                    // digit = the largest d with #(digit >= d) >= k; the k-th largest then has rank k - #(digit > d) inside that digit
+                    const int k = s_k;
+                    const int S = suffix_sum_256(hist, wsum, tid);
+                    const int S1 = S - hist[tid];
+                    if (S >= k && S1 < k) {                               // exactly one thread (S is non-increasing, S(0) >= k)
+                        s_k = k - S1;
+                        s_prefix = prefix | ((uint32_t)tid << (8 * pass));
+                        s_mask = mask | (0xffu << (8 * pass));
+                    }
                 }
                 __syncthreads();
             }
@@ -556,21 +604,32 @@ __global__ void __launch_bounds__(256) k_blur(const __grid_constant__ AfvParams 
         tma_load_3d(&in[0][0], &TM.m[ti.level], &tma_bar, x0 - 16, y0 - 3, f);
     }
     mbar_wait(&tma_bar, 0);
-    // REFLECT_101 patch of the halo that fell outside the level (border tiles only; uniform branch)
+    // REFLECT_101 patch of the halo that fell outside the level.  More than half of all tiles touch a level border (128 x 32 tiles on
+    // levels 640 .. 179 pixels wide), so the patch is kept off the common path of each case: the mirrored pixels are already in the
+    // staged tile (reflection distance <= 3), rows first (top / bottom tiles only), then 3 columns per side with one thread per byte.
     const int xend = min(x0 + BT_W, L.w);                         // outputs exist for gx < xend, taps reach xend + 2
-    if (x0 == 0 || y0 == 0 || xend + 3 > L.w || y0 + BT_H + 3 > L.h) {
-        __syncthreads();
+    (void)img;
+    {
         uint8_t* inb = reinterpret_cast<uint8_t*>(&in[0][0]);
-        for (int r = wrp; r < BT_H + 6; r += 8) {
-            const int gy = y0 - 3 + r;
-            if (gy > L.h + 2) break;
-            const uint8_t* row = img + (long long)refl101(gy, L.h) * L.img_stride;
-            uint8_t* dst = inb + r * (BT_WP * 4) + BT_XOFF - x0;     // dst[gx]
-            if (gy < 0 || gy >= L.h) {
-                for (int gx = x0 - 3 + lane; gx < xend + 3; gx += 32) dst[gx] = row[refl101(gx, L.w)];
-            } else {
-                if (x0 == 0 && lane < 3) dst[-1 - lane] = row[1 + lane];                       // gx = -1,-2,-3
-                if (xend + 3 > L.w && lane < 3 && L.w + lane < xend + 3) dst[L.w + lane] = row[L.w - 2 - lane];
+        constexpr int PB = BT_WP * 4;
+        const bool top = y0 == 0, bot = y0 + BT_H + 3 > L.h;
+        if (top || bot) {                                         // uniform
+            __syncthreads();
+            // staged row r holds image row y0 - 3 + r; rows -3..-1 mirror rows 3..1, rows h..h+2 mirror rows h-2..h-4
+            const int k = tid / 40, wq = tid - k * 40;            // 3 rows x 40 words per side
+            if (k < 3) {
+                if (top) in[2 - k][wq] = in[4 + k][wq];
+                if (bot) { const int rd = L.h + k - (y0 - 3), rs = L.h - 2 - k - (y0 - 3); if (rd < BT_H + 6) in[rd][wq] = in[rs][wq]; }
+            }
+        }
+        const bool lft = x0 == 0, rgt = xend + 3 > L.w;
+        if (lft || rgt) {                                         // uniform
+            __syncthreads();
+            const int r = tid / 6, k = tid - r * 6;               // 38 rows x (3 left + 3 right) bytes
+            if (r < BT_H + 6) {
+                uint8_t* dst = inb + r * PB + BT_XOFF - x0;       // dst[gx]
+                if (k < 3) { if (lft) dst[-1 - k] = dst[1 + k]; }
+                else if (rgt && L.w + (k - 3) < xend + 3) dst[L.w + (k - 3)] = dst[L.w - 2 - (k - 3)];
             }
         }
     }
@@ -803,24 +862,28 @@ int afv_launch_extract(const AfvParams& P, afv_keypoint* d_kps, uint8_t* d_desc,
     cudaMemsetAsync(P.counts, 0, sizeof(int) * 4 * AFV_MAX_LEVELS * P.B, st);
     cudaMemsetAsync(P.status, 0, sizeof(int) * P.B, st);
     for (int l = 1; l < P.nlevels; ++l) {
-        dim3 g((P.lv[l].w + 127) / 128, (P.lv[l].h + 15) / 16, P.B);
+        dim3 g((P.lv[l].w + 127) / 128, (P.lv[l].h + RS_OUT_H - 1) / RS_OUT_H, P.B);
         CUtensorMap tms;
         { const int rc = make_level_tmap(&tms, P.lv[l - 1], P.B, RS_PITCH, RS_ROWS); if (rc) return rc; }
         AfvProfScope ps("k_resize", st);
         k_resize<<<g, 256, 0, st>>>(P, tms, l);
         ++g_afv_launches;
     }
-    // The blur only needs the pyramid: it runs on the auxiliary stream next to the latency-bound selection / octree
-    // kernels of the main stream (it is released after k_fast, which saturates the SMs by itself); k_describe joins.
+    // After k_fast the work forks: the blur (ALU bound, 275 k tiles per 512 frames) stays on the caller's stream, the selection kernels
+    // (latency bound: one CTA per (frame, level), occupancy 37 %) go to the extractor's HIGH-PRIORITY side stream so that the block
+    // scheduler places their CTAs first and the blur fills the remaining slots; k_describe joins both.  (A low-priority blur on the
+    // side stream did not overlap: its tiles were queued first and the selection CTAs waited behind them.)  With per-kernel profiling
+    // on, everything runs on the caller's stream so that the event times are additive.
     { AfvProfScope ps("k_fast", st); k_fast<<<dim3(acc, P.B), 256, 0, st>>>(P, TM); ++g_afv_launches; }
+    const cudaStream_t sst = afv_prof_is_on() ? st : aux.stream;
     cudaEventRecord(aux.ev_pyr, st);
-    cudaStreamWaitEvent(aux.stream, aux.ev_pyr, 0);
-    { AfvProfScope ps("k_blur", aux.stream); k_blur<<<dim3(acc, P.B), 256, 0, aux.stream>>>(P, TMB); ++g_afv_launches; }
-    cudaEventRecord(aux.ev_blur, aux.stream);
-    { AfvProfScope ps("k_harris_select", st); k_harris_select<<<dim3(P.nlevels, P.B), 256, 0, st>>>(P); ++g_afv_launches; }
-    { AfvProfScope ps("k_octree", st);
-      k_octree<<<dim3(P.nlevels, P.B), 256, afv_octree_smem_bytes(P.oct_mcap, P.oct_ncap), st>>>(P, P.oct_mcap, P.oct_ncap);
+    cudaStreamWaitEvent(sst, aux.ev_pyr, 0);
+    { AfvProfScope ps("k_harris_select", sst); k_harris_select<<<dim3(P.nlevels, P.B), 256, 0, sst>>>(P); ++g_afv_launches; }
+    { AfvProfScope ps("k_octree", sst);
+      k_octree<<<dim3(P.nlevels, P.B), 256, afv_octree_smem_bytes(P.oct_mcap, P.oct_ncap), sst>>>(P, P.oct_mcap, P.oct_ncap);
       ++g_afv_launches; }
+    cudaEventRecord(aux.ev_blur, sst);
+    { AfvProfScope ps("k_blur", st); k_blur<<<dim3(acc, P.B), 256, 0, st>>>(P, TMB); ++g_afv_launches; }
     cudaStreamWaitEvent(st, aux.ev_blur, 0);
     { AfvProfScope ps("k_describe", st);
       k_describe<<<dim3((P.out_cap + 7) / 8, P.B), 256, 0, st>>>(P, d_kps, d_desc, d_kpsize, d_n_out); ++g_afv_launches; }

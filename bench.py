@@ -696,8 +696,38 @@ def run_gpu(args):
         gathered = [[torch.empty(pack_bytes, dtype=torch.uint8, device=dev) for _ in range(world)] if rank == 0 else None for _ in range(2)]
     pending = [None, None]
     step_counter = [0]
+    # Matcher overlap: SearchForInitialization is latency bound (one CTA per pair, a sequential resolver: 17 % issue utilisation), the
+    # pixel kernels of the NEXT step are ALU bound.  The matcher (and the pack + gather) of step i therefore run on a second stream
+    # on double-buffered outputs while the main stream already extracts step i + 1; every step's matcher still completes inside the
+    # timed region (finish_steps).
+    OVERLAP = bool(args.overlap_matcher) and not MIXED
+    stream_m = torch.cuda.Stream(device=dev, priority=-1) if OVERLAP else None   # high priority: few CTAs, placed ahead of the pixel tiles
+    outs = [out, ex.alloc_device_outputs(B)] if OVERLAP else [out, out]
+    m12s = [m12, torch.empty_like(m12)] if OVERLAP else [m12, m12]
+    nms = [nm, torch.empty_like(nm)] if OVERLAP else [nm, nm]
+    ev_x = [torch.cuda.Event() for _ in range(2)]; ev_m = [torch.cuda.Event() for _ in range(2)]
+    used = [False, False]
 
-    def device_step(src, collective=True):
+    def device_step(src, collective=True, overlap=True):
+        if OVERLAP and overlap:
+            k = step_counter[0] & 1
+            step_counter[0] += 1
+            if used[k]:
+                stream.wait_event(ev_m[k])                     # the matcher / pack of step i - 2 has released buffer set k
+            ex.extract_batch_device(src, outs[k], stream)
+            ev_x[k].record(stream)
+            stream_m.wait_event(ev_x[k])
+            fm.search_for_initialization(outs[k][0], outs[k][1], outs[k][2], outs[k][3], d_pa, d_pb, None, BOUNDS, MAX_KPT_SIZE,
+                                         window=100, matches12=m12s[k], nmatches=nms[k], stream=stream_m)
+            if world > 1 and args.gather and collective:
+                with torch.cuda.stream(stream_m):
+                    if pending[k] is not None:
+                        pending[k].wait()                      # buffer set k is free again
+                    pkg.sharding.pack_results(d_pack[k], outs[k][3], nms[k], m12s[k], outs[k][0], outs[k][1])
+                    pending[k] = dist.gather(d_pack[k], gathered[k], dst=0, async_op=True)
+            ev_m[k].record(stream_m)
+            used[k] = True
+            return
         ex.extract_batch_device(src, out, stream)
         fm.search_for_initialization(out[0], out[1], out[2], out[3], d_pa, d_pb, None, BOUNDS, MAX_KPT_SIZE,
                                      window=100, matches12=m12, nmatches=nm, stream=stream)
@@ -714,6 +744,16 @@ def run_gpu(args):
             pending[k] = dist.gather(d_pack[k], gathered[k], dst=0, async_op=True)
 
     def drain_collectives():
+        if OVERLAP:
+            with torch.cuda.stream(stream_m):
+                for k in range(2):
+                    if pending[k] is not None:
+                        pending[k].wait()
+                        pending[k] = None
+            done = torch.cuda.Event()
+            done.record(stream_m)
+            stream.wait_event(done)                            # the main stream (where the timing events live) joins the matcher stream
+            return
         for k in range(2):
             if pending[k] is not None:
                 pending[k].wait()
@@ -847,7 +887,7 @@ def run_gpu(args):
         import ctypes as C
         lib.afv_profile_enable(1)
         for _ in range(3):
-            device_step(d_gray, collective=False)      # rank-0-only leg: no collective here
+            device_step(d_gray, collective=False, overlap=False)      # rank-0-only leg: no collective, one stream (additive kernel times)
         torch.cuda.synchronize()
         names = C.create_string_buffer(32 * 32); kms = (C.c_float * 32)(); kcalls = (C.c_int * 32)()
         nk = lib.afv_profile_read(names, kms, kcalls, 32)
@@ -966,7 +1006,8 @@ def run_gpu(args):
             "config": {"workload": WL["name"],
                        "frames_per_step_per_gpu": B, "pairs_per_step_per_gpu": B, "parallelism": "frames sharded, dp%d" % world,
                        "l2": "inputs+intermediates (%.1f GB/step) larger than L2, no flush" % (B * (54e6 * W * H / 921600 if FEAT == "sift128" else 36e6 * W * H / 307200 if FEAT == "akaze61" else 3.1e6 * W * H / 307200) / 1e9),
-                       "gather": bool(world > 1 and args.gather), "gather_mode": "NCCL gather of packed results to rank 0 every step, overlapped with the next step"},
+                       "gather": bool(world > 1 and args.gather), "gather_mode": "NCCL gather of packed results to rank 0 every step, overlapped with the next step",
+                       "matcher_overlap": "matcher of step i on a second stream beside the extraction of step i+1 (double-buffered outputs)" if OVERLAP else "none"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": ms_e2e / args.steps, "h2d_gbs_measured": h2d_gbs, "single_frame_latency_ms": single_ms, "pipeline": "%d chunks of %d frames on 2 streams, host sync after the last step only" % (nchunks, CH)},
             "gpu_launches": int(launches),
@@ -1000,6 +1041,8 @@ def main():
     ap.add_argument("--pairs", type=int, default=10240, help="m1: frame pairs per step")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-gather", dest="gather", action="store_false")
+    ap.add_argument("--no-overlap-matcher", dest="overlap_matcher", action="store_false",
+                    help="run the matcher of a step on the extraction stream instead of overlapping it with the next step's extraction")
     ap.add_argument("--no-c5-block", dest="c5_block", action="store_false",
                     help="skip the extra c5 block (8 fixed 1280x720 streams partitioned over the ranks, strong scaling, validated NCCL gather)")
     ap.add_argument("--c5-frames", type=int, default=C5_FRAMES_PER_STREAM, help="frames per stream of the c5 configuration (BASELINE: 128)")
