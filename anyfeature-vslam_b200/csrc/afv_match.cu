@@ -531,6 +531,16 @@ __device__ __forceinline__ bool sfi_in_window(const SfiQuery& q, int cx, int cy,
     return fabsf(dx) < window && fabsf(dy) < window;
 }
 
+// Hamming distance of a query held in registers against slot `sl` of the word-interleaved staged train descriptors; NW words
+template <int NW>
+__device__ __forceinline__ int sfl_ham(const uint32_t* qd, const uint32_t* y32, int cap) {
+    int d = 0;
+#pragma unroll
+    for (int w = 0; w < NW; ++w) d += __popc(qd[w] ^ y32[(size_t)w * cap]);
+    return d;
+}
+#define SFL_WBUF 256         // per-warp buffer of in-window slots: distances are computed from it with all 32 lanes busy
+
 template <bool BINARY>
 __global__ void __launch_bounds__(SFL_THREADS) k_sfi_lists(int desc_type, int D, int Dpad, int stage_desc,
         const afv_keypoint* __restrict__ kps, const uint8_t* __restrict__ desc, const float* __restrict__ kpsize,
@@ -650,6 +660,41 @@ __global__ void __launch_bounds__(SFL_THREADS) k_sfi_lists(int desc_type, int D,
                     }
                 }
                 int run = off;
+                if (BINARY && stage_desc) {
+                    // The window test passes for about a third of the scanned slots, so computing the distance inside this loop ran at
+                    // 11 of 32 lanes (38 % of the kernel's instructions).  The in-window slots are collected in a per-warp buffer (in
+                    // enumeration order) and the distances are computed from the buffer with every lane busy, NW unrolled.
+                    __shared__ unsigned short wbuf[SFL_THREADS / 32][SFL_WBUF];
+                    unsigned short* wb = wbuf[wid];
+                    uint32_t* pool = reinterpret_cast<uint32_t*>(pool_v) + (long long)p * pool_cap;
+                    int nb = 0;
+                    auto flush = [&]() {
+                        __syncwarp();
+                        for (int j = lane; j < nb; j += 32) {
+                            const int sl = wb[j];
+                            const uint32_t* y32 = reinterpret_cast<const uint32_t*>(sdesc) + sl;
+                            int d;
+                            switch (nw) {
+                                case 8: d = sfl_ham<8>(qd, y32, cap); break;
+                                case 12: d = sfl_ham<12>(qd, y32, cap); break;
+                                default: d = sfl_ham<16>(qd, y32, cap); break;          // 61-byte rows: 16 words, zero padded
+                            }
+                            pool[run + j] = ((uint32_t)d << 20) | (uint32_t)sorig[sl];
+                        }
+                        run += nb; nb = 0;
+                        __syncwarp();
+                    };
+                    for (int sb = s0; sb < s1; sb += 32) {
+                        const int sl = sb + lane;
+                        bool pass = false;
+                        if (sl < s1) { const unsigned short cc = scell[sl]; pass = sfi_in_window(q, cc >> 8, cc & 0xff, sx[sl], sy[sl], window); }
+                        const unsigned m = __ballot_sync(0xffffffffu, pass);
+                        if (pass) wb[nb + __popc(m & ((1u << lane) - 1))] = (unsigned short)sl;
+                        nb += __popc(m);
+                        if (nb > SFL_WBUF - 32) flush();
+                    }
+                    if (nb) flush();
+                } else
                 for (int sb = s0; sb < s1; sb += 32) {
                     const int sl = sb + lane;
                     bool pass = false;

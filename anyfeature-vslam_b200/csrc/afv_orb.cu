@@ -261,11 +261,11 @@ __global__ void __launch_bounds__(256) k_fast(const __grid_constant__ AfvParams 
             base = __shfl_sync(0xffffffffu, base, 31);
         }
         int o = base + incl - cnt;
-        const int i0 = ch * FS1_ROWS * FT_RW + 4 * wc - 15;
+        const int i0 = ((ch * FS1_ROWS) << 8) + 4 * wc - 15;            // list entries are (region row << 8 | region column): no div / mod later
         // predicated, fully unrolled writer (a per-lane `while (smask)` loop ran at 5 of 32 lanes and cost 12 % of the kernel)
 #pragma unroll
         for (int b = 0; b < 4 * FS1_ROWS; ++b)
-            if (smask & (1u << b)) slist[o++] = (uint16_t)(i0 + (b >> 2) * FT_RW + (b & 3));
+            if (smask & (1u << b)) slist[o++] = (uint16_t)(i0 + ((b >> 2) << 8) + (b & 3));
     }
     __syncthreads();
     // stage 2: corner score of every stage-1 survivor = max over the 16 arcs of 9 of min|v - p| (same sign), minus 1 (OpenCV
@@ -281,7 +281,7 @@ __global__ void __launch_bounds__(256) k_fast(const __grid_constant__ AfvParams 
         int i = 0;
         if (j < n1) {
             i = slist[j];
-            const int r = i / FT_RW, c = i % FT_RW;
+            const int r = i >> 8, c = i & 255;
             const uint8_t* p = pb + (r + 3) * PITCH + FT_XOFF + (c + 3);
             const int v = p[0];
             uint32_t e[16];
@@ -318,7 +318,7 @@ __global__ void __launch_bounds__(256) k_fast(const __grid_constant__ AfvParams 
         uint32_t val = 0;
         if (j < nc) {
             const int i = clist[j];
-            const int r = i / FT_RW, c = i % FT_RW;
+            const int r = i >> 8, c = i & 255;
             if (r >= 1 && r <= FT_H && c >= 1 && c <= FT_W) {
                 const int s = score[r][c];
                 keep = s > score[r][c - 1] && s > score[r][c + 1] && s > score[r - 1][c - 1] && s > score[r - 1][c] &&
@@ -596,7 +596,6 @@ __global__ void __launch_bounds__(256) k_blur(const __grid_constant__ AfvParams 
     const AfvLevel& L = P.lv[ti.level];
     const int f = blockIdx.y, tid = threadIdx.x, lane = tid & 31, wrp = tid >> 5;
     const int x0 = ti.x0, y0 = ti.y0;
-    const uint8_t* img = L.img + (long long)f * L.img_fstride;
     if (tid == 0) mbar_init(&tma_bar, 1);
     __syncthreads();
     if (tid == 0) {
@@ -608,7 +607,6 @@ __global__ void __launch_bounds__(256) k_blur(const __grid_constant__ AfvParams 
     // levels 640 .. 179 pixels wide), so the patch is kept off the common path of each case: the mirrored pixels are already in the
     // staged tile (reflection distance <= 3), rows first (top / bottom tiles only), then 3 columns per side with one thread per byte.
     const int xend = min(x0 + BT_W, L.w);                         // outputs exist for gx < xend, taps reach xend + 2
-    (void)img;
     {
         uint8_t* inb = reinterpret_cast<uint8_t*>(&in[0][0]);
         constexpr int PB = BT_WP * 4;
@@ -707,10 +705,15 @@ __device__ __forceinline__ float fast_atan2_deg(float y, float x) {
 __global__ void __launch_bounds__(256, 5) k_describe(const __grid_constant__ AfvParams P, afv_keypoint* __restrict__ kps,
                                                   uint8_t* __restrict__ desc, float* __restrict__ kpsize,
                                                   int* __restrict__ n_out) {
-    __shared__ uint32_t patw[8][32];         // patw[k][lane] = (x0,y0,x1,y1) int8 of test k of descriptor byte `lane`
+    __shared__ float2 patf[8][2][32];        // patf[k][j][lane] = point j (x, y) of test k of descriptor byte `lane`, as floats
     __shared__ int lvl_start[AFV_MAX_LEVELS + 1];
     const int f = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    { const int pl = tid & 31, pk = tid >> 5; patw[pk][pl] = *reinterpret_cast<const uint32_t*>(&c_pattern[pl * 32 + pk * 4]); }
+    {   // the int8 -> float conversion of the 512 pattern points is done once per CTA, not once per tap (6 % of the kernel)
+        const int pl = tid & 31, pk = tid >> 5;
+        const uint32_t pw = *reinterpret_cast<const uint32_t*>(&c_pattern[pl * 32 + pk * 4]);
+        patf[pk][0][pl] = make_float2((float)(int)(int8_t)pw, (float)(int)(int8_t)(pw >> 8));
+        patf[pk][1][pl] = make_float2((float)(int)(int8_t)(pw >> 16), (float)(int)(int8_t)(pw >> 24));
+    }
     if (tid == 0) {
         int acc = 0;
         for (int l = 0; l < P.nlevels; ++l) {
@@ -773,19 +776,35 @@ __global__ void __launch_bounds__(256, 5) k_describe(const __grid_constant__ Afv
     const float a = (float)cos((double)ang), b = (float)sin((double)ang);
     const bool dinner = (cx >= 19 && cy >= 19 && cx + 19 < L.w && cy + 19 < L.h);
     uint32_t byte = 0;
+    if (dinner) {                            // warp-uniform: every tap lies inside the blurred level (rotated pattern radius < 19)
+        const uint8_t* ctr = blr + (long long)cy * L.stride + cx;
+        const int stride = L.stride;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-        const uint32_t pw = patw[k][lane];
-        int tv[2];
+        for (int k = 0; k < 8; ++k) {
+            int tv[2];
 #pragma unroll
-        for (int j = 0; j < 2; ++j) {
-            const float px = (float)(int)(int8_t)(pw >> (16 * j)), py = (float)(int)(int8_t)(pw >> (16 * j + 8));
-            const int ix = cx + __float2int_rn(__fsub_rn(__fmul_rn(px, a), __fmul_rn(py, b)));
-            const int iy = cy + __float2int_rn(__fadd_rn(__fmul_rn(px, b), __fmul_rn(py, a)));
-            if (dinner || (ix >= 0 && ix < L.w && iy >= 0 && iy < L.h)) tv[j] = blr[(long long)iy * L.stride + ix];
-            else tv[j] = img[(long long)refl101(iy, L.h) * L.img_stride + refl101(ix, L.w)];
+            for (int j = 0; j < 2; ++j) {
+                const float2 pt = patf[k][j][lane];
+                const int dx = __float2int_rn(__fsub_rn(__fmul_rn(pt.x, a), __fmul_rn(pt.y, b)));
+                const int dy = __float2int_rn(__fadd_rn(__fmul_rn(pt.x, b), __fmul_rn(pt.y, a)));
+                tv[j] = ctr[dy * stride + dx];
+            }
+            byte |= (uint32_t)(tv[0] < tv[1]) << k;
         }
-        byte |= (uint32_t)(tv[0] < tv[1]) << k;
+    } else {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            int tv[2];
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                const float2 pt = patf[k][j][lane];
+                const int ix = cx + __float2int_rn(__fsub_rn(__fmul_rn(pt.x, a), __fmul_rn(pt.y, b)));
+                const int iy = cy + __float2int_rn(__fadd_rn(__fmul_rn(pt.x, b), __fmul_rn(pt.y, a)));
+                if (ix >= 0 && ix < L.w && iy >= 0 && iy < L.h) tv[j] = blr[(long long)iy * L.stride + ix];
+                else tv[j] = img[(long long)refl101(iy, L.h) * L.img_stride + refl101(ix, L.w)];
+            }
+            byte |= (uint32_t)(tv[0] < tv[1]) << k;
+        }
     }
     const long long o = (long long)f * P.out_cap + i;
     desc[o * 32 + lane] = (uint8_t)byte;
