@@ -364,9 +364,21 @@ __device__ __forceinline__ float ord2f(uint32_t o) {
 __device__ float harris7(const uint8_t* img, int w, int h, int stride, int x0, int y0) {
     // 9x9 support walked with three rolling rows (27 live pixels instead of 81: the full patch cost 128 registers)
     const bool inner = x0 >= 4 && y0 >= 4 && x0 + 4 < w && y0 + 4 < h;
+    // rows are 4-byte aligned (arena strides are multiples of 128, an aliased input has stride % 16 == 0): the 9 bytes of a row come
+    // from three aligned 32-bit loads + funnel shifts instead of nine byte loads (the kernel waits on these loads: 44 % of its stall
+    // samples); the 12-byte window must end inside the row
+    const bool wide = inner && x0 + 8 <= w;
+    const int xa = (x0 - 4) & ~3, sh = ((x0 - 4) & 3) * 8;
     int ra[9], rb[9], rc[9];
     auto load_row = [&](int rr, int* dst) {
-        if (inner) {
+        if (wide) {
+            const uint32_t* q = reinterpret_cast<const uint32_t*>(img + (long long)(y0 - 4 + rr) * stride + xa);
+            const uint32_t w0 = q[0], w1 = q[1], w2 = q[2];
+            const uint32_t u0 = __funnelshift_r(w0, w1, sh), u1 = __funnelshift_r(w1, w2, sh), u2 = w2 >> sh;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) { dst[c] = (u0 >> (8 * c)) & 0xff; dst[4 + c] = (u1 >> (8 * c)) & 0xff; }
+            dst[8] = u2 & 0xff;
+        } else if (inner) {
             const uint8_t* p = img + (long long)(y0 - 4 + rr) * stride + x0 - 4;
 #pragma unroll
             for (int c = 0; c < 9; ++c) dst[c] = p[c];
@@ -773,7 +785,9 @@ __global__ void __launch_bounds__(256, 5) k_describe(const __grid_constant__ Afv
     // descriptor centre as cv::ORB::compute recovers it from the scaled keypoint
     const int cx = __float2int_rn(__fmul_rn(fx, L.inv_scale)), cy = __float2int_rn(__fmul_rn(fy, L.inv_scale));
     const float ang = __fmul_rn(angle, 0x1.1df46ap-6f);            // (float)(CV_PI/180.f)
-    const float a = (float)cos((double)ang), b = (float)sin((double)ang);
+    double sd, cd;
+    sincos((double)ang, &sd, &cd);                                // one argument reduction for both (was 10 % of the kernel as cos + sin)
+    const float a = (float)cd, b = (float)sd;
     const bool dinner = (cx >= 19 && cy >= 19 && cx + 19 < L.w && cy + 19 < L.h);
     uint32_t byte = 0;
     if (dinner) {                            // warp-uniform: every tap lies inside the blurred level (rotated pattern radius < 19)

@@ -279,6 +279,18 @@ def run_reference_real_parts(args, frames, nthreads):
         return None
 
 
+def config_block(args, world, B, overlap):
+    """The `config` object of the JSON line: identical for the b200 arm and for `--impl reference` (same workload, same frames per
+    step), so the driver's same-config comparison holds; arm-specific detail goes to `e2e.pipeline` / `cpu_baseline.sample`."""
+    feat = WL["feature"]
+    per_frame = 54e6 * W * H / 921600 if feat == "sift128" else 36e6 * W * H / 307200 if feat == "akaze61" else 3.1e6 * W * H / 307200
+    return {"workload": WL["name"],
+            "frames_per_step_per_gpu": B, "pairs_per_step_per_gpu": B, "parallelism": "frames sharded, dp%d" % world,
+            "l2": "inputs+intermediates (%.1f GB/step) larger than L2, no flush" % (B * per_frame / 1e9),
+            "gather": bool(world > 1 and args.gather), "gather_mode": "NCCL gather of packed results to rank 0 every step, overlapped with the next step",
+            "matcher_overlap": "matcher of step i on a second stream beside the extraction of step i+1 (double-buffered outputs)" if overlap else "none"}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -289,8 +301,11 @@ def run_reference(args):
     class _P:
         pass
     P = _P(); P.synth = synth
-    frames, pa, pb = make_frames(P, min(args.batch, 256 if WL["feature"] == "orb32" and W <= 640 else 32), 0)
+    # the headline workload (orb32 640x480) runs the b200 arm's full step (same 512 frames); the heavier extractors a bounded sample
+    full_step = WL["feature"] == "orb32" and W <= 640
+    frames, pa, pb = make_frames(P, args.batch if full_step else min(args.batch, 32), 0)
     nthreads = host_threads()
+    cfg = config_block(args, max(args.gpus, 1), args.batch, bool(args.overlap_matcher) and WL["feature"] != "akaze61")
     if WL["feature"] == "orb32" and args.real_parts:
         rp = run_reference_real_parts(args, frames, nthreads)
         if rp is not None:
@@ -299,14 +314,14 @@ def run_reference(args):
                 "impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-                "config": {"workload": WL["name"], "frames_per_step": nfr},
-                "cpu_baseline": {"value": fps, "unit": UNIT, "cores": nthreads, "kind": "reference", "sample": desc},
+                "config": cfg,
+                "cpu_baseline": {"value": fps, "unit": UNIT, "cores": nthreads, "kind": "reference", "sample": desc + " (%d frames per step)" % nfr},
                 "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0,
             }
             print(json.dumps(line))
             return 0
-    step, sample, per_frame = cpu_arm(frames, pb, nthreads, seconds_budget=4.0)
+    step, sample, per_frame = cpu_arm(frames, pb, nthreads, seconds_budget=1.0e9 if full_step else 4.0)
     for _ in range(max(1, min(args.warmup, 1))):
         step(sample)
     t0 = time.perf_counter()
@@ -318,7 +333,7 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": {"workload": WL["name"], "frames_per_step": len(sample)},
+        "config": cfg,
         "cpu_baseline": {"value": fps, "unit": UNIT, "cores": nthreads, "kind": "port",
                          "sample": "%d frames/step x %d steps, oracle C port of the reference path (extractor restated + octree + matcher), %d threads; 1 thread: %.1f fps"
                                    % (len(sample), args.steps, nthreads, 1.0 / per_frame)},
@@ -1003,11 +1018,7 @@ def run_gpu(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong" if STRONG else "weak", "vs_baseline": None,
             "dtype": "u8" if FEAT == "orb32" else "f32", "data": "synthetic",
-            "config": {"workload": WL["name"],
-                       "frames_per_step_per_gpu": B, "pairs_per_step_per_gpu": B, "parallelism": "frames sharded, dp%d" % world,
-                       "l2": "inputs+intermediates (%.1f GB/step) larger than L2, no flush" % (B * (54e6 * W * H / 921600 if FEAT == "sift128" else 36e6 * W * H / 307200 if FEAT == "akaze61" else 3.1e6 * W * H / 307200) / 1e9),
-                       "gather": bool(world > 1 and args.gather), "gather_mode": "NCCL gather of packed results to rank 0 every step, overlapped with the next step",
-                       "matcher_overlap": "matcher of step i on a second stream beside the extraction of step i+1 (double-buffered outputs)" if OVERLAP else "none"},
+            "config": config_block(args, world, B, OVERLAP),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": ms_e2e / args.steps, "h2d_gbs_measured": h2d_gbs, "single_frame_latency_ms": single_ms, "pipeline": "%d chunks of %d frames on 2 streams, host sync after the last step only" % (nchunks, CH)},
             "gpu_launches": int(launches),
