@@ -911,11 +911,30 @@ __global__ void __launch_bounds__(SFR_THREADS) k_sfi_resolve(int desc_type, int 
     }
 }
 
+#define SFI_POOL_CAP (64 * 1024)          // candidate-pool entries per frame pair
+extern "C" size_t afv_search_for_initialization_workspace_bytes(int desc_type, int P, int cap) {
+    const size_t esz = desc_type != AFV_FEAT_SIFT128 ? 4 : 8;
+    return (size_t)P * SFI_POOL_CAP * esz + (size_t)P * cap * sizeof(SfiQMeta) + 2 * (size_t)P * sizeof(int) + 256;
+}
+extern "C" int afv_search_for_initialization_ws(int desc_type, const afv_keypoint* d_kps, const void* d_desc,
+        const float* d_kpsize, const int* d_n, int B, int cap, const int* d_pair_a, const int* d_pair_b, int P,
+        float min_x, float min_y, float max_x, float max_y, float max_kpt_size,
+        float* d_prev_matched, int window, float th_low, float nnratio, int check_orientation,
+        int* d_matches12, int* d_nmatches, void* d_workspace, size_t workspace_bytes, void* cuda_stream);
 extern "C" int afv_search_for_initialization(int desc_type, const afv_keypoint* d_kps, const void* d_desc,
         const float* d_kpsize, const int* d_n, int B, int cap, const int* d_pair_a, const int* d_pair_b, int P,
         float min_x, float min_y, float max_x, float max_y, float max_kpt_size,
         float* d_prev_matched, int window, float th_low, float nnratio, int check_orientation,
         int* d_matches12, int* d_nmatches, void* cuda_stream) {
+    return afv_search_for_initialization_ws(desc_type, d_kps, d_desc, d_kpsize, d_n, B, cap, d_pair_a, d_pair_b, P, min_x, min_y, max_x, max_y,
+                                            max_kpt_size, d_prev_matched, window, th_low, nnratio, check_orientation, d_matches12, d_nmatches,
+                                            nullptr, 0, cuda_stream);
+}
+extern "C" int afv_search_for_initialization_ws(int desc_type, const afv_keypoint* d_kps, const void* d_desc,
+        const float* d_kpsize, const int* d_n, int B, int cap, const int* d_pair_a, const int* d_pair_b, int P,
+        float min_x, float min_y, float max_x, float max_y, float max_kpt_size,
+        float* d_prev_matched, int window, float th_low, float nnratio, int check_orientation,
+        int* d_matches12, int* d_nmatches, void* d_workspace, size_t workspace_bytes, void* cuda_stream) {
     const int D = desc_bytes(desc_type);
     if (D < 0 || !d_kps || !d_desc || !d_kpsize || !d_n || !d_pair_a || !d_pair_b || !d_matches12 ||
         !d_nmatches || B < 1 || P < 0 || cap < 1) { afv_set_error("afv_search_for_initialization: bad argument"); return AFV_ERR_INVALID; }
@@ -944,11 +963,15 @@ extern "C" int afv_search_for_initialization(int desc_type, const afv_keypoint* 
         }
     }
     // candidate pool: entries per pair (u32 for Hamming: dist<<20 | index; u64 for L2: float bits<<32 | index)
-    const int pool_cap = 64 * 1024;
+    const int pool_cap = SFI_POOL_CAP;
     const size_t esz = binary ? 4 : 8;
-    unsigned char* scratch = nullptr;
+    unsigned char* scratch = (unsigned char*)d_workspace;
     const size_t pool_bytes = (size_t)P * pool_cap * esz, meta_bytes = (size_t)P * cap * sizeof(SfiQMeta), nq_bytes = (size_t)P * sizeof(int);
-    AFV_CUDA_CHECK(cudaMallocAsync((void**)&scratch, pool_bytes + meta_bytes + 2 * nq_bytes + 256, st));
+    const size_t need = afv_search_for_initialization_workspace_bytes(desc_type, P, cap);
+    if (scratch && (workspace_bytes < need || ((uintptr_t)scratch & 15))) {
+        afv_set_error("afv_search_for_initialization: workspace %zu B < required %zu B (or not 16-byte aligned)", workspace_bytes, need); return AFV_ERR_INVALID;
+    }
+    if (!scratch) AFV_CUDA_CHECK(cudaMallocAsync((void**)&scratch, need, st));      // no caller workspace: stream-ordered allocation (cached pool)
     void* pool = scratch;
     SfiQMeta* qmeta = reinterpret_cast<SfiQMeta*>(scratch + pool_bytes);
     int* nq = reinterpret_cast<int*>(scratch + pool_bytes + meta_bytes);
@@ -975,7 +998,7 @@ extern "C" int afv_search_for_initialization(int desc_type, const afv_keypoint* 
         ++g_afv_launches;
     }
     AFV_CUDA_CHECK(cudaGetLastError());
-    AFV_CUDA_CHECK(cudaFreeAsync(scratch, st));
+    if (!d_workspace) AFV_CUDA_CHECK(cudaFreeAsync(scratch, st));
     return AFV_OK;
 }
 

@@ -25,8 +25,16 @@ class FeatureMatcher:
         self.th_low = float(th_low)         # TH_LOW == TH_HIGH == reloc thresholds
 
     # -- SearchForInitialization (src/FeatureMatcher.cc:399-557), batched over frame pairs ------------
+    def sfi_workspace(self, P, cap, device):
+        """Caller-owned scratch for search_for_initialization(workspace=...): nothing is allocated on the call path."""
+        import torch
+        lib, _, _, _ = _afv()
+        lib.afv_search_for_initialization_workspace_bytes.restype = C.c_size_t
+        nbytes = int(lib.afv_search_for_initialization_workspace_bytes(self.desc_type, int(P), int(cap)))
+        return torch.empty(nbytes, dtype=torch.uint8, device=device)
+
     def search_for_initialization(self, kps, desc, kpsize, n, pair_a, pair_b, prev_matched, bounds,
-                                  max_kpt_size, window=100, matches12=None, nmatches=None, stream=None):
+                                  max_kpt_size, window=100, matches12=None, nmatches=None, stream=None, workspace=None):
         """kps [B,cap,7] f32, desc [B,cap,D] u8, kpsize [B,cap] f32, n [B] i32, pair_a/pair_b [P] i32,
         prev_matched [P,cap,2] f32 (in/out).  Returns (matches12 [P,cap] i32, nmatches [P] i32)."""
         import torch
@@ -38,11 +46,12 @@ class FeatureMatcher:
         if nmatches is None:
             nmatches = torch.empty((P,), dtype=torch.int32, device=kps.device)
         minx, miny, maxx, maxy = bounds
-        _check(lib.afv_search_for_initialization(
+        ws_ptr, ws_bytes = (None, 0) if workspace is None else (_vp(workspace), workspace.numel() * workspace.element_size())
+        _check(lib.afv_search_for_initialization_ws(
             self.desc_type, _vp(kps), _vp(desc), _vp(kpsize), _vp(n), B, cap, _vp(pair_a), _vp(pair_b), P,
             C.c_float(minx), C.c_float(miny), C.c_float(maxx), C.c_float(maxy), C.c_float(max_kpt_size),
             _vp(prev_matched), int(window), C.c_float(self.th_low), C.c_float(self.nnratio), int(self.check_ori),
-            _vp(matches12), _vp(nmatches), _sp(stream)))
+            _vp(matches12), _vp(nmatches), ws_ptr, C.c_size_t(ws_bytes), _sp(stream)))
         return matches12, nmatches
 
     # -- Frame grid + stateless window search (core of SearchByProjection) ------------------------------

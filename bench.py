@@ -722,6 +722,7 @@ def run_gpu(args):
     nms = [nm, torch.empty_like(nm)] if OVERLAP else [nm, nm]
     ev_x = [torch.cuda.Event() for _ in range(2)]; ev_m = [torch.cuda.Event() for _ in range(2)]
     used = [False, False]
+    sfi_ws = [fm.sfi_workspace(B, cap, dev) for _ in range(2 if OVERLAP else 1)]      # caller-owned scratch: no allocation per step
 
     def device_step(src, collective=True, overlap=True):
         if OVERLAP and overlap:
@@ -733,7 +734,7 @@ def run_gpu(args):
             ev_x[k].record(stream)
             stream_m.wait_event(ev_x[k])
             fm.search_for_initialization(outs[k][0], outs[k][1], outs[k][2], outs[k][3], d_pa, d_pb, None, BOUNDS, MAX_KPT_SIZE,
-                                         window=100, matches12=m12s[k], nmatches=nms[k], stream=stream_m)
+                                         window=100, matches12=m12s[k], nmatches=nms[k], stream=stream_m, workspace=sfi_ws[k])
             if world > 1 and args.gather and collective:
                 with torch.cuda.stream(stream_m):
                     if pending[k] is not None:
@@ -745,7 +746,7 @@ def run_gpu(args):
             return
         ex.extract_batch_device(src, out, stream)
         fm.search_for_initialization(out[0], out[1], out[2], out[3], d_pa, d_pb, None, BOUNDS, MAX_KPT_SIZE,
-                                     window=100, matches12=m12, nmatches=nm, stream=stream)
+                                     window=100, matches12=m12, nmatches=nm, stream=stream, workspace=sfi_ws[0])
         if MIXED:
             ex2.extract_batch_device(src, out2, stream)
             fm48.search_for_initialization(out2[0], out2[1], out2[2], out2[3], d_pa, d_pb, None, BOUNDS, MAX_KPT_SIZE,

@@ -183,6 +183,17 @@ int  afv_search_for_initialization(int desc_type, const afv_keypoint* d_kps, con
                                    int check_orientation, int* d_matches12, int* d_nmatches,
                                    void* cuda_stream);
 
+/* The same with a caller-owned workspace (afv_search_for_initialization_workspace_bytes, 16-byte aligned): no allocation of any kind
+ * on the call path.  The plain form above takes its scratch from the device's stream-ordered pool (cudaMallocAsync, cached). */
+size_t afv_search_for_initialization_workspace_bytes(int desc_type, int P, int cap);
+int  afv_search_for_initialization_ws(int desc_type, const afv_keypoint* d_kps, const void* d_desc,
+                                      const float* d_kpsize, const int* d_n, int B, int cap,
+                                      const int* d_pair_a, const int* d_pair_b, int P,
+                                      float min_x, float min_y, float max_x, float max_y, float max_kpt_size,
+                                      float* d_prev_matched, int window, float th_low, float nnratio,
+                                      int check_orientation, int* d_matches12, int* d_nmatches,
+                                      void* d_workspace, size_t workspace_bytes, void* cuda_stream);
+
 /* SearchByProjection, the two classic variants (src/FeatureMatcher.cc:73-154 TrackLocalMap, :287-397 Sim3); kept as the short form
  * of afv_search_by_projection_ex below (it reads the query count back from the device, i.e. it synchronises the stream once):
  * P independent problems, problem p projects queries q_start[p]..q_start[p+1]
