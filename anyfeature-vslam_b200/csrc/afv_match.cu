@@ -806,7 +806,37 @@ __global__ void __launch_bounds__(SFR_THREADS) k_sfi_resolve(int desc_type, int 
             const int qi = qb + s;
             const SfiQMeta m = qi < SFR_QSTAGE ? qms[qi] : qm[qi];
             const bool ok = m.off >= 0 && m.cnt > 0 && m.cnt <= SFR_LMAX;
-            if (ok) {
+            if (ok && BINARY && cap <= 2048) {
+                // compact keys: Hamming distance (<= 488 < 511: 9 bits) | cell x (6) | cell y (6) | train index (11) fit 32 bits, so a
+                // round is 7 unsigned minima, ONE redux.sync warp minimum and 8 compare-selects instead of 64-bit compare chains and ten
+                // shuffles (the top-K extraction was 60 % of this kernel's instructions and makes it ALU bound at >= 2048 pairs)
+                uint32_t key[SFR_LMAX / 32];
+                const uint32_t NONE32 = 0xffffffffu;
+#pragma unroll
+                for (int u = 0; u < SFR_LMAX / 32; ++u) {
+                    const int j = u * 32 + lane;
+                    uint32_t k = NONE32;
+                    if (j < m.cnt) {
+                        const uint32_t e = reinterpret_cast<const uint32_t*>(pool_v)[(long long)p * pool_cap + m.off + j];
+                        const uint32_t i2 = e & 0xfffffu;
+                        const unsigned short cc = tcell[i2];
+                        k = ((e >> 20) << 23) | ((uint32_t)(cc >> 8) << 17) | ((uint32_t)(cc & 0xff) << 11) | i2;
+                    }
+                    key[u] = k;
+                }
+                for (int r = 0; r < SFR_K; ++r) {
+                    uint32_t lmin = key[0];
+#pragma unroll
+                    for (int u = 1; u < SFR_LMAX / 32; ++u) lmin = min(lmin, key[u]);
+                    const uint32_t g = __reduce_min_sync(0xffffffffu, lmin);
+                    if (g == NONE32) { if (lane == 0) for (int r2 = r; r2 < SFR_K; ++r2) topk[s * SFR_K + r2] = KEY_NONE; break; }
+                    if (lane == 0)      // back to the resolver's key format: float distance bits << 32 | cell x << 26 | cell y << 20 | index
+                        topk[s * SFR_K + r] = ((unsigned long long)__float_as_uint((float)(g >> 23)) << 32) | (((g >> 17) & 63u) << 26) |
+                                              (((g >> 11) & 63u) << 20) | (g & 2047u);
+#pragma unroll
+                    for (int u = 0; u < SFR_LMAX / 32; ++u) if (key[u] == g) key[u] = NONE32;       // keys are unique (index bits)
+                }
+            } else if (ok) {
                 unsigned long long key[SFR_LMAX / 32];
 #pragma unroll
                 for (int u = 0; u < SFR_LMAX / 32; ++u) { const int j = u * 32 + lane; key[u] = j < m.cnt ? pool_key(m, j) : KEY_NONE; }

@@ -1032,6 +1032,10 @@ def run_gpu(args):
                       "brisk48_kps_per_frame": [int(out2[3].min()), int(out2[3].max())] if MIXED else None,
                       "matches48_per_pair_mean": float(nmb.float().mean()) if MIXED else None},
         }
+        if isinstance(c5_block, dict) and "h2d_gbs_aggregate_all_ranks_concurrent" in c5_block:
+            # the host -> device ceiling of THIS box with every rank copying at once (what bounds e2e when several GPUs share a host)
+            line["e2e"]["h2d_gbs_aggregate_all_ranks_concurrent"] = c5_block["h2d_gbs_aggregate_all_ranks_concurrent"]
+            line["e2e"]["h2d_gbs_needed_at_device_rate"] = h2d * world * value / (B * world) / 1e9
         print(json.dumps(line))
     if world > 1:
         dist.barrier()

@@ -1,51 +1,29 @@
-"""Summarise ncu output brought back in gpurun_out/ into markdown tables for profiles/.
-  python tools/ncu_summary.py launches gpurun_out/r01h_launches_c3.csv
-  python tools/ncu_summary.py full gpurun_out/r01h_sift.ncu-rep
-"""
-import csv
-import io
-import subprocess
-import sys
-from collections import OrderedDict
-
-
-def launches(path):
-    rows = [r for r in csv.reader(open(path, errors="ignore")) if len(r) > 5 and r[0].strip('"').isdigit()]
-    acc = OrderedDict()
-    for r in rows:
-        name = r[4].split("(")[0]
-        ns = float(r[-1])
-        a = acc.setdefault(name, [0, 0.0])
-        a[0] += 1; a[1] += ns
-    tot = sum(v[1] for v in acc.values())
-    print("| kernel | launches | total us | share |\n|---|---|---|---|")
-    for k, v in sorted(acc.items(), key=lambda kv: -kv[1][1]):
-        print("| %s | %d | %.1f | %.1f%% |" % (k, v[0], v[1] / 1e3, 100 * v[1] / tot))
-
-
-def full(path):
-    out = subprocess.check_output(["ncu", "-i", path, "--page", "raw", "--csv"], text=True, errors="ignore")
-    rd = list(csv.reader(io.StringIO(out)))
-    hdr = rd[0]
-    want = OrderedDict([("Kernel Name", "kernel"), ("gpu__time_duration.sum", "time"), ("dram__bytes_read.sum", "dram read"),
-                        ("dram__bytes_write.sum", "dram write"), ("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "dram %"),
-                        ("sm__throughput.avg.pct_of_peak_sustained_elapsed", "sm %"), ("sm__warps_active.avg.pct_of_peak_sustained_active", "warps active %"),
-                        ("launch__registers_per_thread", "regs"), ("smsp__inst_executed.sum", "warp instr"),
-                        ("smsp__issue_active.avg.pct", "issue active %"), ("l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "smem wavefronts")])
-    idx = [(hdr.index(k), v) for k, v in want.items() if k in hdr]
-    units = rd[1]
-    print("| " + " | ".join(v for _, v in idx) + " |\n|" + "---|" * len(idx))
-    for r in rd[2:]:
-        if len(r) < len(hdr):
-            continue
-        cells = []
-        for i, v in idx:
-            x = r[i].split("(")[0][:60] if v == "kernel" else r[i]
-            if v in ("time", "dram read", "dram write"):
-                x = "%s %s" % (r[i], units[i])
-            cells.append(x)
-        print("| " + " | ".join(cells) + " |")
-
-
-if __name__ == "__main__":
-    {"launches": launches, "full": full}[sys.argv[1]](sys.argv[2])
+#!/usr/bin/env python3
+"""Markdown table of the key ncu metrics of every kernel launch in an .ncu-rep (read here, without a GPU).
+Usage: tools/ncu_summary.py report.ncu-rep [frames_or_pairs_per_launch]"""
+import csv, subprocess, sys
+rep = sys.argv[1]
+units = float(sys.argv[2]) if len(sys.argv) > 2 else None
+out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+rows = list(csv.reader(out.splitlines()))
+hdr = rows[0]
+col = {n: hdr.index(n) for n in hdr}
+def g(r, n, d="-"):
+    return r[col[n]] if n in col else d
+print("| kernel | time us | warp instr (M) | instr / unit | lanes | issue active % | ALU pipe % | FMA pipe % | LSU pipe % | warps active % | regs | DRAM read MB | DRAM write MB | DRAM % of peak |")
+print("|---|---|---|---|---|---|---|---|---|---|---|---|---|---|")
+for r in rows[2:]:
+    name = g(r, "Kernel Name").split("(")[0].replace("void ", "")
+    t = float(g(r, "gpu__time_duration.sum").replace(",", ""))
+    tu = rows[1][col["gpu__time_duration.sum"]]
+    if tu == "ms": t *= 1000.0
+    inst = float(g(r, "smsp__inst_executed.sum").replace(",", ""))
+    def f(n):
+        try: return "%.1f" % float(g(r, n).replace(",", ""))
+        except Exception: return "-"
+    print("| %s | %.1f | %.2f | %s | %s | %s | %s | %s | %s | %s | %s | %s | %s | %s |" % (
+        name, t, inst / 1e6, ("%.0f" % (inst / units)) if units else "-", f("smsp__thread_inst_executed_per_inst_executed.ratio"),
+        f("smsp__issue_active.avg.pct_of_peak_sustained_active"), f("sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active"),
+        f("sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active"), f("sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active"),
+        f("sm__warps_active.avg.pct_of_peak_sustained_active"), g(r, "launch__registers_per_thread"), f("dram__bytes_read.sum"), f("dram__bytes_write.sum"),
+        f("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed")))
