@@ -47,6 +47,10 @@ WORKLOADS = {
                metric="frame pairs/sec (windowed Hamming matcher r=15, orb32 1000x1000 kp)",
                name="matcher-only: 10240 frame pairs of a resident 512-frame orb32 640x480 extraction; windowed Hamming match r=15/30/100, "
                     "SearchForInitialization, brute force 1000x1000, sift128-layout L2 2000x2000 (SURVEY 8d)"),
+    "c2v": dict(feature="orbslam2", w=640, h=480, nfeat=1000, batch=512, desc_bytes=32, desc_type=0, th_low=75.0,
+                metric="frames/sec (extract+match) vanilla ORB-SLAM2 extractor 640x480x1000kp",
+                name="vanilla ORB-SLAM2 extractor (VANILLA_ORB_SLAM2 build, SURVEY 8f-4) 640x480 synthetic batch, 1000 kp/frame, "
+                     "extract+SearchForInitialization on 1xB200 per rank"),
     "c5": dict(feature="orb32", w=1280, h=720, nfeat=2000, batch=128, desc_bytes=32, desc_type=0, th_low=75.0,
                metric="frames/sec (extract+match) orb32 1280x720x2000kp",
                name="orb32 1280x720 synthetic 8-stream batch, 2000 kp/frame, streams sharded over ranks, NCCL gather (configs[4])"),
@@ -183,6 +187,8 @@ def cpu_arm(frames, pair_b, nthreads, seconds_budget):
             return po.sift_extract_match_batch(fr, pa, pb, NFEAT, threads)
         if WL["feature"] == "akaze61":
             return po.akaze_extract_match_batch(fr, pa, pb, NFEAT, threads)
+        if WL["feature"] == "orbslam2":
+            return po.orbslam2_extract_match_batch(fr, pa, pb, NFEAT, threads)
         return po.extract_match_batch(fr, pa, pb, NFEAT, threads)
 
     step([0, 1], 1)                                              # warm (library load, first-touch)
@@ -956,6 +962,18 @@ def run_gpu(args):
             "k_sfi_lists": B * (2 * N * (WL["desc_bytes"] + 28) + 4 * N + 16 * float(ex.levels()[1][0])),
             "k_sfi_resolve": B * (N * 28 + 16 * float(ex.levels()[1][0]) + 4 * N + 4),
         }
+        if FEAT == "orbslam2":
+            Cdet = float(np.mean([ex.debug_read(43, 0, l).size // 4 for l in range(8)])) * 8       # detect-list entries per frame
+            alg = {
+                "k_os2_resize": B * (2 * P_PIX - W * H - int(np.rint(W / 1.2 ** 7)) * int(np.rint(H / 1.2 ** 7))),
+                "k_os2_score": B * 2.0 * P_PIX,                          # read every level, write its score map
+                "k_os2_cells": B * (2.0 * P_PIX + 4 * Cdet),             # count pass + emit pass over the score map, detect list out
+                "k_os2_octree": B * (4 * Cdet + 8 * N),
+                "k_os2_blur": B * 2.0 * P_PIX,
+                "k_os2_describe": B * N * (8 + 709 + 512 + 28 + 32 + 4),
+                "k_sfi_lists": B * (2 * N * (32 + 28) + 4 * N + 16 * float(ex.levels()[1][0])),
+                "k_sfi_resolve": B * (N * 28 + 16 * float(ex.levels()[1][0]) + 4 * N + 4),
+            }
         dom = max(kern, key=lambda k: kern[k][0])
         peaks = {}
         try:
@@ -1018,7 +1036,7 @@ def run_gpu(args):
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong" if STRONG else "weak", "vs_baseline": None,
-            "dtype": "u8" if FEAT == "orb32" else "f32", "data": "synthetic",
+            "dtype": "u8" if FEAT in ("orb32", "orbslam2") else "f32", "data": "synthetic",
             "config": config_block(args, world, B, OVERLAP),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": ms_e2e / args.steps, "h2d_gbs_measured": h2d_gbs, "single_frame_latency_ms": single_ms, "pipeline": "%d chunks of %d frames on 2 streams, host sync after the last step only" % (nchunks, CH)},

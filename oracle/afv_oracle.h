@@ -224,6 +224,9 @@ void  orc_orbslam2_descriptor(const uint8_t* blur, int stride, int cx, int cy, f
 int   orc_orbslam2_extract(const uint8_t* gray, int w, int h, int stride, int nfeatures, int nlevels, float scale_factor,
                            int ini_th, int min_th, orc_keypoint* kps, uint8_t* desc, float* kpsize, int cap, int* n_out);
 
+long  orc_orbslam2_extract_match_batch(const uint8_t* frames, int B, int w, int h, int nfeatures, int nlevels, float scale_factor,
+                                       const int* pair_a, const int* pair_b, int P, int window, float th_low, float nnratio, int check_ori,
+                                       int nthreads);
 /* Frame::isInFrustum (src/Frame.cc:276-331) + the window prologue of SearchByProjection (src/FeatureMatcher.cc:86-95), M map points. */
 void  orc_is_in_frustum(const float* Pw, const float* normal, const float* min_dist, const float* max_dist, const float* ref_size,
                         const float* ref_sigma, const float* ref_dist, int M, const float* pose16, const float* cam5, const float* bounds4,

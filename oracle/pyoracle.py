@@ -38,6 +38,7 @@ def lib():
         _LIB.orc_descriptor_distance.restype = C.c_float
         _LIB.orc_orb32_extract_match_batch.restype = C.c_long
         _LIB.orc_sift128_extract_match_batch.restype = C.c_long
+        _LIB.orc_orbslam2_extract_match_batch.restype = C.c_long
     return _LIB
 
 
@@ -550,3 +551,14 @@ def is_in_frustum(Pw, normal, min_dist, max_dist, ref_size, ref_sigma, ref_dist,
                             M, _p(f32(pose16)), _p(f32(cam5)), _p(f32(bounds4)), _f(cos_limit), _f(radius_factor), _f(size_tol),
                             _p(iv), _p(proj), _p(track), _p(qr), _p(qmin), _p(qmax))
     return iv, proj, track, qr, qmin, qmax
+
+
+def orbslam2_extract_match_batch(frames, pair_a, pair_b, nfeatures=1000, nthreads=1, window=100, th_low=75.0, nnratio=0.9, check_ori=True):
+    """One bench step of the vanilla ORB-SLAM2 workload on the CPU (pthreads in C).  Returns the total number of matches."""
+    frames = np.ascontiguousarray(frames, np.uint8)
+    B, h, w = frames.shape
+    pa = np.ascontiguousarray(pair_a, np.int32); pb = np.ascontiguousarray(pair_b, np.int32)
+    r = lib().orc_orbslam2_extract_match_batch(_p(frames), B, w, h, nfeatures, 8, _f(1.2), _p(pa), _p(pb), len(pa), int(window), _f(th_low),
+                                               _f(nnratio), int(bool(check_ori)), int(nthreads))
+    assert r >= 0
+    return int(r)
