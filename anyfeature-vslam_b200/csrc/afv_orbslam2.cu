@@ -40,6 +40,7 @@ struct Os2Level {
 struct Os2Params {
     int nlevels, B, ini_th, min_th, out_cap, ncells_total, oct_ncap;
     int* cellcnt;                                        // [frame][ncells_total] count | 1 << 30 when the iniThFAST set is used
+    uint32_t* cellmask;                                  // [frame][ncells_total][32] per-column row masks of the chosen maxima (cells <= 32 x 32)
     int* counts; int* status;
     Os2Level lv[AFV_MAX_LEVELS];
 };
@@ -87,10 +88,13 @@ __global__ void __launch_bounds__(256) k_os2_resize(const __grid_constant__ Os2P
 #define SC_P 72
 __global__ void __launch_bounds__(256) k_os2_score(const __grid_constant__ Os2Params P, int l) {
     __shared__ __align__(4) uint8_t tile[SC_H + 6][SC_P];
+    __shared__ uint16_t slist[SC_W * SC_H];              // pixels that pass the compass pre-test: row << 8 | column
+    __shared__ int nlist;
     const Os2Level& L = P.lv[l];
-    const int f = blockIdx.z, tid = threadIdx.x;
+    const int f = blockIdx.z, tid = threadIdx.x, lane = tid & 31;
     const int tx0 = 19 + blockIdx.x * SC_W, ty0 = 19 + blockIdx.y * SC_H;
     const uint8_t* img = L.img + (long long)f * L.img_fstride;
+    if (tid == 0) nlist = 0;
     for (int i = tid; i < (SC_H + 6) * (SC_W + 6); i += 256) {
         const int r = i / (SC_W + 6), c = i - r * (SC_W + 6);
         const int gx = tx0 - 3 + c, gy = ty0 - 3 + r;
@@ -99,40 +103,57 @@ __global__ void __launch_bounds__(256) k_os2_score(const __grid_constant__ Os2Pa
     __syncthreads();
     const int t = P.min_th;
     uint8_t* sc = L.score + (long long)f * L.fstride;
+    // stage 1: an arc of 9 of the 16 circle pixels holds two ADJACENT compass points, so a corner needs (up or down) and (left or right)
+    // beyond the threshold with one sign.  At minThFAST = 7 a third of all pixels still pass, i.e. every warp would run the ~150
+    // instruction score for all of its pixels: the survivors are compacted first and scored with full warps (as in k_fast).
 #pragma unroll
     for (int rep = 0; rep < 4; ++rep) {
         const int i = tid + 256 * rep;
         const int r = i >> 6, c = i & 63;
         const int gx = tx0 + c, gy = ty0 + r;
-        if (gx >= L.w - 19 || gy >= L.h - 19) continue;
+        const bool in = gx < L.w - 19 && gy < L.h - 19;
+        bool pass = false;
+        if (in) {
+            const uint8_t* p = &tile[r + 3][c + 3];
+            const int v = p[0], hi = v + t, lo = v - t;
+            const int up = p[-3 * SC_P], dn = p[3 * SC_P], lf = p[-3], rt = p[3];
+            pass = (max(up, dn) > hi && max(lf, rt) > hi) || (min(up, dn) < lo && min(lf, rt) < lo);
+            if (!pass) sc[(long long)gy * L.stride + gx] = 0;
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, pass);
+        if (m) {
+            int base = 0;
+            const int leader = __ffs(m) - 1;
+            if (lane == leader) base = atomicAdd(&nlist, __popc(m));
+            base = __shfl_sync(0xffffffffu, base, leader);
+            if (pass) slist[base + __popc(m & ((1u << lane) - 1))] = (uint16_t)((r << 8) | c);
+        }
+    }
+    __syncthreads();
+    // stage 2: OpenCV cornerScore<16> of every survivor (packed (d, -d) sliding minimum over 9 by doubling, see k_fast in afv_orb.cu)
+    const int n = nlist;
+    for (int j = tid; j < n; j += 256) {
+        const int e0 = slist[j], r = e0 >> 8, c = e0 & 255;
         const uint8_t* p = &tile[r + 3][c + 3];
-        const int v = p[0], hi = v + t, lo = v - t;
-        int s = 0;
-        int a = p[3 * SC_P], b = p[-3 * SC_P];
-        bool go = (a > hi || a < lo || b > hi || b < lo);
-        a = p[3]; b = p[-3];
-        go = go && (a > hi || a < lo || b > hi || b < lo);
-        if (go) {
-            uint32_t e[16];
+        const int v = p[0];
+        const uint32_t A = (uint32_t)(256 + v) | ((uint32_t)(256 - v) << 16);
+        uint32_t e[16];
 #define OS2_CIRC(F) F(0, 0, 3) F(1, 1, 3) F(2, 2, 2) F(3, 3, 1) F(4, 3, 0) F(5, 3, -1) F(6, 2, -2) F(7, 1, -3) \
                     F(8, 0, -3) F(9, -1, -3) F(10, -2, -2) F(11, -3, -1) F(12, -3, 0) F(13, -3, 1) F(14, -2, 2) F(15, -1, 3)
-#define FDIFF(k, dx, dy) { const int dv = v - (int)p[(dy) * SC_P + (dx)]; e[k] = ((uint32_t)dv & 0xffffu) | ((uint32_t)(-dv) << 16); }
-            OS2_CIRC(FDIFF)
+#define FDIFF(k, dx, dy) e[k] = (uint32_t)p[(dy) * SC_P + (dx)] * 0xffffu + A;
+        OS2_CIRC(FDIFF)
 #undef FDIFF
-            // packed (d, -d) sliding minimum over 9 by doubling (see k_fast in afv_orb.cu for why the scalar form is avoided)
-            uint32_t m2[16], m4[16];
+        uint32_t m2[16], m4[16];
 #pragma unroll
-            for (int k = 0; k < 16; ++k) m2[k] = __vmins2(e[k], e[(k + 1) & 15]);
+        for (int k = 0; k < 16; ++k) m2[k] = __vmins2(e[k], e[(k + 1) & 15]);
 #pragma unroll
-            for (int k = 0; k < 16; ++k) m4[k] = __vmins2(m2[k], m2[(k + 2) & 15]);
-            uint32_t acc = 0x80008000u;
+        for (int k = 0; k < 16; ++k) m4[k] = __vmins2(m2[k], m2[(k + 2) & 15]);
+        uint32_t acc = 0;
 #pragma unroll
-            for (int k = 0; k < 16; ++k) acc = __vmaxs2(acc, __vmins2(__vmins2(m4[k], m4[(k + 4) & 15]), e[(k + 8) & 15]));
-            const int bd = (int)(short)(acc & 0xffffu), bb = (int)(short)(acc >> 16);
-            const int best = bd > bb ? bd : bb;
-            if (best > t) s = best - 1;
-        }
-        sc[(long long)gy * L.stride + gx] = (uint8_t)s;
+        for (int k = 0; k < 16; ++k) acc = __vmaxs2(acc, __vmins2(__vmins2(m4[k], m4[(k + 4) & 15]), e[(k + 8) & 15]));
+        const int bd = (int)(acc & 0xffffu) - 256, bb = (int)(acc >> 16) - 256;
+        const int best = bd > bb ? bd : bb;
+        sc[(long long)(ty0 + r) * L.stride + tx0 + c] = (uint8_t)(best > t ? best - 1 : 0);
     }
 }
 
@@ -161,6 +182,70 @@ __global__ void __launch_bounds__(256) k_os2_cells(const __grid_constant__ Os2Pa
     int* cc = P.cellcnt + (long long)f * P.ncells_total;
     uint8_t (*T)[CL_P] = tiles[wrp];
     const uint8_t* sc = L.score + (long long)f * L.fstride;
+    if (wv <= 32 && hv <= 32) {
+        // Common case (cells are ceil(width / floor(width / 30)) wide: <= 32 for every level with >= 15 cell columns): lane = column,
+        // the score rows of the cell are read straight from the map (one byte per lane and row, all loads in flight together),
+        // horizontal neighbours come by shuffle, and a neighbour outside the cell is 0 exactly as FAST's sub-image NMS sees it.
+        // Pass 1 leaves, per lane, a 32-bit ROW MASK of the maxima of the chosen set; pass 2 only walks those masks in raster order.
+        uint32_t* cm = P.cellmask + ((long long)f * P.ncells_total + cell) * 32;
+        uint32_t* det = L.det + (long long)f * L.det_cap;
+        const bool act = lane < wv;
+        const uint8_t* col = sc + (long long)vy0 * L.stride + vx0 + lane;
+        if (!EMIT) {
+            int v[32];
+#pragma unroll
+            for (int r = 0; r < 32; ++r) v[r] = (act && r < hv) ? (int)col[(long long)r * L.stride] : 0;
+            uint32_t m_all = 0, m_ini = 0;
+            int h3_prev = 0;
+            int lf = __shfl_up_sync(0xffffffffu, v[0], 1), rt = __shfl_down_sync(0xffffffffu, v[0], 1);
+            if (lane == 0) lf = 0;
+            if (lane == 31) rt = 0;
+            int hlr = max(lf, rt), h3 = max(hlr, v[0]);
+#pragma unroll
+            for (int r = 0; r < 32; ++r) {
+                int hlr_n = 0, h3_n = 0;
+                if (r + 1 < 32) {
+                    int l2 = __shfl_up_sync(0xffffffffu, v[r + 1], 1), r2 = __shfl_down_sync(0xffffffffu, v[r + 1], 1);
+                    if (lane == 0) l2 = 0;
+                    if (lane == 31) r2 = 0;
+                    hlr_n = max(l2, r2); h3_n = max(hlr_n, v[r + 1]);
+                }
+                const int s = v[r];
+                const bool mx = s > 0 && s > hlr && s > h3_prev && s > h3_n;
+                m_all |= (uint32_t)mx << r;
+                m_ini |= (uint32_t)(mx && s >= P.ini_th) << r;
+                h3_prev = h3; hlr = hlr_n; h3 = h3_n;
+            }
+            const int n_all = __reduce_add_sync(0xffffffffu, __popc(m_all)), n_ini = __reduce_add_sync(0xffffffffu, __popc(m_ini));
+            cm[lane] = n_ini ? m_ini : m_all;
+            if (lane == 0) cc[cell] = n_ini ? (n_ini | (1 << 30)) : n_all;
+        } else {
+            int part = 0;
+            for (int k = L.cell_base + lane; k < cell; k += 32) part += cc[k] & 0x3fffffff;
+            const int base = __reduce_add_sync(0xffffffffu, part);
+            const uint32_t m = cm[lane];
+            int run = 0;
+            uint32_t rows_any = __reduce_or_sync(0xffffffffu, m);
+            while (rows_any) {
+                const int r = __ffs(rows_any) - 1;
+                rows_any &= rows_any - 1;
+                const bool bit = (m >> r) & 1u;
+                const unsigned rm = __ballot_sync(0xffffffffu, bit);
+                if (bit) {
+                    const int pos = base + run + __popc(rm & ((1u << lane) - 1));
+                    const uint32_t sv = col[(long long)r * L.stride];
+                    if (pos < L.det_cap) det[pos] = (uint32_t)(vx0 + lane - OS2_MINB) | ((uint32_t)(vy0 + r - OS2_MINB) << 12) | (sv << 24);
+                }
+                run += __popc(rm);
+            }
+            if (lane == 0 && ci == L.ncells - 1) {
+                int tot = base + run;
+                if (tot > L.det_cap) { atomicOr(&P.status[f], OS2_ST_DET_OVERFLOW); tot = L.det_cap; }
+                P.counts[afv_cnt_idx(f, AFV_CNT_DET, l)] = tot;
+            }
+        }
+        return;
+    }
     // stage the valid region with a zero ring: FAST's non-max suppression only sees scores of its own sub-image
     for (int r = 0; r < hv + 2; ++r)
         for (int c = lane; c < wv + 2; c += 32) {
@@ -255,33 +340,64 @@ __global__ void __launch_bounds__(256) k_os2_octree(const __grid_constant__ Os2P
 // columns in 16.16, (v + 2^15) >> 16.
 // ---------------------------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ int os2_refl101(int i, int n) { if (i < 0) i = -i; if (i >= n) i = 2 * n - 2 - i; return min(max(i, 0), n - 1); }
+#define BL_W 64
+#define BL_H 32
+#define BL_P 72                        // staged bytes per row: columns tx0 - 4 .. tx0 + 67 (word aligned)
 __global__ void __launch_bounds__(256) k_os2_blur(const __grid_constant__ Os2Params P, int l) {
-    __shared__ __align__(4) uint8_t in[SC_H + 6][SC_P];
-    __shared__ __align__(4) uint16_t mid[SC_H + 6][SC_W];
+    __shared__ __align__(16) uint8_t in[BL_H + 6][BL_P];
+    __shared__ __align__(16) uint16_t mid[BL_H + 6][BL_W];
     const Os2Level& L = P.lv[l];
     const int f = blockIdx.z, tid = threadIdx.x;
-    const int tx0 = blockIdx.x * SC_W, ty0 = blockIdx.y * SC_H;
+    const int tx0 = blockIdx.x * BL_W, ty0 = blockIdx.y * BL_H;
     const uint8_t* img = L.img + (long long)f * L.img_fstride;
-    for (int i = tid; i < (SC_H + 6) * (SC_W + 6); i += 256) {
-        const int r = i / (SC_W + 6), c = i - r * (SC_W + 6);
-        in[r][c] = img[(long long)os2_refl101(ty0 - 3 + r, L.h) * L.img_stride + os2_refl101(tx0 - 3 + c, L.w)];
+    // stage rows ty0 - 3 .. ty0 + BL_H + 2, columns tx0 - 4 .. tx0 + 67: interior tiles of a 4-byte aligned image with aligned 32-bit
+    // loads, everything else byte by byte through BORDER_REFLECT_101
+    const bool aligned = (((unsigned long long)img | (unsigned long long)L.img_stride) & 3ull) == 0;
+    if (aligned && tx0 >= 4 && ty0 >= 3 && tx0 + BL_W + 4 <= L.w && ty0 + BL_H + 3 <= L.h) {
+        for (int i = tid; i < (BL_H + 6) * (BL_P / 4); i += 256) {
+            const int r = i / (BL_P / 4), q = i - r * (BL_P / 4);
+            reinterpret_cast<uint32_t*>(&in[r][0])[q] =
+                *reinterpret_cast<const uint32_t*>(img + (long long)(ty0 - 3 + r) * L.img_stride + tx0 - 4 + 4 * q);
+        }
+    } else {
+        for (int i = tid; i < (BL_H + 6) * BL_P; i += 256) {
+            const int r = i / BL_P, c = i - r * BL_P;
+            in[r][c] = img[(long long)os2_refl101(ty0 - 3 + r, L.h) * L.img_stride + os2_refl101(tx0 - 4 + c, L.w)];
+        }
     }
     __syncthreads();
-    for (int i = tid; i < (SC_H + 6) * SC_W; i += 256) {
-        const int r = i >> 6, c = i & 63;
-        const uint8_t* p = &in[r][c];
-        mid[r][c] = (uint16_t)(18 * (p[0] + p[6]) + 34 * (p[1] + p[5]) + 48 * (p[2] + p[4]) + 56 * p[3]);
-    }
-    __syncthreads();
-    uint8_t* out = L.blur + (long long)f * L.fstride;
+    // rows: 4 outputs per thread from 3 words (staged bytes 4q + 1 .. 4q + 10), symmetric taps, 8.8 fixed point (<= 65280)
+    for (int i = tid; i < (BL_H + 6) * (BL_W / 4); i += 256) {
+        const int r = i / (BL_W / 4), q = i - r * (BL_W / 4);
+        const uint32_t* w = reinterpret_cast<const uint32_t*>(&in[r][0]) + q;
+        const uint32_t w0 = w[0], w1 = w[1], w2 = w[2];
+        int p[10];
+        p[0] = (w0 >> 8) & 0xff; p[1] = (w0 >> 16) & 0xff; p[2] = w0 >> 24;
+        p[3] = w1 & 0xff; p[4] = (w1 >> 8) & 0xff; p[5] = (w1 >> 16) & 0xff; p[6] = w1 >> 24;
+        p[7] = w2 & 0xff; p[8] = (w2 >> 8) & 0xff; p[9] = (w2 >> 16) & 0xff;
+        uint32_t o[4];
 #pragma unroll
-    for (int rep = 0; rep < 4; ++rep) {
-        const int i = tid + 256 * rep;
-        const int r = i >> 6, c = i & 63;
-        const int gx = tx0 + c, gy = ty0 + r;
+        for (int k = 0; k < 4; ++k) o[k] = 18 * (p[k] + p[k + 6]) + 34 * (p[k + 1] + p[k + 5]) + 48 * (p[k + 2] + p[k + 4]) + 56 * p[k + 3];
+        *reinterpret_cast<uint2*>(&mid[r][4 * q]) = make_uint2(o[0] | (o[1] << 16), o[2] | (o[3] << 16));
+    }
+    __syncthreads();
+    // columns: 4 outputs per thread and row, 16.16 fixed point, (v + 2^15) >> 16
+    uint8_t* out = L.blur + (long long)f * L.fstride;
+    for (int i = tid; i < BL_H * (BL_W / 4); i += 256) {
+        const int r = i / (BL_W / 4), q = i - r * (BL_W / 4);
+        const int gx = tx0 + 4 * q, gy = ty0 + r;
         if (gx >= L.w || gy >= L.h) continue;
-        const uint32_t s = 18u * (mid[r][c] + mid[r + 6][c]) + 34u * (mid[r + 1][c] + mid[r + 5][c]) + 48u * (mid[r + 2][c] + mid[r + 4][c]) + 56u * mid[r + 3][c];
-        out[(long long)gy * L.stride + gx] = (uint8_t)((s + 32768u) >> 16);
+        uint32_t acc[4] = {0, 0, 0, 0};
+        constexpr int KW[7] = {18, 34, 48, 56, 48, 34, 18};
+#pragma unroll
+        for (int j = 0; j < 7; ++j) {
+            const uint2 m = *reinterpret_cast<const uint2*>(&mid[r + j][4 * q]);
+            acc[0] += KW[j] * (m.x & 0xffffu); acc[1] += KW[j] * (m.x >> 16); acc[2] += KW[j] * (m.y & 0xffffu); acc[3] += KW[j] * (m.y >> 16);
+        }
+        uint32_t pk = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) pk |= ((acc[k] + 32768u) >> 16) << (8 * k);
+        *reinterpret_cast<uint32_t*>(out + (long long)gy * L.stride + gx) = pk;          // rows padded to 128 B
     }
 }
 
@@ -395,7 +511,7 @@ struct AfvOs2 {
     unsigned short* knode[AFV_MAX_LEVELS]; unsigned char* kquad[AFV_MAX_LEVELS]; uint2* keep[AFV_MAX_LEVELS]; uint2* tab[AFV_MAX_LEVELS];
     int det_cap[AFV_MAX_LEVELS], keep_cap[AFV_MAX_LEVELS], max_stride[AFV_MAX_LEVELS], max_lh[AFV_MAX_LEVELS], q[AFV_MAX_LEVELS];
     float sf[AFV_MAX_LEVELS], size_norm[AFV_MAX_LEVELS];
-    int* cellcnt; int cells_cap;
+    int* cellcnt; uint32_t* cellmask; int cells_cap;
     uint8_t* gray_stage;
     int* h_status; int* h_counts;
     int cur_w, cur_h, last_B;
@@ -499,6 +615,7 @@ int afv_os2_create(AfvOs2** out, int nfeatures, int nlevels, float scale_factor,
         if (rc == AFV_OK) rc = os2_alloc(s, &s->tab[l], (size_t)(lw[l] + lh[l] + 8));
     }
     if (rc == AFV_OK) rc = os2_alloc(s, &s->cellcnt, (size_t)s->cells_cap * B);
+    if (rc == AFV_OK) rc = os2_alloc(s, &s->cellmask, (size_t)s->cells_cap * 32 * B);
     if (rc == AFV_OK) rc = os2_alloc(s, &s->P.counts, 4 * AFV_MAX_LEVELS * B);
     if (rc == AFV_OK) rc = os2_alloc(s, &s->P.status, B);
     if (rc == AFV_OK) rc = os2_alloc(s, &s->gray_stage, (size_t)max_w * max_h * B);
@@ -541,7 +658,7 @@ static int os2_configure(AfvOs2* s, int w, int h) {
     Os2Params& P = s->P;
     int* counts = P.counts; int* status = P.status;
     memset(&P, 0, sizeof(P));
-    P.counts = counts; P.status = status; P.cellcnt = s->cellcnt;
+    P.counts = counts; P.status = status; P.cellcnt = s->cellcnt; P.cellmask = s->cellmask;
     P.nlevels = s->nlevels; P.ini_th = s->ini_th; P.min_th = s->min_th;
     P.oct_ncap = (int)0;
     int maxq = 0, cells = 0;
@@ -606,7 +723,7 @@ int afv_os2_run(AfvOs2* s, const uint8_t* d_gray, int B, int w, int h, int strid
       k_os2_octree<<<dim3(P.nlevels, B), 256, s->oct_smem, st>>>(P); ++g_afv_launches; }
     for (int l = 0; l < P.nlevels; ++l) {
         AfvProfScope ps("k_os2_blur", st);
-        k_os2_blur<<<dim3((P.lv[l].w + SC_W - 1) / SC_W, (P.lv[l].h + SC_H - 1) / SC_H, B), 256, 0, st>>>(P, l); ++g_afv_launches;
+        k_os2_blur<<<dim3((P.lv[l].w + BL_W - 1) / BL_W, (P.lv[l].h + BL_H - 1) / BL_H, B), 256, 0, st>>>(P, l); ++g_afv_launches;
     }
     { AfvProfScope ps("k_os2_describe", st);
       k_os2_describe<<<dim3((cap + 7) / 8, B), 256, 0, st>>>(P, d_kps, d_desc, d_kpsize, d_n_out); ++g_afv_launches; }
