@@ -63,9 +63,27 @@ __device__ __forceinline__ void oct_carve(unsigned char* base, int ncap, OctWork
 // Distributes M keys (kx, ky in full-image coordinates; any address space) over the quadtree until >= N nodes.
 // On return knode[k] = final list position of key k's node; returns the node count (list order = reference list
 // order).  Called by all 256 threads of the CTA.  overflow is set when the node list would exceed ncap.
+// Key positions come through an accessor (x(k), y(k)): plain float arrays (OctXYArrays, any address space) or, for orb32, level
+// coordinates packed in one word and scaled on the fly (k_octree: 11 instead of 19 bytes of shared memory per key).
+struct OctXYArrays {
+    const float* kx; const float* ky;
+    __device__ __forceinline__ float x(int k) const { return kx[k]; }
+    __device__ __forceinline__ float y(int k) const { return ky[k]; }
+};
+template <class XY>
+__device__ __forceinline__ int oct_distribute_xy(const OctWork& W, const XY xy, unsigned short* knode,
+                                                 unsigned char* kquad, int M, int N, int nIni, float hX, int H, int ncap,
+                                                 int tid, bool& overflow);
 __device__ __forceinline__ int oct_distribute(const OctWork& W, const float* kx, const float* ky, unsigned short* knode,
                                               unsigned char* kquad, int M, int N, int nIni, float hX, int H, int ncap,
                                               int tid, bool& overflow) {
+    OctXYArrays a; a.kx = kx; a.ky = ky;
+    return oct_distribute_xy(W, a, knode, kquad, M, N, nIni, hX, H, ncap, tid, overflow);
+}
+template <class XY>
+__device__ __forceinline__ int oct_distribute_xy(const OctWork& W, const XY xy, unsigned short* knode,
+                                                 unsigned char* kquad, int M, int N, int nIni, float hX, int H, int ncap,
+                                                 int tid, bool& overflow) {
     __shared__ int warp_tot[8];
     __shared__ int s_J, s_nexp;
     OctNode* const* nd = W.nd; int* const* ncnt = W.ncnt;
@@ -78,7 +96,7 @@ __device__ __forceinline__ int oct_distribute(const OctWork& W, const float* kx,
     }
     __syncthreads();
     for (int k = tid; k < M; k += 256) {
-        const int b = min((int)__fdiv_rn(kx[k], hX), nIni - 1);
+        const int b = min((int)__fdiv_rn(xy.x(k), hX), nIni - 1);
         knode[k] = (unsigned short)b;
         atomicAdd(&ncnt[0][b], 1);
     }
@@ -108,7 +126,8 @@ __device__ __forceinline__ int oct_distribute(const OctWork& W, const float* kx,
                 const int halfX = (int)ceilf(__fdiv_rn((float)(n.urx - n.ulx), 2.f));
                 const int halfY = (int)ceilf(__fdiv_rn((float)(n.bry - n.uly), 2.f));
                 const float sx = (float)(n.ulx + halfX), sy = (float)(n.uly + halfY);
-                const int q = (kx[k] < sx) ? ((ky[k] < sy) ? 0 : 2) : ((ky[k] < sy) ? 1 : 3);
+                const float px = xy.x(k), py = xy.y(k);
+                const int q = (px < sx) ? ((py < sy) ? 0 : 2) : ((py < sy) ? 1 : 3);
                 kquad[k] = (unsigned char)q;
                 atomicAdd(&qcnt[p * 4 + q], 1);
             }

@@ -524,16 +524,20 @@ __global__ void __launch_bounds__(256) k_harris_select(const __grid_constant__ A
 // K9: DistributeOctTree, one CTA per (frame, level); the list algorithm is in afv_octree.cuh.
 // The per-node max-response pick prefers the smaller raster index (the oracle's canonical order).
 // ------------------------------------------------------------------------------------------------------
+// keys of one (frame, level) in shared memory: packed level coordinates (scaled to level-0 on the fly exactly as the float arrays
+// were: x * scale, one rounding) + ordered response + node position + quadrant = 11 bytes per key
+struct OctXYPacked {
+    const uint32_t* pk; float scale;
+    __device__ __forceinline__ float x(int k) const { return __fmul_rn((float)(pk[k] & 0xfffu), scale); }
+    __device__ __forceinline__ float y(int k) const { return __fmul_rn((float)((pk[k] >> 12) & 0xfffu), scale); }
+};
 __global__ void __launch_bounds__(256) k_octree(const __grid_constant__ AfvParams P, int mcap, int ncap) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    // keys
-    float* kx = reinterpret_cast<float*>(smem_raw);                  // [mcap] level-0 x
-    float* ky = kx + mcap;                                           // [mcap]
-    uint32_t* kresp = reinterpret_cast<uint32_t*>(ky + mcap);        // [mcap] ordered response
-    uint32_t* kras = kresp + mcap;                                   // [mcap] raster index y*w+x (level coords)
-    unsigned short* knode = reinterpret_cast<unsigned short*>(kras + mcap);   // [mcap] list position of the key's node
+    uint32_t* kpk = reinterpret_cast<uint32_t*>(smem_raw);           // [mcap] x | y << 12 (level coordinates)
+    uint32_t* kresp = kpk + mcap;                                    // [mcap] ordered response
+    unsigned short* knode = reinterpret_cast<unsigned short*>(kresp + mcap);   // [mcap] list position of the key's node
     unsigned char* kquad = reinterpret_cast<unsigned char*>(knode + mcap);    // [mcap]
-    const size_t off = ((size_t)mcap * (4 + 4 + 4 + 4 + 2 + 1) + 15) & ~(size_t)15;
+    const size_t off = ((size_t)mcap * (4 + 4 + 2 + 1) + 15) & ~(size_t)15;
     OctWork W;
     oct_carve(smem_raw + off, ncap, W);
     unsigned long long* best = W.best;
@@ -548,21 +552,23 @@ __global__ void __launch_bounds__(256) k_octree(const __grid_constant__ AfvParam
 
     for (int k = tid; k < M; k += 256) {
         const uint2 d = det[k];
-        const int x = d.x & 0xfff, y = (d.x >> 12) & 0xfff;
-        kx[k] = __fmul_rn((float)x, L.scale); ky[k] = __fmul_rn((float)y, L.scale);
+        kpk[k] = d.x & 0xffffffu;
         kresp[k] = f2ord(__uint_as_float(d.y));
-        kras[k] = (uint32_t)(y * L.w + x);
     }
     __syncthreads();
     bool overflow = false;
-    int size = oct_distribute(W, kx, ky, knode, kquad, M, N, P.n_ini, P.hX, P.H, ncap, tid, overflow);
+    OctXYPacked xy; xy.pk = kpk; xy.scale = L.scale;
+    int size = oct_distribute_xy(W, xy, knode, kquad, M, N, P.n_ini, P.hX, P.H, ncap, tid, overflow);
     if (overflow && tid == 0) atomicOr(&P.status[f], AFV_ST_OCTREE_OVERFLOW);
 
     // ---- best key per node: max response, ties -> smaller raster index
     for (int p = tid; p < size; p += 256) best[p] = 0ull;
     __syncthreads();
-    for (int k = tid; k < M; k += 256)
-        atomicMax(&best[knode[k]], ((unsigned long long)kresp[k] << 32) | (unsigned long long)(0xffffffffu - kras[k]));
+    for (int k = tid; k < M; k += 256) {
+        const uint32_t pk = kpk[k];
+        const uint32_t ras = ((pk >> 12) & 0xfffu) * (uint32_t)L.w + (pk & 0xfffu);
+        atomicMax(&best[knode[k]], ((unsigned long long)kresp[k] << 32) | (unsigned long long)(0xffffffffu - ras));
+    }
     __syncthreads();
     for (int p = tid; p < size; p += 256) {
         const unsigned long long b = best[p];
@@ -577,7 +583,7 @@ __global__ void __launch_bounds__(256) k_octree(const __grid_constant__ AfvParam
 }
 
 size_t afv_octree_smem_bytes(int mcap, int ncap) {
-    const size_t off = ((size_t)mcap * (4 + 4 + 4 + 4 + 2 + 1) + 15) & ~(size_t)15;
+    const size_t off = ((size_t)mcap * (4 + 4 + 2 + 1) + 15) & ~(size_t)15;
     return off + oct_work_bytes(ncap);
 }
 
@@ -716,7 +722,7 @@ __device__ __forceinline__ float fast_atan2_deg(float y, float x) {
     return a;
 }
 
-__global__ void __launch_bounds__(256, 5) k_describe(const __grid_constant__ AfvParams P, afv_keypoint* __restrict__ kps,
+__global__ void __launch_bounds__(256, 6) k_describe(const __grid_constant__ AfvParams P, afv_keypoint* __restrict__ kps,
                                                   uint8_t* __restrict__ desc, float* __restrict__ kpsize,
                                                   int* __restrict__ n_out) {
     __shared__ float2 patf[8][2][32];        // patf[k][j][lane] = point j (x, y) of test k of descriptor byte `lane`, as floats

@@ -448,3 +448,28 @@ def test_undistort_keypoints_and_grid(pkg, extracted, golden_dir):
     cs, ci = pkg.FeatureMatcher.grid_build(un, n_d, BOUNDS)
     torch.cuda.synchronize()
     assert int(cs[0, -1]) <= int(n_d[0])
+
+
+def test_pack_results_kernel_matches_layout(pkg):
+    """afv_pack_results (one launch) == sharding.pack_layout / unpack_results, the message format of the multi-GPU gather."""
+    import torch
+    sh = pkg.sharding
+    rng = np.random.default_rng(3)
+    for B, cap, D in ((3, 40, 32), (2, 36, 48), (4, 64, 61), (1, 16, 512)):
+        n = torch.from_numpy(rng.integers(0, cap, B).astype(np.int32)).cuda()
+        nm = torch.from_numpy(rng.integers(0, 200, B).astype(np.int32)).cuda()
+        m12 = torch.from_numpy(rng.integers(-1, cap, (B, cap)).astype(np.int32)).cuda()
+        kps = torch.from_numpy(rng.normal(size=(B, cap, 7)).astype(np.float32)).cuda()
+        desc = torch.from_numpy(rng.integers(0, 256, (B, cap, D), dtype=np.uint8)).cuda()
+        _, total = sh.pack_layout(B, cap, D)
+        assert total % 4 == 0
+        pack = torch.zeros(total, dtype=torch.uint8, device="cuda")
+        launches = pkg.kernel_launches()
+        sh.pack_results(pack, n, nm, m12, kps, desc)
+        torch.cuda.synchronize()
+        assert pkg.kernel_launches() == launches + 1                      # the library kernel ran, not five torch copies
+        u = sh.unpack_results(pack.cpu().numpy(), B, cap, D)
+        assert (u["n"] == n.cpu().numpy()).all() and (u["nmatches"] == nm.cpu().numpy()).all()
+        assert (u["matches12"] == m12.cpu().numpy()).all()
+        assert (u["kps"].view(np.float32).reshape(B, cap, 7) == kps.cpu().numpy()).all()
+        assert (u["desc"] == desc.cpu().numpy()).all()
