@@ -1,0 +1,102 @@
+#!/usr/bin/env python3
+"""Builds profiles/r02_summary.md from the committed bench lines (profiles/r02A_*.json, r02t_bench_c3/c4) and the ncu reports that were
+brought back in gpurun_out/ (r02A_orb.ncu-rep: final orb32 kernels; r02w_os2.ncu-rep: vanilla kernels before the last rewrite;
+r02r_match.ncu-rep: matcher kernels).  Run here (no GPU needed): python tools/make_r02_summary.py"""
+import json, os, subprocess, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+os.chdir(ROOT)
+
+
+def last(f):
+    return json.loads(open(f).read().strip().splitlines()[-1])
+
+
+def ncu_table(rep, units):
+    if not os.path.exists(rep):
+        return "(report %s not present in this checkout)\n" % rep
+    return subprocess.run([sys.executable, "tools/ncu_summary.py", rep, str(units)], capture_output=True, text=True).stdout
+
+
+c2 = last("profiles/r02A_bench_c2_n1.json"); m1 = last("profiles/r02A_bench_m1.json")
+ns = {n: last("profiles/r02A_bench_c2_n%d.json" % n) for n in (1, 2, 4, 8)}
+c3 = last("profiles/r02t_bench_c3_n1.json"); c4 = last("profiles/r02t_bench_c4_n1.json"); c5 = last("profiles/r02A_bench_c5_n1.json")
+ref = last("profiles/r02A_bench_reference_arm.json"); rp = last("profiles/r02A_bench_reference_real_parts.json"); cv = last("profiles/r02A_bench_c2v_n1.json")
+k = c2["roofline"]["kernel_ms_per_step"]
+out = []
+A = out.append
+A("# Round 2 profile summary (B200, sm_100a; all numbers from `gpurun` boxes, clocks 1965 / 1965 MHz, no throttle reason)\n")
+A("Raw artefacts in this directory: `r02A_bench_c2_n{1,2,4,8}.json` (the default line incl. its `c5` block at 1 / 2 / 4 / 8 GPUs, final tree),")
+A("`r02A_bench_{c5_n1,c2v_n1,m1}.json`, `r02t_bench_{c3,c4}_n1.json`, `r02A_bench_reference_arm.json`, `r02A_bench_reference_real_parts.json`, ncu launch lists")
+A("`r02A_launches_c2_batch512.csv` / `r02A_launches_c2v_batch512.csv` (`--metrics gpu__time_duration.sum --clock-control none`).  The `.ncu-rep` files")
+A("(`--set full --import-source on`, 23-34 MB each) stay in `gpurun_out/`; the tables below are `tools/ncu_summary.py` / `tools/ncu_lines.py` read-outs of them")
+A("(regenerate this file with `tools/make_r02_summary.py`).\n")
+A("## 1. Headline (c2 = BASELINE configs[1]: orb32 640x480, 1000 kp, 512 frames + 512 SearchForInitialization pairs per step, 1 GPU)\n")
+A("| | round 1 | round 2 |\n|---|---|---|")
+A("| inputs resident in HBM | 110.3 k frames/s (4.64 ms / step) | **%.1f k frames/s (%.2f ms / step)** |" % (c2["value"] / 1e3, c2["ms_per_step"]))
+A("| end to end (pinned host frames in, results on host) | 106.9 k | **%.1f k** |" % (c2["e2e"]["value"] / 1e3))
+A("| CPU arm (`--impl reference`, oracle C port, 16 threads, same 512-frame step) | 815 | %.0f |" % ref["value"])
+A("| CPU arm from the reference's real parts (`--real-parts`: cv2 binary + `oracle/_ref`, 16 processes) | - | %.0f (slower than the port, as stated in DESIGN 7) |" % rp["value"])
+A("| end-to-end ratio over the CPU arm | 131 x | %.0f x |\n" % (c2["e2e"]["value"] / ref["value"]))
+A("Per-kernel CUDA-event times of the profile leg (one stream, additive; ms per 512-frame step), round 1 -> round 2:\n")
+r1 = {"k_resize": 0.73, "k_fast": 1.43, "k_harris_select": 0.46, "k_octree": 0.25, "k_blur": 0.81, "k_describe": 0.77, "k_sfi_lists": 0.42, "k_sfi_resolve": 0.42}
+why = {"k_resize": "128x32 tiles (prologue amortised over 16 px per thread)",
+       "k_fast": "packed 16x2 compass test on 4 px per thread-row, stage 2 = score only, (d,-d) differences as one IMAD per circle pixel, interior-tile fast path, warp-aggregated outputs",
+       "k_harris_select": "9-byte Harris rows from three aligned 32-bit loads + funnel shifts (44 % of the stall samples sat on the byte loads); parallel suffix scans",
+       "k_octree": "keys as packed level coordinates scaled on the fly: 11 instead of 19 bytes of shared memory per key, 5 instead of 3 CTAs per SM",
+       "k_blur": "REFLECT_101 patch taken from the staged tile (22 % of the instructions were the per-row global patch loop that >50 % of the tiles ran)",
+       "k_describe": "float pattern table in shared memory, branch-free inner tap path, sincos, 6 CTAs per SM",
+       "k_sfi_lists": "in-window slots buffered per warp, distances with 32 of 32 lanes (was 11), word count unrolled",
+       "k_sfi_resolve": "32-bit compact keys + redux.sync for the sorted-prefix phase"}
+A("| kernel | r1 | r2 | what changed |\n|---|---|---|---|")
+for n in ("k_resize", "k_fast", "k_harris_select", "k_octree", "k_blur", "k_describe", "k_sfi_lists", "k_sfi_resolve"):
+    A("| `%s` | %.2f | %.3f | %s |" % (n, r1[n], k[n], why[n]))
+A("| sum | 5.29 (overlapped: 4.64) | %.2f (overlapped: %.2f) | matcher of step i runs beside the extraction of step i+1 |\n" % (sum(k.values()), c2["ms_per_step"]))
+A("Roofline of the dominant kernel (`roofline` block of the line): `%s` %.1f GB/s of %.1f measured = **%.3f**; the kernel is ALU-pipe bound (table below:" % (c2["roofline"]["kernel"], c2["roofline"]["achieved"], c2["roofline"]["peak"], c2["roofline"]["frac"]))
+A("ALU 74 %%, issue 77 %%, DRAM 6 %%), not HBM bound; whole step %.0f GB/s algorithmic = %.3f of the measured copy peak.\n" % (c2["roofline"]["step_algorithmic_gbs"], c2["roofline"]["step_algorithmic_gbs"] / c2["roofline"]["peak"]))
+A("### ncu `--set full`, batch 128, final kernels (per launch; `instr / unit` = warp instructions per frame)\n")
+A(ncu_table("gpurun_out/r02A_orb.ncu-rep", 128))
+A("\nShares of the serialised launch list at batch 512 (`r02A_launches_c2_batch512.csv`) follow the same ranking as the event times above.\n")
+A("Measured and rejected this round (kept out of the tree, recorded in the kernel comments): a per-warp candidate QUEUE for the windowed matcher (1.31 vs 1.10 ms at r = 15,")
+A("10.6 vs 9.85 ms at r = 100); a per-lane `while (mask)` survivor writer in k_fast (1.17 vs 1.13 ms although it issues fewer instructions: the kernel is bound by the ALU")
+A("pipe, not by issue slots); `__launch_bounds__(256, 4)` on k_harris_select (0.47 vs 0.44 ms, spills); running the selection kernels on a high-priority side stream beside")
+A("k_blur (no overlap: three selection CTAs hold 57 k of the 64 k registers of an SM, so no blur CTA fits next to them).\n")
+A("## 2. Matcher against its own rooflines (`bench.py --workload m1`, 10 240 frame pairs of a resident 512-frame extraction, SURVEY 8d)\n")
+A("| kernel | configuration | ms / 10 240 pairs | fraction of HBM peak on the 112.9 KB / pair algorithmic bytes | fraction of the POPC peak (148 x 16 x 1.965 G) |\n|---|---|---|---|---|")
+for b in m1["matcher_kernels"]:
+    A("| `%s` | %s | %.3f | %s | %s |" % (b["kernel"], b["config"], b["ms"], ("%.4f" % b["frac"]) if b["unit"] == "GB/s" else "-",
+                                      ("%.4f" % b["popc_frac"]) if b.get("popc_frac") else (("%.4f" % b["frac"]) if "popc" in b["unit"] else "-")))
+A("\nRound 1 for comparison (BENCH_r01: one CTA per pair, warp per query): windowed lists 0.024, resolver 0.007 of the HBM peak. The windowed matcher at r = 15 is now at 0.16")
+A("(6.7x), SearchForInitialization end to end at 0.0285 of the HBM figure (9.5 ms at the start of the round -> 6.2 ms); the brute-force kernel runs at 96 % of the POPC peak.")
+A("ncu of the matcher kernels (2 048 pairs per launch; the windowed launches captured are the r = 100 configuration; `k_sfi_resolve` captured BEFORE the compact-key change, which")
+A("cut it from 4.4 to about 2.2 ms per 10 240 pairs):\n")
+A(ncu_table("gpurun_out/r02r_match.ncu-rep", 2048))
+A("\nWhat bounds them: `k_match_window_pairs` -- instruction issue under SIMT divergence (issue active 81 %, 9.4 of 32 lanes: a thread walks its query's cell columns, trip counts")
+A("differ per lane; DRAM 0.3 % because the 512 resident frames (34 MB) live in L2, i.e. the 1.05 TB/s \"HBM-equivalent\" at r = 15 is L2 traffic); `k_sfi_lists` -- issue (73 %), 27 of 32")
+A("lanes after the buffered distance pass; `k_sfi_resolve` -- ALU pipe (73 %) at >= 2 048 pairs (the sorted-prefix extraction) and the sequential per-pair chain (~0.19 ms for 218")
+A("queries) at 512 pairs.  The 60 % HBM target of SURVEY 8d is not met by any of them: per pair the kernels execute 0.3-0.9 M warp instructions for 113 KB of compulsory bytes, i.e. they")
+A("are instruction bound by two orders of magnitude before bandwidth matters.\n")
+A("## 3. Other configurations (1 GPU)\n")
+A("| workload | resident | end to end | CPU port (16 threads) | dominant kernel, fraction of measured HBM peak |\n|---|---|---|---|---|")
+for name, j in (("c3 sift128 1280x720, 2000 kp, B = 64", c3), ("c4 akaze61 + brisk48 640x480 (both extractors + both matchers), B = 256", c4),
+                ("c5 orb32 1280x720, 2000 kp, 8 fixed streams x 128 frames = 1024 frames / step (`--workload c5`, pipelined e2e leg)", c5),
+                ("c2v vanilla ORB-SLAM2 extractor 640x480, 1000 kp, B = 512", cv)):
+    A("| %s | %.1f k | %.1f k | %.0f | `%s` %.3f |" % (name, j["value"] / 1e3, j["e2e"]["value"] / 1e3, j["cpu_baseline"]["value"], j["roofline"]["kernel"], j["roofline"]["frac"]))
+A("\nc2v per-kernel ms / 512 frames (final): " + ", ".join("%s %.2f" % kv for kv in cv["roofline"]["kernel_ms_per_step"].items()) + ".  First version of these kernels: 11.4 ms / step (45.0 k frames/s):")
+A("k_os2_cells 3.82 -> 1.61 (lane = column with shuffles, row masks handed from the count to the emit pass), k_os2_score 3.51 -> 2.98 (compass pre-test + survivor compaction; at")
+A("minThFAST = 7 a third of the pixels pass the pre-test and 13 % are corners before NMS), k_os2_blur 2.08 -> 1.31 (4 px per thread from aligned words).  ncu of the FIRST version (batch 128):\n")
+A(ncu_table("gpurun_out/r02w_os2.ncu-rep", 128))
+A("\n## 4. Several GPUs (default line of `bench.py --gpus N` under torchrun, final tree; the `c5` block = BASELINE configs[4] as SURVEY 8e specifies it)\n")
+A("| GPUs | c2 resident (weak: 512 frames per GPU) | c2 end to end | c5 block, resident (strong: 1024 frames in total) | c5 validated ranks | c5 checksum (N-independent) | concurrent H2D of all ranks |\n|---|---|---|---|---|---|---|")
+for n in (1, 2, 4, 8):
+    j = ns[n]; c = j["c5"]
+    A("| %d | %.1f k (%.3f ms) | %.1f k | %.1f k (%.2f ms) | %d of %d | %s | %.0f GB/s |" % (n, j["value"] / 1e3, j["ms_per_step"], j["e2e"]["value"] / 1e3, c["value"] / 1e3, c["ms_per_step"],
+                                                                                         c["validated_ranks"], n, c["checksum_all_ranks"], c["h2d_gbs_aggregate_all_ranks_concurrent"]))
+v1 = ns[1]["value"]; s1 = ns[1]["c5"]["value"]; e1 = ns[1]["e2e"]["value"]
+A("\nDevice-timed weak scaling of c2: %s.  c5 strong scaling: %s: at 128 frames per GPU the latency-bound kernels" % (
+    ", ".join("%.3f at %d" % (ns[n]["value"] / (n * v1), n) for n in (2, 4, 8)), ", ".join("%.2fx at %d" % (ns[n]["c5"]["value"] / s1, n) for n in (2, 4, 8))))
+A("(one CTA per (frame, level) / per pair) no longer fill the chip.  End to end (%s of linear) is bounded by the HOST: the ranks copying concurrently reach" % ", ".join("%.2f at %d" % (ns[n]["e2e"]["value"] / (n * e1), n) for n in (2, 4, 8)))
+A("56 / 111 / 153 / 187 GB/s in total at 1 / 2 / 4 / 8 GPUs while c2 at the device rate needs %.0f GB/s of input alone at 8 GPUs (`e2e.h2d_gbs_needed_at_device_rate`); with 157 MB in + 34 MB out" % ns[8]["e2e"]["h2d_gbs_needed_at_device_rate"])
+A("per 512 frames and GPU, (1.26 + 0.27) GB per step over 187 GB/s = 8.2 ms per step = 500 k frames/s at best at 8 GPUs; measured %.0f k = %.2f of that ceiling (the box exposes one NUMA node," % (ns[8]["e2e"]["value"] / 1e3, ns[8]["e2e"]["value"] / 500e3))
+A("`nvidia-smi topo`: every GPU on CPUs 0-31, so there is no placement to fix).")
+open("profiles/r02_summary.md", "w").write("\n".join(out) + "\n")
+print("profiles/r02_summary.md written")
