@@ -65,13 +65,14 @@ A("| kernel | configuration | ms / 10 240 pairs | fraction of HBM peak on the 11
 for b in m1["matcher_kernels"]:
     A("| `%s` | %s | %.3f | %s | %s |" % (b["kernel"], b["config"], b["ms"], ("%.4f" % b["frac"]) if b["unit"] == "GB/s" else "-",
                                       ("%.4f" % b["popc_frac"]) if b.get("popc_frac") else (("%.4f" % b["frac"]) if "popc" in b["unit"] else "-")))
-A("\nRound 1 for comparison (BENCH_r01: one CTA per pair, warp per query): windowed lists 0.024, resolver 0.007 of the HBM peak. The windowed matcher at r = 15 is now at 0.16")
-A("(6.7x), SearchForInitialization end to end at 0.0285 of the HBM figure (9.5 ms at the start of the round -> 6.2 ms); the brute-force kernel runs at 96 % of the POPC peak.")
+A("\nRound 1 for comparison (BENCH_r01: one CTA per pair, warp per query): windowed lists 0.024, resolver 0.007 of the HBM peak. The windowed matcher at r = 15 is now at 0.17")
+A("(7x), SearchForInitialization end to end at 0.0285 of the HBM figure (9.5 ms at the start of the round -> 6.2 ms); the brute-force kernel runs at 96 % of the POPC peak.")
 A("ncu of the matcher kernels (2 048 pairs per launch; the windowed launches captured are the r = 100 configuration; `k_sfi_resolve` captured BEFORE the compact-key change, which")
 A("cut it from 4.4 to about 2.2 ms per 10 240 pairs):\n")
 A(ncu_table("gpurun_out/r02r_match.ncu-rep", 2048))
-A("\nWhat bounds them: `k_match_window_pairs` -- instruction issue under SIMT divergence (issue active 81 %, 9.4 of 32 lanes: a thread walks its query's cell columns, trip counts")
-A("differ per lane; DRAM 0.3 % because the 512 resident frames (34 MB) live in L2, i.e. the 1.05 TB/s \"HBM-equivalent\" at r = 15 is L2 traffic); `k_sfi_lists` -- issue (73 %), 27 of 32")
+A("\nWhat bounds them: `k_match_window_pairs` -- instruction issue under SIMT divergence (r = 100: issue active 81 %, 9.4 of 32 lanes; r = 15 (`gpurun_out/r02C_mwp15.ncu-rep`): issue")
+A("active 85 %, 8.1 of 32 lanes, 98 k warp instructions per pair of which 50 % are the distance loop running at 4.4 of 32 lanes: a thread walks its query's cell columns, trip counts")
+A("differ per lane; DRAM 0.3 - 1.8 % because the 512 resident frames (34 MB) live in L2, i.e. the 1.05 TB/s \"HBM-equivalent\" at r = 15 is L2 traffic); `k_sfi_lists` -- issue (73 %), 27 of 32")
 A("lanes after the buffered distance pass; `k_sfi_resolve` -- ALU pipe (73 %) at >= 2 048 pairs (the sorted-prefix extraction) and the sequential per-pair chain (~0.19 ms for 218")
 A("queries) at 512 pairs.  The 60 % HBM target of SURVEY 8d is not met by any of them: per pair the kernels execute 0.3-0.9 M warp instructions for 113 KB of compulsory bytes, i.e. they")
 A("are instruction bound by two orders of magnitude before bandwidth matters.\n")
