@@ -358,7 +358,7 @@ __global__ void __launch_bounds__(256) k_akz_extrema(const __grid_constant__ Akz
     const float v = D[0];
     if (!(v > P.dth && v >= 0.00001f && v > D[-1] && v > D[1] && v > D[-st - 1] && v > D[-st] && v > D[-st + 1] &&
           v > D[st - 1] && v > D[st] && v > D[st + 1])) return;
-    const float smax = 12.0f * 0x1.6a09e6p+0f;
+    const float smax = 10.0f * 0x1.6a09e6p+0f;        // 10 sqrt(2): libAKAZE's descriptor border for SURF / MLDB (12 sqrt 2 is M-SURF); cv2 agrees
     const float ratio = (float)(1 << L.octave);
     const int sigma_size = (int)(L.psize / ratio + 0.5f);
     const int left = akz_fround((float)x - smax * (float)sigma_size) - 1, right = akz_fround((float)x + smax * (float)sigma_size) + 1;

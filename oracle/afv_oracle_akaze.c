@@ -1,7 +1,7 @@
 /*
  * afv_oracle_akaze.c -- CPU ORACLE (TEST INFRASTRUCTURE ONLY) of the akaze61 extraction path.
  *
- * PARITY UNPINNED.  The reference's akaze61 arithmetic lives in libAKAZE (fontan::akaze, un-pinned; upstream
+ * PARITY UNPINNED vs libAKAZE, PINNED to cv2 4.13.0 up to two documented differences.  The reference's akaze61 arithmetic lives in libAKAZE (fontan::akaze, un-pinned; upstream
  * pablofdezalc/akaze; reference call sites src/Feature_akaze61.cpp:7-13 (options), :24-34 (scale space), :36-45
  * (detection), :47-61 (descriptors)), which is NOT vendored under the reference tree.  This file restates the PUBLISHED
  * algorithm (Alcantarilla, Nuevo, Bartoli: "Fast Explicit Diffusion for Accelerated Features in Nonlinear Scale Spaces",
@@ -11,7 +11,14 @@
  * descriptor, 3 channels, pattern size 10), and everything the reference does around it: octave := class_id (evolution
  * level, :63-65), DistributeOctTree per level with quota mnFeaturesPerLevel (src/FeatureExtractor.cpp:276-284), all
  * levels merged before Compute_Descriptors (:51-60), computeSize with powf(scaleFactor0, class_id) (:67-69).
- * cv2.AKAZE (OpenCV's port of libAKAZE by the same author) is used as a FAMILY CHECK in tests/test_oracle_akaze.py.
+ * cv2.AKAZE (OpenCV's port of libAKAZE by the same author) PINS everything except the duplicate filter and the orientation search:
+ * with orc_akaze_set_cv2_filter(1) (OpenCV's restructured cross-level filter, akz_detect_cv below) the oracle reproduces cv2 4.13.0's
+ * AKAZE_create(threshold 5e-4, 2 octaves, 4 layers) keypoint list EXACTLY -- same count, same order, positions to 1e-4 px, sizes
+ * identical, responses to 3e-7 -- and, where the two orientation searches agree (< 0.001 deg, 43 % of the keypoints), 99 % of the
+ * 486-bit descriptors bit for bit (all within 2 bits).  OpenCV quantises the 109 sample angles into 42 slices before sliding the
+ * pi/3 window, libAKAZE (restated here) slides it over the exact angles: 11 % of the keypoints get an orientation > 1 deg apart.
+ * The default mode (libAKAZE's sequential Find_Scale_Space_Extrema) finds 99.8 % of cv2's keypoints plus the ones OpenCV's filter
+ * drops.  tests/test_oracle_akaze.py holds both checks.
  *
  * Arithmetic contract (what the CUDA path reproduces bit for bit): IEEE float32, round to nearest, NO fused multiply-add
  * except the explicit fmaf() of the Gaussian taps, operation order exactly as written; exp / atan2 / sin / cos are the polynomial forms shared with the sift128 oracle;
@@ -310,7 +317,7 @@ typedef struct { float x, y, size, response; int octave, class_id; } akz_pt;
 static int akz_detect(const akz_space* S, float dthreshold, akz_pt** out) {
     int cap = 4096, n = 0;
     akz_pt* A = (akz_pt*)malloc(sizeof(akz_pt) * cap);
-    const float smax = 12.0f * 0x1.6a09e6p+0f;                       /* MLDB: 12 sqrt(2) */
+    const float smax = 10.0f * 0x1.6a09e6p+0f;                       /* MLDB: 10 sqrt(2) (libAKAZE: SURF and MLDB descriptors 10 sqrt 2, M-SURF 12 sqrt 2; cv2 keeps keypoints from row 29 on at sigma_size 2) */
     for (int i = 0; i < S->nl; ++i) {
         const int w = S->L[i].w, h = S->L[i].h;
         const float* D = S->Ldet[i];
@@ -375,6 +382,106 @@ static int akz_detect(const akz_space* S, float dthreshold, akz_pt** out) {
     free(A);
     *out = K;
     return m;
+}
+
+/* ---- detection, OpenCV's variant (cv::AKAZEFeatures::Find_Scale_Space_Extrema + Do_Subpixel_Refinement of OpenCV 4.x) ---------
+ * OpenCV restructured libAKAZE's sequential duplicate filter for parallel execution: (1) per level, a byte mask of the strict 3x3
+ * maxima above the threshold inside the descriptor border, where a new maximum first looks for an already marked one within
+ * sigma_size (first hit of a square raster scan that passes the radius test) and the weaker of the two goes; (2) for every level i >= 1 in raster order, the FIRST marked point of level
+ * i - 1 inside a search window around the projected position (square scan, radius test) is cleared when the level-i response is
+ * larger; (3) the same from the top level down against level i + 1; (4) sub-pixel refinement of what is left, level by level in raster
+ * order.  This mode exists ONLY to pin the rest of the pipeline (scale space, Hessian responses,
+ * sub-pixel fit, orientation, MLDB) to the cv2 4.13.0 binary keypoint by keypoint; the reference links libAKAZE, whose filter is the
+ * default mode above. */
+static int akz_find_neighbor(const unsigned char* mask, int w, int h, int x, int y, int r, int* idx) {
+    for (int i = y - r; i < y + r; ++i) {
+        if (i < 0 || i >= h) continue;
+        for (int j = x - r; j < x + r; ++j) {
+            if (j < 0 || j >= w || !mask[(size_t)i * w + j]) continue;
+            if ((i - y) * (i - y) + (j - x) * (j - x) <= r * r) { *idx = i * w + j; return 1; }
+        }
+    }
+    return 0;
+}
+static int akz_detect_cv(const akz_space* S, float dthreshold, akz_pt** out) {
+    const float smax = 10.0f * 0x1.6a09e6p+0f;
+    unsigned char* mask[ORC_MAX_LEVELS];
+    int total = 0;
+    for (int i = 0; i < S->nl; ++i) {
+        const int w = S->L[i].w, h = S->L[i].h;
+        const float* D = S->Ldet[i];
+        mask[i] = (unsigned char*)calloc((size_t)w * h, 1);
+        const int border = (int)lrintf(smax * (float)S->L[i].sigma_size) + 1;
+        for (int y = border; y < h - border; ++y)
+            for (int x = border; x < w - border; ++x) {
+                const size_t c = (size_t)y * w + x;
+                const float v = D[c];
+                if (!(v > dthreshold && v > D[c - 1] && v > D[c + 1] && v > D[c - w - 1] && v > D[c - w] && v > D[c - w + 1] &&
+                      v > D[c + w - 1] && v > D[c + w] && v > D[c + w + 1])) continue;
+                int idx = 0;                                        /* same scale: the better of two close maxima stays (raster order) */
+                if (akz_find_neighbor(mask[i], w, h, x, y, S->L[i].sigma_size, &idx)) {
+                    if (v > D[idx]) mask[i][idx] = 0; else continue;
+                }
+                mask[i][c] = 1;
+            }
+    }
+    for (int i = 1; i < S->nl; ++i) {                               /* against the lower level */
+        const int w = S->L[i].w, h = S->L[i].h, wp = S->L[i - 1].w, hp = S->L[i - 1].h;
+        const int diff = (1 << S->L[i].octave) / (1 << S->L[i - 1].octave);
+        const int r = S->L[i].sigma_size * diff;
+        for (int y = 0; y < h; ++y)
+            for (int x = 0; x < w; ++x) {
+                if (!mask[i][(size_t)y * w + x]) continue;
+                int idx = 0;
+                if (akz_find_neighbor(mask[i - 1], wp, hp, x * diff, y * diff, r, &idx) && S->Ldet[i][(size_t)y * w + x] > S->Ldet[i - 1][idx])
+                    mask[i - 1][idx] = 0;
+            }
+    }
+    for (int i = S->nl - 2; i >= 0; --i) {                          /* against the upper level */
+        const int w = S->L[i].w, h = S->L[i].h, wn = S->L[i + 1].w, hn = S->L[i + 1].h;
+        const int diff = (1 << S->L[i + 1].octave) / (1 << S->L[i].octave);
+        const int r = S->L[i + 1].sigma_size;
+        for (int y = 0; y < h; ++y)
+            for (int x = 0; x < w; ++x) {
+                if (!mask[i][(size_t)y * w + x]) continue;
+                int idx = 0;
+                if (akz_find_neighbor(mask[i + 1], wn, hn, x / diff, y / diff, r, &idx) && S->Ldet[i][(size_t)y * w + x] > S->Ldet[i + 1][idx])
+                    mask[i + 1][idx] = 0;
+            }
+    }
+    for (int i = 0; i < S->nl; ++i) for (size_t c = 0; c < (size_t)S->L[i].w * S->L[i].h; ++c) total += mask[i][c];
+    akz_pt* K = (akz_pt*)malloc(sizeof(akz_pt) * (size_t)(total + 1));
+    int m = 0;
+    for (int i = 0; i < S->nl; ++i) {
+        const int w = S->L[i].w, h = S->L[i].h;
+        const float* D = S->Ldet[i];
+        const float ratio = (float)(1 << S->L[i].octave);
+        for (int y = 0; y < h; ++y)
+            for (int x = 0; x < w; ++x) {
+                const size_t c = (size_t)y * w + x;
+                if (!mask[i][c]) continue;
+                const float Dx = 0.5f * (D[c + 1] - D[c - 1]), Dy = 0.5f * (D[c + w] - D[c - w]);
+                const float Dxx = (D[c + 1] + D[c - 1]) - 2.0f * D[c], Dyy = (D[c + w] + D[c - w]) - 2.0f * D[c];
+                const float Dxy = 0.25f * (D[c + w + 1] + D[c - w - 1]) - 0.25f * (D[c - w + 1] + D[c + w - 1]);
+                const float det = Dxx * Dyy - Dxy * Dxy;
+                if (det == 0.f) continue;
+                const float ox = (Dxy * Dy - Dyy * Dx) / det, oy = (Dxy * Dx - Dxx * Dy) / det;
+                if (!(fabsf(ox) <= 1.0f && fabsf(oy) <= 1.0f)) continue;
+                akz_pt p;
+                p.x = ((float)x + ox) * ratio + 0.5f * (ratio - 1.0f);
+                p.y = ((float)y + oy) * ratio + 0.5f * (ratio - 1.0f);
+                p.size = S->L[i].esigma * 1.5f * 2.0f; p.response = D[c]; p.octave = S->L[i].octave; p.class_id = i;
+                K[m++] = p;
+            }
+        free(mask[i]);
+    }
+    *out = K;
+    return m;
+}
+static int g_akz_cv_mode = 0;
+void orc_akaze_set_cv2_filter(int on) { g_akz_cv_mode = on; }      /* test hook: selects the detection variant for orc_akaze_* */
+static int akz_detect_dispatch(const akz_space* S, float dthreshold, akz_pt** out) {
+    return g_akz_cv_mode ? akz_detect_cv(S, dthreshold, out) : akz_detect(S, dthreshold, out);
 }
 
 /* ---- descriptors (Compute_Main_Orientation + Get_MLDB_Full_Descriptor) ------------------------------------------- */
@@ -501,7 +608,7 @@ int orc_akaze_detect(const uint8_t* gray, int w, int h, int stride, int omax, in
     int rc = space_build(&S, gray, w, h, stride, omax, nsub);
     if (rc) return rc;
     akz_pt* K = NULL;
-    const int n = akz_detect(&S, dth, &K);
+    const int n = akz_detect_dispatch(&S, dth, &K);
     if (n <= cap) for (int i = 0; i < n; ++i) { out5[5 * i] = K[i].x; out5[5 * i + 1] = K[i].y; out5[5 * i + 2] = K[i].size; out5[5 * i + 3] = K[i].response; out5[5 * i + 4] = (float)K[i].class_id; }
     free(K); space_free(&S);
     return n <= cap ? n : -n;
@@ -515,7 +622,7 @@ int orc_akaze61_extract(const uint8_t* gray, int w, int h, int stride, int nfeat
     int rc = space_build(&S, gray, w, h, stride, nlevels / 4, nlevels / 2);
     if (rc) return rc;
     akz_pt* K = NULL;
-    const int n = akz_detect(&S, detect_th, &K);
+    const int n = akz_detect_dispatch(&S, detect_th, &K);
     if (n_detected) *n_detected = n;
     int q_ext[ORC_MAX_LEVELS];
     orc_features_per_level(nfeatures, nlevels, scale_factor, q_ext);

@@ -1,6 +1,7 @@
 """CPU tests of the akaze61 ORACLE (oracle/afv_oracle_akaze.c).  PARITY UNPINNED vs libAKAZE (not vendored by the
-reference); cv2.AKAZE (OpenCV's port of libAKAZE) stored by tools/make_golden_akaze.py is the family check: same Hessian
-maxima, same responses, nearly identical MLDB descriptors.  Plus the reference-side post-processing."""
+reference); cv2.AKAZE (OpenCV's port of libAKAZE) stored by tools/make_golden_akaze.py PINS the pipeline: with OpenCV's
+variant of the duplicate filter selected the keypoint lists are identical, and MLDB agrees bit for bit where the orientation
+searches agree.  Plus the reference-side post-processing."""
 import ctypes as C
 import os
 
@@ -43,6 +44,35 @@ def test_scale_space_structure(frame):
     assert lt3.var() < lt0.var()
 
 
+def test_pinned_to_cv2_with_opencv_duplicate_filter(frame, golden_dir):
+    """With OpenCV's variant of the duplicate filter selected, the oracle reproduces cv2.AKAZE's keypoint list exactly (count, order,
+    level, position, size, response): this pins the FED scale space, the Hessian, the maxima, the border rule (10 sqrt 2 * sigma_size)
+    and the sub-pixel refinement to the cv2 4.13.0 binary.  MLDB is pinned where the two orientation searches agree."""
+    g = np.load(os.path.join(golden_dir, "akaze_cv2_synth_640x480_s0_t0.npz"))
+    kp = g["kp"]
+    po.lib().orc_akaze_set_cv2_filter(1)
+    try:
+        det = po.akaze_detect(frame)
+        kps, desc, size, nd = po.akaze61_extract(frame, 20000)
+    finally:
+        po.lib().orc_akaze_set_cv2_filter(0)
+    assert len(det) == len(kp) == 1751
+    assert (det[:, 4] == kp[:, 6]).all()                                   # same evolution level, same ORDER
+    assert np.abs(det[:, :2] - kp[:, :2]).max() < 5e-4                     # sub-pixel positions
+    assert (det[:, 2] == kp[:, 2]).all()                                   # size
+    assert (np.abs(det[:, 3] - kp[:, 4]) / kp[:, 4]).max() < 1e-4          # Hessian response
+    from scipy.spatial import cKDTree
+    d2, i2 = cKDTree(kp[:, :2]).query(np.stack([kps["x"], kps["y"]], 1))
+    m = (d2 < 0.05) & (kp[i2, 6] == kps["class_id"])
+    assert m.sum() == len(kp)                                               # no octree at this quota: every keypoint is described
+    da = np.abs(((np.degrees(kps["angle"][m]) - kp[i2[m], 3]) + 180) % 360 - 180)
+    hd = np.unpackbits(desc[m] ^ g["desc"][i2[m]], axis=1).sum(1)
+    close = da < 1e-3                                                       # the two orientation searches agree
+    assert close.mean() > 0.4 and (hd[close] == 0).mean() > 0.98 and hd[close].max() <= 2
+    assert (hd[da < 1e-2] <= 4).all()
+    assert (da > 1.0).mean() < 0.15                                         # OpenCV's 42-slice search vs libAKAZE's exact-angle windows
+
+
 def test_family_check_against_cv2(frame, golden_dir):
     g = np.load(os.path.join(golden_dir, "akaze_cv2_synth_640x480_s0_t0.npz"))
     det = po.akaze_detect(frame)
@@ -50,7 +80,7 @@ def test_family_check_against_cv2(frame, golden_dir):
     tree = cKDTree(det[:, :2])
     d, i = tree.query(g["kp"][:, :2])
     same = (d < 0.05) & (det[i, 4] == g["kp"][:, 6])
-    assert same.mean() > 0.85                                  # cv2's keypoints, same sub-pixel position, same level
+    assert same.mean() > 0.995                                 # libAKAZE's filter keeps (at least) cv2's keypoints: same position, same level
     assert np.allclose(det[i[same], 2], g["kp"][same, 2], rtol=1e-6)                    # size
     rel = np.abs(det[i[same], 3] - g["kp"][same, 4]) / g["kp"][same, 4]
     assert np.median(rel) < 1e-5 and np.percentile(rel, 99) < 1e-3                     # Hessian response
