@@ -5,7 +5,7 @@
  * src/Feature_orb32.cpp:11-65, src/FeatureExtractor.cpp:97-172,276-308, src/ORBextractor.cc:181-458).
  * The numerics behind `cv::ORB::detect/compute` live in OpenCV (un-vendored, unpinned by the reference);
  * they are restated here from OpenCV's algorithm and pinned bit-for-bit to cv2 4.13.0
- * (tests/test_oracle_vs_cv2.py, tests/golden/).  Build with -ffp-contract=off: every float expression
+ * (tests/test_oracle_golden.py, tests/golden/).  Build with -ffp-contract=off: every float expression
  * below is meant to round after each operation (no FMA), which is what the pinned binary does.
  */
 #include "afv_oracle.h"

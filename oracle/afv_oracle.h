@@ -7,7 +7,7 @@
  *
  * Where the reference's arithmetic lives in un-vendored OpenCV (cv::ORB), the algorithm is restated from
  * OpenCV's published behaviour and PINNED against cv2 4.13.0 run in the build container
- * (tests/test_oracle_vs_cv2.py, golden fixtures in tests/golden/ made by tools/make_golden.py).
+ * (tests/test_oracle_golden.py, golden fixtures in tests/golden/ made by tools/make_golden.py).
  * Every function cites the reference file:line (relative to /root/reference) it follows.
  */
 #ifndef AFV_ORACLE_H
