@@ -373,101 +373,199 @@ extern "C" int afv_match_window(int desc_type, const void* d_q, const float* d_q
 // ---- windowed matcher batched over frame pairs (the throughput form of the SearchByProjection / GetFeaturesInArea core) ----
 // One CTA per pair: the train frame (positions, sizes, descriptors) and its prebuilt grid (afv_grid_build = the reference's
 // Frame::AssignFeaturesToGrid, done once per frame) are staged in shared memory with coalesced loads -- these loads ARE the
-// algorithmic HBM traffic of the pair -- then one THREAD per query walks its cell-column ranges in the reference's enumeration
-// order (cell x, cell y, index ascending), so "first minimum wins" needs no tie handling.  Small windows are HBM / latency bound
-// (a few candidates per query), large ones POPC bound (see bench.py --workload m1).  Measured alternatives that were SLOWER on
-// B200 (profiles/r02_matcher.md): enumerate -> flat candidate list -> uniform distance pass -> per-query reduce (2 - 3.5x slower:
-// double enumeration + block barriers), and 4 lanes per query over interleaved cell columns (1.0 - 1.3x slower: same number of
-// warp iterations, the longest column of a warp sets the pace).
-#define MWP_THREADS 512
-template <int NW>                               // descriptor words: 8 orb32, 12 brisk48, 16 akaze61 (61 bytes zero-padded)
-__global__ void __launch_bounds__(MWP_THREADS) k_match_window_pairs(int D, const afv_keypoint* __restrict__ kps, const uint8_t* __restrict__ desc,
+// algorithmic HBM traffic of the pair.  Then the WARP is the unit of work.  A warp takes 32 queries; the cell-column ranges of
+// their windows are walked slot-parallel, the candidates that pass the size and radius gates are pushed (query lane, CSR position)
+// into a per-warp shared-memory queue by ballot compaction, and the queue is drained one SLOT per lane: Hamming distance between
+// the staged train row and the query row (kept word-major in shared memory for the 32 queries of the batch), key = distance << 16 |
+// CSR position.  CSR positions ascend in the reference's enumeration order (cell x, cell y, index), so the smallest key is "first
+// minimum wins" and the second smallest key carries the multiset-second-smallest distance, whatever order the slots are evaluated in.
+// Only __syncwarp() after the staging barrier.
+//
+// What was measured on B200 before this form (10 240 pairs, r = 15 / 100 px; profiles/r02_summary.md):
+//   thread per query walking its cell columns, query in registers ........ 1.03 / 10.1 ms  (issue bound, 8 of 32 lanes: the window
+//                                                                                            populations of 32 neighbouring queries differ)
+//   + lane-per-query cursor feeding the queue, atomicMin top-2 ............ 0.87 / 10.5 ms  (25 walk iterations per batch at 13 lanes)
+//   + scan-based slot expansion of the walk ............................... 0.82 / 13.0 ms  (LSU data pipe 84 %: shared-memory wavefronts)
+//   + chunk-major descriptors read with LDS.128 ........................... 0.79 / 11.9 ms  (bank conflicts 80 M -> 68 M)
+//   + owner read-back of contiguous runs instead of atomics (this kernel) . 0.83 /  9.8 ms  (no pass 2; kept: never behind, no atomics)
+// and, in round 1: enumerate -> flat candidate list -> uniform distance pass -> per-query reduce with block barriers (2 - 3.5x slower),
+// 4 lanes per query over interleaved cell columns (1.0 - 1.3x slower), pairs grouped by train frame to stage it once per 8 pairs
+// (1.20 vs 1.10 ms: wave-quantisation tail; the staging overlaps with other CTAs' query loops anyway).  The kernel sits at 70 - 84 %
+// of the LSU data pipe: 15 - 18 k shared-memory wavefronts per pair (random 16-byte rows, queue traffic, shuffles) against 113 KB
+// = 0.9 k wavefronts of compulsory staging, which is why it stays near 0.2 of the HBM roofline.
+#define MWQ_QCAP 256
+#define MWQ_RUNS 8                                                                      // column steps whose runs can wait for one drain
+template <int NW, int THREADS>
+__global__ void __launch_bounds__(THREADS) k_match_window_pairs(int D, const afv_keypoint* __restrict__ kps, const uint8_t* __restrict__ desc,
         const float* __restrict__ kpsize, const int* __restrict__ n_arr, int cap, const int* __restrict__ cell_start,
         const int* __restrict__ cell_items, const int* __restrict__ pair_a, const int* __restrict__ pair_b,
         const float* __restrict__ qxy, const float* __restrict__ qr, float r_all, const float* __restrict__ qmin, const float* __restrict__ qmax,
         float minX, float minY, float invW, float invH, int* __restrict__ best, float* __restrict__ bestd, float* __restrict__ secondd) {
     extern __shared__ __align__(16) unsigned char sm[];
-    // word-major staged descriptors with a row stride of capp = cap rounded to 4 mod 32 words: the staging stores of 32 consecutive
-    // (row, word) items then hit 32 different banks (a stride of cap = 1024 put all 8 words of a row on ONE bank: 8-way conflicts).
-    // Measured and rejected: sorting the pairs by train frame and staging the frame once per group of 8 pairs (1.20 vs 1.10 ms at
-    // r = 15, 11.2 vs 9.85 ms at r = 100 per 10 240 pairs: 1 536 equal work items leave a 14 % wave-quantisation tail on 592 CTA slots,
-    // and the staging it saves overlaps with other CTAs' query loops anyway).
-    const int capp = ((cap + 31) & ~31) + 4;
-    uint32_t* sdesc = reinterpret_cast<uint32_t*>(sm);                                  // [NW][capp] word-major
-    float2* sxy = reinterpret_cast<float2*>(sdesc + (size_t)NW * capp);                 // [cap]
+    constexpr int WARPS = THREADS / 32;
+    constexpr int NC = NW / 4;                                                          // 16-byte chunks per descriptor
+    constexpr int WSCR = MWQ_QCAP + NW * 32 + MWQ_RUNS * 32;                            // words of scratch per warp
+    // train descriptors chunk-major: sdesc[c][row] is the c-th 16-byte quarter of row `row`.  A drain reads one row per lane with NC
+    // LDS.128; rows are random, and a quarter warp of 8 random 16-byte slots (bank group = row mod 8) collides far less often than
+    // 32 random 4-byte words did in the word-major layout of the thread-per-query kernel (28 -> 19 wavefronts per 32 descriptors).
+    uint4* sdesc = reinterpret_cast<uint4*>(sm);                                        // [NC][cap]
+    uint32_t* wscr = reinterpret_cast<uint32_t*>(sdesc + (size_t)NC * cap);             // [WARPS][WSCR]
+    float2* sxy = reinterpret_cast<float2*>(wscr + WARPS * WSCR);                       // [cap]
     float* ssz = reinterpret_cast<float*>(sxy + cap);                                   // [cap]
     unsigned short* scs = reinterpret_cast<unsigned short*>(ssz + cap);                 // [NCELLS + 1]
     unsigned short* sci = scs + ((NCELLS + 1 + 7) & ~7);                                // [cap]
-    const int p = blockIdx.x, tid = threadIdx.x;
+    const int p = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int fa = pair_a[p], fb = pair_b[p];
     const int n1 = min(n_arr[fa], cap), n2 = min(n_arr[fb], cap);
-    const afv_keypoint* k1 = kps + (long long)fa * cap; const afv_keypoint* k2 = kps + (long long)fb * cap;
+    const afv_keypoint* k1p = kps + (long long)fa * cap; const afv_keypoint* k2p = kps + (long long)fb * cap;
     const uint8_t* d1 = desc + (long long)fa * cap * D; const uint8_t* d2 = desc + (long long)fb * cap * D;
     const float* sz2 = kpsize + (long long)fb * cap;
     const int* cs = cell_start + (long long)fb * (NCELLS + 1); const int* ci = cell_items + (long long)fb * cap;
     // ---- stage the train frame
     if ((D & 15) == 0) {
-        const uint4* w2 = reinterpret_cast<const uint4*>(d2);                           // rows are D bytes: 16-byte aligned when D % 16 == 0
-        constexpr int NQ = NW / 4;
-        for (int i = tid; i < n2 * NQ; i += MWP_THREADS) {
-            const int r = i / NQ, w = (i - r * NQ) * 4;
-            const uint4 v = w2[i];
-            sdesc[(size_t)w * capp + r] = v.x; sdesc[(size_t)(w + 1) * capp + r] = v.y; sdesc[(size_t)(w + 2) * capp + r] = v.z; sdesc[(size_t)(w + 3) * capp + r] = v.w;
-        }
-    } else if ((D & 3) == 0) {
-        const uint32_t* w2 = reinterpret_cast<const uint32_t*>(d2);
-        for (int i = tid; i < n2 * NW; i += MWP_THREADS) { const int r = i / NW, w = i - r * NW; sdesc[(size_t)w * capp + r] = w2[i]; }
+        const uint4* w2 = reinterpret_cast<const uint4*>(d2);
+        for (int i = tid; i < n2 * NC; i += THREADS) { const int r = i / NC, c = i - r * NC; sdesc[(size_t)c * cap + r] = w2[i]; }
     } else {
-        for (int i = tid; i < n2 * NW; i += MWP_THREADS) {
-            const int r = i / NW, w = i - r * NW;
-            uint32_t v = 0;
-            for (int b = 0; b < 4; ++b) { const int o = w * 4 + b; if (o < D) v |= (uint32_t)d2[(long long)r * D + o] << (8 * b); }
-            sdesc[(size_t)w * capp + r] = v;
+        for (int i = tid; i < n2 * NC; i += THREADS) {
+            const int r = i / NC, c = i - r * NC;
+            uint32_t v[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                v[k] = 0;
+                if ((D & 3) == 0) { if (c * 16 + k * 4 < D) v[k] = *reinterpret_cast<const uint32_t*>(d2 + (long long)r * D + c * 16 + k * 4); }
+                else for (int b = 0; b < 4; ++b) { const int o = c * 16 + k * 4 + b; if (o < D) v[k] |= (uint32_t)d2[(long long)r * D + o] << (8 * b); }
+            }
+            sdesc[(size_t)c * cap + r] = make_uint4(v[0], v[1], v[2], v[3]);
         }
     }
-    for (int i = tid; i < n2; i += MWP_THREADS) { sxy[i] = make_float2(k2[i].x, k2[i].y); ssz[i] = sz2[i]; sci[i] = (unsigned short)ci[i]; }
-    for (int i = tid; i <= NCELLS; i += MWP_THREADS) scs[i] = (unsigned short)cs[i];
+    for (int i = tid; i < n2; i += THREADS) { sxy[i] = make_float2(k2p[i].x, k2p[i].y); ssz[i] = sz2[i]; sci[i] = (unsigned short)ci[i]; }
+    for (int i = tid; i <= NCELLS; i += THREADS) scs[i] = (unsigned short)cs[i];
     __syncthreads();
-    // ---- one thread per query
-    for (int qi = tid; qi < n1; qi += MWP_THREADS) {
+    // ---- one warp per batch of 32 queries
+    uint32_t* wq = wscr + warp * WSCR;                                                  // [MWQ_QCAP] queue: lane << 16 | CSR position, then lane << 27 | key
+    uint32_t* wsq = wq + MWQ_QCAP;                                                      // [NW][32] query descriptors of the batch
+    uint32_t* wrun = wsq + NW * 32;                                                     // [MWQ_RUNS][32] finished runs: start << 16 | count
+    const unsigned lt = (1u << lane) - 1u;
+    for (int qb = warp * 32; qb < n1; qb += WARPS * 32) {
+        const int qi = qb + lane;
+        const bool act = qi < n1;
         const long long qo = (long long)p * cap + qi;
-        const float x = qxy ? qxy[2 * qo] : k1[qi].x, y = qxy ? qxy[2 * qo + 1] : k1[qi].y;
-        const float r = qr ? qr[qo] : r_all;
-        const float smin = qmin ? qmin[qo] : -FLT_MAX, smax = qmax ? qmax[qo] : FLT_MAX;
-        uint32_t q[NW];
-        if ((D & 15) == 0) {
-            const uint4* row = reinterpret_cast<const uint4*>(d1 + (long long)qi * D);
+        float x = 0.0f, y = 0.0f, r = -1.0f, smin = -FLT_MAX, smax = FLT_MAX;
+        if (act) {
+            x = qxy ? qxy[2 * qo] : k1p[qi].x; y = qxy ? qxy[2 * qo + 1] : k1p[qi].y;
+            r = qr ? qr[qo] : r_all;
+            if (qmin) smin = qmin[qo];
+            if (qmax) smax = qmax[qo];
+            if ((D & 15) == 0) {
+                const uint4* row = reinterpret_cast<const uint4*>(d1 + (long long)qi * D);
 #pragma unroll
-            for (int w = 0; w < NW / 4; ++w) { const uint4 v = row[w]; q[4 * w] = v.x; q[4 * w + 1] = v.y; q[4 * w + 2] = v.z; q[4 * w + 3] = v.w; }
-        } else if ((D & 3) == 0) {
-            const uint32_t* row = reinterpret_cast<const uint32_t*>(d1 + (long long)qi * D);
+                for (int w = 0; w < NW / 4; ++w) { const uint4 v = row[w]; wsq[(4 * w) * 32 + lane] = v.x; wsq[(4 * w + 1) * 32 + lane] = v.y; wsq[(4 * w + 2) * 32 + lane] = v.z; wsq[(4 * w + 3) * 32 + lane] = v.w; }
+            } else if ((D & 3) == 0) {
+                const uint32_t* row = reinterpret_cast<const uint32_t*>(d1 + (long long)qi * D);
 #pragma unroll
-            for (int w = 0; w < NW; ++w) q[w] = row[w];
-        } else {
+                for (int w = 0; w < NW; ++w) wsq[w * 32 + lane] = row[w];
+            } else {
 #pragma unroll
-            for (int w = 0; w < NW; ++w) { uint32_t v = 0; for (int b = 0; b < 4; ++b) { const int o = w * 4 + b; if (o < D) v |= (uint32_t)d1[(long long)qi * D + o] << (8 * b); } q[w] = v; }
-        }
-        int bi = -1, b1 = 0x7fffffff, b2 = 0x7fffffff;
-        int c0, c1, r0, r1;
-        if (!(r < 0.0f) && window_cells(x, y, r, minX, minY, invW, invH, c0, c1, r0, r1)) {
-            for (int ix = c0; ix <= c1; ++ix) {
-                const int sb = scs[ix * AFV_GRID_ROWS + r0], se = scs[ix * AFV_GRID_ROWS + r1 + 1];
-                for (int j = sb; j < se; ++j) {
-                    const int idx = sci[j];
-                    const float sz = ssz[idx];
-                    if (sz < smin || sz > smax) continue;
-                    const float2 t = sxy[idx];
-                    if (!(fabsf(__fsub_rn(t.x, x)) < r && fabsf(__fsub_rn(t.y, y)) < r)) continue;
-                    int d = 0;
-#pragma unroll
-                    for (int w = 0; w < NW; ++w) d += __popc(q[w] ^ sdesc[(size_t)w * capp + idx]);
-                    if (d < b1) { b2 = b1; b1 = d; bi = idx; } else if (d < b2) b2 = d;
-                }
+                for (int w = 0; w < NW; ++w) { uint32_t v = 0; for (int b = 0; b < 4; ++b) { const int o = w * 4 + b; if (o < D) v |= (uint32_t)d1[(long long)qi * D + o] << (8 * b); } wsq[w * 32 + lane] = v; }
             }
         }
-        best[qo] = bi;
-        bestd[qo] = b1 == 0x7fffffff ? FLT_MAX : (float)b1;
-        secondd[qo] = b2 == 0x7fffffff ? FLT_MAX : (float)b2;
+        uint32_t k1 = 0xffffffffu, k2 = 0xffffffffu;
+        int c0 = 0, c1 = -1, r0 = 0, r1 = 0;
+        bool win = act && !(r < 0.0f) && window_cells(x, y, r, minX, minY, invW, invH, c0, c1, r0, r1);
+        if (win) {
+            // GetFeaturesInArea's floor / ceil cell range is up to two cells wider than the cells that can hold a point passing the
+            // |dx| < r, |dy| < r gate (PosInGrid rounds to the NEAREST cell).  Dropping those cells changes nothing in the result --
+            // CSR positions, hence keys, are the same -- and removes 40 % of the candidates walked at r = 15.  The 0.01-cell margin
+            // (0.1 px) is three orders above the rounding of the float gate and of the cell computation, both monotone in the coordinate.
+            const float gx = __fmul_rn(__fsub_rn(x, minX), invW), gy = __fmul_rn(__fsub_rn(y, minY), invH), rx = r * invW, ry = r * invH;
+            c0 = max(c0, (int)floorf(gx - rx + 0.49f)); c1 = min(c1, (int)floorf(gx + rx + 0.51f));
+            r0 = max(r0, (int)floorf(gy - ry + 0.49f)); r1 = min(r1, (int)floorf(gy + ry + 0.51f));
+            win = c0 <= c1 && r0 <= r1;
+        }
+        // walk: column step k takes the k-th cell column of every query of the batch; the 32 CSR ranges are laid end to end (warp scan
+        // of their lengths) and handed out one SLOT per lane, so the gate runs on full warps however unevenly the ranges are filled
+        // (a lane-per-query cursor ran 25 iterations per batch at 13 of 32 lanes: corners cluster across pyramid levels).  Slots that
+        // pass the gate are appended to the queue in slot order, so the pushes of one query form one contiguous RUN of the queue; the
+        // owner lane tracks (run_start, run_cnt) from the ballot alone.  drain: distances one queue slot per lane, then every owner
+        // reads its run back and folds the keys into its register top-2 -- no atomics, no second pass.
+        const int ncol = win ? c1 - c0 + 1 : 0, dr = r1 + 1 - r0;
+        const int maxcol = __reduce_max_sync(0xffffffffu, ncol);
+        const bool gate_sz = qmin != nullptr || qmax != nullptr;
+        int qn = 0, run_start = 0, run_cnt = 0, nrec = 0;
+        auto drain = [&]() {
+            __syncwarp();
+            for (int s = lane; s < qn; s += 32) {
+                const uint32_t e = wq[s];
+                const int ql = (int)(e >> 16), cj = (int)(e & 0xffffu), idx = sci[cj];
+                int d = 0;
+#pragma unroll
+                for (int c = 0; c < NC; ++c) {
+                    const uint4 tv = sdesc[(size_t)c * cap + idx];
+                    d += __popc(wsq[(4 * c) * 32 + ql] ^ tv.x) + __popc(wsq[(4 * c + 1) * 32 + ql] ^ tv.y) +
+                         __popc(wsq[(4 * c + 2) * 32 + ql] ^ tv.z) + __popc(wsq[(4 * c + 3) * 32 + ql] ^ tv.w);
+                }
+                wq[s] = ((uint32_t)d << 16) | (uint32_t)cj;
+            }
+            __syncwarp();
+            for (int rec = 0; rec <= nrec; ++rec) {                                     // finished runs of earlier column steps, then the open one
+                const uint32_t rv = rec < nrec ? wrun[rec * 32 + lane] : (((uint32_t)run_start << 16) | (uint32_t)run_cnt);
+                const int rs = (int)(rv >> 16), rc = (int)(rv & 0xffffu);
+                for (int i = 0; i < rc; ++i) {
+                    const uint32_t key = wq[rs + i];
+                    if (key < k1) { k2 = k1; k1 = key; } else if (key < k2) k2 = key;
+                }
+            }
+            run_cnt = 0; qn = 0; nrec = 0;
+            __syncwarp();
+        };
+        __syncwarp();
+        for (int k = 0; k < maxcol; ++k) {
+            int j0 = 0, len = 0;
+            if (k < ncol) { const int cp = (c0 + k) * AFV_GRID_ROWS + r0; j0 = scs[cp]; len = (int)scs[cp + dr] - j0; }
+            int incl = len;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+            const int T = __shfl_sync(0xffffffffu, incl, 31);
+            const int excl = incl - len, base = j0 - excl;                              // slot t of this lane's range is CSR position base + t
+            for (int t0 = 0; t0 < T; t0 += 32) {
+                const int t = t0 + lane;
+                int lo = 0;                                                             // owner = first lane whose inclusive sum exceeds t
+#pragma unroll
+                for (int step = 16; step; step >>= 1) { const int v = __shfl_sync(0xffffffffu, incl, lo + step - 1); if (v <= t) lo += step; }
+                const int j = __shfl_sync(0xffffffffu, base, lo) + t;
+                const float ox = __shfl_sync(0xffffffffu, x, lo), oy = __shfl_sync(0xffffffffu, y, lo);
+                const float orr = qr ? __shfl_sync(0xffffffffu, r, lo) : r_all;
+                float omin = -FLT_MAX, omax = FLT_MAX;
+                if (gate_sz) { omin = __shfl_sync(0xffffffffu, smin, lo); omax = __shfl_sync(0xffffffffu, smax, lo); }
+                bool push = false;
+                if (t < T) {
+                    const int idx = sci[j];
+                    const float2 tp = sxy[idx];
+                    push = fabsf(__fsub_rn(tp.x, ox)) < orr && fabsf(__fsub_rn(tp.y, oy)) < orr;
+                    if (gate_sz && push) { const float sz = ssz[idx]; push = !(sz < omin || sz > omax); }
+                }
+                const unsigned pm = __ballot_sync(0xffffffffu, push);
+                if (push) wq[qn + __popc(pm & lt)] = ((uint32_t)lo << 16) | (uint32_t)j;
+                {                                                                       // this lane as an OWNER: its slots of the pass are lanes [a, b)
+                    const int a = min(max(excl - t0, 0), 32), b = min(max(incl - t0, 0), 32);
+                    const unsigned below_a = a >= 32 ? 0xffffffffu : ((1u << a) - 1u), below_b = b >= 32 ? 0xffffffffu : ((1u << b) - 1u);
+                    if (run_cnt == 0) run_start = qn + __popc(pm & below_a);
+                    run_cnt += __popc(pm & below_b & ~below_a);
+                }
+                qn += __popc(pm);
+                if (qn > MWQ_QCAP - 32) drain();
+            }
+            // end of the column step: park this lane's run; drain when the queue or the run table is nearly full, or at the end
+            // (nrec is per lane: only non-empty runs are parked, so the read-back loops over the steps that DID push for this query)
+            if (k == maxcol - 1 || qn > MWQ_QCAP - 64 || __any_sync(0xffffffffu, nrec == MWQ_RUNS - 1)) { if (qn > 0) drain(); }
+            else if (run_cnt > 0) { wrun[nrec * 32 + lane] = ((uint32_t)run_start << 16) | (uint32_t)run_cnt; ++nrec; run_cnt = 0; }
+        }
+        if (act) {
+            best[qo] = k1 == 0xffffffffu ? -1 : (int)sci[k1 & 0xffffu];
+            bestd[qo] = k1 == 0xffffffffu ? FLT_MAX : (float)(k1 >> 16);
+            secondd[qo] = k2 == 0xffffffffu ? FLT_MAX : (float)(k2 >> 16);
+        }
+        __syncwarp();                                                                   // wsq is rewritten by the next batch
     }
 }
 
@@ -479,17 +577,22 @@ extern "C" int afv_match_window_pairs(int desc_type, const afv_keypoint* d_kps, 
     if (D < 0 || desc_type == AFV_FEAT_SIFT128 || !d_kps || !d_desc || !d_kpsize || !d_n || !d_cell_start || !d_cell_items || !d_pair_a || !d_pair_b ||
         !d_best || !d_bestd || !d_secondd || B < 1 || P < 0 || cap < 1 || cap >= 65535) { afv_set_error("afv_match_window_pairs: bad argument (binary descriptors only)"); return AFV_ERR_INVALID; }
     if (P == 0) return AFV_OK;
-    const int NW = (D + 3) / 4;
-    const int capp = ((cap + 31) & ~31) + 4;
-    const size_t smem = (size_t)NW * capp * 4 + (size_t)cap * (8 + 4 + 2) + (size_t)((NCELLS + 1 + 7) & ~7) * 2 + 16;
-    if (smem > 220 * 1024) { afv_set_error("afv_match_window_pairs: cap %d too large for the shared-memory staging", cap); return AFV_ERR_INVALID; }
+    const int NW = (((D + 3) / 4) + 3) & ~3;                                           // descriptor words, whole 16-byte chunks (8 / 12 / 16)
+    const size_t smem_frame = (size_t)NW * cap * 4 + (size_t)cap * (8 + 4 + 2) + (size_t)((NCELLS + 1 + 7) & ~7) * 2 + 16;
+    const size_t scratch_warp = (size_t)(MWQ_QCAP + NW * 32 + MWQ_RUNS * 32) * 4;
+    const size_t smem_limit = 227 * 1024;                                               // dynamic shared memory per CTA on sm_100
+    // 16 warps per CTA when the frame leaves room for their queues, else 8
+    const int threads = smem_frame + 16 * scratch_warp <= smem_limit ? 512 : 256;
+    const size_t smem = smem_frame + (size_t)(threads / 32) * scratch_warp;
+    if (smem > smem_limit) { afv_set_error("afv_match_window_pairs: cap %d too large for the shared-memory staging", cap); return AFV_ERR_INVALID; }
     cudaStream_t st = as_stream(cuda_stream);
     const float invW = (float)AFV_GRID_COLS / (max_x - min_x), invH = (float)AFV_GRID_ROWS / (max_y - min_y);
     AfvProfScope ps("k_match_window_pairs", st);
-#define MWP_LAUNCH(W) do { AFV_CUDA_CHECK(cudaFuncSetAttribute(k_match_window_pairs<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        k_match_window_pairs<W><<<P, MWP_THREADS, smem, st>>>(D, d_kps, (const uint8_t*)d_desc, d_kpsize, d_n, cap, d_cell_start, d_cell_items, d_pair_a, d_pair_b, \
+#define MWP_LAUNCH(W, T) do { AFV_CUDA_CHECK(cudaFuncSetAttribute(k_match_window_pairs<W, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        k_match_window_pairs<W, T><<<P, T, smem, st>>>(D, d_kps, (const uint8_t*)d_desc, d_kpsize, d_n, cap, d_cell_start, d_cell_items, d_pair_a, d_pair_b, \
             d_qxy, d_qr, radius, d_qmin_size, d_qmax_size, min_x, min_y, invW, invH, d_best, d_bestd, d_secondd); } while (0)
-    if (NW == 8) MWP_LAUNCH(8); else if (NW == 12) MWP_LAUNCH(12); else MWP_LAUNCH(16);
+    if (threads == 512) { if (NW == 8) MWP_LAUNCH(8, 512); else if (NW == 12) MWP_LAUNCH(12, 512); else MWP_LAUNCH(16, 512); }
+    else                { if (NW == 8) MWP_LAUNCH(8, 256); else if (NW == 12) MWP_LAUNCH(12, 256); else MWP_LAUNCH(16, 256); }
 #undef MWP_LAUNCH
     ++g_afv_launches;
     AFV_CUDA_CHECK(cudaGetLastError());

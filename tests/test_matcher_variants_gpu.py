@@ -219,6 +219,53 @@ def test_match_window_pairs(pkg, extracted, radius, gated):
         assert (rb >= 0).sum() > 100
 
 
+@pytest.mark.parametrize("feat,cap,n", [("akaze61", 1200, 1100), ("orb32", 4000, 3500), ("brisk48", 3000, 2000), ("akaze61", 2300, 900)])
+def test_match_window_pairs_synthetic(pkg, feat, cap, n):
+    """The same kernel on made-up frames: 61-byte descriptor rows (akaze61, byte staging path), capacities where the train frame
+    only fits next to 8 warps' queues (256-thread launch), and keypoints piled into a few cells so that one column step overflows
+    the per-warp queue (drain in the middle of a step) and many candidates tie on distance (first minimum in enumeration order)."""
+    import torch
+    st = pkg.FEATURE_SETTINGS[feat]
+    dt = st["feature_id"]; D = {"orb32": 32, "brisk48": 48, "akaze61": 61}[feat]
+    rng = np.random.default_rng(cap + n)
+    B = 3
+    kps = np.zeros((B, cap), pkg.KP_DTYPE); desc = np.zeros((B, cap, D), np.uint8); size = np.zeros((B, cap), np.float32)
+    nn = np.array([n, n - 37, n // 2], np.int32)
+    protos = rng.integers(0, 256, (6, D), dtype=np.uint8)
+    for f in range(B):
+        m = int(nn[f])
+        xy = rng.uniform([2, 2], [638, 478], (m, 2)).astype(np.float32)
+        k = m // 3                                              # a third of the points in three 25-px blobs
+        xy[:k] = (np.array([[100, 100], [320, 240], [600, 40]], np.float32)[rng.integers(0, 3, k)] + rng.uniform(-12, 12, (k, 2))).astype(np.float32)
+        xy[k:k + k // 2] = np.round(xy[k:k + k // 2])          # integer coordinates: points exactly on cell and window borders
+        kps[f, :m]["x"] = xy[:, 0]; kps[f, :m]["y"] = xy[:, 1]
+        size[f, :m] = rng.choice([31.0, 37.2, 44.64], m).astype(np.float32); kps[f, :m]["size"] = size[f, :m]
+        d = protos[rng.integers(0, 6, m)].copy()                # few prototypes with a few flipped bits: plenty of equal distances
+        flips = rng.integers(0, D * 8, (m, 3))
+        for j in range(3):
+            d[np.arange(m), flips[:, j] // 8] ^= (1 << (flips[:, j] % 8)).astype(np.uint8)
+        desc[f, :m] = d
+    dk = _t(kps.view(np.uint8).reshape(B, cap, 28).view(np.float32).reshape(B, cap, 7)); dd = _t(desc); ds = _t(size); dn = _t(nn)
+    fm = pkg.FeatureMatcher(desc_type=dt, th_low=float(st["matching_th"]))
+    cs, ci = fm.grid_build(dk, dn, BOUNDS)
+    pairs = [(0, 1), (1, 0), (2, 1), (1, 2), (0, 0)]
+    pa = _t(np.array([p[0] for p in pairs], np.int32)); pb = _t(np.array([p[1] for p in pairs], np.int32))
+    FMAX = np.finfo(np.float32).max
+    for radius in (20.0, 90.0):
+        best, bd, sd = fm.match_window_pairs(dk, dd, ds, dn, cs, ci, pa, pb, BOUNDS, radius=radius)
+        torch.cuda.synchronize()
+        best = best.cpu().numpy(); bd = bd.cpu().numpy(); sd = sd.cpu().numpy()
+        ties = 0
+        for i, (a, b) in enumerate(pairs):
+            na, nb = int(nn[a]), int(nn[b])
+            xy = np.stack([kps[a, :na]["x"], kps[a, :na]["y"]], axis=1).astype(np.float32)
+            rb, rbd, rsd, _, _ = po.match_window(dt, desc[a, :na], xy, np.full(na, radius, np.float32), np.full(na, -FMAX, np.float32),
+                                                 np.full(na, FMAX, np.float32), kps[b, :nb], desc[b, :nb], size[b, :nb], BOUNDS)
+            assert (best[i, :na] == rb).all() and (bd[i, :na] == rbd).all() and (sd[i, :na] == rsd).all(), "r=%g pair %d" % (radius, i)
+            ties += int(((rbd == rsd) & (rb >= 0)).sum())
+        assert ties > 100                                          # best == second distance occurs: the enumeration-order rule is exercised
+
+
 def test_match_bruteforce_pairs(pkg, extracted):
     import torch
     out, host, cap, dt, th, tol = extracted
