@@ -85,7 +85,12 @@ __device__ __forceinline__ int grid_cell(float x, float y, float minX, float min
     if (px < 0 || px >= AFV_GRID_COLS || py < 0 || py >= AFV_GRID_ROWS) return -1;
     return px * AFV_GRID_ROWS + py;
 }
-// Frame::GetFeaturesInArea cell range (src/Frame.cc:339-353). Returns false when the window misses the grid.
+// Frame::GetFeaturesInArea cell range (src/Frame.cc:339-353), trimmed.  Returns false when the window misses the grid.
+// The reference's floor / ceil range is up to two cells wider per axis than the cells that can hold a point passing its own
+// |dx| < r, |dy| < r gate, because PosInGrid rounds to the NEAREST cell.  Every search here applies that gate, so the outer cells
+// contribute nothing: dropping them leaves the enumeration order of the surviving candidates, hence every result, unchanged and
+// removes 40 % of the candidates walked at r = 15 (10 % at r = 100).  The 0.01-cell margin (0.1 px) is three orders above the
+// rounding of the float gate and of the cell computation, both monotone in the coordinate.
 __device__ __forceinline__ bool window_cells(float x, float y, float r, float minX, float minY, float invW, float invH,
                                              int& c0, int& c1, int& r0, int& r1) {
     c0 = max(0, (int)floorf(__fmul_rn(__fsub_rn(__fsub_rn(x, minX), r), invW)));
@@ -96,7 +101,10 @@ __device__ __forceinline__ bool window_cells(float x, float y, float r, float mi
     if (r0 >= AFV_GRID_ROWS) return false;
     r1 = min(AFV_GRID_ROWS - 1, (int)ceilf(__fmul_rn(__fadd_rn(__fsub_rn(y, minY), r), invH)));
     if (r1 < 0) return false;
-    return true;
+    const float gx = __fmul_rn(__fsub_rn(x, minX), invW), gy = __fmul_rn(__fsub_rn(y, minY), invH), rx = r * invW, ry = r * invH;
+    c0 = max(c0, (int)floorf(gx - rx + 0.49f)); c1 = min(c1, (int)floorf(gx + rx + 0.51f));
+    r0 = max(r0, (int)floorf(gy - ry + 0.49f)); r1 = min(r1, (int)floorf(gy + ry + 0.51f));
+    return c0 <= c1 && r0 <= r1;
 }
 
 // One CTA per frame: CSR grid with items ascending inside each cell (== push_back order of the reference).
@@ -471,17 +479,7 @@ __global__ void __launch_bounds__(THREADS) k_match_window_pairs(int D, const afv
         }
         uint32_t k1 = 0xffffffffu, k2 = 0xffffffffu;
         int c0 = 0, c1 = -1, r0 = 0, r1 = 0;
-        bool win = act && !(r < 0.0f) && window_cells(x, y, r, minX, minY, invW, invH, c0, c1, r0, r1);
-        if (win) {
-            // GetFeaturesInArea's floor / ceil cell range is up to two cells wider than the cells that can hold a point passing the
-            // |dx| < r, |dy| < r gate (PosInGrid rounds to the NEAREST cell).  Dropping those cells changes nothing in the result --
-            // CSR positions, hence keys, are the same -- and removes 40 % of the candidates walked at r = 15.  The 0.01-cell margin
-            // (0.1 px) is three orders above the rounding of the float gate and of the cell computation, both monotone in the coordinate.
-            const float gx = __fmul_rn(__fsub_rn(x, minX), invW), gy = __fmul_rn(__fsub_rn(y, minY), invH), rx = r * invW, ry = r * invH;
-            c0 = max(c0, (int)floorf(gx - rx + 0.49f)); c1 = min(c1, (int)floorf(gx + rx + 0.51f));
-            r0 = max(r0, (int)floorf(gy - ry + 0.49f)); r1 = min(r1, (int)floorf(gy + ry + 0.51f));
-            win = c0 <= c1 && r0 <= r1;
-        }
+        const bool win = act && !(r < 0.0f) && window_cells(x, y, r, minX, minY, invW, invH, c0, c1, r0, r1);
         // walk: column step k takes the k-th cell column of every query of the batch; the 32 CSR ranges are laid end to end (warp scan
         // of their lengths) and handed out one SLOT per lane, so the gate runs on full warps however unevenly the ranges are filled
         // (a lane-per-query cursor ran 25 iterations per batch at 13 of 32 lanes: corners cluster across pyramid levels).  Slots that

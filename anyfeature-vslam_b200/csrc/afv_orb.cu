@@ -41,7 +41,9 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t phase) {
     }
 }
 
-static __constant__ __align__(16) int8_t c_pattern[1024] = {
+// Global, not __constant__: the 256 threads of a CTA read 256 different words of it, which the constant cache serialises
+// (7 % of k_describe's stall samples sat on that conversion); as a coalesced LDG.32 per thread it is one L2-resident KB.
+static __device__ __align__(16) int8_t g_pattern[1024] = {
 #include "orb_pattern.inc"
 };
 
@@ -722,34 +724,39 @@ __device__ __forceinline__ float fast_atan2_deg(float y, float x) {
     return a;
 }
 
-__global__ void __launch_bounds__(256, 6) k_describe(const __grid_constant__ AfvParams P, afv_keypoint* __restrict__ kps,
+// 4 CTAs (32 warps) per SM at 64 registers: measured 0.635 ms / 512 frames against 0.652 at 5 CTAs / 48 registers and 0.678 at 6 / 40
+// (spills); the kernel is bound by instruction issue, not by latency (prefetching the next keypoint's rows made it slower).
+__global__ void __launch_bounds__(256, 4) k_describe(const __grid_constant__ AfvParams P, afv_keypoint* __restrict__ kps,
                                                   uint8_t* __restrict__ desc, float* __restrict__ kpsize,
                                                   int* __restrict__ n_out) {
     __shared__ float2 patf[8][2][32];        // patf[k][j][lane] = point j (x, y) of test k of descriptor byte `lane`, as floats
+    __shared__ uint32_t spatch[8][372];      // per warp: 37 rows x 40 bytes of the blurred level around the keypoint
     __shared__ int lvl_start[AFV_MAX_LEVELS + 1];
     const int f = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    {   // the int8 -> float conversion of the 512 pattern points is done once per CTA, not once per tap (6 % of the kernel)
-        const int pl = tid & 31, pk = tid >> 5;
-        const uint32_t pw = *reinterpret_cast<const uint32_t*>(&c_pattern[pl * 32 + pk * 4]);
+    {   // the int8 -> float conversion of the 512 pattern points is done once per CTA, not once per tap (6 % of the kernel):
+        // thread t converts test t = bit (t & 7) of descriptor byte (t >> 3)
+        const int pl = tid >> 3, pk = tid & 7;
+        const uint32_t pw = reinterpret_cast<const uint32_t*>(g_pattern)[tid];
         patf[pk][0][pl] = make_float2((float)(int)(int8_t)pw, (float)(int)(int8_t)(pw >> 8));
         patf[pk][1][pl] = make_float2((float)(int)(int8_t)(pw >> 16), (float)(int)(int8_t)(pw >> 24));
     }
-    if (tid == 0) {
-        int acc = 0;
-        for (int l = 0; l < P.nlevels; ++l) {
-            lvl_start[l] = acc;
-            acc += min(P.counts[afv_cnt_idx(f, AFV_CNT_KEEP, l)], P.lv[l].keep_cap);
-        }
-        lvl_start[P.nlevels] = acc;
-        if (blockIdx.x == 0) {
-            if (acc > P.out_cap) atomicOr(&P.status[f], AFV_ST_OUT_OVERFLOW);
-            n_out[f] = min(acc, P.out_cap);
+    if (warp == 0) {                         // level offsets of the merged output: one count per lane, warp scan (was a serial loop of loads)
+        const int c = lane < P.nlevels ? min(P.counts[afv_cnt_idx(f, AFV_CNT_KEEP, lane)], P.lv[lane].keep_cap) : 0;
+        int incl = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+        if (lane <= P.nlevels) lvl_start[lane] = incl - c;       // lane == nlevels holds the total (its own count is 0)
+        if (blockIdx.x == 0 && lane == 31) {
+            if (incl > P.out_cap) atomicOr(&P.status[f], AFV_ST_OUT_OVERFLOW);
+            n_out[f] = min(incl, P.out_cap);
         }
     }
     __syncthreads();
     const int total = min(lvl_start[P.nlevels], P.out_cap);
-    const int i = blockIdx.x * 8 + warp;
-    if (i >= total) return;
+    // 32 keypoints per CTA, 4 per warp: the prologue above and its barrier were 20 % of the stall samples at 8 keypoints per CTA
+    for (int it = 0; it < 4; ++it) {
+    const int i = blockIdx.x * 32 + it * 8 + warp;
+    if (i >= total) break;
     int l = 0;
     while (i >= lvl_start[l + 1]) ++l;
     const AfvLevel& L = P.lv[l];
@@ -799,8 +806,27 @@ __global__ void __launch_bounds__(256, 6) k_describe(const __grid_constant__ Afv
     const bool dinner = (cx >= 19 && cy >= 19 && cx + 19 < L.w && cy + 19 < L.h);
     uint32_t byte = 0;
     if (dinner) {                            // warp-uniform: every tap lies inside the blurred level (rotated pattern radius < 19)
-        const uint8_t* ctr = blr + (long long)cy * L.stride + cx;
+        // The 512 taps of a keypoint are scattered over a 37 x 37 patch: as global byte loads each of the 16 warp-wide gathers touches
+        // ~20 sectors and the kernel sat at 73 % of the L1 data pipe (ncu r02A).  The patch is copied once -- 37 rows x 10 aligned
+        // words, 12 coalesced LDG.32 -- into this warp's shared-memory tile and the gathers become LDS.U8.
+        uint32_t* sp = spatch[warp];
+        const uint8_t* org = blr + (long long)(cy - 18) * L.stride + (cx - 18);
+        const int shift = (int)((uintptr_t)org & 3);             // rows share it: the level stride is a multiple of 128
+        const uint8_t* al = org - shift;
         const int stride = L.stride;
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {                   // 6 loads in flight at a time
+            uint32_t wv[6];
+#pragma unroll
+            for (int it2 = 0; it2 < 6; ++it2) {
+                const int item = (half * 6 + it2) * 32 + lane, row = item / 10, col = item - row * 10;
+                wv[it2] = item < 370 ? *reinterpret_cast<const uint32_t*>(al + row * stride + col * 4) : 0u;
+            }
+#pragma unroll
+            for (int it2 = 0; it2 < 6; ++it2) { const int item = (half * 6 + it2) * 32 + lane; if (item < 370) sp[item] = wv[it2]; }
+        }
+        __syncwarp();
+        const uint8_t* ctr = reinterpret_cast<const uint8_t*>(sp) + 18 * 40 + 18 + shift;
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
             int tv[2];
@@ -809,7 +835,7 @@ __global__ void __launch_bounds__(256, 6) k_describe(const __grid_constant__ Afv
                 const float2 pt = patf[k][j][lane];
                 const int dx = __float2int_rn(__fsub_rn(__fmul_rn(pt.x, a), __fmul_rn(pt.y, b)));
                 const int dy = __float2int_rn(__fadd_rn(__fmul_rn(pt.x, b), __fmul_rn(pt.y, a)));
-                tv[j] = ctr[dy * stride + dx];
+                tv[j] = ctr[dy * 40 + dx];
             }
             byte |= (uint32_t)(tv[0] < tv[1]) << k;
         }
@@ -836,6 +862,8 @@ __global__ void __launch_bounds__(256, 6) k_describe(const __grid_constant__ Afv
         kp.response = __uint_as_float(kd.y); kp.octave = l; kp.class_id = -1;
         kps[o] = kp;
         if (kpsize) kpsize[o] = L.size_norm;
+    }
+    __syncwarp();                            // spatch is rewritten by the next keypoint
     }
 }
 
@@ -927,6 +955,6 @@ int afv_launch_extract(const AfvParams& P, afv_keypoint* d_kps, uint8_t* d_desc,
     { AfvProfScope ps("k_blur", st); k_blur<<<dim3(acc, P.B), 256, 0, st>>>(P, TMB); ++g_afv_launches; }
     cudaStreamWaitEvent(st, aux.ev_blur, 0);
     { AfvProfScope ps("k_describe", st);
-      k_describe<<<dim3((P.out_cap + 7) / 8, P.B), 256, 0, st>>>(P, d_kps, d_desc, d_kpsize, d_n_out); ++g_afv_launches; }
+      k_describe<<<dim3((P.out_cap + 31) / 32, P.B), 256, 0, st>>>(P, d_kps, d_desc, d_kpsize, d_n_out); ++g_afv_launches; }
     return AFV_OK;
 }
