@@ -17,16 +17,17 @@ def ncu_table(rep, units):
     return subprocess.run([sys.executable, "tools/ncu_summary.py", rep, str(units)], capture_output=True, text=True).stdout
 
 
-c2 = last("profiles/r02A_bench_c2_n1.json"); m1 = last("profiles/r02A_bench_m1.json")
+c2 = last("profiles/r02F_bench_c2_n1.json"); m1 = last("profiles/r02F_bench_m1.json")
 ns = {n: last("profiles/r02A_bench_c2_n%d.json" % n) for n in (1, 2, 4, 8)}
-c3 = last("profiles/r02t_bench_c3_n1.json"); c4 = last("profiles/r02D_bench_c4_n1.json"); c5 = last("profiles/r02A_bench_c5_n1.json")
+c3 = last("profiles/r02t_bench_c3_n1.json"); c4 = last("profiles/r02D_bench_c4_n1.json"); c5 = last("profiles/r02F_bench_c5_n1.json")
 ref = last("profiles/r02A_bench_reference_arm.json"); rp = last("profiles/r02A_bench_reference_real_parts.json"); cv = last("profiles/r02A_bench_c2v_n1.json")
 k = c2["roofline"]["kernel_ms_per_step"]
 out = []
 A = out.append
 A("# Round 2 profile summary (B200, sm_100a; all numbers from `gpurun` boxes, clocks 1965 / 1965 MHz, no throttle reason)\n")
-A("Raw artefacts in this directory: `r02A_bench_c2_n{1,2,4,8}.json` (the default line incl. its `c5` block at 1 / 2 / 4 / 8 GPUs, final tree),")
-A("`r02A_bench_{c5_n1,c2v_n1,m1}.json`, `r02t_bench_c3_n1.json`, `r02D_bench_c4_n1.json`, `r02A_bench_reference_arm.json`, `r02A_bench_reference_real_parts.json`, ncu launch lists")
+A("Raw artefacts in this directory: `r02F_bench_{c2_n1,m1,c5_n1}.json` (final tree: default line, matcher workload, c5 workload), `r02A_bench_c2_n{1,2,4,8}.json` (the default line incl. its `c5`")
+A("block at 1 / 2 / 4 / 8 GPUs, the tree before the last k_describe / windowed-matcher changes: the scaling table below),")
+A("`r02A_bench_{c2v_n1}.json`, `r02t_bench_c3_n1.json`, `r02D_bench_c4_n1.json`, `r02A_bench_reference_arm.json`, `r02A_bench_reference_real_parts.json`, ncu launch lists")
 A("`r02A_launches_c2_batch512.csv` / `r02A_launches_c2v_batch512.csv` (`--metrics gpu__time_duration.sum --clock-control none`).  The `.ncu-rep` files")
 A("(`--set full --import-source on`, 23-34 MB each) stay in `gpurun_out/`; the tables below are `tools/ncu_summary.py` / `tools/ncu_lines.py` read-outs of them")
 A("(regenerate this file with `tools/make_r02_summary.py`).\n")
@@ -44,7 +45,7 @@ why = {"k_resize": "128x32 tiles (prologue amortised over 16 px per thread)",
        "k_harris_select": "9-byte Harris rows from three aligned 32-bit loads + funnel shifts (44 % of the stall samples sat on the byte loads); parallel suffix scans",
        "k_octree": "keys as packed level coordinates scaled on the fly: 11 instead of 19 bytes of shared memory per key, 5 instead of 3 CTAs per SM",
        "k_blur": "REFLECT_101 patch taken from the staged tile (22 % of the instructions were the per-row global patch loop that >50 % of the tiles ran)",
-       "k_describe": "float pattern table in shared memory, branch-free inner tap path, sincos, 6 CTAs per SM",
+       "k_describe": "float pattern table in shared memory, branch-free inner tap path, sincos; 37x37 blurred patch staged per warp in shared memory (taps as LDS.U8, the 16 global gathers per keypoint held the L1 data pipe at 73 %), pattern read from global instead of the constant cache, 32 keypoints per CTA, 4 CTAs per SM at 64 registers",
        "k_sfi_lists": "in-window slots buffered per warp, distances with 32 of 32 lanes (was 11), word count unrolled",
        "k_sfi_resolve": "32-bit compact keys + redux.sync for the sorted-prefix phase"}
 A("| kernel | r1 | r2 | what changed |\n|---|---|---|---|")
@@ -56,26 +57,33 @@ A("ALU 74 %%, issue 77 %%, DRAM 6 %%), not HBM bound; whole step %.0f GB/s algor
 A("### ncu `--set full`, batch 128, final kernels (per launch; `instr / unit` = warp instructions per frame)\n")
 A(ncu_table("gpurun_out/r02A_orb.ncu-rep", 128))
 A("\nShares of the serialised launch list at batch 512 (`r02A_launches_c2_batch512.csv`) follow the same ranking as the event times above.\n")
-A("Measured and rejected this round (kept out of the tree, recorded in the kernel comments): a per-warp candidate QUEUE for the windowed matcher (1.31 vs 1.10 ms at r = 15,")
-A("10.6 vs 9.85 ms at r = 100); a per-lane `while (mask)` survivor writer in k_fast (1.17 vs 1.13 ms although it issues fewer instructions: the kernel is bound by the ALU")
-A("pipe, not by issue slots); `__launch_bounds__(256, 4)` on k_harris_select (0.47 vs 0.44 ms, spills); running the selection kernels on a high-priority side stream beside")
-A("k_blur (no overlap: three selection CTAs hold 57 k of the 64 k registers of an SM, so no blur CTA fits next to them).\n")
+A("Measured and rejected this round (kept out of the tree, recorded in the kernel comments): a per-lane `while (mask)` survivor writer in k_fast (1.17 vs 1.13 ms although it issues")
+A("fewer instructions: the kernel is bound by the ALU pipe, not by issue slots); `__launch_bounds__(256, 4)` on k_harris_select (0.47 vs 0.44 ms, spills) and prefetching the next candidate's")
+A("Harris rows into L1 (0.375 vs 0.338 ms); prefetching the next keypoint's rows in k_describe (0.654 vs 0.635 ms: the kernel is issue bound); running the selection kernels on a")
+A("high-priority side stream beside k_blur (no overlap: three selection CTAs hold 57 k of the 64 k registers of an SM, so no blur CTA fits next to them).  `tools/ncu_stalls.py` (stall")
+A("samples per source line) is what pointed at k_describe's prologue and constant-cache reads.\n")
 A("## 2. Matcher against its own rooflines (`bench.py --workload m1`, 10 240 frame pairs of a resident 512-frame extraction, SURVEY 8d)\n")
 A("| kernel | configuration | ms / 10 240 pairs | fraction of HBM peak on the 112.9 KB / pair algorithmic bytes | fraction of the POPC peak (148 x 16 x 1.965 G) |\n|---|---|---|---|---|")
 for b in m1["matcher_kernels"]:
     A("| `%s` | %s | %.3f | %s | %s |" % (b["kernel"], b["config"], b["ms"], ("%.4f" % b["frac"]) if b["unit"] == "GB/s" else "-",
                                       ("%.4f" % b["popc_frac"]) if b.get("popc_frac") else (("%.4f" % b["frac"]) if "popc" in b["unit"] else "-")))
-A("\nRound 1 for comparison (BENCH_r01: one CTA per pair, warp per query): windowed lists 0.024, resolver 0.007 of the HBM peak. The windowed matcher at r = 15 is now at 0.17")
-A("(7x), SearchForInitialization end to end at 0.0285 of the HBM figure (9.5 ms at the start of the round -> 6.2 ms); the brute-force kernel runs at 96 % of the POPC peak.")
-A("ncu of the matcher kernels (2 048 pairs per launch; the windowed launches captured are the r = 100 configuration; `k_sfi_resolve` captured BEFORE the compact-key change, which")
-A("cut it from 4.4 to about 2.2 ms per 10 240 pairs):\n")
+A("\nRound 1 for comparison (BENCH_r01: one CTA per pair, warp per query): windowed lists 0.024, resolver 0.007 of the HBM peak.  SearchForInitialization end to end is at 0.029 of the")
+A("HBM figure (9.5 ms at the start of the round -> 6.1 ms); the brute-force kernel runs at 96 % of the POPC peak.  The windowed matcher was rebuilt twice this round:\n")
+A("| `k_match_window_pairs`, ms per 10 240 pairs | r = 15 | r = 30 | r = 100 | bound (ncu) |\n|---|---|---|---|---|")
+A("| round-2 first form: thread per query walks its cell columns, query in registers | 1.03 | 2.09 | 10.07 | issue, 8 - 9 of 32 lanes (window populations of neighbouring queries differ) |")
+A("| warp per 32 queries: lane-per-query cursor -> ballot-compacted queue -> distances one queue slot per lane, atomicMin top-2; cell range trimmed | 0.87 | 1.68 | 10.5 | issue 69 %, 26 lanes; walk = 65 % of the instructions at 13 lanes |")
+A("| + walk as warp scan + owner search (slot-parallel gate) | 0.82 | 1.78 | 13.0 | LSU data pipe 84 % (186 M shared wavefronts, 80 M of them bank conflicts) |")
+A("| + chunk-major descriptors, LDS.128 | 0.79 | 1.66 | 11.9 | LSU data pipe 81 %, conflicts 68 M |")
+A("| + owner read-back of contiguous runs instead of atomics (final) | **%.2f** | **%.2f** | **%.2f** | LSU data pipe 70 %%, issue 69 %%; no atomics, no second pass |\n" % tuple(b["ms"] for b in m1["matcher_kernels"][:3]))
+A("Final kernel, r = 15 (`gpurun_out/r02F_mwp15.ncu-rep`, 10 240 pairs in one launch):\n")
+A(ncu_table("gpurun_out/r02F_mwp15.ncu-rep", 10240))
+A("\nWhat bounds it: shared-memory wavefronts and issue slots together -- 15 k shared-memory wavefronts and 64 k warp instructions per pair (27 of 32 lanes) for 113 KB = 0.9 k wavefronts of")
+A("compulsory staging; DRAM 2 % because the 512 resident frames (34 MB) live in L2, i.e. the 1.4 TB/s \"HBM-equivalent\" at r = 15 is L2 traffic.  The random 16-byte descriptor rows, the queue and the")
+A("owner-search shuffles all go through the same LSU data pipe.  The 60 % HBM target of SURVEY 8d is not met: 0.21 at r = 15 (round 1: 0.024).  The other matcher kernels (2 048 pairs per launch;")
+A("`k_sfi_resolve` captured BEFORE the compact-key change, which cut it from 4.4 to about 2.2 ms per 10 240 pairs; the `k_match_window_pairs<8>` rows are the round-2 FIRST form at r = 100):\n")
 A(ncu_table("gpurun_out/r02r_match.ncu-rep", 2048))
-A("\nWhat bounds them: `k_match_window_pairs` -- instruction issue under SIMT divergence (r = 100: issue active 81 %, 9.4 of 32 lanes; r = 15 (`gpurun_out/r02C_mwp15.ncu-rep`): issue")
-A("active 85 %, 8.1 of 32 lanes, 98 k warp instructions per pair of which 50 % are the distance loop running at 4.4 of 32 lanes: a thread walks its query's cell columns, trip counts")
-A("differ per lane; DRAM 0.3 - 1.8 % because the 512 resident frames (34 MB) live in L2, i.e. the 1.05 TB/s \"HBM-equivalent\" at r = 15 is L2 traffic); `k_sfi_lists` -- issue (73 %), 27 of 32")
-A("lanes after the buffered distance pass; `k_sfi_resolve` -- ALU pipe (73 %) at >= 2 048 pairs (the sorted-prefix extraction) and the sequential per-pair chain (~0.19 ms for 218")
-A("queries) at 512 pairs.  The 60 % HBM target of SURVEY 8d is not met by any of them: per pair the kernels execute 0.3-0.9 M warp instructions for 113 KB of compulsory bytes, i.e. they")
-A("are instruction bound by two orders of magnitude before bandwidth matters.\n")
+A("\n`k_sfi_lists` -- issue (73 %), 27 of 32 lanes after the buffered distance pass; `k_sfi_resolve` -- ALU pipe (73 %) at >= 2 048 pairs (the sorted-prefix extraction) and the sequential")
+A("per-pair chain (~0.19 ms for 218 queries) at 512 pairs.\n")
 A("## 3. Other configurations (1 GPU)\n")
 A("| workload | resident | end to end | CPU port (16 threads) | dominant kernel, fraction of measured HBM peak |\n|---|---|---|---|---|")
 for name, j in (("c3 sift128 1280x720, 2000 kp, B = 64", c3), ("c4 akaze61 + brisk48 640x480 (both extractors + both matchers), B = 256", c4),
