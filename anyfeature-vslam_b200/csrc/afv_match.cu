@@ -412,7 +412,7 @@ __global__ void __launch_bounds__(THREADS) k_match_window_pairs(int D, const afv
     extern __shared__ __align__(16) unsigned char sm[];
     constexpr int WARPS = THREADS / 32;
     constexpr int NC = NW / 4;                                                          // 16-byte chunks per descriptor
-    constexpr int WSCR = MWQ_QCAP + NW * 32 + MWQ_RUNS * 32;                            // words of scratch per warp
+    constexpr int WSCR = MWQ_QCAP + NW * 32 + MWQ_RUNS * 32 + 32;                       // words of scratch per warp
     // train descriptors chunk-major: sdesc[c][row] is the c-th 16-byte quarter of row `row`.  A drain reads one row per lane with NC
     // LDS.128; rows are random, and a quarter warp of 8 random 16-byte slots (bank group = row mod 8) collides far less often than
     // 32 random 4-byte words did in the word-major layout of the thread-per-query kernel (28 -> 19 wavefronts per 32 descriptors).
@@ -453,6 +453,7 @@ __global__ void __launch_bounds__(THREADS) k_match_window_pairs(int D, const afv
     uint32_t* wq = wscr + warp * WSCR;                                                  // [MWQ_QCAP] queue: lane << 16 | CSR position, then lane << 27 | key
     uint32_t* wsq = wq + MWQ_QCAP;                                                      // [NW][32] query descriptors of the batch
     uint32_t* wrun = wsq + NW * 32;                                                     // [MWQ_RUNS][32] finished runs: start << 16 | count
+    uint32_t* wown = wrun + MWQ_RUNS * 32;                                              // [32] owner table of the current column step
     const unsigned lt = (1u << lane) - 1u;
     for (int qb = warp * 32; qb < n1; qb += WARPS * 32) {
         const int qi = qb + lane;
@@ -525,12 +526,21 @@ __global__ void __launch_bounds__(THREADS) k_match_window_pairs(int D, const afv
             for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
             const int T = __shfl_sync(0xffffffffu, incl, 31);
             const int excl = incl - len, base = j0 - excl;                              // slot t of this lane's range is CSR position base + t
+            // owner table of the step: the non-empty ranges in lane order, (lane, base) packed in one word.  A slot finds its owner
+            // by RANK -- how many non-empty ranges end at or before it -- from one REDUX.OR mask per pass instead of a five-deep
+            // chain of dependent shuffles (the binary search over the inclusive sums was 13 % of the kernel's stall samples).
+            const unsigned nonempty = __ballot_sync(0xffffffffu, len > 0);
+            __syncwarp();                                                               // readers of the previous step's table are done
+            if (len > 0) wown[__popc(nonempty & lt)] = ((uint32_t)lane << 26) | (uint32_t)(base + (1 << 22));
+            __syncwarp();
             for (int t0 = 0; t0 < T; t0 += 32) {
                 const int t = t0 + lane;
-                int lo = 0;                                                             // owner = first lane whose inclusive sum exceeds t
-#pragma unroll
-                for (int step = 16; step; step >>= 1) { const int v = __shfl_sync(0xffffffffu, incl, lo + step - 1); if (v <= t) lo += step; }
-                const int j = __shfl_sync(0xffffffffu, base, lo) + t;
+                const int e = incl - t0 - 1;                                            // this lane's range ends at slot e of the pass
+                const unsigned ends = __reduce_or_sync(0xffffffffu, (len > 0 && e >= 0 && e < 32) ? (1u << e) : 0u);
+                const int before = __popc(__ballot_sync(0xffffffffu, len > 0 && incl <= t0));
+                const uint32_t ow = wown[min(before + __popc(ends & lt), 31)];
+                const int lo = (int)(ow >> 26);
+                const int j = (int)(ow & 0x03ffffffu) - (1 << 22) + t;
                 const float ox = __shfl_sync(0xffffffffu, x, lo), oy = __shfl_sync(0xffffffffu, y, lo);
                 const float orr = qr ? __shfl_sync(0xffffffffu, r, lo) : r_all;
                 float omin = -FLT_MAX, omax = FLT_MAX;
@@ -577,7 +587,7 @@ extern "C" int afv_match_window_pairs(int desc_type, const afv_keypoint* d_kps, 
     if (P == 0) return AFV_OK;
     const int NW = (((D + 3) / 4) + 3) & ~3;                                           // descriptor words, whole 16-byte chunks (8 / 12 / 16)
     const size_t smem_frame = (size_t)NW * cap * 4 + (size_t)cap * (8 + 4 + 2) + (size_t)((NCELLS + 1 + 7) & ~7) * 2 + 16;
-    const size_t scratch_warp = (size_t)(MWQ_QCAP + NW * 32 + MWQ_RUNS * 32) * 4;
+    const size_t scratch_warp = (size_t)(MWQ_QCAP + NW * 32 + MWQ_RUNS * 32 + 32) * 4;
     const size_t smem_limit = 227 * 1024;                                               // dynamic shared memory per CTA on sm_100
     // 16 warps per CTA when the frame leaves room for their queues, else 8
     const int threads = smem_frame + 16 * scratch_warp <= smem_limit ? 512 : 256;
