@@ -78,6 +78,69 @@ def test_family_check_against_cv2(frame, golden_dir):
         assert abs(np.median(ratio) - 1.0) < 0.02             # and at the same scale (cv2 size = 2 sigma)
 
 
+def _match_cv2(full, g, octaves, pos_tol, dlog=0.15):
+    """For every cv2 keypoint of the given octaves: index of the nearest oracle keypoint of the same scale (|log ratio| < dlog,
+    cv2 size = 2 sigma) and its distance; inf where there is none."""
+    idx = np.where(np.isin(g["octave"], octaves))[0]
+    best = np.full(len(idx), -1, np.int64); dist = np.full(len(idx), np.inf)
+    for n, q in enumerate(idx):
+        d = np.hypot(full[:, 0] - g["xys"][q, 0], full[:, 1] - g["xys"][q, 1])
+        d = np.where(np.abs(np.log(full[:, 2] / (g["xys"][q, 2] / 2.0))) < dlog, d, np.inf)
+        best[n] = int(np.argmin(d)); dist[n] = d[best[n]]
+    return idx, best, dist
+
+
+def test_cv2_default_upscale_bias_explains_the_loose_family_check(frame, golden_dir):
+    """Why the check above only holds at 1 px: cv2's default 2x upsampling carries a constant +0.25 px shift in x and y."""
+    g = np.load(os.path.join(golden_dir, "sift_cv2_synth_640x480_s0_t0.npz"))
+    full, _ = po.sift_detect(frame, 10 ** 7, with_desc=False)
+    idx, best, dist = _match_cv2(full, g, (0, 1), 1.0)
+    hit = dist < 1.0
+    dxy = full[best[hit], :2] - g["xys"][idx[hit], :2]
+    assert np.all(np.abs(dxy.mean(axis=0) + 0.24) < 0.03) and np.all(dxy.std(axis=0) < 0.13)
+
+
+def test_pinned_to_cv2_precise_per_octave(frame, golden_dir):
+    """Position, scale and orientation against cv2.SIFT(enable_precise_upscale=True), octave by octave, with the residual
+    classified.  SiftGPU is not OpenCV's SIFT (one Newton step instead of up to five, its own first octave, threshold 0.02 / 3
+    against 0.04 / 3), so this is agreement between two implementations of one published algorithm, not bit parity:
+      * octave 0 / 1: > 85 % / 90 % of cv2's keypoints have an oracle keypoint of the same scale within 0.25 px;
+        no systematic offset (|mean| < 0.03 px), 0.08 - 0.10 px standard deviation per axis; scale ratio median within 1 %;
+      * orientation of those pairs: constant -5.0 degrees (the oracle, like SiftGPU's shader as restated, maps a histogram peak to
+        the lower edge of its floor()-ed 10-degree bin, cv2 to the centre of a round()-ed one) with 2.2 degrees of spread;
+      * what cv2 finds and the oracle does not: two thirds sit on the FINEST layer of octave 0 (sigma ~ 2, where the two ways of
+        building the first octave -- blur of the input vs. decimated blur of the upsampled input -- differ most), the rest are
+        displaced by 0.5 - 1.5 px at the same scale (refinement) or sit one layer off."""
+    g = np.load(os.path.join(golden_dir, "sift_cv2_precise_synth_640x480_s0_t0.npz"))
+    full, _ = po.sift_detect(frame, 10 ** 7, with_desc=False)
+    for o, need in ((0, 0.85), (1, 0.90)):
+        idx, best, dist = _match_cv2(full, g, (o,), 0.25)
+        hit = dist < 0.25
+        assert hit.mean() > need, (o, hit.mean())
+        dxy = full[best[hit], :2] - g["xys"][idx[hit], :2]
+        assert np.all(np.abs(dxy.mean(axis=0)) < 0.03) and np.all(dxy.std(axis=0) < 0.12), (o, dxy.mean(axis=0), dxy.std(axis=0))
+        ratio = full[best[hit], 2] / (g["xys"][idx[hit], 2] / 2.0)
+        assert abs(np.median(ratio) - 1.0) < 0.01
+        # orientation: nearest of the (up to two) orientations the oracle emits at that position
+        sd = []
+        for q, b in zip(idx[hit], best[hit]):
+            same = np.where((np.abs(full[:, 0] - full[b, 0]) < 1e-4) & (np.abs(full[:, 1] - full[b, 1]) < 1e-4) & (np.abs(full[:, 2] - full[b, 2]) < 1e-4))[0]
+            dd = (np.degrees(full[same, 3]) - g["angle"][q] + 180.0) % 360.0 - 180.0
+            sd.append(dd[np.argmin(np.abs(dd))])
+        sd = np.array(sd)
+        core = sd[np.abs(sd) < 15.0]
+        assert len(core) > 0.9 * len(sd)                              # the rest: a second peak only one of the two kept
+        assert abs(np.median(core) + 5.0) < 0.5 and core.std() < 3.0, (o, np.median(core), core.std())
+    # residual of octave 0
+    idx, best, dist = _match_cv2(full, g, (0,), 0.5)
+    miss = idx[dist >= 0.5]
+    assert len(miss) < 0.13 * len(idx)
+    finest = (g["layer"][miss] == 1).mean()
+    assert finest > 0.55, finest
+    near_same_scale = (dist[dist >= 0.5] < 1.5).mean()
+    assert near_same_scale < 0.25                                      # most misses have no counterpart at all, they are not mislocalised
+
+
 def test_rotation_180(frame):
     """The detector is symmetric under a 180 degree rotation (clamped borders, symmetric taps)."""
     a, _ = po.sift_detect(frame, 10 ** 7, with_desc=False)
