@@ -302,7 +302,7 @@ __global__ void __launch_bounds__(256) k_sift_orient(const __grid_constant__ Sif
                 for (int b = 0; b < 36; ++b) {
                     const float lf = hs[(b + 35) % 36], rt = hs[(b + 1) % 36], c = hs[b];
                     if (c > lf && c > rt && c >= th) {
-                        float bin = (float)b + 0.5f * (lf - rt) / ((lf - 2.0f * c) + rt);
+                        float bin = ((float)b + 0.5f) + 0.5f * (lf - rt) / ((lf - 2.0f * c) + rt);      // peak referred to the bin centre
                         if (bin < 0.f) bin = bin + 36.0f;
                         if (bin >= 36.0f) bin = bin - 36.0f;
                         const float oo = bin * (SIFT_2PI / 36.0f);

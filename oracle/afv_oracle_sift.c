@@ -19,9 +19,9 @@
  *
  * Cross-check (tests/test_oracle_sift.py::test_pinned_to_cv2_precise_per_octave): against cv2 4.13.0 SIFT with
  * enable_precise_upscale, 86 / 92 % of cv2's octave 0 / 1 keypoints have a keypoint of this file at the same scale within
- * 0.25 px (no systematic offset, 0.08 px std per axis); orientations differ by a constant -5.0 degrees because
- * sift_orientations() maps a peak to the lower edge of its floor()-ed 10-degree bin (SiftGPU's shader as restated) where
- * cv2 uses the centre of a round()-ed bin -- the one restated detail that changes descriptors and cannot be settled here.
+ * 0.25 px (no systematic offset, 0.08 px std per axis) and their orientations agree to 2.2 degrees of spread with no
+ * offset.  (Until that check existed sift_orientations() mapped a histogram peak to the LOWER EDGE of its 10-degree bin:
+ * a constant -5.0 degrees against cv2, sift++ and Lowe, all of which refer the peak to the bin centre; corrected.)
  *
  * Arithmetic contract (what the CUDA path must reproduce bit for bit): IEEE float32, round-to-nearest, NO fused
  * multiply-add except the explicit fmaf() of the Gaussian taps, operation order exactly as written here; exp / atan2 / sin / cos are the polynomial forms below (not
@@ -320,7 +320,8 @@ static int sift_orientations(const float* G, int w, int h, float xo, float yo, f
     for (int b = 0; b < 36; ++b) {
         const float l = hs[(b + 35) % 36], r = hs[(b + 1) % 36], c = hs[b];
         if (c > l && c > r && c >= th) {
-            float bin = (float)b + 0.5f * (l - r) / ((l - 2.0f * c) + r);
+            /* bin b covers [10 b, 10 b + 10) degrees: the peak is referred to the bin CENTRE (sift++: th = 2 pi (i + di + 0.5) / nbins) */
+            float bin = ((float)b + 0.5f) + 0.5f * (l - r) / ((l - 2.0f * c) + r);
             if (bin < 0.f) bin = bin + 36.0f;
             if (bin >= 36.0f) bin = bin - 36.0f;
             const float o = bin * (SIFT_2PI / 36.0f);
