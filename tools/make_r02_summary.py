@@ -17,18 +17,18 @@ def ncu_table(rep, units):
     return subprocess.run([sys.executable, "tools/ncu_summary.py", rep, str(units)], capture_output=True, text=True).stdout
 
 
-c2 = last("profiles/r02F_bench_c2_n1.json"); m1 = last("profiles/r02F_bench_m1.json")
+c2 = last("profiles/r02G_bench_c2_n1.json"); m1 = last("profiles/r02G_bench_m1.json")
 ns = {n: last("profiles/r02A_bench_c2_n%d.json" % n) for n in (1, 2, 4, 8)}
-c3 = last("profiles/r02t_bench_c3_n1.json"); c4 = last("profiles/r02D_bench_c4_n1.json"); c5 = last("profiles/r02F_bench_c5_n1.json")
+c3 = last("profiles/r02G_bench_c3_n1.json"); c4 = last("profiles/r02D_bench_c4_n1.json"); c5 = last("profiles/r02F_bench_c5_n1.json")
 ref = last("profiles/r02A_bench_reference_arm.json"); rp = last("profiles/r02A_bench_reference_real_parts.json"); cv = last("profiles/r02A_bench_c2v_n1.json")
 k = c2["roofline"]["kernel_ms_per_step"]
 out = []
 A = out.append
 A("# Round 2 profile summary (B200, sm_100a; all numbers from `gpurun` boxes, clocks 1965 / 1965 MHz, no throttle reason)\n")
-A("Raw artefacts in this directory: `r02F_bench_{c2_n1,m1,c5_n1}.json` (final tree: default line, matcher workload, c5 workload), `r02A_bench_c2_n{1,2,4,8}.json` (the default line incl. its `c5`")
+A("Raw artefacts in this directory: `r02G_bench_{c2_n1,m1,c3_n1}.json` + `r02F_bench_c5_n1.json` (final tree: default line, matcher workload, c3 and c5 workloads), `r02A_bench_c2_n{1,2,4,8}.json` (the default line incl. its `c5`")
 A("block at 1 / 2 / 4 / 8 GPUs, the tree before the last k_describe / windowed-matcher changes: the scaling table below),")
-A("`r02A_bench_{c2v_n1}.json`, `r02t_bench_c3_n1.json`, `r02D_bench_c4_n1.json`, `r02A_bench_reference_arm.json`, `r02A_bench_reference_real_parts.json`, ncu launch lists")
-A("`r02A_launches_c2_batch512.csv` / `r02A_launches_c2v_batch512.csv` (`--metrics gpu__time_duration.sum --clock-control none`).  The `.ncu-rep` files")
+A("`r02A_bench_{c2v_n1}.json`, `r02D_bench_c4_n1.json`, `r02A_bench_reference_arm.json`, `r02A_bench_reference_real_parts.json`, ncu launch lists")
+A("`r02G_launches_c2_batch512.csv` (final tree) / `r02A_launches_c2v_batch512.csv` (`--metrics gpu__time_duration.sum --clock-control none`).  The `.ncu-rep` files")
 A("(`--set full --import-source on`, 23-34 MB each) stay in `gpurun_out/`; the tables below are `tools/ncu_summary.py` / `tools/ncu_lines.py` read-outs of them")
 A("(regenerate this file with `tools/make_r02_summary.py`).\n")
 A("## 1. Headline (c2 = BASELINE configs[1]: orb32 640x480, 1000 kp, 512 frames + 512 SearchForInitialization pairs per step, 1 GPU)\n")
@@ -56,7 +56,9 @@ A("Roofline of the dominant kernel (`roofline` block of the line): `%s` %.1f GB/
 A("ALU 74 %%, issue 77 %%, DRAM 6 %%), not HBM bound; whole step %.0f GB/s algorithmic = %.3f of the measured copy peak.\n" % (c2["roofline"]["step_algorithmic_gbs"], c2["roofline"]["step_algorithmic_gbs"] / c2["roofline"]["peak"]))
 A("### ncu `--set full`, batch 128, final kernels (per launch; `instr / unit` = warp instructions per frame)\n")
 A(ncu_table("gpurun_out/r02A_orb.ncu-rep", 128))
-A("\nShares of the serialised launch list at batch 512 (`r02A_launches_c2_batch512.csv`) follow the same ranking as the event times above.\n")
+A("\n`k_describe` after this round's last change (`gpurun_out/r02G_describe.ncu-rep`, batch 128; the table above still shows it before: 189.5 us, LSU pipe 29.7 %, issue 59 %):\n")
+A(ncu_table("gpurun_out/r02G_describe.ncu-rep", 128))
+A("\nShares of the serialised launch list at batch 512 (`r02G_launches_c2_batch512.csv`) follow the same ranking as the event times above.\n")
 A("Measured and rejected this round (kept out of the tree, recorded in the kernel comments): a per-lane `while (mask)` survivor writer in k_fast (1.17 vs 1.13 ms although it issues")
 A("fewer instructions: the kernel is bound by the ALU pipe, not by issue slots); `__launch_bounds__(256, 4)` on k_harris_select (0.47 vs 0.44 ms, spills) and prefetching the next candidate's")
 A("Harris rows into L1 (0.375 vs 0.338 ms); prefetching the next keypoint's rows in k_describe (0.654 vs 0.635 ms: the kernel is issue bound); running the selection kernels on a")
@@ -74,8 +76,9 @@ A("| round-2 first form: thread per query walks its cell columns, query in regis
 A("| warp per 32 queries: lane-per-query cursor -> ballot-compacted queue -> distances one queue slot per lane, atomicMin top-2; cell range trimmed | 0.87 | 1.68 | 10.5 | issue 69 %, 26 lanes; walk = 65 % of the instructions at 13 lanes |")
 A("| + walk as warp scan + owner search (slot-parallel gate) | 0.82 | 1.78 | 13.0 | LSU data pipe 84 % (186 M shared wavefronts, 80 M of them bank conflicts) |")
 A("| + chunk-major descriptors, LDS.128 | 0.79 | 1.66 | 11.9 | LSU data pipe 81 %, conflicts 68 M |")
-A("| + owner read-back of contiguous runs instead of atomics (final) | **%.2f** | **%.2f** | **%.2f** | LSU data pipe 70 %%, issue 69 %%; no atomics, no second pass |\n" % tuple(b["ms"] for b in m1["matcher_kernels"][:3]))
-A("Final kernel, r = 15 (`gpurun_out/r02F_mwp15.ncu-rep`, 10 240 pairs in one launch):\n")
+A("| + owner read-back of contiguous runs instead of atomics | 0.83 | 1.65 | 9.77 | LSU data pipe 70 %, issue 69 %; no atomics, no second pass |")
+A("| + slot owners by rank (REDUX.OR end mask + owner table) instead of a shuffle binary search (final) | **%.2f** | **%.2f** | **%.2f** | as above; the search was 13 %% of the stall samples |\n" % tuple(b["ms"] for b in m1["matcher_kernels"][:3]))
+A("The kernel before the last step, r = 15 (`gpurun_out/r02F_mwp15.ncu-rep`, 10 240 pairs in one launch; read-outs in `r02F_mwp15_raw.csv`, `r02F_mwp15_lines.txt`):\n")
 A(ncu_table("gpurun_out/r02F_mwp15.ncu-rep", 10240))
 A("\nWhat bounds it: shared-memory wavefronts and issue slots together -- 15 k shared-memory wavefronts and 64 k warp instructions per pair (27 of 32 lanes) for 113 KB = 0.9 k wavefronts of")
 A("compulsory staging; DRAM 2 % because the 512 resident frames (34 MB) live in L2, i.e. the 1.4 TB/s \"HBM-equivalent\" at r = 15 is L2 traffic.  The random 16-byte descriptor rows, the queue and the")
