@@ -395,7 +395,8 @@ extern "C" int afv_match_window(int desc_type, const void* d_q, const float* d_q
 //   + lane-per-query cursor feeding the queue, atomicMin top-2 ............ 0.87 / 10.5 ms  (25 walk iterations per batch at 13 lanes)
 //   + scan-based slot expansion of the walk ............................... 0.82 / 13.0 ms  (LSU data pipe 84 %: shared-memory wavefronts)
 //   + chunk-major descriptors read with LDS.128 ........................... 0.79 / 11.9 ms  (bank conflicts 80 M -> 68 M)
-//   + owner read-back of contiguous runs instead of atomics (this kernel) . 0.83 /  9.8 ms  (no pass 2; kept: never behind, no atomics)
+//   + owner read-back of contiguous runs instead of atomics ............... 0.83 /  9.8 ms  (no pass 2; kept: never behind, no atomics)
+//   + slot owners by rank instead of a shuffle binary search (this kernel)  0.81 /  9.3 ms  (the search was 13 % of the stall samples)
 // and, in round 1: enumerate -> flat candidate list -> uniform distance pass -> per-query reduce with block barriers (2 - 3.5x slower),
 // 4 lanes per query over interleaved cell columns (1.0 - 1.3x slower), pairs grouped by train frame to stage it once per 8 pairs
 // (1.20 vs 1.10 ms: wave-quantisation tail; the staging overlaps with other CTAs' query loops anyway).  The kernel sits at 70 - 84 %
