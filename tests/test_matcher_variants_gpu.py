@@ -266,6 +266,64 @@ def test_match_window_pairs_synthetic(pkg, feat, cap, n):
         assert ties > 100                                          # best == second distance occurs: the enumeration-order rule is exercised
 
 
+def test_match_window_pairs_full_size_properties(pkg, synth):
+    """BASELINE size (bench.py --workload m1: 10 240 frame pairs of 1000-keypoint orb32 frames) through properties that do not need
+    the oracle at that size: the result of a pair does not depend on which launch or which CTA computed it (one launch of
+    10 240 pairs == launches of 257), two runs are identical, a frame matched against itself returns every keypoint as its own
+    best at distance 0 -- or, for keypoints that share position and descriptor with an earlier one, the first of them in
+    enumeration order --, best < second wherever both exist; and a random sample of the pairs equals the oracle."""
+    import torch
+    B, P = 64, 10240
+    frames = np.concatenate([synth.stream_frames(640, 480, s, 16)[0] for s in (30, 31, 32, 33)], axis=0)
+    ex = pkg.FeatureExtractor("orb32", nfeatures=1000, max_batch=B, max_w=640, max_h=480)
+    out = ex.alloc_device_outputs(B)
+    ex.extract_batch_device(torch.from_numpy(frames).cuda(), out)
+    torch.cuda.synchronize(); ex.status()
+    cap = ex.cap
+    n = out[3].cpu().numpy()
+    fm = pkg.FeatureMatcher(desc_type=0, th_low=50.0)
+    cs, ci = fm.grid_build(out[0], out[3], BOUNDS)
+    rng = np.random.default_rng(7)
+    pa = rng.integers(0, B, P).astype(np.int32); pb = rng.integers(0, B, P).astype(np.int32)
+    pa[:B] = np.arange(B); pb[:B] = np.arange(B)                       # the first B pairs are (f, f)
+    d_pa, d_pb = _t(pa), _t(pb)
+    def run(a, b):                                                     # rows past a frame's keypoint count are not written: start from zeros
+        res = (torch.zeros((a.shape[0], cap), dtype=torch.int32, device="cuda"), torch.zeros((a.shape[0], cap), dtype=torch.float32, device="cuda"),
+               torch.zeros((a.shape[0], cap), dtype=torch.float32, device="cuda"))
+        return fm.match_window_pairs(out[0], out[1], out[2], out[3], cs, ci, a, b, BOUNDS, radius=15.0, out=res)
+    best, bd, sd = run(d_pa, d_pb)
+    again = run(d_pa, d_pb)
+    torch.cuda.synchronize()
+    assert all(torch.equal(a, b) for a, b in zip((best, bd, sd), again))
+    for lo in range(0, P, 257):                                        # partition invariance
+        hi = min(lo + 257, P)
+        part = run(d_pa[lo:hi].contiguous(), d_pb[lo:hi].contiguous())
+        assert torch.equal(part[0], best[lo:hi]) and torch.equal(part[1], bd[lo:hi]) and torch.equal(part[2], sd[lo:hi])
+    hb = best.cpu().numpy(); hbd = bd.cpu().numpy(); hsd = sd.cpu().numpy()
+    FMAX = np.finfo(np.float32).max
+    for f in range(B):                                                 # self pairs
+        m = int(n[f])
+        assert (hbd[f, :m] == 0).all()
+        other = np.where(hb[f, :m] != np.arange(m))[0]
+        k = pkg.kps_from_device(out[0][f], m); d = out[1][f, :m].cpu().numpy()
+        for i in other:                                                # an identical twin earlier in enumeration order
+            j = hb[f, i]
+            assert (d[i] == d[j]).all() and abs(k["x"][i] - k["x"][j]) < 15 and abs(k["y"][i] - k["y"][j]) < 15
+        assert len(other) < 0.05 * m
+    for p in range(P):
+        m = int(n[pa[p]])
+        has2 = hsd[p, :m] < FMAX
+        assert (hbd[p, :m][has2] <= hsd[p, :m][has2]).all() and ((hb[p, :m] >= 0) == (hbd[p, :m] < FMAX)).all()
+    for p in rng.choice(P, 24, replace=False):                         # oracle on a sample
+        a, b = int(pa[p]), int(pb[p]); na, nb = int(n[a]), int(n[b])
+        ka = pkg.kps_from_device(out[0][a], na); kb = pkg.kps_from_device(out[0][b], nb)
+        xy = np.stack([ka["x"], ka["y"]], axis=1).astype(np.float32)
+        rb, rbd, rsd, _, _ = po.match_window(0, out[1][a, :na].cpu().numpy(), xy, np.full(na, 15.0, np.float32), np.full(na, -FMAX, np.float32),
+                                             np.full(na, FMAX, np.float32), kb, out[1][b, :nb].cpu().numpy(), out[2][b, :nb].cpu().numpy(), BOUNDS)
+        assert (hb[p, :na] == rb).all() and (hbd[p, :na] == rbd).all() and (hsd[p, :na] == rsd).all()
+    ex.close()
+
+
 def test_match_bruteforce_pairs(pkg, extracted):
     import torch
     out, host, cap, dt, th, tol = extracted
