@@ -303,9 +303,12 @@ def test_match_window_pairs_full_size_properties(pkg, synth):
     FMAX = np.finfo(np.float32).max
     for f in range(B):                                                 # self pairs
         m = int(n[f])
-        assert (hbd[f, :m] == 0).all()
-        other = np.where(hb[f, :m] != np.arange(m))[0]
         k = pkg.kps_from_device(out[0][f], m); d = out[1][f, :m].cpu().numpy()
+        # Frame::PosInGrid rounds to the nearest cell and drops keypoints that round to column 64 / row 48 (x >= 635, y >= 475):
+        # the reference cannot find those in ANY window, itself included -- they are not candidates here either
+        ingrid = (k["x"] < 634.0) & (k["y"] < 474.0)
+        assert (hbd[f, :m][ingrid] == 0).all() and ingrid.mean() > 0.98
+        other = np.where((hb[f, :m] != np.arange(m)) & ingrid)[0]
         for i in other:                                                # an identical twin earlier in enumeration order
             j = hb[f, i]
             assert (d[i] == d[j]).all() and abs(k["x"][i] - k["x"][j]) < 15 and abs(k["y"][i] - k["y"][j]) < 15
