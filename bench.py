@@ -635,7 +635,9 @@ def c5_strong(pkg, torch, dist, rank, world, local, steps, warmup, frames_per_st
         if rank == 0:
             for r in range(world):
                 h_gathered[r].copy_(gathered[k][r] if world > 1 else d_pack[k], non_blocking=True)
-    e2e_step(); drain(); torch.cuda.synchronize()
+    for _ in range(3):                                      # warm both packing buffers, the pinned pages and the copy path
+        e2e_step()
+    drain(); torch.cuda.synchronize()
     f0 = torch.cuda.Event(enable_timing=True); f1 = torch.cuda.Event(enable_timing=True)
     barrier(); t0 = time.perf_counter(); f0.record()
     for _ in range(steps):
