@@ -17,15 +17,16 @@ def ncu_table(rep, units):
     return subprocess.run([sys.executable, "tools/ncu_summary.py", rep, str(units)], capture_output=True, text=True).stdout
 
 
-c2 = last("profiles/r02G_bench_c2_n1.json"); m1 = last("profiles/r02G_bench_m1.json")
+c2 = last("profiles/r02H_bench_c2_n1.json"); m1 = last("profiles/r02G_bench_m1.json")
 ns = {n: last("profiles/r02A_bench_c2_n%d.json" % n) for n in (1, 2, 4, 8)}
 c3 = last("profiles/r02G_bench_c3_n1.json"); c4 = last("profiles/r02D_bench_c4_n1.json"); c5 = last("profiles/r02F_bench_c5_n1.json")
 ref = last("profiles/r02A_bench_reference_arm.json"); rp = last("profiles/r02A_bench_reference_real_parts.json"); cv = last("profiles/r02A_bench_c2v_n1.json")
+n2 = last("profiles/r02H_bench_c2_n2.json")
 k = c2["roofline"]["kernel_ms_per_step"]
 out = []
 A = out.append
 A("# Round 2 profile summary (B200, sm_100a; all numbers from `gpurun` boxes, clocks 1965 / 1965 MHz, no throttle reason)\n")
-A("Raw artefacts in this directory: `r02G_bench_{c2_n1,m1,c3_n1}.json` + `r02F_bench_c5_n1.json` (final tree: default line, matcher workload, c3 and c5 workloads), `r02A_bench_c2_n{1,2,4,8}.json` (the default line incl. its `c5`")
+A("Raw artefacts in this directory: `r02H_bench_c2_n{1,2}.json` (final tree: default line at 1 and 2 GPUs), `r02G_bench_{m1,c3_n1}.json` + `r02F_bench_c5_n1.json` (matcher workload, c3 and c5 workloads), `r02A_bench_c2_n{1,2,4,8}.json` (the default line incl. its `c5`")
 A("block at 1 / 2 / 4 / 8 GPUs, the tree before the last k_describe / windowed-matcher changes: the scaling table below),")
 A("`r02A_bench_{c2v_n1}.json`, `r02D_bench_c4_n1.json`, `r02A_bench_reference_arm.json`, `r02A_bench_reference_real_parts.json`, ncu launch lists")
 A("`r02G_launches_c2_batch512.csv` (final tree) / `r02A_launches_c2v_batch512.csv` (`--metrics gpu__time_duration.sum --clock-control none`).  The `.ncu-rep` files")
@@ -97,7 +98,7 @@ A("\nc2v per-kernel ms / 512 frames (final): " + ", ".join("%s %.2f" % kv for kv
 A("k_os2_cells 3.82 -> 1.61 (lane = column with shuffles, row masks handed from the count to the emit pass), k_os2_score 3.51 -> 2.98 (compass pre-test + survivor compaction; at")
 A("minThFAST = 7 a third of the pixels pass the pre-test and 13 % are corners before NMS), k_os2_blur 2.08 -> 1.31 (4 px per thread from aligned words).  ncu of the FIRST version (batch 128):\n")
 A(ncu_table("gpurun_out/r02w_os2.ncu-rep", 128))
-A("\n## 4. Several GPUs (default line of `bench.py --gpus N` under torchrun, final tree; the `c5` block = BASELINE configs[4] as SURVEY 8e specifies it)\n")
+A("\n## 4. Several GPUs (default line of `bench.py --gpus N` under torchrun, the tree before the last k_describe / matcher changes; the `c5` block = BASELINE configs[4] as SURVEY 8e specifies it)\n")
 A("| GPUs | c2 resident (weak: 512 frames per GPU) | c2 end to end | c5 block, resident (strong: 1024 frames in total) | c5 validated ranks | c5 checksum (N-independent) | concurrent H2D of all ranks |\n|---|---|---|---|---|---|---|")
 for n in (1, 2, 4, 8):
     j = ns[n]; c = j["c5"]
@@ -109,6 +110,7 @@ A("\nDevice-timed weak scaling of c2: %s.  c5 strong scaling: %s: at 128 frames 
 A("(one CTA per (frame, level) / per pair) no longer fill the chip.  End to end (%s of linear) is bounded by the HOST: the ranks copying concurrently reach" % ", ".join("%.2f at %d" % (ns[n]["e2e"]["value"] / (n * e1), n) for n in (2, 4, 8)))
 A("56 / 111 / 153 / 187 GB/s in total at 1 / 2 / 4 / 8 GPUs while c2 at the device rate needs %.0f GB/s of input alone at 8 GPUs (`e2e.h2d_gbs_needed_at_device_rate`); with 157 MB in + 34 MB out" % ns[8]["e2e"]["h2d_gbs_needed_at_device_rate"])
 A("per 512 frames and GPU, (1.26 + 0.27) GB per step over 187 GB/s = 8.2 ms per step = 500 k frames/s at best at 8 GPUs; measured %.0f k = %.2f of that ceiling (the box exposes one NUMA node," % (ns[8]["e2e"]["value"] / 1e3, ns[8]["e2e"]["value"] / 500e3))
-A("`nvidia-smi topo`: every GPU on CPUs 0-31, so there is no placement to fix).")
+A("`nvidia-smi topo`: every GPU on CPUs 0-31, so there is no placement to fix).  Final tree at 2 GPUs (`r02H_bench_c2_n2.json`): c2 %.1f k resident (%.3f of linear against %.1f k at 1 GPU),"  % (n2["value"] / 1e3, n2["value"] / (2 * c2["value"]), c2["value"] / 1e3))
+A("%.1f k end to end, c5 block %.1f k with %d of 2 ranks validated." % (n2["e2e"]["value"] / 1e3, n2["c5"]["value"] / 1e3, n2["c5"]["validated_ranks"]))
 open("profiles/r02_summary.md", "w").write("\n".join(out) + "\n")
 print("profiles/r02_summary.md written")
