@@ -193,7 +193,7 @@ long  orc_akaze_scale_space(const uint8_t* gray, int w, int h, int stride, int o
 int   orc_akaze_detect(const uint8_t* gray, int w, int h, int stride, int omax, int nsub, float dth, float* out5, int cap);
 int   orc_akaze61_extract(const uint8_t* gray, int w, int h, int stride, int nfeatures, int nlevels, float scale_factor,
                           float detect_th, orc_keypoint* kps, uint8_t* desc, float* kpsize, int cap, int* n_out, int* n_detected);
-void  orc_akaze_set_cv2_filter(int on);   /* test hook: 1 = OpenCV's cross-level duplicate filter instead of libAKAZE's (pins the rest to cv2) */
+void  orc_akaze_set_cv2_filter(int on);   /* test hook, bit 0: OpenCV's cross-level duplicate filter, bit 1: OpenCV's orientation search, instead of libAKAZE's (pins the rest to cv2) */
 long  orc_akaze61_extract_match_batch(const uint8_t* frames, int B, int w, int h, int nfeatures, int nlevels, float scale_factor,
                                       float detect_th, const int* pair_a, const int* pair_b, int P, int window, float th_akaze,
                                       float th_brisk, float nnratio, int check_ori, int nthreads);

@@ -17,6 +17,10 @@
  * identical, responses to 3e-7 -- and, where the two orientation searches agree (< 0.001 deg, 43 % of the keypoints), 99 % of the
  * 486-bit descriptors bit for bit (all within 2 bits).  OpenCV quantises the 109 sample angles into 42 slices before sliding the
  * pi/3 window, libAKAZE (restated here) slides it over the exact angles: 11 % of the keypoints get an orientation > 1 deg apart.
+ * With OpenCV's orientation search selected as well (orc_akaze_set_cv2_filter(3), akz_orientation_cv below) ALL 1751 orientations
+ * agree with cv2 (99.9 % within 0.01 deg, none above 1 deg: the derivative arrays differ in the last bits) and 95.7 % of the
+ * descriptors are identical, 99.8 % within 2 bits -- so the sampling and MLDB code is pinned on every keypoint, and the two
+ * places where the default mode follows libAKAZE instead of OpenCV are exactly the two selectable functions.
  * The default mode (libAKAZE's sequential Find_Scale_Space_Extrema) finds 99.8 % of cv2's keypoints plus the ones OpenCV's filter
  * drops.  tests/test_oracle_akaze.py holds both checks.
  *
@@ -479,9 +483,9 @@ static int akz_detect_cv(const akz_space* S, float dthreshold, akz_pt** out) {
     return m;
 }
 static int g_akz_cv_mode = 0;
-void orc_akaze_set_cv2_filter(int on) { g_akz_cv_mode = on; }      /* test hook: selects the detection variant for orc_akaze_* */
+void orc_akaze_set_cv2_filter(int on) { g_akz_cv_mode = on; }      /* test hook, bit 0: OpenCV's duplicate filter, bit 1: OpenCV's orientation search */
 static int akz_detect_dispatch(const akz_space* S, float dthreshold, akz_pt** out) {
-    return g_akz_cv_mode ? akz_detect_cv(S, dthreshold, out) : akz_detect(S, dthreshold, out);
+    return (g_akz_cv_mode & 1) ? akz_detect_cv(S, dthreshold, out) : akz_detect(S, dthreshold, out);
 }
 
 /* ---- descriptors (Compute_Main_Orientation + Get_MLDB_Full_Descriptor) ------------------------------------------- */
@@ -557,6 +561,85 @@ static float akz_orientation(const akz_space* S, const akz_pt* kp) {
         if (m > best) { best = m; angle = akz_atan2(fy, fx); }
     }
     return angle;
+}
+
+/* OpenCV's Compute_Main_Orientation (modules/features2d/src/kaze/AKAZEFeatures.cpp), selected with orc_akaze_set_cv2_filter(mode & 2):
+ * the TEST-ONLY variant that pins the sampling and MLDB code below to the cv2 binary on every keypoint, not only where the two
+ * orientation searches happen to agree.  Differences from libAKAZE's search restated above: the centre and the scale are rounded
+ * first (cvRound) and the 109 samples sit on that integer lattice; the weights are the 8-decimal gauss25 literals; angles come from
+ * hal::fastAtan2 (radians) and are counting-sorted into 42 slices of 2 pi / 42; the pi / 3 window is 7 whole slices, summed in
+ * float in sorted order (slices ascending, original index descending inside a slice); the result is getAngle(sumX, sumY). */
+static float akz_fast_atan2_rad(float y, float x) {                    /* cv::hal::fastAtan32f, angleInDegrees = false */
+    const float p1 = 0.9997878412794807f * 57.29577951308232f, p3 = -0.3258083974640975f * 57.29577951308232f;
+    const float p5 = 0.1555786518463281f * 57.29577951308232f, p7 = -0.04432655554792128f * 57.29577951308232f;
+    const float ax = fabsf(x), ay = fabsf(y);
+    float a, c, c2;
+    if (ax >= ay) { c = ay / (ax + 2.220446049250313e-16f); c2 = c * c; a = (((p7 * c2 + p5) * c2 + p3) * c2 + p1) * c; }
+    else { c = ax / (ay + 2.220446049250313e-16f); c2 = c * c; a = 90.f - (((p7 * c2 + p5) * c2 + p3) * c2 + p1) * c; }
+    if (x < 0.f) a = 180.f - a;
+    if (y < 0.f) a = 360.f - a;
+    return a * 0.017453292519943295f;
+}
+static float akz_get_angle_cv(float x, float y) {                      /* kaze/utils.h getAngle */
+    if (x >= 0 && y >= 0) return atanf(y / x);
+    if (x < 0 && y >= 0) return AKZ_PI - atanf(-y / x);
+    if (x < 0 && y < 0) return AKZ_PI + atanf(y / x);
+    if (x >= 0 && y < 0) return AKZ_2PI - atanf(-y / x);
+    return 0.f;
+}
+static float akz_orientation_cv(const akz_space* S, const akz_pt* kp) {
+    const int lv = kp->class_id, w = S->L[lv].w, h = S->L[lv].h;
+    const float ratio = (float)(1 << kp->octave);
+    const int scale = (int)lrintf(0.5f * kp->size / ratio);
+    const int x0 = (int)lrintf(kp->x / ratio), y0 = (int)lrintf(kp->y / ratio);
+    static float g25[7][7];
+    static int g25_ok = 0;
+    if (!g25_ok) {                                                     /* the table's literals: the closed form rounded to 8 decimals */
+        for (int i = 0; i < 7; ++i)
+            for (int j = 0; j < 7; ++j) {
+                const double v = exp(-(double)(i * i + j * j) / 12.5) / (2.0 * 3.14159265358979323846 * 6.25);
+                g25[i][j] = (float)(floor(v * 1e8 + 0.5) / 1e8);
+            }
+        g25_ok = 1;
+    }
+    float rx[109], ry[109], ang[109];
+    int n = 0;
+    for (int i = -6; i <= 6; ++i)
+        for (int j = -6; j <= 6; ++j) {
+            if (i * i + j * j >= 36) continue;
+            const int y = clampi(y0 + j * scale, 0, h - 1), x = clampi(x0 + i * scale, 0, w - 1);
+            const float g = g25[i < 0 ? -i : i][j < 0 ? -j : j];
+            rx[n] = g * S->Lx[lv][(size_t)y * w + x]; ry[n] = g * S->Ly[lv][(size_t)y * w + x];
+            ang[n] = akz_fast_atan2_rad(ry[n], rx[n]);
+            ++n;
+        }
+    enum { SL = 42, WIN = 7 };
+    const float step = (float)(2.0 * 3.14159265358979323846 / SL);
+    int cum[SL + 1], sorted[109];
+    memset(cum, 0, sizeof(cum));
+    for (int i = 0; i < n; ++i) { int b = (int)(ang[i] / step); if (b < 0 || b >= SL) b = 0; cum[b]++; }
+    for (int i = 1; i <= SL; ++i) cum[i] += cum[i - 1];
+    for (int i = 0; i < n; ++i) { int b = (int)(ang[i] / step); if (b < 0 || b >= SL) b = 0; sorted[--cum[b]] = i; }
+    float maxX = 0.f, maxY = 0.f;
+    for (int i = cum[0]; i < cum[WIN]; ++i) { maxX += rx[sorted[i]]; maxY += ry[sorted[i]]; }
+    float maxNorm = maxX * maxX + maxY * maxY;
+    for (int sn = 1; sn <= SL - WIN; ++sn) {
+        if (cum[sn] == cum[sn - 1] && cum[sn + WIN] == cum[sn + WIN - 1]) continue;
+        float sx = 0.f, sy = 0.f;
+        for (int i = cum[sn]; i < cum[sn + WIN]; ++i) { sx += rx[sorted[i]]; sy += ry[sorted[i]]; }
+        const float nm = sx * sx + sy * sy;
+        if (nm > maxNorm) { maxNorm = nm; maxX = sx; maxY = sy; }
+    }
+    for (int sn = SL - WIN + 1; sn < SL; ++sn) {
+        const int remain = sn + WIN - SL;
+        if (cum[sn] == cum[sn - 1] && cum[remain] == cum[remain - 1]) continue;
+        float sx = 0.f, sy = 0.f;
+        for (int i = cum[sn]; i < cum[SL]; ++i) { sx += rx[sorted[i]]; sy += ry[sorted[i]]; }
+        for (int i = cum[0]; i < cum[remain]; ++i) { sx += rx[sorted[i]]; sy += ry[sorted[i]]; }
+        const float nm = sx * sx + sy * sy;
+        if (nm > maxNorm) { maxNorm = nm; maxX = sx; maxY = sy; }
+    }
+    return akz_get_angle_cv(maxX, maxY);
 }
 
 static void akz_mldb(const akz_space* S, const akz_pt* kp, float angle, uint8_t* desc) {
@@ -638,7 +721,7 @@ int orc_akaze61_extract(const uint8_t* gray, int w, int h, int stride, int nfeat
         for (int j = 0; j < nk; ++j) {
             const akz_pt* p = &K[idx[keep[j]]];
             if (m >= cap) { rc = -2; break; }
-            const float ang = akz_orientation(&S, p);
+            const float ang = (g_akz_cv_mode & 2) ? akz_orientation_cv(&S, p) : akz_orientation(&S, p);
             orc_keypoint* kp = &kps[m];
             kp->x = p->x; kp->y = p->y; kp->size = p->size; kp->angle = ang; kp->response = p->response; kp->octave = p->octave; kp->class_id = p->class_id;
             akz_mldb(&S, p, ang, desc + (size_t)61 * m);

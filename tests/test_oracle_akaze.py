@@ -47,7 +47,8 @@ def test_scale_space_structure(frame):
 def test_pinned_to_cv2_with_opencv_duplicate_filter(frame, golden_dir):
     """With OpenCV's variant of the duplicate filter selected, the oracle reproduces cv2.AKAZE's keypoint list exactly (count, order,
     level, position, size, response): this pins the FED scale space, the Hessian, the maxima, the border rule (10 sqrt 2 * sigma_size)
-    and the sub-pixel refinement to the cv2 4.13.0 binary.  MLDB is pinned where the two orientation searches agree."""
+    and the sub-pixel refinement to the cv2 4.13.0 binary.  MLDB is pinned where the two orientation searches agree, and -- with OpenCV's
+    orientation search selected too -- on every keypoint."""
     g = np.load(os.path.join(golden_dir, "akaze_cv2_synth_640x480_s0_t0.npz"))
     kp = g["kp"]
     po.lib().orc_akaze_set_cv2_filter(1)
@@ -71,6 +72,19 @@ def test_pinned_to_cv2_with_opencv_duplicate_filter(frame, golden_dir):
     assert close.mean() > 0.4 and (hd[close] == 0).mean() > 0.98 and hd[close].max() <= 2
     assert (hd[da < 1e-2] <= 4).all()
     assert (da > 1.0).mean() < 0.15                                         # OpenCV's 42-slice search vs libAKAZE's exact-angle windows
+    # ... and with OpenCV's orientation search selected as well (mode bits 0 + 1) the sampling and MLDB code is pinned on EVERY keypoint:
+    po.lib().orc_akaze_set_cv2_filter(3)
+    try:
+        kps, desc, size, nd = po.akaze61_extract(frame, 20000)
+    finally:
+        po.lib().orc_akaze_set_cv2_filter(0)
+    d2, i2 = cKDTree(kp[:, :2]).query(np.stack([kps["x"], kps["y"]], 1))
+    m = (d2 < 0.05) & (kp[i2, 6] == kps["class_id"])
+    assert m.sum() == len(kp)
+    da = np.abs(((np.degrees(kps["angle"][m]) - kp[i2[m], 3]) + 180) % 360 - 180)
+    hd = np.unpackbits(desc[m] ^ g["desc"][i2[m]], axis=1).sum(1)
+    assert (da < 1e-2).mean() > 0.995 and da.max() < 1.0                    # all 1751 orientations (the derivative arrays differ in the last bits)
+    assert (hd == 0).mean() > 0.94 and (hd <= 2).mean() > 0.995             # 95.7 % of the 486-bit descriptors identical, 99.8 % within 2 bits
 
 
 def test_family_check_against_cv2(frame, golden_dir):
