@@ -179,7 +179,7 @@ def test_search_for_triangulation(pkg, extracted):
 
 @pytest.mark.parametrize("radius,gated", [(15.0, False), (100.0, False), (30.0, True)])
 def test_match_window_pairs(pkg, extracted, radius, gated):
-    """Batched windowed matcher (thread per query, train frame + grid staged in shared memory) == the oracle's GetFeaturesInArea
+    """Batched windowed matcher (train frame + grid staged in shared memory, warp per 32 queries with a candidate queue) == the oracle's GetFeaturesInArea
     window search, pair by pair: best index (first minimum in reference enumeration order), best and second distance."""
     import torch
     out, host, cap, dt, th, tol = extracted
