@@ -277,7 +277,7 @@ int  afv_match_bruteforce_pairs(int desc_type, const void* d_desc, const int* d_
  * and enumeration order as Frame::GetFeaturesInArea (src/Frame.cc:333-382) -- train keypoints that Frame::PosInGrid drops
  * (they round to column 64 / row 48) are not candidates, a frame matched against itself included; binary descriptors.
  * Outputs are P x cap; only the first d_n[d_pair_a[p]] entries of a row are written.  The train frame is staged in shared memory:
- * AFV_ERR_INVALID when cap exceeds what fits (about 4300 / 3100 / 2500 keypoints for 32 / 48 / 61-byte descriptors). */
+ * AFV_ERR_INVALID when cap exceeds what fits (about 4300 / 3100 / 2400 keypoints for 32 / 48 / 61-byte descriptors). */
 int  afv_match_window_pairs(int desc_type, const afv_keypoint* d_kps, const void* d_desc, const float* d_kpsize, const int* d_n,
                             int B, int cap, const int* d_cell_start, const int* d_cell_items, const int* d_pair_a,
                             const int* d_pair_b, int P, const float* d_qxy, const float* d_qr, float radius,
