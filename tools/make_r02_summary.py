@@ -19,8 +19,8 @@ def ncu_table(rep, units):
 
 c2 = last("profiles/r02H_bench_c2_n1.json"); m1 = last("profiles/r02G_bench_m1.json")
 ns = {n: last("profiles/r02A_bench_c2_n%d.json" % n) for n in (1, 2, 4, 8)}
-c3 = last("profiles/r02G_bench_c3_n1.json"); c4 = last("profiles/r02D_bench_c4_n1.json"); c5 = last("profiles/r02F_bench_c5_n1.json")
-ref = last("profiles/r02A_bench_reference_arm.json"); rp = last("profiles/r02A_bench_reference_real_parts.json"); cv = last("profiles/r02A_bench_c2v_n1.json")
+c3 = last("profiles/r02G_bench_c3_n1.json"); c4 = last("profiles/r02H_bench_c4_n1.json"); c5 = last("profiles/r02F_bench_c5_n1.json")
+ref = last("profiles/r02A_bench_reference_arm.json"); rp = last("profiles/r02A_bench_reference_real_parts.json"); cv = last("profiles/r02H_bench_c2v_n1.json")
 n2 = last("profiles/r02H_bench_c2_n2.json")
 k = c2["roofline"]["kernel_ms_per_step"]
 out = []
@@ -28,7 +28,7 @@ A = out.append
 A("# Round 2 profile summary (B200, sm_100a; all numbers from `gpurun` boxes, clocks 1965 / 1965 MHz, no throttle reason)\n")
 A("Raw artefacts in this directory: `r02H_bench_c2_n{1,2}.json` (final tree: default line at 1 and 2 GPUs), `r02G_bench_{m1,c3_n1}.json` + `r02F_bench_c5_n1.json` (matcher workload, c3 and c5 workloads), `r02A_bench_c2_n{1,2,4,8}.json` (the default line incl. its `c5`")
 A("block at 1 / 2 / 4 / 8 GPUs, the tree before the last k_describe / windowed-matcher changes: the scaling table below),")
-A("`r02A_bench_{c2v_n1}.json`, `r02D_bench_c4_n1.json`, `r02A_bench_reference_arm.json`, `r02A_bench_reference_real_parts.json`, ncu launch lists")
+A("`r02H_bench_{c4_n1,c2v_n1}.json`, `r02A_bench_reference_arm.json`, `r02A_bench_reference_real_parts.json`, ncu launch lists")
 A("`r02G_launches_c2_batch512.csv` (final tree) / `r02A_launches_c2v_batch512.csv` (`--metrics gpu__time_duration.sum --clock-control none`).  The `.ncu-rep` files")
 A("(`--set full --import-source on`, 23-34 MB each) stay in `gpurun_out/`; the tables below are `tools/ncu_summary.py` / `tools/ncu_lines.py` read-outs of them")
 A("(regenerate this file with `tools/make_r02_summary.py`).\n")
