@@ -608,10 +608,8 @@ __constant__ float c_g7[7] = {0x1.1f5f62p-4f, 0x1.0c70fcp-3f, 0x1.869472p-3f, 0x
 // pass: one thread = 4 columns x 4 rows from 10 float4 rows.
 #define BT_WP 40                      // words per staged row
 #define BT_XOFF 16                    // byte offset of pixel x0 inside a staged row
-__device__ __forceinline__ uint32_t sat_u8(float v) {       // cv::saturate_cast<uchar>(float): round-half-even, clamp
-    uint32_t r;
-    asm("cvt.rni.sat.u8.f32 %0, %1;" : "=r"(r) : "f"(v));
-    return r;
+__device__ __forceinline__ float u8f(uint32_t w, int k) {   // (float) of byte k of w: 0x4B0000bb is 2^23 + bb
+    return __fsub_rn(__uint_as_float(__byte_perm(w, 0x4B000000u, 0x7440 | k)), 8388608.0f);
 }
 __global__ void __launch_bounds__(256) k_blur(const __grid_constant__ AfvParams P, const __grid_constant__ AfvTmaps TM) {
     __shared__ __align__(128) uint32_t in[BT_H + 6][BT_WP];
@@ -661,10 +659,12 @@ __global__ void __launch_bounds__(256) k_blur(const __grid_constant__ AfvParams 
     for (int r = wrp; r < BT_H + 6; r += 8) {
         const int q = lane;
         const uint32_t w0 = in[r][q + 3], w1 = in[r][q + 4], w2 = in[r][q + 5];      // staged bytes 4q+13 .. 4q+22
+        // byte -> float without the conversion unit: one PRMT drops the byte into the mantissa of 2^23 and one FADD removes the 2^23
+        // (exact).  The I2F / F2I conversions were this kernel's busiest pipe (XU 55 % in ncu r02A, 16 lanes per clock per SM).
         float pf[10];
-        pf[0] = (float)((w0 >> 8) & 0xff); pf[1] = (float)((w0 >> 16) & 0xff); pf[2] = (float)(w0 >> 24);
-        pf[3] = (float)(w1 & 0xff); pf[4] = (float)((w1 >> 8) & 0xff); pf[5] = (float)((w1 >> 16) & 0xff); pf[6] = (float)(w1 >> 24);
-        pf[7] = (float)(w2 & 0xff); pf[8] = (float)((w2 >> 8) & 0xff); pf[9] = (float)((w2 >> 16) & 0xff);
+        pf[0] = u8f(w0, 1); pf[1] = u8f(w0, 2); pf[2] = u8f(w0, 3);
+        pf[3] = u8f(w1, 0); pf[4] = u8f(w1, 1); pf[5] = u8f(w1, 2); pf[6] = u8f(w1, 3);
+        pf[7] = u8f(w2, 0); pf[8] = u8f(w2, 1); pf[9] = u8f(w2, 2);
         float4 o;
         float* op = &o.x;
 #pragma unroll
@@ -689,15 +689,18 @@ __global__ void __launch_bounds__(256) k_blur(const __grid_constant__ AfvParams 
             for (int rr = 0; rr < 4; ++rr) {
                 const int gy = y0 + 4 * rg + rr;
                 if (gy >= L.h) break;
-                uint32_t pk = 0;
+                uint32_t ub[4];
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
                     float sacc = __fmul_rn(c_g7[3], (&m[rr + 3].x)[k]);
 #pragma unroll
                     for (int j = 1; j <= 3; ++j)
                         sacc = __fmaf_rn(c_g7[3 + j], __fadd_rn((&m[rr + 3 + j].x)[k], (&m[rr + 3 - j].x)[k]), sacc);
-                    pk |= sat_u8(sacc) << (8 * k);
+                    // cv::saturate_cast<uchar>(float) = round half to even, clamp.  0 <= sacc <= 254.99997 (positive taps whose float sum
+                    // is below 1, u8 inputs), so adding 1.5 * 2^23 leaves rint(sacc) in the low mantissa byte and the clamp never acts
+                    ub[k] = __float_as_uint(__fadd_rn(sacc, 12582912.0f));
                 }
+                const uint32_t pk = __byte_perm(__byte_perm(ub[0], ub[1], 0x0040), __byte_perm(ub[2], ub[3], 0x0040), 0x5410);
                 *reinterpret_cast<uint32_t*>(out + (long long)gy * L.stride + gx) = pk;
             }
         }
