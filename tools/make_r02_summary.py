@@ -17,7 +17,7 @@ def ncu_table(rep, units):
     return subprocess.run([sys.executable, "tools/ncu_summary.py", rep, str(units)], capture_output=True, text=True).stdout
 
 
-c2 = last("profiles/r02H_bench_c2_n1.json"); m1 = last("profiles/r02G_bench_m1.json")
+c2 = last("profiles/r02I_bench_c2_n1.json"); m1 = last("profiles/r02G_bench_m1.json")
 ns = {n: last("profiles/r02A_bench_c2_n%d.json" % n) for n in (1, 2, 4, 8)}
 c3 = last("profiles/r02G_bench_c3_n1.json"); c4 = last("profiles/r02H_bench_c4_n1.json"); c5 = last("profiles/r02F_bench_c5_n1.json")
 ref = last("profiles/r02A_bench_reference_arm.json"); rp = last("profiles/r02A_bench_reference_real_parts.json"); cv = last("profiles/r02H_bench_c2v_n1.json")
@@ -26,7 +26,7 @@ k = c2["roofline"]["kernel_ms_per_step"]
 out = []
 A = out.append
 A("# Round 2 profile summary (B200, sm_100a; all numbers from `gpurun` boxes, clocks 1965 / 1965 MHz, no throttle reason)\n")
-A("Raw artefacts in this directory: `r02H_bench_c2_n{1,2}.json` (final tree: default line at 1 and 2 GPUs), `r02G_bench_{m1,c3_n1}.json` + `r02F_bench_c5_n1.json` (matcher workload, c3 and c5 workloads), `r02A_bench_c2_n{1,2,4,8}.json` (the default line incl. its `c5`")
+A("Raw artefacts in this directory: `r02I_bench_c2_n1.json` / `r02H_bench_c2_n2.json` (final tree: default line at 1 and 2 GPUs), `r02G_bench_{m1,c3_n1}.json` + `r02F_bench_c5_n1.json` (matcher workload, c3 and c5 workloads), `r02A_bench_c2_n{1,2,4,8}.json` (the default line incl. its `c5`")
 A("block at 1 / 2 / 4 / 8 GPUs, the tree before the last k_describe / windowed-matcher changes: the scaling table below),")
 A("`r02H_bench_{c4_n1,c2v_n1}.json`, `r02A_bench_reference_arm.json`, `r02A_bench_reference_real_parts.json`, ncu launch lists")
 A("`r02G_launches_c2_batch512.csv` (final tree) / `r02A_launches_c2v_batch512.csv` (`--metrics gpu__time_duration.sum --clock-control none`).  The `.ncu-rep` files")
@@ -45,7 +45,7 @@ why = {"k_resize": "128x32 tiles (prologue amortised over 16 px per thread)",
        "k_fast": "packed 16x2 compass test on 4 px per thread-row, stage 2 = score only, (d,-d) differences as one IMAD per circle pixel, interior-tile fast path, warp-aggregated outputs",
        "k_harris_select": "9-byte Harris rows from three aligned 32-bit loads + funnel shifts (44 % of the stall samples sat on the byte loads); parallel suffix scans",
        "k_octree": "keys as packed level coordinates scaled on the fly: 11 instead of 19 bytes of shared memory per key, 5 instead of 3 CTAs per SM",
-       "k_blur": "REFLECT_101 patch taken from the staged tile (22 % of the instructions were the per-row global patch loop that >50 % of the tiles ran)",
+       "k_blur": "REFLECT_101 patch taken from the staged tile (22 % of the instructions were the per-row global patch loop that >50 % of the tiles ran); byte <-> float through the mantissa instead of the conversion unit (XU was its busiest pipe at 55 %)",
        "k_describe": "float pattern table in shared memory, branch-free inner tap path, sincos; 37x37 blurred patch staged per warp in shared memory (taps as LDS.U8, the 16 global gathers per keypoint held the L1 data pipe at 73 %), pattern read from global instead of the constant cache, 32 keypoints per CTA, 4 CTAs per SM at 64 registers",
        "k_sfi_lists": "in-window slots buffered per warp, distances with 32 of 32 lanes (was 11), word count unrolled",
        "k_sfi_resolve": "32-bit compact keys + redux.sync for the sorted-prefix phase"}
