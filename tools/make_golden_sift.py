@@ -30,11 +30,12 @@ print(out, len(k), np.bincount(oc + 1))
 # compensation) shifts every keypoint by +0.25 px in x and y; the precise variant removes that bias, and only against it can
 # positions be compared below half a pixel.  Stored with layer, angle and response so that the test can classify the residual.
 sift = cv2.SIFT_create(nfeatures=0, nOctaveLayers=3, contrastThreshold=0.04, edgeThreshold=10, sigma=1.6, enable_precise_upscale=True)
-k = sift.detect(frames[0], None)
+k, dsc = sift.detectAndCompute(frames[0], None)
+assert (dsc == np.round(dsc)).all() and dsc.min() >= 0 and dsc.max() <= 255      # cv2 quantises to integers in [0, 255]
 oc = np.array([(p.octave & 255) if (p.octave & 255) < 128 else (p.octave & 255) - 256 for p in k], np.int32)
 layer = np.array([(p.octave >> 8) & 255 for p in k], np.int32)
 xys = np.array([[p.pt[0], p.pt[1], p.size] for p in k], np.float32)
 out = os.path.join(ROOT, "tests", "golden", "sift_cv2_precise_synth_640x480_s0_t0.npz")
 np.savez_compressed(out, xys=xys, octave=oc, layer=layer, angle=np.array([p.angle for p in k], np.float32),
-                    response=np.array([p.response for p in k], np.float32), cv2_version=cv2.__version__)
+                    response=np.array([p.response for p in k], np.float32), desc=dsc.astype(np.uint8), cv2_version=cv2.__version__)
 print(out, len(k), np.bincount(oc + 1))
