@@ -15,7 +15,7 @@
 #include <string.h>
 #include <vector>
 
-long long g_afv_launches = 0;
+std::atomic<long long> g_afv_launches{0};
 static thread_local char g_err[512] = "";
 
 void afv_set_error(const char* fmt, ...) {
@@ -24,35 +24,41 @@ void afv_set_error(const char* fmt, ...) {
     va_end(ap);
 }
 extern "C" const char* afv_last_error(void) { return g_err; }
-extern "C" long long afv_kernel_launches(void) { return g_afv_launches; }
+extern "C" long long afv_kernel_launches(void) { return g_afv_launches.load(); }
 extern "C" const char* afv_version(void) { return "afv-b200 0.1 (sm_100a)"; }
 
 // ---- per-kernel event timing --------------------------------------------------------------------------
 #include <map>
 #include <string>
-static bool g_prof_on = false;
+#include <mutex>
+static std::atomic<bool> g_prof_on{false};
 struct ProfRec { std::string name; cudaEvent_t e0, e1; };
+static std::mutex g_prof_mu;                         // records and event pool (matcher calls arrive from several host threads)
 static std::vector<ProfRec> g_prof_recs;
 static std::vector<cudaEvent_t> g_prof_pool;
 static cudaEvent_t prof_event() {
     if (!g_prof_pool.empty()) { cudaEvent_t e = g_prof_pool.back(); g_prof_pool.pop_back(); return e; }
     cudaEvent_t e; cudaEventCreate(&e); return e;
 }
-void afv_prof_begin(const char* name, cudaStream_t st) {
-    if (!g_prof_on) return;
+int afv_prof_begin(const char* name, cudaStream_t st) {
+    if (!g_prof_on.load()) return -1;
+    std::lock_guard<std::mutex> lk(g_prof_mu);
     ProfRec r; r.name = name; r.e0 = prof_event(); r.e1 = prof_event();
     cudaEventRecord(r.e0, st);
     g_prof_recs.push_back(r);
+    return (int)g_prof_recs.size() - 1;
 }
-void afv_prof_end(cudaStream_t st) {
-    if (!g_prof_on || g_prof_recs.empty()) return;
-    cudaEventRecord(g_prof_recs.back().e1, st);
+void afv_prof_end(int id, cudaStream_t st) {
+    if (id < 0) return;
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    if (id < (int)g_prof_recs.size()) cudaEventRecord(g_prof_recs[id].e1, st);
 }
-bool afv_prof_is_on() { return g_prof_on; }
-extern "C" int afv_profile_enable(int on) { g_prof_on = on != 0; return AFV_OK; }
+bool afv_prof_is_on() { return g_prof_on.load(); }
+extern "C" int afv_profile_enable(int on) { g_prof_on.store(on != 0); return AFV_OK; }
 // Synchronises, sums the recorded launches per kernel name and clears the records.
 // names: max_n x 32 chars; ms / calls: max_n.  Returns the number of distinct kernels.
 extern "C" int afv_profile_read(char* names, float* ms, int* calls, int max_n) {
+    std::lock_guard<std::mutex> lk(g_prof_mu);
     std::map<std::string, std::pair<double, int>> acc;
     std::vector<std::string> order;
     for (auto& r : g_prof_recs) {

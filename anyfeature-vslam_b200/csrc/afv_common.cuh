@@ -1,5 +1,6 @@
 // afv_common.cuh -- shared declarations of the B200 feature front end (device layout + launch plumbing).
 #pragma once
+#include <atomic>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include "../../include/afv.h"
@@ -74,12 +75,12 @@ int afv_orb_configure(int max_det_cap, int max_keep_cap, int* mcap_out, int* nca
 
 // matcher launches (afv_match.cu) are called directly from afv_capi.cu through the C ABI.
 
-extern long long g_afv_launches;
+extern std::atomic<long long> g_afv_launches;     // kernels launched by this library (host threads of a SLAM system call in concurrently)
 // optional per-kernel CUDA-event timing (bench.py's roofline leg): AFV_PROF_BEGIN/END bracket one launch
-void afv_prof_begin(const char* name, cudaStream_t st);
-void afv_prof_end(cudaStream_t st);
+int  afv_prof_begin(const char* name, cudaStream_t st);       // returns the record id (-1 when profiling is off)
+void afv_prof_end(int id, cudaStream_t st);
 bool afv_prof_is_on();
-struct AfvProfScope { cudaStream_t st; AfvProfScope(const char* n, cudaStream_t s) : st(s) { afv_prof_begin(n, s); } ~AfvProfScope() { afv_prof_end(st); } };
+struct AfvProfScope { cudaStream_t st; int id; AfvProfScope(const char* n, cudaStream_t s) : st(s), id(afv_prof_begin(n, s)) {} ~AfvProfScope() { afv_prof_end(id, st); } };
 void afv_set_error(const char* fmt, ...);
 #define AFV_CUDA_CHECK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { \
     afv_set_error("%s failed: %s (%s:%d)", #x, cudaGetErrorString(e_), __FILE__, __LINE__); return AFV_ERR_CUDA; } } while (0)
